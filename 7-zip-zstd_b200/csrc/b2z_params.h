@@ -1,0 +1,38 @@
+/* b2z_params.h -- algorithm constants shared by the CUDA kernels and (read-only) by the
+ * oracle restatement, so that both state the same algorithm.  Plain C, host+device. */
+#ifndef B2Z_PARAMS_H
+#define B2Z_PARAMS_H
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define B2Z_HD __host__ __device__ __forceinline__
+#else
+#define B2Z_HD static inline
+#endif
+
+#define B2Z_DEF_FRAMELOG   22      /* independent zstd frame = 4 MiB of input                */
+#define B2Z_DEF_HASHLOG_L  17      /* long (8-byte) hash table entries  (clevels.h:31 H17)   */
+#define B2Z_DEF_HASHLOG_S  16      /* short (5-byte) hash table entries (clevels.h:31 C16)   */
+#define B2Z_STEP           32u     /* positions per warp step                                */
+#define B2Z_LAZY_GAIN      2u      /* defer a match when the next position's is this much longer */
+#define B2Z_MAX_FRAMELOG   24
+#define B2Z_CAP            64u     /* stage-M match length cap (pieces re-joined in stage E) */
+#define B2Z_MAXSEQ         32768u  /* raw sequences per 128 KiB block (min match 4)          */
+#define B2Z_BLOCK          131072u
+#define B2Z_FRAME_HDR_MAX  10
+#define B2Z_LIT_HUF_MIN    64u     /* fewer literals than this are stored raw                */
+#define B2Z_LIT_RLE_MIN    8u
+
+/* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
+#define B2Z_PRIME5 889523592379ULL
+#define B2Z_PRIME8 0xCF1BBCDCB7A56463ULL
+
+/* match acceptance: a match must pay for its ~offset bits */
+B2Z_HD int b2z_accept(uint32_t len, uint32_t off) {
+    if (len >= 6) return 1;
+    if (len == 5) return off < (1u << 18);
+    if (len == 4) return off < (1u << 8);
+    return 0;
+}
+
+#endif

@@ -1,0 +1,41 @@
+/* oracle.h -- C API of the CPU oracle (liboracle.so).  TEST INFRASTRUCTURE ONLY:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it. */
+#ifndef B2ZO_ORACLE_H
+#define B2ZO_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+uint64_t b2zo_xxh64(const void *data, size_t len, uint64_t seed);
+
+/* Decode every frame (zstd + skippable) in src; returns size or <0 (-1 corrupt, -2 dst too
+ * small, -3 checksum, -4 dictionary needed). */
+int64_t b2zo_zstd_decompress(void *dst, size_t dstCap, const void *src, size_t srcSize);
+
+/* Encoder restatement: the exact algorithm the CUDA kernels implement (see zstd_enc_oracle.c).
+ * Output is byte-identical to the GPU path for the same parameters. */
+typedef struct {
+    uint32_t frameLog;      /* log2 of independent frame size (default 22 = 4 MiB)            */
+    uint32_t hashLogL;      /* long (8-byte) hash table log (default 17)                      */
+    uint32_t hashLogS;      /* short (5-byte) hash table log (default 16)                     */
+    uint32_t windowLog;     /* max match distance log (default = frameLog)                    */
+    uint32_t reserved;
+    uint32_t flags;         /* bit0: skippable size hints before each frame; bit1: checksum   */
+} b2zo_enc_params;
+
+void   b2zo_enc_default_params(b2zo_enc_params *p, int level);
+size_t b2zo_zstd_compress_bound(size_t srcSize, const b2zo_enc_params *p);
+int64_t b2zo_zstd_compress(void *dst, size_t dstCap, const void *src, size_t srcSize, const b2zo_enc_params *p);
+
+/* Debug taps for stage-level parity with the GPU (tests compare these arrays). */
+typedef struct { uint32_t off; uint32_t poslen; } b2zo_rawseq;   /* poslen = pos | (len-3)<<17 */
+int64_t b2zo_zstd_find_sequences(const void *src, size_t srcSize, const b2zo_enc_params *p,
+                                 b2zo_rawseq *seqs /* [nblocks*32768] */, uint32_t *nseq /* [nblocks] */,
+                                 uint8_t *lits /* [srcSize] */, uint32_t *nlit /* [nblocks] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

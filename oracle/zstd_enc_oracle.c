@@ -1,0 +1,591 @@
+/* zstd_enc_oracle.c -- plain-C restatement of the B200 block-parallel Zstandard encoder.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  This is the single-threaded statement of the
+ * algorithm that 7-zip-zstd_b200/csrc/zstd_enc_*.cu implements with one CTA per frame
+ * (stage M) and one warp per 128 KiB block (stage E).  Every decision below is integer and
+ * order-independent by construction, so the CUDA path must reproduce these bytes exactly;
+ * tests compare stage taps (raw sequences, literals) and final frames byte-for-byte.
+ *
+ * What it replaces in the reference (level 3 = dfast; /root/reference/C/zstd/):
+ *   ZSTDMT job slicing ............... zstdmt_compress.c:1184-1246  -> independent frames of 2^frameLog
+ *   ZSTD_compress_frameChunk ......... zstd_compress.c:4591          -> 128 KiB blocks, 3-byte headers
+ *   ZSTD_compressBlock_doubleFast .... zstd_double_fast.c:103-330    -> stage M (dual hash, all positions)
+ *   ZSTD_hash5Ptr / ZSTD_hash8Ptr .... zstd_compress_internal.h:903-924 (same multiplicative hashes)
+ *   ZSTD_storeSeq / ZSTD_updateRep ... zstd_compress_internal.h:775,817 -> merge + repcode pass
+ *   ZSTD_compressLiterals ............ zstd_compress_literals.c:129-235
+ *   HUF_buildCTable / writeCTable .... huf_compress.c:755,248        -> own length-limited builder
+ *   HUF_compress4X_usingCTable ....... huf_compress.c:1167
+ *   ZSTD_seqToCodes .................. zstd_compress.c:2693
+ *   ZSTD_buildSequencesStatistics .... zstd_compress.c:2763; zstd_compress_sequences.c:156,242
+ *   FSE_normalizeCount/writeNCount/buildCTable  fse_compress.c:465,330,68 -> own normaliser
+ *   ZSTD_encodeSequences ............. zstd_compress_sequences.c:291-382
+ *   ZSTD_writeFrameHeader/Epilogue ... zstd_compress.c:4695,5344
+ * The encoder's OUTPUT BYTES are not pinned by the reference (no known-answer
+ * test exists); parity = the reference decoder round-trips every frame + ratio delta.
+ *
+ * Parallel semantics restated sequentially:
+ *   - one warp owns one frame and walks it in steps of 32 positions; table state + the lower
+ *     lanes of the step give each position the nearest previous occurrence of its hash key.
+ *   - the parse is the greedy path with one-position lazy deferral inside a step, entered
+ *     where the previous step's last match ended.
+ *   - match lengths are capped at B2Z_CAP in stage M; stage E re-joins capped pieces.
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "zstd_format.h"
+#include "oracle.h"
+#include "b2z_params.h"
+
+static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static inline void wr16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+static inline void wr24(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); }
+static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
+
+void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
+    (void)level;
+    p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
+    p->windowLog = B2Z_DEF_FRAMELOG; p->reserved = 0; p->flags = 0;
+}
+
+size_t b2zo_zstd_compress_bound(size_t n, const b2zo_enc_params *p) {
+    size_t frames = (n >> p->frameLog) + 1, blocks = (n >> 17) + frames;
+    return n + blocks * 3 + frames * (B2Z_FRAME_HDR_MAX + 12 + 4) + 64;
+}
+
+/* ======================================================================= stage M */
+static size_t count_match(const uint8_t *a, const uint8_t *b, size_t maxLen) {
+    size_t n = 0;
+    while (n + 8 <= maxLen) {
+        uint64_t x = rd64(a + n) ^ rd64(b + n);
+        if (x) return n + ((size_t)__builtin_ctzll(x) >> 3);
+        n += 8;
+    }
+    while (n < maxLen && a[n] == b[n]) n++;
+    return n;
+}
+
+typedef struct { uint32_t off; uint16_t len; } cand_t;
+
+/* One frame: src[0..n).  Emits, per 128 KiB block, raw sequences and the literal bytes.
+ * The GPU runs this with one warp per frame: a step is B2Z_STEP (=32) consecutive positions,
+ * lane i owning position base+i; "tables + lower lanes of the same step" (resolved with
+ * __match_any_sync) give every position exactly the nearest previous occurrence of its hash
+ * key, which is what the position-by-position loop below states. */
+static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_params *P,
+                                 b2zo_rawseq *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
+    const uint32_t HL = P->hashLogL, HS = P->hashLogS;
+    const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
+    const size_t W = (size_t)1 << P->windowLog;
+    uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
+    cand_t cand[B2Z_STEP];
+    size_t entry = 0;                                       /* greedy path entry point (frame-relative) */
+    size_t nblocks = (n + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
+    for (size_t b = 0; b < nblocks; b++) { nseq[b] = 0; nlit[b] = 0; }
+    for (size_t c0 = 0; c0 < n; c0 += B2Z_STEP) {
+        size_t c1 = c0 + B2Z_STEP < n ? c0 + B2Z_STEP : n;
+        size_t blk = c0 / ZF_BLOCK_MAX, blkStart = blk * ZF_BLOCK_MAX;
+        size_t blkEnd = blkStart + ZF_BLOCK_MAX < n ? blkStart + ZF_BLOCK_MAX : n;
+        int search = entry < c1;                            /* whole step inside a match: insert only */
+        for (size_t p = c0; p < c1; p++) {
+            cand_t best = { 0, 0 };
+            if (p + 8 <= n) {
+                uint64_t v = rd64(src + p);
+                uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
+                uint32_t *sl = &TL[hl >> (64 - HL)], *ss = &TS[hs >> (64 - HS)];
+                uint32_t tL = (uint32_t)(hl >> (64 - HL - tagBits)) & tagMask;
+                uint32_t tS = (uint32_t)(hs >> (64 - HS - tagBits)) & tagMask;
+                if (search) {
+                    uint32_t eL = *sl, eS = *ss;
+                    size_t maxLen = blkEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
+                    uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
+                    if (eL && (eL & tagMask) == tL) {
+                        size_t q = (eL >> tagBits) - 1;
+                        if (p - q <= W) { offL = (uint32_t)(p - q); lenL = (uint32_t)count_match(src + q, src + p, maxLen); }
+                    }
+                    if (eS && (eS & tagMask) == tS) {
+                        size_t q = (eS >> tagBits) - 1;
+                        if (p - q <= W) { offS = (uint32_t)(p - q); lenS = (uint32_t)count_match(src + q, src + p, maxLen); }
+                    }
+                    uint32_t len = lenL, off = offL;
+                    if (lenS > lenL || (lenS == lenL && offS < offL)) { len = lenS; off = offS; }
+                    if (b2z_accept(len, off)) { best.off = off; best.len = (uint16_t)len; }
+                }
+                *sl = (((uint32_t)p + 1) << tagBits) | tL;  /* latest position wins */
+                *ss = (((uint32_t)p + 1) << tagBits) | tS;
+            }
+            cand[p - c0] = best;
+        }
+        /* ---- path through this step: greedy with one-position lazy deferral inside the step */
+        while (entry < c1) {
+            size_t p = entry;
+            const cand_t *cd = &cand[p - c0];
+            if (cd->len && !(p + 1 < c1 && cand[p + 1 - c0].len >= cd->len + B2Z_LAZY_GAIN)) {
+                b2zo_rawseq *s = &seqs[blk * B2Z_MAXSEQ + nseq[blk]++];
+                s->off = cd->off; s->poslen = (uint32_t)(p - blkStart) | ((uint32_t)(cd->len - 3) << 17);
+                entry = p + cd->len;
+            } else {
+                lits[blkStart + nlit[blk]++] = src[p];
+                entry = p + 1;
+            }
+        }
+    }
+    free(TL); free(TS);
+}
+
+int64_t b2zo_zstd_find_sequences(const void *srcv, size_t srcSize, const b2zo_enc_params *P,
+                                 b2zo_rawseq *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
+    const uint8_t *src = (const uint8_t *)srcv;
+    size_t F = (size_t)1 << P->frameLog, blkBase = 0;
+    for (size_t f0 = 0; f0 < srcSize; f0 += F) {
+        size_t fn = srcSize - f0 < F ? srcSize - f0 : F;
+        find_sequences_frame(src + f0, fn, P, seqs + blkBase * B2Z_MAXSEQ, nseq + blkBase, lits + f0, nlit + blkBase);
+        blkBase += (fn + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
+    }
+    return (int64_t)blkBase;
+}
+
+/* ======================================================================= stage E helpers */
+typedef struct { uint8_t *p; uint64_t acc; uint32_t nb; } bitw_t;       /* LSB-first writer */
+static inline void bw_init(bitw_t *b, uint8_t *p) { b->p = p; b->acc = 0; b->nb = 0; }
+static inline void bw_add(bitw_t *b, uint32_t v, uint32_t n) {           /* n <= 32 */
+    b->acc |= (uint64_t)(v & (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1))) << b->nb; b->nb += n;
+    while (b->nb >= 8) { *b->p++ = (uint8_t)b->acc; b->acc >>= 8; b->nb -= 8; }
+}
+static inline uint8_t *bw_close(bitw_t *b) {                             /* end mark + pad */
+    bw_add(b, 1, 1);
+    if (b->nb) { *b->p++ = (uint8_t)b->acc; b->acc = 0; b->nb = 0; }
+    return b->p;
+}
+
+/* ---- FSE encoding tables -------------------------------------------------------------- */
+typedef struct { int32_t deltaFindState; uint32_t deltaNbBits; } fse_symtt;
+typedef struct { uint16_t state[512]; fse_symtt tt[64]; uint32_t log; } fse_ctable;
+
+static void fse_build_ctable(fse_ctable *ct, const int16_t *norm, uint32_t maxSym, uint32_t log) {
+    uint32_t size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    uint8_t spread[512]; uint32_t cumul[65], high = size - 1;
+    cumul[0] = 0;
+    for (uint32_t s = 0; s <= maxSym; s++) {
+        if (norm[s] == -1) { cumul[s + 1] = cumul[s] + 1; spread[high--] = (uint8_t)s; }
+        else cumul[s + 1] = cumul[s] + (uint32_t)norm[s];
+    }
+    uint32_t pos = 0;
+    for (uint32_t s = 0; s <= maxSym; s++)
+        for (int i = 0; i < norm[s]; i++) { spread[pos] = (uint8_t)s; pos = (pos + step) & mask; while (pos > high) pos = (pos + step) & mask; }
+    for (uint32_t u = 0; u < size; u++) { uint32_t s = spread[u]; ct->state[cumul[s]++] = (uint16_t)(size + u); }
+    uint32_t total = 0;
+    for (uint32_t s = 0; s <= maxSym; s++) {
+        int n = norm[s];
+        if (n == 0) { ct->tt[s].deltaNbBits = ((log + 1) << 16) - size; ct->tt[s].deltaFindState = 0; }
+        else if (n == 1 || n == -1) { ct->tt[s].deltaNbBits = (log << 16) - size; ct->tt[s].deltaFindState = (int32_t)total - 1; total++; }
+        else {
+            uint32_t maxBitsOut = log - zf_highbit32((uint32_t)n - 1), minStatePlus = (uint32_t)n << maxBitsOut;
+            ct->tt[s].deltaNbBits = (maxBitsOut << 16) - minStatePlus;
+            ct->tt[s].deltaFindState = (int32_t)total - n; total += (uint32_t)n;
+        }
+    }
+    ct->log = log;
+}
+static inline uint32_t fse_init_state(const fse_ctable *ct, uint32_t sym) {
+    uint32_t nb = (ct->tt[sym].deltaNbBits + (1u << 15)) >> 16;
+    uint32_t v = (nb << 16) - ct->tt[sym].deltaNbBits;
+    return ct->state[(v >> nb) + ct->tt[sym].deltaFindState];
+}
+static inline uint32_t fse_encode(const fse_ctable *ct, uint32_t *state, uint32_t sym, uint32_t *nbOut) {
+    uint32_t nb = (*state + ct->tt[sym].deltaNbBits) >> 16, bits = *state & ((1u << nb) - 1);
+    *state = ct->state[(*state >> nb) + ct->tt[sym].deltaFindState];
+    *nbOut = nb; return bits;
+}
+
+/* ---- normalisation (own scheme; any valid normalisation is format-legal) ------------------
+ * norm[s] = max(1, round(count*2^log/total)) for present symbols, then the rounding error is
+ * settled on the largest entries.  No "-1" (low-probability) entries are produced. */
+static void fse_normalize(int16_t *norm, uint32_t log, const uint32_t *count, uint32_t total, uint32_t maxSym) {
+    uint32_t size = 1u << log; int32_t sum = 0;
+    for (uint32_t s = 0; s <= maxSym; s++) {
+        if (!count[s]) { norm[s] = 0; continue; }
+        uint64_t p = ((uint64_t)count[s] * size * 2 + total) / (2ull * total);
+        if (p < 1) p = 1;
+        norm[s] = (int16_t)p; sum += (int32_t)p;
+    }
+    int32_t delta = (int32_t)size - sum;
+    while (delta != 0) {                                    /* settle on the currently largest entry */
+        uint32_t big = 0;
+        for (uint32_t s = 1; s <= maxSym; s++) if (norm[s] > norm[big]) big = s;
+        if (delta > 0) { norm[big] = (int16_t)(norm[big] + delta); delta = 0; }
+        else {
+            int32_t take = norm[big] - 1 < -delta ? norm[big] - 1 : -delta;
+            if (take > (norm[big] >> 1) && norm[big] > 2) take = norm[big] >> 1;   /* spread large deficits */
+            norm[big] = (int16_t)(norm[big] - take); delta += take;
+        }
+    }
+}
+
+/* Serialise normalised counts (fse_compress.c:233-345 semantics). Returns bytes written. */
+static size_t fse_write_ncount(uint8_t *dst, const int16_t *norm, uint32_t maxSym, uint32_t log) {
+    bitw_t b; bw_init(&b, dst);
+    bw_add(&b, log - 5, 4);
+    int32_t remaining = (int32_t)(1u << log);
+    uint32_t s = 0;
+    while (remaining > 0 && s <= maxSym) {
+        int nb = (int)zf_highbit32((uint32_t)remaining + 1) + 1;
+        uint32_t T = 1u << (nb - 1), max = 2 * T - 1 - ((uint32_t)remaining + 1);
+        int32_t proba = norm[s++];
+        uint32_t count = (uint32_t)(proba + 1);
+        remaining -= proba < 0 ? 1 : proba;
+        if (count < max) bw_add(&b, count, (uint32_t)nb - 1);
+        else if (count < T) bw_add(&b, count, (uint32_t)nb);
+        else bw_add(&b, count + max, (uint32_t)nb);
+        if (proba == 0) {                                   /* run of zeros: 2-bit repeat counts */
+            for (;;) {
+                uint32_t run = 0;
+                while (run < 3 && s <= maxSym && norm[s] == 0) { run++; s++; }
+                bw_add(&b, run, 2);
+                if (run < 3) break;
+            }
+        }
+    }
+    if (b.nb) { *b.p++ = (uint8_t)b.acc; }
+    return (size_t)(b.p - dst);
+}
+
+/* ---- fixed-point costs ------------------------------------------------------------------ */
+/* log2(x) * 256 for x >= 1, integer only (8 fractional bits from a 32-entry mantissa table) */
+static uint32_t log2_fx8(uint32_t x) {
+    static const uint8_t frac[32] = { 0, 11, 22, 33, 43, 53, 63, 72, 82, 91, 100, 108, 116, 125, 132, 140,
+                                      148, 155, 162, 169, 176, 182, 189, 195, 201, 207, 213, 219, 225, 230, 236, 241 };
+    uint32_t hb = zf_highbit32(x);
+    uint32_t m = hb >= 5 ? (x >> (hb - 5)) & 31 : (x << (5 - hb)) & 31;
+    return (hb << 8) + frac[m];
+}
+/* cost in 1/256 bit of coding `count` with table (norm, log) */
+static uint64_t fse_cost_fx8(const uint32_t *count, const int16_t *norm, uint32_t maxSym, uint32_t log) {
+    uint64_t c = 0;
+    for (uint32_t s = 0; s <= maxSym; s++) {
+        if (!count[s]) continue;
+        if (norm[s] == 0) return ~0ull;                     /* symbol not representable */
+        uint32_t n = norm[s] < 0 ? 1u : (uint32_t)norm[s];
+        c += (uint64_t)count[s] * ((log << 8) - log2_fx8(n));
+    }
+    return c;
+}
+
+/* ======================================================================= Huffman */
+typedef struct { uint16_t code[256]; uint8_t len[256]; uint32_t maxBits; uint32_t maxSym; } huf_ctable;
+
+/* Code lengths by the textbook two-queue construction on (count, symbol)-sorted leaves; if the
+ * tree is deeper than 11 the counts are halved (floor at 1) and the tree rebuilt -- always a
+ * complete prefix code, hence representable as zstd weights. */
+static void huf_build(huf_ctable *h, const uint32_t *count0) {
+    uint32_t count[256]; memcpy(count, count0, sizeof(count));
+    uint32_t order[256], n;
+    for (;;) {
+        n = 0;
+        for (uint32_t s = 0; s < 256; s++) if (count[s]) order[n++] = s;
+        /* stable sort by count ascending (symbols already ascending) */
+        for (uint32_t i = 1; i < n; i++) { uint32_t s = order[i]; int j = (int)i - 1; while (j >= 0 && count[order[j]] > count[s]) { order[j + 1] = order[j]; j--; } order[j + 1] = s; }
+        uint32_t w[512]; int parent[512];
+        for (uint32_t i = 0; i < n; i++) w[i] = count[order[i]];
+        uint32_t li = 0, ii = n, ie = n;                    /* leaf head, internal head, internal end */
+        while ((n - li) + (ie - ii) > 1) {
+            uint32_t a, b;
+            if (li < n && (ii >= ie || w[li] <= w[ii])) a = li++; else a = ii++;
+            if (li < n && (ii >= ie || w[li] <= w[ii])) b = li++; else b = ii++;
+            w[ie] = w[a] + w[b]; parent[a] = (int)ie; parent[b] = (int)ie; ie++;
+        }
+        uint32_t depth[512], maxd = 0; depth[ie - 1] = 0;
+        for (int i = (int)ie - 2; i >= 0; i--) depth[i] = depth[parent[i]] + 1;
+        for (uint32_t i = 0; i < n; i++) if (depth[i] > maxd) maxd = depth[i];
+        if (maxd <= ZF_HUF_MAXBITS) {
+            memset(h->len, 0, 256);
+            for (uint32_t i = 0; i < n; i++) h->len[order[i]] = (uint8_t)depth[i];
+            h->maxBits = maxd; h->maxSym = order[0];
+            for (uint32_t s = 0; s < 256; s++) if (count[s]) h->maxSym = s;
+            break;
+        }
+        for (uint32_t s = 0; s < 256; s++) if (count[s]) count[s] = (count[s] + 1) >> 1;
+    }
+    /* canonical values in zstd order: weight w = maxBits+1-len; cells filled by ascending weight,
+       symbols ascending inside a weight; value = firstCell >> (w-1) */
+    uint32_t rank[ZF_HUF_MAXBITS + 2] = { 0 }, start[ZF_HUF_MAXBITS + 2], pos = 0;
+    for (uint32_t s = 0; s < 256; s++) if (h->len[s]) rank[h->maxBits + 1 - h->len[s]]++;
+    for (uint32_t r = 1; r <= h->maxBits; r++) { start[r] = pos; pos += rank[r] << (r - 1); }
+    for (uint32_t s = 0; s < 256; s++) {
+        if (!h->len[s]) { h->code[s] = 0; continue; }
+        uint32_t r = h->maxBits + 1 - h->len[s];
+        h->code[s] = (uint16_t)(start[r] >> (r - 1)); start[r] += 1u << (r - 1);
+    }
+}
+
+/* Tree description: FSE-compressed weights when that is smaller than raw nibbles.
+ * Returns bytes written, 0 if not representable (caller stores literals raw). */
+static size_t huf_write_table(uint8_t *dst, const huf_ctable *h) {
+    uint8_t w[256]; uint32_t nw = h->maxSym;                /* last weight is implicit */
+    for (uint32_t s = 0; s < nw; s++) w[s] = h->len[s] ? (uint8_t)(h->maxBits + 1 - h->len[s]) : 0;
+    size_t fseSize = 0; uint8_t tmp[160];
+    if (nw > 1) {
+        uint32_t cnt[16] = { 0 }, maxW = 0, maxCnt = 0;
+        for (uint32_t i = 0; i < nw; i++) { cnt[w[i]]++; if (w[i] > maxW) maxW = w[i]; }
+        for (uint32_t i = 0; i <= maxW; i++) if (cnt[i] > maxCnt) maxCnt = cnt[i];
+        if (maxCnt != nw && maxCnt > 1) {
+            uint32_t log = 6;                               /* weights table log: <= 6 */
+            uint32_t minBits = zf_highbit32(nw) + 1, symBits = zf_highbit32(maxW + 1) + 2;
+            uint32_t lo = minBits < symBits ? minBits : symBits;
+            uint32_t want = zf_highbit32(nw - 1) >= 2 ? zf_highbit32(nw - 1) - 2 : 0;
+            if (want < log) log = want;
+            if (log < lo) log = lo;
+            if (log < 5) log = 5;
+            if (log > 6) log = 6;
+            int16_t norm[16]; fse_normalize(norm, log, cnt, nw, maxW);
+            size_t hs = fse_write_ncount(tmp, norm, maxW, log);
+            fse_ctable ct; fse_build_ctable(&ct, norm, maxW, log);
+            bitw_t b; bw_init(&b, tmp + hs);
+            /* two interleaved states, symbols walked last -> first (fse_compress.c:558-622 order) */
+            uint32_t i = nw, s1, s2, nb, bits;
+            if (nw & 1) { s1 = fse_init_state(&ct, w[--i]); s2 = fse_init_state(&ct, w[--i]);
+                          bits = fse_encode(&ct, &s1, w[--i], &nb); bw_add(&b, bits, nb); }
+            else { s2 = fse_init_state(&ct, w[--i]); s1 = fse_init_state(&ct, w[--i]); }
+            while (i > 0) {
+                bits = fse_encode(&ct, &s2, w[--i], &nb); bw_add(&b, bits, nb);
+                bits = fse_encode(&ct, &s1, w[--i], &nb); bw_add(&b, bits, nb);
+            }
+            bw_add(&b, s2, log); bw_add(&b, s1, log);
+            fseSize = (size_t)(bw_close(&b) - tmp);
+        }
+    }
+    size_t rawSize = (nw + 1) / 2;
+    if (fseSize && fseSize < 128 && (fseSize < rawSize || nw > 128)) {
+        dst[0] = (uint8_t)fseSize; memcpy(dst + 1, tmp, fseSize); return 1 + fseSize;
+    }
+    if (nw > 128 || nw == 0) return 0;
+    dst[0] = (uint8_t)(127 + nw);
+    for (uint32_t i = 0; i < nw; i += 2) dst[1 + i / 2] = (uint8_t)((w[i] << 4) | (i + 1 < nw ? w[i + 1] : 0));
+    return 1 + rawSize;
+}
+
+static size_t huf_encode_stream(uint8_t *dst, const uint8_t *lit, size_t n, const huf_ctable *h) {
+    bitw_t b; bw_init(&b, dst);
+    for (size_t i = n; i-- > 0;) bw_add(&b, h->code[lit[i]], h->len[lit[i]]);
+    return (size_t)(bw_close(&b) - dst);
+}
+
+/* Literals section. Returns bytes written. */
+static size_t write_literals(uint8_t *dst, const uint8_t *lit, size_t n) {
+    uint32_t count[256] = { 0 }, ns = 0;
+    for (size_t i = 0; i < n; i++) count[lit[i]]++;
+    for (uint32_t s = 0; s < 256; s++) ns += count[s] != 0;
+    size_t rawHdr = n < 32 ? 1 : (n < 4096 ? 2 : 3);
+    if (n >= B2Z_LIT_RLE_MIN && ns == 1) {                  /* RLE literals */
+        if (rawHdr == 1) dst[0] = (uint8_t)(1 | (n << 3));
+        else if (rawHdr == 2) wr16(dst, (uint32_t)(1 | (1 << 2) | (n << 4)));
+        else wr24(dst, (uint32_t)(1 | (3 << 2) | (n << 4)));
+        dst[rawHdr] = lit[0]; return rawHdr + 1;
+    }
+    if (n >= B2Z_LIT_HUF_MIN && ns >= 2) {
+        huf_ctable h; huf_build(&h, count);
+        uint8_t *tmp = (uint8_t *)malloc(n + n / 2 + 512);
+        size_t ts = huf_write_table(tmp, &h);
+        if (ts) {
+            int four = n >= 256;
+            size_t lh = n < 1024 ? 3 : (n < 16384 ? 4 : 5);
+            uint8_t *p = tmp + ts; size_t body;
+            if (!four) body = huf_encode_stream(p, lit, n, &h);
+            else {
+                size_t seg = (n + 3) / 4; uint8_t *q = p + 6; size_t s;
+                s = huf_encode_stream(q, lit, seg, &h); wr16(p, (uint32_t)s); q += s;
+                s = huf_encode_stream(q, lit + seg, seg, &h); wr16(p + 2, (uint32_t)s); q += s;
+                s = huf_encode_stream(q, lit + 2 * seg, seg, &h); wr16(p + 4, (uint32_t)s); q += s;
+                s = huf_encode_stream(q, lit + 3 * seg, n - 3 * seg, &h); q += s;
+                body = (size_t)(q - p);
+            }
+            size_t csize = ts + body;
+            if (lh + csize < rawHdr + n) {
+                uint32_t sf = !four ? 0 : (lh == 3 ? 1 : (lh == 4 ? 2 : 3));
+                if (lh == 3) wr24(dst, (uint32_t)(2 | (sf << 2) | (n << 4) | (csize << 14)));
+                else if (lh == 4) wr32(dst, (uint32_t)(2 | (sf << 2) | (n << 4) | (csize << 18)));
+                else { uint64_t v = 2 | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)csize << 22); wr32(dst, (uint32_t)v); dst[4] = (uint8_t)(v >> 32); }
+                memcpy(dst + lh, tmp, csize); free(tmp);
+                return lh + csize;
+            }
+        }
+        free(tmp);
+    }
+    /* raw literals */
+    if (rawHdr == 1) dst[0] = (uint8_t)(n << 3);
+    else if (rawHdr == 2) wr16(dst, (uint32_t)((1 << 2) | (n << 4)));
+    else wr24(dst, (uint32_t)((3 << 2) | (n << 4)));
+    memcpy(dst + rawHdr, lit, n);
+    return rawHdr + n;
+}
+
+/* ======================================================================= sequences */
+typedef struct { uint32_t ll, ml, offBase; } fseq_t;
+
+/* merge capped pieces + repcode resolution (sequential per block; rep history unknown (=0) at
+ * block start so blocks stay independent). Returns final sequence count. */
+static uint32_t merge_and_resolve(fseq_t *out, const b2zo_rawseq *raw, uint32_t nraw,
+                                  const uint8_t *frame, size_t blkStart) {
+    uint32_t n = 0, rep[3] = { 0, 0, 0 };
+    uint32_t prevEnd = 0, prevOff = 0, prevRawLen = 0, prevValid = 0;
+    /* pass 1: merge into (pos,len,off) kept in `out` as ll/ml/offBase(=raw offset) */
+    for (uint32_t i = 0; i < nraw; i++) {
+        uint32_t pos = raw[i].poslen & 0x1FFFF, len = (raw[i].poslen >> 17) + 3, off = raw[i].off;
+        if (prevValid && pos == prevEnd && prevRawLen == B2Z_CAP) {
+            int same = off == prevOff;
+            if (!same) {
+                const uint8_t *p = frame + blkStart + pos;
+                same = count_match(p - prevOff, p, len) == len;
+            }
+            if (same) { out[n - 1].ml += len; prevEnd += len; prevRawLen = len; continue; }
+        }
+        out[n].ll = pos - prevEnd; out[n].ml = len; out[n].offBase = off; n++;
+        prevEnd = pos + len; prevOff = off; prevRawLen = len; prevValid = 1;
+    }
+    /* pass 2: repcodes */
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t off = out[i].offBase, ll0 = out[i].ll == 0, code = 0;
+        if (!ll0) { if (off == rep[0]) code = 1; else if (off == rep[1]) code = 2; else if (off == rep[2]) code = 3; }
+        else { if (off == rep[1]) code = 1; else if (off == rep[2]) code = 2; else if (rep[0] > 1 && off == rep[0] - 1) code = 3; }
+        if (code == 0) { out[i].offBase = off + 3; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+        else {
+            out[i].offBase = code;
+            uint32_t idx = code - 1 + ll0;                  /* 0..3 */
+            if (idx != 0) {
+                uint32_t cur = idx == 3 ? rep[0] - 1 : rep[idx];
+                if (idx != 1) rep[2] = rep[1];
+                rep[1] = rep[0]; rep[0] = cur;
+            }
+        }
+    }
+    return n;
+}
+
+/* choose table mode for one symbol type and serialise its description */
+typedef struct { fse_ctable ct; uint32_t mode; } seq_table_choice;
+static size_t choose_seq_table(seq_table_choice *ch, uint8_t *dst, const uint8_t *codes, uint32_t nbSeq,
+                               uint32_t maxSymAll, uint32_t maxLog, const int16_t *defNorm, uint32_t defMaxSym, uint32_t defLog) {
+    uint32_t count[64] = { 0 }, maxSym = 0, present = 0, big = 0;
+    for (uint32_t i = 0; i < nbSeq; i++) count[codes[i]]++;
+    for (uint32_t s = 0; s <= maxSymAll; s++) if (count[s]) { maxSym = s; present++; if (count[s] > big) big = count[s]; }
+    if (big == nbSeq && !(nbSeq <= 2 && maxSym <= defMaxSym)) {   /* RLE: single zero-bit state */
+        memset(&ch->ct, 0, sizeof(ch->ct));
+        ch->mode = 1; dst[0] = (uint8_t)maxSym; return 1;
+    }
+    uint64_t costDef = maxSym <= defMaxSym ? fse_cost_fx8(count, defNorm, maxSym, defLog) : ~0ull;
+    /* compressed */
+    uint32_t log = zf_highbit32(nbSeq > 1 ? nbSeq - 1 : 1) >= 2 ? zf_highbit32(nbSeq > 1 ? nbSeq - 1 : 1) - 2 : 0;
+    uint32_t minA = zf_highbit32(nbSeq) + 1, minB = zf_highbit32(maxSym ? maxSym : 1) + 2, lo = minA < minB ? minA : minB;
+    if (log > maxLog) log = maxLog;
+    if (log < lo) log = lo;
+    if (log < 5) log = 5;
+    if (log > maxLog) log = maxLog;
+    while ((1u << log) < present) log++;
+    int16_t norm[64]; uint8_t hdr[64];
+    fse_normalize(norm, log, count, nbSeq, maxSym);
+    size_t hs = fse_write_ncount(hdr, norm, maxSym, log);
+    uint64_t costFse = fse_cost_fx8(count, norm, maxSym, log) + ((uint64_t)hs << 11);
+    if (costDef <= costFse || big == nbSeq) {
+        fse_build_ctable(&ch->ct, defNorm, defMaxSym, defLog); ch->mode = 0; return 0;
+    }
+    fse_build_ctable(&ch->ct, norm, maxSym, log); ch->mode = 2; memcpy(dst, hdr, hs); return hs;
+}
+
+static size_t write_sequences(uint8_t *dst, const fseq_t *seq, uint32_t nbSeq) {
+    uint8_t *op = dst;
+    if (nbSeq < 128) *op++ = (uint8_t)nbSeq;
+    else if (nbSeq < 0x7F00) { *op++ = (uint8_t)((nbSeq >> 8) + 128); *op++ = (uint8_t)nbSeq; }
+    else { *op++ = 255; wr16(op, nbSeq - 0x7F00); op += 2; }
+    if (nbSeq == 0) return (size_t)(op - dst);
+    uint8_t *llc = (uint8_t *)malloc(3 * (size_t)nbSeq), *ofc = llc + nbSeq, *mlc = ofc + nbSeq;
+    for (uint32_t i = 0; i < nbSeq; i++) {
+        llc[i] = (uint8_t)zf_ll_code(seq[i].ll); mlc[i] = (uint8_t)zf_ml_code(seq[i].ml - 3); ofc[i] = (uint8_t)zf_highbit32(seq[i].offBase);
+    }
+    uint8_t *modes = op++;
+    seq_table_choice L, O, M;
+    op += choose_seq_table(&L, op, llc, nbSeq, ZF_MAXLL, ZF_LL_FSELOG, ZF_LL_defaultNorm, 35, ZF_LL_DEFLOG);
+    op += choose_seq_table(&O, op, ofc, nbSeq, ZF_MAXOFF, ZF_OF_FSELOG, ZF_OF_defaultNorm, 28, ZF_OF_DEFLOG);
+    op += choose_seq_table(&M, op, mlc, nbSeq, ZF_MAXML, ZF_ML_FSELOG, ZF_ML_defaultNorm, 52, ZF_ML_DEFLOG);
+    *modes = (uint8_t)((L.mode << 6) | (O.mode << 4) | (M.mode << 2));
+    bitw_t b; bw_init(&b, op);
+    uint32_t i = nbSeq - 1, nb, bits;
+    uint32_t sM = fse_init_state(&M.ct, mlc[i]), sO = fse_init_state(&O.ct, ofc[i]), sL = fse_init_state(&L.ct, llc[i]);
+    bw_add(&b, seq[i].ll - ZF_LL_base[llc[i]], ZF_LL_bits[llc[i]]);
+    bw_add(&b, seq[i].ml - ZF_ML_base[mlc[i]], ZF_ML_bits[mlc[i]]);
+    bw_add(&b, seq[i].offBase - (1u << ofc[i]), ofc[i]);
+    while (i-- > 0) {
+        bits = fse_encode(&O.ct, &sO, ofc[i], &nb); bw_add(&b, bits, nb);
+        bits = fse_encode(&M.ct, &sM, mlc[i], &nb); bw_add(&b, bits, nb);
+        bits = fse_encode(&L.ct, &sL, llc[i], &nb); bw_add(&b, bits, nb);
+        bw_add(&b, seq[i].ll - ZF_LL_base[llc[i]], ZF_LL_bits[llc[i]]);
+        bw_add(&b, seq[i].ml - ZF_ML_base[mlc[i]], ZF_ML_bits[mlc[i]]);
+        bw_add(&b, seq[i].offBase - (1u << ofc[i]), ofc[i]);
+    }
+    bw_add(&b, sM, M.ct.log); bw_add(&b, sO, O.ct.log); bw_add(&b, sL, L.ct.log);
+    op = bw_close(&b);
+    free(llc);
+    return (size_t)(op - dst);
+}
+
+/* One block: returns bytes written including the 3-byte header. */
+static size_t compress_block(uint8_t *dst, const uint8_t *frame, size_t blkStart, size_t blkSize, int last,
+                             const b2zo_rawseq *raw, uint32_t nraw, const uint8_t *lits, uint32_t nlit) {
+    fseq_t *seq = (fseq_t *)malloc(sizeof(fseq_t) * (nraw + 1));
+    uint32_t nbSeq = merge_and_resolve(seq, raw, nraw, frame, blkStart);
+    const uint8_t *src = frame + blkStart;
+    size_t out;
+    if (blkSize > 1 && nbSeq == 1 && nlit == 1 && seq[0].ll == 1 && seq[0].ml == blkSize - 1 && seq[0].offBase == 1 + 3) {
+        wr24(dst, (uint32_t)(last | (1 << 1) | (blkSize << 3))); dst[3] = src[0]; out = 4;   /* RLE block */
+    } else {
+        uint8_t *body = (uint8_t *)malloc(blkSize + blkSize / 2 + 1024);
+        size_t ls = write_literals(body, lits, nlit);
+        size_t ss = write_sequences(body + ls, seq, nbSeq);
+        if (ls + ss < blkSize) { wr24(dst, (uint32_t)(last | (2 << 1) | ((ls + ss) << 3))); memcpy(dst + 3, body, ls + ss); out = 3 + ls + ss; }
+        else { wr24(dst, (uint32_t)(last | (blkSize << 3))); memcpy(dst + 3, src, blkSize); out = 3 + blkSize; }
+        free(body);
+    }
+    free(seq);
+    return out;
+}
+
+static size_t write_frame_header(uint8_t *dst, size_t n, const b2zo_enc_params *P) {
+    wr32(dst, ZF_MAGIC);
+    if (n == 0) { dst[4] = 0x20; dst[5] = 0; return 6; }     /* single segment, FCS = 0 */
+    uint32_t wl = 10; while (((size_t)1 << wl) < n && wl < P->windowLog) wl++;
+    dst[4] = (uint8_t)(0x80 | ((P->flags & 2) ? 4 : 0));     /* 4-byte FCS, window descriptor present */
+    dst[5] = (uint8_t)((wl - 10) << 3);
+    wr32(dst + 6, (uint32_t)n);
+    return 10;
+}
+
+int64_t b2zo_zstd_compress(void *dstv, size_t dstCap, const void *srcv, size_t srcSize, const b2zo_enc_params *P) {
+    const uint8_t *src = (const uint8_t *)srcv; uint8_t *dst = (uint8_t *)dstv, *op = dst;
+    if (dstCap < b2zo_zstd_compress_bound(srcSize, P)) return -2;
+    size_t F = (size_t)1 << P->frameLog;
+    size_t nblkMax = (F + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
+    b2zo_rawseq *seqs = (b2zo_rawseq *)malloc(sizeof(b2zo_rawseq) * B2Z_MAXSEQ * nblkMax);
+    uint32_t *nseq = (uint32_t *)malloc(4 * nblkMax * 2), *nlit = nseq + nblkMax;
+    uint8_t *lits = (uint8_t *)malloc(F);
+    size_t f0 = 0;
+    do {
+        size_t fn = srcSize - f0 < F ? srcSize - f0 : F;
+        const uint8_t *frame = src + f0;
+        uint8_t *hint = NULL;
+        if (P->flags & 1) { wr32(op, ZF_MAGIC_SKIP); wr32(op + 4, 4); hint = op + 8; op += 12; }
+        uint8_t *fstart = op;
+        op += write_frame_header(op, fn, P);
+        if (fn == 0) { wr24(op, 1); op += 3; }
+        else {
+            find_sequences_frame(frame, fn, P, seqs, nseq, lits, nlit);
+            size_t nblk = (fn + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
+            for (size_t b = 0; b < nblk; b++) {
+                size_t bs = b * ZF_BLOCK_MAX, bn = fn - bs < ZF_BLOCK_MAX ? fn - bs : ZF_BLOCK_MAX;
+                op += compress_block(op, frame, bs, bn, b + 1 == nblk, seqs + b * B2Z_MAXSEQ, nseq[b], lits + bs, nlit[b]);
+            }
+        }
+        if (P->flags & 2) { wr32(op, (uint32_t)b2zo_xxh64(frame, fn, 0)); op += 4; }
+        if (hint) wr32(hint, (uint32_t)(op - fstart));
+        f0 += fn;
+    } while (f0 < srcSize);
+    free(lits); free(nseq); free(seqs);
+    return (int64_t)(op - dst);
+}
