@@ -1,0 +1,20 @@
+#!/bin/bash
+# Build libb200z.so (sm_100a only) and the corpus helper in-tree.  Usage: ./build.sh [-v]
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Icsrc -I../include"
+[ "$1" = "-v" ] && FLAGS="$FLAGS -Xptxas -v"
+mkdir -p build
+objs=""
+for f in csrc/*.cu; do
+  o=build/$(basename "${f%.cu}").o
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find csrc ../include -name '*.h' -newer "$o" -o -name '*.cuh' -newer "$o")" ]; then
+    $NVCC $FLAGS -c "$f" -o "$o" &
+  fi
+  objs="$objs $o"
+done
+wait
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libb200z.so $objs -lcudart
+gcc -O2 -shared -fPIC -pthread -o corpus/libb200z_corpus.so corpus/g2gen.c
+echo "built $(pwd)/libb200z.so"

@@ -1,0 +1,302 @@
+// b2z_api.cu -- the extern "C" shim of libb200z.so (see include/b200z.h).
+//
+// Host dispatcher for one device: owns the stream, the scratch arenas (hash tables, per-block
+// sequence/literal/slot arrays) and the staging buffers of the host-pointer entry points.
+// Replaces the job/worker plumbing of C/zstd/zstdmt_compress.c (ZSTDMT_compressStream_generic
+// :1853, ZSTDMT_createCompressionJob :1403, ZSTDMT_flushProduced :1488): frames are the jobs,
+// warps are the workers, the assemble kernels are the ordered flush.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "../../include/b200z.h"
+#include "b2z_kernels.h"
+#include "b2z_dec.h"
+
+using namespace b2z;
+
+struct Arena {                       // grow-only device buffer
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = n; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct b200z_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    EncGeom geom{};
+    int level = 3;
+    uint32_t batchLog = 32;
+    uint32_t smCount = 148;
+    Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut;
+    Arena decScratch[8];
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double stat[16] = {0};
+    char err[256] = {0};
+};
+
+static int fail(b200z_ctx* c, int code, const char* fmt, const char* detail = "") {
+    if (c) snprintf(c->err, sizeof(c->err), fmt, detail);
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError(); \
+    return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? B200Z_E_MEMORY : B200Z_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } } while (0)
+
+extern "C" {
+
+int b200z_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b200z_create(b200z_ctx** out, int device) {
+    if (!out) return B200Z_E_PARAM;
+    *out = nullptr;
+    int n = b200z_device_count();
+    if (n <= 0 || device < 0 || device >= n) return B200Z_E_NODEVICE;   // no CPU fallback, by design
+    b200z_ctx* ctx = new (std::nothrow) b200z_ctx();
+    if (!ctx) return B200Z_E_MEMORY;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B200Z_E_NODEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->smCount = (uint32_t)prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+    ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
+    ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 0;
+    *out = ctx;
+    return B200Z_OK;
+}
+
+void b200z_destroy(b200z_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut };
+    for (Arena* a : all) a->release();
+    for (Arena& a : ctx->decScratch) a.release();
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
+    if (!ctx) return B200Z_E_PARAM;
+    switch (param) {
+    case B200Z_P_LEVEL:     if (v < 1 || v > 22) return fail(ctx, B200Z_E_PARAM, "level out of range%s"); ctx->level = (int)v; return 0;
+    case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");
+                            ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v; return 0;
+    case B200Z_P_HASHLOG_L: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
+    case B200Z_P_HASHLOG_S: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogS out of range%s"); ctx->geom.hashLogS = (uint32_t)v; return 0;
+    case B200Z_P_WINDOWLOG: if (v < 10 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "windowLog out of range%s"); ctx->geom.windowLog = (uint32_t)v; return 0;
+    case B200Z_P_FLAGS:     if (v & ~1ll) return fail(ctx, B200Z_E_UNSUPPORTED, "only flag bit0 (skippable size hints) is supported%s"); ctx->geom.flags = (uint32_t)v; return 0;
+    case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
+    }
+    return fail(ctx, B200Z_E_PARAM, "unknown parameter%s");
+}
+
+int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
+    if (!ctx || !v) return B200Z_E_PARAM;
+    switch (param) {
+    case B200Z_P_LEVEL: *v = ctx->level; return 0;
+    case B200Z_P_FRAMELOG: *v = ctx->geom.frameLog; return 0;
+    case B200Z_P_HASHLOG_L: *v = ctx->geom.hashLogL; return 0;
+    case B200Z_P_HASHLOG_S: *v = ctx->geom.hashLogS; return 0;
+    case B200Z_P_WINDOWLOG: *v = ctx->geom.windowLog; return 0;
+    case B200Z_P_FLAGS: *v = ctx->geom.flags; return 0;
+    case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
+    }
+    return B200Z_E_PARAM;
+}
+
+const char* b200z_last_error(b200z_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+double b200z_get_stat(b200z_ctx* ctx, int s) { return (ctx && s > 0 && s < 16) ? ctx->stat[s] : 0.0; }
+void b200z_reset_stats(b200z_ctx* ctx) { if (ctx) memset(ctx->stat, 0, sizeof(ctx->stat)); }
+
+size_t b200z_zstd_compress_bound(b200z_ctx* ctx, size_t n) {
+    const uint32_t fl = ctx ? ctx->geom.frameLog : B2Z_DEF_FRAMELOG;
+    const size_t frames = (n >> fl) + 1, blocks = (n >> 17) + frames;
+    return n + blocks * 3 + frames * (B2Z_FRAME_HDR_MAX + 12 + 4) + 64;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- encoder driver
+static uint32_t match_warps(const b200z_ctx* ctx, uint64_t nFrames) {
+    const uint64_t cap = (uint64_t)ctx->smCount * 32u;
+    return (uint32_t)(nFrames < cap ? nFrames : cap);
+}
+
+static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
+    const uint64_t F = 1ull << ctx->geom.frameLog;
+    const uint64_t nFrames = (batchBytes + F - 1) / F;
+    const uint64_t nBlocks = (batchBytes + B2Z_BLOCK - 1) / B2Z_BLOCK + 1;
+    const uint32_t nWarps = match_warps(ctx, nFrames);
+    const size_t tableBytes = ((size_t)(1u << ctx->geom.hashLogL) + (1u << ctx->geom.hashLogS)) * 4u;
+    int bad = 0;
+    bad |= ctx->tables.reserve(tableBytes * nWarps);
+    bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);
+    bad |= ctx->nseq.reserve(nBlocks * 4);
+    bad |= ctx->lits.reserve(nBlocks * (size_t)B2Z_BLOCK);
+    bad |= ctx->nlit.reserve(nBlocks * 4);
+    bad |= ctx->slots.reserve(nBlocks * (size_t)B2Z_SLOT);
+    bad |= ctx->slotSize.reserve(nBlocks * 4);
+    bad |= ctx->blockOff.reserve((nBlocks + 1) * 8);
+    bad |= ctx->frameOff.reserve((nFrames + 2) * 8);
+    bad |= ctx->scalars.reserve(64);
+    return bad ? fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s") : 0;
+}
+
+// compress [d_src, d_src+n) (n > 0, one batch) to d_dst; returns produced bytes through *produced
+static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t* produced, bool stageMOnly) {
+    int rc = enc_reserve(ctx, n);
+    if (rc) return rc;
+    const EncGeom& g = ctx->geom;
+    const uint64_t F = 1ull << g.frameLog;
+    const uint64_t nFrames = (n + F - 1) / F;
+    const uint32_t nBlocks = (uint32_t)((n >> 17) + ((n & (B2Z_BLOCK - 1)) ? 1 : 0));
+    // blocks are numbered per frame with a fixed stride (frames are multiples of 128 KiB)
+    const uint32_t nWarps = match_warps(ctx, nFrames);
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    launch_zstd_enc_match(d_src, n, g, (uint32_t*)ctx->tables.p, nWarps, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
+                          (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[1], st));
+    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+    if (!stageMOnly) {
+        launch_zstd_enc_entropy(d_src, n, g, (const uint64_t*)ctx->seqs.p, (const uint32_t*)ctx->nseq.p, (const uint8_t*)ctx->lits.p,
+                                (const uint32_t*)ctx->nlit.p, (uint8_t*)ctx->slots.p, (uint32_t*)ctx->slotSize.p, nBlocks, st);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[2], st));
+        launch_zstd_enc_assemble(n, g, (const uint8_t*)ctx->slots.p, (const uint32_t*)ctx->slotSize.p, nBlocks, (uint64_t*)ctx->blockOff.p,
+                                 d_dst, (uint64_t*)ctx->scalars.p, (uint64_t*)ctx->frameOff.p, st);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[3], st));
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
+        uint64_t out = 0;
+        CU(cudaMemcpyAsync(&out, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        *produced = out;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_ENC_ENTROPY_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stat[B200Z_S_ENC_ASSEMBLE_MS] += ms;
+    } else {
+        CU(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+    }
+    return 0;
+}
+
+static const uint8_t kEmptyFrame[9] = { 0x28, 0xB5, 0x2F, 0xFD, 0x20, 0x00, 0x01, 0x00, 0x00 };
+
+extern "C" {
+
+int b200z_zstd_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_dst, size_t dstCap, size_t* dstSize) {
+    if (!ctx || !dstSize || (!d_src && srcSize) || !d_dst) return B200Z_E_PARAM;
+    if ((uintptr_t)d_src & 15u) return fail(ctx, B200Z_E_PARAM, "device source must be 16-byte aligned%s");
+    if (dstCap < b200z_zstd_compress_bound(ctx, srcSize)) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_bound%s");
+    CU(cudaSetDevice(ctx->device));
+    if (srcSize == 0) {
+        size_t o = 0; uint8_t tmp[21];
+        if (ctx->geom.flags & 1u) { const uint8_t k[12] = { 0x50, 0x2A, 0x4D, 0x18, 4, 0, 0, 0, 9, 0, 0, 0 }; memcpy(tmp, k, 12); o = 12; }
+        memcpy(tmp + o, kEmptyFrame, 9); o += 9;
+        CU(cudaMemcpyAsync(d_dst, tmp, o, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *dstSize = o; return 0;
+    }
+    // batches are whole frames
+    const uint64_t F = 1ull << ctx->geom.frameLog;
+    uint64_t batch = 1ull << ctx->batchLog; if (batch < F) batch = F;
+    uint64_t done = 0, outPos = 0;
+    while (done < srcSize) {
+        const uint64_t n = (srcSize - done) < batch ? (srcSize - done) : batch;
+        uint64_t produced = 0;
+        int rc = enc_batch(ctx, (const uint8_t*)d_src + done, n, (uint8_t*)d_dst + outPos, &produced, false);
+        if (rc) return rc;
+        done += n; outPos += produced;
+    }
+    *dstSize = (size_t)outPos;
+    return 0;
+}
+
+int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize) {
+    if (!ctx || !dstSize || (!src && srcSize) || !dst) return B200Z_E_PARAM;
+    const size_t bound = b200z_zstd_compress_bound(ctx, srcSize);
+    if (dstCap < bound) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_bound%s");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(bound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+    if (srcSize) CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
+    size_t out = 0;
+    int rc = b200z_zstd_compress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, bound, &out);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
+    *dstSize = out;
+    return 0;
+}
+
+int b200z_zstd_enc_stage_m(b200z_ctx* ctx, const void* d_src, size_t srcSize, uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit) {
+    if (!ctx || !d_src || !srcSize) return B200Z_E_PARAM;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t produced = 0;
+    int rc = enc_batch(ctx, (const uint8_t*)d_src, srcSize, nullptr, &produced, true);
+    if (rc) return rc;
+    // per-frame block stride -> dense block numbering of the oracle (identical unless the last frame is short)
+    const uint64_t F = 1ull << ctx->geom.frameLog; const uint32_t bpf = (uint32_t)(F >> 17);
+    const uint64_t nFrames = (srcSize + F - 1) / F;
+    uint64_t dense = 0;
+    for (uint64_t f = 0; f < nFrames; f++) {
+        const uint64_t fn = (srcSize - f * F) < F ? (srcSize - f * F) : F;
+        const uint32_t nb = (uint32_t)((fn + B2Z_BLOCK - 1) / B2Z_BLOCK);
+        const size_t sb = (size_t)f * bpf;
+        CU(cudaMemcpy(nseq + dense, (uint32_t*)ctx->nseq.p + sb, nb * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(nlit + dense, (uint32_t*)ctx->nlit.p + sb, nb * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(seqs + dense * B2Z_MAXSEQ, (uint64_t*)ctx->seqs.p + sb * B2Z_MAXSEQ, (size_t)nb * B2Z_MAXSEQ * 8, cudaMemcpyDeviceToHost));
+        dense += nb;
+    }
+    CU(cudaMemcpy(lits, ctx->lits.p, srcSize, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------- device memory helpers
+int b200z_dev_alloc(b200z_ctx* ctx, void** d_ptr, size_t bytes) {
+    if (!ctx || !d_ptr) return B200Z_E_PARAM;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return 0;
+}
+int b200z_dev_free(b200z_ctx* ctx, void* d_ptr) { if (!ctx) return B200Z_E_PARAM; CU(cudaSetDevice(ctx->device)); CU(cudaFree(d_ptr)); return 0; }
+int b200z_dev_upload(b200z_ctx* ctx, void* d_dst, const void* src, size_t bytes) {
+    if (!ctx) return B200Z_E_PARAM;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stat[B200Z_S_H2D_BYTES] += (double)bytes; return 0;
+}
+int b200z_dev_download(b200z_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
+    if (!ctx) return B200Z_E_PARAM;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stat[B200Z_S_D2H_BYTES] += (double)bytes; return 0;
+}
+int b200z_host_alloc_pinned(void** ptr, size_t bytes) {
+    if (!ptr) return B200Z_E_PARAM;
+    if (cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return B200Z_E_MEMORY; }
+    return 0;
+}
+int b200z_host_free_pinned(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 : B200Z_E_CUDA; }
+
+}  // extern "C"

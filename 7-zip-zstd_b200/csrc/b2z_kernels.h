@@ -1,0 +1,30 @@
+// b2z_kernels.h -- host-visible launchers of the sm_100a kernels (internal to libb200z.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b2z_params.h"
+
+#define B2Z_MATCH_THREADS   32      // one frame-warp per CTA: spreads few frames over many SMs
+#define B2Z_ENT_WARPS       4       // stage E: warps (= blocks of input) per CTA
+#define B2Z_SLOT            (B2Z_BODY_CAP + 64u) // per-block output slot: 3-byte header + body (<= B2Z_BODY_CAP), 16-B multiple
+
+namespace b2z {
+
+struct EncGeom { uint32_t frameLog, hashLogL, hashLogS, windowLog, flags; };
+
+// stage M: one warp per frame -> per-block final sequences + literal bytes
+void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,
+                           uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, cudaStream_t st);
+
+// stage E: one warp per 128 KiB block -> compressed block (with 3-byte header) in its slot
+void launch_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, const EncGeom& g,
+                             const uint64_t* seqs, const uint32_t* nseq, const uint8_t* lits, const uint32_t* nlit,
+                             uint8_t* slots, uint32_t* slotSize, uint32_t nBlocks, cudaStream_t st);
+
+// frame assembly: offsets (one CTA scan) + gather of slots into contiguous frames
+void launch_zstd_enc_assemble(uint64_t srcSize, const EncGeom& g, const uint8_t* slots, const uint32_t* slotSize,
+                              uint32_t nBlocks, uint64_t* blockOff /* [nBlocks+1] scratch */, uint8_t* dst,
+                              uint64_t* outSize /* device scalar */, uint64_t* frameOff /* [nFrames+1] or null */,
+                              cudaStream_t st);
+
+}  // namespace b2z

@@ -22,6 +22,13 @@
 #define B2Z_FRAME_HDR_MAX  10
 #define B2Z_LIT_HUF_MIN    64u     /* fewer literals than this are stored raw                */
 #define B2Z_LIT_RLE_MIN    8u
+#define B2Z_BODY_CAP       196608u /* a block body whose size upper bound exceeds this is stored raw */
+
+/* final sequence record: offBase (25 bits) | litLength (18) | matchLength (18) */
+#define B2Z_PACK_SEQ(offBase, ll, ml) ((uint64_t)(offBase) | ((uint64_t)(ll) << 25) | ((uint64_t)(ml) << 43))
+#define B2Z_SEQ_OFFBASE(s) ((uint32_t)((s) & 0x1FFFFFFu))
+#define B2Z_SEQ_LL(s)      ((uint32_t)(((s) >> 25) & 0x3FFFFu))
+#define B2Z_SEQ_ML(s)      ((uint32_t)(((s) >> 43) & 0x3FFFFu))
 
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL

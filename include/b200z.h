@@ -1,0 +1,106 @@
+/* b200z.h -- C ABI of libb200z.so: the B200 block-parallel codec engine behind 7-Zip's
+ * ZSTD (method 4F71101) and LZMA2/FLZMA2 (method 21) coders.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The host-side
+ * coder classes (7-zip-zstd_b200/codec/, mirroring CPP/7zip/Compress/ZstdEncoder.cpp etc.) and
+ * any other FFI (ctypes, cgo, JNI) bind exactly these entry points.
+ *
+ * Which reference interface each entry point replaces (paths under /root/reference):
+ *   b200z_create / b200z_destroy ........ ZSTD_createCCtx / ZSTD_freeCCtx as used by
+ *                                         CPP/7zip/Compress/ZstdEncoder.cpp:262-265, ZstdDecoder.cpp:76-80
+ *   b200z_set_param ..................... ZSTD_CCtx_setParameter calls, ZstdEncoder.cpp:268-396
+ *   b200z_zstd_compress_bound ........... ZSTD_compressBound (C/zstd/zstd.h)
+ *   b200z_zstd_compress_{host,device} ... the ZSTD_compressStream2 loop of ZstdEncoder.cpp:398-461
+ *                                         (one call = one whole Code() input; the zstdmt job slicing of
+ *                                         C/zstd/zstdmt_compress.c:1184-1246 is the frame slicing here)
+ *   b200z_zstd_decompress_{host,device} . the ZSTD_decompressStream loop of ZstdDecoder.cpp:108-173
+ *   b200z_zstd_frame_info ............... ZSTD_getFrameHeader / ZSTD_findFrameCompressedSize
+ *   b200z_last_error .................... ZSTD_getErrorName (ZstdEncoder.cpp:427-441 maps codes to HRESULT)
+ *
+ * All functions return B200Z_OK (0) or a negative B200Z_E_* code.  There is NO CPU fallback:
+ * without a usable CUDA device every call fails with B200Z_E_NODEVICE.
+ */
+#ifndef B200Z_H
+#define B200Z_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Z_OK            0
+#define B200Z_E_NODEVICE   -1   /* no CUDA device / driver error                          */
+#define B200Z_E_MEMORY     -2   /* device or pinned-host allocation failed  (E_OUTOFMEMORY) */
+#define B200Z_E_PARAM      -3   /* bad parameter                             (E_INVALIDARG)  */
+#define B200Z_E_DSTSIZE    -4   /* destination too small                                     */
+#define B200Z_E_CORRUPT    -5   /* malformed compressed data                 (S_FALSE)       */
+#define B200Z_E_UNSUPPORTED -6  /* valid but unsupported input (dictionary, legacy frame) (E_NOTIMPL) */
+#define B200Z_E_CUDA       -7   /* kernel launch / execution error           (E_FAIL)        */
+#define B200Z_E_CHECKSUM   -8   /* content checksum mismatch                 (S_FALSE)       */
+
+/* parameters (b200z_set_param) */
+#define B200Z_P_LEVEL       1   /* 1..22; every level currently maps to the level-3 (dfast-class) parser */
+#define B200Z_P_FRAMELOG    2   /* log2 of the independent frame ("job") size, 17..24, default 22       */
+#define B200Z_P_HASHLOG_L   3   /* long-hash table log, default 17  (clevels.h:31 hashLog)               */
+#define B200Z_P_HASHLOG_S   4   /* short-hash table log, default 16 (clevels.h:31 chainLog)              */
+#define B200Z_P_WINDOWLOG   5   /* max match distance log, default = frameLog                            */
+#define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention)   */
+#define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
+
+/* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
+ * measured with CUDA events on the context's stream around each stage */
+#define B200Z_S_ENC_MATCH_MS    1
+#define B200Z_S_ENC_ENTROPY_MS  2
+#define B200Z_S_ENC_ASSEMBLE_MS 3
+#define B200Z_S_DEC_ENTROPY_MS  4
+#define B200Z_S_DEC_EXEC_MS     5
+#define B200Z_S_KERNEL_LAUNCHES 6   /* number of kernels launched */
+#define B200Z_S_H2D_BYTES       7
+#define B200Z_S_D2H_BYTES       8
+
+typedef struct b200z_ctx b200z_ctx;
+
+int  b200z_device_count(void);
+int  b200z_create(b200z_ctx **out, int device);
+void b200z_destroy(b200z_ctx *ctx);
+int  b200z_set_param(b200z_ctx *ctx, int param, int64_t value);
+int  b200z_get_param(b200z_ctx *ctx, int param, int64_t *value);
+const char *b200z_last_error(b200z_ctx *ctx);
+double b200z_get_stat(b200z_ctx *ctx, int stat);
+void b200z_reset_stats(b200z_ctx *ctx);
+
+size_t b200z_zstd_compress_bound(b200z_ctx *ctx, size_t srcSize);
+
+/* src/dst are DEVICE pointers (src 16-byte aligned); synchronous on the context's stream */
+int b200z_zstd_compress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize,
+                               void *d_dst, size_t dstCap, size_t *dstSize);
+/* src/dst are HOST pointers (pinned or pageable): H2D copy, compress, D2H copy */
+int b200z_zstd_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
+                             void *dst, size_t dstCap, size_t *dstSize);
+
+/* Sum of the decompressed sizes of all frames in a host buffer (needs frame content sizes or
+ * cheap block-header walks; returns B200Z_E_UNSUPPORTED if a frame's size is not declared). */
+int b200z_zstd_frame_info(const void *src, size_t srcSize, uint64_t *contentSize, uint32_t *nFrames);
+
+int b200z_zstd_decompress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize,
+                                 void *d_dst, size_t dstCap, size_t *dstSize);
+int b200z_zstd_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
+                               void *dst, size_t dstCap, size_t *dstSize);
+
+/* Test tap: run only stage M (match finding + parse) on a device buffer and copy its per-block
+ * outputs to host arrays (same layout as the oracle's b2zo_zstd_find_sequences). */
+int b200z_zstd_enc_stage_m(b200z_ctx *ctx, const void *d_src, size_t srcSize,
+                           uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit);
+
+/* device memory helpers so FFI users need no CUDA binding of their own */
+int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);
+int b200z_dev_free(b200z_ctx *ctx, void *d_ptr);
+int b200z_dev_upload(b200z_ctx *ctx, void *d_dst, const void *src, size_t bytes);
+int b200z_dev_download(b200z_ctx *ctx, void *dst, const void *d_src, size_t bytes);
+int b200z_host_alloc_pinned(void **ptr, size_t bytes);
+int b200z_host_free_pinned(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -29,10 +29,10 @@ void   b2zo_enc_default_params(b2zo_enc_params *p, int level);
 size_t b2zo_zstd_compress_bound(size_t srcSize, const b2zo_enc_params *p);
 int64_t b2zo_zstd_compress(void *dst, size_t dstCap, const void *src, size_t srcSize, const b2zo_enc_params *p);
 
-/* Debug taps for stage-level parity with the GPU (tests compare these arrays). */
-typedef struct { uint32_t off; uint32_t poslen; } b2zo_rawseq;   /* poslen = pos | (len-3)<<17 */
+/* Stage tap for parity with the GPU's stage M: per 128 KiB block, final sequences packed as
+ * B2Z_PACK_SEQ(offBase, ll, ml) (b2z_params.h) and the literal bytes (at the block's offset). */
 int64_t b2zo_zstd_find_sequences(const void *src, size_t srcSize, const b2zo_enc_params *p,
-                                 b2zo_rawseq *seqs /* [nblocks*32768] */, uint32_t *nseq /* [nblocks] */,
+                                 uint64_t *seqs /* [nblocks*B2Z_MAXSEQ] */, uint32_t *nseq /* [nblocks] */,
                                  uint8_t *lits /* [srcSize] */, uint32_t *nlit /* [nblocks] */);
 
 #ifdef __cplusplus

@@ -66,25 +66,68 @@ static size_t count_match(const uint8_t *a, const uint8_t *b, size_t maxLen) {
 
 typedef struct { uint32_t off; uint16_t len; } cand_t;
 
-/* One frame: src[0..n).  Emits, per 128 KiB block, raw sequences and the literal bytes.
+/* Per-block sequence emitter: joins capped pieces, resolves repcodes, packs (ll, ml, offBase).
+ * Sequential per block; rep history is "unknown" (0) at block start so that blocks stay
+ * independent of each other (ZSTD_updateRep semantics, zstd_compress_internal.h:817-835). */
+typedef struct {
+    uint32_t rep[3];
+    uint32_t pendPos, pendLen, pendOff, pendLastPiece, pendValid;   /* block-relative */
+    uint32_t prevEnd;                                                /* end of last flushed sequence */
+    uint64_t *out; uint32_t n;
+} emitter_t;
+
+static void emit_flush(emitter_t *e) {
+    if (!e->pendValid) return;
+    uint32_t ll = e->pendPos - e->prevEnd, off = e->pendOff, ll0 = ll == 0, code = 0, offBase;
+    uint32_t *rep = e->rep;
+    if (!ll0) { if (off == rep[0]) code = 1; else if (off == rep[1]) code = 2; else if (off == rep[2]) code = 3; }
+    else { if (off == rep[1]) code = 1; else if (off == rep[2]) code = 2; else if (rep[0] > 1 && off == rep[0] - 1) code = 3; }
+    if (code == 0) { offBase = off + 3; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
+    else {
+        offBase = code;
+        uint32_t idx = code - 1 + ll0;                      /* 0..3 */
+        if (idx != 0) {
+            uint32_t cur = idx == 3 ? rep[0] - 1 : rep[idx];
+            if (idx != 1) rep[2] = rep[1];
+            rep[1] = rep[0]; rep[0] = cur;
+        }
+    }
+    e->out[e->n++] = B2Z_PACK_SEQ(offBase, ll, e->pendLen);
+    e->prevEnd = e->pendPos + e->pendLen; e->pendValid = 0;
+}
+
+/* a match chosen by the parse at block-relative `pos` */
+static void emit_match(emitter_t *e, const uint8_t *blk, uint32_t pos, uint32_t len, uint32_t off) {
+    if (e->pendValid && pos == e->pendPos + e->pendLen && e->pendLastPiece == B2Z_CAP) {
+        int same = off == e->pendOff;
+        if (!same) same = count_match(blk + pos - e->pendOff, blk + pos, len) == len;
+        if (same) { e->pendLen += len; e->pendLastPiece = len; return; }
+    }
+    emit_flush(e);
+    e->pendPos = pos; e->pendLen = len; e->pendOff = off; e->pendLastPiece = len; e->pendValid = 1;
+}
+
+/* One frame: src[0..n).  Emits, per 128 KiB block, final sequences and the literal bytes.
  * The GPU runs this with one warp per frame: a step is B2Z_STEP (=32) consecutive positions,
  * lane i owning position base+i; "tables + lower lanes of the same step" (resolved with
  * __match_any_sync) give every position exactly the nearest previous occurrence of its hash
  * key, which is what the position-by-position loop below states. */
 static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_params *P,
-                                 b2zo_rawseq *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
+                                 uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
     const uint32_t HL = P->hashLogL, HS = P->hashLogS;
     const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
     const size_t W = (size_t)1 << P->windowLog;
     uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
     cand_t cand[B2Z_STEP];
-    size_t entry = 0;                                       /* greedy path entry point (frame-relative) */
+    size_t entry = 0;                                       /* path entry point (frame-relative) */
     size_t nblocks = (n + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
+    emitter_t em; memset(&em, 0, sizeof(em));
     for (size_t b = 0; b < nblocks; b++) { nseq[b] = 0; nlit[b] = 0; }
     for (size_t c0 = 0; c0 < n; c0 += B2Z_STEP) {
         size_t c1 = c0 + B2Z_STEP < n ? c0 + B2Z_STEP : n;
         size_t blk = c0 / ZF_BLOCK_MAX, blkStart = blk * ZF_BLOCK_MAX;
         size_t blkEnd = blkStart + ZF_BLOCK_MAX < n ? blkStart + ZF_BLOCK_MAX : n;
+        if (c0 == blkStart) { memset(&em, 0, sizeof(em)); em.out = seqs + blk * B2Z_MAXSEQ; }
         int search = entry < c1;                            /* whole step inside a match: insert only */
         for (size_t p = c0; p < c1; p++) {
             cand_t best = { 0, 0 };
@@ -120,20 +163,20 @@ static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_pa
             size_t p = entry;
             const cand_t *cd = &cand[p - c0];
             if (cd->len && !(p + 1 < c1 && cand[p + 1 - c0].len >= cd->len + B2Z_LAZY_GAIN)) {
-                b2zo_rawseq *s = &seqs[blk * B2Z_MAXSEQ + nseq[blk]++];
-                s->off = cd->off; s->poslen = (uint32_t)(p - blkStart) | ((uint32_t)(cd->len - 3) << 17);
+                emit_match(&em, src + blkStart, (uint32_t)(p - blkStart), cd->len, cd->off);
                 entry = p + cd->len;
             } else {
                 lits[blkStart + nlit[blk]++] = src[p];
                 entry = p + 1;
             }
         }
+        if (c1 == blkEnd) { emit_flush(&em); nseq[blk] = em.n; }
     }
     free(TL); free(TS);
 }
 
 int64_t b2zo_zstd_find_sequences(const void *srcv, size_t srcSize, const b2zo_enc_params *P,
-                                 b2zo_rawseq *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
+                                 uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
     const uint8_t *src = (const uint8_t *)srcv;
     size_t F = (size_t)1 << P->frameLog, blkBase = 0;
     for (size_t f0 = 0; f0 < srcSize; f0 += F) {
@@ -277,9 +320,10 @@ typedef struct { uint16_t code[256]; uint8_t len[256]; uint32_t maxBits; uint32_
  * tree is deeper than 11 the counts are halved (floor at 1) and the tree rebuilt -- always a
  * complete prefix code, hence representable as zstd weights. */
 static void huf_build(huf_ctable *h, const uint32_t *count0) {
-    uint32_t count[256]; memcpy(count, count0, sizeof(count));
+    uint32_t count[256];
     uint32_t order[256], n;
-    for (;;) {
+    for (uint32_t k = 0;; k++) {                            /* k = number of halvings: ceil(count / 2^k) */
+        for (uint32_t s = 0; s < 256; s++) count[s] = count0[s] ? (count0[s] + (1u << k) - 1) >> k : 0;
         n = 0;
         for (uint32_t s = 0; s < 256; s++) if (count[s]) order[n++] = s;
         /* stable sort by count ascending (symbols already ascending) */
@@ -303,7 +347,6 @@ static void huf_build(huf_ctable *h, const uint32_t *count0) {
             for (uint32_t s = 0; s < 256; s++) if (count[s]) h->maxSym = s;
             break;
         }
-        for (uint32_t s = 0; s < 256; s++) if (count[s]) count[s] = (count[s] + 1) >> 1;
     }
     /* canonical values in zstd order: weight w = maxBits+1-len; cells filled by ascending weight,
        symbols ascending inside a weight; value = firstCell >> (w-1) */
@@ -388,18 +431,21 @@ static size_t write_literals(uint8_t *dst, const uint8_t *lit, size_t n) {
         if (ts) {
             int four = n >= 256;
             size_t lh = n < 1024 ? 3 : (n < 16384 ? 4 : 5);
-            uint8_t *p = tmp + ts; size_t body;
-            if (!four) body = huf_encode_stream(p, lit, n, &h);
-            else {
-                size_t seg = (n + 3) / 4; uint8_t *q = p + 6; size_t s;
-                s = huf_encode_stream(q, lit, seg, &h); wr16(p, (uint32_t)s); q += s;
-                s = huf_encode_stream(q, lit + seg, seg, &h); wr16(p + 2, (uint32_t)s); q += s;
-                s = huf_encode_stream(q, lit + 2 * seg, seg, &h); wr16(p + 4, (uint32_t)s); q += s;
-                s = huf_encode_stream(q, lit + 3 * seg, n - 3 * seg, &h); q += s;
-                body = (size_t)(q - p);
-            }
-            size_t csize = ts + body;
-            if (lh + csize < rawHdr + n) {
+            uint64_t T = 0;                                 /* exact payload bits; decision on the byte bound */
+            for (uint32_t sy = 0; sy < 256; sy++) T += (uint64_t)count[sy] * h.len[sy];
+            size_t est = ts + (four ? 6 : 0) + (size_t)((T + 7) / 8) + (four ? 4 : 1);
+            if (lh + est < rawHdr + n) {
+                uint8_t *p = tmp + ts; size_t body;
+                if (!four) body = huf_encode_stream(p, lit, n, &h);
+                else {
+                    size_t seg = (n + 3) / 4; uint8_t *q = p + 6; size_t s;
+                    s = huf_encode_stream(q, lit, seg, &h); wr16(p, (uint32_t)s); q += s;
+                    s = huf_encode_stream(q, lit + seg, seg, &h); wr16(p + 2, (uint32_t)s); q += s;
+                    s = huf_encode_stream(q, lit + 2 * seg, seg, &h); wr16(p + 4, (uint32_t)s); q += s;
+                    s = huf_encode_stream(q, lit + 3 * seg, n - 3 * seg, &h); q += s;
+                    body = (size_t)(q - p);
+                }
+                size_t csize = ts + body;
                 uint32_t sf = !four ? 0 : (lh == 3 ? 1 : (lh == 4 ? 2 : 3));
                 if (lh == 3) wr24(dst, (uint32_t)(2 | (sf << 2) | (n << 4) | (csize << 14)));
                 else if (lh == 4) wr32(dst, (uint32_t)(2 | (sf << 2) | (n << 4) | (csize << 18)));
@@ -420,45 +466,6 @@ static size_t write_literals(uint8_t *dst, const uint8_t *lit, size_t n) {
 
 /* ======================================================================= sequences */
 typedef struct { uint32_t ll, ml, offBase; } fseq_t;
-
-/* merge capped pieces + repcode resolution (sequential per block; rep history unknown (=0) at
- * block start so blocks stay independent). Returns final sequence count. */
-static uint32_t merge_and_resolve(fseq_t *out, const b2zo_rawseq *raw, uint32_t nraw,
-                                  const uint8_t *frame, size_t blkStart) {
-    uint32_t n = 0, rep[3] = { 0, 0, 0 };
-    uint32_t prevEnd = 0, prevOff = 0, prevRawLen = 0, prevValid = 0;
-    /* pass 1: merge into (pos,len,off) kept in `out` as ll/ml/offBase(=raw offset) */
-    for (uint32_t i = 0; i < nraw; i++) {
-        uint32_t pos = raw[i].poslen & 0x1FFFF, len = (raw[i].poslen >> 17) + 3, off = raw[i].off;
-        if (prevValid && pos == prevEnd && prevRawLen == B2Z_CAP) {
-            int same = off == prevOff;
-            if (!same) {
-                const uint8_t *p = frame + blkStart + pos;
-                same = count_match(p - prevOff, p, len) == len;
-            }
-            if (same) { out[n - 1].ml += len; prevEnd += len; prevRawLen = len; continue; }
-        }
-        out[n].ll = pos - prevEnd; out[n].ml = len; out[n].offBase = off; n++;
-        prevEnd = pos + len; prevOff = off; prevRawLen = len; prevValid = 1;
-    }
-    /* pass 2: repcodes */
-    for (uint32_t i = 0; i < n; i++) {
-        uint32_t off = out[i].offBase, ll0 = out[i].ll == 0, code = 0;
-        if (!ll0) { if (off == rep[0]) code = 1; else if (off == rep[1]) code = 2; else if (off == rep[2]) code = 3; }
-        else { if (off == rep[1]) code = 1; else if (off == rep[2]) code = 2; else if (rep[0] > 1 && off == rep[0] - 1) code = 3; }
-        if (code == 0) { out[i].offBase = off + 3; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-        else {
-            out[i].offBase = code;
-            uint32_t idx = code - 1 + ll0;                  /* 0..3 */
-            if (idx != 0) {
-                uint32_t cur = idx == 3 ? rep[0] - 1 : rep[idx];
-                if (idx != 1) rep[2] = rep[1];
-                rep[1] = rep[0]; rep[0] = cur;
-            }
-        }
-    }
-    return n;
-}
 
 /* choose table mode for one symbol type and serialise its description */
 typedef struct { fse_ctable ct; uint32_t mode; } seq_table_choice;
@@ -490,7 +497,8 @@ static size_t choose_seq_table(seq_table_choice *ch, uint8_t *dst, const uint8_t
     fse_build_ctable(&ch->ct, norm, maxSym, log); ch->mode = 2; memcpy(dst, hdr, hs); return hs;
 }
 
-static size_t write_sequences(uint8_t *dst, const fseq_t *seq, uint32_t nbSeq) {
+/* returns section size, or (size_t)-1 when litSize + the section's size upper bound exceeds B2Z_BODY_CAP */
+static size_t write_sequences(uint8_t *dst, const fseq_t *seq, uint32_t nbSeq, size_t litSize) {
     uint8_t *op = dst;
     if (nbSeq < 128) *op++ = (uint8_t)nbSeq;
     else if (nbSeq < 0x7F00) { *op++ = (uint8_t)((nbSeq >> 8) + 128); *op++ = (uint8_t)nbSeq; }
@@ -506,6 +514,11 @@ static size_t write_sequences(uint8_t *dst, const fseq_t *seq, uint32_t nbSeq) {
     op += choose_seq_table(&O, op, ofc, nbSeq, ZF_MAXOFF, ZF_OF_FSELOG, ZF_OF_defaultNorm, 28, ZF_OF_DEFLOG);
     op += choose_seq_table(&M, op, mlc, nbSeq, ZF_MAXML, ZF_ML_FSELOG, ZF_ML_defaultNorm, 52, ZF_ML_DEFLOG);
     *modes = (uint8_t)((L.mode << 6) | (O.mode << 4) | (M.mode << 2));
+    {
+        uint64_t upper = (uint64_t)nbSeq * (L.ct.log + O.ct.log + M.ct.log) + 1;
+        for (uint32_t k = 0; k < nbSeq; k++) upper += ZF_LL_bits[llc[k]] + ZF_ML_bits[mlc[k]] + ofc[k];
+        if (litSize + (size_t)(op - dst) + (size_t)((upper + 7) / 8) > B2Z_BODY_CAP) { free(llc); return (size_t)-1; }
+    }
     bitw_t b; bw_init(&b, op);
     uint32_t i = nbSeq - 1, nb, bits;
     uint32_t sM = fse_init_state(&M.ct, mlc[i]), sO = fse_init_state(&O.ct, ofc[i]), sL = fse_init_state(&L.ct, llc[i]);
@@ -528,18 +541,18 @@ static size_t write_sequences(uint8_t *dst, const fseq_t *seq, uint32_t nbSeq) {
 
 /* One block: returns bytes written including the 3-byte header. */
 static size_t compress_block(uint8_t *dst, const uint8_t *frame, size_t blkStart, size_t blkSize, int last,
-                             const b2zo_rawseq *raw, uint32_t nraw, const uint8_t *lits, uint32_t nlit) {
-    fseq_t *seq = (fseq_t *)malloc(sizeof(fseq_t) * (nraw + 1));
-    uint32_t nbSeq = merge_and_resolve(seq, raw, nraw, frame, blkStart);
+                             const uint64_t *packed, uint32_t nbSeq, const uint8_t *lits, uint32_t nlit) {
+    fseq_t *seq = (fseq_t *)malloc(sizeof(fseq_t) * (nbSeq + 1));
+    for (uint32_t i = 0; i < nbSeq; i++) { seq[i].offBase = B2Z_SEQ_OFFBASE(packed[i]); seq[i].ll = B2Z_SEQ_LL(packed[i]); seq[i].ml = B2Z_SEQ_ML(packed[i]); }
     const uint8_t *src = frame + blkStart;
     size_t out;
     if (blkSize > 1 && nbSeq == 1 && nlit == 1 && seq[0].ll == 1 && seq[0].ml == blkSize - 1 && seq[0].offBase == 1 + 3) {
         wr24(dst, (uint32_t)(last | (1 << 1) | (blkSize << 3))); dst[3] = src[0]; out = 4;   /* RLE block */
     } else {
-        uint8_t *body = (uint8_t *)malloc(blkSize + blkSize / 2 + 1024);
+        uint8_t *body = (uint8_t *)malloc(B2Z_BODY_CAP + 1024);
         size_t ls = write_literals(body, lits, nlit);
-        size_t ss = write_sequences(body + ls, seq, nbSeq);
-        if (ls + ss < blkSize) { wr24(dst, (uint32_t)(last | (2 << 1) | ((ls + ss) << 3))); memcpy(dst + 3, body, ls + ss); out = 3 + ls + ss; }
+        size_t ss = write_sequences(body + ls, seq, nbSeq, ls);
+        if (ss != (size_t)-1 && ls + ss < blkSize) { wr24(dst, (uint32_t)(last | (2 << 1) | ((ls + ss) << 3))); memcpy(dst + 3, body, ls + ss); out = 3 + ls + ss; }
         else { wr24(dst, (uint32_t)(last | (blkSize << 3))); memcpy(dst + 3, src, blkSize); out = 3 + blkSize; }
         free(body);
     }
@@ -562,7 +575,7 @@ int64_t b2zo_zstd_compress(void *dstv, size_t dstCap, const void *srcv, size_t s
     if (dstCap < b2zo_zstd_compress_bound(srcSize, P)) return -2;
     size_t F = (size_t)1 << P->frameLog;
     size_t nblkMax = (F + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
-    b2zo_rawseq *seqs = (b2zo_rawseq *)malloc(sizeof(b2zo_rawseq) * B2Z_MAXSEQ * nblkMax);
+    uint64_t *seqs = (uint64_t *)malloc(sizeof(uint64_t) * B2Z_MAXSEQ * nblkMax);
     uint32_t *nseq = (uint32_t *)malloc(4 * nblkMax * 2), *nlit = nseq + nblkMax;
     uint8_t *lits = (uint8_t *)malloc(F);
     size_t f0 = 0;

@@ -1,0 +1,145 @@
+"""Test-side access to the checker libraries: oracle/liboracle.so (our C restatement) and
+oracle/_ref/libref_zstd.so (the unmodified reference, compiled by oracle/Makefile)."""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAXSEQ = 32768
+
+
+class EncParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "reserved", "flags")]
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        O = ctypes.CDLL(path)
+        O.b2zo_zstd_decompress.restype = ctypes.c_int64
+        O.b2zo_zstd_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        O.b2zo_zstd_compress.restype = ctypes.c_int64
+        O.b2zo_zstd_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(EncParams)]
+        O.b2zo_zstd_compress_bound.restype = ctypes.c_size_t
+        O.b2zo_zstd_compress_bound.argtypes = [ctypes.c_size_t, ctypes.POINTER(EncParams)]
+        O.b2zo_zstd_find_sequences.restype = ctypes.c_int64
+        O.b2zo_zstd_find_sequences.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(EncParams)] + [ctypes.c_void_p] * 4
+        O.b2zo_xxh64.restype = ctypes.c_uint64
+        O.b2zo_xxh64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]
+        _oracle = O
+    return _oracle
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_zstd.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        Z = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_zstd.so"))
+        Z.ZSTD_compressBound.restype = ctypes.c_size_t; Z.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+        Z.ZSTD_createCCtx.restype = ctypes.c_void_p
+        Z.ZSTD_freeCCtx.argtypes = [ctypes.c_void_p]
+        Z.ZSTD_CCtx_setParameter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]; Z.ZSTD_CCtx_setParameter.restype = ctypes.c_size_t
+        Z.ZSTD_compress2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]; Z.ZSTD_compress2.restype = ctypes.c_size_t
+        Z.ZSTD_decompress.restype = ctypes.c_size_t; Z.ZSTD_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        Z.ZSTD_isError.argtypes = [ctypes.c_size_t]
+        Z.ZSTD_getErrorName.restype = ctypes.c_char_p; Z.ZSTD_getErrorName.argtypes = [ctypes.c_size_t]
+        _ref = Z
+    return _ref
+
+
+def _np(data):
+    return np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+
+
+def enc_params(**kw):
+    p = EncParams()
+    oracle().b2zo_enc_default_params(ctypes.byref(p), 3)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def oracle_compress(data, **kw) -> bytes:
+    p = enc_params(**kw)
+    src = _np(data)
+    out = np.empty(oracle().b2zo_zstd_compress_bound(len(data), ctypes.byref(p)), dtype=np.uint8)
+    r = oracle().b2zo_zstd_compress(out.ctypes.data, out.size, src.ctypes.data, len(data), ctypes.byref(p))
+    assert r > 0, r
+    return out[:r].tobytes()
+
+
+def oracle_find_sequences(data, **kw):
+    p = enc_params(**kw)
+    src = _np(data); n = len(data)
+    nblk = (n + 131071) // 131072
+    seqs = np.zeros(nblk * MAXSEQ, dtype=np.uint64)
+    nseq = np.zeros(nblk, dtype=np.uint32); nlit = np.zeros(nblk, dtype=np.uint32)
+    lits = np.zeros(max(n, 1), dtype=np.uint8)
+    r = oracle().b2zo_zstd_find_sequences(src.ctypes.data, n, ctypes.byref(p), seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
+    assert r == nblk
+    return seqs, nseq, lits[:n], nlit
+
+
+def oracle_decompress(comp, n) -> bytes:
+    dst = np.empty(n + 1, dtype=np.uint8); src = _np(comp)
+    r = oracle().b2zo_zstd_decompress(dst.ctypes.data, n, src.ctypes.data, len(comp))
+    if r < 0:
+        raise ValueError(f"oracle decoder error {r}")
+    return dst[:r].tobytes()
+
+
+def ref_compress(data, level=3, checksum=0, **kw) -> bytes:
+    Z = ref()
+    c = Z.ZSTD_createCCtx()
+    Z.ZSTD_CCtx_setParameter(c, 100, level); Z.ZSTD_CCtx_setParameter(c, 201, checksum)
+    ids = dict(windowLog=101, hashLog=102, chainLog=103, searchLog=104, minMatch=105, targetLength=106, strategy=107,
+               nbWorkers=400, enableLongDistanceMatching=160, contentSizeFlag=200)
+    for k, v in kw.items():
+        Z.ZSTD_CCtx_setParameter(c, ids[k], v)
+    src = _np(data)
+    out = np.empty(Z.ZSTD_compressBound(len(data)), dtype=np.uint8)
+    r = Z.ZSTD_compress2(c, out.ctypes.data, out.size, src.ctypes.data, len(data))
+    Z.ZSTD_freeCCtx(c)
+    assert not Z.ZSTD_isError(r), Z.ZSTD_getErrorName(r)
+    return out[:r].tobytes()
+
+
+def ref_decompress(comp, n) -> bytes:
+    Z = ref()
+    dst = np.empty(n + 1, dtype=np.uint8); src = _np(comp)
+    r = Z.ZSTD_decompress(dst.ctypes.data, n + 1, src.ctypes.data, len(comp))
+    if Z.ZSTD_isError(r):
+        raise ValueError(Z.ZSTD_getErrorName(r).decode())
+    return dst[:r].tobytes()
+
+
+def sample_inputs(pkg, big=False):
+    """name -> bytes: the seeded inputs shared by the CPU and GPU tests (edge cases included)."""
+    g2 = pkg.corpus.g2
+    cls = pkg.corpus.entropy_class
+    d = {
+        "empty": b"", "one": b"a", "tiny": b"hello hello hello hello", "seven": b"1234567", "eight": b"12345678",
+        "g2_100k": g2(100_000).tobytes(),
+        "g2_128k": g2(131072).tobytes(),
+        "g2_128k+1": g2(131073).tobytes(),
+        "g2_1m": g2(1 << 20).tobytes(),
+        "noise": cls(1, 300_000).tobytes(), "skew": cls(2, 700_000).tobytes(), "tile": cls(3, 900_000).tobytes(),
+        "zeros": bytes(500_000), "ones_33": b"\x01" * 33,
+        "payload": b"TEST\n" + b" " * 999990 + b"\nEND.",       # the reference's regression payload (tests/regression.test:181)
+        "mixed": g2(200_000).tobytes() + bytes(150_000) + cls(1, 100_000).tobytes() + cls(3, 250_000).tobytes(),
+    }
+    if big:
+        d["g2_9m"] = g2(9 * (1 << 20) + 4321).tobytes()           # 3 frames, ragged tail
+    return d

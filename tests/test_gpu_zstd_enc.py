@@ -1,0 +1,91 @@
+"""GPU parity tests of the zstd encoder path (through the C ABI in include/b200z.h).
+
+Parity bar (north_star): frames are format-valid and the reference's own decoder
+(oracle/_ref, built from /root/reference/C/zstd) round-trips them to identical bytes; in
+addition the CUDA path must equal the oracle restatement byte for byte (integer algorithm).
+"""
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def inputs(pkg):
+    return helpers.sample_inputs(pkg, big=True)
+
+
+def test_stage_m_matches_oracle(pkg, codec, inputs):
+    """stage M taps (final sequences + literals per block) == oracle find_sequences."""
+    for name in ("g2_1m", "tile", "zeros", "mixed", "g2_128k+1", "skew", "g2_9m"):
+        data = inputs[name]
+        seqs, nseq, lits, nlit = codec.stage_m(data)
+        oseqs, onseq, olits, onlit = helpers.oracle_find_sequences(data)
+        assert np.array_equal(nseq, onseq), (name, nseq[:8], onseq[:8])
+        assert np.array_equal(nlit, onlit), (name, nlit[:8], onlit[:8])
+        for b in range(len(nseq)):
+            s = slice(b * helpers.MAXSEQ, b * helpers.MAXSEQ + int(nseq[b]))
+            if not np.array_equal(seqs[s], oseqs[s]):
+                i = int(np.nonzero(seqs[s] != oseqs[s])[0][0])
+                raise AssertionError(f"{name}: block {b} seq {i}: gpu {int(seqs[s][i]):#x} oracle {int(oseqs[s][i]):#x}")
+            l = slice(b * 131072, b * 131072 + int(nlit[b]))
+            assert np.array_equal(lits[l], olits[l]), (name, b)
+
+
+def test_frames_equal_oracle_and_roundtrip(pkg, codec, inputs):
+    for name, data in inputs.items():
+        comp = codec.compress(data)
+        want = helpers.oracle_compress(data)
+        if comp != want:
+            n = min(len(comp), len(want))
+            i = next((k for k in range(n) if comp[k] != want[k]), n)
+            raise AssertionError(f"{name}: frame bytes differ from oracle at {i} (sizes {len(comp)} vs {len(want)})")
+        assert helpers.oracle_decompress(comp, len(data)) == data, name
+        if helpers.ref_available():
+            assert helpers.ref_decompress(comp, len(data)) == data, name
+
+
+def test_params_and_hints(pkg, inputs):
+    """non-default geometry and the skippable size hints stay byte-identical to the oracle and decodable."""
+    data = inputs["g2_9m"][: 3 * (1 << 20) + 77]
+    c = pkg.Codec(0, frame_log=20, hash_log_l=15, hash_log_s=14, flags=1)
+    comp = c.compress(data)
+    assert comp == helpers.oracle_compress(data, frameLog=20, windowLog=20, hashLogL=15, hashLogS=14, flags=1)
+    assert comp[:4] == b"\x50\x2a\x4d\x18"
+    if helpers.ref_available():
+        assert helpers.ref_decompress(comp, len(data)) == data
+    c.close()
+
+
+def test_ratio_vs_reference_level3(pkg, codec):
+    """ratio within 1 % of the reference's level 3 on the BASELINE cfg2 text shape (16 MiB sample)."""
+    if not helpers.ref_available():
+        pytest.skip("oracle/_ref not built")
+    data = pkg.corpus.g2(16 << 20).tobytes()
+    ours = len(codec.compress(data)); ref = len(helpers.ref_compress(data, 3))
+    assert ours <= ref * 1.01, (ours, ref)
+
+
+def test_device_resident_and_stats(pkg, codec):
+    import torch
+    data = pkg.corpus.g2(8 << 20)
+    src = torch.from_numpy(data).cuda()
+    dst = torch.empty(codec.compress_bound(src.numel()), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    codec.reset_stats()
+    n = codec.compress_device(src.data_ptr(), src.numel(), dst.data_ptr(), dst.numel())
+    comp = dst[:n].cpu().numpy().tobytes()
+    assert comp == helpers.oracle_compress(data.tobytes())
+    assert codec.stat(6) >= 4 and codec.stat(1) > 0 and codec.stat(2) > 0
+
+
+def test_bad_arguments(pkg, codec):
+    with pytest.raises(pkg.B200zError):
+        codec.set("frame_log", 40)
+    import ctypes
+    sz = ctypes.c_size_t()
+    buf = np.zeros(64, dtype=np.uint8)
+    rc = pkg.load_library().b200z_zstd_compress_host(codec.h, buf.ctypes.data, 64, buf.ctypes.data, 8, ctypes.byref(sz))
+    assert rc == -4
