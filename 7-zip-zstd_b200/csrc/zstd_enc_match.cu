@@ -45,18 +45,21 @@ __device__ __forceinline__ StepA stage_a(const uint64_t* __restrict__ w, uint32_
     uint32_t* ss = TS + (keyS >> tagBits);
     uint32_t eL = 0, eS = 0;
     if (hashable) { eL = __ldcg(sl); eS = __ldcg(ss); }
-    // same-step resolution: lanes with the same (bucket|tag) key
-    const uint32_t uniq = 0x80000000u | lane;                // keys are < 2^26
-    const uint32_t mL = __match_any_sync(B2Z_FULL, hashable ? keyL : uniq);
-    const uint32_t mS = __match_any_sync(B2Z_FULL, hashable ? keyS : uniq);
+    // same-step resolution: the latest lower lane that hits the same BUCKET owns the slot (it would
+    // have overwritten it in sequential order); it is a candidate only if its tag matches too
+    const uint32_t uniq = 0x80000000u | lane;                // buckets are < 2^22
+    const uint32_t mL = __match_any_sync(B2Z_FULL, hashable ? (keyL >> tagBits) : uniq);
+    const uint32_t mS = __match_any_sync(B2Z_FULL, hashable ? (keyS >> tagBits) : uniq);
+    const uint32_t lt = lanemask_lt();
+    const uint32_t lowL = mL & lt, lowS = mS & lt;
+    const uint32_t jL = lowL ? highbit32(lowL) : 0u, jS = lowS ? highbit32(lowS) : 0u;
+    const uint32_t keyLj = __shfl_sync(B2Z_FULL, keyL, jL), keySj = __shfl_sync(B2Z_FULL, keyS, jS);
     if (hashable) {
-        const uint32_t lt = lanemask_lt();
-        const uint32_t lowL = mL & lt, lowS = mS & lt;
-        if (lowL) r.candL = base + highbit32(lowL) + 1u;
+        if (lowL) { if (keyLj == keyL) r.candL = base + jL + 1u; }
         else if (eL && (eL & tagMask) == (keyL & tagMask)) r.candL = eL >> tagBits;
-        if (lowS) r.candS = base + highbit32(lowS) + 1u;
+        if (lowS) { if (keySj == keyS) r.candS = base + jS + 1u; }
         else if (eS && (eS & tagMask) == (keyS & tagMask)) r.candS = eS >> tagBits;
-        // insert: the highest lane of each key group holds the latest position
+        // insert: the highest lane of each bucket group holds the latest position
         if ((mL >> lane) == 1u) __stcg(sl, ((p + 1u) << tagBits) | (keyL & tagMask));
         if ((mS >> lane) == 1u) __stcg(ss, ((p + 1u) << tagBits) | (keyS & tagMask));
     }
