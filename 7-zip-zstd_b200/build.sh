@@ -10,11 +10,13 @@ objs=""
 for f in csrc/*.cu; do
   o=build/$(basename "${f%.cu}").o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find csrc ../include -name '*.h' -newer "$o" -o -name '*.cuh' -newer "$o")" ]; then
+    rm -f "$o"
     $NVCC $FLAGS -c "$f" -o "$o" &
+    pids="$pids $!"
   fi
   objs="$objs $o"
 done
-wait
+for p in $pids; do wait $p || { echo "build.sh: compilation FAILED" >&2; exit 1; }; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libb200z.so $objs -lcudart
 gcc -O2 -shared -fPIC -pthread -o corpus/libb200z_corpus.so corpus/g2gen.c
 echo "built $(pwd)/libb200z.so"

@@ -1,0 +1,44 @@
+// b2z_ctx.h -- the context object behind the C ABI (internal to libb200z.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "../../include/b200z.h"
+#include "b2z_kernels.h"
+#include "b2z_dec.h"
+
+struct Arena {                       // grow-only device buffer
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = n; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct b200z_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    b2z::EncGeom geom{};
+    int level = 3;
+    uint32_t batchLog = 32;
+    uint32_t smCount = 148;
+    Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut;
+    Arena decScratch[8];
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double stat[16] = {0};
+    char err[256] = {0};
+};
+
+static inline int fail(b200z_ctx* c, int code, const char* fmt, const char* detail = "") {
+    if (c) snprintf(c->err, sizeof(c->err), fmt, detail);
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError(); \
+    return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? B200Z_E_MEMORY : B200Z_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } } while (0)
+

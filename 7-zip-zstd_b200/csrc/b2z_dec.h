@@ -1,4 +1,57 @@
-// b2z_dec.h -- decoder-side launchers (internal to libb200z.so).
+// b2z_dec.h -- decoder-side structures and launchers (internal to libb200z.so).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+namespace b2z {
+
+#define B2Z_DEC_MAXSEQ   65536u      // sequences per block (format max: 128 KiB / 3 < 43691)
+#define B2Z_DEC_WARPS    2           // stage D1: warps (= blocks) per CTA
+
+// error bits (per block / global)
+#define B2Z_DERR_CORRUPT      1u
+#define B2Z_DERR_UNSUPPORTED  2u
+#define B2Z_DERR_TABLE_FULL   4u
+#define B2Z_DERR_DSTSIZE      8u
+
+struct DecFrame {
+    uint64_t srcOff;        // first byte of the frame header
+    uint64_t dstOff;        // output offset (filled by the layout kernel)
+    uint64_t contentSize;   // ~0 if not declared
+    uint64_t windowSize;
+    uint64_t regen;         // sum of block sizes (filled by the layout kernel)
+    uint32_t firstBlock, nBlocks;
+    uint32_t checksum;      // 1 if a 4-byte content checksum follows the last block
+    uint32_t pad;
+};
+
+struct DecBlock {
+    uint64_t srcOff;        // first byte of block content (after the 3-byte header)
+    uint32_t cSize;         // content bytes (RLE: 1)
+    uint32_t rawSize;       // regenerated size for raw/RLE blocks
+    uint32_t type;          // 0 raw, 1 RLE, 2 compressed
+    uint32_t frame;
+    int32_t  hufSrc;        // block whose literals section defines the Huffman table (-1: none needed)
+    int32_t  tblSrc[3];     // LL, OF, ML: block whose sequences section defines the table
+    uint32_t regen;         // regenerated size            (stage D1)
+    uint32_t nbSeq;         // sequences decoded           (stage D1)
+    uint32_t litSize;       // literals decoded            (stage D1)
+    uint32_t status;        // B2Z_DERR_* bits             (stage D1 / D3)
+};
+
+struct DecCounts { uint32_t nFrames, nBlocks, status, pad; uint64_t srcUsed; };
+
+// stage D0: frame/block walk (single thread; sequential by format) -> tables + counts
+void launch_zstd_dec_prepass(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap,
+                             DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st);
+// stage D1: one warp per compressed block: literals (Huffman) + sequences (FSE) into scratch
+void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks,
+                             uint8_t* lits, uint64_t* seqs, cudaStream_t st);
+// stage D2: per-frame sizes and output offsets
+void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* blocks, uint64_t dstCap,
+                            DecCounts* counts, uint64_t* total, cudaStream_t st);
+// stage D3: one warp per frame: execute sequences block after block
+void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks,
+                          const uint8_t* lits, const uint64_t* seqs, uint8_t* dst, DecCounts* counts, cudaStream_t st);
+
+}  // namespace b2z

@@ -1,0 +1,605 @@
+// zstd_dec.cu -- Zstandard decoder kernels (sm_100a), bit-exact for any valid frame whose
+// window is <= 2^29 and that needs no dictionary.
+//
+//   D0 prepass  (1 thread)          walk frame and block headers (sequential by format), record
+//                                   per block where its entropy tables come from (treeless
+//                                   literals / repeat-mode FSE tables chain back to an earlier block)
+//   D1 entropy  (1 warp / block)    Huffman-decode the literals (4 streams -> 4 lanes) and FSE-decode
+//                                   the sequences (one backward bitstream -> lane 0) into scratch
+//   D2 layout   (1 thread / frame)  block sizes -> frame sizes -> output offsets
+//   D3 execute  (1 warp / frame)    literal + match copies, block after block (matches may reach
+//                                   into earlier blocks of the frame), repcode history carried
+//
+// Replaces (reference, /root/reference/C/zstd/): zstd_decompress.c:702,1275,2086 (frame/stream
+// loop), zstd_decompress_block.c:63 (block header), :134-340 (literals), huf_decompress.c:385,897,
+// entropy_common.c:42,242 (NCount / Huffman stats), zstd_decompress_block.c:485,647,695 (FSE
+// tables + sequence header), :1229 (ZSTD_decodeSequence), :1001 (ZSTD_execSequence).
+// The sequential statement is oracle/zstd_dec_oracle.c; outputs must be identical.
+#include "b2z_device.cuh"
+#include "b2z_dec.h"
+
+namespace b2z {
+
+// ---------------------------------------------------------------- format constants
+__device__ const uint32_t k_LL_base[36] = { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,
+    16,18,20,22,24,28,32,40,48,64,0x80,0x100,0x200,0x400,0x800,0x1000,0x2000,0x4000,0x8000,0x10000 };
+__device__ const uint8_t k_LL_bits[36] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,
+    1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16 };
+__device__ const uint32_t k_ML_base[53] = { 3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,
+    19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,
+    35,37,39,41,43,47,51,59,67,83,99,0x83,0x103,0x203,0x403,0x803,0x1003,0x2003,0x4003,0x8003,0x10003 };
+__device__ const uint8_t k_ML_bits[53] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,
+    0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,
+    1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16 };
+__device__ const int16_t k_LL_defNorm[36] = { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,
+    2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 };
+__device__ const int16_t k_ML_defNorm[53] = { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,
+    1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,
+    1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 };
+__device__ const int16_t k_OF_defNorm[29] = { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,
+    1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 };
+
+// ---------------------------------------------------------------- guarded byte access to the source
+struct Src {
+    const uint64_t* w; uint64_t nWords; uint64_t size;      // 8-byte aligned buffer, size bytes
+    __device__ __forceinline__ uint64_t word(uint64_t i) const { return i < nWords ? __ldg(w + i) : 0ull; }
+    __device__ __forceinline__ uint64_t le64(uint64_t off) const {       // unaligned 8 bytes, zero past the end
+        const uint64_t i = off >> 3; const uint32_t s = (uint32_t)(off & 7u) * 8u;
+        const uint64_t a = word(i), b = s ? word(i + 1) : 0ull;
+        return funnel64(a, b, s);
+    }
+    __device__ __forceinline__ uint32_t u8(uint64_t off) const { return (uint32_t)(word(off >> 3) >> ((off & 7u) * 8u)) & 255u; }
+    __device__ __forceinline__ uint32_t le24(uint64_t off) const { return (uint32_t)le64(off) & 0xFFFFFFu; }
+    __device__ __forceinline__ uint32_t le32(uint64_t off) const { return (uint32_t)le64(off); }
+};
+
+// ---------------------------------------------------------------- literals / sequences header parsing
+struct LitHdr { uint32_t type, regen, csize, hdr, streams; bool ok; };
+__device__ LitHdr parse_lit_hdr(const Src& S, uint64_t off, uint32_t blockSize) {
+    LitHdr h; h.ok = false; h.csize = 0; h.streams = 1; h.regen = 0; h.hdr = 0; h.type = 0;
+    if (blockSize < 1) return h;
+    const uint64_t v = S.le64(off);
+    const uint32_t b0 = (uint32_t)v & 255u;
+    h.type = b0 & 3u; const uint32_t sf = (b0 >> 2) & 3u;
+    if (h.type <= 1) {
+        if (sf == 0 || sf == 2) { h.regen = b0 >> 3; h.hdr = 1; }
+        else if (sf == 1) { h.regen = ((uint32_t)v >> 4) & 0xFFFu; h.hdr = 2; }
+        else { h.regen = ((uint32_t)v >> 4) & 0xFFFFFu; h.hdr = 3; }
+        h.csize = h.type == 0 ? h.regen : 1u;
+    } else {
+        if (blockSize < 5) return h;
+        if (sf <= 1) { h.regen = ((uint32_t)v >> 4) & 0x3FFu; h.csize = ((uint32_t)v >> 14) & 0x3FFu; h.hdr = 3; h.streams = sf == 0 ? 1u : 4u; }
+        else if (sf == 2) { h.regen = ((uint32_t)v >> 4) & 0x3FFFu; h.csize = (uint32_t)v >> 18; h.hdr = 4; h.streams = 4; }
+        else { h.regen = (uint32_t)(v >> 4) & 0x3FFFFu; h.csize = (uint32_t)(v >> 22) & 0x3FFFFu; h.hdr = 5; h.streams = 4; }
+    }
+    if (h.regen > 131072u || (uint64_t)h.hdr + h.csize > blockSize) return h;
+    h.ok = true; return h;
+}
+
+struct SeqHdr { uint32_t nbSeq, modes, hdr; bool ok; };   // hdr = bytes up to and including the modes byte
+__device__ SeqHdr parse_seq_hdr(const Src& S, uint64_t off, uint32_t avail) {
+    SeqHdr h; h.ok = false; h.nbSeq = 0; h.modes = 0; h.hdr = 0;
+    if (avail < 1) return h;
+    const uint32_t v = S.le32(off);
+    uint32_t n = v & 255u, used = 1;
+    if (n >= 128) {
+        if (n == 255) { if (avail < 3) return h; n = ((v >> 8) & 0xFFFFu) + 0x7F00u; used = 3; }
+        else { if (avail < 2) return h; n = ((n - 128u) << 8) + ((v >> 8) & 255u); used = 2; }
+    }
+    h.nbSeq = n;
+    if (n == 0) { h.hdr = used; h.ok = (used == avail); return h; }
+    if (avail < used + 1) return h;
+    h.modes = S.u8(off + used); h.hdr = used + 1;
+    h.ok = (h.modes & 3u) == 0;
+    return h;
+}
+
+// ---------------------------------------------------------------- D0: prepass
+__global__ void zstd_dec_prepass_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap,
+                                        DecBlock* blocks, uint32_t blockCap, DecCounts* counts) {
+    if (threadIdx.x || blockIdx.x) return;
+    Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
+    uint64_t ip = 0; uint32_t nf = 0, nb = 0, status = 0;
+    while (ip < srcSize && !status) {
+        if (srcSize - ip < 4) { status = B2Z_DERR_CORRUPT; break; }
+        const uint32_t magic = S.le32(ip);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+            if (srcSize - ip < 8) { status = B2Z_DERR_CORRUPT; break; }
+            const uint64_t sz = S.le32(ip + 4);
+            if (srcSize - ip < 8 + sz) { status = B2Z_DERR_CORRUPT; break; }
+            ip += 8 + sz; continue;
+        }
+        if (magic != 0xFD2FB528u) { status = B2Z_DERR_CORRUPT; break; }
+        if (srcSize - ip < 6) { status = B2Z_DERR_CORRUPT; break; }
+        if (nf >= frameCap) { status = B2Z_DERR_TABLE_FULL; break; }
+        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.regen = 0; fr.firstBlock = nb; fr.pad = 0;
+        const uint32_t fhd = S.u8(ip + 4); ip += 5;
+        const uint32_t fcsFlag = fhd >> 6, single = (fhd >> 5) & 1u, didFlag = fhd & 3u;
+        fr.checksum = (fhd >> 2) & 1u;
+        if (fhd & 8u) { status = B2Z_DERR_CORRUPT; break; }
+        uint64_t windowSize = 0;
+        if (!single) {
+            const uint32_t wd = S.u8(ip++); const uint32_t wl = 10u + (wd >> 3);
+            if (wl > 31) { status = B2Z_DERR_CORRUPT; break; }
+            windowSize = (1ull << wl) + ((1ull << wl) >> 3) * (wd & 7u);
+        }
+        const uint32_t didBytes = didFlag == 3 ? 4u : didFlag;
+        uint32_t did = 0; for (uint32_t i = 0; i < didBytes; i++) did |= S.u8(ip + i) << (8 * i);
+        ip += didBytes;
+        if (did) { status = B2Z_DERR_UNSUPPORTED; break; }
+        const uint32_t fcsBytes = fcsFlag == 0 ? single : (fcsFlag == 1 ? 2u : (fcsFlag == 2 ? 4u : 8u));
+        if (srcSize - ip < fcsBytes) { status = B2Z_DERR_CORRUPT; break; }
+        uint64_t fcs = ~0ull;
+        if (fcsBytes) { fcs = 0; for (uint32_t i = 0; i < fcsBytes; i++) fcs |= (uint64_t)S.u8(ip + i) << (8 * i); if (fcsBytes == 2) fcs += 256; }
+        ip += fcsBytes;
+        if (single) windowSize = fcs;
+        if (windowSize > (1ull << 30) - 16) { status = B2Z_DERR_UNSUPPORTED; break; }
+        fr.contentSize = fcs; fr.windowSize = windowSize;
+        int32_t lastHuf = -1, lastTbl[3] = { -1, -1, -1 };
+        for (;;) {
+            if (srcSize - ip < 3) { status = B2Z_DERR_CORRUPT; break; }
+            if (nb >= blockCap) { status = B2Z_DERR_TABLE_FULL; break; }
+            const uint32_t bh = S.le24(ip); ip += 3;
+            const uint32_t last = bh & 1u, type = (bh >> 1) & 3u, bsize = bh >> 3;
+            if (type == 3 || bsize > 131072u) { status = B2Z_DERR_CORRUPT; break; }
+            DecBlock b; b.srcOff = ip; b.type = type; b.frame = nf; b.hufSrc = -1; b.tblSrc[0] = b.tblSrc[1] = b.tblSrc[2] = -1;
+            b.regen = 0; b.nbSeq = 0; b.litSize = 0; b.status = 0; b.rawSize = 0;
+            b.cSize = type == 1 ? 1u : bsize;
+            if (srcSize - ip < b.cSize) { status = B2Z_DERR_CORRUPT; break; }
+            if (type != 2) { b.rawSize = bsize; b.regen = bsize; }
+            else {
+                const LitHdr lh = parse_lit_hdr(S, ip, bsize);
+                if (!lh.ok) { status = B2Z_DERR_CORRUPT; break; }
+                if (lh.type == 2) { b.hufSrc = (int32_t)nb; lastHuf = (int32_t)nb; }
+                else if (lh.type == 3) { if (lastHuf < 0) { status = B2Z_DERR_CORRUPT; break; } b.hufSrc = lastHuf; }
+                const uint32_t so = lh.hdr + lh.csize;
+                const SeqHdr sh = parse_seq_hdr(S, ip + so, bsize - so);
+                if (!sh.ok) { status = B2Z_DERR_CORRUPT; break; }
+                if (sh.nbSeq) {
+                    for (int t = 0; t < 3; t++) {
+                        const uint32_t mode = (sh.modes >> (6 - 2 * t)) & 3u;      // LL, OF, ML
+                        if (mode == 3) { if (lastTbl[t] < 0) { status = B2Z_DERR_CORRUPT; break; } b.tblSrc[t] = lastTbl[t]; }
+                        else { b.tblSrc[t] = (int32_t)nb; lastTbl[t] = (int32_t)nb; }
+                    }
+                    if (status) break;
+                }
+            }
+            blocks[nb++] = b;
+            ip += b.cSize;
+            if (last) break;
+        }
+        if (status) break;
+        fr.nBlocks = nb - fr.firstBlock;
+        if (fr.checksum) { if (srcSize - ip < 4) { status = B2Z_DERR_CORRUPT; break; } ip += 4; }
+        frames[nf++] = fr;
+    }
+    counts->nFrames = nf; counts->nBlocks = nb; counts->status = status; counts->srcUsed = ip;
+}
+
+// ---------------------------------------------------------------- bit readers (single lane)
+struct FwdBits {                                // LSB-first, used for NCount headers
+    const Src* S; uint64_t base; uint32_t size; uint32_t bitpos;
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const {
+        const uint32_t byte = bitpos >> 3;
+        uint64_t v = S->le64(base + byte);
+        if (byte + 8 > size) { const uint32_t valid = byte < size ? (size - byte) * 8u : 0u; v = valid ? (v & (valid >= 64 ? ~0ull : ((1ull << valid) - 1ull))) : 0ull; }
+        return (uint32_t)(v >> (bitpos & 7u)) & ((1u << n) - 1u);
+    }
+};
+
+struct BwdBits {                                // backward stream with end mark; bits below the start read as 0
+    const Src* S; uint64_t base; int64_t bitpos; int64_t winBit; uint64_t win; bool overflow;
+    __device__ __forceinline__ int init(const Src* s, uint64_t b, uint32_t size) {
+        S = s; base = b; overflow = false; win = 0; winBit = (int64_t)1 << 40;
+        if (!size) return -1;
+        const uint32_t lastByte = S->u8(b + size - 1);
+        if (!lastByte) return -1;
+        bitpos = (int64_t)(size - 1) * 8 + (int64_t)highbit32(lastByte);
+        return 0;
+    }
+    __device__ __forceinline__ void refill(int64_t hi) {            // window = 64 bits ending at byte-rounded hi
+        winBit = ((hi + 7) & ~7ll) - 64;
+        if (winBit >= 0) win = S->le64(base + (uint64_t)(winBit >> 3));
+        else if (winBit > -64) win = S->le64(base) << (uint32_t)(-winBit);
+        else win = 0;
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t n) {          // n in 1..32, does not consume
+        const int64_t lo = bitpos - (int64_t)n;
+        if (lo < winBit || bitpos > winBit + 64) refill(bitpos);
+        return (uint32_t)(win >> (uint32_t)(lo - winBit)) & (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
+    }
+    __device__ __forceinline__ uint32_t read(uint32_t n) {
+        if (!n) return 0;
+        const uint32_t v = peek(n);
+        bitpos -= n; if (bitpos < 0) overflow = true;
+        return v;
+    }
+};
+
+// ---------------------------------------------------------------- per-warp workspace of D1
+struct SeqEnt { uint32_t base; uint8_t nbAdd, nbBits; uint16_t next; };
+struct DecWS {
+    uint16_t huf[2048];          // symbol | nbBits << 8
+    SeqEnt   tab[3][512];        // LL, OF, ML
+    uint32_t tabLog[3];
+    uint32_t hufBits;
+    int16_t  norm[256];
+    uint16_t nxt[256];
+    uint8_t  sym[512];           // FSE symbol per state (build scratch) / Huffman weights
+};
+
+// FSE normalized counts; returns bytes consumed or 0
+__device__ uint32_t fse_read_ncount(int16_t* norm, uint32_t* maxSym, uint32_t* tableLog, const Src& S, uint64_t off, uint32_t size, uint32_t maxLog) {
+    if (size < 1) return 0;
+    FwdBits b; b.S = &S; b.base = off; b.size = size; b.bitpos = 0;
+    const uint32_t al = b.peek(4) + 5u; b.bitpos += 4;
+    if (al > maxLog) return 0;
+    int32_t remaining = 1 << al;
+    uint32_t sym = 0; const uint32_t limit = *maxSym;
+    while (remaining > 0 && sym <= limit) {
+        const uint32_t nb = highbit32((uint32_t)remaining + 1u) + 1u;
+        const uint32_t T = 1u << (nb - 1u), mx = 2u * T - 1u - ((uint32_t)remaining + 1u);
+        const uint32_t bits = b.peek(nb);
+        uint32_t count;
+        if ((bits & (T - 1u)) < mx) { count = bits & (T - 1u); b.bitpos += nb - 1u; }
+        else { count = bits & (2u * T - 1u); if (count >= T) count -= mx; b.bitpos += nb; }
+        const int32_t proba = (int32_t)count - 1;
+        remaining -= proba < 0 ? 1 : proba;
+        norm[sym++] = (int16_t)proba;
+        if (proba == 0) {
+            uint32_t rep;
+            do { rep = b.peek(2); b.bitpos += 2; for (uint32_t i = 0; i < rep; i++) { if (sym > limit) return 0; norm[sym++] = 0; } } while (rep == 3);
+        }
+        if ((b.bitpos >> 3) > size + 1u) return 0;
+    }
+    if (remaining != 0 || sym == 0) return 0;
+    const uint32_t used = (b.bitpos + 7u) >> 3;
+    if (used > size) return 0;
+    *maxSym = sym - 1u; *tableLog = al;
+    return used;
+}
+
+// generic FSE decode table: symbol per state in ws->sym, (nbBits, newState) returned through arrays
+__device__ bool fse_spread(DecWS* ws, const int16_t* norm, uint32_t maxSym, uint32_t log) {
+    const uint32_t size = 1u << log, mask = size - 1u; uint32_t high = size - 1u;
+    for (uint32_t s = 0; s <= maxSym; s++) {
+        if (norm[s] == -1) { ws->sym[high--] = (uint8_t)s; ws->nxt[s] = 1; } else ws->nxt[s] = (uint16_t)norm[s];
+    }
+    const uint32_t step = (size >> 1) + (size >> 3) + 3u; uint32_t pos = 0;
+    for (uint32_t s = 0; s <= maxSym; s++)
+        for (int i = 0; i < norm[s]; i++) { ws->sym[pos] = (uint8_t)s; pos = (pos + step) & mask; while (pos > high) pos = (pos + step) & mask; }
+    return pos == 0;
+}
+
+__device__ bool build_seq_table(DecWS* ws, int t, const int16_t* norm, uint32_t maxSym, uint32_t log) {
+    if (!fse_spread(ws, norm, maxSym, log)) return false;
+    const uint32_t size = 1u << log;
+    for (uint32_t u = 0; u < size; u++) {
+        const uint32_t s = ws->sym[u], ns = ws->nxt[s]++;
+        SeqEnt e; e.nbBits = (uint8_t)(log - highbit32(ns)); e.next = (uint16_t)((ns << e.nbBits) - size);
+        if (t == 0) { e.base = k_LL_base[s]; e.nbAdd = k_LL_bits[s]; }
+        else if (t == 2) { e.base = k_ML_base[s]; e.nbAdd = k_ML_bits[s]; }
+        else { e.base = 1u << s; e.nbAdd = (uint8_t)s; }
+        ws->tab[t][u] = e;
+    }
+    ws->tabLog[t] = log;
+    return true;
+}
+
+// Walk the table descriptions of block `blk`'s sequences section; returns the offset (absolute in src)
+// and mode of type t's description.  false on malformed data.
+__device__ bool locate_seq_table(const Src& S, const DecBlock& blk, int t, DecWS* ws, uint64_t* descOff, uint32_t* mode, uint32_t* avail) {
+    const LitHdr lh = parse_lit_hdr(S, blk.srcOff, blk.cSize);
+    if (!lh.ok) return false;
+    const uint32_t so = lh.hdr + lh.csize;
+    const SeqHdr sh = parse_seq_hdr(S, blk.srcOff + so, blk.cSize - so);
+    if (!sh.ok || !sh.nbSeq) return false;
+    uint64_t p = blk.srcOff + so + sh.hdr; uint32_t left = blk.cSize - so - sh.hdr;
+    const uint32_t maxSymT[3] = { 35, 31, 52 }, maxLogT[3] = { 9, 8, 9 };
+    for (int k = 0; k < 3; k++) {
+        const uint32_t m = (sh.modes >> (6 - 2 * k)) & 3u;
+        if (k == t) { *descOff = p; *mode = m; *avail = left; return true; }
+        uint32_t used = 0;
+        if (m == 1) used = 1;
+        else if (m == 2) { uint32_t ms = maxSymT[k], lg; used = fse_read_ncount(ws->norm, &ms, &lg, S, p, left, maxLogT[k]); if (!used) return false; }
+        if (used > left) return false;
+        p += used; left -= used;
+    }
+    return false;
+}
+
+// Huffman decoding table from the description at `off`; returns description bytes or 0
+__device__ uint32_t huf_read_table(DecWS* ws, const Src& S, uint64_t off, uint32_t size) {
+    if (size < 1) return 0;
+    uint8_t* w = ws->sym; uint32_t nw = 0;
+    const uint32_t hb = S.u8(off); uint32_t used;
+    if (hb >= 128) {
+        nw = hb - 127u; used = 1u + (nw + 1u) / 2u;
+        if (used > size) return 0;
+        for (uint32_t i = 0; i < nw; i++) { const uint32_t v = S.u8(off + 1 + i / 2); w[i] = (uint8_t)((i & 1u) ? (v & 15u) : (v >> 4)); }
+    } else {
+        used = 1u + hb;
+        if (hb == 0 || used > size) return 0;
+        uint32_t maxSym = 255, al;
+        const uint32_t hs = fse_read_ncount(ws->norm, &maxSym, &al, S, off + 1, hb, 6);
+        if (!hs || hs >= hb) return 0;
+        // weights FSE table: symbols in ws->sym[256..], nbBits/newState packed in ws->huf[0..63]
+        uint8_t* fsym = ws->sym + 256;
+        {
+            const uint32_t size2 = 1u << al, mask = size2 - 1u; uint32_t high = size2 - 1u;
+            for (uint32_t s = 0; s <= maxSym; s++) { if (ws->norm[s] == -1) { fsym[high--] = (uint8_t)s; ws->nxt[s] = 1; } else ws->nxt[s] = (uint16_t)ws->norm[s]; }
+            const uint32_t step = (size2 >> 1) + (size2 >> 3) + 3u; uint32_t pos = 0;
+            for (uint32_t s = 0; s <= maxSym; s++)
+                for (int i = 0; i < ws->norm[s]; i++) { fsym[pos] = (uint8_t)s; pos = (pos + step) & mask; while (pos > high) pos = (pos + step) & mask; }
+            if (pos != 0) return 0;
+            for (uint32_t u = 0; u < size2; u++) {
+                const uint32_t s = fsym[u], ns = ws->nxt[s]++;
+                const uint32_t nbb = al - highbit32(ns);
+                ws->huf[u] = (uint16_t)(nbb | ((((ns << nbb) - size2) & 0xFFu) << 8));     // newState < 64
+            }
+        }
+        BwdBits b; if (b.init(&S, off + 1 + hs, hb - hs)) return 0;
+        uint32_t s1 = b.read(al), s2 = b.read(al);
+        if (b.overflow) return 0;
+        for (;;) {
+            if (nw > 253) return 0;
+            w[nw++] = fsym[s1]; { const uint32_t e = ws->huf[s1]; s1 = (e >> 8) + b.read(e & 255u); }
+            if (b.overflow) { w[nw++] = fsym[s2]; break; }
+            if (nw > 253) return 0;
+            w[nw++] = fsym[s2]; { const uint32_t e = ws->huf[s2]; s2 = (e >> 8) + b.read(e & 255u); }
+            if (b.overflow) { w[nw++] = fsym[s1]; break; }
+        }
+    }
+    uint32_t sum = 0, rank[13];
+    for (uint32_t r = 0; r < 13; r++) rank[r] = 0;
+    for (uint32_t i = 0; i < nw; i++) { if (w[i] > 11) return 0; if (w[i]) sum += 1u << (w[i] - 1u); }
+    if (!sum) return 0;
+    const uint32_t maxBits = highbit32(sum) + 1u;
+    if (maxBits > 11) return 0;
+    const uint32_t rest = (1u << maxBits) - sum;
+    if (rest & (rest - 1u)) return 0;
+    w[nw++] = (uint8_t)(highbit32(rest) + 1u);
+    for (uint32_t i = 0; i < nw; i++) rank[w[i]]++;
+    if (rank[1] < 2 || (rank[1] & 1u)) return 0;
+    uint32_t start[13], pos = 0;
+    for (uint32_t r = 1; r <= maxBits; r++) { start[r] = pos; pos += rank[r] << (r - 1u); }
+    for (uint32_t s = 0; s < nw; s++) {
+        const uint32_t r = w[s]; if (!r) continue;
+        const uint32_t len = 1u << (r - 1u); const uint16_t e = (uint16_t)(s | ((maxBits + 1u - r) << 8));
+        for (uint32_t i = 0; i < len; i++) ws->huf[start[r] + i] = e;
+        start[r] += len;
+    }
+    ws->hufBits = maxBits;
+    return used;
+}
+
+// one Huffman stream, one lane
+__device__ bool huf_decode_stream(const DecWS* ws, const Src& S, uint64_t off, uint32_t size, uint8_t* dst, uint32_t n) {
+    BwdBits b; if (b.init(&S, off, size)) return false;
+    const uint32_t mb = ws->hufBits;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t e = ws->huf[b.peek(mb)];
+        dst[i] = (uint8_t)e; b.bitpos -= (e >> 8);
+    }
+    return b.bitpos == 0;
+}
+
+// ---------------------------------------------------------------- D1: entropy decode
+#define SEQ_PACK(ob, ll, ml) ((uint64_t)(ob) | ((uint64_t)(ll) << 30) | ((uint64_t)((ml) - 3u) << 47))
+
+__global__ void __launch_bounds__(B2Z_DEC_WARPS * 32)
+zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBlock* __restrict__ blocks, uint32_t nBlocks,
+                        uint8_t* __restrict__ lits, uint64_t* __restrict__ seqs) {
+    __shared__ DecWS wsAll[B2Z_DEC_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    DecWS* ws = &wsAll[wib];
+    Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
+    for (uint32_t bi = blockIdx.x * B2Z_DEC_WARPS + wib; bi < nBlocks; bi += gridDim.x * B2Z_DEC_WARPS) {
+        const DecBlock blk = blocks[bi];
+        if (blk.type != 2) continue;
+        uint32_t err = 0;
+        const LitHdr lh = parse_lit_hdr(S, blk.srcOff, blk.cSize);
+        uint8_t* lit = lits + (size_t)bi * 131072u;
+        // ---- literals
+        if (lh.type == 0) { for (uint32_t i = lane; i < lh.regen; i += 32) lit[i] = (uint8_t)S.u8(blk.srcOff + lh.hdr + i); }
+        else if (lh.type == 1) { const uint8_t v = (uint8_t)S.u8(blk.srcOff + lh.hdr); for (uint32_t i = lane; i < lh.regen; i += 32) lit[i] = v; }
+        else {
+            uint32_t tdesc = 0;                                  // this block's own table description bytes
+            if (lane == 0) {
+                const DecBlock sb = blocks[blk.hufSrc];
+                const LitHdr sh = parse_lit_hdr(S, sb.srcOff, sb.cSize);
+                const uint32_t u = (sh.ok && sh.type == 2) ? huf_read_table(ws, S, sb.srcOff + sh.hdr, sh.csize) : 0u;
+                if (!u) err = B2Z_DERR_CORRUPT;
+                if (lh.type == 2) tdesc = u;
+            }
+            err = __shfl_sync(B2Z_FULL, err, 0); tdesc = __shfl_sync(B2Z_FULL, tdesc, 0);
+            __syncwarp();
+            if (!err) {
+                const uint64_t hs = blk.srcOff + lh.hdr + tdesc; const uint32_t hsz = lh.csize - tdesc;
+                bool ok = true;
+                if (tdesc > lh.csize) ok = false;
+                else if (lh.streams == 1) { if (lane == 0) ok = huf_decode_stream(ws, S, hs, hsz, lit, lh.regen); }
+                else {
+                    if (hsz < 6) ok = false;
+                    else {
+                        const uint64_t j = S.le64(hs);
+                        const uint32_t s1 = (uint32_t)j & 0xFFFFu, s2 = (uint32_t)(j >> 16) & 0xFFFFu, s3 = (uint32_t)(j >> 32) & 0xFFFFu;
+                        const uint32_t seg = (lh.regen + 3u) / 4u;
+                        if (6u + s1 + s2 + s3 > hsz || seg * 3u > lh.regen) ok = false;
+                        else if (lane < 4) {
+                            const uint32_t s4 = hsz - 6u - s1 - s2 - s3;
+                            const uint32_t so = lane == 0 ? 0u : (lane == 1 ? s1 : (lane == 2 ? s1 + s2 : s1 + s2 + s3));
+                            const uint32_t sz = lane == 0 ? s1 : (lane == 1 ? s2 : (lane == 2 ? s3 : s4));
+                            const uint32_t cnt = lane < 3 ? seg : lh.regen - 3u * seg;
+                            ok = huf_decode_stream(ws, S, hs + 6u + so, sz, lit + lane * seg, cnt);
+                        }
+                    }
+                }
+                if (!__all_sync(B2Z_FULL, ok)) err = B2Z_DERR_CORRUPT;
+            }
+        }
+        __syncwarp();
+        // ---- sequences (lane 0)
+        uint32_t nbSeq = 0, regen = 0;
+        if (lane == 0 && !err) {
+            const uint32_t so = lh.hdr + lh.csize;
+            const SeqHdr sh = parse_seq_hdr(S, blk.srcOff + so, blk.cSize - so);
+            nbSeq = sh.nbSeq; regen = lh.regen;
+            if (nbSeq > B2Z_DEC_MAXSEQ) err = B2Z_DERR_CORRUPT;
+            if (nbSeq && !err) {
+                const uint32_t maxSymT[3] = { 35, 31, 52 }, maxLogT[3] = { 9, 8, 9 }, defMax[3] = { 35, 28, 52 }, defLog[3] = { 6, 5, 6 };
+                uint64_t bsOff = blk.srcOff + so + sh.hdr; uint32_t bsLeft = blk.cSize - so - sh.hdr;
+                for (int t = 0; t < 3 && !err; t++) {
+                    uint64_t d; uint32_t mode, avail;
+                    const uint32_t ownMode = (sh.modes >> (6 - 2 * t)) & 3u;
+                    if (ownMode == 3) {
+                        if (!locate_seq_table(S, blocks[blk.tblSrc[t]], t, ws, &d, &mode, &avail) || mode == 3) { err = B2Z_DERR_CORRUPT; break; }
+                    } else { d = bsOff; mode = ownMode; avail = bsLeft; }
+                    uint32_t used = 0;
+                    if (mode == 0) {
+                        const int16_t* dn = t == 0 ? k_LL_defNorm : (t == 1 ? k_OF_defNorm : k_ML_defNorm);
+                        for (uint32_t s = 0; s <= defMax[t]; s++) ws->norm[s] = dn[s];
+                        if (!build_seq_table(ws, t, ws->norm, defMax[t], defLog[t])) err = B2Z_DERR_CORRUPT;
+                    } else if (mode == 1) {
+                        const uint32_t s = S.u8(d);
+                        if (avail < 1 || s > maxSymT[t]) err = B2Z_DERR_CORRUPT;
+                        else {
+                            SeqEnt e; e.nbBits = 0; e.next = 0;
+                            if (t == 0) { e.base = k_LL_base[s]; e.nbAdd = k_LL_bits[s]; } else if (t == 2) { e.base = k_ML_base[s]; e.nbAdd = k_ML_bits[s]; } else { e.base = 1u << s; e.nbAdd = (uint8_t)s; }
+                            ws->tab[t][0] = e; ws->tabLog[t] = 0; used = 1;
+                        }
+                    } else {
+                        uint32_t ms = maxSymT[t], lg;
+                        used = fse_read_ncount(ws->norm, &ms, &lg, S, d, avail, maxLogT[t]);
+                        if (!used || !build_seq_table(ws, t, ws->norm, ms, lg)) err = B2Z_DERR_CORRUPT;
+                    }
+                    if (ownMode != 3) { if (used > bsLeft) err = B2Z_DERR_CORRUPT; else { bsOff += used; bsLeft -= used; } }
+                }
+                if (!err) {
+                    BwdBits b;
+                    if (b.init(&S, bsOff, bsLeft)) err = B2Z_DERR_CORRUPT;
+                    else {
+                        uint32_t sL = b.read(ws->tabLog[0]), sO = b.read(ws->tabLog[1]), sM = b.read(ws->tabLog[2]);
+                        if (b.overflow) err = B2Z_DERR_CORRUPT;
+                        uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+                        uint32_t litUsed = 0, total = 0;
+                        for (uint32_t i = 0; i < nbSeq && !err; i++) {
+                            const SeqEnt eL = ws->tab[0][sL], eO = ws->tab[1][sO], eM = ws->tab[2][sM];
+                            if (eO.nbAdd > 30) { err = B2Z_DERR_UNSUPPORTED; break; }
+                            const uint32_t ob = eO.base + b.read(eO.nbAdd);
+                            const uint32_t ml = eM.base + b.read(eM.nbAdd);
+                            const uint32_t ll = eL.base + b.read(eL.nbAdd);
+                            if (i + 1 < nbSeq) { sL = eL.next + b.read(eL.nbBits); sM = eM.next + b.read(eM.nbBits); sO = eO.next + b.read(eO.nbBits); }
+                            litUsed += ll; total += ll + ml;
+                            if (b.overflow || litUsed > lh.regen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
+                            out[i] = SEQ_PACK(ob, ll, ml);
+                        }
+                        if (!err && b.bitpos != 0) err = B2Z_DERR_CORRUPT;
+                        regen = total + (lh.regen - litUsed);
+                        if (regen > 131072u) err = B2Z_DERR_CORRUPT;
+                    }
+                }
+            }
+        }
+        if (lane == 0) { blocks[bi].regen = err ? 0u : regen; blocks[bi].nbSeq = nbSeq; blocks[bi].litSize = lh.regen; blocks[bi].status = err; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- D2: layout
+__global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, const DecBlock* __restrict__ blocks, DecCounts* counts) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFrames) return;
+    uint64_t total = 0; uint32_t st = 0;
+    const uint32_t b0 = frames[f].firstBlock, nb = frames[f].nBlocks;
+    for (uint32_t i = 0; i < nb; i++) { total += blocks[b0 + i].regen; st |= blocks[b0 + i].status; }
+    if (frames[f].contentSize != ~0ull && frames[f].contentSize != total) st |= B2Z_DERR_CORRUPT;
+    frames[f].regen = total;
+    if (st) atomicOr(&counts->status, st);
+}
+__global__ void zstd_dec_frame_offsets_kernel(DecFrame* frames, uint32_t nFrames, uint64_t dstCap, DecCounts* counts, uint64_t* total) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint64_t o = 0;
+    for (uint32_t f = 0; f < nFrames; f++) { frames[f].dstOff = o; o += frames[f].regen; }
+    *total = o;
+    if (o > dstCap) atomicOr(&counts->status, B2Z_DERR_DSTSIZE);
+}
+
+// ---------------------------------------------------------------- D3: execute
+__global__ void __launch_bounds__(32)
+zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ frames, uint32_t nFrames, DecBlock* __restrict__ blocks,
+                     const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* dst, DecCounts* counts) {
+    if (counts->status) return;                                  // a failed stage: nothing is written
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t f = blockIdx.x; f < nFrames; f += gridDim.x) {
+        const DecFrame fr = frames[f];
+        uint8_t* out = dst + fr.dstOff;
+        uint64_t o = 0;                                          // bytes produced in this frame
+        uint32_t rep0 = 1, rep1 = 4, rep2 = 8, err = 0;
+        for (uint32_t bi = fr.firstBlock; bi < fr.firstBlock + fr.nBlocks && !err; bi++) {
+            const DecBlock blk = blocks[bi];
+            if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = src[blk.srcOff + i]; o += blk.rawSize; __syncwarp(); continue; }
+            if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = v; o += blk.rawSize; __syncwarp(); continue; }
+            const uint8_t* lit = lits + (size_t)bi * 131072u;
+            const uint64_t* sq = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+            uint32_t lp = 0;
+            for (uint32_t i0 = 0; i0 < blk.nbSeq && !err; i0 += 32) {
+                const uint32_t cnt = (blk.nbSeq - i0) < 32u ? (blk.nbSeq - i0) : 32u;
+                const uint64_t mine = lane < cnt ? sq[i0 + lane] : 0ull;
+                for (uint32_t k = 0; k < cnt; k++) {
+                    const uint64_t s = __shfl_sync(B2Z_FULL, mine, k);
+                    const uint32_t ob = (uint32_t)s & 0x3FFFFFFFu, ll = (uint32_t)(s >> 30) & 0x1FFFFu, ml = (uint32_t)(s >> 47) + 3u;
+                    uint32_t offset;
+                    if (ob > 3) { offset = ob - 3u; rep2 = rep1; rep1 = rep0; rep0 = offset; }
+                    else {
+                        const uint32_t idx = ob - 1u + (ll == 0u);
+                        if (idx == 0) offset = rep0;
+                        else {
+                            offset = idx == 3 ? rep0 - 1u : (idx == 1 ? rep1 : rep2);
+                            if (idx != 1) rep2 = rep1;
+                            rep1 = rep0; rep0 = offset;
+                        }
+                    }
+                    // literals
+                    for (uint32_t i = lane; i < ll; i += 32) out[o + i] = lit[lp + i];
+                    o += ll; lp += ll;
+                    if (offset == 0 || offset > o || offset > fr.windowSize) { err = B2Z_DERR_CORRUPT; break; }
+                    // match: periodic extension makes every byte independent of this copy's own output
+                    const uint8_t* m = out + o - offset;
+                    if (offset >= ml) { for (uint32_t i = lane; i < ml; i += 32) out[o + i] = __ldcg(m + i); }
+                    else { for (uint32_t i = lane; i < ml; i += 32) out[o + i] = __ldcg(m + (i % offset)); }
+                    o += ml;
+                    __syncwarp();
+                }
+            }
+            if (!err) { const uint32_t tail = blk.litSize - lp; for (uint32_t i = lane; i < tail; i += 32) out[o + i] = lit[lp + i]; o += tail; }
+            __syncwarp();
+        }
+        if (!err && o != fr.regen) err = B2Z_DERR_CORRUPT;
+        if (err && lane == 0) atomicOr(&counts->status, err);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+void launch_zstd_dec_prepass(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap,
+                             DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st) {
+    zstd_dec_prepass_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, blocks, blockCap, counts);
+}
+void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks, uint8_t* lits, uint64_t* seqs, cudaStream_t st) {
+    if (!nBlocks) return;
+    uint32_t grid = (nBlocks + B2Z_DEC_WARPS - 1) / B2Z_DEC_WARPS;
+    if (grid > 148u * 32u) grid = 148u * 32u;
+    zstd_dec_entropy_kernel<<<grid, B2Z_DEC_WARPS * 32, 0, st>>>(src, srcSize, blocks, nBlocks, lits, seqs);
+}
+void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* blocks, uint64_t dstCap, DecCounts* counts, uint64_t* total, cudaStream_t st) {
+    if (nFrames) zstd_dec_frame_sizes_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(frames, nFrames, blocks, counts);
+    zstd_dec_frame_offsets_kernel<<<1, 32, 0, st>>>(frames, nFrames, dstCap, counts, total);
+}
+void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, const uint8_t* lits, const uint64_t* seqs,
+                          uint8_t* dst, DecCounts* counts, cudaStream_t st) {
+    if (!nFrames) return;
+    const uint32_t grid = nFrames < 148u * 32u ? nFrames : 148u * 32u;
+    zstd_dec_exec_kernel<<<grid, 32, 0, st>>>(src, frames, nFrames, blocks, lits, seqs, dst, counts);
+}
+
+}  // namespace b2z

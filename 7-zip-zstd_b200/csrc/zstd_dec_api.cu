@@ -1,9 +1,21 @@
-// zstd_dec_api.cu -- decoder half of the C ABI (placeholder until the decode kernels land).
-#include <cuda_runtime.h>
-#include <cstring>
-#include "../../include/b200z.h"
+// zstd_dec_api.cu -- decoder half of the C ABI (include/b200z.h): drives stages D0..D3.
+//
+// Replaces the streaming loop of CPP/7zip/Compress/ZstdDecoder.cpp:108-173 (ZSTD_decompressStream
+// over 128 KiB reads, frame after frame): here one call takes the whole Code() input, every frame
+// of it (zstd or skippable) is located by the prepass and decoded in parallel.
+#include "b2z_ctx.h"
+
+using namespace b2z;
 
 static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+static int dec_status_to_rc(b200z_ctx* ctx, uint32_t st) {
+    if (st & B2Z_DERR_TABLE_FULL) return fail(ctx, B200Z_E_UNSUPPORTED, "more frames/blocks than the decoder tables hold%s");
+    if (st & B2Z_DERR_UNSUPPORTED) return fail(ctx, B200Z_E_UNSUPPORTED, "dictionary or window > 1 GiB frames are not supported%s");
+    if (st & B2Z_DERR_DSTSIZE) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
+    if (st & B2Z_DERR_CORRUPT) return fail(ctx, B200Z_E_CORRUPT, "corrupt zstd data%s");
+    return 0;
+}
 
 extern "C" {
 
@@ -41,6 +53,7 @@ int b200z_zstd_frame_info(const void* srcv, size_t srcSize, uint64_t* contentSiz
             if (type == 3) return B200Z_E_CORRUPT;
             const size_t adv = type == 1 ? 1 : bsize;
             if ((size_t)(iend - ip) < adv) return B200Z_E_CORRUPT;
+            if (!fcsBytes && type != 2) total += bsize;          // lower bound only; flagged unknown below
             ip += adv;
             if (last) break;
         }
@@ -52,7 +65,72 @@ int b200z_zstd_frame_info(const void* srcv, size_t srcSize, uint64_t* contentSiz
     return unknown ? B200Z_E_UNSUPPORTED : B200Z_OK;
 }
 
-int b200z_zstd_decompress_device(b200z_ctx*, const void*, size_t, void*, size_t, size_t*) { return B200Z_E_UNSUPPORTED; }
-int b200z_zstd_decompress_host(b200z_ctx*, const void*, size_t, void*, size_t, size_t*) { return B200Z_E_UNSUPPORTED; }
+int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_dst, size_t dstCap, size_t* dstSize) {
+    if (!ctx || !dstSize || (!d_src && srcSize) || (!d_dst && dstCap)) return B200Z_E_PARAM;
+    if ((uintptr_t)d_src & 7u) return fail(ctx, B200Z_E_PARAM, "device source must be 8-byte aligned%s");
+    *dstSize = 0;
+    if (!srcSize) return 0;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // table capacities: frames >= 9 bytes each, blocks >= 3 bytes each; bounded to keep the tables small
+    uint64_t frameCap = srcSize / 9 + 2; if (frameCap > (1u << 22)) frameCap = 1u << 22;
+    uint64_t blockCap = srcSize / 3 + 2; { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }
+    if (blockCap > 0x7FFFFFFFull) blockCap = 0x7FFFFFFFull;
+    Arena& aFrames = ctx->decScratch[0]; Arena& aBlocks = ctx->decScratch[1]; Arena& aCounts = ctx->decScratch[2];
+    Arena& aLits = ctx->decScratch[3]; Arena& aSeqs = ctx->decScratch[4];
+    if (aFrames.reserve(frameCap * sizeof(DecFrame)) || aBlocks.reserve(blockCap * sizeof(DecBlock)) || aCounts.reserve(64))
+        return fail(ctx, B200Z_E_MEMORY, "decoder table allocation failed%s");
+    DecFrame* frames = (DecFrame*)aFrames.p; DecBlock* blocks = (DecBlock*)aBlocks.p;
+    DecCounts* counts = (DecCounts*)aCounts.p; uint64_t* total = (uint64_t*)((uint8_t*)aCounts.p + 32);
+    CU(cudaMemsetAsync(aCounts.p, 0, 64, st));
+    CU(cudaEventRecord(ctx->ev[0], st));
+    launch_zstd_dec_prepass((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, blocks, (uint32_t)blockCap, counts, st);
+    CU(cudaGetLastError());
+    DecCounts hc;
+    CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+    if (hc.status) return dec_status_to_rc(ctx, hc.status);
+    if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64))
+        return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (input too large for one pass)%s");
+    launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[1], st));
+    launch_zstd_dec_layout(frames, hc.nFrames, blocks, dstCap, counts, total, st);
+    CU(cudaGetLastError());
+    launch_zstd_dec_exec((const uint8_t*)d_src, frames, hc.nFrames, blocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
+                         (uint8_t*)d_dst, counts, st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[2], st));
+    struct { DecCounts c; uint64_t total; } hr;
+    CU(cudaMemcpyAsync(&hr.c, counts, sizeof(DecCounts), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hr.total, total, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_DEC_ENTROPY_MS] += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_DEC_EXEC_MS] += ms;
+    if (hr.c.status) return dec_status_to_rc(ctx, hr.c.status);
+    *dstSize = (size_t)hr.total;
+    return 0;
+}
+
+int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize) {
+    if (!ctx || !dstSize || (!src && srcSize) || (!dst && dstCap)) return B200Z_E_PARAM;
+    *dstSize = 0;
+    if (!srcSize) return 0;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(dstCap + 64)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+    CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
+    size_t out = 0;
+    int rc = b200z_zstd_decompress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, dstCap, &out);
+    if (rc) return rc;
+    if (out) CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
+    *dstSize = out;
+    return 0;
+}
 
 }  // extern "C"

@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 zstd hot path (BASELINE.json configs[1]).
+
+One "step" = one pass of the hot path over one batch of synthetic input: zstd level-3 encode of
+the rank's corpus shard followed by decode of the produced frames (round trip verified on the
+device, outside the timed region).  Metric: MB/s of uncompressed data through encode+decode,
+MB = 1e6 bytes:   value = units / (t_enc + t_dec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size-mib M] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, weak scaling)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size-mib", type=int, default=4096, help="uncompressed MiB per GPU per step (cfg2: 4 GiB)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-mib", type=int, default=1024, help="bounded sample for the CPU reference arm")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- clocks sampler (nvidia-smi)
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index; self.samples = []; self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.samples:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- CPU reference arm
+def cpu_reference(sample_bytes, seed_offset=0):
+    """The reference's own CPU implementation of the path (oracle/_ref/libref_zstd.so compiled from
+    /root/reference/C/zstd): level 3, zstdmt with all host threads for encode (ZstdEncoder.cpp:300
+    nbWorkers = #CPUs), single-threaded decode (ZstdDecoder.cpp:260-263: SetNumberOfThreads is a no-op)."""
+    import ctypes
+    import numpy as np
+    import helpers
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    cores = os.cpu_count() or 1
+    data = pkg.corpus.g2(sample_bytes, offset=seed_offset)
+    if helpers.ref_available():
+        Z = helpers.ref(); kind = "reference"
+        out = np.zeros(Z.ZSTD_compressBound(sample_bytes), dtype=np.uint8)      # pre-faulted: page faults are not the codec
+        c = Z.ZSTD_createCCtx()
+        Z.ZSTD_CCtx_setParameter(c, 100, 3); Z.ZSTD_CCtx_setParameter(c, 400, min(cores, 200))
+        t = time.perf_counter(); r = Z.ZSTD_compress2(c, out.ctypes.data, out.size, data.ctypes.data, sample_bytes); t_enc = time.perf_counter() - t
+        Z.ZSTD_freeCCtx(c)
+        back = np.zeros(sample_bytes, dtype=np.uint8)
+        t = time.perf_counter(); d = Z.ZSTD_decompress(back.ctypes.data, sample_bytes, out.ctypes.data, r); t_dec = time.perf_counter() - t
+        assert d == sample_bytes
+        enc_threads, dec_threads = min(cores, 200), 1
+    else:                                                   # oracle port (single-threaded C restatement)
+        O = helpers.oracle(); kind = "port"
+        p = helpers.enc_params()
+        out = np.empty(O.b2zo_zstd_compress_bound(sample_bytes, ctypes.byref(p)), dtype=np.uint8)
+        t = time.perf_counter(); r = O.b2zo_zstd_compress(out.ctypes.data, out.size, data.ctypes.data, sample_bytes, ctypes.byref(p)); t_enc = time.perf_counter() - t
+        back = np.empty(sample_bytes, dtype=np.uint8)
+        t = time.perf_counter(); d = O.b2zo_zstd_decompress(back.ctypes.data, sample_bytes, out.ctypes.data, r); t_dec = time.perf_counter() - t
+        assert d == sample_bytes
+        enc_threads, dec_threads = 1, 1
+    mb = sample_bytes / 1e6
+    return {"value": mb / (t_enc + t_dec), "unit": "MB/s", "cores": cores, "kind": kind,
+            "sample": f"{sample_bytes >> 20} MiB of the same G2 text, zstd level 3: encode {enc_threads} threads (zstdmt), decode {dec_threads} thread (reference decoder is single-threaded)",
+            "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": sample_bytes / r, "t_enc_s": t_enc, "t_dec_s": t_dec}
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    unit_bytes = a.size_mib << 20
+    workload = f"zstd level 3, {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 128 KiB blocks"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sample = a.cpu_sample_mib << 20
+        for _ in range(max(0, min(a.warmup, 1))):
+            cpu_reference(min(sample, 64 << 20))
+        t_tot = 0.0; res = None
+        for _ in range(a.steps):
+            res = cpu_reference(sample); t_tot += res["t_enc_s"] + res["t_dec_s"]
+        value = a.steps * sample / 1e6 / t_tot
+        line = {"impl": "reference", "metric": "zstd-L3 encode+decode throughput", "value": value, "unit": "MB/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": workload, "sample": res["sample"]},
+                "cpu_baseline": {k: res[k] for k in ("unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")} | {"value": value},
+                "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line)); return
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    codec = pkg.Codec(local)
+    # ---- corpus shard: rank r owns bytes [r*unit, (r+1)*unit) of the seeded G2 stream (weak scaling)
+    host_in = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
+    pkg.corpus.g2_into(host_in.data_ptr(), unit_bytes, offset=rank * unit_bytes, threads=max(1, (os.cpu_count() or 8) // max(1, world)))
+    d_in = host_in.cuda(non_blocking=False)
+    bound = codec.compress_bound(unit_bytes)
+    d_comp = torch.empty(bound, dtype=torch.uint8, device="cuda")
+    d_back = torch.empty(unit_bytes, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        t0 = time.perf_counter(); c = codec.compress_device(d_in.data_ptr(), unit_bytes, d_comp.data_ptr(), bound); t1 = time.perf_counter()
+        n = codec.decompress_device(d_comp.data_ptr(), c, d_back.data_ptr(), unit_bytes); t2 = time.perf_counter()
+        assert n == unit_bytes
+        return c, t1 - t0, t2 - t1
+
+    for _ in range(a.warmup):
+        csize, _, _ = step_device()
+    assert torch.equal(d_back, d_in), "round trip mismatch"                      # bit-exact round trip (outside the timed region)
+    ratio = unit_bytes / csize
+
+    sampler = ClockSampler(local); sampler.start()
+    codec.reset_stats()
+    barrier(); T0 = time.perf_counter()
+    t_enc = t_dec = 0.0
+    for _ in range(a.steps):
+        _, te, td = step_device(); t_enc += te; t_dec += td
+    barrier(); T1 = time.perf_counter()
+    clocks = sampler.stop(T0, T1)
+    elapsed = T1 - T0
+    stats = {k: codec.stat(v) for k, v in dict(match_ms=1, entropy_ms=2, assemble_ms=3, dec_entropy_ms=4, dec_exec_ms=5, launches=6).items()}
+    if dist:
+        t = torch.tensor([elapsed, t_enc, t_dec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); elapsed, t_enc, t_dec = (float(x) for x in t.cpu())
+    units_mb = world * a.steps * unit_bytes / 1e6
+    value = units_mb / elapsed
+
+    # ---- end to end through the host-pointer C ABI (what the 7-Zip coder wrapper calls): pinned host
+    #      buffers, H2D of the input and D2H of the result inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        host_comp = torch.empty(bound, dtype=torch.uint8).pin_memory()
+        host_back = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
+
+        def step_host():
+            c = codec.compress_into(host_in.data_ptr(), unit_bytes, host_comp.data_ptr(), bound)
+            n = codec.decompress_into(host_comp.data_ptr(), c, host_back.data_ptr(), unit_bytes)
+            assert n == unit_bytes
+            return c
+        c = step_host()
+        barrier(); E0 = time.perf_counter()
+        for _ in range(a.steps):
+            c = step_host()
+        barrier(); E1 = time.perf_counter()
+        assert torch.equal(host_back, host_in)
+        e_el = E1 - E0
+        if dist:
+            t = torch.tensor([e_el], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e_el = float(t.cpu()[0])
+        e2e = {"value": units_mb / e_el, "unit": "MB/s", "h2d_bytes_per_step": unit_bytes + c, "d2h_bytes_per_step": c + unit_bytes}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (stage M, zstd_enc_match_kernel): algorithmic bytes per launch
+    #      = U * (1 + 1/ratio)  (encode reads the input once, writes the compressed stream once)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0); peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    match_ms = stats["match_ms"] / a.steps
+    algo_bytes = unit_bytes * (1.0 + 1.0 / ratio)
+    achieved = algo_bytes / 1e9 / (match_ms / 1e3) if match_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
+    except Exception:
+        pass
+    line = {
+        "metric": "zstd-L3 encode+decode throughput", "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload, "global_uncompressed_bytes_per_step": world * unit_bytes, "frame_log": codec.get("frame_log"),
+                   "parallelism": f"{world} independent shard(s), no collective", "l2": "inputs (4 GiB) larger than L2; no flush needed",
+                   "ratio": ratio, "enc_MBps": units_mb / t_enc, "dec_MBps": units_mb / t_dec,
+                   "kernel_ms_per_step": {k: v / a.steps for k, v in stats.items() if k != "launches"}},
+        "roofline": {"bound": "hbm", "kernel": "zstd_enc_match_kernel", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": match_ms},
+        "clocks": clocks, "gpu_launches": int(stats["launches"]), "e2e": e2e,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        cb = cpu_reference(a.cpu_sample_mib << 20)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""GPU parity tests of the zstd decoder path (through the C ABI): output must be bit-exact
+against the reference for any valid frame -- checked on frames produced by the reference encoder
+(oracle/_ref) at many levels, on the committed golden fixtures (reference test vector + reference
+encoder outputs), on our own encoder's frames, and on corrupted inputs against the oracle decoder."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def inputs(pkg):
+    return helpers.sample_inputs(pkg, big=True)
+
+
+def test_golden_reference_vector(codec):
+    comp = open(os.path.join(GOLDEN, "test.txt.zstd"), "rb").read()
+    out = codec.decompress(comp, max_size=1_000_000)      # the vector declares no content size
+    assert hashlib.sha256(out).hexdigest() == open(os.path.join(GOLDEN, "test.txt.sha256")).read().strip()
+
+
+def test_golden_reference_frames(codec):
+    idx = json.load(open(os.path.join(GOLDEN, "frames.json")))
+    for name, meta in idx.items():
+        comp = open(os.path.join(GOLDEN, name), "rb").read()
+        out = codec.decompress(comp, max_size=meta["size"])
+        assert hashlib.sha256(out).hexdigest() == meta["sha256"], name
+
+
+def test_own_frames_roundtrip(codec, inputs):
+    for name, data in inputs.items():
+        comp = codec.compress(data)
+        assert codec.decompress(comp) == data, name
+
+
+@pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref not built")
+def test_reference_encoder_frames(codec, inputs):
+    for name, d in inputs.items():
+        for lv in (-5, 1, 3, 6, 13, 19):
+            for cs in (0, 1):
+                if len(d) > 1_100_000 and lv > 6:
+                    continue
+                comp = helpers.ref_compress(d, lv, cs)
+                assert codec.decompress(comp, max_size=len(d)) == d, (name, lv, cs)
+    d = inputs["g2_1m"]
+    multi = helpers.ref_compress(d, 3) + b"\x50\x2a\x4d\x18\x04\x00\x00\x00ABCD" + helpers.ref_compress(inputs["mixed"], 5, 1) + helpers.ref_compress(b"", 3)
+    assert codec.decompress(multi, max_size=len(d) + len(inputs["mixed"])) == d + inputs["mixed"]
+    mt = helpers.ref_compress(d + d, 3, 0, nbWorkers=2)                 # zstdmt: one frame, jobs without frame headers
+    assert codec.decompress(mt, max_size=2 * len(d)) == d + d
+    nofcs = helpers.ref_compress(inputs["mixed"], 4, 0, contentSizeFlag=0)     # streaming-style frame: no content size
+    assert codec.decompress(nofcs, max_size=len(inputs["mixed"])) == inputs["mixed"]
+
+
+def test_corrupted_inputs_match_oracle(pkg, codec, inputs):
+    """bit flips: the GPU decoder must fail cleanly or produce exactly what the oracle decoder produces"""
+    d = inputs["mixed"][:300_000]
+    comp = bytearray(codec.compress(d))
+    rnd = random.Random(11)
+    for _ in range(40):
+        c2 = bytearray(comp)
+        for _k in range(rnd.randrange(1, 3)):
+            i = rnd.randrange(len(c2)); c2[i] ^= 1 << rnd.randrange(8)
+        try:
+            want = helpers.oracle_decompress(bytes(c2), len(d) + 4096)
+        except ValueError:
+            want = None
+        try:
+            got = codec.decompress(bytes(c2), max_size=len(d) + 4096)
+        except pkg.B200zError:
+            got = None
+        assert got == want
+    with pytest.raises(pkg.B200zError):
+        codec.decompress(b"not a zstd frame at all", max_size=100)
+    with pytest.raises(pkg.B200zError):
+        codec.decompress(bytes(comp[: len(comp) // 2]), max_size=len(d))
+
+
+def test_dst_too_small(pkg, codec, inputs):
+    comp = codec.compress(inputs["g2_1m"])
+    with pytest.raises(pkg.B200zError) as e:
+        codec.decompress(comp, max_size=1000)
+    assert e.value.code == -4
+
+
+def test_device_resident_decode(pkg, codec):
+    import torch
+    data = pkg.corpus.g2(8 << 20)
+    comp = np.frombuffer(codec.compress(data.tobytes()), dtype=np.uint8)
+    src = torch.from_numpy(comp.copy()).cuda()
+    dst = torch.empty(data.size, dtype=torch.uint8, device="cuda")
+    codec.reset_stats()
+    n = codec.decompress_device(src.data_ptr(), src.numel(), dst.data_ptr(), dst.numel())
+    assert n == data.size and bytes(dst.cpu().numpy()) == data.tobytes()
+    assert codec.stat(4) > 0 and codec.stat(5) > 0
