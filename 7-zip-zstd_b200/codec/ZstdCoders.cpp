@@ -1,0 +1,290 @@
+// ZstdCoders.cpp -- NCompress::NZSTD::CEncoder / CDecoder for method 4F71101 on top of the
+// b200z C ABI, plus the codec-module exports.  Host-side mirror of the reference wrappers:
+//   CPP/7zip/Compress/ZstdEncoder.{h,cpp}  (props :51-229, 5-byte header :17-32/:245, Code :250-461)
+//   CPP/7zip/Compress/ZstdDecoder.{h,cpp}  (SetDecoderProperties2 :32-49, CodeSpec :66-173)
+//   CPP/7zip/Compress/ZstdRegister.cpp:13-17, Compress/CodecExports.cpp:153-378 (module exports)
+// Same interface sets, property semantics, header bytes and HRESULT mapping; below them the
+// stream is cut into batches of whole frames and handed to the GPU engine (b200z_zstd_*_host).
+//
+// Build: g++ -std=c++17 -O2 -fPIC -shared ZstdCoders.cpp -I../../include -L.. -lb200z -o ../libb200z_7z.so
+#include <atomic>
+#include <new>
+#include <vector>
+#include "b2z_7zip_abi.h"
+#include "../../include/b200z.h"
+
+namespace {
+
+const uint64_t kZstdMethodId = 0x4F71101;
+const uint32_t kZ7Major = 26, kZ7Minor = 1;                // module version reported to the host (C/7zVersion.h)
+const Byte kZstdVerMajor = 1, kZstdVerMinor = 5;           // header bytes (ZstdEncoder.h:17-32)
+const uint32_t kFastLevInc = 32, kUltimateLev = 128;       // ICoder.h:163-166
+
+HRESULT hr_from_b200z(int rc) {
+    switch (rc) {
+    case B200Z_OK: return S_OK;
+    case B200Z_E_MEMORY: return E_OUTOFMEMORY;
+    case B200Z_E_PARAM: return E_INVALIDARG;
+    case B200Z_E_CORRUPT: case B200Z_E_CHECKSUM: return S_FALSE;      // data error (ZstdDecoder.cpp:115-130)
+    case B200Z_E_UNSUPPORTED: return E_NOTIMPL;
+    default: return E_FAIL;                                           // incl. no device: there is no CPU fallback
+    }
+}
+
+HRESULT read_stream(ISequentialInStream* s, void* data, size_t* size) {   // StreamUtils.cpp:54 semantics
+    size_t want = *size; *size = 0;
+    while (want) {
+        UInt32 cur = want < (1u << 30) ? (UInt32)want : (1u << 30), got = 0;
+        HRESULT r = s->Read(data, cur, &got);
+        *size += got; data = (Byte*)data + got; want -= got;
+        if (r != S_OK) return r;
+        if (got == 0) return S_OK;
+    }
+    return S_OK;
+}
+HRESULT write_stream(ISequentialOutStream* s, const void* data, size_t size) {   // StreamUtils.cpp:87
+    while (size) {
+        UInt32 cur = size < (1u << 30) ? (UInt32)size : (1u << 30), done = 0;
+        HRESULT r = s->Write(data, cur, &done);
+        data = (const Byte*)data + done; size -= done;
+        if (r != S_OK) return r;
+        if (done == 0) return E_FAIL;
+    }
+    return S_OK;
+}
+
+struct PinnedBuf {                                          // pinned host staging (grown on demand)
+    void* p = nullptr; size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        void* q = nullptr;
+        if (b200z_host_alloc_pinned(&q, n) != 0) return false;
+        if (p) { memcpy(q, p, cap); b200z_host_free_pinned(p); }
+        p = q; cap = n; return true;
+    }
+    ~PinnedBuf() { if (p) b200z_host_free_pinned(p); }
+};
+
+template <class T> struct RefCounted : T {
+    std::atomic<UInt32> refs{0};
+    UInt32 AddRef() override { return ++refs; }
+    UInt32 Release() override { UInt32 r = --refs; if (r == 0) delete this; return r; }
+    virtual ~RefCounted() {}
+};
+
+// one C++ object exposing several COM-style interfaces: a small aggregate with inner facets
+struct CoderBase {
+    b200z_ctx* ctx = nullptr;
+    HRESULT ensure_ctx() {
+        if (ctx) return S_OK;
+        int dev = 0;
+        if (const char* e = getenv("B200Z_DEVICE")) dev = atoi(e);      // device selection without a new PROPID
+        return hr_from_b200z(b200z_create(&ctx, dev));
+    }
+    ~CoderBase() { if (ctx) b200z_destroy(ctx); }
+};
+
+// ------------------------------------------------------------------ encoder
+class CEncoder final : public ICompressCoder, public ICompressSetCoderMt, public ICompressSetCoderProperties,
+                       public ICompressSetCoderPropertiesOpt, public ICompressWriteCoderProperties, CoderBase {
+    std::atomic<UInt32> refs_{0};
+    Byte props_[5] = { kZstdVerMajor, kZstdVerMinor, 3, 0, 0 };
+    int level_ = 3; bool max_ = false; UInt32 numThreads_ = 1;
+    int windowLog_ = -1, hashLog_ = -1, chainLog_ = -1;
+    PinnedBuf in_, out_;
+public:
+    UInt64 processedIn = 0, processedOut = 0;
+    HRESULT QueryInterface(const GUID& iid, void** out) override {
+        *out = nullptr;
+        if (iid == kIID_IUnknown || iid == b2z_iid(4, kIID_Coder)) *out = static_cast<ICompressCoder*>(this);
+        else if (iid == b2z_iid(4, kIID_SetMt)) *out = static_cast<ICompressSetCoderMt*>(this);
+        else if (iid == b2z_iid(4, kIID_SetProps)) *out = static_cast<ICompressSetCoderProperties*>(this);
+        else if (iid == b2z_iid(4, kIID_SetPropsOpt)) *out = static_cast<ICompressSetCoderPropertiesOpt*>(this);
+        else if (iid == b2z_iid(4, kIID_WriteProps)) *out = static_cast<ICompressWriteCoderProperties*>(this);
+        else return E_NOINTERFACE;
+        ++refs_; return S_OK;
+    }
+    UInt32 AddRef() override { return ++refs_; }
+    UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
+
+    HRESULT SetNumberOfThreads(UInt32 n) override {            // ZstdEncoder.cpp:463-474: clamp 1..256
+        numThreads_ = n < 1 ? 1 : (n > 256 ? 256 : n); return S_OK;
+    }
+    HRESULT SetCoderProperties(const PROPID* ids, const PROPVARIANT* pv, UInt32 n) override {
+        props_[0] = kZstdVerMajor; props_[1] = kZstdVerMinor; props_[2] = 3; props_[3] = props_[4] = 0;
+        for (UInt32 i = 0; i < n; i++) {
+            UInt32 v = pv[i].ulVal;
+            switch (ids[i]) {
+            case NCoderPropID::kNumThreads: SetNumberOfThreads(v); break;
+            case NCoderPropID::kAdvMax:
+                if (!v) break;
+                max_ = true; level_ = 22; props_[2] = (Byte)kUltimateLev; break;
+            case NCoderPropID::kLevel:
+                if (v < 1) v = 1;
+                if (v > 22) {
+                    if (v > kFastLevInc && v != kUltimateLev) { v -= kFastLevInc; goto fast; }   // fast-level inverter
+                    if (v == kUltimateLev) max_ = true;
+                    v = 22;
+                }
+                level_ = (int)v; props_[2] = (Byte)(max_ ? kUltimateLev : v); break;
+            case NCoderPropID::kFast:
+            fast:
+                if (max_) break;
+                if (v < 1) v = 1; if (v > 64) v = 64;
+                level_ = -(int)v; props_[2] = (Byte)(v + kFastLevInc); break;
+            case NCoderPropID::kLong: windowLog_ = v == 0 ? 27 : (int)(v < 10 ? 10 : (v > 31 ? 31 : v)); break;
+            case NCoderPropID::kWindowLog: if (v < 10 || v > 31) return E_INVALIDARG; windowLog_ = (int)v; break;
+            case NCoderPropID::kHashLog: if (v < 6 || v > 30) return E_INVALIDARG; hashLog_ = (int)v; break;
+            case NCoderPropID::kChainLog: if (v < 6 || v > 30) return E_INVALIDARG; chainLog_ = (int)v; break;
+            case NCoderPropID::kStrategy: case NCoderPropID::kSearchLog: case NCoderPropID::kMinMatch: case NCoderPropID::kTargetLen:
+            case NCoderPropID::kOverlapLog: case NCoderPropID::kLdmHashLog: case NCoderPropID::kLdmSearchLength:
+            case NCoderPropID::kLdmBucketSizeLog: case NCoderPropID::kLdmHashRateLog:
+                break;                                        // accepted; the GPU parser has no equivalent knob yet
+            default: break;
+            }
+        }
+        return S_OK;
+    }
+    HRESULT SetCoderPropertiesOpt(const PROPID*, const PROPVARIANT*, UInt32) override { return S_OK; }   // kExpectedDataSize: not needed
+    HRESULT WriteCoderProperties(ISequentialOutStream* out) override { return write_stream(out, props_, 5); }
+
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64*, ICompressProgressInfo* progress) override {
+        processedIn = processedOut = 0;
+        HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
+        b200z_set_param(ctx, B200Z_P_LEVEL, level_ < 1 ? 1 : level_);
+        b200z_set_param(ctx, B200Z_P_FLAGS, 1);               // mcmilk MT frame convention: size hint before each frame
+        if (hashLog_ >= 10 && hashLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_L, hashLog_);
+        if (chainLog_ >= 10 && chainLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_S, chainLog_);
+        if (windowLog_ >= 17) { int64_t fl = 0; b200z_get_param(ctx, B200Z_P_FRAMELOG, &fl); b200z_set_param(ctx, B200Z_P_WINDOWLOG, windowLog_ < fl ? windowLog_ : fl); }
+        // batches of whole frames: 256 MiB of input per GPU pass (ring of pinned host memory)
+        const size_t batch = (size_t)256 << 20;
+        if (!in_.reserve(batch) || !out_.reserve(b200z_zstd_compress_bound(ctx, batch))) return E_OUTOFMEMORY;
+        bool wroteAny = false;
+        for (;;) {
+            size_t got = batch;
+            hr = read_stream(inS, in_.p, &got);
+            if (hr != S_OK) return hr;
+            if (got == 0 && wroteAny) break;
+            size_t produced = 0;
+            int rc = b200z_zstd_compress_host(ctx, in_.p, got, out_.p, out_.cap, &produced);
+            if (rc) return hr_from_b200z(rc);
+            hr = write_stream(outS, out_.p, produced);
+            if (hr != S_OK) return hr;
+            wroteAny = true;
+            processedIn += got; processedOut += produced;
+            if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }   // E_ABORT on user break
+            if (got < batch) break;
+        }
+        return S_OK;
+    }
+};
+
+// ------------------------------------------------------------------ decoder
+class CDecoder final : public ICompressCoder, public ICompressSetDecoderProperties2, public ICompressSetCoderMt, CoderBase {
+    std::atomic<UInt32> refs_{0};
+    std::vector<Byte> in_;
+    PinnedBuf out_;
+public:
+    UInt64 processedIn = 0, processedOut = 0;
+    HRESULT QueryInterface(const GUID& iid, void** out) override {
+        *out = nullptr;
+        if (iid == kIID_IUnknown || iid == b2z_iid(4, kIID_Coder)) *out = static_cast<ICompressCoder*>(this);
+        else if (iid == b2z_iid(4, kIID_SetDecProps2)) *out = static_cast<ICompressSetDecoderProperties2*>(this);
+        else if (iid == b2z_iid(4, kIID_SetMt)) *out = static_cast<ICompressSetCoderMt*>(this);
+        else return E_NOINTERFACE;
+        ++refs_; return S_OK;
+    }
+    UInt32 AddRef() override { return ++refs_; }
+    UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
+    HRESULT SetDecoderProperties2(const Byte*, UInt32 size) override {   // ZstdDecoder.cpp:32-49: 1/3/5 bytes, content ignored
+        return (size == 1 || size == 3 || size == 5) ? S_OK : E_NOTIMPL;
+    }
+    HRESULT SetNumberOfThreads(UInt32) override { return S_OK; }         // no-op, as in ZstdDecoder.cpp:260-263
+
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
+        processedIn = processedOut = 0;
+        HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
+        // the frames of one Code() input are decoded together: read the packed stream to its end
+        in_.clear();
+        for (;;) {
+            const size_t chunk = (size_t)8 << 20, at = in_.size();
+            in_.resize(at + chunk);
+            size_t got = chunk;
+            hr = read_stream(inS, in_.data() + at, &got);
+            in_.resize(at + got);
+            if (hr != S_OK) return hr;
+            if (got < chunk) break;
+        }
+        if (in_.empty()) return S_OK;
+        uint64_t content = 0; uint32_t frames = 0;
+        int rc = b200z_zstd_frame_info(in_.data(), in_.size(), &content, &frames);
+        if (rc == B200Z_E_CORRUPT) return S_FALSE;
+        size_t cap;
+        if (rc == 0) cap = (size_t)content;
+        else if (outSize) cap = (size_t)*outSize;                        // 7z folders pass the unpacked size
+        else cap = in_.size() * 64 + ((size_t)1 << 20);                  // undeclared size: generous bound, grown on demand
+        for (;;) {
+            if (!out_.reserve(cap + 64)) return E_OUTOFMEMORY;
+            size_t produced = 0;
+            rc = b200z_zstd_decompress_host(ctx, in_.data(), in_.size(), out_.p, cap, &produced);
+            if (rc == B200Z_E_DSTSIZE && !(outSize || content)) { cap *= 4; continue; }
+            if (rc) return hr_from_b200z(rc);
+            processedIn = in_.size(); processedOut = produced;
+            hr = write_stream(outS, out_.p, produced);
+            if (hr != S_OK) return hr;
+            break;
+        }
+        if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
+        return S_OK;
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ module exports (CodecExports.cpp:153-378)
+extern "C" {
+
+HRESULT GetNumberOfMethods(UInt32* n) { *n = 1; return S_OK; }
+
+HRESULT GetMethodProperty(UInt32 index, PROPID propID, PROPVARIANT* value) {
+    memset(value, 0, sizeof(*value));
+    if (index != 0) return E_INVALIDARG;
+    switch (propID) {
+    case NMethodPropID::kID: value->vt = VT_UI8; value->uhVal = kZstdMethodId; break;
+    case NMethodPropID::kName: value->bstrVal = b2z_alloc_bstr_ascii("ZSTD"); if (!value->bstrVal) return E_OUTOFMEMORY; value->vt = VT_BSTR; break;
+    case NMethodPropID::kDecoder: case NMethodPropID::kEncoder: {
+        const GUID g = b2z_clsid(propID == NMethodPropID::kEncoder, kZstdMethodId);
+        value->bstrVal = b2z_alloc_bstr_bytes(&g, sizeof(g)); if (!value->bstrVal) return E_OUTOFMEMORY; value->vt = VT_BSTR; break; }
+    case NMethodPropID::kDecoderIsAssigned: case NMethodPropID::kEncoderIsAssigned: value->vt = VT_BOOL; value->boolVal = -1; break;
+    case NMethodPropID::kIsFilter: value->vt = VT_BOOL; value->boolVal = 0; break;
+    default: break;                                            // kPackStreams: 1 stream -> left empty, as the reference does
+    }
+    return S_OK;
+}
+
+static HRESULT create_coder(bool encoder, const GUID* iid, void** out) {
+    *out = nullptr;
+    if (!(*iid == b2z_iid(4, kIID_Coder))) return E_NOINTERFACE;
+    try {
+        ICompressCoder* c = encoder ? static_cast<ICompressCoder*>(new CEncoder()) : static_cast<ICompressCoder*>(new CDecoder());
+        c->AddRef(); *out = c; return S_OK;
+    } catch (...) { return E_OUTOFMEMORY; }
+}
+HRESULT CreateEncoder(UInt32 index, const GUID* iid, void** out) { return index == 0 ? create_coder(true, iid, out) : E_INVALIDARG; }
+HRESULT CreateDecoder(UInt32 index, const GUID* iid, void** out) { return index == 0 ? create_coder(false, iid, out) : E_INVALIDARG; }
+
+HRESULT CreateObject(const GUID* clsid, const GUID* iid, void** out) {
+    *out = nullptr;
+    if (*clsid == b2z_clsid(true, kZstdMethodId)) return create_coder(true, iid, out);
+    if (*clsid == b2z_clsid(false, kZstdMethodId)) return create_coder(false, iid, out);
+    return CLASS_E_CLASSNOTAVAILABLE;
+}
+
+HRESULT GetModuleProp(PROPID propID, PROPVARIANT* value) {
+    memset(value, 0, sizeof(*value));
+    if (propID == NModulePropID::kInterfaceType) { value->vt = VT_UI4; value->ulVal = 0; }          // IUnknown without virtual destructor
+    else if (propID == NModulePropID::kVersion) { value->vt = VT_UI4; value->ulVal = (kZ7Major << 16) | kZ7Minor; }
+    return S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// coder_roundtrip.cpp -- drives libb200z_7z.so exactly as 7-Zip's codec loader does
+// (CPP/7zip/UI/Common/LoadCodecs.cpp:279-303,528-563: dlsym the exports, GetModuleProp check,
+// GetMethodProperty, CreateEncoder/CreateDecoder by index, then ICompressCoder::Code()).
+// usage: coder_roundtrip <lib.so> <input file> <packed output file> [level]      (needs a GPU)
+//        coder_roundtrip <lib.so> --exports                                      (no GPU needed)
+#include <dlfcn.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../7-zip-zstd_b200/codec/b2z_7zip_abi.h"
+
+struct MemIn final : ISequentialInStream {
+    const std::vector<Byte>& d; size_t pos = 0; UInt32 refs = 1;
+    explicit MemIn(const std::vector<Byte>& v) : d(v) {}
+    HRESULT QueryInterface(const GUID&, void** o) override { *o = nullptr; return E_NOINTERFACE; }
+    UInt32 AddRef() override { return ++refs; }
+    UInt32 Release() override { return --refs; }
+    HRESULT Read(void* data, UInt32 size, UInt32* processed) override {
+        size_t n = d.size() - pos; if (n > size) n = size; if (n > 100000) n = 100000 + (pos % 7777);   // short reads on purpose
+        if (n > d.size() - pos) n = d.size() - pos;
+        memcpy(data, d.data() + pos, n); pos += n; if (processed) *processed = (UInt32)n; return S_OK;
+    }
+};
+struct MemOut final : ISequentialOutStream {
+    std::vector<Byte> d; UInt32 refs = 1;
+    HRESULT QueryInterface(const GUID&, void** o) override { *o = nullptr; return E_NOINTERFACE; }
+    UInt32 AddRef() override { return ++refs; }
+    UInt32 Release() override { return --refs; }
+    HRESULT Write(const void* data, UInt32 size, UInt32* processed) override {
+        d.insert(d.end(), (const Byte*)data, (const Byte*)data + size); if (processed) *processed = size; return S_OK;
+    }
+};
+struct Progress final : ICompressProgressInfo {
+    int calls = 0; UInt32 refs = 1;
+    HRESULT QueryInterface(const GUID&, void** o) override { *o = nullptr; return E_NOINTERFACE; }
+    UInt32 AddRef() override { return ++refs; }
+    UInt32 Release() override { return --refs; }
+    HRESULT SetRatioInfo(const UInt64*, const UInt64*) override { calls++; return S_OK; }
+};
+
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    if (argc < 3) return 2;
+    void* h = dlopen(argv[1], RTLD_NOW);
+    if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 1; }
+    auto GetNumberOfMethods = (HRESULT(*)(UInt32*))dlsym(h, "GetNumberOfMethods");
+    auto GetMethodProperty = (HRESULT(*)(UInt32, PROPID, PROPVARIANT*))dlsym(h, "GetMethodProperty");
+    auto CreateEncoder = (HRESULT(*)(UInt32, const GUID*, void**))dlsym(h, "CreateEncoder");
+    auto CreateDecoder = (HRESULT(*)(UInt32, const GUID*, void**))dlsym(h, "CreateDecoder");
+    auto CreateObject = (HRESULT(*)(const GUID*, const GUID*, void**))dlsym(h, "CreateObject");
+    auto GetModuleProp = (HRESULT(*)(PROPID, PROPVARIANT*))dlsym(h, "GetModuleProp");
+    CHECK(GetNumberOfMethods && GetMethodProperty && CreateEncoder && CreateDecoder && CreateObject && GetModuleProp);
+    UInt32 n = 0; CHECK(GetNumberOfMethods(&n) == S_OK && n == 1);
+    PROPVARIANT v;
+    CHECK(GetModuleProp(NModulePropID::kInterfaceType, &v) == S_OK && v.vt == VT_UI4 && v.ulVal == 0);
+    CHECK(GetModuleProp(NModulePropID::kVersion, &v) == S_OK && v.ulVal == ((26u << 16) | 1u));
+    CHECK(GetMethodProperty(0, NMethodPropID::kID, &v) == S_OK && v.vt == VT_UI8 && v.uhVal == 0x4F71101);
+    CHECK(GetMethodProperty(0, NMethodPropID::kName, &v) == S_OK && v.vt == VT_BSTR && v.bstrVal[0] == L'Z' && v.bstrVal[3] == L'D' && v.bstrVal[4] == 0);
+    CHECK(GetMethodProperty(0, NMethodPropID::kEncoder, &v) == S_OK && v.vt == VT_BSTR);
+    { GUID g; memcpy(&g, v.bstrVal, 16); CHECK(g == b2z_clsid(true, 0x4F71101)); uint32_t len; memcpy(&len, (char*)v.bstrVal - 4, 4); CHECK(len == 16); }
+    CHECK(GetMethodProperty(0, NMethodPropID::kIsFilter, &v) == S_OK && v.vt == VT_BOOL && v.boolVal == 0);
+    const GUID iidCoder = b2z_iid(4, kIID_Coder);
+    void* obj = nullptr;
+    CHECK(CreateEncoder(0, &iidCoder, &obj) == S_OK && obj);
+    ICompressCoder* enc = (ICompressCoder*)obj;
+    ICompressSetCoderProperties* sp = nullptr; ICompressWriteCoderProperties* wp = nullptr; ICompressSetCoderMt* mt = nullptr;
+    CHECK(enc->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&sp) == S_OK);
+    CHECK(enc->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&wp) == S_OK);
+    CHECK(enc->QueryInterface(b2z_iid(4, kIID_SetMt), (void**)&mt) == S_OK);
+    void* bogus = nullptr; CHECK(enc->QueryInterface(b2z_iid(4, 0x99), &bogus) == E_NOINTERFACE);
+    const int level = argc > 4 ? atoi(argv[4]) : 3;
+    PROPID ids[2] = { NCoderPropID::kLevel, NCoderPropID::kNumThreads }; PROPVARIANT pv[2]; memset(pv, 0, sizeof(pv));
+    pv[0].vt = VT_UI4; pv[0].ulVal = (UInt32)level; pv[1].vt = VT_UI4; pv[1].ulVal = 8;
+    CHECK(sp->SetCoderProperties(ids, pv, 2) == S_OK);
+    MemOut hdr; CHECK(wp->WriteCoderProperties(&hdr) == S_OK && hdr.d.size() == 5 && hdr.d[0] == 1 && hdr.d[1] == 5 && hdr.d[2] == (Byte)level);
+    // fast-level inverter and max (ZstdEncoder.cpp:81-121)
+    { PROPID i2[1] = { NCoderPropID::kFast }; PROPVARIANT p2[1]; memset(p2, 0, sizeof(p2)); p2[0].vt = VT_UI4; p2[0].ulVal = 5;
+      void* o2 = nullptr; CHECK(CreateObject(new GUID(b2z_clsid(true, 0x4F71101)), &iidCoder, &o2) == S_OK);
+      ICompressCoder* e2 = (ICompressCoder*)o2; ICompressSetCoderProperties* s2; ICompressWriteCoderProperties* w2;
+      e2->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&s2); e2->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&w2);
+      CHECK(s2->SetCoderProperties(i2, p2, 1) == S_OK); MemOut h2; w2->WriteCoderProperties(&h2); CHECK(h2.d[2] == 32 + 5);
+      s2->Release(); w2->Release(); CHECK(e2->Release() == 0); }
+    if (std::string(argv[2]) == "--exports") { printf("exports ok\n"); return 0; }
+
+    std::vector<Byte> input;
+    { FILE* f = fopen(argv[2], "rb"); CHECK(f); Byte buf[1 << 16]; size_t k; while ((k = fread(buf, 1, sizeof(buf), f)) > 0) input.insert(input.end(), buf, buf + k); fclose(f); }
+    MemIn in(input); MemOut packed; Progress prog;
+    HRESULT r = enc->Code(&in, &packed, nullptr, nullptr, &prog);
+    if (r != S_OK) { fprintf(stderr, "encoder Code() = 0x%08x\n", (unsigned)r); return 1; }
+    CHECK(prog.calls >= 1);
+    CHECK(CreateDecoder(0, &iidCoder, &obj) == S_OK);
+    ICompressCoder* dec = (ICompressCoder*)obj; ICompressSetDecoderProperties2* dp = nullptr;
+    CHECK(dec->QueryInterface(b2z_iid(4, kIID_SetDecProps2), (void**)&dp) == S_OK);
+    CHECK(dp->SetDecoderProperties2(hdr.d.data(), 5) == S_OK && dp->SetDecoderProperties2(hdr.d.data(), 2) == E_NOTIMPL);
+    MemIn pin(packed.d); MemOut back; UInt64 outSize = input.size();
+    r = dec->Code(&pin, &back, nullptr, &outSize, nullptr);
+    if (r != S_OK) { fprintf(stderr, "decoder Code() = 0x%08x\n", (unsigned)r); return 1; }
+    CHECK(back.d == input);
+    // corrupt stream -> S_FALSE (data error)
+    { std::vector<Byte> bad(packed.d.begin(), packed.d.begin() + packed.d.size() / 2); MemIn bi(bad); MemOut bo; CHECK(dec->Code(&bi, &bo, nullptr, &outSize, nullptr) == S_FALSE); }
+    { FILE* f = fopen(argv[3], "wb"); CHECK(f); fwrite(packed.d.data(), 1, packed.d.size(), f); fclose(f); }
+    sp->Release(); wp->Release(); mt->Release(); dp->Release();
+    CHECK(enc->Release() == 0 && dec->Release() == 0);
+    printf("roundtrip ok: %zu -> %zu bytes\n", input.size(), packed.d.size());
+    return 0;
+}

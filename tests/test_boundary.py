@@ -1,0 +1,64 @@
+"""The drop-in boundary: the C-ABI library exports every symbol include/b200z.h declares, the
+7-Zip codec module exports the loader's entry points with the reference's method properties
+(CPU, no compute), and -- on a GPU -- ICompressCoder::Code() round-trips through the module and
+the reference decoder accepts what it wrote."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import helpers
+
+ROOT = helpers.ROOT
+PKG = os.path.join(ROOT, "7-zip-zstd_b200")
+
+
+def test_c_abi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "b200z.h")).read()
+    declared = set(re.findall(r"\b(b200z_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(os.path.join(PKG, "libb200z.so"))          # loading needs libcudart only, no GPU
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_device_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.B200zError):
+        pkg.Codec(0)                                                # no CPU fallback
+
+
+def test_codec_module_exports():
+    out = subprocess.run([os.path.join(PKG, "build", "coder_roundtrip"), os.path.join(PKG, "libb200z_7z.so"), "--exports", "x"],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "exports ok" in out.stdout, out.stderr
+
+
+def test_frame_info_host_only():
+    lib = ctypes.CDLL(os.path.join(PKG, "libb200z.so"))
+    lib.b200z_zstd_frame_info.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
+    comp = helpers.oracle_compress(b"abc" * 100000, frameLog=17, windowLog=17, flags=1)
+    cs, nf = ctypes.c_uint64(), ctypes.c_uint32()
+    buf = ctypes.create_string_buffer(comp, len(comp))
+    assert lib.b200z_zstd_frame_info(buf, len(comp), ctypes.byref(cs), ctypes.byref(nf)) == 0
+    assert cs.value == 300000 and nf.value == 3
+    assert lib.b200z_zstd_frame_info(buf, len(comp) - 5, ctypes.byref(cs), ctypes.byref(nf)) == -5
+
+
+@pytest.mark.gpu
+def test_icompresscoder_roundtrip(pkg, tmp_path):
+    data = pkg.corpus.g2(5 * (1 << 20) + 999).tobytes() + bytes(300000)
+    src = tmp_path / "in.bin"; packed = tmp_path / "packed.zst"
+    src.write_bytes(data)
+    out = subprocess.run([os.path.join(PKG, "build", "coder_roundtrip"), os.path.join(PKG, "libb200z_7z.so"), str(src), str(packed), "3"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "roundtrip ok" in out.stdout, out.stderr + out.stdout
+    comp = packed.read_bytes()
+    assert comp[:4] == b"\x50\x2a\x4d\x18"                            # mcmilk MT size hint in front of the first frame
+    assert helpers.oracle_decompress(comp, len(data)) == data
+    if helpers.ref_available():
+        assert helpers.ref_decompress(comp, len(data)) == data
