@@ -1,21 +1,18 @@
-import sys, time, os
-sys.path.insert(0, os.getcwd())
-import torch, numpy as np
+"""Experiment driver: stage timings for different table sizes / frame sizes (device resident)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch
 import __graft_entry__ as ge
 pkg = ge.load_package()
 n = int(sys.argv[1]) << 20
-t=time.time(); data = pkg.corpus.g2(n); print('gen s', time.time()-t, 'cores', os.cpu_count())
-src = torch.from_numpy(data).cuda()
-c = pkg.Codec(0)
-dst = torch.empty(c.compress_bound(n) + (n >> 10) + (1<<20), dtype=torch.uint8, device="cuda")
-for it in range(3):
-    c.reset_stats(); torch.cuda.synchronize(); t=time.time()
-    m = c.compress_device(src.data_ptr(), n, dst.data_ptr(), dst.numel())
-    dt=time.time()-t
-    print(f'iter {it}: {n/1e6/dt:.0f} MB/s wall; match {c.stat(1):.2f} ms entropy {c.stat(2):.2f} ms assemble {c.stat(3):.2f} ms; ratio {n/m:.4f}')
-for fl in (21, 20, 19, 18):
-    c2 = pkg.Codec(0, frame_log=fl)
+src = torch.from_numpy(pkg.corpus.g2(n)).cuda()
+dst = torch.empty(n + (n >> 6) + (1 << 20), dtype=torch.uint8, device="cuda")
+back = torch.empty(n, dtype=torch.uint8, device="cuda")
+for spec in sys.argv[2:]:
+    fl, hl, hs = (int(x) for x in spec.split(","))
+    c = pkg.Codec(0, frame_log=fl, hash_log_l=hl, hash_log_s=hs)
     for it in range(2):
-        c2.reset_stats(); m = c2.compress_device(src.data_ptr(), n, dst.data_ptr(), dst.numel())
-    print(f'frameLog {fl}: match {c2.stat(1):.2f} ms entropy {c2.stat(2):.2f} ms assemble {c2.stat(3):.2f}; ratio {n/m:.4f}')
-    c2.close()
+        c.reset_stats(); m = c.compress_device(src.data_ptr(), n, dst.data_ptr(), dst.numel())
+    k = c.decompress_device(dst.data_ptr(), m, back.data_ptr(), n)
+    print(f"fl={fl} hl={hl} hs={hs}: match {c.stat(1):.1f} ms entropy {c.stat(2):.1f} ms | dec entropy {c.stat(4):.1f} exec {c.stat(5):.1f} ms | ratio {n/m:.4f} ok={k==n}")
+    c.close()
