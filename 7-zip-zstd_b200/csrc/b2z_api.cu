@@ -29,7 +29,7 @@ int b200z_create(b200z_ctx** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->smCount = (uint32_t)prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
-    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
     ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 0;
     *out = ctx;
@@ -44,7 +44,7 @@ void b200z_destroy(b200z_ctx* ctx) {
                      &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
-    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -30,7 +30,7 @@ struct b200z_ctx {
     uint32_t smCount = 148;
     Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut;
     Arena decScratch[8];
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
     double stat[16] = {0};
     char err[256] = {0};
 };

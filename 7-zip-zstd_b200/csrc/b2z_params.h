@@ -10,7 +10,7 @@
 #define B2Z_HD static inline
 #endif
 
-#define B2Z_DEF_FRAMELOG   22      /* independent zstd frame = 4 MiB of input                */
+#define B2Z_DEF_FRAMELOG   20      /* independent zstd frame = 1 MiB of input                */
 #define B2Z_DEF_HASHLOG_L  17      /* long (8-byte) hash table entries  (clevels.h:31 H17)   */
 #define B2Z_DEF_HASHLOG_S  16      /* short (5-byte) hash table entries (clevels.h:31 C16)   */
 #define B2Z_STEP           32u     /* positions per warp step                                */

@@ -220,7 +220,9 @@ struct BwdBits {                                // backward stream with end mark
 struct SeqEnt { uint32_t base; uint8_t nbAdd, nbBits; uint16_t next; };
 struct DecWS {
     uint16_t huf[2048];          // symbol | nbBits << 8
-    SeqEnt   tab[3][512];        // LL, OF, ML
+    SeqEnt   tabs[1280];         // LL [0,512), OF [512,768), ML [768,1280)
+    __device__ __forceinline__ SeqEnt* tab(int t) { return tabs + (t == 0 ? 0 : (t == 1 ? 512 : 768)); }
+    __device__ __forceinline__ const SeqEnt* tab(int t) const { return tabs + (t == 0 ? 0 : (t == 1 ? 512 : 768)); }
     uint32_t tabLog[3];
     uint32_t hufBits;
     int16_t  norm[256];
@@ -280,7 +282,7 @@ __device__ bool build_seq_table(DecWS* ws, int t, const int16_t* norm, uint32_t 
         if (t == 0) { e.base = k_LL_base[s]; e.nbAdd = k_LL_bits[s]; }
         else if (t == 2) { e.base = k_ML_base[s]; e.nbAdd = k_ML_bits[s]; }
         else { e.base = 1u << s; e.nbAdd = (uint8_t)s; }
-        ws->tab[t][u] = e;
+        ws->tab(t)[u] = e;
     }
     ws->tabLog[t] = log;
     return true;
@@ -373,15 +375,45 @@ __device__ uint32_t huf_read_table(DecWS* ws, const Src& S, uint64_t off, uint32
     return used;
 }
 
+// Hot-loop reader: a 64-bit container positioned by reload(); after a reload at least 57 bits can be
+// consumed before the next one.  Bits below the stream start read as zero (pos goes negative).
+struct FastBwd {
+    const Src* S; uint64_t base; int64_t pos, cbit; uint64_t cont;
+    __device__ __forceinline__ int init(const Src* s, uint64_t b, uint32_t size) {
+        S = s; base = b;
+        if (!size) return -1;
+        const uint32_t lastByte = S->u8(b + size - 1);
+        if (!lastByte) return -1;
+        pos = (int64_t)(size - 1) * 8 + (int64_t)highbit32(lastByte);
+        reload();
+        return 0;
+    }
+    __device__ __forceinline__ void reload() {
+        cbit = ((pos + 7) & ~7ll) - 64;
+        if (cbit >= 0) cont = S->le64(base + (uint64_t)(cbit >> 3));
+        else if (cbit > -64) cont = S->le64(base) << (uint32_t)(-cbit);
+        else cont = 0;
+    }
+    __device__ __forceinline__ uint32_t read(uint32_t n) {          // n <= 32; caller keeps <= 57 bits between reloads
+        pos -= n;
+        const int64_t sh = pos - cbit;
+        if (n == 0 || sh < 0) return 0;
+        return (uint32_t)(cont >> (uint32_t)sh) & (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
+    }
+};
+
 // one Huffman stream, one lane
 __device__ bool huf_decode_stream(const DecWS* ws, const Src& S, uint64_t off, uint32_t size, uint8_t* dst, uint32_t n) {
-    BwdBits b; if (b.init(&S, off, size)) return false;
+    FastBwd b; if (b.init(&S, off, size)) return false;
     const uint32_t mb = ws->hufBits;
     for (uint32_t i = 0; i < n; i++) {
-        const uint32_t e = ws->huf[b.peek(mb)];
-        dst[i] = (uint8_t)e; b.bitpos -= (e >> 8);
+        if (b.pos - (int64_t)mb < b.cbit) b.reload();
+        const int64_t sh = b.pos - (int64_t)mb - b.cbit;            // >= 0 after the reload unless far below the start
+        const uint32_t idx = sh >= 0 ? ((uint32_t)(b.cont >> (uint32_t)sh) & ((1u << mb) - 1u)) : 0u;
+        const uint32_t e = ws->huf[idx];
+        dst[i] = (uint8_t)e; b.pos -= (e >> 8);
     }
-    return b.bitpos == 0;
+    return b.pos == 0;
 }
 
 // ---------------------------------------------------------------- D1: entropy decode
@@ -466,7 +498,7 @@ zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBl
                         else {
                             SeqEnt e; e.nbBits = 0; e.next = 0;
                             if (t == 0) { e.base = k_LL_base[s]; e.nbAdd = k_LL_bits[s]; } else if (t == 2) { e.base = k_ML_base[s]; e.nbAdd = k_ML_bits[s]; } else { e.base = 1u << s; e.nbAdd = (uint8_t)s; }
-                            ws->tab[t][0] = e; ws->tabLog[t] = 0; used = 1;
+                            ws->tab(t)[0] = e; ws->tabLog[t] = 0; used = 1;
                         }
                     } else {
                         uint32_t ms = maxSymT[t], lg;
@@ -476,25 +508,30 @@ zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBl
                     if (ownMode != 3) { if (used > bsLeft) err = B2Z_DERR_CORRUPT; else { bsOff += used; bsLeft -= used; } }
                 }
                 if (!err) {
-                    BwdBits b;
+                    FastBwd b;
                     if (b.init(&S, bsOff, bsLeft)) err = B2Z_DERR_CORRUPT;
                     else {
-                        uint32_t sL = b.read(ws->tabLog[0]), sO = b.read(ws->tabLog[1]), sM = b.read(ws->tabLog[2]);
-                        if (b.overflow) err = B2Z_DERR_CORRUPT;
+                        uint32_t sL = b.read(ws->tabLog[0]), sO = b.read(ws->tabLog[1]), sM = b.read(ws->tabLog[2]);   // <= 26 bits
+                        if (b.pos < 0) err = B2Z_DERR_CORRUPT;
                         uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
                         uint32_t litUsed = 0, total = 0;
                         for (uint32_t i = 0; i < nbSeq && !err; i++) {
-                            const SeqEnt eL = ws->tab[0][sL], eO = ws->tab[1][sO], eM = ws->tab[2][sM];
+                            const SeqEnt eL = ws->tabs[sL], eO = ws->tabs[512 + sO], eM = ws->tabs[768 + sM];
                             if (eO.nbAdd > 30) { err = B2Z_DERR_UNSUPPORTED; break; }
+                            b.reload();
                             const uint32_t ob = eO.base + b.read(eO.nbAdd);
+                            if ((uint32_t)eO.nbAdd + eM.nbAdd + eL.nbAdd > 56u) b.reload();
                             const uint32_t ml = eM.base + b.read(eM.nbAdd);
                             const uint32_t ll = eL.base + b.read(eL.nbAdd);
-                            if (i + 1 < nbSeq) { sL = eL.next + b.read(eL.nbBits); sM = eM.next + b.read(eM.nbBits); sO = eO.next + b.read(eO.nbBits); }
+                            if (i + 1 < nbSeq) {
+                                if ((uint32_t)eO.nbAdd + eM.nbAdd + eL.nbAdd > 30u) b.reload();                 // + <= 26 state bits
+                                sL = eL.next + b.read(eL.nbBits); sM = eM.next + b.read(eM.nbBits); sO = eO.next + b.read(eO.nbBits);
+                            }
                             litUsed += ll; total += ll + ml;
-                            if (b.overflow || litUsed > lh.regen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
+                            if (b.pos < 0 || litUsed > lh.regen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
                             out[i] = SEQ_PACK(ob, ll, ml);
                         }
-                        if (!err && b.bitpos != 0) err = B2Z_DERR_CORRUPT;
+                        if (!err && b.pos != 0) err = B2Z_DERR_CORRUPT;
                         regen = total + (lh.regen - litUsed);
                         if (regen > 131072u) err = B2Z_DERR_CORRUPT;
                     }

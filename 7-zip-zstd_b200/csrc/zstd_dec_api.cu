@@ -86,6 +86,7 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     CU(cudaEventRecord(ctx->ev[0], st));
     launch_zstd_dec_prepass((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, blocks, (uint32_t)blockCap, counts, st);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[3], st));
     DecCounts hc;
     CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -108,7 +109,8 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     CU(cudaStreamSynchronize(st));
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
     float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_DEC_ENTROPY_MS] += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stat[B200Z_S_DEC_PREPASS_MS] += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[1]); ctx->stat[B200Z_S_DEC_ENTROPY_MS] += ms;
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_DEC_EXEC_MS] += ms;
     if (hr.c.status) return dec_status_to_rc(ctx, hr.c.status);
     *dstSize = (size_t)hr.total;

@@ -57,6 +57,7 @@ extern "C" {
 #define B200Z_S_KERNEL_LAUNCHES 6   /* number of kernels launched */
 #define B200Z_S_H2D_BYTES       7
 #define B200Z_S_D2H_BYTES       8
+#define B200Z_S_DEC_PREPASS_MS  9
 
 typedef struct b200z_ctx b200z_ctx;
 

@@ -14,5 +14,5 @@ for spec in sys.argv[2:]:
     for it in range(2):
         c.reset_stats(); m = c.compress_device(src.data_ptr(), n, dst.data_ptr(), dst.numel())
     k = c.decompress_device(dst.data_ptr(), m, back.data_ptr(), n)
-    print(f"fl={fl} hl={hl} hs={hs}: match {c.stat(1):.1f} ms entropy {c.stat(2):.1f} ms | dec entropy {c.stat(4):.1f} exec {c.stat(5):.1f} ms | ratio {n/m:.4f} ok={k==n}")
+    print(f"fl={fl} hl={hl} hs={hs}: match {c.stat(1):.1f} ms entropy {c.stat(2):.1f} ms | dec prepass {c.stat(9):.1f} entropy {c.stat(4):.1f} exec {c.stat(5):.1f} ms | ratio {n/m:.4f} ok={k==n}")
     c.close()
