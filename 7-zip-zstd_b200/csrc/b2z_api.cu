@@ -28,6 +28,10 @@ int b200z_create(b200z_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B200Z_E_NODEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->smCount = (uint32_t)prop.multiProcessorCount;
+    // The match finder's table accesses are random 4-byte reads: ask L2 to fetch 32-byte sectors from DRAM
+    // instead of 64-byte pairs (a hint; B200Z_L2_FETCH overrides it for experiments).
+    { size_t gran = 32; if (const char* e = getenv("B200Z_L2_FETCH")) gran = (size_t)atoi(e);
+      if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
