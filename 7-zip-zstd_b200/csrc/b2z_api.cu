@@ -35,7 +35,7 @@ int b200z_create(b200z_ctx** out, int device) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
-    ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 0;
+    ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1;   // size hints on: lets any decoder (ours included) find frames without walking blocks
     *out = ctx;
     return B200Z_OK;
 }

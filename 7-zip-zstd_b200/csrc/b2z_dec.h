@@ -6,7 +6,7 @@
 namespace b2z {
 
 #define B2Z_DEC_MAXSEQ   65536u      // sequences per block (format max: 128 KiB / 3 < 43691)
-#define B2Z_DEC_WARPS    2           // stage D1: warps (= blocks) per CTA
+#define B2Z_DEC_WARPS    2           // D1: warps (= blocks) per CTA
 
 // error bits (per block / global)
 #define B2Z_DERR_CORRUPT      1u
@@ -19,10 +19,10 @@ struct DecFrame {
     uint64_t dstOff;        // output offset (filled by the layout kernel)
     uint64_t contentSize;   // ~0 if not declared
     uint64_t windowSize;
-    uint64_t regen;         // sum of block sizes (filled by the layout kernel)
+    uint64_t regen;         // D0: end offset of the frame in src; from D2 on: sum of block sizes
     uint32_t firstBlock, nBlocks;
     uint32_t checksum;      // 1 if a 4-byte content checksum follows the last block
-    uint32_t pad;
+    uint32_t pad;           // D0 scratch (frame header bytes)
 };
 
 struct DecBlock {
@@ -41,9 +41,10 @@ struct DecBlock {
 
 struct DecCounts { uint32_t nFrames, nBlocks, status, pad; uint64_t srcUsed; };
 
-// stage D0: frame/block walk (single thread; sequential by format) -> tables + counts
-void launch_zstd_dec_prepass(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap,
-                             DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st);
+// stage D0: frame discovery (1 thread; hops over mcmilk size hints when present), then per-frame block indexing
+void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st);
+void launch_zstd_dec_index_blocks(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames,
+                                  DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st);
 // stage D1: one warp per compressed block: literals (Huffman) + sequences (FSE) into scratch
 void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks,
                              uint8_t* lits, uint64_t* seqs, cudaStream_t st);

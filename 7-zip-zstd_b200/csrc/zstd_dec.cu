@@ -95,11 +95,90 @@ __device__ SeqHdr parse_seq_hdr(const Src& S, uint64_t off, uint32_t avail) {
 }
 
 // ---------------------------------------------------------------- D0: prepass
-__global__ void zstd_dec_prepass_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap,
-                                        DecBlock* blocks, uint32_t blockCap, DecCounts* counts) {
+// Frame discovery is sequential by format (a frame's end is only known by walking its block headers) unless
+// the stream carries mcmilk's 12-byte skippable size hints (magic 0x184D2A50, size 4, payload = size of the
+// following frame; DOC/Methods-Extern.md:91), which our encoder writes when flag bit0 is set: then one thread
+// hops from hint to hint and the per-frame block walks run in parallel (one thread per frame).
+//   D0a (1 thread)      frames[f].srcOff / pad (= end offset, 0 if unknown); walks unhinted frames itself
+//   D0b (thread/frame)  frame header + block count (and end-offset check)
+//   D0c (1 thread)      firstBlock = exclusive scan of the block counts
+//   D0d (thread/frame)  block table entries incl. where each block's entropy tables come from
+struct FrameHdr { uint64_t contentSize, windowSize; uint32_t checksum, hdrBytes, status; };
+__device__ FrameHdr parse_frame_hdr(const Src& S, uint64_t ip, uint64_t srcSize) {
+    FrameHdr h; h.status = 0; h.contentSize = ~0ull; h.windowSize = 0; h.checksum = 0; h.hdrBytes = 0;
+    if (srcSize - ip < 6) { h.status = B2Z_DERR_CORRUPT; return h; }
+    const uint64_t ip0 = ip;
+    const uint32_t fhd = S.u8(ip + 4); ip += 5;
+    const uint32_t fcsFlag = fhd >> 6, single = (fhd >> 5) & 1u, didFlag = fhd & 3u;
+    h.checksum = (fhd >> 2) & 1u;
+    if (fhd & 8u) { h.status = B2Z_DERR_CORRUPT; return h; }
+    if (!single) {
+        const uint32_t wd = S.u8(ip++); const uint32_t wl = 10u + (wd >> 3);
+        if (wl > 31) { h.status = B2Z_DERR_CORRUPT; return h; }
+        h.windowSize = (1ull << wl) + ((1ull << wl) >> 3) * (wd & 7u);
+    }
+    const uint32_t didBytes = didFlag == 3 ? 4u : didFlag;
+    uint32_t did = 0; for (uint32_t i = 0; i < didBytes; i++) did |= S.u8(ip + i) << (8 * i);
+    ip += didBytes;
+    if (did) { h.status = B2Z_DERR_UNSUPPORTED; return h; }
+    const uint32_t fcsBytes = fcsFlag == 0 ? single : (fcsFlag == 1 ? 2u : (fcsFlag == 2 ? 4u : 8u));
+    if (srcSize < ip || srcSize - ip < fcsBytes) { h.status = B2Z_DERR_CORRUPT; return h; }
+    if (fcsBytes) { uint64_t fcs = 0; for (uint32_t i = 0; i < fcsBytes; i++) fcs |= (uint64_t)S.u8(ip + i) << (8 * i); if (fcsBytes == 2) fcs += 256; h.contentSize = fcs; }
+    ip += fcsBytes;
+    if (single) h.windowSize = h.contentSize;
+    if (h.windowSize > (1ull << 30) - 16) { h.status = B2Z_DERR_UNSUPPORTED; return h; }
+    h.hdrBytes = (uint32_t)(ip - ip0);
+    return h;
+}
+
+// Walk the block headers of one frame starting at `ip` (first block header). Returns the status; *nb = blocks,
+// *ipEnd = offset after the last block.  With `out` != null also fills the block entries.
+__device__ uint32_t walk_blocks(const Src& S, uint64_t ip, uint64_t srcSize, uint32_t* nbOut, uint64_t* ipEnd,
+                                DecBlock* out, uint32_t firstBlock, uint32_t frameIdx, uint32_t blockCap) {
+    uint32_t nb = 0; int32_t lastHuf = -1, lastTbl[3] = { -1, -1, -1 };
+    for (;;) {
+        if (srcSize < ip || srcSize - ip < 3) return B2Z_DERR_CORRUPT;
+        const uint32_t bh = S.le24(ip); ip += 3;
+        const uint32_t last = bh & 1u, type = (bh >> 1) & 3u, bsize = bh >> 3;
+        if (type == 3 || bsize > 131072u) return B2Z_DERR_CORRUPT;
+        const uint32_t cSize = type == 1 ? 1u : bsize;
+        if (srcSize - ip < cSize) return B2Z_DERR_CORRUPT;
+        if (out) {
+            if (firstBlock + nb >= blockCap) return B2Z_DERR_TABLE_FULL;
+            const int32_t self = (int32_t)(firstBlock + nb);
+            DecBlock b; b.srcOff = ip; b.type = type; b.frame = frameIdx; b.hufSrc = -1; b.tblSrc[0] = b.tblSrc[1] = b.tblSrc[2] = -1;
+            b.regen = 0; b.nbSeq = 0; b.litSize = 0; b.status = 0; b.rawSize = 0; b.cSize = cSize;
+            if (type != 2) { b.rawSize = bsize; b.regen = bsize; }
+            else {
+                const LitHdr lh = parse_lit_hdr(S, ip, bsize);
+                if (!lh.ok) return B2Z_DERR_CORRUPT;
+                if (lh.type == 2) { b.hufSrc = self; lastHuf = self; }
+                else if (lh.type == 3) { if (lastHuf < 0) return B2Z_DERR_CORRUPT; b.hufSrc = lastHuf; }
+                const uint32_t so = lh.hdr + lh.csize;
+                const SeqHdr sh = parse_seq_hdr(S, ip + so, bsize - so);
+                if (!sh.ok) return B2Z_DERR_CORRUPT;
+                if (sh.nbSeq) {
+                    for (int t = 0; t < 3; t++) {
+                        const uint32_t mode = (sh.modes >> (6 - 2 * t)) & 3u;      // LL, OF, ML
+                        if (mode == 3) { if (lastTbl[t] < 0) return B2Z_DERR_CORRUPT; b.tblSrc[t] = lastTbl[t]; }
+                        else { b.tblSrc[t] = self; lastTbl[t] = self; }
+                    }
+                }
+            }
+            out[firstBlock + nb] = b;
+        }
+        nb++;
+        ip += cSize;
+        if (last) break;
+    }
+    *nbOut = nb; *ipEnd = ip;
+    return 0;
+}
+
+__global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts) {
     if (threadIdx.x || blockIdx.x) return;
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
-    uint64_t ip = 0; uint32_t nf = 0, nb = 0, status = 0;
+    uint64_t ip = 0; uint32_t nf = 0, status = 0;
     while (ip < srcSize && !status) {
         if (srcSize - ip < 4) { status = B2Z_DERR_CORRUPT; break; }
         const uint32_t magic = S.le32(ip);
@@ -107,73 +186,67 @@ __global__ void zstd_dec_prepass_kernel(const uint8_t* __restrict__ src, uint64_
             if (srcSize - ip < 8) { status = B2Z_DERR_CORRUPT; break; }
             const uint64_t sz = S.le32(ip + 4);
             if (srcSize - ip < 8 + sz) { status = B2Z_DERR_CORRUPT; break; }
+            // a size hint? (payload = compressed size of the zstd frame that follows; verified by D0b)
+            if (magic == 0x184D2A50u && sz == 4 && srcSize - ip >= 16 && S.le32(ip + 12) == 0xFD2FB528u) {
+                const uint64_t fsz = S.le32(ip + 8);
+                if (fsz >= 9 && srcSize - (ip + 12) >= fsz) {
+                    if (nf >= frameCap) { status = B2Z_DERR_TABLE_FULL; break; }
+                    DecFrame fr; fr.srcOff = ip + 12; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = ip + 12 + fsz;   // regen: end offset (until D2)
+                    fr.firstBlock = 0; fr.nBlocks = 0; fr.checksum = 0; fr.pad = 1;                                                     // pad: 1 = end offset is a hint
+                    frames[nf++] = fr;
+                    ip += 12 + fsz; continue;
+                }
+            }
             ip += 8 + sz; continue;
         }
         if (magic != 0xFD2FB528u) { status = B2Z_DERR_CORRUPT; break; }
-        if (srcSize - ip < 6) { status = B2Z_DERR_CORRUPT; break; }
         if (nf >= frameCap) { status = B2Z_DERR_TABLE_FULL; break; }
-        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.regen = 0; fr.firstBlock = nb; fr.pad = 0;
-        const uint32_t fhd = S.u8(ip + 4); ip += 5;
-        const uint32_t fcsFlag = fhd >> 6, single = (fhd >> 5) & 1u, didFlag = fhd & 3u;
-        fr.checksum = (fhd >> 2) & 1u;
-        if (fhd & 8u) { status = B2Z_DERR_CORRUPT; break; }
-        uint64_t windowSize = 0;
-        if (!single) {
-            const uint32_t wd = S.u8(ip++); const uint32_t wl = 10u + (wd >> 3);
-            if (wl > 31) { status = B2Z_DERR_CORRUPT; break; }
-            windowSize = (1ull << wl) + ((1ull << wl) >> 3) * (wd & 7u);
-        }
-        const uint32_t didBytes = didFlag == 3 ? 4u : didFlag;
-        uint32_t did = 0; for (uint32_t i = 0; i < didBytes; i++) did |= S.u8(ip + i) << (8 * i);
-        ip += didBytes;
-        if (did) { status = B2Z_DERR_UNSUPPORTED; break; }
-        const uint32_t fcsBytes = fcsFlag == 0 ? single : (fcsFlag == 1 ? 2u : (fcsFlag == 2 ? 4u : 8u));
-        if (srcSize - ip < fcsBytes) { status = B2Z_DERR_CORRUPT; break; }
-        uint64_t fcs = ~0ull;
-        if (fcsBytes) { fcs = 0; for (uint32_t i = 0; i < fcsBytes; i++) fcs |= (uint64_t)S.u8(ip + i) << (8 * i); if (fcsBytes == 2) fcs += 256; }
-        ip += fcsBytes;
-        if (single) windowSize = fcs;
-        if (windowSize > (1ull << 30) - 16) { status = B2Z_DERR_UNSUPPORTED; break; }
-        fr.contentSize = fcs; fr.windowSize = windowSize;
-        int32_t lastHuf = -1, lastTbl[3] = { -1, -1, -1 };
-        for (;;) {
-            if (srcSize - ip < 3) { status = B2Z_DERR_CORRUPT; break; }
-            if (nb >= blockCap) { status = B2Z_DERR_TABLE_FULL; break; }
-            const uint32_t bh = S.le24(ip); ip += 3;
-            const uint32_t last = bh & 1u, type = (bh >> 1) & 3u, bsize = bh >> 3;
-            if (type == 3 || bsize > 131072u) { status = B2Z_DERR_CORRUPT; break; }
-            DecBlock b; b.srcOff = ip; b.type = type; b.frame = nf; b.hufSrc = -1; b.tblSrc[0] = b.tblSrc[1] = b.tblSrc[2] = -1;
-            b.regen = 0; b.nbSeq = 0; b.litSize = 0; b.status = 0; b.rawSize = 0;
-            b.cSize = type == 1 ? 1u : bsize;
-            if (srcSize - ip < b.cSize) { status = B2Z_DERR_CORRUPT; break; }
-            if (type != 2) { b.rawSize = bsize; b.regen = bsize; }
-            else {
-                const LitHdr lh = parse_lit_hdr(S, ip, bsize);
-                if (!lh.ok) { status = B2Z_DERR_CORRUPT; break; }
-                if (lh.type == 2) { b.hufSrc = (int32_t)nb; lastHuf = (int32_t)nb; }
-                else if (lh.type == 3) { if (lastHuf < 0) { status = B2Z_DERR_CORRUPT; break; } b.hufSrc = lastHuf; }
-                const uint32_t so = lh.hdr + lh.csize;
-                const SeqHdr sh = parse_seq_hdr(S, ip + so, bsize - so);
-                if (!sh.ok) { status = B2Z_DERR_CORRUPT; break; }
-                if (sh.nbSeq) {
-                    for (int t = 0; t < 3; t++) {
-                        const uint32_t mode = (sh.modes >> (6 - 2 * t)) & 3u;      // LL, OF, ML
-                        if (mode == 3) { if (lastTbl[t] < 0) { status = B2Z_DERR_CORRUPT; break; } b.tblSrc[t] = lastTbl[t]; }
-                        else { b.tblSrc[t] = (int32_t)nb; lastTbl[t] = (int32_t)nb; }
-                    }
-                    if (status) break;
-                }
-            }
-            blocks[nb++] = b;
-            ip += b.cSize;
-            if (last) break;
-        }
+        const FrameHdr h = parse_frame_hdr(S, ip, srcSize);
+        if (h.status) { status = h.status; break; }
+        uint32_t nb; uint64_t end;
+        status = walk_blocks(S, ip + h.hdrBytes, srcSize, &nb, &end, nullptr, 0, nf, 0);
         if (status) break;
-        fr.nBlocks = nb - fr.firstBlock;
-        if (fr.checksum) { if (srcSize - ip < 4) { status = B2Z_DERR_CORRUPT; break; } ip += 4; }
+        if (h.checksum) { if (srcSize - end < 4) { status = B2Z_DERR_CORRUPT; break; } end += 4; }
+        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = end; fr.firstBlock = 0; fr.nBlocks = nb; fr.checksum = 0; fr.pad = 0;
         frames[nf++] = fr;
+        ip = end;
     }
-    counts->nFrames = nf; counts->nBlocks = nb; counts->status = status; counts->srcUsed = ip;
+    counts->nFrames = nf; counts->nBlocks = 0; counts->status = status; counts->srcUsed = ip;
+}
+
+__global__ void zstd_dec_count_blocks_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames, DecCounts* counts) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFrames) return;
+    Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
+    DecFrame fr = frames[f];
+    const FrameHdr h = parse_frame_hdr(S, fr.srcOff, srcSize);
+    uint32_t status = h.status, nb = 0; uint64_t end = 0;
+    if (!status) status = walk_blocks(S, fr.srcOff + h.hdrBytes, srcSize, &nb, &end, nullptr, 0, f, 0);
+    if (!status && h.checksum) { if (srcSize - end < 4) status = B2Z_DERR_CORRUPT; else end += 4; }
+    if (!status && end != fr.regen) status = B2Z_DERR_CORRUPT;          // a size hint that does not match its frame
+    fr.contentSize = h.contentSize; fr.windowSize = h.windowSize; fr.checksum = h.checksum; fr.nBlocks = nb; fr.pad = h.hdrBytes;
+    frames[f] = fr;
+    if (status) atomicOr(&counts->status, status);
+}
+
+__global__ void zstd_dec_scan_blocks_kernel(DecFrame* frames, uint32_t nFrames, uint32_t blockCap, DecCounts* counts) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t total = 0;
+    for (uint32_t f = 0; f < nFrames; f++) { frames[f].firstBlock = total; total += frames[f].nBlocks; }
+    counts->nBlocks = total;
+    if (total > blockCap) counts->status |= B2Z_DERR_TABLE_FULL;
+}
+
+__global__ void zstd_dec_fill_blocks_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames,
+                                            DecBlock* blocks, uint32_t blockCap, DecCounts* counts) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFrames || counts->status) return;
+    Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
+    const DecFrame fr = frames[f];
+    uint32_t nb; uint64_t end;
+    const uint32_t status = walk_blocks(S, fr.srcOff + fr.pad, srcSize, &nb, &end, blocks, fr.firstBlock, f, blockCap);
+    frames[f].regen = 0; frames[f].pad = 0;
+    if (status) atomicOr(&counts->status, status);
 }
 
 // ---------------------------------------------------------------- bit readers (single lane)
@@ -563,6 +636,23 @@ __global__ void zstd_dec_frame_offsets_kernel(DecFrame* frames, uint32_t nFrames
 }
 
 // ---------------------------------------------------------------- D3: execute
+// One warp per frame, blocks in order.  Sequences are taken 32 at a time (one per lane):
+//   1. repcode history is resolved in order (warp-uniform registers) -> every lane knows its offset;
+//   2. prefix sums give every lane its output position and literal source;
+//   3. all literal runs are copied in parallel;
+//   4. every match whose source ends before the batch's first output byte is copied in parallel;
+//   5. the remaining matches (source overlaps this batch's output) are copied in sequence order,
+//      each as a periodic extension (dst[i] = src[i mod offset]) so its bytes are independent.
+// Long runs (> 32 bytes) are copied by the whole warp instead of one lane.
+__device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane) {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__device__ __forceinline__ void warp_copy_match(uint8_t* dst, uint32_t offset, uint32_t n, uint32_t lane) {
+    const uint8_t* m = dst - offset;
+    if (offset >= n) { for (uint32_t i = lane; i < n; i += 32) dst[i] = __ldcg(m + i); }
+    else { for (uint32_t i = lane; i < n; i += 32) dst[i] = __ldcg(m + (i % offset)); }
+}
+
 __global__ void __launch_bounds__(32)
 zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ frames, uint32_t nFrames, DecBlock* __restrict__ blocks,
                      const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* dst, DecCounts* counts) {
@@ -583,13 +673,17 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
             for (uint32_t i0 = 0; i0 < blk.nbSeq && !err; i0 += 32) {
                 const uint32_t cnt = (blk.nbSeq - i0) < 32u ? (blk.nbSeq - i0) : 32u;
                 const uint64_t mine = lane < cnt ? sq[i0 + lane] : 0ull;
+                const uint32_t ll = lane < cnt ? ((uint32_t)(mine >> 30) & 0x1FFFFu) : 0u;
+                const uint32_t ml = lane < cnt ? ((uint32_t)(mine >> 47) + 3u) : 0u;
+                // 1. repcodes, in order
+                uint32_t myOff = 0;
                 for (uint32_t k = 0; k < cnt; k++) {
                     const uint64_t s = __shfl_sync(B2Z_FULL, mine, k);
-                    const uint32_t ob = (uint32_t)s & 0x3FFFFFFFu, ll = (uint32_t)(s >> 30) & 0x1FFFFu, ml = (uint32_t)(s >> 47) + 3u;
+                    const uint32_t ob = (uint32_t)s & 0x3FFFFFFFu, llk = (uint32_t)(s >> 30) & 0x1FFFFu;
                     uint32_t offset;
                     if (ob > 3) { offset = ob - 3u; rep2 = rep1; rep1 = rep0; rep0 = offset; }
                     else {
-                        const uint32_t idx = ob - 1u + (ll == 0u);
+                        const uint32_t idx = ob - 1u + (llk == 0u);
                         if (idx == 0) offset = rep0;
                         else {
                             offset = idx == 3 ? rep0 - 1u : (idx == 1 ? rep1 : rep2);
@@ -597,17 +691,37 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
                             rep1 = rep0; rep0 = offset;
                         }
                     }
-                    // literals
-                    for (uint32_t i = lane; i < ll; i += 32) out[o + i] = lit[lp + i];
-                    o += ll; lp += ll;
-                    if (offset == 0 || offset > o || offset > fr.windowSize) { err = B2Z_DERR_CORRUPT; break; }
-                    // match: periodic extension makes every byte independent of this copy's own output
-                    const uint8_t* m = out + o - offset;
-                    if (offset >= ml) { for (uint32_t i = lane; i < ml; i += 32) out[o + i] = __ldcg(m + i); }
-                    else { for (uint32_t i = lane; i < ml; i += 32) out[o + i] = __ldcg(m + (i % offset)); }
-                    o += ml;
+                    if (lane == k) myOff = offset;
+                }
+                // 2. positions
+                uint32_t total, litTotal;
+                const uint32_t excl = warp_excl_scan(ll + ml, lane, &total);
+                const uint32_t litExcl = warp_excl_scan(ll, lane, &litTotal);
+                const uint64_t myOut = o + excl, myDst = myOut + ll;                     // frame-relative
+                const bool bad = lane < cnt && (myOff == 0 || myOff > myDst || myOff > fr.windowSize);
+                if (__any_sync(B2Z_FULL, bad)) { err = B2Z_DERR_CORRUPT; break; }
+                // 3. literals
+                if (ll <= 32u) { for (uint32_t i = 0; i < ll; i++) out[myOut + i] = lit[lp + litExcl + i]; }
+                for (uint32_t big = __ballot_sync(B2Z_FULL, ll > 32u); big; big &= big - 1u) {
+                    const uint32_t k = (uint32_t)__ffs((int)big) - 1u;
+                    warp_copy_lit(out + __shfl_sync(B2Z_FULL, myOut, k), lit + lp + __shfl_sync(B2Z_FULL, litExcl, k), __shfl_sync(B2Z_FULL, ll, k), lane);
+                }
+                __syncwarp();
+                // 4. matches that read only bytes produced before this batch
+                const bool indep = lane < cnt && (myDst - myOff + ml <= o);
+                if (indep && ml <= 32u) { const uint8_t* m = out + myDst - myOff; for (uint32_t i = 0; i < ml; i++) out[myDst + i] = __ldcg(m + i); }
+                for (uint32_t big = __ballot_sync(B2Z_FULL, indep && ml > 32u); big; big &= big - 1u) {
+                    const uint32_t k = (uint32_t)__ffs((int)big) - 1u;
+                    warp_copy_match(out + __shfl_sync(B2Z_FULL, myDst, k), __shfl_sync(B2Z_FULL, myOff, k), __shfl_sync(B2Z_FULL, ml, k), lane);
+                }
+                __syncwarp();
+                // 5. the rest, in order
+                for (uint32_t dep = __ballot_sync(B2Z_FULL, lane < cnt && !indep); dep; dep &= dep - 1u) {
+                    const uint32_t k = (uint32_t)__ffs((int)dep) - 1u;
+                    warp_copy_match(out + __shfl_sync(B2Z_FULL, myDst, k), __shfl_sync(B2Z_FULL, myOff, k), __shfl_sync(B2Z_FULL, ml, k), lane);
                     __syncwarp();
                 }
+                o += total; lp += litTotal;
             }
             if (!err) { const uint32_t tail = blk.litSize - lp; for (uint32_t i = lane; i < tail; i += 32) out[o + i] = lit[lp + i]; o += tail; }
             __syncwarp();
@@ -618,9 +732,16 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
 }
 
 // ---------------------------------------------------------------- launchers
-void launch_zstd_dec_prepass(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap,
-                             DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st) {
-    zstd_dec_prepass_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, blocks, blockCap, counts);
+void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st) {
+    zstd_dec_find_frames_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, counts);
+}
+void launch_zstd_dec_index_blocks(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames,
+                                  DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st) {
+    if (!nFrames) return;
+    const uint32_t grid = (nFrames + 63) / 64;
+    zstd_dec_count_blocks_kernel<<<grid, 64, 0, st>>>(src, srcSize, frames, nFrames, counts);
+    zstd_dec_scan_blocks_kernel<<<1, 32, 0, st>>>(frames, nFrames, blockCap, counts);
+    zstd_dec_fill_blocks_kernel<<<grid, 64, 0, st>>>(src, srcSize, frames, nFrames, blocks, blockCap, counts);
 }
 void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks, uint8_t* lits, uint64_t* seqs, cudaStream_t st) {
     if (!nBlocks) return;

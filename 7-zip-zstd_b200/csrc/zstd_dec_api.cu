@@ -84,13 +84,18 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     DecCounts* counts = (DecCounts*)aCounts.p; uint64_t* total = (uint64_t*)((uint8_t*)aCounts.p + 32);
     CU(cudaMemsetAsync(aCounts.p, 0, 64, st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    launch_zstd_dec_prepass((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, blocks, (uint32_t)blockCap, counts, st);
+    launch_zstd_dec_find_frames((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, counts, st);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(ctx->ev[3], st));
     DecCounts hc;
     CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+    if (hc.status) return dec_status_to_rc(ctx, hc.status);
+    launch_zstd_dec_index_blocks((const uint8_t*)d_src, srcSize, frames, hc.nFrames, blocks, (uint32_t)blockCap, counts, st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[3], st));
+    CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
     if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64))
         return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (input too large for one pass)%s");
