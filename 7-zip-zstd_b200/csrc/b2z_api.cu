@@ -33,6 +33,7 @@ int b200z_create(b200z_ctx** out, int device) {
     { size_t gran = 32; if (const char* e = getenv("B200Z_L2_FETCH")) gran = (size_t)atoi(e);
       if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
     ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1;   // size hints on: lets any decoder (ours included) find frames without walking blocks
@@ -50,6 +51,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 

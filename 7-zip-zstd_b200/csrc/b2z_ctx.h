@@ -24,6 +24,7 @@ struct Arena {                       // grow-only device buffer
 struct b200z_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // side stream (decoder: literals kernel next to the sequences kernel)
     b2z::EncGeom geom{};
     int level = 3;
     uint32_t batchLog = 32;

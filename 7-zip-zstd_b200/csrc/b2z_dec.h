@@ -6,7 +6,6 @@
 namespace b2z {
 
 #define B2Z_DEC_MAXSEQ   65536u      // sequences per block (format max: 128 KiB / 3 < 43691)
-#define B2Z_DEC_WARPS    2           // D1: warps (= blocks) per CTA
 
 // error bits (per block / global)
 #define B2Z_DERR_CORRUPT      1u
@@ -45,9 +44,10 @@ struct DecCounts { uint32_t nFrames, nBlocks, status, pad; uint64_t srcUsed; };
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st);
 void launch_zstd_dec_index_blocks(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames,
                                   DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st);
-// stage D1: one warp per compressed block: literals (Huffman) + sequences (FSE) into scratch
+// stage D1: tables (one warp per block) then streams (one thread per stream); literals | sequences on two CUDA streams
 void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks,
-                             uint8_t* lits, uint64_t* seqs, cudaStream_t st);
+                             uint8_t* lits, uint64_t* seqs, void* scratch, cudaStream_t st, cudaStream_t stLit, cudaEvent_t evFork, cudaEvent_t evJoin);
+size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks);
 // stage D2: per-frame sizes and output offsets
 void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* blocks, uint64_t dstCap,
                             DecCounts* counts, uint64_t* total, cudaStream_t st);

@@ -291,9 +291,10 @@ struct BwdBits {                                // backward stream with end mark
 
 // ---------------------------------------------------------------- per-warp workspace of D1
 struct SeqEnt { uint32_t base; uint8_t nbAdd, nbBits; uint16_t next; };
-struct DecWS {
-    uint16_t huf[2048];          // symbol | nbBits << 8
-    SeqEnt   tabs[1280];         // LL [0,512), OF [512,768), ML [768,1280)
+// ROLE 0 = literals kernel (needs the Huffman table), ROLE 1 = sequences kernel (needs the three FSE tables)
+template <int ROLE> struct DecWST {
+    uint16_t huf[ROLE == 0 ? 2048 : 64];     // symbol | nbBits << 8
+    SeqEnt   tabs[ROLE == 1 ? 1280 : 1];     // LL [0,512), OF [512,768), ML [768,1280)
     __device__ __forceinline__ SeqEnt* tab(int t) { return tabs + (t == 0 ? 0 : (t == 1 ? 512 : 768)); }
     __device__ __forceinline__ const SeqEnt* tab(int t) const { return tabs + (t == 0 ? 0 : (t == 1 ? 512 : 768)); }
     uint32_t tabLog[3];
@@ -335,7 +336,7 @@ __device__ uint32_t fse_read_ncount(int16_t* norm, uint32_t* maxSym, uint32_t* t
 }
 
 // generic FSE decode table: symbol per state in ws->sym, (nbBits, newState) returned through arrays
-__device__ bool fse_spread(DecWS* ws, const int16_t* norm, uint32_t maxSym, uint32_t log) {
+template <class WS> __device__ bool fse_spread(WS* ws, const int16_t* norm, uint32_t maxSym, uint32_t log) {
     const uint32_t size = 1u << log, mask = size - 1u; uint32_t high = size - 1u;
     for (uint32_t s = 0; s <= maxSym; s++) {
         if (norm[s] == -1) { ws->sym[high--] = (uint8_t)s; ws->nxt[s] = 1; } else ws->nxt[s] = (uint16_t)norm[s];
@@ -346,7 +347,7 @@ __device__ bool fse_spread(DecWS* ws, const int16_t* norm, uint32_t maxSym, uint
     return pos == 0;
 }
 
-__device__ bool build_seq_table(DecWS* ws, int t, const int16_t* norm, uint32_t maxSym, uint32_t log) {
+template <class WS> __device__ bool build_seq_table(WS* ws, int t, const int16_t* norm, uint32_t maxSym, uint32_t log) {
     if (!fse_spread(ws, norm, maxSym, log)) return false;
     const uint32_t size = 1u << log;
     for (uint32_t u = 0; u < size; u++) {
@@ -363,7 +364,7 @@ __device__ bool build_seq_table(DecWS* ws, int t, const int16_t* norm, uint32_t 
 
 // Walk the table descriptions of block `blk`'s sequences section; returns the offset (absolute in src)
 // and mode of type t's description.  false on malformed data.
-__device__ bool locate_seq_table(const Src& S, const DecBlock& blk, int t, DecWS* ws, uint64_t* descOff, uint32_t* mode, uint32_t* avail) {
+template <class WS> __device__ bool locate_seq_table(const Src& S, const DecBlock& blk, int t, WS* ws, uint64_t* descOff, uint32_t* mode, uint32_t* avail) {
     const LitHdr lh = parse_lit_hdr(S, blk.srcOff, blk.cSize);
     if (!lh.ok) return false;
     const uint32_t so = lh.hdr + lh.csize;
@@ -384,7 +385,7 @@ __device__ bool locate_seq_table(const Src& S, const DecBlock& blk, int t, DecWS
 }
 
 // Huffman decoding table from the description at `off`; returns description bytes or 0
-__device__ uint32_t huf_read_table(DecWS* ws, const Src& S, uint64_t off, uint32_t size) {
+template <class WS> __device__ uint32_t huf_read_table(WS* ws, const Src& S, uint64_t off, uint32_t size) {
     if (size < 1) return 0;
     uint8_t* w = ws->sym; uint32_t nw = 0;
     const uint32_t hb = S.u8(off); uint32_t used;
@@ -448,64 +449,73 @@ __device__ uint32_t huf_read_table(DecWS* ws, const Src& S, uint64_t off, uint32
     return used;
 }
 
-// Hot-loop reader: a 64-bit container positioned by reload(); after a reload at least 57 bits can be
-// consumed before the next one.  Bits below the stream start read as zero (pos goes negative).
+// Hot-loop reader (32-bit arithmetic): `cont` holds stream bytes [bytePos, bytePos+8); the next unread bit is
+// bit (63 - consumed) of it.  After reload() consumed <= 7, so 57 bits can be read before the next reload.
+// Bytes below the stream start read as zero; left() < 0 means the stream was over-read.
 struct FastBwd {
-    const Src* S; uint64_t base; int64_t pos, cbit; uint64_t cont;
+    const Src* S; uint64_t base; uint64_t cont; int32_t bytePos; uint32_t consumed;
+    __device__ __forceinline__ uint64_t fetch() const {
+        if (bytePos >= 0) return S->le64(base + (uint32_t)bytePos);
+        if (bytePos > -8) return S->le64(base) << ((uint32_t)(-bytePos) * 8u);
+        return 0ull;
+    }
     __device__ __forceinline__ int init(const Src* s, uint64_t b, uint32_t size) {
         S = s; base = b;
         if (!size) return -1;
         const uint32_t lastByte = S->u8(b + size - 1);
         if (!lastByte) return -1;
-        pos = (int64_t)(size - 1) * 8 + (int64_t)highbit32(lastByte);
-        reload();
+        bytePos = (int32_t)size - 8; consumed = 8u - highbit32(lastByte);      // skip the padding and the end mark
+        cont = fetch();
         return 0;
     }
-    __device__ __forceinline__ void reload() {
-        cbit = ((pos + 7) & ~7ll) - 64;
-        if (cbit >= 0) cont = S->le64(base + (uint64_t)(cbit >> 3));
-        else if (cbit > -64) cont = S->le64(base) << (uint32_t)(-cbit);
-        else cont = 0;
+    __device__ __forceinline__ void reload() { bytePos -= (int32_t)(consumed >> 3); consumed &= 7u; cont = fetch(); }
+    __device__ __forceinline__ uint32_t read(uint32_t n) {                      // n <= 32 (0 allowed)
+        const uint32_t v = (uint32_t)(((cont << consumed) >> 1) >> (63u - n));
+        consumed += n;
+        return v;
     }
-    __device__ __forceinline__ uint32_t read(uint32_t n) {          // n <= 32; caller keeps <= 57 bits between reloads
-        pos -= n;
-        const int64_t sh = pos - cbit;
-        if (n == 0 || sh < 0) return 0;
-        return (uint32_t)(cont >> (uint32_t)sh) & (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u));
-    }
+    __device__ __forceinline__ int32_t left() const { return bytePos * 8 + 64 - (int32_t)consumed; }   // unread bits
 };
 
 // one Huffman stream, one lane
-__device__ bool huf_decode_stream(const DecWS* ws, const Src& S, uint64_t off, uint32_t size, uint8_t* dst, uint32_t n) {
+template <class WS> __device__ bool huf_decode_stream(const WS* ws, const Src& S, uint64_t off, uint32_t size, uint8_t* dst, uint32_t n) {
     FastBwd b; if (b.init(&S, off, size)) return false;
     const uint32_t mb = ws->hufBits;
     for (uint32_t i = 0; i < n; i++) {
-        if (b.pos - (int64_t)mb < b.cbit) b.reload();
-        const int64_t sh = b.pos - (int64_t)mb - b.cbit;            // >= 0 after the reload unless far below the start
-        const uint32_t idx = sh >= 0 ? ((uint32_t)(b.cont >> (uint32_t)sh) & ((1u << mb) - 1u)) : 0u;
-        const uint32_t e = ws->huf[idx];
-        dst[i] = (uint8_t)e; b.pos -= (e >> 8);
+        if (b.consumed > 64u - 11u) b.reload();
+        const uint32_t e = ws->huf[(uint32_t)((b.cont << b.consumed) >> (64u - mb))];
+        dst[i] = (uint8_t)e; b.consumed += (e >> 8);
     }
-    return b.pos == 0;
+    return b.left() == 0;
 }
 
 // ---------------------------------------------------------------- D1: entropy decode
 #define SEQ_PACK(ob, ll, ml) ((uint64_t)(ob) | ((uint64_t)(ll) << 30) | ((uint64_t)((ml) - 3u) << 47))
 
-__global__ void __launch_bounds__(B2Z_DEC_WARPS * 32)
+// Table stage, one warp per compressed block.  ROLE 0: raw/RLE literals are expanded here, for Huffman literals the
+// decoding table is built (lane 0) and spilled to global scratch; ROLE 1: the three FSE tables of the sequences
+// section are built and spilled.  The serial bitstreams themselves are decoded by the *_streams kernels below with
+// ONE THREAD PER STREAM, so that thousands of dependent chains overlap instead of one per warp.
+struct LitJob { uint64_t off; uint32_t size, regen, streams, hufBits; };
+struct SeqJob { uint64_t bsOff; uint32_t bsLeft, nbSeq, litRegen, logs; };
+#define D1_WARPS(ROLE) ((ROLE) == 0 ? 6 : 4)
+template <int ROLE> __global__ void __launch_bounds__(D1_WARPS(ROLE) * 32)
 zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBlock* __restrict__ blocks, uint32_t nBlocks,
-                        uint8_t* __restrict__ lits, uint64_t* __restrict__ seqs) {
-    __shared__ DecWS wsAll[B2Z_DEC_WARPS];
+                        uint8_t* __restrict__ lits, uint16_t* __restrict__ hufTabs, LitJob* __restrict__ litJobs,
+                        SeqEnt* __restrict__ seqTabs, SeqJob* __restrict__ seqJobs) {
+    typedef DecWST<ROLE> DecWS;
+    __shared__ DecWS wsAll[D1_WARPS(ROLE)];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     DecWS* ws = &wsAll[wib];
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
-    for (uint32_t bi = blockIdx.x * B2Z_DEC_WARPS + wib; bi < nBlocks; bi += gridDim.x * B2Z_DEC_WARPS) {
+    for (uint32_t bi = blockIdx.x * D1_WARPS(ROLE) + wib; bi < nBlocks; bi += gridDim.x * D1_WARPS(ROLE)) {
         const DecBlock blk = blocks[bi];
         if (blk.type != 2) continue;
         uint32_t err = 0;
         const LitHdr lh = parse_lit_hdr(S, blk.srcOff, blk.cSize);
         uint8_t* lit = lits + (size_t)bi * 131072u;
         // ---- literals
+        if (ROLE == 0) {
         if (lh.type == 0) { for (uint32_t i = lane; i < lh.regen; i += 32) lit[i] = (uint8_t)S.u8(blk.srcOff + lh.hdr + i); }
         else if (lh.type == 1) { const uint8_t v = (uint8_t)S.u8(blk.srcOff + lh.hdr); for (uint32_t i = lane; i < lh.regen; i += 32) lit[i] = v; }
         else {
@@ -520,36 +530,25 @@ zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBl
             err = __shfl_sync(B2Z_FULL, err, 0); tdesc = __shfl_sync(B2Z_FULL, tdesc, 0);
             __syncwarp();
             if (!err) {
-                const uint64_t hs = blk.srcOff + lh.hdr + tdesc; const uint32_t hsz = lh.csize - tdesc;
-                bool ok = true;
-                if (tdesc > lh.csize) ok = false;
-                else if (lh.streams == 1) { if (lane == 0) ok = huf_decode_stream(ws, S, hs, hsz, lit, lh.regen); }
-                else {
-                    if (hsz < 6) ok = false;
-                    else {
-                        const uint64_t j = S.le64(hs);
-                        const uint32_t s1 = (uint32_t)j & 0xFFFFu, s2 = (uint32_t)(j >> 16) & 0xFFFFu, s3 = (uint32_t)(j >> 32) & 0xFFFFu;
-                        const uint32_t seg = (lh.regen + 3u) / 4u;
-                        if (6u + s1 + s2 + s3 > hsz || seg * 3u > lh.regen) ok = false;
-                        else if (lane < 4) {
-                            const uint32_t s4 = hsz - 6u - s1 - s2 - s3;
-                            const uint32_t so = lane == 0 ? 0u : (lane == 1 ? s1 : (lane == 2 ? s1 + s2 : s1 + s2 + s3));
-                            const uint32_t sz = lane == 0 ? s1 : (lane == 1 ? s2 : (lane == 2 ? s3 : s4));
-                            const uint32_t cnt = lane < 3 ? seg : lh.regen - 3u * seg;
-                            ok = huf_decode_stream(ws, S, hs + 6u + so, sz, lit + lane * seg, cnt);
-                        }
-                    }
-                }
-                if (!__all_sync(B2Z_FULL, ok)) err = B2Z_DERR_CORRUPT;
+                // spill the decoding table; the streams are decoded by zstd_dec_lit_streams_kernel (one thread per stream)
+                uint16_t* gt = hufTabs + (size_t)bi * 2048u;
+                const uint32_t nEnt = 1u << ws->hufBits;
+                for (uint32_t i = lane; i < nEnt; i += 32) gt[i] = ws->huf[i];
+                if (lane == 0) { LitJob j; j.off = blk.srcOff + lh.hdr + tdesc; j.size = tdesc <= lh.csize ? lh.csize - tdesc : 0xFFFFFFFFu; j.regen = lh.regen; j.streams = lh.streams; j.hufBits = ws->hufBits; litJobs[bi] = j; }
             }
+        }
+        if (lane == 0 && (err || lh.type < 2)) { LitJob j; j.off = 0; j.size = 0; j.regen = 0; j.streams = 0; j.hufBits = 0; litJobs[bi] = j; }
+        if (lane == 0 && err) atomicOr(&blocks[bi].status, err);
         }
         __syncwarp();
         // ---- sequences (lane 0)
-        uint32_t nbSeq = 0, regen = 0;
+        uint32_t nbSeq = 0;
+        if (ROLE == 1) {
+        SeqJob job; job.bsOff = 0; job.bsLeft = 0; job.nbSeq = 0; job.litRegen = lh.regen; job.logs = 0;
         if (lane == 0 && !err) {
             const uint32_t so = lh.hdr + lh.csize;
             const SeqHdr sh = parse_seq_hdr(S, blk.srcOff + so, blk.cSize - so);
-            nbSeq = sh.nbSeq; regen = lh.regen;
+            nbSeq = sh.nbSeq;
             if (nbSeq > B2Z_DEC_MAXSEQ) err = B2Z_DERR_CORRUPT;
             if (nbSeq && !err) {
                 const uint32_t maxSymT[3] = { 35, 31, 52 }, maxLogT[3] = { 9, 8, 9 }, defMax[3] = { 35, 28, 52 }, defLog[3] = { 6, 5, 6 };
@@ -580,40 +579,118 @@ zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBl
                     }
                     if (ownMode != 3) { if (used > bsLeft) err = B2Z_DERR_CORRUPT; else { bsOff += used; bsLeft -= used; } }
                 }
-                if (!err) {
-                    FastBwd b;
-                    if (b.init(&S, bsOff, bsLeft)) err = B2Z_DERR_CORRUPT;
-                    else {
-                        uint32_t sL = b.read(ws->tabLog[0]), sO = b.read(ws->tabLog[1]), sM = b.read(ws->tabLog[2]);   // <= 26 bits
-                        if (b.pos < 0) err = B2Z_DERR_CORRUPT;
-                        uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
-                        uint32_t litUsed = 0, total = 0;
-                        for (uint32_t i = 0; i < nbSeq && !err; i++) {
-                            const SeqEnt eL = ws->tabs[sL], eO = ws->tabs[512 + sO], eM = ws->tabs[768 + sM];
-                            if (eO.nbAdd > 30) { err = B2Z_DERR_UNSUPPORTED; break; }
-                            b.reload();
-                            const uint32_t ob = eO.base + b.read(eO.nbAdd);
-                            if ((uint32_t)eO.nbAdd + eM.nbAdd + eL.nbAdd > 56u) b.reload();
-                            const uint32_t ml = eM.base + b.read(eM.nbAdd);
-                            const uint32_t ll = eL.base + b.read(eL.nbAdd);
-                            if (i + 1 < nbSeq) {
-                                if ((uint32_t)eO.nbAdd + eM.nbAdd + eL.nbAdd > 30u) b.reload();                 // + <= 26 state bits
-                                sL = eL.next + b.read(eL.nbBits); sM = eM.next + b.read(eM.nbBits); sO = eO.next + b.read(eO.nbBits);
-                            }
-                            litUsed += ll; total += ll + ml;
-                            if (b.pos < 0 || litUsed > lh.regen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
-                            out[i] = SEQ_PACK(ob, ll, ml);
-                        }
-                        if (!err && b.pos != 0) err = B2Z_DERR_CORRUPT;
-                        regen = total + (lh.regen - litUsed);
-                        if (regen > 131072u) err = B2Z_DERR_CORRUPT;
-                    }
-                }
+                if (!err) { job.bsOff = bsOff; job.bsLeft = bsLeft; job.nbSeq = nbSeq; job.litRegen = lh.regen; job.logs = ws->tabLog[0] | (ws->tabLog[1] << 8) | (ws->tabLog[2] << 16); }
             }
         }
-        if (lane == 0) { blocks[bi].regen = err ? 0u : regen; blocks[bi].nbSeq = nbSeq; blocks[bi].litSize = lh.regen; blocks[bi].status = err; }
+        err = __shfl_sync(B2Z_FULL, err, 0); nbSeq = __shfl_sync(B2Z_FULL, nbSeq, 0);
+        __syncwarp();                                                 // lane 0's tables are visible to the warp
+        if (!err && nbSeq) {                                          // spill the three tables (LL 512 | OF 256 | ML 512 entries)
+            uint2* gt = reinterpret_cast<uint2*>(seqTabs + (size_t)bi * 1280u);
+            const uint2* st2 = reinterpret_cast<const uint2*>(ws->tabs);
+            const uint32_t nL = 1u << ws->tabLog[0], nO = 1u << ws->tabLog[1], nM = 1u << ws->tabLog[2];
+            for (uint32_t i = lane; i < nL; i += 32) gt[i] = st2[i];
+            for (uint32_t i = lane; i < nO; i += 32) gt[512 + i] = st2[512 + i];
+            for (uint32_t i = lane; i < nM; i += 32) gt[768 + i] = st2[768 + i];
+        }
+        if (lane == 0) {
+            if (err) { job.nbSeq = 0; job.bsLeft = 0; }
+            if (!nbSeq && !err) { job.bsOff = 0; job.bsLeft = 0; job.nbSeq = 0; job.litRegen = lh.regen; job.logs = 0; }
+            seqJobs[bi] = job;
+            blocks[bi].regen = (err || nbSeq) ? 0u : lh.regen; blocks[bi].nbSeq = 0; blocks[bi].litSize = lh.regen; if (err) atomicOr(&blocks[bi].status, err);
+        }
+        }
         __syncwarp();
     }
+}
+
+// ---------------------------------------------------------------- D1b: one thread per stream
+__global__ void __launch_bounds__(128)
+zstd_dec_lit_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBlock* __restrict__ blocks, uint32_t nBlocks,
+                            uint8_t* __restrict__ lits, const uint16_t* __restrict__ hufTabs, const LitJob* __restrict__ litJobs) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t bi = t >> 2, k = t & 3u;
+    if (bi >= nBlocks) return;
+    const LitJob j = litJobs[bi];
+    if (!j.streams || blocks[bi].type != 2) return;
+    Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
+    uint8_t* lit = lits + (size_t)bi * 131072u;
+    const uint16_t* __restrict__ tab = hufTabs + (size_t)bi * 2048u;
+    bool ok = true;
+    uint64_t off = 0; uint32_t size = 0, cnt = 0; uint8_t* dst = lit;
+    if (j.size == 0xFFFFFFFFu) ok = false;
+    else if (j.streams == 1) { if (k) return; off = j.off; size = j.size; cnt = j.regen; }
+    else {
+        if (j.size < 6) ok = false;
+        else {
+            const uint64_t jt = S.le64(j.off);
+            const uint32_t s1 = (uint32_t)jt & 0xFFFFu, s2 = (uint32_t)(jt >> 16) & 0xFFFFu, s3 = (uint32_t)(jt >> 32) & 0xFFFFu;
+            const uint32_t seg = (j.regen + 3u) / 4u;
+            if (6u + s1 + s2 + s3 > j.size || seg * 3u > j.regen) ok = false;
+            else {
+                const uint32_t s4 = j.size - 6u - s1 - s2 - s3;
+                const uint32_t so = k == 0 ? 0u : (k == 1 ? s1 : (k == 2 ? s1 + s2 : s1 + s2 + s3));
+                size = k == 0 ? s1 : (k == 1 ? s2 : (k == 2 ? s3 : s4));
+                cnt = k < 3 ? seg : j.regen - 3u * seg;
+                off = j.off + 6u + so; dst = lit + k * seg;
+            }
+        }
+    }
+    if (ok) {
+        FastBwd b;
+        if (b.init(&S, off, size)) ok = false;
+        else {
+            const uint32_t mb = j.hufBits;
+            for (uint32_t i = 0; i < cnt; i++) {
+                if (b.consumed > 64u - 11u) b.reload();
+                const uint32_t e = __ldg(tab + (uint32_t)((b.cont << b.consumed) >> (64u - mb)));
+                dst[i] = (uint8_t)e; b.consumed += (e >> 8);
+            }
+            ok = b.left() == 0;
+        }
+    }
+    if (!ok) atomicOr(&blocks[bi].status, B2Z_DERR_CORRUPT);
+}
+
+__global__ void __launch_bounds__(128)
+zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBlock* __restrict__ blocks, uint32_t nBlocks,
+                            uint64_t* __restrict__ seqs, const SeqEnt* __restrict__ seqTabs, const SeqJob* __restrict__ seqJobs) {
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nBlocks || blocks[bi].type != 2) return;
+    const SeqJob j = seqJobs[bi];
+    if (!j.nbSeq) return;
+    Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
+    const uint2* __restrict__ tab = reinterpret_cast<const uint2*>(seqTabs + (size_t)bi * 1280u);
+    uint32_t err = 0, regen = 0;
+    FastBwd b;
+    if (b.init(&S, j.bsOff, j.bsLeft)) err = B2Z_DERR_CORRUPT;
+    else {
+        uint32_t sL = b.read(j.logs & 255u), sO = b.read((j.logs >> 8) & 255u), sM = b.read((j.logs >> 16) & 255u);   // <= 26 bits
+        if (b.left() < 0) err = B2Z_DERR_CORRUPT;
+        uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+        uint32_t litUsed = 0, total = 0;
+        for (uint32_t i = 0; i < j.nbSeq && !err; i++) {
+            const uint2 rL = __ldg(tab + sL), rO = __ldg(tab + 512u + sO), rM = __ldg(tab + 768u + sM);     // {base, nbAdd | nbBits<<8 | next<<16}
+            const uint32_t aL = rL.y & 255u, aO = rO.y & 255u, aM = rM.y & 255u;
+            if (aO > 30u) { err = B2Z_DERR_UNSUPPORTED; break; }
+            b.reload();
+            const uint32_t ob = rO.x + b.read(aO);
+            if (aO + aM + aL > 56u) b.reload();
+            const uint32_t ml = rM.x + b.read(aM);
+            const uint32_t ll = rL.x + b.read(aL);
+            if (i + 1 < j.nbSeq) {
+                if (aO + aM + aL > 30u) b.reload();                                                     // + <= 26 state bits
+                sL = (rL.y >> 16) + b.read((rL.y >> 8) & 255u); sM = (rM.y >> 16) + b.read((rM.y >> 8) & 255u); sO = (rO.y >> 16) + b.read((rO.y >> 8) & 255u);
+            }
+            litUsed += ll; total += ll + ml;
+            if (b.left() < 0 || litUsed > j.litRegen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
+            out[i] = SEQ_PACK(ob, ll, ml);
+        }
+        if (!err && b.left() != 0) err = B2Z_DERR_CORRUPT;
+        regen = total + (j.litRegen - litUsed);
+        if (regen > 131072u) err = B2Z_DERR_CORRUPT;
+    }
+    blocks[bi].regen = err ? 0u : regen; blocks[bi].nbSeq = err ? 0u : j.nbSeq;
+    if (err) atomicOr(&blocks[bi].status, err);
 }
 
 // ---------------------------------------------------------------- D2: layout
@@ -743,12 +820,28 @@ void launch_zstd_dec_index_blocks(const uint8_t* src, uint64_t srcSize, DecFrame
     zstd_dec_scan_blocks_kernel<<<1, 32, 0, st>>>(frames, nFrames, blockCap, counts);
     zstd_dec_fill_blocks_kernel<<<grid, 64, 0, st>>>(src, srcSize, frames, nFrames, blocks, blockCap, counts);
 }
-void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks, uint8_t* lits, uint64_t* seqs, cudaStream_t st) {
+void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blocks, uint32_t nBlocks, uint8_t* lits, uint64_t* seqs,
+                             void* scratch, cudaStream_t st, cudaStream_t stLit, cudaEvent_t evFork, cudaEvent_t evJoin) {
     if (!nBlocks) return;
-    uint32_t grid = (nBlocks + B2Z_DEC_WARPS - 1) / B2Z_DEC_WARPS;
-    if (grid > 148u * 32u) grid = 148u * 32u;
-    zstd_dec_entropy_kernel<<<grid, B2Z_DEC_WARPS * 32, 0, st>>>(src, srcSize, blocks, nBlocks, lits, seqs);
+    // scratch layout: hufTabs [nBlocks][2048] u16 | seqTabs [nBlocks][1280] SeqEnt | litJobs | seqJobs
+    uint8_t* p = (uint8_t*)scratch;
+    uint16_t* hufTabs = (uint16_t*)p; p += (size_t)nBlocks * 4096u;
+    SeqEnt* seqTabs = (SeqEnt*)p; p += (size_t)nBlocks * 1280u * sizeof(SeqEnt);
+    LitJob* litJobs = (LitJob*)p; p += (size_t)nBlocks * sizeof(LitJob);
+    SeqJob* seqJobs = (SeqJob*)p;
+    // literals on the side stream, sequences on the main one; both only read src/blocks and write disjoint outputs
+    cudaEventRecord(evFork, st);
+    cudaStreamWaitEvent(stLit, evFork, 0);
+    { uint32_t grid = (nBlocks + D1_WARPS(0) - 1) / D1_WARPS(0); if (grid > 148u * 16u) grid = 148u * 16u;
+      zstd_dec_entropy_kernel<0><<<grid, D1_WARPS(0) * 32, 0, stLit>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs, seqTabs, seqJobs);
+      zstd_dec_lit_streams_kernel<<<(nBlocks * 4u + 127u) / 128u, 128, 0, stLit>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs); }
+    { uint32_t grid = (nBlocks + D1_WARPS(1) - 1) / D1_WARPS(1); if (grid > 148u * 16u) grid = 148u * 16u;
+      zstd_dec_entropy_kernel<1><<<grid, D1_WARPS(1) * 32, 0, st>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs, seqTabs, seqJobs);
+      zstd_dec_seq_streams_kernel<<<(nBlocks + 127u) / 128u, 128, 0, st>>>(src, srcSize, blocks, nBlocks, seqs, seqTabs, seqJobs); }
+    cudaEventRecord(evJoin, stLit);
+    cudaStreamWaitEvent(st, evJoin, 0);
 }
+size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks) { return (size_t)nBlocks * (4096u + 1280u * sizeof(SeqEnt) + sizeof(LitJob) + sizeof(SeqJob)) + 256u; }
 void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* blocks, uint64_t dstCap, DecCounts* counts, uint64_t* total, cudaStream_t st) {
     if (nFrames) zstd_dec_frame_sizes_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(frames, nFrames, blocks, counts);
     zstd_dec_frame_offsets_kernel<<<1, 32, 0, st>>>(frames, nFrames, dstCap, counts, total);

@@ -97,9 +97,10 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     CU(cudaStreamSynchronize(st));
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
-    if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64))
+    if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64) ||
+        ctx->decScratch[5].reserve(zstd_dec_entropy_scratch_bytes(hc.nBlocks)))
         return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (input too large for one pass)%s");
-    launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, st);
+    launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, ctx->decScratch[5].p, st, ctx->stream2, ctx->ev[4], ctx->ev[5]);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
     launch_zstd_dec_layout(frames, hc.nFrames, blocks, dstCap, counts, total, st);
@@ -112,7 +113,7 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     CU(cudaMemcpyAsync(&hr.c, counts, sizeof(DecCounts), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&hr.total, total, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
+    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 7;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stat[B200Z_S_DEC_PREPASS_MS] += ms;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[1]); ctx->stat[B200Z_S_DEC_ENTROPY_MS] += ms;
