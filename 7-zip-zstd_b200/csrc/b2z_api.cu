@@ -34,6 +34,8 @@ int b200z_create(b200z_ctx** out, int device) {
       if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
+    for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&ctx->pe[i], cudaEventDisableTiming);
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
     ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1;   // size hints on: lets any decoder (ours included) find frames without walking blocks
@@ -52,6 +54,8 @@ void b200z_destroy(b200z_ctx* ctx) {
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    for (int i = 0; i < 4; i++) if (ctx->pe[i]) cudaEventDestroy(ctx->pe[i]);
     delete ctx;
 }
 
@@ -66,6 +70,7 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_WINDOWLOG: if (v < 10 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "windowLog out of range%s"); ctx->geom.windowLog = (uint32_t)v; return 0;
     case B200Z_P_FLAGS:     if (v & ~1ll) return fail(ctx, B200Z_E_UNSUPPORTED, "only flag bit0 (skippable size hints) is supported%s"); ctx->geom.flags = (uint32_t)v; return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
+    case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
     return fail(ctx, B200Z_E_PARAM, "unknown parameter%s");
 }
@@ -80,6 +85,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_WINDOWLOG: *v = ctx->geom.windowLog; return 0;
     case B200Z_P_FLAGS: *v = ctx->geom.flags; return 0;
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
+    case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     }
     return B200Z_E_PARAM;
 }
@@ -197,21 +203,59 @@ int b200z_zstd_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize
     return 0;
 }
 
+// Host-pointer compress: the stream is cut into batches of whole frames that flow through a three-stage
+// pipeline -- H2D copy of batch i+1 (stream2) | kernels of batch i (stream) | D2H copy of batch i-1 (stream3) --
+// with double-buffered device staging, so PCIe time hides under kernel time when the host buffers are pinned.
+// (The ordered output mirrors ZSTDMT_flushProduced, zstdmt_compress.c:1488.)
 int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize) {
     if (!ctx || !dstSize || (!src && srcSize) || !dst) return B200Z_E_PARAM;
     const size_t bound = b200z_zstd_compress_bound(ctx, srcSize);
     if (dstCap < bound) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_bound%s");
     CU(cudaSetDevice(ctx->device));
-    if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(bound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
-    if (srcSize) CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
-    size_t out = 0;
-    int rc = b200z_zstd_compress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, bound, &out);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
-    *dstSize = out;
+    const uint64_t F = 1ull << ctx->geom.frameLog;
+    uint64_t batch = 1ull << ctx->hostBatchLog; if (batch < F) batch = F;
+    if (srcSize <= batch) {                                        // small input: one shot
+        if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(bound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+        if (srcSize) CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
+        size_t out = 0;
+        int rc = b200z_zstd_compress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, bound, &out);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
+        *dstSize = out;
+        return 0;
+    }
+    const size_t batchBound = b200z_zstd_compress_bound(ctx, batch);
+    if (ctx->dIn.reserve(2 * (batch + 64)) || ctx->dOut.reserve(2 * batchBound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+    uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + batch + 64 };
+    uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + batchBound };
+    const uint64_t nBatches = (srcSize + batch - 1) / batch;
+    auto bsize = [&](uint64_t i) { return (size_t)((srcSize - i * batch) < batch ? (srcSize - i * batch) : batch); };
+    // pe[0..1]: input of buffer b uploaded; pe[2..3]: output of buffer b downloaded
+    CU(cudaMemcpyAsync(dIn[0], src, bsize(0), cudaMemcpyHostToDevice, ctx->stream2));
+    CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
+    size_t outPos = 0;
+    for (uint64_t i = 0; i < nBatches; i++) {
+        const int b = (int)(i & 1);
+        if (i + 1 < nBatches) {                                   // upload the next batch while this one is compressed
+            // its buffer was last read by the kernels of batch i-1, which have been synchronised already
+            CU(cudaMemcpyAsync(dIn[b ^ 1], (const uint8_t*)src + (i + 1) * batch, bsize(i + 1), cudaMemcpyHostToDevice, ctx->stream2));
+            CU(cudaEventRecord(ctx->pe[b ^ 1], ctx->stream2));
+        }
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));                 // input there
+        if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0)); // output buffer drained
+        uint64_t produced = 0;
+        int rc = enc_batch(ctx, dIn[b], bsize(i), dOut[b], &produced, false);   // synchronises ctx->stream
+        if (rc) return rc;
+        CU(cudaMemcpyAsync((uint8_t*)dst + outPos, dOut[b], produced, cudaMemcpyDeviceToHost, ctx->stream3));
+        CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
+        outPos += produced;
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)bsize(i); ctx->stat[B200Z_S_D2H_BYTES] += (double)produced;
+    }
+    CU(cudaStreamSynchronize(ctx->stream3));
+    *dstSize = outPos;
     return 0;
 }
 

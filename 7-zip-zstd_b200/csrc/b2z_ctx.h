@@ -24,7 +24,11 @@ struct Arena {                       // grow-only device buffer
 struct b200z_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;   // side stream (decoder: literals kernel next to the sequences kernel)
+    cudaStream_t stream2 = nullptr;   // side stream (decoder: literals kernel next to the sequences kernel; host path: uploads)
+    cudaStream_t stream3 = nullptr;   // host path: downloads
+    cudaEvent_t pe[4] = {};           // host-path pipeline events
+    uint32_t hostBatchLog = 32;       // bytes per pipeline batch of the host-pointer entry points (4 GiB: a batch must hold
+                                      // thousands of frames to fill the GPU; larger inputs are pipelined)
     b2z::EncGeom geom{};
     int level = 3;
     uint32_t batchLog = 32;

@@ -4,6 +4,7 @@
 // over 128 KiB reads, frame after frame): here one call takes the whole Code() input, every frame
 // of it (zstd or skippable) is located by the prepass and decoded in parallel.
 #include "b2z_ctx.h"
+#include <vector>
 
 using namespace b2z;
 
@@ -123,21 +124,99 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     return 0;
 }
 
+// Host-side split of a compressed stream into batches of whole frames (only when every frame declares its
+// content size): returns false if the stream cannot be split that way (the caller then decodes in one shot).
+struct HostBatch { size_t srcOff, srcEnd; uint64_t dstOff, dstSize; };
+static bool split_frames(const uint8_t* src, size_t srcSize, uint64_t targetOut, std::vector<HostBatch>& out) {
+    size_t ip = 0; HostBatch cur{0, 0, 0, 0}; uint64_t dstPos = 0;
+    while (ip < srcSize) {
+        if (srcSize - ip < 4) return false;
+        const uint32_t magic = rd32(src + ip);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+            if (srcSize - ip < 8) return false;
+            const size_t sz = rd32(src + ip + 4);
+            if (srcSize - ip < 8 + sz) return false;
+            ip += 8 + sz; continue;                                  // hints/skippable data stay attached to the following frame
+        }
+        if (magic != 0xFD2FB528u || srcSize - ip < 6) return false;
+        size_t p = ip + 5; const uint32_t fhd = src[ip + 4];
+        const uint32_t fcsFlag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, didFlag = fhd & 3;
+        if (!single) p += 1;
+        p += didFlag == 3 ? 4 : didFlag;
+        const int fcsBytes = fcsFlag == 0 ? (int)single : (fcsFlag == 1 ? 2 : (fcsFlag == 2 ? 4 : 8));
+        if (!fcsBytes || srcSize < p + (size_t)fcsBytes) return false;
+        uint64_t fcs = 0; for (int i = 0; i < fcsBytes; i++) fcs |= (uint64_t)src[p + i] << (8 * i); if (fcsBytes == 2) fcs += 256;
+        p += fcsBytes;
+        for (;;) {
+            if (srcSize - p < 3) return false;
+            const uint32_t bh = src[p] | (src[p + 1] << 8) | (src[p + 2] << 16); p += 3;
+            const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+            if (type == 3) return false;
+            const size_t adv = type == 1 ? 1 : bsize;
+            if (srcSize - p < adv) return false;
+            p += adv;
+            if (last) break;
+        }
+        if (checksum) { if (srcSize - p < 4) return false; p += 4; }
+        ip = p;
+        cur.srcEnd = ip; cur.dstSize += fcs; dstPos += fcs;
+        if (cur.dstSize >= targetOut) { out.push_back(cur); cur = HostBatch{ ip, ip, dstPos, 0 }; }
+    }
+    if (cur.srcEnd > cur.srcOff || cur.dstSize) { cur.srcEnd = srcSize; out.push_back(cur); }
+    else if (!out.empty()) out.back().srcEnd = srcSize;
+    return true;
+}
+
+// Host-pointer decompress: batches of whole frames flow through H2D (stream2) | decode kernels (stream) | D2H (stream3).
 int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize) {
     if (!ctx || !dstSize || (!src && srcSize) || (!dst && dstCap)) return B200Z_E_PARAM;
     *dstSize = 0;
     if (!srcSize) return 0;
     CU(cudaSetDevice(ctx->device));
-    if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(dstCap + 64)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
-    CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
-    size_t out = 0;
-    int rc = b200z_zstd_decompress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, dstCap, &out);
-    if (rc) return rc;
-    if (out) CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
-    *dstSize = out;
+    std::vector<HostBatch> batches;
+    const uint64_t target = 1ull << ctx->hostBatchLog;
+    if (srcSize <= (target >> 2) || !split_frames((const uint8_t*)src, srcSize, target, batches) || batches.size() < 2) {
+        // one shot
+        if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(dstCap + 64)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+        CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
+        size_t out = 0;
+        int rc = b200z_zstd_decompress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, dstCap, &out);
+        if (rc) return rc;
+        if (out) CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
+        *dstSize = out;
+        return 0;
+    }
+    size_t maxIn = 0; uint64_t maxOut = 0, total = 0;
+    for (const HostBatch& b : batches) { if (b.srcEnd - b.srcOff > maxIn) maxIn = b.srcEnd - b.srcOff; if (b.dstSize > maxOut) maxOut = b.dstSize; total += b.dstSize; }
+    if (total > dstCap) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
+    const size_t inStride = (maxIn + 64 + 255) & ~(size_t)255, outStride = ((size_t)maxOut + 64 + 255) & ~(size_t)255;
+    if (ctx->dIn.reserve(2 * inStride) || ctx->dOut.reserve(2 * outStride)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+    uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + inStride };
+    uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + outStride };
+    const size_t nB = batches.size();
+    CU(cudaMemcpyAsync(dIn[0], (const uint8_t*)src + batches[0].srcOff, batches[0].srcEnd - batches[0].srcOff, cudaMemcpyHostToDevice, ctx->stream2));
+    CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
+    for (size_t i = 0; i < nB; i++) {
+        const int b = (int)(i & 1);
+        if (i + 1 < nB) {
+            CU(cudaMemcpyAsync(dIn[b ^ 1], (const uint8_t*)src + batches[i + 1].srcOff, batches[i + 1].srcEnd - batches[i + 1].srcOff, cudaMemcpyHostToDevice, ctx->stream2));
+            CU(cudaEventRecord(ctx->pe[b ^ 1], ctx->stream2));
+        }
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));
+        if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0));
+        size_t out = 0;
+        int rc = b200z_zstd_decompress_device(ctx, dIn[b], batches[i].srcEnd - batches[i].srcOff, dOut[b], (size_t)batches[i].dstSize, &out);
+        if (rc) return rc;
+        if (out != batches[i].dstSize) return fail(ctx, B200Z_E_CORRUPT, "frame content size mismatch%s");
+        if (out) CU(cudaMemcpyAsync((uint8_t*)dst + batches[i].dstOff, dOut[b], out, cudaMemcpyDeviceToHost, ctx->stream3));
+        CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)(batches[i].srcEnd - batches[i].srcOff); ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
+    }
+    CU(cudaStreamSynchronize(ctx->stream3));
+    *dstSize = (size_t)total;
     return 0;
 }
 

@@ -188,7 +188,7 @@ def main():
     barrier(); T1 = time.perf_counter()
     clocks = sampler.stop(T0, T1)
     elapsed = T1 - T0
-    stats = {k: codec.stat(v) for k, v in dict(match_ms=1, entropy_ms=2, assemble_ms=3, dec_entropy_ms=4, dec_exec_ms=5, launches=6).items()}
+    stats = {k: codec.stat(v) for k, v in dict(match_ms=1, entropy_ms=2, assemble_ms=3, dec_prepass_ms=9, dec_entropy_ms=4, dec_exec_ms=5, launches=6).items()}
     if dist:
         t = torch.tensor([elapsed, t_enc, t_dec], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX); elapsed, t_enc, t_dec = (float(x) for x in t.cpu())

@@ -46,6 +46,7 @@ extern "C" {
 #define B200Z_P_WINDOWLOG   5   /* max match distance log, default = frameLog                            */
 #define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention)   */
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
+#define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
  * measured with CUDA events on the context's stream around each stage */

@@ -100,3 +100,13 @@ def test_device_resident_decode(pkg, codec):
     n = codec.decompress_device(src.data_ptr(), src.numel(), dst.data_ptr(), dst.numel())
     assert n == data.size and bytes(dst.cpu().numpy()) == data.tobytes()
     assert codec.stat(4) > 0 and codec.stat(5) > 0
+
+
+def test_host_pipeline_batches(pkg):
+    """the H2D | kernels | D2H pipeline of the host-pointer entry points (many small batches) gives the same bytes"""
+    data = pkg.corpus.g2(37 * (1 << 20) + 4567).tobytes()
+    c = pkg.Codec(0, host_batch_log=22)
+    comp = c.compress(data)
+    assert comp == helpers.oracle_compress(data)
+    assert c.decompress(comp) == data
+    c.close()
