@@ -48,7 +48,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
-                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut };
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -68,7 +68,7 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_HASHLOG_L: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
     case B200Z_P_HASHLOG_S: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogS out of range%s"); ctx->geom.hashLogS = (uint32_t)v; return 0;
     case B200Z_P_WINDOWLOG: if (v < 10 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "windowLog out of range%s"); ctx->geom.windowLog = (uint32_t)v; return 0;
-    case B200Z_P_FLAGS:     if (v & ~1ll) return fail(ctx, B200Z_E_UNSUPPORTED, "only flag bit0 (skippable size hints) is supported%s"); ctx->geom.flags = (uint32_t)v; return 0;
+    case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (uint32_t)v; return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
@@ -125,6 +125,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
     bad |= ctx->blockOff.reserve((nBlocks + 1) * 8);
     bad |= ctx->frameOff.reserve((nFrames + 2) * 8);
     bad |= ctx->scalars.reserve(64);
+    bad |= ctx->cks.reserve((nFrames + 2) * 4);
     return bad ? fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s") : 0;
 }
 
@@ -150,8 +151,8 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
                                 (const uint32_t*)ctx->nlit.p, (uint8_t*)ctx->slots.p, (uint32_t*)ctx->slotSize.p, nBlocks, st);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[2], st));
-        launch_zstd_enc_assemble(n, g, (const uint8_t*)ctx->slots.p, (const uint32_t*)ctx->slotSize.p, nBlocks, (uint64_t*)ctx->blockOff.p,
-                                 d_dst, (uint64_t*)ctx->scalars.p, (uint64_t*)ctx->frameOff.p, st);
+        launch_zstd_enc_assemble(d_src, n, g, (const uint8_t*)ctx->slots.p, (const uint32_t*)ctx->slotSize.p, nBlocks, (uint64_t*)ctx->blockOff.p,
+                                 d_dst, (uint64_t*)ctx->scalars.p, (uint64_t*)ctx->frameOff.p, (uint32_t*)ctx->cks.p, st);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[3], st));
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
@@ -181,9 +182,11 @@ int b200z_zstd_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize
     if (dstCap < b200z_zstd_compress_bound(ctx, srcSize)) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_bound%s");
     CU(cudaSetDevice(ctx->device));
     if (srcSize == 0) {
-        size_t o = 0; uint8_t tmp[21];
-        if (ctx->geom.flags & 1u) { const uint8_t k[12] = { 0x50, 0x2A, 0x4D, 0x18, 4, 0, 0, 0, 9, 0, 0, 0 }; memcpy(tmp, k, 12); o = 12; }
-        memcpy(tmp + o, kEmptyFrame, 9); o += 9;
+        size_t o = 0; uint8_t tmp[32];
+        const bool ck = (ctx->geom.flags & 2u) != 0;
+        if (ctx->geom.flags & 1u) { const uint8_t k[12] = { 0x50, 0x2A, 0x4D, 0x18, 4, 0, 0, 0, (uint8_t)(ck ? 13 : 9), 0, 0, 0 }; memcpy(tmp, k, 12); o = 12; }
+        memcpy(tmp + o, kEmptyFrame, 9); if (ck) tmp[o + 4] = 0x24; o += 9;
+        if (ck) { const uint8_t x[4] = { 0x99, 0xE9, 0xD8, 0x51 }; memcpy(tmp + o, x, 4); o += 4; }      // XXH64("") low 32 bits
         CU(cudaMemcpyAsync(d_dst, tmp, o, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         *dstSize = o; return 0;

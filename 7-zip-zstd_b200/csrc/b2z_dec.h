@@ -12,6 +12,7 @@ namespace b2z {
 #define B2Z_DERR_UNSUPPORTED  2u
 #define B2Z_DERR_TABLE_FULL   4u
 #define B2Z_DERR_DSTSIZE      8u
+#define B2Z_DERR_CHECKSUM     16u
 
 struct DecFrame {
     uint64_t srcOff;        // first byte of the frame header
@@ -22,6 +23,7 @@ struct DecFrame {
     uint32_t firstBlock, nBlocks;
     uint32_t checksum;      // 1 if a 4-byte content checksum follows the last block
     uint32_t pad;           // D0 scratch (frame header bytes)
+    uint64_t endOff;        // offset just past the frame in src (the checksum, if any, is the 4 bytes before it)
 };
 
 struct DecBlock {
@@ -54,5 +56,8 @@ void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* 
 // stage D3: one warp per frame: execute sequences block after block
 void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks,
                           const uint8_t* lits, const uint64_t* seqs, uint8_t* dst, DecCounts* counts, cudaStream_t st);
+
+// content checksums (XXH64 low 32 bits) of the frames that carry one: one thread per frame, after D3
+void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st);
 
 }  // namespace b2z

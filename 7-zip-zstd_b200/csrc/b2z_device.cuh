@@ -54,4 +54,56 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
     return x - v;
 }
 
+// XXH64 (seed 0) of `len` bytes at an 8-byte aligned address; one thread walks one buffer (four independent
+// accumulators give the instruction-level parallelism).  Content checksum of a zstd frame = low 32 bits
+// (C/zstd/zstd_compress.c:5344-5400, ../hashes/xxhash.c).
+__device__ __forceinline__ uint64_t xxh_rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t in) { return xxh_rotl(acc + in * 0xC2B2AE3D27D4EB4Full, 31) * 0x9E3779B185EBCA87ull; }
+__device__ __forceinline__ uint64_t xxh_merge(uint64_t h, uint64_t v) { return (h ^ xxh_round(0, v)) * 0x9E3779B185EBCA87ull + 0x85EBCA77C2B2AE63ull; }
+__device__ inline uint64_t xxh64_device(const uint8_t* data, uint64_t len) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(data);
+    uint64_t i = 0, h;
+    if (len >= 32) {
+        uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0ull - P1;
+        const uint64_t nStripes = len >> 5;
+        for (uint64_t k = 0; k < nStripes; k++) { v1 = xxh_round(v1, w[4 * k]); v2 = xxh_round(v2, w[4 * k + 1]); v3 = xxh_round(v3, w[4 * k + 2]); v4 = xxh_round(v4, w[4 * k + 3]); }
+        i = nStripes << 5;
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    } else h = P5;
+    h += len;
+    for (; i + 8 <= len; i += 8) { h ^= xxh_round(0, w[i >> 3]); h = xxh_rotl(h, 27) * P1 + P4; }
+    if (i + 4 <= len) { h ^= (uint64_t)(*reinterpret_cast<const uint32_t*>(data + i)) * P1; h = xxh_rotl(h, 23) * P2 + P3; i += 4; }
+    for (; i < len; i++) { h ^= data[i] * P5; h = xxh_rotl(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
+// same for a buffer at any byte alignment (decoder outputs of frames that follow an odd-sized frame)
+__device__ inline uint64_t xxh64_device_unaligned(const uint8_t* data, uint64_t len) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(data) & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 7u) * 8u;
+    auto rd = [&](uint64_t byteOff) -> uint64_t {                     // 8 bytes at data+byteOff (multiple of 8), never reading past data+len
+        if (byteOff + 16 <= len) { const uint64_t i = byteOff >> 3; return funnel64(w[i], w[i + 1], sh); }
+        uint64_t v = 0; for (int b = 0; b < 8; b++) v |= (uint64_t)data[byteOff + b] << (8 * b); return v;
+    };
+    uint64_t i = 0, h;
+    if (len >= 32) {
+        uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0ull - P1;
+        const uint64_t nStripes = len >> 5;
+        for (uint64_t k = 0; k < nStripes; k++) { v1 = xxh_round(v1, rd(32 * k)); v2 = xxh_round(v2, rd(32 * k + 8)); v3 = xxh_round(v3, rd(32 * k + 16)); v4 = xxh_round(v4, rd(32 * k + 24)); }
+        i = nStripes << 5;
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    } else h = P5;
+    h += len;
+    for (; i + 8 <= len; i += 8) { h ^= xxh_round(0, rd(i)); h = xxh_rotl(h, 27) * P1 + P4; }
+    if (i + 4 <= len) { uint32_t v = 0; for (int b = 0; b < 4; b++) v |= (uint32_t)data[i + b] << (8 * b); h ^= (uint64_t)v * P1; h = xxh_rotl(h, 23) * P2 + P3; i += 4; }
+    for (; i < len; i++) { h ^= data[i] * P5; h = xxh_rotl(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
 }  // namespace b2z

@@ -22,9 +22,9 @@ void launch_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, const EncGeom
                              uint8_t* slots, uint32_t* slotSize, uint32_t nBlocks, cudaStream_t st);
 
 // frame assembly: offsets (one CTA scan) + gather of slots into contiguous frames
-void launch_zstd_enc_assemble(uint64_t srcSize, const EncGeom& g, const uint8_t* slots, const uint32_t* slotSize,
+void launch_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint8_t* slots, const uint32_t* slotSize,
                               uint32_t nBlocks, uint64_t* blockOff /* [nBlocks+1] scratch */, uint8_t* dst,
                               uint64_t* outSize /* device scalar */, uint64_t* frameOff /* [nFrames+1] or null */,
-                              cudaStream_t st);
+                              uint32_t* cks /* [nFrames] scratch (flag bit1) */, cudaStream_t st);
 
 }  // namespace b2z

@@ -192,7 +192,7 @@ __global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uin
                 if (fsz >= 9 && srcSize - (ip + 12) >= fsz) {
                     if (nf >= frameCap) { status = B2Z_DERR_TABLE_FULL; break; }
                     DecFrame fr; fr.srcOff = ip + 12; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = ip + 12 + fsz;   // regen: end offset (until D2)
-                    fr.firstBlock = 0; fr.nBlocks = 0; fr.checksum = 0; fr.pad = 1;                                                     // pad: 1 = end offset is a hint
+                    fr.firstBlock = 0; fr.nBlocks = 0; fr.checksum = 0; fr.pad = 1; fr.endOff = ip + 12 + fsz;                          // pad: 1 = end offset is a hint
                     frames[nf++] = fr;
                     ip += 12 + fsz; continue;
                 }
@@ -207,7 +207,7 @@ __global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uin
         status = walk_blocks(S, ip + h.hdrBytes, srcSize, &nb, &end, nullptr, 0, nf, 0);
         if (status) break;
         if (h.checksum) { if (srcSize - end < 4) { status = B2Z_DERR_CORRUPT; break; } end += 4; }
-        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = end; fr.firstBlock = 0; fr.nBlocks = nb; fr.checksum = 0; fr.pad = 0;
+        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = end; fr.firstBlock = 0; fr.nBlocks = nb; fr.checksum = 0; fr.pad = 0; fr.endOff = end;
         frames[nf++] = fr;
         ip = end;
     }
@@ -808,7 +808,27 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
     }
 }
 
+// ---------------------------------------------------------------- checksum verification
+__global__ void zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, uint32_t nFrames,
+                                       const uint8_t* __restrict__ dst, DecCounts* counts) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFrames || counts->status) return;
+    const DecFrame fr = frames[f];
+    if (!fr.checksum) return;
+    const uint8_t* c = src + fr.endOff - 4;
+    const uint32_t want = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+    // frame outputs start at arbitrary byte offsets: hash from the aligned base when possible, else byte-wise tail rules apply
+    const uint8_t* p = dst + fr.dstOff;
+    uint64_t h;
+    if (((uintptr_t)p & 7u) == 0) h = xxh64_device(p, fr.regen);
+    else h = xxh64_device_unaligned(p, fr.regen);
+    if ((uint32_t)h != want) atomicOr(&counts->status, B2Z_DERR_CHECKSUM);
+}
+
 // ---------------------------------------------------------------- launchers
+void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st) {
+    if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 63) / 64, 64, 0, st>>>(src, frames, nFrames, dst, counts);
+}
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st) {
     zstd_dec_find_frames_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, counts);
 }

@@ -15,6 +15,7 @@ static int dec_status_to_rc(b200z_ctx* ctx, uint32_t st) {
     if (st & B2Z_DERR_UNSUPPORTED) return fail(ctx, B200Z_E_UNSUPPORTED, "dictionary or window > 1 GiB frames are not supported%s");
     if (st & B2Z_DERR_DSTSIZE) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
     if (st & B2Z_DERR_CORRUPT) return fail(ctx, B200Z_E_CORRUPT, "corrupt zstd data%s");
+    if (st & B2Z_DERR_CHECKSUM) return fail(ctx, B200Z_E_CHECKSUM, "content checksum mismatch%s");
     return 0;
 }
 
@@ -108,6 +109,8 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     CU(cudaGetLastError());
     launch_zstd_dec_exec((const uint8_t*)d_src, frames, hc.nFrames, blocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
                          (uint8_t*)d_dst, counts, st);
+    CU(cudaGetLastError());
+    launch_zstd_dec_verify((const uint8_t*)d_src, frames, hc.nFrames, (const uint8_t*)d_dst, counts, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[2], st));
     struct { DecCounts c; uint64_t total; } hr;

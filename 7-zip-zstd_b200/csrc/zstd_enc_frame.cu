@@ -65,9 +65,18 @@ zstd_enc_offsets_kernel(uint64_t srcSize, EncGeom g, const uint32_t* __restrict_
     (void)srcSize;
 }
 
+// content checksum of every frame (flag bit1): one thread per frame
+__global__ void zstd_enc_checksum_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cks, uint32_t nFrames) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFrames) return;
+    const uint64_t F = 1ull << g.frameLog, f0 = (uint64_t)f << g.frameLog;
+    const uint64_t fn = (srcSize - f0) < F ? (srcSize - f0) : F;
+    cks[f] = (uint32_t)xxh64_device(src + f0, fn);
+}
+
 __global__ void __launch_bounds__(256)
 zstd_enc_gather_kernel(uint64_t srcSize, EncGeom g, const uint8_t* __restrict__ slots, const uint32_t* __restrict__ slotSize,
-                       const uint64_t* __restrict__ blockOff, uint32_t nBlocks, uint8_t* __restrict__ dst) {
+                       const uint64_t* __restrict__ blockOff, uint32_t nBlocks, uint8_t* __restrict__ dst, const uint32_t* __restrict__ cks) {
     const uint32_t b = blockIdx.x, tid = threadIdx.x;
     const uint32_t bpf = 1u << (g.frameLog - 17u);
     const uint8_t* s = slots + (size_t)b * B2Z_SLOT;
@@ -91,6 +100,11 @@ zstd_enc_gather_kernel(uint64_t srcSize, EncGeom g, const uint8_t* __restrict__ 
         dq[i] = v;
     }
     for (uint32_t i = h + body + tid; i < n; i += 256u) d[i] = s[i];
+    // content checksum after the frame's last block
+    if ((g.flags & 2u) && tid == 0 && ((b % bpf) == bpf - 1u || b == nBlocks - 1u)) {
+        const uint32_t c = cks[b / bpf];
+        d[n] = (uint8_t)c; d[n + 1] = (uint8_t)(c >> 8); d[n + 2] = (uint8_t)(c >> 16); d[n + 3] = (uint8_t)(c >> 24);
+    }
     // frame header by the first block's CTA
     if ((b % bpf) == 0 && tid == 0) {
         const uint64_t f = b / bpf, F = 1ull << g.frameLog;
@@ -112,12 +126,14 @@ zstd_enc_gather_kernel(uint64_t srcSize, EncGeom g, const uint8_t* __restrict__ 
     }
 }
 
-void launch_zstd_enc_assemble(uint64_t srcSize, const EncGeom& g, const uint8_t* slots, const uint32_t* slotSize,
+void launch_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint8_t* slots, const uint32_t* slotSize,
                               uint32_t nBlocks, uint64_t* blockOff, uint8_t* dst, uint64_t* outSize, uint64_t* frameOff,
-                              cudaStream_t st) {
+                              uint32_t* cks, cudaStream_t st) {
     if (!nBlocks) return;
+    if (g.flags & 2u) { const uint32_t nFrames = (uint32_t)((srcSize + (1ull << g.frameLog) - 1) >> g.frameLog);
+                        zstd_enc_checksum_kernel<<<(nFrames + 63) / 64, 64, 0, st>>>(src, srcSize, g, cks, nFrames); }
     zstd_enc_offsets_kernel<<<1, 1024, 0, st>>>(srcSize, g, slotSize, nBlocks, blockOff, outSize, frameOff);
-    zstd_enc_gather_kernel<<<nBlocks, 256, 0, st>>>(srcSize, g, slots, slotSize, blockOff, nBlocks, dst);
+    zstd_enc_gather_kernel<<<nBlocks, 256, 0, st>>>(srcSize, g, slots, slotSize, blockOff, nBlocks, dst, cks);
 }
 
 }  // namespace b2z

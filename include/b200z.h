@@ -44,7 +44,8 @@ extern "C" {
 #define B200Z_P_HASHLOG_L   3   /* long-hash table log, default 17  (clevels.h:31 hashLog)               */
 #define B200Z_P_HASHLOG_S   4   /* short-hash table log, default 16 (clevels.h:31 chainLog)              */
 #define B200Z_P_WINDOWLOG   5   /* max match distance log, default = frameLog                            */
-#define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention)   */
+#define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention; default on)
+                                   bit1: XXH64 content checksum per frame (ZstdHandler.cpp:275 sets it for .zst) */
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 

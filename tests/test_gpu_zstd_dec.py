@@ -110,3 +110,30 @@ def test_host_pipeline_batches(pkg):
     assert comp == helpers.oracle_compress(data)
     assert c.decompress(comp) == data
     c.close()
+
+
+def test_content_checksums(pkg, inputs):
+    """flag bit1: frames carry XXH64 checksums -- same bytes as the oracle, accepted by the reference decoder
+    (which verifies them), verified by the GPU decoder, and a flipped checksum is reported as such."""
+    data = inputs["mixed"] + inputs["g2_1m"][:777_777]
+    c = pkg.Codec(0, flags=3)
+    comp = c.compress(data)
+    assert comp == helpers.oracle_compress(data, flags=3)
+    assert c.compress(b"") == helpers.oracle_compress(b"", flags=3)
+    if helpers.ref_available():
+        assert helpers.ref_decompress(comp, len(data)) == data
+        assert helpers.ref_decompress(c.compress(b""), 0) == b""
+    assert c.decompress(comp) == data
+    bad = bytearray(comp); bad[-1] ^= 0x40                                   # last byte = part of the last frame's checksum
+    with pytest.raises(pkg.B200zError) as e:
+        c.decompress(bytes(bad), max_size=len(data))
+    assert e.value.code == -8
+    if helpers.ref_available():                                               # reference-made frames with checksums at odd output offsets
+        a, b = inputs["g2_100k"][:99_999], inputs["tile"][:123_457]
+        two = helpers.ref_compress(a, 3, 1) + helpers.ref_compress(b, 5, 1)
+        assert c.decompress(two, max_size=len(a) + len(b)) == a + b
+        bad = bytearray(two); bad[len(helpers.ref_compress(a, 3, 1)) - 2] ^= 1
+        with pytest.raises(pkg.B200zError) as e:
+            c.decompress(bytes(bad), max_size=len(a) + len(b))
+        assert e.value.code == -8
+    c.close()
