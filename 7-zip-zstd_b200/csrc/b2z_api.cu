@@ -48,7 +48,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
-                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks };
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -56,6 +56,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     for (int i = 0; i < 4; i++) if (ctx->pe[i]) cudaEventDestroy(ctx->pe[i]);
+    if (ctx->hostOne) cudaFreeHost(ctx->hostOne);
     delete ctx;
 }
 
@@ -130,7 +131,8 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
 }
 
 // compress [d_src, d_src+n) (n > 0, one batch) to d_dst; returns produced bytes through *produced
-static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t* produced, bool stageMOnly) {
+static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t* produced, bool stageMOnly,
+                     const uint32_t* ready = nullptr, uint32_t readyShift = 0) {
     int rc = enc_reserve(ctx, n);
     if (rc) return rc;
     const EncGeom& g = ctx->geom;
@@ -142,7 +144,7 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev[0], st));
     launch_zstd_enc_match(d_src, n, g, (uint32_t*)ctx->tables.p, nWarps, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
-                          (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, st);
+                          (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, ready, readyShift, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
@@ -217,13 +219,30 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
     CU(cudaSetDevice(ctx->device));
     const uint64_t F = 1ull << ctx->geom.frameLog;
     uint64_t batch = 1ull << ctx->hostBatchLog; if (batch < F) batch = F;
-    if (srcSize <= batch) {                                        // small input: one shot
-        if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(bound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
-        if (srcSize) CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
+    if (srcSize <= batch) {
+        // one batch: the upload is cut into chunks on stream2, each followed by a flag write; stage M starts at once and
+        // its frame-warps wait for their chunk, so the H2D time hides under the match kernel
+        if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(bound) || ctx->ready.reserve(256)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+        if (!ctx->hostOne) { if (cudaHostAlloc((void**)&ctx->hostOne, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(ctx, B200Z_E_MEMORY, "pinned allocation failed%s"); } *ctx->hostOne = 1u; }
         size_t out = 0;
-        int rc = b200z_zstd_compress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, bound, &out);
-        if (rc) return rc;
+        if (srcSize == 0) { int rc = b200z_zstd_compress_device(ctx, ctx->dIn.p, 0, ctx->dOut.p, bound, &out); if (rc) return rc; }
+        else {
+            uint32_t shift = 20; while (((srcSize - 1) >> shift) >= 16) shift++;          // <= 16 chunks of >= 1 MiB
+            const uint32_t nChunks = (uint32_t)(((srcSize - 1) >> shift) + 1);
+            CU(cudaMemsetAsync(ctx->ready.p, 0, 256, ctx->stream));
+            CU(cudaEventRecord(ctx->pe[0], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->stream2, ctx->pe[0], 0));
+            for (uint32_t c = 0; c < nChunks; c++) {
+                const size_t off = (size_t)c << shift, len = (srcSize - off) < ((size_t)1 << shift) ? (srcSize - off) : ((size_t)1 << shift);
+                CU(cudaMemcpyAsync((uint8_t*)ctx->dIn.p + off, (const uint8_t*)src + off, len, cudaMemcpyHostToDevice, ctx->stream2));
+                CU(cudaMemcpyAsync((uint32_t*)ctx->ready.p + c, ctx->hostOne, 4, cudaMemcpyHostToDevice, ctx->stream2));
+            }
+            uint64_t produced = 0;
+            int rc = enc_batch(ctx, (const uint8_t*)ctx->dIn.p, srcSize, (uint8_t*)ctx->dOut.p, &produced, false, (const uint32_t*)ctx->ready.p, shift);
+            if (rc) { cudaStreamSynchronize(ctx->stream2); return rc; }
+            out = (size_t)produced;
+        }
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
         CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         ctx->stat[B200Z_S_D2H_BYTES] += (double)out;

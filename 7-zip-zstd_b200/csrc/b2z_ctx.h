@@ -33,7 +33,8 @@ struct b200z_ctx {
     int level = 3;
     uint32_t batchLog = 32;
     uint32_t smCount = 148;
-    Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks;
+    Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready;
+    uint32_t* hostOne = nullptr;      // pinned constant 1 (chunk-arrival flags of the host-pointer path)
     Arena decScratch[8];
     cudaEvent_t ev[8] = {};
     double stat[16] = {0};

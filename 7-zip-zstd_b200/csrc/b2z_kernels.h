@@ -14,7 +14,8 @@ struct EncGeom { uint32_t frameLog, hashLogL, hashLogS, windowLog, flags; };
 
 // stage M: one warp per frame -> per-block final sequences + literal bytes
 void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,
-                           uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, cudaStream_t st);
+                           uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit,
+                           const uint32_t* ready /* null, or per-chunk arrival flags */, uint32_t readyShift, cudaStream_t st);
 
 // stage E: one warp per 128 KiB block -> compressed block (with 3-byte header) in its slot
 void launch_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, const EncGeom& g,

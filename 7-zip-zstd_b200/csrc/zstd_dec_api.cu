@@ -67,7 +67,11 @@ int b200z_zstd_frame_info(const void* srcv, size_t srcSize, uint64_t* contentSiz
     return unknown ? B200Z_E_UNSUPPORTED : B200Z_OK;
 }
 
-int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_dst, size_t dstCap, size_t* dstSize) {
+}  // extern "C"
+
+// hostDst != null: the output is also downloaded (after the execute kernel: every frame-warp is latency-bound and
+// they all finish together, so splitting the download by frame groups only serialises the groups -- measured)
+static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_dst, size_t dstCap, size_t* dstSize, void* hostDst) {
     if (!ctx || !dstSize || (!d_src && srcSize) || (!d_dst && dstCap)) return B200Z_E_PARAM;
     if ((uintptr_t)d_src & 7u) return fail(ctx, B200Z_E_PARAM, "device source must be 8-byte aligned%s");
     *dstSize = 0;
@@ -123,8 +127,15 @@ int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSi
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[1]); ctx->stat[B200Z_S_DEC_ENTROPY_MS] += ms;
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_DEC_EXEC_MS] += ms;
     if (hr.c.status) return dec_status_to_rc(ctx, hr.c.status);
+    if (hostDst && hr.total) { CU(cudaMemcpyAsync(hostDst, d_dst, hr.total, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); ctx->stat[B200Z_S_D2H_BYTES] += (double)hr.total; }
     *dstSize = (size_t)hr.total;
     return 0;
+}
+
+extern "C" {
+
+int b200z_zstd_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_dst, size_t dstCap, size_t* dstSize) {
+    return dec_impl(ctx, d_src, srcSize, d_dst, dstCap, dstSize, nullptr);
 }
 
 // Host-side split of a compressed stream into batches of whole frames (only when every frame declares its
@@ -184,11 +195,8 @@ int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, 
         CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
         ctx->stat[B200Z_S_H2D_BYTES] += (double)srcSize;
         size_t out = 0;
-        int rc = b200z_zstd_decompress_device(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, dstCap, &out);
+        int rc = dec_impl(ctx, ctx->dIn.p, srcSize, ctx->dOut.p, dstCap, &out, dst);
         if (rc) return rc;
-        if (out) CU(cudaMemcpyAsync(dst, ctx->dOut.p, out, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
         *dstSize = out;
         return 0;
     }

@@ -100,7 +100,8 @@ struct Emitter {
 __global__ void __launch_bounds__(B2Z_MATCH_THREADS)
 zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ tables,
                       uint64_t* __restrict__ seqs, uint32_t* __restrict__ nseq,
-                      uint8_t* __restrict__ lits, uint32_t* __restrict__ nlit) {
+                      uint8_t* __restrict__ lits, uint32_t* __restrict__ nlit,
+                      const volatile uint32_t* ready, uint32_t readyShift) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warpSlot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -118,6 +119,9 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
         const uint32_t n = (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
         const uint64_t* __restrict__ w = reinterpret_cast<const uint64_t*>(src + f0);
         const uint32_t nWords = (n + 7u) >> 3;
+        // host-pointer path: the input is still being uploaded chunk by chunk while this kernel runs; a frame starts
+        // once the flag of the chunk that holds its last byte has been set (by a stream-ordered copy after the chunk)
+        if (ready) { uint32_t spins = 0; while (ready[(f0 + n - 1u) >> readyShift] == 0u && ++spins < (1u << 21)) __nanosleep(2000); __syncwarp(); }   // bounded: never hangs the GPU
         // clear this warp's tables (16-byte stores)
         {
             uint4* t4 = reinterpret_cast<uint4*>(TL);
@@ -203,11 +207,12 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
 }
 
 void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,
-                           uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, cudaStream_t st) {
+                           uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, const uint32_t* ready, uint32_t readyShift,
+                           cudaStream_t st) {
     if (srcSize == 0) return;
     const uint32_t warpsPerCta = B2Z_MATCH_THREADS / 32;
     const uint32_t grid = (nWarps + warpsPerCta - 1) / warpsPerCta;
-    zstd_enc_match_kernel<<<grid, B2Z_MATCH_THREADS, 0, st>>>(src, srcSize, g, tables, seqs, nseq, lits, nlit);
+    zstd_enc_match_kernel<<<grid, B2Z_MATCH_THREADS, 0, st>>>(src, srcSize, g, tables, seqs, nseq, lits, nlit, ready, readyShift);
 }
 
 }  // namespace b2z
