@@ -38,6 +38,7 @@ int b200z_create(b200z_ctx** out, int device) {
     for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&ctx->pe[i], cudaEventDisableTiming);
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
+    ctx->geom.rowLog = B2Z_DEF_ROWLOG;
     ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1;   // size hints on: lets any decoder (ours included) find frames without walking blocks
     *out = ctx;
     return B200Z_OK;
@@ -71,6 +72,7 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_WINDOWLOG: if (v < 10 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "windowLog out of range%s"); ctx->geom.windowLog = (uint32_t)v; return 0;
     case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (uint32_t)v; return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
+    case B200Z_P_ROWLOG:    if (v < 8 || v > 18) return fail(ctx, B200Z_E_PARAM, "rowLog out of range%s"); ctx->geom.rowLog = (uint32_t)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
     return fail(ctx, B200Z_E_PARAM, "unknown parameter%s");
@@ -87,6 +89,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_FLAGS: *v = ctx->geom.flags; return 0;
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
+    case B200Z_P_ROWLOG: *v = ctx->geom.rowLog; return 0;
     }
     return B200Z_E_PARAM;
 }
@@ -114,7 +117,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
     const uint64_t nFrames = (batchBytes + F - 1) / F;
     const uint64_t nBlocks = (batchBytes + B2Z_BLOCK - 1) / B2Z_BLOCK + 1;
     const uint32_t nWarps = match_warps(ctx, nFrames);
-    const size_t tableBytes = ((size_t)(1u << ctx->geom.hashLogL) + (1u << ctx->geom.hashLogS)) * 4u;
+    const size_t tableBytes = (size_t)64 << ctx->geom.rowLog;           // row-hash table: 2^rowLog rows of 64 bytes per frame-warp
     int bad = 0;
     bad |= ctx->tables.reserve(tableBytes * nWarps);
     bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);

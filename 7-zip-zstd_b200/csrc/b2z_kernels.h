@@ -10,7 +10,7 @@
 
 namespace b2z {
 
-struct EncGeom { uint32_t frameLog, hashLogL, hashLogS, windowLog, flags; };
+struct EncGeom { uint32_t frameLog, hashLogL, hashLogS, windowLog, flags, rowLog; };
 
 // stage M: one warp per frame -> per-block final sequences + literal bytes
 void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,

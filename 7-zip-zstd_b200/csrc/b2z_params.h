@@ -13,6 +13,8 @@
 #define B2Z_DEF_FRAMELOG   20      /* independent zstd frame = 1 MiB of input                */
 #define B2Z_DEF_HASHLOG_L  17      /* long (8-byte) hash table entries  (clevels.h:31 H17)   */
 #define B2Z_DEF_HASHLOG_S  16      /* short (5-byte) hash table entries (clevels.h:31 C16)   */
+#define B2Z_DEF_ROWLOG     14      /* row-hash match finder: 2^14 rows of 64 bytes = 1 MiB per frame-warp   */
+#define B2Z_ROW_WAYS       15u     /* entries per 64-byte row of the row-hash finder (16th word = head) */
 #define B2Z_STEP           32u     /* positions per warp step                                */
 #define B2Z_LAZY_GAIN      2u      /* defer a match when the next position's is this much longer */
 #define B2Z_MAX_FRAMELOG   24

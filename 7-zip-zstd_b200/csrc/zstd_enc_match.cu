@@ -32,36 +32,66 @@ struct StepA {               // per-lane results of stage A
     uint32_t candL, candS;   // candidate position + 1 (0 = none), frame-relative
 };
 
+// Row-hash match finder, one step.  The table is 2^rowLog rows of 64 bytes: 15 entries (newest at head-1, circular)
+// + the head index in word 15.  A position's row is chosen by the 5-byte hash, entries carry a tag from the
+// 8-byte hash, so ONE 64-byte line per position answers both questions of the reference's double-fast finder
+// (zstd_double_fast.c:103-330): "newest entry with my tag" (8-byte class, long candidate) and "newest entry"
+// (5-byte class, short candidate).  Lanes of one step that fall into the same row behave as if they had inserted
+// in lane order (oracle: position-by-position loop): a lane sees the entries of its lower lanes first, then the
+// 15 - rank newest entries of the stored row; every lane writes its own slot head+rank, the highest lane the head.
 __device__ __forceinline__ StepA stage_a(const uint64_t* __restrict__ w, uint32_t nWords, uint32_t n, uint32_t base,
-                                         uint32_t lane, uint32_t* __restrict__ TL, uint32_t* __restrict__ TS,
-                                         uint32_t HL, uint32_t HS, uint32_t tagBits) {
+                                         uint32_t lane, uint32_t* __restrict__ TR, uint32_t rowLog, uint32_t tagBits) {
     StepA r; r.candL = 0; r.candS = 0;
     const uint32_t p = base + lane, tagMask = (1u << tagBits) - 1u;
     r.v = ld64u(w, p, nWords);
     const bool hashable = p + 8u <= n;
     const uint64_t hl = r.v * B2Z_PRIME8, hs = (r.v << 24) * B2Z_PRIME5;
-    const uint32_t keyL = (uint32_t)(hl >> (64u - HL - tagBits)), keyS = (uint32_t)(hs >> (64u - HS - tagBits));
-    uint32_t* sl = TL + (keyL >> tagBits);
-    uint32_t* ss = TS + (keyS >> tagBits);
-    uint32_t eL = 0, eS = 0;
-    if (hashable) { eL = __ldcg(sl); eS = __ldcg(ss); }
-    // same-step resolution: the latest lower lane that hits the same BUCKET owns the slot (it would
-    // have overwritten it in sequential order); it is a candidate only if its tag matches too
-    const uint32_t uniq = 0x80000000u | lane;                // buckets are < 2^22
-    const uint32_t mL = __match_any_sync(B2Z_FULL, hashable ? (keyL >> tagBits) : uniq);
-    const uint32_t mS = __match_any_sync(B2Z_FULL, hashable ? (keyS >> tagBits) : uniq);
-    const uint32_t lt = lanemask_lt();
-    const uint32_t lowL = mL & lt, lowS = mS & lt;
-    const uint32_t jL = lowL ? highbit32(lowL) : 0u, jS = lowS ? highbit32(lowS) : 0u;
-    const uint32_t keyLj = __shfl_sync(B2Z_FULL, keyL, jL), keySj = __shfl_sync(B2Z_FULL, keyS, jS);
+    const uint32_t rowIdx = (uint32_t)(hs >> (64u - rowLog)), t8 = (uint32_t)(hl >> (64u - tagBits)) & tagMask;
+    uint32_t* row = TR + (size_t)rowIdx * 16u;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
     if (hashable) {
-        if (lowL) { if (keyLj == keyL) r.candL = base + jL + 1u; }
-        else if (eL && (eL & tagMask) == (keyL & tagMask)) r.candL = eL >> tagBits;
-        if (lowS) { if (keySj == keyS) r.candS = base + jS + 1u; }
-        else if (eS && (eS & tagMask) == (keyS & tagMask)) r.candS = eS >> tagBits;
-        // insert: the highest lane of each bucket group holds the latest position
-        if ((mL >> lane) == 1u) __stcg(sl, ((p + 1u) << tagBits) | (keyL & tagMask));
-        if ((mS >> lane) == 1u) __stcg(ss, ((p + 1u) << tagBits) | (keyS & tagMask));
+        const uint4* r4 = reinterpret_cast<const uint4*>(row);
+        q0 = __ldcg(r4); q1 = __ldcg(r4 + 1); q2 = __ldcg(r4 + 2); q3 = __ldcg(r4 + 3);
+    }
+    const uint32_t g = __match_any_sync(B2Z_FULL, hashable ? rowIdx : (0x80000000u | lane));
+    const uint32_t lower = g & lanemask_lt();
+    const uint32_t rank = (uint32_t)__popc(lower), gsize = (uint32_t)__popc(g);
+    // lower lanes of my row: newest first = highest lane first (rare: only when some row is hit twice in this step)
+    uint32_t intraL = 0xFFFFFFFFu;                              // lane index of the highest lower lane with my tag
+    if (__any_sync(B2Z_FULL, lower != 0u)) {
+        for (uint32_t j = 0; j < 31u; j++) {
+            const uint32_t tj = __shfl_sync(B2Z_FULL, t8, j);
+            // lane j's entry is still in the row when I arrive only if fewer than 15 group lanes sit between us
+            if (((lower >> j) & 1u) && tj == t8 && rank - (uint32_t)__popc(g & ((1u << j) - 1u)) <= B2Z_ROW_WAYS) intraL = j;
+        }
+    }
+    if (hashable) {
+        const uint32_t e[16] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
+        const uint32_t head = e[15];
+        uint32_t cl = 0, cs = 0;
+        if (lower) { cs = base + (31u - (uint32_t)__clz((int)lower)) + 1u; if (intraL != 0xFFFFFFFFu) cl = base + intraL + 1u; }
+        if (!cl && rank < B2Z_ROW_WAYS) {
+            // stored entries, newest first; only the 15 - rank newest are still there after my lower lanes' inserts
+            const uint32_t alive = B2Z_ROW_WAYS - rank;
+#pragma unroll
+            for (uint32_t k = 1; k <= B2Z_ROW_WAYS; k++) {
+                if (k <= alive) {
+                    // slot (head + WAYS - k) % WAYS, selected without dynamic register indexing
+                    const uint32_t slot = (head + B2Z_ROW_WAYS - k) % B2Z_ROW_WAYS;
+                    uint32_t ev = 0;
+#pragma unroll
+                    for (uint32_t i = 0; i < B2Z_ROW_WAYS; i++) if (slot == i) ev = e[i];
+                    if (!ev) break;
+                    if (!cs) cs = ev >> tagBits;
+                    if ((ev & tagMask) == t8) { cl = ev >> tagBits; break; }
+                }
+            }
+        }
+        // the short candidate of the stored row when no lower lane supplied it (the loop above may have stopped early)
+        r.candL = cl; r.candS = (cs != cl) ? cs : 0u;
+        // inserts: my slot, unless more than 15 later lanes of my group will overwrite it; the highest lane writes the head
+        if (gsize - rank <= B2Z_ROW_WAYS) __stcg(row + (head + rank) % B2Z_ROW_WAYS, ((p + 1u) << tagBits) | t8);
+        if (rank == gsize - 1u) __stcg(row + 15, (head + gsize) % B2Z_ROW_WAYS);
     }
     __syncwarp();
     return r;
@@ -105,14 +135,13 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warpSlot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t HL = g.hashLogL, HS = g.hashLogS, tagBits = 32u - (g.frameLog + 1u);
+    const uint32_t rowLog = g.rowLog, tagBits = 32u - (g.frameLog + 1u);
     const uint64_t F = 1ull << g.frameLog;
     const uint32_t W = g.windowLog >= 32 ? 0xFFFFFFFFu : (1u << g.windowLog);
     const uint32_t blocksPerFrame = (uint32_t)(F >> 17);
     const uint64_t nFrames = (srcSize + F - 1) >> g.frameLog;
-    const uint32_t tableWords = (1u << HL) + (1u << HS);
-    uint32_t* TL = tables + (size_t)warpSlot * tableWords;
-    uint32_t* TS = TL + (1u << HL);
+    const uint32_t tableWords = 16u << rowLog;
+    uint32_t* TR = tables + (size_t)warpSlot * tableWords;
 
     for (uint64_t f = warpSlot; f < nFrames; f += nWarps) {
         const uint64_t f0 = f << g.frameLog;
@@ -124,7 +153,7 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
         if (ready) { uint32_t spins = 0; while (ready[(f0 + n - 1u) >> readyShift] == 0u && ++spins < (1u << 21)) __nanosleep(2000); __syncwarp(); }   // bounded: never hangs the GPU
         // clear this warp's tables (16-byte stores)
         {
-            uint4* t4 = reinterpret_cast<uint4*>(TL);
+            uint4* t4 = reinterpret_cast<uint4*>(TR);
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (uint32_t i = lane; i < tableWords / 4u; i += 32u) __stcg(t4 + i, z);
             __syncwarp();
@@ -132,14 +161,14 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
         const size_t blk0 = (size_t)f * blocksPerFrame;
         uint32_t entry = 0, nlitB = 0;
         Emitter em; em.reset(seqs + blk0 * B2Z_MAXSEQ);
-        StepA cur = stage_a(w, nWords, n, 0, lane, TL, TS, HL, HS, tagBits);
+        StepA cur = stage_a(w, nWords, n, 0, lane, TR, rowLog, tagBits);
         for (uint32_t base = 0; base < n; base += 32u) {
             const uint32_t blk = base >> 17, blkStart = blk << 17;
             const uint32_t blkEnd = (blkStart + B2Z_BLOCK < n) ? blkStart + B2Z_BLOCK : n;
             const uint32_t p = base + lane;
             // ---- stage A of the next step (table traffic in flight during stage B)
             StepA nxt; nxt.v = 0; nxt.candL = 0; nxt.candS = 0;
-            if (base + 32u < n) nxt = stage_a(w, nWords, n, base + 32u, lane, TL, TS, HL, HS, tagBits);
+            if (base + 32u < n) nxt = stage_a(w, nWords, n, base + 32u, lane, TR, rowLog, tagBits);
             // ---- stage B
             const uint32_t cnt = (n - base) < 32u ? (n - base) : 32u;       // valid lanes
             if (entry < base + cnt) {
@@ -150,7 +179,7 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
                     if (cur.candL) { const uint32_t q = cur.candL - 1u; if (p - q <= W) { offL = p - q; lenL = match_len(w, q, p, maxLen, nWords); } }
                     if (cur.candS) { const uint32_t q = cur.candS - 1u; if (p - q <= W) { offS = p - q; lenS = match_len(w, q, p, maxLen, nWords); } }
                     len = lenL; off = offL;
-                    if (lenS > lenL || (lenS == lenL && offS < offL)) { len = lenS; off = offS; }
+                    if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
                     if (!b2z_accept(len, off)) { len = 0; off = 0; }
                 }
                 // path through the step: greedy with one-position lazy deferral

@@ -41,12 +41,13 @@ extern "C" {
 /* parameters (b200z_set_param) */
 #define B200Z_P_LEVEL       1   /* 1..22; every level currently maps to the level-3 (dfast-class) parser */
 #define B200Z_P_FRAMELOG    2   /* log2 of the independent frame ("job") size, 17..24, default 22       */
-#define B200Z_P_HASHLOG_L   3   /* long-hash table log, default 17  (clevels.h:31 hashLog)               */
-#define B200Z_P_HASHLOG_S   4   /* short-hash table log, default 16 (clevels.h:31 chainLog)              */
+#define B200Z_P_HASHLOG_L   3   /* accepted for compatibility (dual-table finder of the first version); unused */
+#define B200Z_P_HASHLOG_S   4   /* accepted for compatibility; unused                                        */
 #define B200Z_P_WINDOWLOG   5   /* max match distance log, default = frameLog                            */
 #define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention; default on)
                                    bit1: XXH64 content checksum per frame (ZstdHandler.cpp:275 sets it for .zst) */
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
+#define B200Z_P_ROWLOG      9   /* log2 rows of the row-hash match finder (64-byte rows), 8..18, default 14   */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,

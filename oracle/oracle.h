@@ -21,7 +21,7 @@ typedef struct {
     uint32_t hashLogL;      /* long (8-byte) hash table log (default 17)                      */
     uint32_t hashLogS;      /* short (5-byte) hash table log (default 16)                     */
     uint32_t windowLog;     /* max match distance log (default = frameLog)                    */
-    uint32_t reserved;
+    uint32_t rowLog;        /* log2 rows of the row-hash match finder (default 14; 0 = dual hash tables) */
     uint32_t flags;         /* bit0: skippable size hints before each frame; bit1: checksum   */
 } b2zo_enc_params;
 

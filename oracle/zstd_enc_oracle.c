@@ -44,7 +44,7 @@ static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
     (void)level;
     p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
-    p->windowLog = B2Z_DEF_FRAMELOG; p->reserved = 0; p->flags = 1;
+    p->windowLog = B2Z_DEF_FRAMELOG; p->rowLog = B2Z_DEF_ROWLOG; p->flags = 1;
 }
 
 size_t b2zo_zstd_compress_bound(size_t n, const b2zo_enc_params *p) {
@@ -118,6 +118,8 @@ static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_pa
     const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
     const size_t W = (size_t)1 << P->windowLog;
     uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
+    const uint32_t ROWLOG = P->rowLog;                   /* 0: dual tables; else log2(rows) of the row-hash finder */
+    uint32_t *TR = ROWLOG ? (uint32_t *)calloc((size_t)16 << ROWLOG, 4) : NULL;
     cand_t cand[B2Z_STEP];
     size_t entry = 0;                                       /* path entry point (frame-relative) */
     size_t nblocks = (n + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
@@ -131,6 +133,26 @@ static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_pa
         int search = entry < c1;                            /* whole step inside a match: insert only */
         for (size_t p = c0; p < c1; p++) {
             cand_t best = { 0, 0 };
+            if (p + 8 <= n && ROWLOG) {
+                /* row-hash finder: ONE 64-byte row per position (15 entries + head), row chosen by the 5-byte hash, entries
+                 * tagged with bits of the 8-byte hash.  long candidate = newest entry with my tag, short = newest entry. */
+                uint64_t v = rd64(src + p);
+                uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
+                uint32_t *row = &TR[(hs >> (64 - ROWLOG)) * 16];
+                uint32_t t8 = (uint32_t)(hl >> (64 - tagBits)) & tagMask, head = row[15];
+                if (search) {
+                    uint32_t cl = 0, cs = 0;
+                    for (uint32_t k = 1; k <= B2Z_ROW_WAYS; k++) { uint32_t e = row[(head + B2Z_ROW_WAYS - k) % B2Z_ROW_WAYS]; if (!e) break; if (!cs) cs = e; if ((e & tagMask) == t8) { cl = e; break; } }
+                    size_t maxLen = blkEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
+                    uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
+                    if (cl) { size_t q = (cl >> tagBits) - 1; if (p - q <= W) { offL = (uint32_t)(p - q); lenL = (uint32_t)count_match(src + q, src + p, maxLen); } }
+                    if (cs && cs != cl) { size_t q = (cs >> tagBits) - 1; if (p - q <= W) { offS = (uint32_t)(p - q); lenS = (uint32_t)count_match(src + q, src + p, maxLen); } }
+                    uint32_t len = lenL, off = offL;
+                    if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
+                    if (b2z_accept(len, off)) { best.off = off; best.len = (uint16_t)len; }
+                }
+                row[head] = (((uint32_t)p + 1) << tagBits) | t8; row[15] = (head + 1) % B2Z_ROW_WAYS;
+            } else
             if (p + 8 <= n) {
                 uint64_t v = rd64(src + p);
                 uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
@@ -172,7 +194,7 @@ static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_pa
         }
         if (c1 == blkEnd) { emit_flush(&em); nseq[blk] = em.n; }
     }
-    free(TL); free(TS);
+    free(TL); free(TS); free(TR);
 }
 
 int64_t b2zo_zstd_find_sequences(const void *srcv, size_t srcSize, const b2zo_enc_params *P,

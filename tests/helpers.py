@@ -10,7 +10,7 @@ MAXSEQ = 32768
 
 
 class EncParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "reserved", "flags")]
+    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "rowLog", "flags")]
 
 
 _oracle = None

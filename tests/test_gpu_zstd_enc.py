@@ -50,9 +50,9 @@ def test_frames_equal_oracle_and_roundtrip(pkg, codec, inputs):
 def test_params_and_hints(pkg, inputs):
     """non-default geometry and the skippable size hints stay byte-identical to the oracle and decodable."""
     data = inputs["g2_9m"][: 3 * (1 << 20) + 77]
-    c = pkg.Codec(0, frame_log=20, hash_log_l=15, hash_log_s=14, flags=1)
+    c = pkg.Codec(0, frame_log=19, row_log=12, flags=1)
     comp = c.compress(data)
-    assert comp == helpers.oracle_compress(data, frameLog=20, windowLog=20, hashLogL=15, hashLogS=14, flags=1)
+    assert comp == helpers.oracle_compress(data, frameLog=19, windowLog=19, rowLog=12, flags=1)
     assert comp[:4] == b"\x50\x2a\x4d\x18"
     if helpers.ref_available():
         assert helpers.ref_decompress(comp, len(data)) == data
