@@ -32,13 +32,14 @@ struct StepA {               // per-lane results of stage A
     uint32_t candL, candS;   // candidate position + 1 (0 = none), frame-relative
 };
 
-// Row-hash match finder, one step.  The table is 2^rowLog rows of 64 bytes: 15 entries (newest at head-1, circular)
-// + the head index in word 15.  A position's row is chosen by the 5-byte hash, entries carry a tag from the
-// 8-byte hash, so ONE 64-byte line per position answers both questions of the reference's double-fast finder
+// Row-hash match finder, one step.  The table is 2^rowLog rows of 64 bytes holding the 15 most recent entries of the
+// row, NEWEST FIRST (word 15 unused): a lookup is one 64-byte load and static register reads, an insert rewrites the
+// row shifted by one (the line is dirty anyway).  A position's row is chosen by the 5-byte hash, entries carry a tag
+// from the 8-byte hash, so ONE line per position answers both questions of the reference's double-fast finder
 // (zstd_double_fast.c:103-330): "newest entry with my tag" (8-byte class, long candidate) and "newest entry"
-// (5-byte class, short candidate).  Lanes of one step that fall into the same row behave as if they had inserted
-// in lane order (oracle: position-by-position loop): a lane sees the entries of its lower lanes first, then the
-// 15 - rank newest entries of the stored row; every lane writes its own slot head+rank, the highest lane the head.
+// (5-byte class, short candidate).  Lanes of one step that fall into the same row behave as if they had inserted in
+// lane order (oracle: position-by-position loop; its circular layout holds the same logical content): a lane sees the
+// entries of its lower lanes first, then the 15 - rank newest stored ones; the highest lane of the group writes the row.
 __device__ __forceinline__ StepA stage_a(const uint64_t* __restrict__ w, uint32_t nWords, uint32_t n, uint32_t base,
                                          uint32_t lane, uint32_t* __restrict__ TR, uint32_t rowLog, uint32_t tagBits) {
     StepA r; r.candL = 0; r.candS = 0;
@@ -47,51 +48,50 @@ __device__ __forceinline__ StepA stage_a(const uint64_t* __restrict__ w, uint32_
     const bool hashable = p + 8u <= n;
     const uint64_t hl = r.v * B2Z_PRIME8, hs = (r.v << 24) * B2Z_PRIME5;
     const uint32_t rowIdx = (uint32_t)(hs >> (64u - rowLog)), t8 = (uint32_t)(hl >> (64u - tagBits)) & tagMask;
-    uint32_t* row = TR + (size_t)rowIdx * 16u;
-    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-    if (hashable) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(row);
-        q0 = __ldcg(r4); q1 = __ldcg(r4 + 1); q2 = __ldcg(r4 + 2); q3 = __ldcg(r4 + 3);
+    const uint32_t mine = ((p + 1u) << tagBits) | t8;
+    uint4* row4 = reinterpret_cast<uint4*>(TR + (size_t)rowIdx * 16u);
+    uint32_t e[16];
+    {
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+        if (hashable) { q0 = __ldcg(row4); q1 = __ldcg(row4 + 1); q2 = __ldcg(row4 + 2); q3 = __ldcg(row4 + 3); }
+        e[0] = q0.x; e[1] = q0.y; e[2] = q0.z; e[3] = q0.w; e[4] = q1.x; e[5] = q1.y; e[6] = q1.z; e[7] = q1.w;
+        e[8] = q2.x; e[9] = q2.y; e[10] = q2.z; e[11] = q2.w; e[12] = q3.x; e[13] = q3.y; e[14] = q3.z; e[15] = 0;
     }
     const uint32_t g = __match_any_sync(B2Z_FULL, hashable ? rowIdx : (0x80000000u | lane));
     const uint32_t lower = g & lanemask_lt();
-    const uint32_t rank = (uint32_t)__popc(lower), gsize = (uint32_t)__popc(g);
-    // lower lanes of my row: newest first = highest lane first (rare: only when some row is hit twice in this step)
-    uint32_t intraL = 0xFFFFFFFFu;                              // lane index of the highest lower lane with my tag
-    if (__any_sync(B2Z_FULL, lower != 0u)) {
-        for (uint32_t j = 0; j < 31u; j++) {
-            const uint32_t tj = __shfl_sync(B2Z_FULL, t8, j);
-            // lane j's entry is still in the row when I arrive only if fewer than 15 group lanes sit between us
-            if (((lower >> j) & 1u) && tj == t8 && rank - (uint32_t)__popc(g & ((1u << j) - 1u)) <= B2Z_ROW_WAYS) intraL = j;
+    if (!__any_sync(B2Z_FULL, lower != 0u)) {
+        // ---- common case: every row of this step is hit once
+        if (hashable) {
+            uint32_t cl = 0;
+#pragma unroll
+            for (int k = (int)B2Z_ROW_WAYS - 1; k >= 0; k--) if (e[k] && (e[k] & tagMask) == t8) cl = e[k];   // newest match wins
+            const uint32_t cs = e[0];
+            r.candL = cl >> tagBits; r.candS = (cs != cl) ? (cs >> tagBits) : 0u;
+            __stcg(row4, make_uint4(mine, e[0], e[1], e[2])); __stcg(row4 + 1, make_uint4(e[3], e[4], e[5], e[6]));
+            __stcg(row4 + 2, make_uint4(e[7], e[8], e[9], e[10])); __stcg(row4 + 3, make_uint4(e[11], e[12], e[13], 0u));
         }
-    }
-    if (hashable) {
-        const uint32_t e[16] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
-        const uint32_t head = e[15];
+    } else {
+        // ---- some row is hit by several lanes: replay their inserts in lane order (ascending = oldest first)
+        const uint32_t rank = (uint32_t)__popc(lower), gsize = (uint32_t)__popc(g);
         uint32_t cl = 0, cs = 0;
-        if (lower) { cs = base + (31u - (uint32_t)__clz((int)lower)) + 1u; if (intraL != 0xFFFFFFFFu) cl = base + intraL + 1u; }
-        if (!cl && rank < B2Z_ROW_WAYS) {
-            // stored entries, newest first; only the 15 - rank newest are still there after my lower lanes' inserts
-            const uint32_t alive = B2Z_ROW_WAYS - rank;
+        for (uint32_t j = 0; j < 32u; j++) {
+            const uint32_t ej = __shfl_sync(B2Z_FULL, mine, j);
+            if ((lower >> j) & 1u) {                                  // lane j inserted before me: push its entry in front
 #pragma unroll
-            for (uint32_t k = 1; k <= B2Z_ROW_WAYS; k++) {
-                if (k <= alive) {
-                    // slot (head + WAYS - k) % WAYS, selected without dynamic register indexing
-                    const uint32_t slot = (head + B2Z_ROW_WAYS - k) % B2Z_ROW_WAYS;
-                    uint32_t ev = 0;
-#pragma unroll
-                    for (uint32_t i = 0; i < B2Z_ROW_WAYS; i++) if (slot == i) ev = e[i];
-                    if (!ev) break;
-                    if (!cs) cs = ev >> tagBits;
-                    if ((ev & tagMask) == t8) { cl = ev >> tagBits; break; }
-                }
+                for (int k = (int)B2Z_ROW_WAYS - 1; k > 0; k--) e[k] = e[k - 1];
+                e[0] = ej;
             }
         }
-        // the short candidate of the stored row when no lower lane supplied it (the loop above may have stopped early)
-        r.candL = cl; r.candS = (cs != cl) ? cs : 0u;
-        // inserts: my slot, unless more than 15 later lanes of my group will overwrite it; the highest lane writes the head
-        if (gsize - rank <= B2Z_ROW_WAYS) __stcg(row + (head + rank) % B2Z_ROW_WAYS, ((p + 1u) << tagBits) | t8);
-        if (rank == gsize - 1u) __stcg(row + 15, (head + gsize) % B2Z_ROW_WAYS);
+        if (hashable) {
+#pragma unroll
+            for (int k = (int)B2Z_ROW_WAYS - 1; k >= 0; k--) if (e[k] && (e[k] & tagMask) == t8) cl = e[k];
+            cs = e[0];
+            r.candL = cl >> tagBits; r.candS = (cs != cl) ? (cs >> tagBits) : 0u;
+            if (rank == gsize - 1u) {                                 // the newest lane of the group writes the row
+                __stcg(row4, make_uint4(mine, e[0], e[1], e[2])); __stcg(row4 + 1, make_uint4(e[3], e[4], e[5], e[6]));
+                __stcg(row4 + 2, make_uint4(e[7], e[8], e[9], e[10])); __stcg(row4 + 3, make_uint4(e[11], e[12], e[13], 0u));
+            }
+        }
     }
     __syncwarp();
     return r;
