@@ -44,6 +44,29 @@ __device__ __forceinline__ uint32_t match_len(const uint64_t* __restrict__ w, ui
     return len < maxLen ? len : maxLen;
 }
 
+// same, when the first 8 bytes at p are already in a register (`pv`): most candidates differ inside those 8 bytes,
+// and then no p-side load is needed at all
+__device__ __forceinline__ uint32_t match_len_pv(const uint64_t* __restrict__ w, uint32_t q, uint32_t p, uint64_t pv,
+                                                 uint32_t maxLen, uint32_t nWords) {
+    const uint32_t qi = q >> 3, qs = (q & 7u) * 8u;
+    const uint64_t qa = ldw(w, qi, nWords), qb = ldw(w, qi + 1, nWords);
+    const uint64_t x = funnel64(qa, qb, qs) ^ pv;
+    uint32_t len;
+    if (x) len = (uint32_t)(__ffsll((long long)x) - 1) >> 3;
+    else {
+        len = 8;
+        uint32_t qj = qi + 1, pj = (p >> 3) + 1; const uint32_t ps = (p & 7u) * 8u;
+        uint64_t qc = qb, pc = ldw(w, pj, nWords);
+        while (len < maxLen) {
+            const uint64_t qd = ldw(w, qj + 1, nWords), pd = ldw(w, pj + 1, nWords);
+            const uint64_t y = funnel64(qc, qd, qs) ^ funnel64(pc, pd, ps);
+            if (y) { len += (uint32_t)(__ffsll((long long)y) - 1) >> 3; break; }
+            len += 8; qc = qd; pc = pd; qj++; pj++;
+        }
+    }
+    return len < maxLen ? len : maxLen;
+}
+
 __device__ __forceinline__ uint32_t highbit32(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, uint32_t* total) {

@@ -176,8 +176,8 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
                 if (p + 8u <= n) {
                     uint32_t maxLen = blkEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
                     uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
-                    if (cur.candL) { const uint32_t q = cur.candL - 1u; if (p - q <= W) { offL = p - q; lenL = match_len(w, q, p, maxLen, nWords); } }
-                    if (cur.candS) { const uint32_t q = cur.candS - 1u; if (p - q <= W) { offS = p - q; lenS = match_len(w, q, p, maxLen, nWords); } }
+                    if (cur.candL) { const uint32_t q = cur.candL - 1u; if (p - q <= W) { offL = p - q; lenL = match_len_pv(w, q, p, cur.v, maxLen, nWords); } }
+                    if (cur.candS) { const uint32_t q = cur.candS - 1u; if (p - q <= W) { offS = p - q; lenS = match_len_pv(w, q, p, cur.v, maxLen, nWords); } }
                     len = lenL; off = offL;
                     if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
                     if (!b2z_accept(len, off)) { len = 0; off = 0; }
