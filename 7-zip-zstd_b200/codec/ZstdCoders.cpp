@@ -156,8 +156,9 @@ public:
         if (hashLog_ >= 10 && hashLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_L, hashLog_);
         if (chainLog_ >= 10 && chainLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_S, chainLog_);
         if (windowLog_ >= 17) { int64_t fl = 0; b200z_get_param(ctx, B200Z_P_FRAMELOG, &fl); b200z_set_param(ctx, B200Z_P_WINDOWLOG, windowLog_ < fl ? windowLog_ : fl); }
-        // batches of whole frames: 256 MiB of input per GPU pass (ring of pinned host memory)
-        const size_t batch = (size_t)256 << 20;
+        // batches of whole frames: 1 GiB of input per GPU pass (pinned host memory); a batch has to hold about a
+        // thousand 1 MiB frames to keep the frame-parallel match finder busy
+        const size_t batch = (size_t)1 << 30;
         if (!in_.reserve(batch) || !out_.reserve(b200z_zstd_compress_bound(ctx, batch))) return E_OUTOFMEMORY;
         bool wroteAny = false;
         for (;;) {
