@@ -122,7 +122,7 @@ struct Emitter {
                 rep1 = rep0; rep0 = cur;
             }
         }
-        if (lane == 0) out[n] = B2Z_PACK_SEQ(offBase, ll, pendLen);
+        if (lane == 0) __stcs(reinterpret_cast<unsigned long long*>(out + n), (unsigned long long)B2Z_PACK_SEQ(offBase, ll, pendLen));   // streaming: keep L2 for the rows
         n++; prevEnd = pendPos + pendLen; pendValid = 0;
     }
 };
@@ -220,7 +220,7 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
                     c += mLen;
                 }
                 entry = base + c;
-                if (litMask >> lane & 1u) lits[f0 + blkStart + nlitB + __popc(litMask & lanemask_lt())] = (uint8_t)cur.v;
+                if (litMask >> lane & 1u) __stcs(lits + f0 + blkStart + nlitB + __popc(litMask & lanemask_lt()), (uint8_t)cur.v);
                 nlitB += __popc(litMask);
             }
             if (base + cnt == blkEnd) {                                         // block finished

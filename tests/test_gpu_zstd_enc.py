@@ -89,3 +89,12 @@ def test_bad_arguments(pkg, codec):
     buf = np.zeros(64, dtype=np.uint8)
     rc = pkg.load_library().b200z_zstd_compress_host(codec.h, buf.ctypes.data, 64, buf.ctypes.data, 8, ctypes.byref(sz))
     assert rc == -4
+
+
+def test_device_batches_are_invisible(pkg):
+    """inputs larger than one kernel batch are compressed batch after batch; the bytes do not depend on the batch size"""
+    data = pkg.corpus.g2(21 * (1 << 20) + 3210).tobytes()
+    c = pkg.Codec(0, batch_log=22)
+    comp = c.compress(data)
+    assert comp == helpers.oracle_compress(data)
+    c.close()
