@@ -35,6 +35,11 @@ int64_t b2zo_zstd_find_sequences(const void *src, size_t srcSize, const b2zo_enc
                                  uint64_t *seqs /* [nblocks*B2Z_MAXSEQ] */, uint32_t *nseq /* [nblocks] */,
                                  uint8_t *lits /* [srcSize] */, uint32_t *nlit /* [nblocks] */);
 
+
+/* ---- LZMA2 (method 21) decoder: lzma2_dec_oracle.c ---- */
+/* raw LZMA2 chunk stream -> dst; dictProp = the coder's 1-byte property. returns size, -1 corrupt, -2 dst too small */
+int64_t b2zo_lzma2_decompress(void *dst, size_t dstCap, const void *src, size_t srcSize, uint32_t dictProp, size_t *srcUsed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,94 @@ def sample_inputs(pkg, big=False):
     if big:
         d["g2_9m"] = g2(9 * (1 << 20) + 4321).tobytes()           # 3 frames, ragged tail
     return d
+
+
+# ---------------------------------------------------------------- LZMA2 (method 21) ----------------------------------------
+_ref_lzma = None
+
+
+def ref_lzma_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_lzma.so"))
+
+
+class _LzmaEncProps(ctypes.Structure):      # C/LzmaEnc.h:13-39
+    _fields_ = [("level", ctypes.c_int), ("dictSize", ctypes.c_uint32), ("lc", ctypes.c_int), ("lp", ctypes.c_int), ("pb", ctypes.c_int),
+                ("algo", ctypes.c_int), ("fb", ctypes.c_int), ("btMode", ctypes.c_int), ("numHashBytes", ctypes.c_int),
+                ("numHashOutBits", ctypes.c_uint), ("mc", ctypes.c_uint32), ("writeEndMark", ctypes.c_uint), ("numThreads", ctypes.c_int),
+                ("affinityGroup", ctypes.c_int32), ("reduceSize", ctypes.c_uint64), ("affinity", ctypes.c_uint64), ("affinityInGroup", ctypes.c_uint64)]
+
+
+class _Lzma2EncProps(ctypes.Structure):     # C/Lzma2Enc.h:15-23
+    _fields_ = [("lzmaProps", _LzmaEncProps), ("blockSize", ctypes.c_uint64), ("numBlockThreads_Reduced", ctypes.c_int),
+                ("numBlockThreads_Max", ctypes.c_int), ("numTotalThreads", ctypes.c_int), ("numThreadGroups", ctypes.c_uint)]
+
+
+def ref_lzma():
+    global _ref_lzma
+    if _ref_lzma is None:
+        L = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_lzma.so"))
+        L.FL2_compressBound.restype = ctypes.c_size_t; L.FL2_compressBound.argtypes = [ctypes.c_size_t]
+        L.FL2_compressMt.restype = ctypes.c_size_t
+        L.FL2_compressMt.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint]
+        L.Lzma2Decode.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t),
+                                  ctypes.c_ubyte, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+        L.FL2_isError.argtypes = [ctypes.c_size_t]
+        L.Lzma2Enc_Create.restype = ctypes.c_void_p; L.Lzma2Enc_Create.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.Lzma2Enc_Destroy.argtypes = [ctypes.c_void_p]
+        L.Lzma2Enc_SetProps.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Lzma2EncProps)]
+        L.Lzma2Enc_WriteProperties.restype = ctypes.c_ubyte; L.Lzma2Enc_WriteProperties.argtypes = [ctypes.c_void_p]
+        L.Lzma2Enc_Encode2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.Lzma2EncProps_Init.argtypes = [ctypes.POINTER(_Lzma2EncProps)]
+        _ref_lzma = L
+    return _ref_lzma
+
+
+def ref_fl2_compress(data, level=5, threads=1):
+    """reference Fast-LZMA2 encoder (C/fast-lzma2/fl2_compress.c) -> (dictProp, raw LZMA2 stream).
+    FL2_compress prepends the 1-byte dictionary property (and may append a hash after the 0x00 end marker)."""
+    L = ref_lzma(); src = _np(data)
+    out = np.empty(L.FL2_compressBound(len(data)) + 64, dtype=np.uint8)
+    r = L.FL2_compressMt(out.ctypes.data, out.size, src.ctypes.data, len(data), level, threads)
+    assert not L.FL2_isError(r)
+    return int(out[0]) & 0x3F, out[1:r].tobytes()
+
+
+def ref_lzma2_compress(data, level=5, dict_size=0, lc=-1, lp=-1, pb=-1, block_size=0, threads=1):
+    """reference stock LZMA2 encoder (C/Lzma2Enc.c) -> (dictProp, raw LZMA2 stream)."""
+    L = ref_lzma(); src = _np(data)
+    p = _Lzma2EncProps(); L.Lzma2EncProps_Init(ctypes.byref(p))
+    p.lzmaProps.level = level; p.lzmaProps.dictSize = dict_size; p.lzmaProps.lc = lc; p.lzmaProps.lp = lp; p.lzmaProps.pb = pb
+    p.blockSize = block_size; p.numTotalThreads = threads; p.numBlockThreads_Max = threads
+    alloc = ctypes.c_void_p.in_dll(L, "g_Alloc"); big = ctypes.c_void_p.in_dll(L, "g_BigAlloc")
+    h = L.Lzma2Enc_Create(ctypes.addressof(alloc), ctypes.addressof(big))
+    assert h
+    assert L.Lzma2Enc_SetProps(h, ctypes.byref(p)) == 0
+    prop = L.Lzma2Enc_WriteProperties(h)
+    out = np.empty(len(data) + len(data) // 3 + 4096, dtype=np.uint8); n = ctypes.c_size_t(out.size)
+    rc = L.Lzma2Enc_Encode2(h, None, out.ctypes.data, ctypes.byref(n), None, src.ctypes.data, len(data), None)
+    L.Lzma2Enc_Destroy(h)
+    assert rc == 0, rc
+    return int(prop), out[:n.value].tobytes()
+
+
+def oracle_lzma2_decompress(comp, n, dict_prop):
+    O = oracle()
+    O.b2zo_lzma2_decompress.restype = ctypes.c_int64
+    O.b2zo_lzma2_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p]
+    dst = np.empty(n + 1, dtype=np.uint8); src = _np(comp); used = ctypes.c_size_t(0)
+    r = O.b2zo_lzma2_decompress(dst.ctypes.data, n, src.ctypes.data, len(comp), dict_prop, ctypes.byref(used))
+    if r < 0:
+        raise ValueError(f"oracle lzma2 decoder error {r}")
+    return dst[:r].tobytes(), used.value
+
+
+def ref_lzma2_decompress(comp, n, dict_prop):
+    """reference decoder, one-call form (C/Lzma2Dec.c: Lzma2Decode)."""
+    L = ref_lzma(); src = _np(comp); dst = np.empty(n + 1, dtype=np.uint8)
+    dl = ctypes.c_size_t(n); sl = ctypes.c_size_t(len(comp)); st = ctypes.c_int(0)
+    alloc = ctypes.c_void_p.in_dll(L, "g_Alloc")
+    rc = L.Lzma2Decode(dst.ctypes.data, ctypes.byref(dl), src.ctypes.data, ctypes.byref(sl), dict_prop, 1, ctypes.byref(st), ctypes.addressof(alloc))
+    if rc != 0:
+        raise ValueError(f"reference lzma2 decoder error {rc}")
+    return dst[:dl.value].tobytes(), sl.value
