@@ -60,6 +60,9 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.b200z_zstd_frame_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
     L.b200z_zstd_enc_stage_m.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+    L.b200z_lzma2_stream_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(sz)]
+    for name in ("b200z_lzma2_decompress_device", "b200z_lzma2_decompress_host"):
+        getattr(L, name).argtypes = [vp, vp, sz, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
     L.b200z_dev_alloc.argtypes = [vp, ctypes.POINTER(vp), sz]
     L.b200z_dev_free.argtypes = [vp, vp]
     L.b200z_dev_upload.argtypes = [vp, vp, vp, sz]
@@ -107,7 +110,7 @@ class Codec:
             raise B200zError(rc, self.L.b200z_last_error(self.h).decode())
 
     _PARAMS = dict(level=P_LEVEL, frame_log=P_FRAMELOG, hash_log_l=P_HASHLOG_L, hash_log_s=P_HASHLOG_S,
-                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, row_log=9)
+                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, row_log=9, lzma2_model=10)
 
     def set(self, name, value):
         self._check(self.L.b200z_set_param(self.h, self._PARAMS[name], int(value)))
@@ -167,6 +170,37 @@ class Codec:
     def decompress_device(self, d_src, n, d_dst, cap):
         sz = ctypes.c_size_t()
         self._check(self.L.b200z_zstd_decompress_device(self.h, d_src, n, d_dst, cap, ctypes.byref(sz)))
+        return sz.value
+
+    # ---- LZMA2 (method 21): raw chunk stream + the coder's 1-byte dictionary property
+    def lzma2_stream_info(self, data):
+        """(decoded size, independent blocks, bytes up to and including the end marker) from the chunk headers (host walk)"""
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8)
+        cs, nb, used = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_size_t()
+        rc = self.L.b200z_lzma2_stream_info(src.ctypes.data if src.nbytes else None, src.nbytes, ctypes.byref(cs), ctypes.byref(nb), ctypes.byref(used))
+        if rc:
+            raise B200zError(rc, "LZMA2: malformed stream")
+        return cs.value, nb.value, used.value
+
+    def lzma2_decompress(self, data, dict_prop, max_size=None) -> bytes:
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8)
+        if max_size is None:
+            max_size = self.lzma2_stream_info(data)[0]
+        out = np.empty(max(max_size, 1), dtype=np.uint8)
+        sz = ctypes.c_size_t()
+        self._check(self.L.b200z_lzma2_decompress_host(self.h, src.ctypes.data if src.nbytes else None, src.nbytes, dict_prop, out.ctypes.data, max_size, ctypes.byref(sz)))
+        return out[:sz.value].tobytes()
+
+    def lzma2_decompress_into(self, src_ptr, n, dict_prop, dst_ptr, cap):
+        sz = ctypes.c_size_t()
+        self._check(self.L.b200z_lzma2_decompress_host(self.h, src_ptr, n, dict_prop, dst_ptr, cap, ctypes.byref(sz)))
+        return sz.value
+
+    def lzma2_decompress_device(self, d_src, n, dict_prop, d_dst, cap):
+        sz = ctypes.c_size_t()
+        self._check(self.L.b200z_lzma2_decompress_device(self.h, d_src, n, dict_prop, d_dst, cap, ctypes.byref(sz)))
         return sz.value
 
     # ---- test tap: stage M outputs (same layout as oracle b2zo_zstd_find_sequences)

@@ -73,6 +73,7 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (uint32_t)v; return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
     case B200Z_P_ROWLOG:    if (v < 8 || v > 18) return fail(ctx, B200Z_E_PARAM, "rowLog out of range%s"); ctx->geom.rowLog = (uint32_t)v; return 0;
+    case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
     return fail(ctx, B200Z_E_PARAM, "unknown parameter%s");
@@ -89,6 +90,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_FLAGS: *v = ctx->geom.flags; return 0;
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
+    case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
     case B200Z_P_ROWLOG: *v = ctx->geom.rowLog; return 0;
     }
     return B200Z_E_PARAM;

@@ -48,6 +48,7 @@ extern "C" {
                                    bit1: XXH64 content checksum per frame (ZstdHandler.cpp:275 sets it for .zst) */
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
 #define B200Z_P_ROWLOG      9   /* log2 rows of the row-hash match finder (64-byte rows), 8..18, default 14   */
+#define B200Z_P_LZMA2_MODEL 10  /* LZMA2 decoder: literal model in 1 = shared memory (13 warps/SM), 2 = global memory (32 warps/SM), 0 = by block count */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
@@ -95,6 +96,18 @@ int b200z_zstd_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
  * outputs to host arrays (same layout as the oracle's b2zo_zstd_find_sequences). */
 int b200z_zstd_enc_stage_m(b200z_ctx *ctx, const void *d_src, size_t srcSize,
                            uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit);
+
+/* ---- LZMA2 / FLZMA2 (method 21) decoder --------------------------------------------------------------
+ * src is the raw LZMA2 chunk stream a 7z folder stores for coder 21 (chunks ... 0x00 end marker); dictProp is the
+ * coder's 1-byte property (0..40).  Replaces NCompress::NLzma2::CDecoder::Code -> Lzma2DecMt_Decode
+ * (CPP/7zip/Compress/Lzma2Decoder.cpp:95-200, C/Lzma2DecMt.c:802) and Lzma2Decode (C/Lzma2Dec.c:452).
+ * Parallel unit: every run of chunks that starts with a dictionary reset (control 0x01 / >= 0xE0), as in
+ * Lzma2DecMt_MtCallback_Parse (C/Lzma2DecMt.c:237).  A stream with a single reset decodes on a single warp. */
+int b200z_lzma2_stream_info(const void *src, size_t srcSize, uint64_t *contentSize, uint32_t *nBlocks, size_t *srcUsed);
+int b200z_lzma2_decompress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize, uint32_t dictProp,
+                                  void *d_dst, size_t dstCap, size_t *dstSize);
+int b200z_lzma2_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, uint32_t dictProp,
+                                void *dst, size_t dstCap, size_t *dstSize);
 
 /* device memory helpers so FFI users need no CUDA binding of their own */
 int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);

@@ -41,7 +41,6 @@ typedef struct {
     len_coder len, repLen;
     prob_t *lit;                                   /* 0x300 << (lc+lp) */
     uint32_t lc, lp, pb, state, rep[4];
-    uint32_t remainLen;                            /* a match cut by a chunk boundary continues in the next chunk */
     /* range coder */
     const uint8_t *in, *inEnd; uint32_t range, code; int rcErr;
 } lzma_t;
@@ -50,7 +49,7 @@ static void reset_probs(lzma_t *z) {
     prob_t *p = (prob_t *)z->isMatch; size_t n = ((uint8_t *)&z->lit - (uint8_t *)z->isMatch) / sizeof(prob_t);
     for (size_t i = 0; i < n; i++) p[i] = PROB_INIT;
     for (size_t i = 0; i < ((size_t)0x300 << (z->lc + z->lp)); i++) z->lit[i] = PROB_INIT;
-    z->state = 0; z->rep[0] = z->rep[1] = z->rep[2] = z->rep[3] = 0; z->remainLen = 0;
+    z->state = 0; z->rep[0] = z->rep[1] = z->rep[2] = z->rep[3] = 0;
 }
 
 static inline uint32_t rc_byte(lzma_t *z) { if (z->in < z->inEnd) return *z->in++; z->rcErr = 1; return 0; }
@@ -84,7 +83,6 @@ static int lzma_chunk(lzma_t *z, uint8_t *dic, size_t dicStart, size_t *posIO, s
     if (z->inEnd - z->in < 5 || z->in[0] != 0) return -1;
     z->code = ((uint32_t)z->in[1] << 24) | ((uint32_t)z->in[2] << 16) | ((uint32_t)z->in[3] << 8) | z->in[4]; z->in += 5; z->range = 0xFFFFFFFFu; z->rcErr = 0;
     const uint32_t pbMask = (1u << z->pb) - 1, lpMask = (1u << z->lp) - 1;
-    while (z->remainLen && pos < end) { dic[pos] = dic[pos - z->rep[0] - 1]; pos++; z->remainLen--; }
     while (pos < end) {
         const uint32_t ps = (uint32_t)(pos - dicStart) & pbMask;
         if (!rc_bit(z, &z->isMatch[z->state][ps])) {
@@ -133,12 +131,12 @@ static int lzma_chunk(lzma_t *z, uint8_t *dic, size_t dicStart, size_t *posIO, s
             z->state = z->state < 7 ? 8 : 11;
         }
         if (z->rep[0] >= pos - dicStart || z->rep[0] >= dictSize) return -1;
-        size_t n = len; if (n > end - pos) { z->remainLen = (uint32_t)(n - (end - pos)); n = end - pos; }
-        for (size_t i = 0; i < n; i++) { dic[pos] = dic[pos - z->rep[0] - 1]; pos++; }
+        if (len > end - pos) return -1;                           /* a match may not cross the chunk end (LzmaDec.c:1030-1033) */
+        for (size_t i = 0; i < len; i++) { dic[pos] = dic[pos - z->rep[0] - 1]; pos++; }
         if (z->rcErr) return -1;
     }
     if (z->range < kTop) { z->range <<= 8; z->code = (z->code << 8) | rc_byte(z); }      /* final normalisation */
-    if (z->rcErr) return -1;
+    if (z->rcErr || z->code != 0) return -1;                       /* LzmaDec.c:1020: a finished chunk leaves code == 0 */
     *posIO = pos;
     return 0;
 }
@@ -152,7 +150,8 @@ int64_t b2zo_lzma2_decompress(void *dstv, size_t dstCap, const void *srcv, size_
     const uint32_t dictSize = dictProp == 40 ? 0xFFFFFFFFu : ((2u | (dictProp & 1)) << (dictProp / 2 + 11));
     lzma_t *z = (lzma_t *)calloc(1, sizeof(lzma_t));
     z->lit = (prob_t *)malloc(sizeof(prob_t) * ((size_t)0x300 << 4));
-    size_t pos = 0, dicStart = 0; int needDict = 1, needProps = 1, needState = 1; int64_t rc = -1;
+    size_t pos = 0, dicStart = 0; int64_t rc = -1;
+    uint32_t needInit = 0xE0;                       /* Lzma2Dec.c:108-121: lowest LZMA control byte acceptable next */
     for (;;) {
         if (ip >= iend) goto done;
         const uint32_t ctl = *ip++;
@@ -160,26 +159,26 @@ int64_t b2zo_lzma2_decompress(void *dstv, size_t dstCap, const void *srcv, size_
         if (ctl == 1 || ctl == 2) {
             if (iend - ip < 2) goto done;
             const size_t n = (((size_t)ip[0] << 8) | ip[1]) + 1; ip += 2;
-            if (ctl == 1) { dicStart = pos; needDict = 0; needState = 1; } else if (needDict) goto done;
+            if (ctl == 1) { dicStart = pos; needInit = 0xC0; } else if (needInit == 0xE0) goto done;
             if ((size_t)(iend - ip) < n) goto done;
             if (dstCap - pos < n) { rc = -2; goto done; }
             memcpy(dst + pos, ip, n); pos += n; ip += n;
             continue;
         }
-        if (ctl < 0x80) goto done;
+        if (ctl < 0x80 || ctl < needInit) goto done;
+        needInit = 0;
         if (iend - ip < 4) goto done;
         const size_t unpack = ((((size_t)ctl & 0x1F) << 16) | ((size_t)ip[0] << 8) | ip[1]) + 1;
         const size_t pack = (((size_t)ip[2] << 8) | ip[3]) + 1; ip += 4;
         const uint32_t mode = (ctl >> 5) & 3;
-        if (mode == 3) { dicStart = pos; needDict = 0; } else if (needDict) goto done;
+        if (mode == 3) dicStart = pos;
         if (mode >= 2) {
             if (ip >= iend) goto done;
             uint32_t d = *ip++; if (d >= 9 * 5 * 5) goto done;
             z->lc = d % 9; d /= 9; z->pb = d / 5; z->lp = d % 5;
             if (z->lc + z->lp > 4) goto done;
-            needProps = 0;
-        } else if (needProps) goto done;
-        if (mode >= 1) { reset_probs(z); needState = 0; } else if (needState) goto done;
+        }
+        if (mode >= 1) reset_probs(z);
         if ((size_t)(iend - ip) < pack) goto done;
         if (dstCap - pos < unpack) { rc = -2; goto done; }
         z->in = ip; z->inEnd = ip + pack;

@@ -47,3 +47,19 @@ def test_errors():
         assert hashlib.sha256(out).hexdigest() != IDX["lzma2_fl2_g2_100k.bin"]["sha256"]
     except ValueError:
         pass
+
+
+def test_stream_info_host_walk():
+    """b200z_lzma2_stream_info is host-only (chunk headers): sizes, block counts and malformed-stream detection, no GPU."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(H.ROOT, "7-zip-zstd_b200", "libb200z.so"))
+    lib.b200z_lzma2_stream_info.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t)]
+    for name, meta in IDX.items():
+        comp = open(os.path.join(GOLD, name), "rb").read()
+        buf = ctypes.create_string_buffer(comp, len(comp))
+        cs, nb, used = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_size_t()
+        assert lib.b200z_lzma2_stream_info(buf, len(comp), ctypes.byref(cs), ctypes.byref(nb), ctypes.byref(used)) == 0
+        assert cs.value == meta["size"] and comp[used.value - 1] == 0
+        assert nb.value == (4 if name == "lzma2_lzma2_tile_blocks.bin" else (0 if meta["size"] == 0 else 1)), (name, nb.value)
+        if len(comp) > 10:
+            assert lib.b200z_lzma2_stream_info(buf, len(comp) // 2, ctypes.byref(cs), ctypes.byref(nb), ctypes.byref(used)) == -5
