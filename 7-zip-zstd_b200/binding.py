@@ -60,6 +60,9 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.b200z_zstd_frame_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
     L.b200z_zstd_enc_stage_m.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+    L.b200z_lzma2_compress_bound.argtypes = [vp, sz]; L.b200z_lzma2_compress_bound.restype = sz
+    for name in ("b200z_lzma2_compress_device", "b200z_lzma2_compress_host"):
+        getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint32)]
     L.b200z_lzma2_stream_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(sz)]
     for name in ("b200z_lzma2_decompress_device", "b200z_lzma2_decompress_host"):
         getattr(L, name).argtypes = [vp, vp, sz, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
@@ -182,6 +185,29 @@ class Codec:
         if rc:
             raise B200zError(rc, "LZMA2: malformed stream")
         return cs.value, nb.value, used.value
+
+    def lzma2_compress(self, data):
+        """-> (dictProp, raw LZMA2 stream)"""
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else data
+        n = src.nbytes
+        out = np.empty(self.L.b200z_lzma2_compress_bound(self.h, n), dtype=np.uint8)
+        sz, prop = ctypes.c_size_t(), ctypes.c_uint32()
+        self._check(self.L.b200z_lzma2_compress_host(self.h, src.ctypes.data if n else None, n, out.ctypes.data, out.nbytes, ctypes.byref(sz), ctypes.byref(prop)))
+        return prop.value, out[:sz.value].tobytes()
+
+    def lzma2_compress_into(self, src_ptr, n, dst_ptr, cap):
+        sz, prop = ctypes.c_size_t(), ctypes.c_uint32()
+        self._check(self.L.b200z_lzma2_compress_host(self.h, src_ptr, n, dst_ptr, cap, ctypes.byref(sz), ctypes.byref(prop)))
+        return sz.value, prop.value
+
+    def lzma2_compress_device(self, d_src, n, d_dst, cap):
+        sz, prop = ctypes.c_size_t(), ctypes.c_uint32()
+        self._check(self.L.b200z_lzma2_compress_device(self.h, d_src, n, d_dst, cap, ctypes.byref(sz), ctypes.byref(prop)))
+        return sz.value, prop.value
+
+    def lzma2_compress_bound(self, n):
+        return self.L.b200z_lzma2_compress_bound(self.h, n)
 
     def lzma2_decompress(self, data, dict_prop, max_size=None) -> bytes:
         import numpy as np

@@ -6,6 +6,7 @@
 // :1853, ZSTDMT_createCompressionJob :1403, ZSTDMT_flushProduced :1488): frames are the jobs,
 // warps are the workers, the assemble kernels are the ordered flush.
 #include "b2z_ctx.h"
+#include "b2z_lzma2.h"
 
 using namespace b2z;
 
@@ -114,7 +115,7 @@ static uint32_t match_warps(const b200z_ctx* ctx, uint64_t nFrames) {
     return (uint32_t)(nFrames < cap ? nFrames : cap);
 }
 
-static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
+static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     const uint64_t F = 1ull << ctx->geom.frameLog;
     const uint64_t nFrames = (batchBytes + F - 1) / F;
     const uint64_t nBlocks = (batchBytes + B2Z_BLOCK - 1) / B2Z_BLOCK + 1;
@@ -126,7 +127,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
     bad |= ctx->nseq.reserve(nBlocks * 4);
     bad |= ctx->lits.reserve(nBlocks * (size_t)B2Z_BLOCK);
     bad |= ctx->nlit.reserve(nBlocks * 4);
-    bad |= ctx->slots.reserve(nBlocks * (size_t)B2Z_SLOT);
+    bad |= ctx->slots.reserve(codec == 1 ? nFrames * lzma2_enc_slot_stride(ctx->geom.frameLog) : nBlocks * (size_t)B2Z_SLOT);
     bad |= ctx->slotSize.reserve(nBlocks * 4);
     bad |= ctx->blockOff.reserve((nBlocks + 1) * 8);
     bad |= ctx->frameOff.reserve((nFrames + 2) * 8);
@@ -137,8 +138,8 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes) {
 
 // compress [d_src, d_src+n) (n > 0, one batch) to d_dst; returns produced bytes through *produced
 static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* d_dst, uint64_t* produced, bool stageMOnly,
-                     const uint32_t* ready = nullptr, uint32_t readyShift = 0) {
-    int rc = enc_reserve(ctx, n);
+                     const uint32_t* ready = nullptr, uint32_t readyShift = 0, int codec = 0) {
+    int rc = enc_reserve(ctx, n, codec);
     if (rc) return rc;
     const EncGeom& g = ctx->geom;
     const uint64_t F = 1ull << g.frameLog;
@@ -153,7 +154,34 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
-    if (!stageMOnly) {
+    if (!stageMOnly && codec == 1) {
+        // LZMA2: stage R (range coding, one thread per frame) + assembly of the frame slots into one chunk stream
+        constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
+        uint16_t* spill = nullptr;
+        if (ctx->lz2Mode != 1 && nFrames > 13ull * ctx->smCount / 2u && ctx->decScratch[5].reserve((size_t)nFrames * LITN * 2u) == 0) spill = (uint16_t*)ctx->decScratch[5].p;
+        if (ctx->lz2Mode == 2 && !spill) {
+            if (ctx->decScratch[5].reserve((size_t)nFrames * LITN * 2u)) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");
+            spill = (uint16_t*)ctx->decScratch[5].p;
+        }
+        CU(cudaMemsetAsync(ctx->scalars.p, 0, 64, st));
+        CU(launch_lzma2_enc_range(d_src, n, g, (const uint64_t*)ctx->seqs.p, (const uint32_t*)ctx->nseq.p, (uint8_t*)ctx->slots.p,
+                                  (uint32_t*)ctx->slotSize.p, (uint32_t)nFrames, spill, ctx->smCount, ctx->lz2Mode, (uint32_t*)ctx->scalars.p + 4, st));
+        CU(cudaEventRecord(ctx->ev[2], st));
+        launch_lzma2_enc_assemble((const uint8_t*)ctx->slots.p, (const uint32_t*)ctx->slotSize.p, (uint32_t)nFrames, g.frameLog,
+                                  (uint64_t*)ctx->frameOff.p, d_dst, (uint64_t*)ctx->scalars.p, st);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[3], st));
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
+        uint64_t hs[3] = {0, 0, 0};
+        CU(cudaMemcpyAsync(hs, ctx->scalars.p, 24, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((uint32_t)hs[2]) return fail(ctx, B200Z_E_CUDA, "LZMA2: frame slot overflow%s");
+        *produced = hs[0];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_ENC_ENTROPY_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stat[B200Z_S_ENC_ASSEMBLE_MS] += ms;
+    } else if (!stageMOnly) {
         launch_zstd_enc_entropy(d_src, n, g, (const uint64_t*)ctx->seqs.p, (const uint32_t*)ctx->nseq.p, (const uint8_t*)ctx->lits.p,
                                 (const uint32_t*)ctx->nlit.p, (uint8_t*)ctx->slots.p, (uint32_t*)ctx->slotSize.p, nBlocks, st);
         CU(cudaGetLastError());
@@ -243,7 +271,7 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
                 CU(cudaMemcpyAsync((uint32_t*)ctx->ready.p + c, ctx->hostOne, 4, cudaMemcpyHostToDevice, ctx->stream2));
             }
             uint64_t produced = 0;
-            int rc = enc_batch(ctx, (const uint8_t*)ctx->dIn.p, srcSize, (uint8_t*)ctx->dOut.p, &produced, false, (const uint32_t*)ctx->ready.p, shift);
+            int rc = enc_batch(ctx, (const uint8_t*)ctx->dIn.p, srcSize, (uint8_t*)ctx->dOut.p, &produced, false, (const uint32_t*)ctx->ready.p, shift, 0);
             if (rc) { cudaStreamSynchronize(ctx->stream2); return rc; }
             out = (size_t)produced;
         }
@@ -306,6 +334,74 @@ int b200z_zstd_enc_stage_m(b200z_ctx* ctx, const void* d_src, size_t srcSize, ui
         dense += nb;
     }
     CU(cudaMemcpy(lits, ctx->lits.p, srcSize, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------- LZMA2 (method 21) encoder
+size_t b200z_lzma2_compress_bound(b200z_ctx* ctx, size_t srcSize) {
+    const uint32_t fl = ctx ? ctx->geom.frameLog : B2Z_DEF_FRAMELOG;
+    const size_t F = (size_t)1 << fl, frames = (srcSize + F - 1) / F;
+    return srcSize + frames * ((F / 8192u + 2u) * 8u + 16u) + 64u;      // every finished chunk <= its input + 6, >= 8 KiB of input per chunk
+}
+
+int b200z_lzma2_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_dst, size_t dstCap, size_t* dstSize, uint32_t* dictProp) {
+    if (!ctx || !dstSize || (!d_src && srcSize) || !d_dst) return B200Z_E_PARAM;
+    if ((uintptr_t)d_src & 15u) return fail(ctx, B200Z_E_PARAM, "device source must be 16-byte aligned%s");
+    if (dstCap < b200z_lzma2_compress_bound(ctx, srcSize)) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_lzma2_compress_bound%s");
+    if (dictProp) *dictProp = (ctx->geom.frameLog - 12u) * 2u;           // dictionary = frame size (Lzma2Enc_WriteProperties, Lzma2Enc.c:671)
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t F = 1ull << ctx->geom.frameLog;
+    uint64_t batch = 1ull << ctx->batchLog; if (batch < F) batch = F;
+    uint64_t done = 0, outPos = 0;
+    while (done < srcSize) {
+        const uint64_t n = (srcSize - done) < batch ? (srcSize - done) : batch;
+        uint64_t produced = 0;
+        int rc = enc_batch(ctx, (const uint8_t*)d_src + done, n, (uint8_t*)d_dst + outPos, &produced, false, nullptr, 0, 1);
+        if (rc) return rc;
+        done += n; outPos += produced - 1;                               // the next batch overwrites this batch's end marker
+    }
+    if (!srcSize) CU(cudaMemsetAsync(d_dst, 0, 1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *dstSize = (size_t)outPos + 1;
+    return 0;
+}
+
+// Host-pointer form; one batch: chunked upload overlapped with stage M (as the zstd path), kernels, download.
+int b200z_lzma2_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize, uint32_t* dictProp) {
+    if (!ctx || !dstSize || (!src && srcSize) || !dst) return B200Z_E_PARAM;
+    const size_t bound = b200z_lzma2_compress_bound(ctx, srcSize);
+    if (dstCap < bound) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_lzma2_compress_bound%s");
+    if (dictProp) *dictProp = (ctx->geom.frameLog - 12u) * 2u;
+    if (!srcSize) { *(uint8_t*)dst = 0; *dstSize = 1; return 0; }
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t F = 1ull << ctx->geom.frameLog;
+    uint64_t batch = 1ull << ctx->hostBatchLog; if (batch < F) batch = F;
+    const uint64_t maxIn = srcSize < batch ? srcSize : batch;
+    if (ctx->dIn.reserve(maxIn + 64) || ctx->dOut.reserve(b200z_lzma2_compress_bound(ctx, maxIn)) || ctx->ready.reserve(256))
+        return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+    if (!ctx->hostOne) { if (cudaHostAlloc((void**)&ctx->hostOne, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(ctx, B200Z_E_MEMORY, "pinned allocation failed%s"); } *ctx->hostOne = 1u; }
+    uint64_t done = 0, outPos = 0;
+    while (done < srcSize) {
+        const uint64_t n = (srcSize - done) < batch ? (srcSize - done) : batch;
+        uint32_t shift = 20; while (((n - 1) >> shift) >= 16) shift++;
+        const uint32_t nChunks = (uint32_t)(((n - 1) >> shift) + 1);
+        CU(cudaMemsetAsync(ctx->ready.p, 0, 256, ctx->stream));
+        CU(cudaEventRecord(ctx->pe[0], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->pe[0], 0));
+        for (uint32_t c = 0; c < nChunks; c++) {
+            const size_t off = (size_t)c << shift, len = (n - off) < ((size_t)1 << shift) ? (n - off) : ((size_t)1 << shift);
+            CU(cudaMemcpyAsync((uint8_t*)ctx->dIn.p + off, (const uint8_t*)src + done + off, len, cudaMemcpyHostToDevice, ctx->stream2));
+            CU(cudaMemcpyAsync((uint32_t*)ctx->ready.p + c, ctx->hostOne, 4, cudaMemcpyHostToDevice, ctx->stream2));
+        }
+        uint64_t produced = 0;
+        int rc = enc_batch(ctx, (const uint8_t*)ctx->dIn.p, n, (uint8_t*)ctx->dOut.p, &produced, false, (const uint32_t*)ctx->ready.p, shift, 1);
+        if (rc) { cudaStreamSynchronize(ctx->stream2); return rc; }
+        CU(cudaMemcpyAsync((uint8_t*)dst + outPos, ctx->dOut.p, produced, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)n; ctx->stat[B200Z_S_D2H_BYTES] += (double)produced;
+        done += n; outPos += produced - 1;
+    }
+    *dstSize = (size_t)outPos + 1;
     return 0;
 }
 

@@ -70,6 +70,31 @@ __host__ __device__ inline void lzma2_walk(const uint8_t* src, uint64_t srcSize,
     c.nBlocks = nb; c.status = status; c.maxLcLp = maxLcLp; c.pad = 0; c.srcUsed = ip; c.total = total;
 }
 
+// probability model layout shared by decoder and encoder (uint16 probabilities; own layout, same sets as LzmaDec.c:130-227)
+enum : uint32_t {
+    P_ISMATCH = 0,                    // [12][16]
+    P_ISREP = 192,                    // [12]
+    P_ISREPG0 = 204, P_ISREPG1 = 216, P_ISREPG2 = 228,
+    P_ISREP0LONG = 240,               // [12][16]
+    P_POSSLOT = 432,                  // [4][64]
+    P_SPECPOS = 688,                  // [115] (+1 pad)
+    P_ALIGN = 804,                    // [16]
+    P_LEN = 820,                      // choice, choice2, low[16][8], mid[16][8], high[256]  = 514
+    P_REPLEN = 1334,
+    P_LIT = 1848,                     // [0x300 << (lc+lp)]
+    L_CHOICE = 0, L_CHOICE2 = 1, L_LOW = 2, L_MID = 130, L_HIGH = 258
+};
+
+// ---- encoder (stage R): one thread per frame turns the stage-M sequences into one dictionary-reset LZMA2 block in its slot
+struct EncGeom;
+size_t lzma2_enc_slot_stride(uint32_t frameLog);
+cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
+                                   uint8_t* slots, uint32_t* slotSize, uint32_t nFrames, uint16_t* litSpill, uint32_t smCount, int mode,
+                                   uint32_t* status, cudaStream_t st);
+// offsets (one CTA scan) + gather of the frame slots into the contiguous chunk stream, end marker appended
+void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nFrames, uint32_t frameLog, uint64_t* frameOff,
+                               uint8_t* dst, uint64_t* outSize, cudaStream_t st);
+
 void launch_lzma2_walk(const uint8_t* src, uint64_t srcSize, Lz2Block* blocks, uint32_t cap, Lz2Counts* counts, cudaStream_t st);
 // one warp per block; returns cudaError of the launch configuration (shared memory opt-in)
 size_t lzma2_lit_spill_bytes(uint32_t nBlocks, uint32_t maxLcLp);

@@ -32,6 +32,19 @@
 #define B2Z_SEQ_LL(s)      ((uint32_t)(((s) >> 25) & 0x3FFFFu))
 #define B2Z_SEQ_ML(s)      ((uint32_t)(((s) >> 43) & 0x3FFFFu))
 
+/* ---- LZMA2 encoder (stage R: range coding of the stage-M sequences of one frame = one dictionary-reset block) ---- */
+#define B2Z_LZ2_LC 3u
+#define B2Z_LZ2_LP 0u
+#define B2Z_LZ2_PB 2u
+#define B2Z_LZ2_PROPS ((B2Z_LZ2_PB * 5u + B2Z_LZ2_LP) * 9u + B2Z_LZ2_LC)   /* 0x5D */
+#define B2Z_LZ2_PACK_LIMIT   (65536u - 64u)        /* a chunk is closed once this many packed bytes are pending (format max 64 KiB) */
+#define B2Z_LZ2_UNPACK_LIMIT ((1u << 21) - 512u)   /* ... or this many input bytes are covered (format max 2 MiB)                 */
+#define B2Z_LZ2_MAXLEN 273u
+/* worst-case bytes of one frame's chunk stream while it is being produced: every finished chunk is at most its input + 6
+ * (raw fallback), a chunk covers >= 8 KiB of input (a literal costs < 7 bytes even with saturated models), plus the
+ * chunk in flight */
+#define B2Z_LZ2_FRAME_BOUND(n) ((n) + ((n) / 8192u + 2u) * 8u + 65536u + 128u)
+
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL
 #define B2Z_PRIME8 0xCF1BBCDCB7A56463ULL

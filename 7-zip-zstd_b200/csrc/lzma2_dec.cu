@@ -38,22 +38,6 @@ void launch_lzma2_walk(const uint8_t* src, uint64_t srcSize, Lz2Block* blocks, u
     lzma2_walk_kernel<<<1, 32, 0, st>>>(src, srcSize, blocks, cap, counts);
 }
 
-// ---------------------------------------------------------------------------------------------------- model layout
-// (uint16 probabilities; own layout, same sets as LzmaDec.c:130-227)
-enum : uint32_t {
-    P_ISMATCH = 0,                    // [12][16]
-    P_ISREP = 192,                    // [12]
-    P_ISREPG0 = 204, P_ISREPG1 = 216, P_ISREPG2 = 228,
-    P_ISREP0LONG = 240,               // [12][16]
-    P_POSSLOT = 432,                  // [4][64]
-    P_SPECPOS = 688,                  // [115] (+1 pad)
-    P_ALIGN = 804,                    // [16]
-    P_LEN = 820,                      // choice, choice2, low[16][8], mid[16][8], high[256]  = 514
-    P_REPLEN = 1334,
-    P_LIT = 1848,                     // [0x300 << (lc+lp)]
-    L_CHOICE = 0, L_CHOICE2 = 1, L_LOW = 2, L_MID = 130, L_HIGH = 258
-};
-
 enum : uint32_t { OP_END = 0, OP_MATCH = 1, OP_RAW = 2, OP_RESET = 3, OP_ERROR = 4 };
 
 struct Rc {

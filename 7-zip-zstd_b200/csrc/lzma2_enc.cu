@@ -1,0 +1,299 @@
+// lzma2_enc.cu -- stage R of the block-parallel LZMA2 encoder (7-Zip method 21) for sm_100a.
+//
+// A frame (2^frameLog input bytes) becomes one dictionary-reset LZMA2 block -- the independent unit the reference's own
+// MT coders use (Lzma2Enc.c:241-330 block split; fast-lzma2 slices, lzma2_enc.c:1937-2099).  Stage M (zstd_enc_match.cu,
+// shared with the zstd path) has already found the frame's sequences; here one thread per frame codes them as LZMA
+// packets with the adaptive binary range coder, which is a strictly serial chain of ~100 instructions per input byte:
+// the parallelism is across frames (thousands per batch), not inside one.
+//   model      11-bit probabilities in shared memory (16 KiB, 13 frames/SM) or, when there are more frames than that
+//              fills, the 12 KiB literal part in global memory (32 frames/SM)
+//   input      bytes the next packet needs (its symbol, the previous byte, the byte at rep0) are loaded before the
+//              current packet is coded, so their L2 latency hides under ~10^3 cycles of range coding
+//   chunks     closed at 64 KiB - 64 packed bytes or 2 MiB - 512 covered; a chunk that does not shrink is rewritten as
+//              an uncompressed chunk and the next one resets the model (Lzma2Enc.c:183-238)
+//
+// Replaces (reference, /root/reference/C/): LzmaEnc.c:691-760 (range coder), :795-860 (literals), :934-1010 (lengths),
+// :2388-2600 (packets), Lzma2Enc.c:129-238 (chunks), fast-lzma2/range_enc.c, lzma2_enc.c:1937-2099.
+// Oracle statement: oracle/lzma2_enc_oracle.c (byte-exact).
+#include "b2z_device.cuh"
+#include "b2z_kernels.h"
+#include "b2z_lzma2.h"
+#include "b2z_params.h"
+
+namespace b2z {
+
+struct RcE {
+    uint64_t low; uint32_t range, cacheSize, cache;
+    uint8_t* out; uint32_t op;
+};
+
+__device__ __forceinline__ void rce_shift_low(RcE& e) {
+    if ((uint32_t)e.low < 0xFF000000u || (uint32_t)(e.low >> 32) != 0u) {
+        const uint32_t carry = (uint32_t)(e.low >> 32);
+        uint32_t c = e.cache;
+        do { e.out[e.op++] = (uint8_t)(c + carry); c = 0xFFu; } while (--e.cacheSize != 0u);
+        e.cache = ((uint32_t)e.low >> 24) & 0xFFu;
+    }
+    e.cacheSize++;
+    e.low = (e.low & 0x00FFFFFFull) << 8;
+}
+__device__ __forceinline__ void rce_bit(RcE& e, uint16_t* p, uint32_t bit) {
+    const uint32_t v = *p, bound = (e.range >> 11) * v;
+    if (!bit) { e.range = bound; *p = (uint16_t)(v + ((2048u - v) >> 5)); }
+    else { e.low += bound; e.range -= bound; *p = (uint16_t)(v - (v >> 5)); }
+    while (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }
+}
+__device__ __forceinline__ void rce_direct(RcE& e, uint32_t v, uint32_t n) {
+    while (n--) {
+        e.range >>= 1;
+        if ((v >> n) & 1u) e.low += e.range;
+        while (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }
+    }
+}
+__device__ __forceinline__ void rce_tree(RcE& e, uint16_t* p, uint32_t bits, uint32_t v) {
+    uint32_t m = 1;
+    for (uint32_t i = bits; i--;) { const uint32_t b = (v >> i) & 1u; rce_bit(e, p + m, b); m = (m << 1) | b; }
+}
+__device__ __forceinline__ void rce_tree_rev(RcE& e, uint16_t* p, uint32_t bits, uint32_t v) {
+    uint32_t m = 1;
+    for (uint32_t i = 0; i < bits; i++) { const uint32_t b = (v >> i) & 1u; rce_bit(e, p + m, b); m = (m << 1) | b; }
+}
+__device__ __forceinline__ void rce_len(RcE& e, uint16_t* l, uint32_t len, uint32_t ps) {
+    len -= 2u;
+    if (len < 8u) { rce_bit(e, l + L_CHOICE, 0); rce_tree(e, l + L_LOW + ps * 8u, 3, len); }
+    else if (len < 16u) { rce_bit(e, l + L_CHOICE, 1); rce_bit(e, l + L_CHOICE2, 0); rce_tree(e, l + L_MID + ps * 8u, 3, len - 8u); }
+    else { rce_bit(e, l + L_CHOICE, 1); rce_bit(e, l + L_CHOICE2, 1); rce_tree(e, l + L_HIGH, 8, len - 16u); }
+}
+
+template <bool GLIT>
+__global__ void __launch_bounds__(32)
+lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint64_t* __restrict__ seqs,
+                       const uint32_t* __restrict__ nseq, uint8_t* __restrict__ slots, uint32_t slotStride,
+                       uint32_t* __restrict__ slotSize, uint16_t* __restrict__ litSpill, uint32_t* __restrict__ status) {
+    extern __shared__ uint16_t probs[];
+    if (threadIdx.x) return;                                        // one thread per frame; see the header comment
+    const uint32_t f = blockIdx.x;
+    const uint64_t f0 = (uint64_t)f << g.frameLog, F = 1ull << g.frameLog;
+    const uint32_t n = (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
+    const uint8_t* __restrict__ base = src + f0;
+    const uint32_t bpf = (uint32_t)(F >> 17), nblk = (n + B2Z_BLOCK - 1u) / B2Z_BLOCK;
+    constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
+    uint16_t* const lit = GLIT ? litSpill + (size_t)f * LITN : probs + P_LIT;
+    constexpr uint32_t PBM = (1u << B2Z_LZ2_PB) - 1u, LPM = (1u << B2Z_LZ2_LP) - 1u;
+
+    RcE e; e.low = 0; e.range = 0; e.cacheSize = 0; e.cache = 0; e.out = slots + (size_t)f * slotStride; e.op = 0;
+    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
+    uint32_t chunkPos = 0, chunkOut = 0, hdr = 0;
+    bool open = false, needDict = true, needProps = true, needState = true, overflow = false;
+
+    auto chunk_close = [&](uint32_t pos) {
+        for (int i = 0; i < 5; i++) rce_shift_low(e);
+        const uint32_t unpack = pos - chunkPos, pack = e.op - chunkOut - hdr;
+        uint8_t* h = e.out + chunkOut;
+        if (pack + 2u >= unpack) {                                  // store the chunk uncompressed
+            h[0] = needDict ? 1 : 2; h[1] = (uint8_t)((unpack - 1u) >> 8); h[2] = (uint8_t)(unpack - 1u);
+            const uint8_t* s = base + chunkPos;
+            for (uint32_t i = 0; i < unpack; i++) h[3u + i] = __ldg(s + i);
+            e.op = chunkOut + 3u + unpack;
+            needDict = false; needState = true;
+        } else {
+            const uint32_t mode = needDict ? 3u : (needProps ? 2u : (needState ? 1u : 0u));
+            h[0] = (uint8_t)(0x80u | (mode << 5) | ((unpack - 1u) >> 16)); h[1] = (uint8_t)((unpack - 1u) >> 8); h[2] = (uint8_t)(unpack - 1u);
+            h[3] = (uint8_t)((pack - 1u) >> 8); h[4] = (uint8_t)(pack - 1u);
+            if (mode >= 2u) h[5] = (uint8_t)B2Z_LZ2_PROPS;
+            needDict = needProps = needState = false;
+        }
+        open = false;
+    };
+    auto chunk_step = [&](uint32_t pos) {                           // before every packet
+        if (open && (e.op - chunkOut - hdr + e.cacheSize >= B2Z_LZ2_PACK_LIMIT || pos - chunkPos >= B2Z_LZ2_UNPACK_LIMIT)) chunk_close(pos);
+        if (!open) {
+            if (e.op + 65536u + 96u > slotStride) { overflow = true; return; }
+            chunkPos = pos; chunkOut = e.op;
+            hdr = (needDict || needProps) ? 6u : 5u;
+            if (needDict || needProps || needState) {
+                uint32_t* w = reinterpret_cast<uint32_t*>(probs);
+                for (uint32_t i = 0; i < (GLIT ? P_LIT : P_LIT + LITN) / 2u; i++) w[i] = 0x04000400u;
+                if (GLIT) { uint32_t* gl = reinterpret_cast<uint32_t*>(lit); for (uint32_t i = 0; i < LITN / 2u; i++) gl[i] = 0x04000400u; }
+                state = 0; rep0 = rep1 = rep2 = rep3 = 0;
+            }
+            e.op += hdr;
+            e.low = 0; e.range = 0xFFFFFFFFu; e.cache = 0; e.cacheSize = 1;
+            open = true;
+        }
+    };
+
+    // bytes of the packet about to be coded: cur = base[pos], prev = base[pos-1], mb = base[pos-rep0-1] (meaningful when state >= 7)
+    uint32_t pos = 0, cur = n ? (uint32_t)__ldg(base) : 0u, prev = 0, mb = 0;
+
+    auto literal = [&]() {
+        const uint32_t nxt = (pos + 1u < n) ? (uint32_t)__ldg(base + pos + 1u) : 0u;         // for the next packet
+        rce_bit(e, probs + P_ISMATCH + state * 16u + (pos & PBM), 0);
+        uint16_t* p = lit + 0x300u * (((pos & LPM) << B2Z_LZ2_LC) + (prev >> (8u - B2Z_LZ2_LC)));
+        uint32_t m = 1; bool matched = state >= 7u;
+        for (uint32_t i = 8; i--;) {
+            const uint32_t b = (cur >> i) & 1u;
+            if (matched) { const uint32_t mbit = (mb >> i) & 1u; rce_bit(e, p + ((1u + mbit) << 8) + m, b); if (mbit != b) matched = false; }
+            else rce_bit(e, p + m, b);
+            m = (m << 1) | b;
+        }
+        state = state < 4u ? 0u : (state < 10u ? state - 3u : state - 6u);
+        prev = cur; cur = nxt; pos++;
+    };
+    auto match = [&](uint32_t len, uint32_t dist) {                  // dist = distance - 1
+        const uint32_t pN = pos + len;
+        const uint32_t nxt = (pN < n) ? (uint32_t)__ldg(base + pN) : 0u, prevN = __ldg(base + pN - 1u), mbN = __ldg(base + pN - dist - 1u);
+        const uint32_t ps = pos & PBM;
+        rce_bit(e, probs + P_ISMATCH + state * 16u + ps, 1);
+        int r = dist == rep0 ? 0 : (dist == rep1 ? 1 : (dist == rep2 ? 2 : (dist == rep3 ? 3 : -1)));
+        if (r < 0) {
+            rce_bit(e, probs + P_ISREP + state, 0);
+            rce_len(e, probs + P_LEN, len, ps);
+            state = state < 7u ? 7u : 10u;
+            uint32_t slot;
+            if (dist < 4u) slot = dist; else { const uint32_t nb = highbit32(dist); slot = (nb << 1) | ((dist >> (nb - 1u)) & 1u); }
+            rce_tree(e, probs + P_POSSLOT + (len - 2u < 4u ? len - 2u : 3u) * 64u, 6, slot);
+            if (slot >= 4u) {
+                const uint32_t fb = (slot >> 1) - 1u, b = (2u | (slot & 1u)) << fb, red = dist - b;
+                if (slot < 14u) rce_tree_rev(e, probs + P_SPECPOS + b - slot - 1u, fb, red);
+                else { rce_direct(e, red >> 4, fb - 4u); rce_tree_rev(e, probs + P_ALIGN, 4, red & 15u); }
+            }
+            rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = dist;
+        } else {
+            rce_bit(e, probs + P_ISREP + state, 1);
+            if (r == 0) { rce_bit(e, probs + P_ISREPG0 + state, 0); rce_bit(e, probs + P_ISREP0LONG + state * 16u + ps, 1); }
+            else {
+                rce_bit(e, probs + P_ISREPG0 + state, 1);
+                if (r == 1) rce_bit(e, probs + P_ISREPG1 + state, 0);
+                else { rce_bit(e, probs + P_ISREPG1 + state, 1); rce_bit(e, probs + P_ISREPG2 + state, (uint32_t)(r - 2)); }
+                if (r == 3) rep3 = rep2;
+                if (r >= 2) rep2 = rep1;
+                rep1 = rep0; rep0 = dist;
+            }
+            rce_len(e, probs + P_REPLEN, len, ps);
+            state = state < 7u ? 8u : 11u;
+        }
+        cur = nxt; prev = prevN; mb = mbN; pos = pN;
+    };
+
+    for (uint32_t b = 0; b < nblk && !overflow; b++) {
+        const uint32_t bend = (b + 1u) * B2Z_BLOCK < n ? (b + 1u) * B2Z_BLOCK : n;
+        const uint64_t* __restrict__ sq = seqs + ((size_t)f * bpf + b) * B2Z_MAXSEQ;
+        const uint32_t ns = nseq[(size_t)f * bpf + b];
+        uint32_t z0 = 0, z1 = 0, z2 = 0;                             // zstd repcode history of the block, to undo offBase (Emitter::flush)
+        uint64_t sNext = ns ? __ldg(sq) : 0ull;
+        for (uint32_t i = 0; i < ns && !overflow; i++) {
+            const uint64_t s = sNext;
+            if (i + 1u < ns) sNext = __ldg(sq + i + 1u);
+            const uint32_t ll = B2Z_SEQ_LL(s), ob = B2Z_SEQ_OFFBASE(s); uint32_t ml = B2Z_SEQ_ML(s), off;
+            if (ob > 3u) { off = ob - 3u; z2 = z1; z1 = z0; z0 = off; }
+            else {
+                const uint32_t idx = ob - 1u + (ll == 0u);
+                off = idx == 3u ? z0 - 1u : (idx == 0u ? z0 : (idx == 1u ? z1 : z2));
+                if (idx != 0u) { if (idx != 1u) z2 = z1; z1 = z0; z0 = off; }
+            }
+            for (uint32_t j = 0; j < ll && !overflow; j++) { chunk_step(pos); if (!overflow) literal(); }
+            while (ml && !overflow) {
+                uint32_t len = ml > B2Z_LZ2_MAXLEN ? B2Z_LZ2_MAXLEN : ml;
+                if (ml - len == 1u) len--;
+                chunk_step(pos); if (overflow) break;
+                match(len, off - 1u); ml -= len;
+            }
+        }
+        while (pos < bend && !overflow) { chunk_step(pos); if (!overflow) literal(); }
+    }
+    if (open && !overflow) chunk_close(pos);
+    if (overflow) atomicOr(status, 1u);
+    slotSize[f] = e.op;
+}
+
+size_t lzma2_enc_slot_stride(uint32_t frameLog) { return ((size_t)B2Z_LZ2_FRAME_BOUND(1u << frameLog) + 255u) & ~(size_t)255u; }
+
+cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
+                                   uint8_t* slots, uint32_t* slotSize, uint32_t nFrames, uint16_t* litSpill, uint32_t smCount, int mode,
+                                   uint32_t* status, cudaStream_t st) {
+    if (!nFrames) return cudaSuccess;
+    constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
+    const size_t smemFull = ((size_t)P_LIT + LITN) * sizeof(uint16_t);
+    const uint32_t slotsResident = (uint32_t)((227u * 1024u) / (smemFull + 1024)) * smCount;
+    const bool glit = mode == 2 || (mode == 0 && litSpill && nFrames > slotsResident);
+    const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g.frameLog);
+    if (glit) {
+        lzma2_enc_range_kernel<true><<<nFrames, 32, P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status);
+    } else {
+        lzma2_enc_range_kernel<false><<<nFrames, 32, smemFull, st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, nullptr, status);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------- assembly
+__global__ void __launch_bounds__(1024)
+lzma2_enc_offsets_kernel(const uint32_t* __restrict__ slotSize, uint32_t nFrames, uint64_t* __restrict__ frameOff, uint64_t* __restrict__ outSize) {
+    __shared__ uint64_t warpSum[32];
+    __shared__ uint64_t carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nFrames; b0 += 1024u) {
+        const uint32_t i = b0 + tid;
+        const uint64_t v = i < nFrames ? slotSize[i] : 0u;
+        uint64_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t y = __shfl_up_sync(B2Z_FULL, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (lane == 31) warpSum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t s = warpSum[lane], t = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint64_t y = __shfl_up_sync(B2Z_FULL, t, d); if (lane >= (uint32_t)d) t += y; }
+            warpSum[lane] = t - s;
+        }
+        __syncthreads();
+        const uint64_t excl = carry + warpSum[wid] + (x - v);
+        if (i < nFrames) frameOff[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) { frameOff[nFrames] = carry; *outSize = carry + 1u; }
+}
+
+// CTA (x, y): part y of 8 of frame x's slot -> its place in the stream (16-byte stores fed by aligned 4-byte reads)
+__global__ void __launch_bounds__(256)
+lzma2_enc_gather_kernel(const uint8_t* __restrict__ slots, uint32_t slotStride, const uint32_t* __restrict__ slotSize,
+                        const uint64_t* __restrict__ frameOff, uint32_t nFrames, uint8_t* __restrict__ dst) {
+    const uint32_t f = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
+    const uint32_t total = slotSize[f];
+    const uint32_t per = ((total + 7u) / 8u + 15u) & ~15u;          // 16-byte aligned split of the slot
+    const uint32_t s0 = part * per;
+    if (f == nFrames - 1u && part == 0 && tid == 0) dst[frameOff[nFrames]] = 0;     // LZMA2 end marker
+    if (s0 >= total) return;
+    const uint32_t n = (total - s0) < per ? (total - s0) : per;
+    const uint8_t* s = slots + (size_t)f * slotStride + s0;
+    uint8_t* d = dst + frameOff[f] + s0;
+    const uint32_t head = (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u);
+    const uint32_t h = head < n ? head : n;
+    if (tid < h) d[tid] = s[tid];
+    const uint32_t body = (n - h) & ~15u;
+    const uint32_t sh = (h & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s + (h & ~3u));
+    uint4* dq = reinterpret_cast<uint4*>(d + h);
+    for (uint32_t i = tid; i < body / 16u; i += 256u) {
+        const uint32_t* q = sw + i * 4u;
+        const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = sh ? q[4] : 0u;
+        uint4 v;
+        v.x = __funnelshift_r(a0, a1, sh); v.y = __funnelshift_r(a1, a2, sh);
+        v.z = __funnelshift_r(a2, a3, sh); v.w = __funnelshift_r(a3, a4, sh);
+        dq[i] = v;
+    }
+    for (uint32_t i = h + body + tid; i < n; i += 256u) d[i] = s[i];
+}
+
+void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nFrames, uint32_t frameLog, uint64_t* frameOff,
+                               uint8_t* dst, uint64_t* outSize, cudaStream_t st) {
+    if (!nFrames) return;
+    lzma2_enc_offsets_kernel<<<1, 1024, 0, st>>>(slotSize, nFrames, frameOff, outSize);
+    lzma2_enc_gather_kernel<<<dim3(nFrames, 8), 256, 0, st>>>(slots, (uint32_t)lzma2_enc_slot_stride(frameLog), slotSize, frameOff, nFrames, dst);
+}
+
+}  // namespace b2z

@@ -109,6 +109,18 @@ int b200z_lzma2_decompress_device(b200z_ctx *ctx, const void *d_src, size_t srcS
 int b200z_lzma2_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, uint32_t dictProp,
                                 void *dst, size_t dstCap, size_t *dstSize);
 
+/* ---- LZMA2 / FLZMA2 (method 21) encoder --------------------------------------------------------------
+ * Writes a raw LZMA2 chunk stream (+ end marker) of independent dictionary-reset blocks, one per 2^FRAMELOG input bytes,
+ * and returns the 1-byte coder property for the 7z folder (what ICompressWriteCoderProperties emits,
+ * Lzma2Encoder.cpp:117-121 / FastLzma2 :353-364).  Replaces NCompress::NLzma2::CEncoder::Code -> Lzma2Enc_Encode2
+ * (Lzma2Encoder.cpp:124-134, C/Lzma2Enc.c:717) and CFastEncoder::Code -> FL2_compressStream (Lzma2Encoder.cpp:280-340,
+ * C/fast-lzma2/fl2_compress.c).  lc/lp/pb are fixed at 3/0/2. */
+size_t b200z_lzma2_compress_bound(b200z_ctx *ctx, size_t srcSize);
+int b200z_lzma2_compress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize, void *d_dst, size_t dstCap,
+                                size_t *dstSize, uint32_t *dictProp);
+int b200z_lzma2_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap,
+                              size_t *dstSize, uint32_t *dictProp);
+
 /* device memory helpers so FFI users need no CUDA binding of their own */
 int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);
 int b200z_dev_free(b200z_ctx *ctx, void *d_ptr);

@@ -40,6 +40,10 @@ int64_t b2zo_zstd_find_sequences(const void *src, size_t srcSize, const b2zo_enc
 /* raw LZMA2 chunk stream -> dst; dictProp = the coder's 1-byte property. returns size, -1 corrupt, -2 dst too small */
 int64_t b2zo_lzma2_decompress(void *dst, size_t dstCap, const void *src, size_t srcSize, uint32_t dictProp, size_t *srcUsed);
 
+/* ---- LZMA2 (method 21) encoder: lzma2_enc_oracle.c (sequential statement of the GPU encoder) ---- */
+size_t  b2zo_lzma2_compress_bound(size_t srcSize, const b2zo_enc_params *p);
+int64_t b2zo_lzma2_compress(void *dst, size_t dstCap, const void *src, size_t srcSize, const b2zo_enc_params *p, uint32_t *dictProp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,3 +234,15 @@ def ref_lzma2_decompress(comp, n, dict_prop):
     if rc != 0:
         raise ValueError(f"reference lzma2 decoder error {rc}")
     return dst[:dl.value].tobytes(), sl.value
+
+
+def oracle_lzma2_compress(data, **kw):
+    """sequential statement of the GPU LZMA2 encoder -> (dictProp, raw LZMA2 stream)"""
+    O = oracle(); p = enc_params(**kw); src = _np(data)
+    O.b2zo_lzma2_compress_bound.restype = ctypes.c_size_t; O.b2zo_lzma2_compress_bound.argtypes = [ctypes.c_size_t, ctypes.POINTER(EncParams)]
+    O.b2zo_lzma2_compress.restype = ctypes.c_int64
+    O.b2zo_lzma2_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(EncParams), ctypes.POINTER(ctypes.c_uint32)]
+    out = np.empty(O.b2zo_lzma2_compress_bound(len(data), ctypes.byref(p)), dtype=np.uint8); prop = ctypes.c_uint32(0)
+    r = O.b2zo_lzma2_compress(out.ctypes.data, out.size, src.ctypes.data, len(data), ctypes.byref(p), ctypes.byref(prop))
+    assert r > 0, r
+    return prop.value, out[:r].tobytes()
