@@ -1,0 +1,159 @@
+// Lzma2Coders.cpp -- NCompress::NLzma2::CEncoder / CFastEncoder / CDecoder for method 21 on top of the b200z C ABI.
+// Host-side mirror of the reference wrappers:
+//   CPP/7zip/Compress/Lzma2Encoder.{h,cpp}  (SetLzma2Prop :42-77, SetCoderProperties :80-91, WriteCoderProperties :117-121,
+//                                            Code :124-150; CFastEncoder :178-364: algo > 3 rejected, block size -> reset interval,
+//                                            1-byte property)
+//   CPP/7zip/Compress/Lzma2Decoder.{h,cpp}  (SetDecoderProperties2 :40-48 size 1 / <= 40 else E_NOTIMPL, SetFinishMode :51-55,
+//                                            Code :95-186, GetInStreamProcessedSize :189-193)
+// Same interface sets, property meaning and HRESULT mapping.  Below them: the encoder cuts the input into independent
+// dictionary-reset blocks (B200Z_P_FRAMELOG, taken from kBlockSize / kDictionarySize when given) and codes them on the GPU;
+// the decoder hands the whole packed stream of a folder to the GPU, which decodes its dictionary-reset blocks in parallel
+// (the unit Lzma2DecMt.c:237 uses).
+#include "b2z_coder_common.h"
+
+namespace {
+
+int log2_floor(uint64_t v) { int r = 0; while (v >>= 1) r++; return r; }
+
+class CLzma2Encoder final : public ICompressCoder, public ICompressSetCoderProperties, public ICompressSetCoderPropertiesOpt,
+                            public ICompressWriteCoderProperties, CoderBase {
+    std::atomic<UInt32> refs_{0};
+    const bool fast_;
+    int frameLog_ = 20;                                        // 1 MiB blocks: thousands of independent blocks per GiB
+    PinnedBuf in_, out_;
+public:
+    UInt64 processedIn = 0, processedOut = 0;
+    explicit CLzma2Encoder(bool fast) : fast_(fast) {}
+    HRESULT QueryInterface(const GUID& iid, void** out) override {
+        *out = nullptr;
+        if (iid == kIID_IUnknown || iid == b2z_iid(4, kIID_Coder)) *out = static_cast<ICompressCoder*>(this);
+        else if (iid == b2z_iid(4, kIID_SetProps)) *out = static_cast<ICompressSetCoderProperties*>(this);
+        else if (iid == b2z_iid(4, kIID_SetPropsOpt) && !fast_) *out = static_cast<ICompressSetCoderPropertiesOpt*>(this);   // CFastEncoder has no Opt interface
+        else if (iid == b2z_iid(4, kIID_WriteProps)) *out = static_cast<ICompressWriteCoderProperties*>(this);
+        else return E_NOINTERFACE;
+        ++refs_; return S_OK;
+    }
+    UInt32 AddRef() override { return ++refs_; }
+    UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
+
+    HRESULT SetCoderProperties(const PROPID* ids, const PROPVARIANT* pv, UInt32 n) override {
+        uint64_t blockSize = 0, dictSize = 0;
+        for (UInt32 i = 0; i < n; i++) {
+            const PROPVARIANT& p = pv[i];
+            switch (ids[i]) {
+            case NCoderPropID::kBlockSize:                     // Lzma2Encoder.cpp:46-55
+                if (p.vt == VT_UI4) blockSize = p.ulVal; else if (p.vt == VT_UI8) blockSize = p.uhVal; else return E_INVALIDARG;
+                break;
+            case NCoderPropID::kNumThreads: if (p.vt != VT_UI4) return E_INVALIDARG; break;
+            case NCoderPropID::kNumThreadGroups: if (p.vt != VT_UI4 || p.ulVal >= (1u << 16)) return E_INVALIDARG; break;
+            case NCoderPropID::kDictionarySize: if (p.vt != VT_UI4 && p.vt != VT_UI8) return E_INVALIDARG; dictSize = p.vt == VT_UI4 ? p.ulVal : p.uhVal; break;
+            case NCoderPropID::kAlgorithm: if (p.vt != VT_UI4) return E_INVALIDARG; if (fast_ && p.ulVal > 3) return E_INVALIDARG; break;   // Lzma2Encoder.cpp:197-199
+            case NCoderPropID::kLitContextBits: case NCoderPropID::kLitPosBits: case NCoderPropID::kPosStateBits:
+            case NCoderPropID::kNumFastBytes: case NCoderPropID::kMatchFinderCycles: case NCoderPropID::kLevel:
+                if (p.vt != VT_UI4) return E_INVALIDARG;      // accepted; the GPU coder runs lc3 lp0 pb2 and its own parser
+                break;
+            default: break;                                    // kMatchFinder, kEndMarker, kReduceSize, kAffinity ...: accepted
+            }
+        }
+        // independent block = dictionary = frame: the explicit block size wins, else the dictionary size, else 1 MiB
+        const uint64_t want = (blockSize && blockSize != ~0ull) ? blockSize : dictSize;
+        if (want) { int fl = log2_floor(want); frameLog_ = fl < 17 ? 17 : (fl > 24 ? 24 : fl); }
+        return S_OK;
+    }
+    HRESULT SetCoderPropertiesOpt(const PROPID*, const PROPVARIANT*, UInt32) override { return S_OK; }   // kExpectedDataSize
+    HRESULT WriteCoderProperties(ISequentialOutStream* out) override {
+        const Byte prop = (Byte)((frameLog_ - 12) * 2);        // dictionary size 2^frameLog (Lzma2Enc_WriteProperties, Lzma2Enc.c:671-690)
+        return write_stream(out, &prop, 1);
+    }
+
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64*, ICompressProgressInfo* progress) override {
+        processedIn = processedOut = 0;
+        HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
+        b200z_set_param(ctx, B200Z_P_FRAMELOG, frameLog_);
+        b200z_set_param(ctx, B200Z_P_WINDOWLOG, frameLog_);
+        const size_t batch = (size_t)1 << 30;                  // 1 GiB of input per GPU pass (about a thousand blocks)
+        if (!in_.reserve(batch) || !out_.reserve(b200z_lzma2_compress_bound(ctx, batch))) return E_OUTOFMEMORY;
+        for (;;) {
+            size_t got = batch;
+            hr = read_stream(inS, in_.p, &got);
+            if (hr != S_OK) return hr;
+            if (got == 0) break;
+            size_t produced = 0; uint32_t prop = 0;
+            int rc = b200z_lzma2_compress_host(ctx, in_.p, got, out_.p, out_.cap, &produced, &prop);
+            if (rc) return hr_from_b200z(rc);
+            hr = write_stream(outS, out_.p, produced - 1);     // every batch ends with the end marker: kept for the very end only
+            if (hr != S_OK) return hr;
+            processedIn += got; processedOut += produced - 1;
+            if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
+            if (got < batch) break;
+        }
+        const Byte endMark = 0;
+        processedOut += 1;
+        return write_stream(outS, &endMark, 1);
+    }
+};
+
+class CLzma2Decoder final : public ICompressCoder, public ICompressSetDecoderProperties2, public ICompressSetFinishMode,
+                            public ICompressGetInStreamProcessedSize, public ICompressSetCoderMt, CoderBase {
+    std::atomic<UInt32> refs_{0};
+    Byte prop_ = 40; bool finishMode_ = false; UInt64 inProcessed_ = 0;
+    std::vector<Byte> in_;
+    PinnedBuf out_;
+public:
+    UInt64 processedIn = 0, processedOut = 0;
+    HRESULT QueryInterface(const GUID& iid, void** out) override {
+        *out = nullptr;
+        if (iid == kIID_IUnknown || iid == b2z_iid(4, kIID_Coder)) *out = static_cast<ICompressCoder*>(this);
+        else if (iid == b2z_iid(4, kIID_SetDecProps2)) *out = static_cast<ICompressSetDecoderProperties2*>(this);
+        else if (iid == b2z_iid(4, kIID_SetFinishMode)) *out = static_cast<ICompressSetFinishMode*>(this);
+        else if (iid == b2z_iid(4, kIID_GetInProcessed)) *out = static_cast<ICompressGetInStreamProcessedSize*>(this);
+        else if (iid == b2z_iid(4, kIID_SetMt)) *out = static_cast<ICompressSetCoderMt*>(this);
+        else return E_NOINTERFACE;
+        ++refs_; return S_OK;
+    }
+    UInt32 AddRef() override { return ++refs_; }
+    UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
+    HRESULT SetDecoderProperties2(const Byte* p, UInt32 size) override {       // Lzma2Decoder.cpp:40-48
+        if (size != 1 || p[0] > 40) return E_NOTIMPL;
+        prop_ = p[0]; return S_OK;
+    }
+    HRESULT SetFinishMode(UInt32 m) override { finishMode_ = m != 0; return S_OK; }
+    HRESULT GetInStreamProcessedSize(UInt64* v) override { *v = inProcessed_; return S_OK; }
+    HRESULT SetNumberOfThreads(UInt32) override { return S_OK; }                // parallelism = blocks in the stream
+
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
+        processedIn = processedOut = 0; inProcessed_ = 0;
+        HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
+        in_.clear();
+        for (;;) {                                             // the blocks of one folder are decoded together: read the packed stream to its end
+            const size_t chunk = (size_t)8 << 20, at = in_.size();
+            in_.resize(at + chunk);
+            size_t got = chunk;
+            hr = read_stream(inS, in_.data() + at, &got);
+            in_.resize(at + got);
+            if (hr != S_OK) return hr;
+            if (got < chunk) break;
+        }
+        uint64_t content = 0; uint32_t blocks = 0; size_t used = 0;
+        int rc = b200z_lzma2_stream_info(in_.data(), in_.size(), &content, &blocks, &used);
+        if (rc) return hr_from_b200z(rc);
+        if (!out_.reserve((size_t)content + 64)) return E_OUTOFMEMORY;
+        size_t produced = 0;
+        rc = b200z_lzma2_decompress_host(ctx, in_.data(), used, prop_, out_.p, (size_t)content, &produced);
+        if (rc) return hr_from_b200z(rc);
+        inProcessed_ = processedIn = used;
+        size_t toWrite = produced;
+        if (outSize && *outSize < toWrite) toWrite = (size_t)*outSize;          // the folder's unpack size bounds the output
+        processedOut = toWrite;
+        hr = write_stream(outS, out_.p, toWrite);
+        if (hr != S_OK) return hr;
+        if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
+        if (finishMode_ && outSize && *outSize != produced) return S_FALSE;     // Lzma2Decoder.cpp:177-183: stream must end exactly there
+        return S_OK;
+    }
+};
+
+}  // namespace
+
+ICompressCoder* b2z_new_lzma2_encoder(bool fast) { return new CLzma2Encoder(fast); }
+ICompressCoder* b2z_new_lzma2_decoder() { return new CLzma2Decoder(); }

@@ -10,8 +10,7 @@
 #include <atomic>
 #include <new>
 #include <vector>
-#include "b2z_7zip_abi.h"
-#include "../../include/b200z.h"
+#include "b2z_coder_common.h"
 
 namespace {
 
@@ -19,70 +18,6 @@ const uint64_t kZstdMethodId = 0x4F71101;
 const uint32_t kZ7Major = 26, kZ7Minor = 1;                // module version reported to the host (C/7zVersion.h)
 const Byte kZstdVerMajor = 1, kZstdVerMinor = 5;           // header bytes (ZstdEncoder.h:17-32)
 const uint32_t kFastLevInc = 32, kUltimateLev = 128;       // ICoder.h:163-166
-
-HRESULT hr_from_b200z(int rc) {
-    switch (rc) {
-    case B200Z_OK: return S_OK;
-    case B200Z_E_MEMORY: return E_OUTOFMEMORY;
-    case B200Z_E_PARAM: return E_INVALIDARG;
-    case B200Z_E_CORRUPT: case B200Z_E_CHECKSUM: return S_FALSE;      // data error (ZstdDecoder.cpp:115-130)
-    case B200Z_E_UNSUPPORTED: return E_NOTIMPL;
-    default: return E_FAIL;                                           // incl. no device: there is no CPU fallback
-    }
-}
-
-HRESULT read_stream(ISequentialInStream* s, void* data, size_t* size) {   // StreamUtils.cpp:54 semantics
-    size_t want = *size; *size = 0;
-    while (want) {
-        UInt32 cur = want < (1u << 30) ? (UInt32)want : (1u << 30), got = 0;
-        HRESULT r = s->Read(data, cur, &got);
-        *size += got; data = (Byte*)data + got; want -= got;
-        if (r != S_OK) return r;
-        if (got == 0) return S_OK;
-    }
-    return S_OK;
-}
-HRESULT write_stream(ISequentialOutStream* s, const void* data, size_t size) {   // StreamUtils.cpp:87
-    while (size) {
-        UInt32 cur = size < (1u << 30) ? (UInt32)size : (1u << 30), done = 0;
-        HRESULT r = s->Write(data, cur, &done);
-        data = (const Byte*)data + done; size -= done;
-        if (r != S_OK) return r;
-        if (done == 0) return E_FAIL;
-    }
-    return S_OK;
-}
-
-struct PinnedBuf {                                          // pinned host staging (grown on demand)
-    void* p = nullptr; size_t cap = 0;
-    bool reserve(size_t n) {
-        if (n <= cap) return true;
-        void* q = nullptr;
-        if (b200z_host_alloc_pinned(&q, n) != 0) return false;
-        if (p) { memcpy(q, p, cap); b200z_host_free_pinned(p); }
-        p = q; cap = n; return true;
-    }
-    ~PinnedBuf() { if (p) b200z_host_free_pinned(p); }
-};
-
-template <class T> struct RefCounted : T {
-    std::atomic<UInt32> refs{0};
-    UInt32 AddRef() override { return ++refs; }
-    UInt32 Release() override { UInt32 r = --refs; if (r == 0) delete this; return r; }
-    virtual ~RefCounted() {}
-};
-
-// one C++ object exposing several COM-style interfaces: a small aggregate with inner facets
-struct CoderBase {
-    b200z_ctx* ctx = nullptr;
-    HRESULT ensure_ctx() {
-        if (ctx) return S_OK;
-        int dev = 0;
-        if (const char* e = getenv("B200Z_DEVICE")) dev = atoi(e);      // device selection without a new PROPID
-        return hr_from_b200z(b200z_create(&ctx, dev));
-    }
-    ~CoderBase() { if (ctx) b200z_destroy(ctx); }
-};
 
 // ------------------------------------------------------------------ encoder
 class CEncoder final : public ICompressCoder, public ICompressSetCoderMt, public ICompressSetCoderProperties,
@@ -243,18 +178,32 @@ public:
 }  // namespace
 
 // ------------------------------------------------------------------ module exports (CodecExports.cpp:153-378)
+// Methods, in the reference's registration order: ZSTD (ZstdRegister.cpp:13-17), LZMA2 (Lzma2Register.cpp:16-20) and
+// FLZMA2 (FastLzma2Register.cpp:13-18) -- the last two share ID 0x21: encoders are chosen by name, decoders by ID.
+ICompressCoder* b2z_new_lzma2_encoder(bool fast);        // Lzma2Coders.cpp
+ICompressCoder* b2z_new_lzma2_decoder();
+
+namespace {
+const uint64_t kLzma2MethodId = 0x21;
+struct MethodInfo { uint64_t id; const char* name; };
+const MethodInfo kMethods[3] = { { kZstdMethodId, "ZSTD" }, { kLzma2MethodId, "LZMA2" }, { kLzma2MethodId, "FLZMA2" } };
+// class ids: the reference derives them from the method id alone, so LZMA2 and FLZMA2 encoders would collide; as in
+// CodecExports.cpp:95-125 CreateObject resolves a clsid to the FIRST method with that id (LZMA2)
+}
+
 extern "C" {
 
-HRESULT GetNumberOfMethods(UInt32* n) { *n = 1; return S_OK; }
+HRESULT GetNumberOfMethods(UInt32* n) { *n = 3; return S_OK; }
 
 HRESULT GetMethodProperty(UInt32 index, PROPID propID, PROPVARIANT* value) {
     memset(value, 0, sizeof(*value));
-    if (index != 0) return E_INVALIDARG;
+    if (index >= 3) return E_INVALIDARG;
+    const MethodInfo& m = kMethods[index];
     switch (propID) {
-    case NMethodPropID::kID: value->vt = VT_UI8; value->uhVal = kZstdMethodId; break;
-    case NMethodPropID::kName: value->bstrVal = b2z_alloc_bstr_ascii("ZSTD"); if (!value->bstrVal) return E_OUTOFMEMORY; value->vt = VT_BSTR; break;
+    case NMethodPropID::kID: value->vt = VT_UI8; value->uhVal = m.id; break;
+    case NMethodPropID::kName: value->bstrVal = b2z_alloc_bstr_ascii(m.name); if (!value->bstrVal) return E_OUTOFMEMORY; value->vt = VT_BSTR; break;
     case NMethodPropID::kDecoder: case NMethodPropID::kEncoder: {
-        const GUID g = b2z_clsid(propID == NMethodPropID::kEncoder, kZstdMethodId);
+        const GUID g = b2z_clsid(propID == NMethodPropID::kEncoder, m.id);
         value->bstrVal = b2z_alloc_bstr_bytes(&g, sizeof(g)); if (!value->bstrVal) return E_OUTOFMEMORY; value->vt = VT_BSTR; break; }
     case NMethodPropID::kDecoderIsAssigned: case NMethodPropID::kEncoderIsAssigned: value->vt = VT_BOOL; value->boolVal = -1; break;
     case NMethodPropID::kIsFilter: value->vt = VT_BOOL; value->boolVal = 0; break;
@@ -263,21 +212,26 @@ HRESULT GetMethodProperty(UInt32 index, PROPID propID, PROPVARIANT* value) {
     return S_OK;
 }
 
-static HRESULT create_coder(bool encoder, const GUID* iid, void** out) {
+static HRESULT create_coder(UInt32 index, bool encoder, const GUID* iid, void** out) {
     *out = nullptr;
+    if (index >= 3) return E_INVALIDARG;
     if (!(*iid == b2z_iid(4, kIID_Coder))) return E_NOINTERFACE;
     try {
-        ICompressCoder* c = encoder ? static_cast<ICompressCoder*>(new CEncoder()) : static_cast<ICompressCoder*>(new CDecoder());
+        ICompressCoder* c;
+        if (index == 0) c = encoder ? static_cast<ICompressCoder*>(new CEncoder()) : static_cast<ICompressCoder*>(new CDecoder());
+        else c = encoder ? b2z_new_lzma2_encoder(index == 2) : b2z_new_lzma2_decoder();
         c->AddRef(); *out = c; return S_OK;
     } catch (...) { return E_OUTOFMEMORY; }
 }
-HRESULT CreateEncoder(UInt32 index, const GUID* iid, void** out) { return index == 0 ? create_coder(true, iid, out) : E_INVALIDARG; }
-HRESULT CreateDecoder(UInt32 index, const GUID* iid, void** out) { return index == 0 ? create_coder(false, iid, out) : E_INVALIDARG; }
+HRESULT CreateEncoder(UInt32 index, const GUID* iid, void** out) { return create_coder(index, true, iid, out); }
+HRESULT CreateDecoder(UInt32 index, const GUID* iid, void** out) { return create_coder(index, false, iid, out); }
 
 HRESULT CreateObject(const GUID* clsid, const GUID* iid, void** out) {
     *out = nullptr;
-    if (*clsid == b2z_clsid(true, kZstdMethodId)) return create_coder(true, iid, out);
-    if (*clsid == b2z_clsid(false, kZstdMethodId)) return create_coder(false, iid, out);
+    for (UInt32 i = 0; i < 3; i++) {
+        if (*clsid == b2z_clsid(true, kMethods[i].id)) return create_coder(i, true, iid, out);
+        if (*clsid == b2z_clsid(false, kMethods[i].id)) return create_coder(i, false, iid, out);
+    }
     return CLASS_E_CLASSNOTAVAILABLE;
 }
 

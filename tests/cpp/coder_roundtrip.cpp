@@ -1,7 +1,7 @@
 // coder_roundtrip.cpp -- drives libb200z_7z.so exactly as 7-Zip's codec loader does
 // (CPP/7zip/UI/Common/LoadCodecs.cpp:279-303,528-563: dlsym the exports, GetModuleProp check,
 // GetMethodProperty, CreateEncoder/CreateDecoder by index, then ICompressCoder::Code()).
-// usage: coder_roundtrip <lib.so> <input file> <packed output file> [level]      (needs a GPU)
+// usage: coder_roundtrip <lib.so> <input file> <packed output file> [level] [zstd|lzma2|flzma2]      (needs a GPU)
 //        coder_roundtrip <lib.so> --exports                                      (no GPU needed)
 #include <dlfcn.h>
 #include <cstdio>
@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
     auto CreateObject = (HRESULT(*)(const GUID*, const GUID*, void**))dlsym(h, "CreateObject");
     auto GetModuleProp = (HRESULT(*)(PROPID, PROPVARIANT*))dlsym(h, "GetModuleProp");
     CHECK(GetNumberOfMethods && GetMethodProperty && CreateEncoder && CreateDecoder && CreateObject && GetModuleProp);
-    UInt32 n = 0; CHECK(GetNumberOfMethods(&n) == S_OK && n == 1);
+    UInt32 n = 0; CHECK(GetNumberOfMethods(&n) == S_OK && n == 3);
     PROPVARIANT v;
     CHECK(GetModuleProp(NModulePropID::kInterfaceType, &v) == S_OK && v.vt == VT_UI4 && v.ulVal == 0);
     CHECK(GetModuleProp(NModulePropID::kVersion, &v) == S_OK && v.ulVal == ((26u << 16) | 1u));
@@ -60,8 +60,67 @@ int main(int argc, char** argv) {
     CHECK(GetMethodProperty(0, NMethodPropID::kEncoder, &v) == S_OK && v.vt == VT_BSTR);
     { GUID g; memcpy(&g, v.bstrVal, 16); CHECK(g == b2z_clsid(true, 0x4F71101)); uint32_t len; memcpy(&len, (char*)v.bstrVal - 4, 4); CHECK(len == 16); }
     CHECK(GetMethodProperty(0, NMethodPropID::kIsFilter, &v) == S_OK && v.vt == VT_BOOL && v.boolVal == 0);
+    // methods 1, 2: LZMA2 and FLZMA2 share ID 0x21 (Lzma2Register.cpp:16-20, FastLzma2Register.cpp:13-18)
+    CHECK(GetMethodProperty(1, NMethodPropID::kID, &v) == S_OK && v.uhVal == 0x21 && GetMethodProperty(2, NMethodPropID::kID, &v) == S_OK && v.uhVal == 0x21);
+    CHECK(GetMethodProperty(1, NMethodPropID::kName, &v) == S_OK && v.bstrVal[0] == L'L' && v.bstrVal[4] == L'2' && v.bstrVal[5] == 0);
+    CHECK(GetMethodProperty(2, NMethodPropID::kName, &v) == S_OK && v.bstrVal[0] == L'F' && v.bstrVal[5] == L'2' && v.bstrVal[6] == 0);
+    CHECK(GetMethodProperty(3, NMethodPropID::kID, &v) == E_INVALIDARG);
     const GUID iidCoder = b2z_iid(4, kIID_Coder);
     void* obj = nullptr;
+    {   // LZMA2 coder objects: interface sets and property semantics (no GPU needed)
+        void* o = nullptr; CHECK(CreateEncoder(2, &iidCoder, &o) == S_OK && o);
+        ICompressCoder* fe = (ICompressCoder*)o; ICompressSetCoderProperties* fs = nullptr; ICompressWriteCoderProperties* fw = nullptr; void* none = nullptr;
+        CHECK(fe->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&fs) == S_OK && fe->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&fw) == S_OK);
+        CHECK(fe->QueryInterface(b2z_iid(4, kIID_SetPropsOpt), &none) == E_NOINTERFACE);              // CFastEncoder has no ...PropertiesOpt
+        PROPID ia[1] = { NCoderPropID::kAlgorithm }; PROPVARIANT pa[1]; memset(pa, 0, sizeof(pa)); pa[0].vt = VT_UI4; pa[0].ulVal = 4;
+        CHECK(fs->SetCoderProperties(ia, pa, 1) == E_INVALIDARG);                                    // Lzma2Encoder.cpp:197-199
+        PROPID ib[2] = { NCoderPropID::kDictionarySize, NCoderPropID::kLevel }; PROPVARIANT pb[2]; memset(pb, 0, sizeof(pb));
+        pb[0].vt = VT_UI4; pb[0].ulVal = 1u << 22; pb[1].vt = VT_UI4; pb[1].ulVal = 5;
+        CHECK(fs->SetCoderProperties(ib, pb, 2) == S_OK);
+        MemOut ph; CHECK(fw->WriteCoderProperties(&ph) == S_OK && ph.d.size() == 1 && ph.d[0] == 20);   // 4 MiB dictionary -> property 20
+        fs->Release(); fw->Release(); CHECK(fe->Release() == 0);
+        CHECK(CreateDecoder(1, &iidCoder, &o) == S_OK && o);
+        ICompressCoder* ld = (ICompressCoder*)o; ICompressSetDecoderProperties2* lp = nullptr; ICompressSetFinishMode* lf = nullptr; ICompressGetInStreamProcessedSize* lg = nullptr;
+        CHECK(ld->QueryInterface(b2z_iid(4, kIID_SetDecProps2), (void**)&lp) == S_OK && ld->QueryInterface(b2z_iid(4, kIID_SetFinishMode), (void**)&lf) == S_OK);
+        CHECK(ld->QueryInterface(b2z_iid(4, kIID_GetInProcessed), (void**)&lg) == S_OK);
+        const Byte ok1[1] = { 24 }, bad1[1] = { 41 };
+        CHECK(lp->SetDecoderProperties2(ok1, 1) == S_OK && lp->SetDecoderProperties2(bad1, 1) == E_NOTIMPL && lp->SetDecoderProperties2(ok1, 5) == E_NOTIMPL);
+        lp->Release(); lf->Release(); lg->Release(); CHECK(ld->Release() == 0);
+    }
+    const std::string method = argc > 5 ? argv[5] : "zstd";
+    if (method != "zstd" && std::string(argv[2]) != "--exports") {
+        const UInt32 idx = method == "flzma2" ? 2 : 1;
+        std::vector<Byte> input;
+        { FILE* f = fopen(argv[2], "rb"); CHECK(f); Byte buf[1 << 16]; size_t k; while ((k = fread(buf, 1, sizeof(buf), f)) > 0) input.insert(input.end(), buf, buf + k); fclose(f); }
+        void* o = nullptr; CHECK(CreateEncoder(idx, &iidCoder, &o) == S_OK && o);
+        ICompressCoder* e = (ICompressCoder*)o; ICompressSetCoderProperties* s = nullptr; ICompressWriteCoderProperties* w = nullptr;
+        CHECK(e->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&s) == S_OK && e->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&w) == S_OK);
+        PROPID ids2[2] = { NCoderPropID::kLevel, NCoderPropID::kNumThreads }; PROPVARIANT pv2[2]; memset(pv2, 0, sizeof(pv2));
+        pv2[0].vt = VT_UI4; pv2[0].ulVal = 5; pv2[1].vt = VT_UI4; pv2[1].ulVal = 8;
+        CHECK(s->SetCoderProperties(ids2, pv2, 2) == S_OK);
+        MemOut ph; CHECK(w->WriteCoderProperties(&ph) == S_OK && ph.d.size() == 1 && ph.d[0] == 16);
+        MemIn in(input); MemOut packed; Progress prog;
+        HRESULT r = e->Code(&in, &packed, nullptr, nullptr, &prog);
+        if (r != S_OK) { fprintf(stderr, "lzma2 encoder Code() = 0x%08x\n", (unsigned)r); return 1; }
+        CHECK(prog.calls >= 1 && !packed.d.empty() && packed.d.back() == 0);
+        CHECK(CreateDecoder(idx, &iidCoder, &o) == S_OK);
+        ICompressCoder* d = (ICompressCoder*)o; ICompressSetDecoderProperties2* dp = nullptr; ICompressSetFinishMode* fm = nullptr; ICompressGetInStreamProcessedSize* gp = nullptr;
+        CHECK(d->QueryInterface(b2z_iid(4, kIID_SetDecProps2), (void**)&dp) == S_OK && d->QueryInterface(b2z_iid(4, kIID_SetFinishMode), (void**)&fm) == S_OK);
+        CHECK(d->QueryInterface(b2z_iid(4, kIID_GetInProcessed), (void**)&gp) == S_OK);
+        CHECK(dp->SetDecoderProperties2(ph.d.data(), 1) == S_OK && fm->SetFinishMode(1) == S_OK);
+        MemIn pin(packed.d); MemOut back; UInt64 outSize = input.size();
+        r = d->Code(&pin, &back, nullptr, &outSize, nullptr);
+        if (r != S_OK) { fprintf(stderr, "lzma2 decoder Code() = 0x%08x\n", (unsigned)r); return 1; }
+        CHECK(back.d == input);
+        UInt64 inProc = 0; CHECK(gp->GetInStreamProcessedSize(&inProc) == S_OK && inProc == packed.d.size());
+        { std::vector<Byte> bad(packed.d.begin(), packed.d.begin() + packed.d.size() / 2); MemIn bi(bad); MemOut bo; CHECK(d->Code(&bi, &bo, nullptr, &outSize, nullptr) == S_FALSE); }
+        { UInt64 wrong = input.size() + 1; MemIn p2(packed.d); MemOut b2; CHECK(d->Code(&p2, &b2, nullptr, &wrong, nullptr) == S_FALSE); }   // finish mode: sizes must agree
+        { FILE* f = fopen(argv[3], "wb"); CHECK(f); fwrite(packed.d.data(), 1, packed.d.size(), f); fclose(f); }
+        s->Release(); w->Release(); dp->Release(); fm->Release(); gp->Release();
+        CHECK(e->Release() == 0 && d->Release() == 0);
+        printf("roundtrip ok: %zu -> %zu bytes (%s)\n", input.size(), packed.d.size(), method.c_str());
+        return 0;
+    }
     CHECK(CreateEncoder(0, &iidCoder, &obj) == S_OK && obj);
     ICompressCoder* enc = (ICompressCoder*)obj;
     ICompressSetCoderProperties* sp = nullptr; ICompressWriteCoderProperties* wp = nullptr; ICompressSetCoderMt* mt = nullptr;
