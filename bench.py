@@ -32,6 +32,8 @@ def parse_args():
     ap.add_argument("--size-mib", type=int, default=4096, help="uncompressed MiB per GPU per step (cfg2: 4 GiB)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-mib", type=int, default=1024, help="bounded sample for the CPU reference arm")
+    ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
+                    help="zstd: method 4F71101 level 3 (the headline, BASELINE configs[1]); lzma2: method 21 (configs[3])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -118,23 +120,50 @@ def cpu_reference(sample_bytes, seed_offset=0):
             "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": sample_bytes / r, "t_enc_s": t_enc, "t_dec_s": t_dec}
 
 
+def cpu_reference_lzma2(sample_bytes, seed_offset=0):
+    """Method 21 on the host cores, the way the reference's coders run it: Fast-LZMA2 level 5 with all threads for encode
+    (CFastEncoder -> FL2_compressStream, Lzma2Encoder.cpp:280-340; FL2_compressMt keeps the same level table and reset
+    interval) and the multi-threaded LZMA2 decoder for decode (Lzma2Decoder.cpp:95-186 -> Lzma2DecMt_Decode, driven by
+    oracle/ref_harness/lzma2_decmt_harness.c with memory streams)."""
+    import helpers
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    cores = os.cpu_count() or 1
+    if not helpers.ref_lzma_available():
+        raise SystemExit("bench.py --codec lzma2: oracle/_ref/libref_lzma.so missing (built by __graft_entry__.build() where /root/reference exists)")
+    data = pkg.corpus.g2(sample_bytes, offset=seed_offset).tobytes()
+    t = time.perf_counter(); prop, comp = helpers.ref_fl2_compress(data, 5, threads=0); t_enc = time.perf_counter() - t
+    t = time.perf_counter(); back, mt = helpers.ref_lzma2_decompress_mt(comp, sample_bytes, prop, min(cores, 64)); t_dec = time.perf_counter() - t
+    assert back == data
+    mb = sample_bytes / 1e6
+    return {"value": mb / (t_enc + t_dec), "unit": "MB/s", "cores": cores, "kind": "reference",
+            "sample": f"{sample_bytes >> 20} MiB of the same G2 text: Fast-LZMA2 level 5 encode on all threads (FL2_compressMt), reference MT decoder "
+                      f"({min(cores, 64)} threads; ran {'multi' if mt else 'single'}-threaded: parallelism = dictionary resets in the stream)",
+            "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": sample_bytes / len(comp), "t_enc_s": t_enc, "t_dec_s": t_dec}
+
+
 def main():
     a = parse_args()
+    lz = a.codec == "lzma2"
+    cpu_ref = cpu_reference_lzma2 if lz else cpu_reference
+    metric_name = "LZMA2 (method 21) encode+decode throughput" if lz else "zstd-L3 encode+decode throughput"
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     unit_bytes = a.size_mib << 20
     workload = f"zstd level 3, {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 128 KiB blocks"
+    if lz:
+        workload = f"LZMA2 / Fast-LZMA2 coder (method 21), {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 1 MiB dictionary-reset blocks"
 
     if a.impl == "reference":
         if rank != 0:
             return
         sample = a.cpu_sample_mib << 20
         for _ in range(max(0, min(a.warmup, 1))):
-            cpu_reference(min(sample, 64 << 20))
+            cpu_ref(min(sample, 64 << 20))
         t_tot = 0.0; res = None
         for _ in range(a.steps):
-            res = cpu_reference(sample); t_tot += res["t_enc_s"] + res["t_dec_s"]
+            res = cpu_ref(sample); t_tot += res["t_enc_s"] + res["t_dec_s"]
         value = a.steps * sample / 1e6 / t_tot
-        line = {"impl": "reference", "metric": "zstd-L3 encode+decode throughput", "value": value, "unit": "MB/s", "n_gpus": a.gpus,
+        line = {"impl": "reference", "metric": metric_name, "value": value, "unit": "MB/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_tot / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": workload, "sample": res["sample"]},
@@ -164,11 +193,16 @@ def main():
     host_in = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
     pkg.corpus.g2_into(host_in.data_ptr(), unit_bytes, offset=rank * unit_bytes, threads=max(1, (os.cpu_count() or 8) // max(1, world)))
     d_in = host_in.cuda(non_blocking=False)
-    bound = codec.compress_bound(unit_bytes)
+    bound = codec.lzma2_compress_bound(unit_bytes) if lz else codec.compress_bound(unit_bytes)
     d_comp = torch.empty(bound, dtype=torch.uint8, device="cuda")
     d_back = torch.empty(unit_bytes, dtype=torch.uint8, device="cuda")
 
     def step_device():
+        if lz:
+            t0 = time.perf_counter(); c, prop = codec.lzma2_compress_device(d_in.data_ptr(), unit_bytes, d_comp.data_ptr(), bound); t1 = time.perf_counter()
+            n = codec.lzma2_decompress_device(d_comp.data_ptr(), c, prop, d_back.data_ptr(), unit_bytes); t2 = time.perf_counter()
+            assert n == unit_bytes
+            return c, t1 - t0, t2 - t1
         t0 = time.perf_counter(); c = codec.compress_device(d_in.data_ptr(), unit_bytes, d_comp.data_ptr(), bound); t1 = time.perf_counter()
         n = codec.decompress_device(d_comp.data_ptr(), c, d_back.data_ptr(), unit_bytes); t2 = time.perf_counter()
         assert n == unit_bytes
@@ -203,6 +237,11 @@ def main():
         host_back = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
 
         def step_host():
+            if lz:
+                c, prop = codec.lzma2_compress_into(host_in.data_ptr(), unit_bytes, host_comp.data_ptr(), bound)
+                n = codec.lzma2_decompress_into(host_comp.data_ptr(), c, prop, host_back.data_ptr(), unit_bytes)
+                assert n == unit_bytes
+                return c
             c = codec.compress_into(host_in.data_ptr(), unit_bytes, host_comp.data_ptr(), bound)
             n = codec.decompress_into(host_comp.data_ptr(), c, host_back.data_ptr(), unit_bytes)
             assert n == unit_bytes
@@ -230,27 +269,29 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0); peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
-    match_ms = stats["match_ms"] / a.steps
+    # LZMA2: the dominant kernel is stage R (lzma2_enc_range_kernel: one serial range-coder chain per 1 MiB block)
+    dom_kernel = "lzma2_enc_range_kernel" if lz else "zstd_enc_match_kernel"
+    match_ms = (stats["entropy_ms"] if lz else stats["match_ms"]) / a.steps
     algo_bytes = unit_bytes * (1.0 + 1.0 / ratio)
     achieved = algo_bytes / 1e9 / (match_ms / 1e3) if match_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lzma2_range_traffic.json" if lz else "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
     except Exception:
         pass
     line = {
-        "metric": "zstd-L3 encode+decode throughput", "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": metric_name, "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "global_uncompressed_bytes_per_step": world * unit_bytes, "frame_log": codec.get("frame_log"),
                    "parallelism": f"{world} independent shard(s), no collective", "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
                    "ratio": ratio, "enc_MBps": units_mb / t_enc, "dec_MBps": units_mb / t_dec,
                    "kernel_ms_per_step": {k: v / a.steps for k, v in stats.items() if k != "launches"}},
-        "roofline": {"bound": "hbm", "kernel": "zstd_enc_match_kernel", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": match_ms},
         "clocks": clocks, "gpu_launches": int(stats["launches"]), "e2e": e2e,
     }
     if not a.no_cpu_baseline and world == 1:
-        cb = cpu_reference(a.cpu_sample_mib << 20)
+        cb = cpu_ref(a.cpu_sample_mib << 20)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
     print(json.dumps(line))
     if dist:

@@ -246,3 +246,15 @@ def oracle_lzma2_compress(data, **kw):
     r = O.b2zo_lzma2_compress(out.ctypes.data, out.size, src.ctypes.data, len(data), ctypes.byref(p), ctypes.byref(prop))
     assert r > 0, r
     return prop.value, out[:r].tobytes()
+
+
+def ref_lzma2_decompress_mt(comp, n, dict_prop, threads):
+    """the reference's MT decoder path (C/Lzma2DecMt.c driven as Lzma2Decoder.cpp:95-186 does) -> (bytes, ran_multithreaded)"""
+    L = ref_lzma(); src = _np(comp); dst = np.empty(n + 1, dtype=np.uint8)
+    L.refh_lzma2_decode_mt.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p, ctypes.c_size_t,
+                                       ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(ctypes.c_int)]
+    out = ctypes.c_size_t(0); mt = ctypes.c_int(0)
+    rc = L.refh_lzma2_decode_mt(dst.ctypes.data, n, ctypes.byref(out), src.ctypes.data, len(comp), dict_prop, threads, ctypes.byref(mt))
+    if rc != 0:
+        raise ValueError(f"reference lzma2 MT decoder error {rc}")
+    return dst[:out.value].tobytes(), bool(mt.value)
