@@ -41,13 +41,13 @@ __device__ __forceinline__ void rce_bit(RcE& e, uint16_t* p, uint32_t bit) {
     const uint32_t v = *p, bound = (e.range >> 11) * v;
     if (!bit) { e.range = bound; *p = (uint16_t)(v + ((2048u - v) >> 5)); }
     else { e.low += bound; e.range -= bound; *p = (uint16_t)(v - (v >> 5)); }
-    while (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }
+    if (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }     // one step suffices: v >= 31, so range >= 2^13 * 31 before it
 }
 __device__ __forceinline__ void rce_direct(RcE& e, uint32_t v, uint32_t n) {
     while (n--) {
         e.range >>= 1;
         if ((v >> n) & 1u) e.low += e.range;
-        while (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }
+        if (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }
     }
 }
 __device__ __forceinline__ void rce_tree(RcE& e, uint16_t* p, uint32_t bits, uint32_t v) {
@@ -130,13 +130,17 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
         const uint32_t nxt = (pos + 1u < n) ? (uint32_t)__ldg(base + pos + 1u) : 0u;         // for the next packet
         rce_bit(e, probs + P_ISMATCH + state * 16u + (pos & PBM), 0);
         uint16_t* p = lit + 0x300u * (((pos & LPM) << B2Z_LZ2_LC) + (prev >> (8u - B2Z_LZ2_LC)));
-        uint32_t m = 1; bool matched = state >= 7u;
-        for (uint32_t i = 8; i--;) {
-            const uint32_t b = (cur >> i) & 1u;
-            if (matched) { const uint32_t mbit = (mb >> i) & 1u; rce_bit(e, p + ((1u + mbit) << 8) + m, b); if (mbit != b) matched = false; }
-            else rce_bit(e, p + m, b);
-            m = (m << 1) | b;
+        uint32_t m = 1, i = 8;
+        if (state >= 7u) {                                          // matched literal: context follows the byte at rep0 while it agrees
+            while (i) {
+                --i;
+                const uint32_t b = (cur >> i) & 1u, mbit = (mb >> i) & 1u;
+                rce_bit(e, p + ((1u + mbit) << 8) + m, b);
+                m = (m << 1) | b;
+                if (mbit != b) break;
+            }
         }
+        while (i) { --i; const uint32_t b = (cur >> i) & 1u; rce_bit(e, p + m, b); m = (m << 1) | b; }
         state = state < 4u ? 0u : (state < 10u ? state - 3u : state - 6u);
         prev = cur; cur = nxt; pos++;
     };
