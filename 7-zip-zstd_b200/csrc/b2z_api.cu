@@ -40,7 +40,7 @@ int b200z_create(b200z_ctx** out, int device) {
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
     ctx->geom.rowLog = B2Z_DEF_ROWLOG;
-    ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1;   // size hints on: lets any decoder (ours included) find frames without walking blocks
+    ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);   // size hints on: lets any decoder (ours included) find frames without walking blocks
     *out = ctx;
     return B200Z_OK;
 }
@@ -71,7 +71,9 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_HASHLOG_L: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
     case B200Z_P_HASHLOG_S: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogS out of range%s"); ctx->geom.hashLogS = (uint32_t)v; return 0;
     case B200Z_P_WINDOWLOG: if (v < 10 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "windowLog out of range%s"); ctx->geom.windowLog = (uint32_t)v; return 0;
-    case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (uint32_t)v; return 0;
+    case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (ctx->geom.flags & ~3u) | (uint32_t)v; return 0;
+    case B200Z_P_LZMA2_SLICELOG: if (v < 0 || v > 3) return fail(ctx, B200Z_E_PARAM, "lzma2 sliceLog out of range%s");
+                            ctx->geom.flags = (ctx->geom.flags & ~0x700u) | ((uint32_t)v << 8); return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
     case B200Z_P_ROWLOG:    if (v < 8 || v > 18) return fail(ctx, B200Z_E_PARAM, "rowLog out of range%s"); ctx->geom.rowLog = (uint32_t)v; return 0;
     case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
@@ -88,7 +90,8 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_HASHLOG_L: *v = ctx->geom.hashLogL; return 0;
     case B200Z_P_HASHLOG_S: *v = ctx->geom.hashLogS; return 0;
     case B200Z_P_WINDOWLOG: *v = ctx->geom.windowLog; return 0;
-    case B200Z_P_FLAGS: *v = ctx->geom.flags; return 0;
+    case B200Z_P_FLAGS: *v = ctx->geom.flags & 3u; return 0;
+    case B200Z_P_LZMA2_SLICELOG: *v = B2Z_LZ2_SLICELOG(ctx->geom.flags); return 0;
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
@@ -127,10 +130,10 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     bad |= ctx->nseq.reserve(nBlocks * 4);
     bad |= ctx->lits.reserve(nBlocks * (size_t)B2Z_BLOCK);
     bad |= ctx->nlit.reserve(nBlocks * 4);
-    bad |= ctx->slots.reserve(codec == 1 ? nFrames * lzma2_enc_slot_stride(ctx->geom.frameLog) : nBlocks * (size_t)B2Z_SLOT);
+    bad |= ctx->slots.reserve(codec == 1 ? nFrames * lzma2_enc_slices_per_frame(ctx->geom) * lzma2_enc_slot_stride(ctx->geom) : nBlocks * (size_t)B2Z_SLOT);
     bad |= ctx->slotSize.reserve(nBlocks * 4);
     bad |= ctx->blockOff.reserve((nBlocks + 1) * 8);
-    bad |= ctx->frameOff.reserve((nFrames + 2) * 8);
+    bad |= ctx->frameOff.reserve((nFrames * (codec == 1 ? lzma2_enc_slices_per_frame(ctx->geom) : 1u) + 2) * 8);
     bad |= ctx->scalars.reserve(64);
     bad |= ctx->cks.reserve((nFrames + 2) * 4);
     return bad ? fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s") : 0;
@@ -158,16 +161,17 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         // LZMA2: stage R (range coding, one thread per frame) + assembly of the frame slots into one chunk stream
         constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
         uint16_t* spill = nullptr;
-        if (ctx->lz2Mode != 1 && nFrames > 13ull * ctx->smCount / 2u && ctx->decScratch[5].reserve((size_t)nFrames * LITN * 2u) == 0) spill = (uint16_t*)ctx->decScratch[5].p;
+        const uint64_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
+        if (ctx->lz2Mode != 1 && nChains > 13ull * ctx->smCount / 2u && ctx->decScratch[5].reserve((size_t)nChains * LITN * 2u) == 0) spill = (uint16_t*)ctx->decScratch[5].p;
         if (ctx->lz2Mode == 2 && !spill) {
-            if (ctx->decScratch[5].reserve((size_t)nFrames * LITN * 2u)) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");
+            if (ctx->decScratch[5].reserve((size_t)nChains * LITN * 2u)) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");
             spill = (uint16_t*)ctx->decScratch[5].p;
         }
         CU(cudaMemsetAsync(ctx->scalars.p, 0, 64, st));
         CU(launch_lzma2_enc_range(d_src, n, g, (const uint64_t*)ctx->seqs.p, (const uint32_t*)ctx->nseq.p, (uint8_t*)ctx->slots.p,
                                   (uint32_t*)ctx->slotSize.p, (uint32_t)nFrames, spill, ctx->smCount, ctx->lz2Mode, (uint32_t*)ctx->scalars.p + 4, st));
         CU(cudaEventRecord(ctx->ev[2], st));
-        launch_lzma2_enc_assemble((const uint8_t*)ctx->slots.p, (const uint32_t*)ctx->slotSize.p, (uint32_t)nFrames, g.frameLog,
+        launch_lzma2_enc_assemble((const uint8_t*)ctx->slots.p, (const uint32_t*)ctx->slotSize.p, (uint32_t)nChains, (uint32_t)lzma2_enc_slot_stride(g),
                                   (uint64_t*)ctx->frameOff.p, d_dst, (uint64_t*)ctx->scalars.p, st);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[3], st));

@@ -87,12 +87,13 @@ enum : uint32_t {
 
 // ---- encoder (stage R): one thread per frame turns the stage-M sequences into one dictionary-reset LZMA2 block in its slot
 struct EncGeom;
-size_t lzma2_enc_slot_stride(uint32_t frameLog);
+size_t lzma2_enc_slot_stride(const EncGeom& g);
+uint32_t lzma2_enc_slices_per_frame(const EncGeom& g);
 cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
                                    uint8_t* slots, uint32_t* slotSize, uint32_t nFrames, uint16_t* litSpill, uint32_t smCount, int mode,
                                    uint32_t* status, cudaStream_t st);
 // offsets (one CTA scan) + gather of the frame slots into the contiguous chunk stream, end marker appended
-void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nFrames, uint32_t frameLog, uint64_t* frameOff,
+void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nPieces, uint32_t slotStride, uint64_t* pieceOff,
                                uint8_t* dst, uint64_t* outSize, cudaStream_t st);
 
 void launch_lzma2_walk(const uint8_t* src, uint64_t srcSize, Lz2Block* blocks, uint32_t cap, Lz2Counts* counts, cudaStream_t st);

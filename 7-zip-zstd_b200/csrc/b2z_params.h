@@ -40,6 +40,11 @@
 #define B2Z_LZ2_PACK_LIMIT   (65536u - 64u)        /* a chunk is closed once this many packed bytes are pending (format max 64 KiB) */
 #define B2Z_LZ2_UNPACK_LIMIT ((1u << 21) - 512u)   /* ... or this many input bytes are covered (format max 2 MiB)                 */
 #define B2Z_LZ2_MAXLEN 273u
+/* flags bits 8..10: log2 of the state-reset slices a frame's range coding is split into (0..3, clamped to the frame's blocks) */
+#define B2Z_DEF_LZ2_SLICELOG 2u
+#define B2Z_LZ2_SLICELOG(flags) (((flags) >> 8) & 7u)
+#define B2Z_LZ2_SLICE_BLOCKS(frameLog, flags) \
+    ((B2Z_LZ2_SLICELOG(flags) >= (frameLog) - 17u) ? 1u : (1u << ((frameLog) - 17u - B2Z_LZ2_SLICELOG(flags))))
 /* worst-case bytes of one frame's chunk stream while it is being produced: every finished chunk is at most its input + 6
  * (raw fallback), a chunk covers >= 8 KiB of input (a literal costs < 7 bytes even with saturated models), plus the
  * chunk in flight */

@@ -66,25 +66,33 @@ __device__ __forceinline__ void rce_len(RcE& e, uint16_t* l, uint32_t len, uint3
 }
 
 template <bool GLIT>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint64_t* __restrict__ seqs,
                        const uint32_t* __restrict__ nseq, uint8_t* __restrict__ slots, uint32_t slotStride,
-                       uint32_t* __restrict__ slotSize, uint16_t* __restrict__ litSpill, uint32_t* __restrict__ status) {
-    extern __shared__ uint16_t probs[];
-    if (threadIdx.x) return;                                        // one thread per frame; see the header comment
-    const uint32_t f = blockIdx.x;
-    const uint64_t f0 = (uint64_t)f << g.frameLog, F = 1ull << g.frameLog;
+                       uint32_t* __restrict__ slotSize, uint16_t* __restrict__ litSpill, uint32_t* __restrict__ status, uint32_t nChains) {
+    extern __shared__ uint16_t probsAll[];
+    if (threadIdx.x & 31u) return;                                  // one thread per chain; see the header comment
+    // chain = (frame, slice): a frame's range coding is split into state-reset slices of sliceBlocks 128 KiB blocks
+    const uint32_t chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (chain >= nChains) return;
+    constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
+    uint16_t* const probs = probsAll + (size_t)(threadIdx.x >> 5) * (GLIT ? P_LIT : P_LIT + LITN);
+    const uint64_t F = 1ull << g.frameLog;
+    const uint32_t bpf = (uint32_t)(F >> 17), sliceBlocks = B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags), spf = bpf / sliceBlocks;
+    const uint32_t f = chain / spf, sl = chain - f * spf;
+    const uint64_t f0 = (uint64_t)f << g.frameLog;
     const uint32_t n = (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
     const uint8_t* __restrict__ base = src + f0;
-    const uint32_t bpf = (uint32_t)(F >> 17), nblk = (n + B2Z_BLOCK - 1u) / B2Z_BLOCK;
-    constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
-    uint16_t* const lit = GLIT ? litSpill + (size_t)f * LITN : probs + P_LIT;
+    const uint32_t nblkFrame = (n + B2Z_BLOCK - 1u) / B2Z_BLOCK;
+    const uint32_t b0 = sl * sliceBlocks, b1 = (b0 + sliceBlocks) < nblkFrame ? (b0 + sliceBlocks) : nblkFrame;
+    uint16_t* const lit = GLIT ? litSpill + (size_t)chain * LITN : probs + P_LIT;
     constexpr uint32_t PBM = (1u << B2Z_LZ2_PB) - 1u, LPM = (1u << B2Z_LZ2_LP) - 1u;
 
-    RcE e; e.low = 0; e.range = 0; e.cacheSize = 0; e.cache = 0; e.out = slots + (size_t)f * slotStride; e.op = 0;
+    RcE e; e.low = 0; e.range = 0; e.cacheSize = 0; e.cache = 0; e.out = slots + (size_t)chain * slotStride; e.op = 0;
     uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
     uint32_t chunkPos = 0, chunkOut = 0, hdr = 0;
-    bool open = false, needDict = true, needProps = true, needState = true, overflow = false;
+    bool open = false, needDict = sl == 0, needProps = true, needState = true, overflow = false;
+    if (b0 >= nblkFrame) { slotSize[chain] = 0; return; }           // slice beyond the end of a short last frame
 
     auto chunk_close = [&](uint32_t pos) {
         for (int i = 0; i < 5; i++) rce_shift_low(e);
@@ -124,7 +132,7 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
     };
 
     // bytes of the packet about to be coded: cur = base[pos], prev = base[pos-1], mb = base[pos-rep0-1] (meaningful when state >= 7)
-    uint32_t pos = 0, cur = n ? (uint32_t)__ldg(base) : 0u, prev = 0, mb = 0;
+    uint32_t pos = b0 * B2Z_BLOCK, cur = __ldg(base + pos), prev = pos ? (uint32_t)__ldg(base + pos - 1u) : 0u, mb = 0;
 
     auto literal = [&]() {
         const uint32_t nxt = (pos + 1u < n) ? (uint32_t)__ldg(base + pos + 1u) : 0u;         // for the next packet
@@ -180,7 +188,7 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
         cur = nxt; prev = prevN; mb = mbN; pos = pN;
     };
 
-    for (uint32_t b = 0; b < nblk && !overflow; b++) {
+    for (uint32_t b = b0; b < b1 && !overflow; b++) {
         const uint32_t bend = (b + 1u) * B2Z_BLOCK < n ? (b + 1u) * B2Z_BLOCK : n;
         const uint64_t* __restrict__ sq = seqs + ((size_t)f * bpf + b) * B2Z_MAXSEQ;
         const uint32_t ns = nseq[(size_t)f * bpf + b];
@@ -208,24 +216,32 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
     }
     if (open && !overflow) chunk_close(pos);
     if (overflow) atomicOr(status, 1u);
-    slotSize[f] = e.op;
+    slotSize[chain] = e.op;
 }
 
-size_t lzma2_enc_slot_stride(uint32_t frameLog) { return ((size_t)B2Z_LZ2_FRAME_BOUND(1u << frameLog) + 255u) & ~(size_t)255u; }
+uint32_t lzma2_enc_slices_per_frame(const EncGeom& g) { return (1u << (g.frameLog - 17u)) / B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags); }
+// slot of one chain (slice): worst case of its chunk stream while it is being produced
+size_t lzma2_enc_slot_stride(const EncGeom& g) {
+    const uint32_t sliceBytes = B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags) * B2Z_BLOCK;
+    return ((size_t)B2Z_LZ2_FRAME_BOUND(sliceBytes) + 255u) & ~(size_t)255u;
+}
 
 cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
                                    uint8_t* slots, uint32_t* slotSize, uint32_t nFrames, uint16_t* litSpill, uint32_t smCount, int mode,
                                    uint32_t* status, cudaStream_t st) {
     if (!nFrames) return cudaSuccess;
     constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
+    const uint32_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
     const size_t smemFull = ((size_t)P_LIT + LITN) * sizeof(uint16_t);
     const uint32_t slotsResident = (uint32_t)((227u * 1024u) / (smemFull + 1024)) * smCount;
-    const bool glit = mode == 2 || (mode == 0 && litSpill && nFrames > slotsResident);
-    const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g.frameLog);
-    if (glit) {
-        lzma2_enc_range_kernel<true><<<nFrames, 32, P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status);
+    const bool glit = mode == 2 || (mode == 0 && litSpill && nChains > slotsResident);
+    const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
+    if (glit) {     // two chains per CTA: 32 CTAs/SM would cap residency at 32 chains; 3.6 KiB of model each -> ~60 per SM
+        lzma2_enc_range_kernel<true><<<(nChains + 1u) / 2u, 64, 2u * P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);
     } else {
-        lzma2_enc_range_kernel<false><<<nFrames, 32, smemFull, st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, nullptr, status);
+        cudaError_t e = cudaFuncSetAttribute(lzma2_enc_range_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemFull);
+        if (e != cudaSuccess) return e;
+        lzma2_enc_range_kernel<false><<<nChains, 32, smemFull, st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, nullptr, status, nChains);
     }
     return cudaGetLastError();
 }
@@ -262,13 +278,13 @@ lzma2_enc_offsets_kernel(const uint32_t* __restrict__ slotSize, uint32_t nFrames
     if (tid == 0) { frameOff[nFrames] = carry; *outSize = carry + 1u; }
 }
 
-// CTA (x, y): part y of 8 of frame x's slot -> its place in the stream (16-byte stores fed by aligned 4-byte reads)
+// CTA (x, y): part y of gridDim.y of piece x's slot -> its place in the stream (16-byte stores fed by aligned 4-byte reads)
 __global__ void __launch_bounds__(256)
 lzma2_enc_gather_kernel(const uint8_t* __restrict__ slots, uint32_t slotStride, const uint32_t* __restrict__ slotSize,
                         const uint64_t* __restrict__ frameOff, uint32_t nFrames, uint8_t* __restrict__ dst) {
     const uint32_t f = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
     const uint32_t total = slotSize[f];
-    const uint32_t per = ((total + 7u) / 8u + 15u) & ~15u;          // 16-byte aligned split of the slot
+    const uint32_t per = ((total + gridDim.y - 1u) / gridDim.y + 15u) & ~15u;     // 16-byte aligned split of the slot
     const uint32_t s0 = part * per;
     if (f == nFrames - 1u && part == 0 && tid == 0) dst[frameOff[nFrames]] = 0;     // LZMA2 end marker
     if (s0 >= total) return;
@@ -293,11 +309,12 @@ lzma2_enc_gather_kernel(const uint8_t* __restrict__ slots, uint32_t slotStride, 
     for (uint32_t i = h + body + tid; i < n; i += 256u) d[i] = s[i];
 }
 
-void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nFrames, uint32_t frameLog, uint64_t* frameOff,
+// pieces = chains (frame slices) in stream order
+void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nPieces, uint32_t slotStride, uint64_t* pieceOff,
                                uint8_t* dst, uint64_t* outSize, cudaStream_t st) {
-    if (!nFrames) return;
-    lzma2_enc_offsets_kernel<<<1, 1024, 0, st>>>(slotSize, nFrames, frameOff, outSize);
-    lzma2_enc_gather_kernel<<<dim3(nFrames, 8), 256, 0, st>>>(slots, (uint32_t)lzma2_enc_slot_stride(frameLog), slotSize, frameOff, nFrames, dst);
+    if (!nPieces) return;
+    lzma2_enc_offsets_kernel<<<1, 1024, 0, st>>>(slotSize, nPieces, pieceOff, outSize);
+    lzma2_enc_gather_kernel<<<dim3(nPieces, 4), 256, 0, st>>>(slots, slotStride, slotSize, pieceOff, nPieces, dst);
 }
 
 }  // namespace b2z

@@ -49,6 +49,8 @@ extern "C" {
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
 #define B200Z_P_ROWLOG      9   /* log2 rows of the row-hash match finder (64-byte rows), 8..18, default 14   */
 #define B200Z_P_LZMA2_MODEL 10  /* LZMA2 decoder: literal model in 1 = shared memory (13 warps/SM), 2 = global memory (32 warps/SM), 0 = by block count */
+#define B200Z_P_LZMA2_SLICELOG 11 /* LZMA2 encoder: log2 of the state-reset slices a block's range coding is split into (0..3, default 2):
+                                   independent range-coder chains per block, as fast-lzma2's encoder threads (lzma2_enc.c:1937) */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,

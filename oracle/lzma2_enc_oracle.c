@@ -157,7 +157,10 @@ static void chunk_step(chunker *c, uint32_t pos) {
     if (!c->open) chunk_open(c, pos);
 }
 
-static size_t encode_frame(enc_t *e, const uint8_t *base, uint32_t n, const uint64_t *seqs, const uint32_t *nseq, uint8_t *out) {
+/* sliceBlocks: a frame is coded as slices of this many 128 KiB blocks; every slice after the first starts a new chunk with a
+ * state reset (control 0xA0: fresh model, same dictionary), which makes the slices' range coders independent of each other --
+ * the scheme of fast-lzma2's encoder threads (lzma2_enc.c:1937-2099 "props/state reset at slice start") */
+static size_t encode_frame(enc_t *e, const uint8_t *base, uint32_t n, const uint64_t *seqs, const uint32_t *nseq, uint8_t *out, uint32_t sliceBlocks) {
     chunker c; memset(&c, 0, sizeof(c));
     c.e = e; c.base = base; c.needDict = c.needProps = c.needState = 1;
     e->out = out; e->op = 0;
@@ -165,6 +168,7 @@ static size_t encode_frame(enc_t *e, const uint8_t *base, uint32_t n, const uint
     uint32_t pos = 0;
     for (uint32_t b = 0; b < nblk; b++) {
         const uint32_t bend = (b + 1) * B2Z_BLOCK < n ? (b + 1) * B2Z_BLOCK : n;
+        if (b && b % sliceBlocks == 0) { chunk_close(&c, pos); c.needState = c.needProps = 1; }   /* a slice never depends on what the previous one emitted */
         uint32_t zr[3] = {0, 0, 0};                             /* zstd repcode history of the block (0 = unknown), to undo offBase */
         for (uint32_t i = 0; i < nseq[b]; i++) {
             const uint64_t s = seqs[(size_t)b * B2Z_MAXSEQ + i];
@@ -211,7 +215,7 @@ int64_t b2zo_lzma2_compress(void *dstv, size_t dstCap, const void *srcv, size_t 
         int fail = 0;
         for (size_t f = 0, f0 = 0; f0 < srcSize; f++, f0 += F) {
             const uint32_t n = (uint32_t)(srcSize - f0 < F ? srcSize - f0 : F);
-            const size_t sz = encode_frame(e, src + f0, n, seqs + f * bpf * B2Z_MAXSEQ, nseq + f * bpf, tmp);
+            const size_t sz = encode_frame(e, src + f0, n, seqs + f * bpf * B2Z_MAXSEQ, nseq + f * bpf, tmp, B2Z_LZ2_SLICE_BLOCKS(p->frameLog, p->flags));
             if (op + sz + 1 > dstCap) { fail = 1; break; }
             memcpy(dst + op, tmp, sz); op += sz;
         }

@@ -44,7 +44,7 @@ static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
     (void)level;
     p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
-    p->windowLog = B2Z_DEF_FRAMELOG; p->rowLog = B2Z_DEF_ROWLOG; p->flags = 1;
+    p->windowLog = B2Z_DEF_FRAMELOG; p->rowLog = B2Z_DEF_ROWLOG; p->flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);
 }
 
 size_t b2zo_zstd_compress_bound(size_t n, const b2zo_enc_params *p) {

@@ -46,6 +46,10 @@ def test_geometry_model_placement_and_batches(pkg, inputs):
             c = pkg.Codec(0, frame_log=fl, window_log=fl, lzma2_model=model)
             assert c.lzma2_compress(data) == want[fl], (fl, model)
             c.close()
+    for sl in (0, 1, 3):                                    # state-reset slices per block (default 2 is what every other test runs)
+        c = pkg.Codec(0, lzma2_slice_log=sl)
+        assert c.lzma2_compress(data) == helpers.oracle_lzma2_compress(data, flags=1 | (sl << 8)), sl
+        c.close()
     # device-pointer entry with several kernel batches: same bytes (every batch's end marker is overwritten by the next)
     import torch
     c = pkg.Codec(0, batch_log=22)

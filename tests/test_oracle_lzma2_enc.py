@@ -56,3 +56,19 @@ def test_incompressible_and_chunk_rollover(pkg):
     assert H.oracle_lzma2_decompress(comp, len(mixed), prop)[0] == mixed
     if H.ref_lzma_available():
         assert H.ref_lzma2_decompress(comp, len(mixed), prop)[0] == mixed
+
+
+def test_state_reset_slices(pkg):
+    """flags bits 8..10: a block's range coding split into state-reset slices (independent chains for the GPU): still one
+    dictionary-reset block per frame, every decoder restores the input, and the ratio cost stays small."""
+    data = pkg.corpus.g2(2 * (1 << 20) + 300_000).tobytes() + pkg.corpus.entropy_class(1, 200_000).tobytes()
+    sizes = []
+    for sl in range(4):
+        prop, comp = H.oracle_lzma2_compress(data, flags=1 | (sl << 8))
+        assert H.oracle_lzma2_decompress(comp, len(data), prop) == (data, len(comp))
+        assert lzma.LZMADecompressor(format=lzma.FORMAT_RAW, filters=[{"id": lzma.FILTER_LZMA2, "dict_size": _dict_size(prop)}]).decompress(comp) == data
+        if H.ref_lzma_available():
+            assert H.ref_lzma2_decompress(comp, len(data), prop) == (data, len(comp))
+            assert H.ref_lzma2_decompress_mt(comp, len(data), prop, 4) == (data, True)
+        sizes.append(len(comp))
+    assert sizes[0] <= sizes[1] <= sizes[2] <= sizes[3] < sizes[0] * 1.01
