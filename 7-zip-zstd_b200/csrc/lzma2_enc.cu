@@ -24,14 +24,19 @@ namespace b2z {
 
 struct RcE {
     uint64_t low; uint32_t range, cacheSize, cache;
-    uint8_t* out; uint32_t op;
+    uint8_t* out; uint32_t op;       // out: slot base; op: bytes written so far
 };
 
-__device__ __forceinline__ void rce_shift_low(RcE& e) {
+// Not inlined on purpose: it runs once per ~13 coded bits, and inlining it at the ~25 rce_bit sites (with its byte loop
+// unrolled) made the kernel 145 KB of SASS -- ncu showed 1.2 "no instruction" stall cycles per issue (i-cache misses).
+__device__ __noinline__ void rce_shift_low(RcE& e) {
     if ((uint32_t)e.low < 0xFF000000u || (uint32_t)(e.low >> 32) != 0u) {
         const uint32_t carry = (uint32_t)(e.low >> 32);
         uint32_t c = e.cache;
-        do { e.out[e.op++] = (uint8_t)(c + carry); c = 0xFFu; } while (--e.cacheSize != 0u);
+        uint8_t* o = e.out + e.op;
+        e.op += e.cacheSize;
+#pragma unroll 1
+        do { *o++ = (uint8_t)(c + carry); c = 0xFFu; } while (--e.cacheSize != 0u);
         e.cache = ((uint32_t)e.low >> 24) & 0xFFu;
     }
     e.cacheSize++;
@@ -85,7 +90,9 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
     const uint8_t* __restrict__ base = src + f0;
     const uint32_t nblkFrame = (n + B2Z_BLOCK - 1u) / B2Z_BLOCK;
     const uint32_t b0 = sl * sliceBlocks, b1 = (b0 + sliceBlocks) < nblkFrame ? (b0 + sliceBlocks) : nblkFrame;
-    uint16_t* const lit = GLIT ? litSpill + (size_t)chain * LITN : probs + P_LIT;
+    uint16_t* lit = GLIT ? litSpill + (size_t)chain * LITN : probs + P_LIT;
+    if (GLIT) asm volatile("" : "+l"(lit));                         // keep the base in registers: ptxas otherwise rebuilds it from the
+                                                                    // kernel parameters at every probability access (5 instructions per bit)
     constexpr uint32_t PBM = (1u << B2Z_LZ2_PB) - 1u, LPM = (1u << B2Z_LZ2_LP) - 1u;
 
     RcE e; e.low = 0; e.range = 0; e.cacheSize = 0; e.cache = 0; e.out = slots + (size_t)chain * slotStride; e.op = 0;
@@ -234,6 +241,8 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
     const uint32_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
     const size_t smemFull = ((size_t)P_LIT + LITN) * sizeof(uint16_t);
     const uint32_t slotsResident = (uint32_t)((227u * 1024u) / (smemFull + 1024)) * smCount;
+    // Measured (4 GiB, 16384 chains): literal model in global memory, 60 chains per SM: 903 ms; whole model in shared memory
+    // (9.6 KiB at lc = 2, 23 chains per SM): 1226 ms -- residency beats the ~6 extra instructions per literal bit.
     const bool glit = mode == 2 || (mode == 0 && litSpill && nChains > slotsResident);
     const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
     if (glit) {     // two chains per CTA: 32 CTAs/SM would cap residency at 32 chains; 3.6 KiB of model each -> ~60 per SM
