@@ -15,6 +15,7 @@
 // Replaces (reference, /root/reference/C/): LzmaEnc.c:691-760 (range coder), :795-860 (literals), :934-1010 (lengths),
 // :2388-2600 (packets), Lzma2Enc.c:129-238 (chunks), fast-lzma2/range_enc.c, lzma2_enc.c:1937-2099.
 // Oracle statement: oracle/lzma2_enc_oracle.c (byte-exact).
+#include <cstdlib>
 #include "b2z_device.cuh"
 #include "b2z_kernels.h"
 #include "b2z_lzma2.h"
@@ -44,8 +45,9 @@ __device__ __noinline__ void rce_shift_low(RcE& e) {
 }
 __device__ __forceinline__ void rce_bit(RcE& e, uint16_t* p, uint32_t bit) {
     const uint32_t v = *p, bound = (e.range >> 11) * v;
-    if (!bit) { e.range = bound; *p = (uint16_t)(v + ((2048u - v) >> 5)); }
-    else { e.low += bound; e.range -= bound; *p = (uint16_t)(v - (v >> 5)); }
+    // v += (2048 - v) >> 5  |  v -= v >> 5, as one expression: floor((31 - v) / 32) == -(v >> 5)
+    *p = (uint16_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5));
+    if (!bit) e.range = bound; else { e.low += bound; e.range -= bound; }
     if (e.range < (1u << 24)) { e.range <<= 8; rce_shift_low(e); }     // one step suffices: v >= 31, so range >= 2^13 * 31 before it
 }
 __device__ __forceinline__ void rce_direct(RcE& e, uint32_t v, uint32_t n) {
@@ -70,18 +72,25 @@ __device__ __forceinline__ void rce_len(RcE& e, uint16_t* l, uint32_t len, uint3
     else { rce_bit(e, l + L_CHOICE, 1); rce_bit(e, l + L_CHOICE2, 1); rce_tree(e, l + L_HIGH, 8, len - 16u); }
 }
 
-template <bool GLIT>
-__global__ void __launch_bounds__(64)
+// L: chains per warp (lanes 0, 32/L, 2*32/L ... each run one chain).  Only L = 1 is launched: measured on 4 GiB, L = 2/4/8
+// take 1566/1952/2007 ms against 836 ms -- the chains' control flow diverges at every coded bit, so the hardware
+// serialises them and the shared convergent code does not pay for it.
+template <bool GLIT, int L>
+// <= 64 registers: they are allocated for all 32 lanes of a chain's warp, so registers -- not shared memory -- bound the
+// chains per SM (32 at 64 registers)
+__global__ void __launch_bounds__(64, 16)
 lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint64_t* __restrict__ seqs,
                        const uint32_t* __restrict__ nseq, uint8_t* __restrict__ slots, uint32_t slotStride,
                        uint32_t* __restrict__ slotSize, uint16_t* __restrict__ litSpill, uint32_t* __restrict__ status, uint32_t nChains) {
     extern __shared__ uint16_t probsAll[];
-    if (threadIdx.x & 31u) return;                                  // one thread per chain; see the header comment
+    constexpr uint32_t LSTEP = 32u / (uint32_t)L;
+    if ((threadIdx.x & 31u) % LSTEP) return;                        // one thread per chain; see the header comment
     // chain = (frame, slice): a frame's range coding is split into state-reset slices of sliceBlocks 128 KiB blocks
-    const uint32_t chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t slotInCta = (threadIdx.x >> 5) * (uint32_t)L + (threadIdx.x & 31u) / LSTEP;
+    const uint32_t chain = blockIdx.x * (blockDim.x >> 5) * (uint32_t)L + slotInCta;
     if (chain >= nChains) return;
     constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
-    uint16_t* const probs = probsAll + (size_t)(threadIdx.x >> 5) * (GLIT ? P_LIT : P_LIT + LITN);
+    uint16_t* const probs = probsAll + (size_t)slotInCta * (GLIT ? P_LIT : P_LIT + LITN);
     const uint64_t F = 1ull << g.frameLog;
     const uint32_t bpf = (uint32_t)(F >> 17), sliceBlocks = B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags), spf = bpf / sliceBlocks;
     const uint32_t f = chain / spf, sl = chain - f * spf;
@@ -147,6 +156,7 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
         uint16_t* p = lit + 0x300u * (((pos & LPM) << B2Z_LZ2_LC) + (prev >> (8u - B2Z_LZ2_LC)));
         uint32_t m = 1, i = 8;
         if (state >= 7u) {                                          // matched literal: context follows the byte at rep0 while it agrees
+#pragma unroll 1
             while (i) {
                 --i;
                 const uint32_t b = (cur >> i) & 1u, mbit = (mb >> i) & 1u;
@@ -155,7 +165,11 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
                 if (mbit != b) break;
             }
         }
-        while (i) { --i; const uint32_t b = (cur >> i) & 1u; rce_bit(e, p + m, b); m = (m << 1) | b; }
+        // the tree walk keeps the 64-bit address p + m itself (p + 2m + b = (p + m) + m + b): one wide multiply-add per
+        // bit instead of rebuilding the address from the model base
+        uint16_t* pm = p + m;
+#pragma unroll 1
+        while (i) { --i; const uint32_t b = (cur >> i) & 1u; rce_bit(e, pm, b); pm += m + b; m = (m << 1) | b; }
         state = state < 4u ? 0u : (state < 10u ? state - 3u : state - 6u);
         prev = cur; cur = nxt; pos++;
     };
@@ -245,12 +259,12 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
     // (9.6 KiB at lc = 2, 23 chains per SM): 1226 ms -- residency beats the ~6 extra instructions per literal bit.
     const bool glit = mode == 2 || (mode == 0 && litSpill && nChains > slotsResident);
     const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
-    if (glit) {     // two chains per CTA: 32 CTAs/SM would cap residency at 32 chains; 3.6 KiB of model each -> ~60 per SM
-        lzma2_enc_range_kernel<true><<<(nChains + 1u) / 2u, 64, 2u * P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);
+    if (glit) {     // two warps (chains) per CTA: 32 CTAs/SM would otherwise cap residency below the register limit
+        lzma2_enc_range_kernel<true, 1><<<(nChains + 1u) / 2u, 64, 2u * P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);
     } else {
-        cudaError_t e = cudaFuncSetAttribute(lzma2_enc_range_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemFull);
+        cudaError_t e = cudaFuncSetAttribute(lzma2_enc_range_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemFull);
         if (e != cudaSuccess) return e;
-        lzma2_enc_range_kernel<false><<<nChains, 32, smemFull, st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, nullptr, status, nChains);
+        lzma2_enc_range_kernel<false, 1><<<nChains, 32, smemFull, st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, nullptr, status, nChains);
     }
     return cudaGetLastError();
 }
