@@ -60,6 +60,8 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.b200z_zstd_frame_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
     L.b200z_zstd_enc_stage_m.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+    L.b200z_zstd_compress_batch_bound.argtypes = [vp, sz, ctypes.c_uint32]; L.b200z_zstd_compress_batch_bound.restype = sz
+    L.b200z_zstd_compress_batch_host.argtypes = [vp, vp, vp, ctypes.c_uint32, vp, sz, vp]
     L.b200z_lzma2_compress_bound.argtypes = [vp, sz]; L.b200z_lzma2_compress_bound.restype = sz
     for name in ("b200z_lzma2_compress_device", "b200z_lzma2_compress_host"):
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint32)]
@@ -141,6 +143,16 @@ class Codec:
         sz = ctypes.c_size_t()
         self._check(self.L.b200z_zstd_compress_host(self.h, src.ctypes.data if n else None, n, out.ctypes.data, out.nbytes, ctypes.byref(sz)))
         return out[:sz.value].tobytes()
+
+    def compress_batch(self, files):
+        """files: list of bytes -> list of compressed bytes (one independent run of frames per file), one GPU call"""
+        import numpy as np
+        sizes = np.array([len(f) for f in files], dtype=np.uint64)
+        src = np.frombuffer(b"".join(files), dtype=np.uint8) if int(sizes.sum()) else np.zeros(1, dtype=np.uint8)
+        cap = self.L.b200z_zstd_compress_batch_bound(self.h, int(sizes.sum()), len(files))
+        out = np.empty(cap, dtype=np.uint8); offs = np.zeros(len(files) + 1, dtype=np.uint64)
+        self._check(self.L.b200z_zstd_compress_batch_host(self.h, src.ctypes.data, sizes.ctypes.data, len(files), out.ctypes.data, cap, offs.ctypes.data))
+        return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(files))], out[:int(offs[-1])].tobytes()
 
     def compress_into(self, src_ptr, n, dst_ptr, cap):
         sz = ctypes.c_size_t()

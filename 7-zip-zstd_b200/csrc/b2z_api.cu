@@ -5,6 +5,7 @@
 // Replaces the job/worker plumbing of C/zstd/zstdmt_compress.c (ZSTDMT_compressStream_generic
 // :1853, ZSTDMT_createCompressionJob :1403, ZSTDMT_flushProduced :1488): frames are the jobs,
 // warps are the workers, the assemble kernels are the ordered flush.
+#include <vector>
 #include "b2z_ctx.h"
 #include "b2z_lzma2.h"
 
@@ -50,7 +51,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
-                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready };
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -338,6 +339,74 @@ int b200z_zstd_enc_stage_m(b200z_ctx* ctx, const void* d_src, size_t srcSize, ui
         dense += nb;
     }
     CU(cudaMemcpy(lits, ctx->lits.p, srcSize, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------- many independent files in one call (BASELINE configs[4])
+size_t b200z_zstd_compress_batch_bound(b200z_ctx* ctx, size_t totalBytes, uint32_t nFiles) {
+    (void)ctx;
+    const size_t frames = (totalBytes >> 17) + nFiles + 1;
+    return totalBytes + frames * (3 + B2Z_FRAME_HDR_MAX + 12 + 4) + 64;
+}
+
+// src: the files back to back; sizes[i]: bytes of file i.  Every file becomes its own run of 128 KiB frames (first frame of
+// file i at dst + dstOffsets[i], dstOffsets[nFiles] = total), so any file can be decoded alone -- the per-file fan-out of a
+// non-solid 7z archive (7zUpdate.cpp / 7zEncode.cpp:325-332 run one Code() per file; here one call runs them all).
+int b200z_zstd_compress_batch_host(b200z_ctx* ctx, const void* src, const uint64_t* sizes, uint32_t nFiles,
+                                   void* dst, size_t dstCap, uint64_t* dstOffsets) {
+    if (!ctx || !sizes || !dstOffsets || !dst) return B200Z_E_PARAM;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nFiles; i++) total += sizes[i];
+    if (total && !src) return B200Z_E_PARAM;
+    if (dstCap < b200z_zstd_compress_batch_bound(ctx, (size_t)total, nFiles)) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_batch_bound%s");
+    CU(cudaSetDevice(ctx->device));
+    const EncGeom saved = ctx->geom;
+    struct Restore { b200z_ctx* c; EncGeom g; ~Restore() { c->geom = g; } } restore{ctx, saved};
+    ctx->geom.frameLog = 17; if (ctx->geom.windowLog > 17) ctx->geom.windowLog = 17;
+    const uint64_t F = 1ull << 17;
+    uint64_t capFrames = (1ull << ctx->batchLog) >> 17; if (capFrames < 1) capFrames = 1;
+    std::vector<uint64_t> off; std::vector<uint32_t> sz, firstFrame;
+    uint64_t outPos = 0, srcPos = 0;
+    uint32_t file = 0;
+    cudaStream_t st = ctx->stream;
+    while (file < nFiles) {
+        // group whole files into one batch of at most capFrames frames (a single larger file still goes alone)
+        off.clear(); sz.clear(); firstFrame.clear();
+        const uint32_t file0 = file; const uint64_t src0 = srcPos;
+        while (file < nFiles) {
+            const uint64_t fr = (sizes[file] + F - 1) / F;
+            if (!off.empty() && off.size() + fr > capFrames) break;
+            firstFrame.push_back((uint32_t)off.size());
+            for (uint64_t k = 0; k < fr; k++) { off.push_back(srcPos - src0 + k * F); sz.push_back((uint32_t)((sizes[file] - k * F) < F ? (sizes[file] - k * F) : F)); }
+            srcPos += sizes[file]; file++;
+        }
+        const uint64_t nFr = off.size(), inBytes = srcPos - src0;
+        if (nFr == 0) { for (uint32_t i = file0; i < file; i++) dstOffsets[i] = outPos; continue; }      // only empty files
+        const size_t bound = b200z_zstd_compress_bound(ctx, nFr * F);
+        if (ctx->dIn.reserve(inBytes + 64) || ctx->batchStage.reserve(nFr * F + 64) || ctx->batchOff.reserve(nFr * 8) || ctx->batchSize.reserve(nFr * 4) ||
+            ctx->dOut.reserve(bound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+        CU(cudaMemcpyAsync(ctx->dIn.p, (const uint8_t*)src + src0, inBytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->batchOff.p, off.data(), nFr * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->batchSize.p, sz.data(), nFr * 4, cudaMemcpyHostToDevice, st));
+        launch_zstd_enc_scatter((const uint8_t*)ctx->dIn.p, (const uint64_t*)ctx->batchOff.p, (const uint32_t*)ctx->batchSize.p, (uint32_t)nFr, 17,
+                                (uint8_t*)ctx->batchStage.p, st);
+        CU(cudaGetLastError());
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        ctx->geom.frameSizes = (const uint32_t*)ctx->batchSize.p;
+        uint64_t produced = 0;
+        int rc = enc_batch(ctx, (const uint8_t*)ctx->batchStage.p, nFr * F, (uint8_t*)ctx->dOut.p, &produced, false);
+        ctx->geom.frameSizes = nullptr;
+        if (rc) return rc;
+        if (outPos + produced > dstCap) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
+        std::vector<uint64_t> fo(nFr + 1);
+        CU(cudaMemcpyAsync(fo.data(), ctx->frameOff.p, (nFr + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync((uint8_t*)dst + outPos, ctx->dOut.p, produced, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->stat[B200Z_S_H2D_BYTES] += (double)inBytes; ctx->stat[B200Z_S_D2H_BYTES] += (double)produced;
+        for (uint32_t i = file0, k = 0; i < file; i++, k++) dstOffsets[i] = outPos + fo[firstFrame[k]];   // an empty file owns no frame: zero length
+        outPos += produced;
+    }
+    dstOffsets[nFiles] = outPos;
     return 0;
 }
 

@@ -10,7 +10,16 @@
 
 namespace b2z {
 
-struct EncGeom { uint32_t frameLog, hashLogL, hashLogS, windowLog, flags, rowLog; };
+struct EncGeom {
+    uint32_t frameLog, hashLogL, hashLogS, windowLog, flags, rowLog;
+    const uint32_t* frameSizes;      // null: frames are dense (all 2^frameLog bytes but the last).  Batch mode (frameLog 17, one block
+                                     // per frame): bytes of every frame, frames sit at multiples of 2^frameLog in the staging buffer
+};
+__host__ __device__ inline uint32_t enc_frame_bytes(const EncGeom& g, uint64_t srcSize, uint64_t f) {
+    if (g.frameSizes) return g.frameSizes[f];
+    const uint64_t F = 1ull << g.frameLog, f0 = f << g.frameLog;
+    return (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
+}
 
 // stage M: one warp per frame -> per-block final sequences + literal bytes
 void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,
@@ -27,5 +36,9 @@ void launch_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, const EncGeo
                               uint32_t nBlocks, uint64_t* blockOff /* [nBlocks+1] scratch */, uint8_t* dst,
                               uint64_t* outSize /* device scalar */, uint64_t* frameOff /* [nFrames+1] or null */,
                               uint32_t* cks /* [nFrames] scratch (flag bit1) */, cudaStream_t st);
+
+// batch mode: frame f = size[f] bytes at src + off[f]  ->  stage + (f << frameLog)   (one CTA per frame)
+void launch_zstd_enc_scatter(const uint8_t* src, const uint64_t* off, const uint32_t* size, uint32_t nFrames, uint32_t frameLog,
+                             uint8_t* stage, cudaStream_t st);
 
 }  // namespace b2z

@@ -395,12 +395,11 @@ zstd_enc_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGe
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     WarpWS* ws = &wsAll[wib];
     const uint32_t blocksPerFrame = 1u << (g.frameLog - 17u);
-    const uint64_t F = 1ull << g.frameLog;
     for (uint32_t blk = blockIdx.x * B2Z_ENT_WARPS + wib; blk < nBlocks; blk += gridDim.x * B2Z_ENT_WARPS) {
         // geometry of this block
         const uint64_t frame = blk / blocksPerFrame; const uint32_t bif = blk % blocksPerFrame;
         const uint64_t f0 = frame << g.frameLog;
-        const uint64_t fn = (srcSize - f0) < F ? (srcSize - f0) : F;
+        const uint64_t fn = enc_frame_bytes(g, srcSize, frame);
         const uint64_t b0 = (uint64_t)bif << 17;
         const uint32_t blkSize = (uint32_t)((fn - b0) < B2Z_BLOCK ? (fn - b0) : B2Z_BLOCK);
         const uint32_t last = (b0 + blkSize == fn) ? 1u : 0u;

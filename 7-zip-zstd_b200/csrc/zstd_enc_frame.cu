@@ -69,8 +69,8 @@ zstd_enc_offsets_kernel(uint64_t srcSize, EncGeom g, const uint32_t* __restrict_
 __global__ void zstd_enc_checksum_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cks, uint32_t nFrames) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFrames) return;
-    const uint64_t F = 1ull << g.frameLog, f0 = (uint64_t)f << g.frameLog;
-    const uint64_t fn = (srcSize - f0) < F ? (srcSize - f0) : F;
+    const uint64_t f0 = (uint64_t)f << g.frameLog;
+    const uint64_t fn = enc_frame_bytes(g, srcSize, f);
     cks[f] = (uint32_t)xxh64_device(src + f0, fn);
 }
 
@@ -107,9 +107,8 @@ zstd_enc_gather_kernel(uint64_t srcSize, EncGeom g, const uint8_t* __restrict__ 
     }
     // frame header by the first block's CTA
     if ((b % bpf) == 0 && tid == 0) {
-        const uint64_t f = b / bpf, F = 1ull << g.frameLog;
-        const uint64_t f0 = f << g.frameLog;
-        const uint64_t fn = (srcSize - f0) < F ? (srcSize - f0) : F;
+        const uint64_t f = b / bpf;
+        const uint64_t fn = enc_frame_bytes(g, srcSize, f);
         const uint32_t lastB = (uint32_t)(((f + 1) * bpf < nBlocks) ? (f + 1) * bpf : nBlocks);
         uint8_t* hp = d - 10;
         if (g.flags & 1u) {
@@ -124,6 +123,28 @@ zstd_enc_gather_kernel(uint64_t srcSize, EncGeom g, const uint8_t* __restrict__ 
         hp[5] = (uint8_t)((wl - 10u) << 3);
         hp[6] = (uint8_t)fn; hp[7] = (uint8_t)(fn >> 8); hp[8] = (uint8_t)(fn >> 16); hp[9] = (uint8_t)(fn >> 24);
     }
+}
+
+// Batch mode (many independent files, BASELINE configs[4]): files arrive back to back; every frame is copied to a
+// 2^frameLog-aligned slot of the staging buffer so that the frame kernels keep their aligned 8-byte loads.
+__global__ void __launch_bounds__(256)
+zstd_enc_scatter_kernel(const uint8_t* __restrict__ src, const uint64_t* __restrict__ off, const uint32_t* __restrict__ size,
+                        uint32_t frameLog, uint8_t* __restrict__ stage) {
+    const uint32_t f = blockIdx.x, n = size[f];
+    const uint8_t* s = src + off[f];
+    uint64_t* d = reinterpret_cast<uint64_t*>(stage + ((size_t)f << frameLog));
+    const uint64_t* sa = reinterpret_cast<const uint64_t*>((uintptr_t)s & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)((uintptr_t)s & 7u) * 8u;
+    const uint32_t nWords = (n + 7u) >> 3;
+    for (uint32_t i = threadIdx.x; i < nWords; i += 256u) {
+        const uint64_t a = sa[i], b = sh ? sa[i + 1] : 0ull;          // the source buffer carries 64 bytes of slack
+        d[i] = sh ? ((a >> sh) | (b << (64u - sh))) : a;
+    }
+}
+
+void launch_zstd_enc_scatter(const uint8_t* src, const uint64_t* off, const uint32_t* size, uint32_t nFrames, uint32_t frameLog,
+                             uint8_t* stage, cudaStream_t st) {
+    if (nFrames) zstd_enc_scatter_kernel<<<nFrames, 256, 0, st>>>(src, off, size, frameLog, stage);
 }
 
 void launch_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint8_t* slots, const uint32_t* slotSize,

@@ -145,7 +145,7 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
 
     for (uint64_t f = warpSlot; f < nFrames; f += nWarps) {
         const uint64_t f0 = f << g.frameLog;
-        const uint32_t n = (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
+        const uint32_t n = enc_frame_bytes(g, srcSize, f);
         const uint64_t* __restrict__ w = reinterpret_cast<const uint64_t*>(src + f0);
         const uint32_t nWords = (n + 7u) >> 3;
         // host-pointer path: the input is still being uploaded chunk by chunk while this kernel runs; a frame starts

@@ -85,6 +85,14 @@ int b200z_zstd_compress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize
 int b200z_zstd_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
                              void *dst, size_t dstCap, size_t *dstSize);
 
+/* Many independent files in one call (the per-file fan-out of a non-solid archive: 7zEncode.cpp:325-332 runs one Code() per
+ * file).  src: the files back to back, sizes[i] bytes each.  File i becomes its own run of 128 KiB frames at
+ * dst[dstOffsets[i] .. dstOffsets[i+1]) -- byte-identical to compressing it alone with FRAMELOG 17 -- and decodes alone;
+ * b200z_zstd_decompress_host on the whole output returns the files back to back.  An empty file yields zero bytes. */
+size_t b200z_zstd_compress_batch_bound(b200z_ctx *ctx, size_t totalBytes, uint32_t nFiles);
+int b200z_zstd_compress_batch_host(b200z_ctx *ctx, const void *src, const uint64_t *sizes, uint32_t nFiles,
+                                   void *dst, size_t dstCap, uint64_t *dstOffsets /* [nFiles + 1] */);
+
 /* Sum of the decompressed sizes of all frames in a host buffer (needs frame content sizes or
  * cheap block-header walks; returns B200Z_E_UNSUPPORTED if a frame's size is not declared). */
 int b200z_zstd_frame_info(const void *src, size_t srcSize, uint64_t *contentSize, uint32_t *nFrames);

@@ -98,3 +98,40 @@ def test_device_batches_are_invisible(pkg):
     comp = c.compress(data)
     assert comp == helpers.oracle_compress(data)
     c.close()
+
+
+def test_batch_of_files(codec, pkg):
+    """Many independent files in one call (BASELINE configs[4] shape: mixed-entropy files around 64 KiB): each file's bytes
+    equal compressing it alone with 128 KiB frames (oracle), the reference decoder restores each file on its own, and the
+    concatenated output decodes to the files back to back."""
+    import random
+    rng = random.Random(11)
+    g2 = pkg.corpus.g2(6 << 20).tobytes()
+    files = []
+    for i in range(150):
+        n = rng.choice([0, 1, 7, 1000, 65536, 65536, 65536, 70000, 131072, 131073, 300000, rng.randrange(1, 200000)])
+        kind = i % 4
+        if kind == 0:
+            o = rng.randrange(0, len(g2) - n - 1); f = g2[o:o + n]
+        elif kind == 1:
+            f = pkg.corpus.entropy_class(1 + (i % 3), n).tobytes() if n else b""
+        elif kind == 2:
+            f = bytes(n)
+        else:
+            f = (b"abcdefgh" * (n // 8 + 1))[:n]
+        files.append(f)
+    parts, whole = codec.compress_batch(files)
+    assert b"".join(parts) == whole
+    for i, (f, c) in enumerate(zip(files, parts)):
+        if not f:
+            assert c == b""
+            continue
+        assert c == helpers.oracle_compress(f, frameLog=17, windowLog=17, flags=1), i
+        if i % 7 == 0 and helpers.ref_available():
+            assert helpers.ref_decompress(c, len(f)) == f
+    assert codec.decompress(whole, max_size=sum(map(len, files))) == b"".join(files)
+    # several kernel batches (batch_log 22 = 32 frames per batch): same bytes
+    c2 = pkg.Codec(0, batch_log=22)
+    parts2, whole2 = c2.compress_batch(files)
+    assert whole2 == whole and parts2 == parts
+    c2.close()
