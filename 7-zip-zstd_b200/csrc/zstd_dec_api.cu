@@ -106,7 +106,7 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64) ||
         ctx->decScratch[5].reserve(zstd_dec_entropy_scratch_bytes(hc.nBlocks)))
         return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (input too large for one pass)%s");
-    launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, ctx->decScratch[5].p, st, ctx->stream2, ctx->ev[4], ctx->ev[5]);
+    launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, ctx->decScratch[5].p, st, st, ctx->ev[4], ctx->ev[5]);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
     launch_zstd_dec_layout(frames, hc.nFrames, blocks, dstCap, counts, total, st);
