@@ -24,10 +24,11 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     shard = pkg.corpus.g2(UNIT, offset=rank * UNIT, threads=2)
     comp = helpers.oracle_compress(shard.tobytes())            # stands in for the rank's GPU (bytes are identical by test_gpu_*)
+    lz = helpers.oracle_lzma2_compress(shard.tobytes())[1]     # method 21: the rank's chunk stream (ends with its own 0x00)
     t = torch.tensor([0.25 + rank, float(len(comp))], dtype=torch.float64)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    q.put((rank, hashlib.sha256(shard.tobytes()).hexdigest(), comp, float(tmax[0]), float(tsum[1])))
+    q.put((rank, hashlib.sha256(shard.tobytes()).hexdigest(), comp, float(tmax[0]), float(tsum[1]), lz))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -44,10 +45,14 @@ def test_two_rank_sharding(pkg):
         p.join(timeout=60)
         assert p.exitcode == 0
     whole = pkg.corpus.g2(world * UNIT).tobytes()
-    for r, sha, comp, tmax, tsum in res:
+    for r, sha, comp, tmax, tsum, _lz in res:
         assert sha == hashlib.sha256(whole[r * UNIT:(r + 1) * UNIT]).hexdigest()      # shards tile the stream
         assert tmax == 0.25 + (world - 1)                                              # max over ranks
         assert tsum == sum(len(x[2]) for x in res)
     joined = b"".join(x[2] for x in res)
     assert joined == helpers.oracle_compress(whole)                                    # invariant to the rank count
     assert helpers.oracle_decompress(joined, len(whole)) == whole
+    # method 21: shards are runs of dictionary-reset blocks; dropping every rank's end marker but the last gives the one-process stream
+    lzj = b"".join(x[5][:-1] for x in res) + b"\x00"
+    prop, want = helpers.oracle_lzma2_compress(whole)
+    assert lzj == want and helpers.oracle_lzma2_decompress(lzj, len(whole), prop)[0] == whole
