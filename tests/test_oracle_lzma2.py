@@ -63,3 +63,32 @@ def test_stream_info_host_walk():
         assert nb.value == (4 if name == "lzma2_lzma2_tile_blocks.bin" else (0 if meta["size"] == 0 else 1)), (name, nb.value)
         if len(comp) > 10:
             assert lib.b200z_lzma2_stream_info(buf, len(comp) // 2, ctypes.byref(cs), ctypes.byref(nb), ctypes.byref(used)) == -5
+
+
+@pytest.mark.skipif(not H.ref_lzma_available(), reason="oracle/_ref/libref_lzma.so not built")
+def test_corruption_parity_with_reference():
+    """Bit flips and truncations: the oracle accepts exactly what the reference decoder (C/Lzma2Dec.c: Lzma2Decode) accepts,
+    with the same bytes and the same consumed count -- the error behaviour the GPU decoder is then tested against."""
+    import random
+    rng = random.Random(3)
+    accepted = 0
+    for name, meta in IDX.items():
+        comp = open(os.path.join(GOLD, name), "rb").read()
+        if len(comp) < 50:
+            continue
+        for _ in range(60):
+            bad = bytearray(comp); k = rng.randrange(len(comp)); bad[k] ^= 1 << rng.randrange(8)
+            if rng.random() < 0.2:
+                bad = bad[:rng.randrange(1, len(bad))]
+            bad = bytes(bad)
+            try:
+                o = H.oracle_lzma2_decompress(bad, meta["size"], meta["dict_prop"])
+            except ValueError:
+                o = None
+            try:
+                r = H.ref_lzma2_decompress(bad, meta["size"], meta["dict_prop"])
+            except ValueError:
+                r = None
+            assert o == r, (name, k)
+            accepted += o is not None
+    assert accepted > 10          # some corruptions are harmless (bytes after the end marker, FL2's trailing hash)
