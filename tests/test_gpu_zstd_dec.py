@@ -137,3 +137,12 @@ def test_content_checksums(pkg, inputs):
             c.decompress(bytes(bad), max_size=len(a) + len(b))
         assert e.value.code == -8
     c.close()
+
+
+def test_reference_regression_archives(codec):
+    """Packed streams of the reference's own regression archives (tests/regr-arc/*.7z): both methods, solid folders, ZSTD:max."""
+    idx = json.load(open(os.path.join(GOLDEN, "regr.json")))
+    for name, meta in idx.items():
+        comp = open(os.path.join(GOLDEN, name), "rb").read()
+        out = codec.decompress(comp, max_size=meta["size"]) if meta["method"] == "zstd" else codec.lzma2_decompress(comp, meta["dict_prop"])
+        assert len(out) == meta["size"] and hashlib.sha256(out).hexdigest() == meta["sha256"], name

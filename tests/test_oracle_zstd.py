@@ -92,3 +92,21 @@ def test_encoder_ratio_vs_reference(pkg):
     d = pkg.corpus.g2(8 << 20).tobytes()
     ours = len(helpers.oracle_compress(d)); ref = len(helpers.ref_compress(d, 3))
     assert ours <= ref * 1.01, (ours, ref)
+
+
+def test_reference_regression_archives():
+    """Packed streams of the reference's own regression archives (tests/regr-arc/*.7z -> tests/golden/regr_*, see
+    make_golden_regr.py): level 17, ZSTD:max and solid folders; payload SHA-256 as regression.test expects."""
+    import hashlib, json
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    idx = json.load(open(os.path.join(gold, "regr.json")))
+    seen = 0
+    for name, meta in idx.items():
+        comp = open(os.path.join(gold, name), "rb").read()
+        if meta["method"] == "zstd":
+            out = helpers.oracle_decompress(comp, meta["size"])
+        else:
+            out, used = helpers.oracle_lzma2_decompress(comp, meta["size"], meta["dict_prop"]); assert used == len(comp)
+        assert len(out) == meta["size"] and hashlib.sha256(out).hexdigest() == meta["sha256"], name
+        seen += 1
+    assert seen == 4
