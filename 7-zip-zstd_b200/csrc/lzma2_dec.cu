@@ -58,8 +58,11 @@ __device__ __forceinline__ uint32_t rc_bit(Rc& r, uint16_t* p) {
     rc_norm(r);
     const uint32_t v = *p;
     const uint32_t bound = (r.range >> 11) * v;
-    if (r.code < bound) { r.range = bound; *p = (uint16_t)(v + ((2048u - v) >> 5)); return 0u; }
-    r.range -= bound; r.code -= bound; *p = (uint16_t)(v - (v >> 5)); return 1u;
+    const uint32_t bit = r.code >= bound ? 1u : 0u;
+    // v += (2048 - v) >> 5  |  v -= v >> 5 as one expression: floor((31 - v) / 32) == -(v >> 5)
+    *p = (uint16_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5));
+    if (bit) { r.range -= bound; r.code -= bound; } else r.range = bound;
+    return bit;
 }
 __device__ __forceinline__ uint32_t rc_direct(Rc& r, uint32_t n) {
     uint32_t x = 0;
@@ -170,7 +173,8 @@ lzma2_decode_kernel(const uint8_t* __restrict__ src, const Lz2Block* __restrict_
                             if (mbit != bit) break;
                         } while (sym < 0x100u);
                     }
-                    while (sym < 0x100u) sym = (sym << 1) | rc_bit(rc, p + sym);
+                    // the tree walk carries the address p + sym itself: p + 2 sym + b = (p + sym) + sym + b
+                    for (uint16_t* pm = p + sym; sym < 0x100u;) { const uint32_t b_ = rc_bit(rc, pm); pm += sym + b_; sym = (sym << 1) | b_; }
                     prev = sym & 0xFFu; mbValid = false;
                     out[pos++] = (uint8_t)prev;
                     state = state < 4 ? 0 : (state < 10 ? state - 3 : state - 6);

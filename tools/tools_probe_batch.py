@@ -1,4 +1,6 @@
 """GPU probe: cfg5 shape -- 100k files of 64 KiB, mixed entropy, one batch call"""
+import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
 import sys, time
 import numpy as np
 import __graft_entry__ as ge

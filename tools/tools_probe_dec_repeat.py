@@ -1,4 +1,6 @@
 """GPU probe: is the zstd decode stage time stable across repeated calls / alternation with encode?"""
+import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
 import sys, torch
 import __graft_entry__ as ge
 pkg = ge.load_package()

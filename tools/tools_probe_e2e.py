@@ -1,4 +1,6 @@
 """Experiment driver: host-pointer (e2e) timings and raw PCIe copy bandwidth."""
+import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch

@@ -1,4 +1,6 @@
 """GPU probe: LZMA2 decode throughput vs. number of independent blocks (streams made by the reference encoder)."""
+import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
 import ctypes, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))

@@ -1,4 +1,6 @@
 """GPU probe: LZMA2 encode (stage M + stage R) and decode of our own streams, device-resident."""
+import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))

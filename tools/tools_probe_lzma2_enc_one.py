@@ -1,5 +1,7 @@
 """one LZMA2 encode (stage M + stage R) for ncu"""
 import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
+import os, sys
 import __graft_entry__ as ge
 import torch
 pkg = ge.load_package(); c = pkg.Codec(0)

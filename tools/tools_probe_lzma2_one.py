@@ -1,5 +1,7 @@
 """one LZMA2 decode launch for ncu (stream made by the reference encoder)"""
 import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
+import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
 import helpers as H
 import __graft_entry__ as ge

@@ -1,5 +1,7 @@
 """Profiling driver: one compress of N MiB of G2 text, device resident (used under ncu)."""
 import os, sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0] = [_ROOT, os.path.join(_ROOT, "tests")]
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import __graft_entry__ as ge
