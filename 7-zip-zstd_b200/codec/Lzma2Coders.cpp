@@ -94,12 +94,18 @@ public:
 };
 
 class CLzma2Decoder final : public ICompressCoder, public ICompressSetDecoderProperties2, public ICompressSetFinishMode,
-                            public ICompressGetInStreamProcessedSize, public ICompressSetCoderMt, CoderBase {
+                            public ICompressGetInStreamProcessedSize, public ICompressSetCoderMt, public ICompressSetBufSize,
+                            public ICompressSetMemLimit, public ICompressSetOutStreamSize, public ICompressSetInStream,
+                            public ISequentialInStream, CoderBase {
     std::atomic<UInt32> refs_{0};
     Byte prop_ = 40; bool finishMode_ = false; UInt64 inProcessed_ = 0;
     std::vector<Byte> in_;
     PinnedBuf out_;
+    // pull mode (Lzma2Decoder.cpp:196-265): SetInStream + SetOutStreamSize, then Read() until it returns 0 bytes
+    ISequentialInStream* pullIn_ = nullptr; bool pullDone_ = false; size_t pullSize_ = 0, pullPos_ = 0;
+    bool haveOutSize_ = false; UInt64 outSize_ = 0;
 public:
+    ~CLzma2Decoder() { if (pullIn_) pullIn_->Release(); }
     UInt64 processedIn = 0, processedOut = 0;
     HRESULT QueryInterface(const GUID& iid, void** out) override {
         *out = nullptr;
@@ -108,11 +114,39 @@ public:
         else if (iid == b2z_iid(4, kIID_SetFinishMode)) *out = static_cast<ICompressSetFinishMode*>(this);
         else if (iid == b2z_iid(4, kIID_GetInProcessed)) *out = static_cast<ICompressGetInStreamProcessedSize*>(this);
         else if (iid == b2z_iid(4, kIID_SetMt)) *out = static_cast<ICompressSetCoderMt*>(this);
+        else if (iid == b2z_iid(4, kIID_SetBufSize)) *out = static_cast<ICompressSetBufSize*>(this);
+        else if (iid == b2z_iid(4, kIID_SetMemLimit)) *out = static_cast<ICompressSetMemLimit*>(this);
+        else if (iid == b2z_iid(4, kIID_SetOutStreamSize)) *out = static_cast<ICompressSetOutStreamSize*>(this);
+        else if (iid == b2z_iid(4, kIID_SetInStream)) *out = static_cast<ICompressSetInStream*>(this);
+        else if (iid == b2z_iid(3, kIID_SeqIn)) *out = static_cast<ISequentialInStream*>(this);
         else return E_NOINTERFACE;
         ++refs_; return S_OK;
     }
     UInt32 AddRef() override { return ++refs_; }
     UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
+    HRESULT SetInBufSize(UInt32, UInt32) override { return S_OK; }              // Lzma2Decoder.cpp:58-59: staging is sized by the stream here
+    HRESULT SetOutBufSize(UInt32, UInt32) override { return S_OK; }
+    HRESULT SetMemLimit(UInt64) override { return S_OK; }                       // limits the reference's MT block buffers; no equivalent
+    HRESULT SetOutStreamSize(const UInt64* outSize) override {                  // Lzma2Decoder.cpp:208-243
+        haveOutSize_ = outSize != nullptr; outSize_ = outSize ? *outSize : 0;
+        pullDone_ = false; pullSize_ = pullPos_ = 0; processedIn = processedOut = 0; inProcessed_ = 0;
+        return S_OK;
+    }
+    HRESULT SetInStream(ISequentialInStream* in) override { if (in) in->AddRef(); if (pullIn_) pullIn_->Release(); pullIn_ = in; return S_OK; }
+    HRESULT ReleaseInStream() override { if (pullIn_) pullIn_->Release(); pullIn_ = nullptr; return S_OK; }
+    HRESULT Read(void* data, UInt32 size, UInt32* processed) override {
+        if (processed) *processed = 0;
+        if (!pullIn_) return E_FAIL;
+        if (!pullDone_) {                                                       // the GPU decodes a folder's blocks together: all on the first Read
+            HRESULT hr = decode_all(pullIn_, haveOutSize_ ? &outSize_ : nullptr, &pullSize_);
+            if (hr != S_OK) return hr;
+            pullDone_ = true; pullPos_ = 0;
+        }
+        size_t n = pullSize_ - pullPos_; if (n > size) n = size;
+        memcpy(data, (const Byte*)out_.p + pullPos_, n); pullPos_ += n;
+        if (processed) *processed = (UInt32)n;
+        return S_OK;
+    }
     HRESULT SetDecoderProperties2(const Byte* p, UInt32 size) override {       // Lzma2Decoder.cpp:40-48
         if (size != 1 || p[0] > 40) return E_NOTIMPL;
         prop_ = p[0]; return S_OK;
@@ -121,11 +155,12 @@ public:
     HRESULT GetInStreamProcessedSize(UInt64* v) override { *v = inProcessed_; return S_OK; }
     HRESULT SetNumberOfThreads(UInt32) override { return S_OK; }                // parallelism = blocks in the stream
 
-    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
-        processedIn = processedOut = 0; inProcessed_ = 0;
+    // reads the packed stream to its end, decodes it on the GPU into out_; *toWrite = bytes the caller gets (bounded by outSize)
+    HRESULT decode_all(ISequentialInStream* inS, const UInt64* outSize, size_t* toWrite) {
+        *toWrite = 0;
         HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
         in_.clear();
-        for (;;) {                                             // the blocks of one folder are decoded together: read the packed stream to its end
+        for (;;) {
             const size_t chunk = (size_t)8 << 20, at = in_.size();
             in_.resize(at + chunk);
             size_t got = chunk;
@@ -142,14 +177,23 @@ public:
         rc = b200z_lzma2_decompress_host(ctx, in_.data(), used, prop_, out_.p, (size_t)content, &produced);
         if (rc) return hr_from_b200z(rc);
         inProcessed_ = processedIn = used;
-        size_t toWrite = produced;
-        if (outSize && *outSize < toWrite) toWrite = (size_t)*outSize;          // the folder's unpack size bounds the output
-        processedOut = toWrite;
-        hr = write_stream(outS, out_.p, toWrite);
+        *toWrite = produced;
+        if (outSize && *outSize < *toWrite) *toWrite = (size_t)*outSize;        // the folder's unpack size bounds the output
+        processedOut = *toWrite;
+        if (finishMode_ && outSize && *outSize != produced) return S_FALSE;     // Lzma2Decoder.cpp:177-183: the stream must end exactly there
+        return S_OK;
+    }
+
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
+        processedIn = processedOut = 0; inProcessed_ = 0;
+        size_t toWrite = 0;
+        HRESULT dec = decode_all(inS, outSize, &toWrite);
+        if (dec != S_OK && dec != S_FALSE) return dec;
+        if (dec == S_FALSE && toWrite == 0) return S_FALSE;
+        HRESULT hr = write_stream(outS, out_.p, toWrite);
         if (hr != S_OK) return hr;
         if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
-        if (finishMode_ && outSize && *outSize != produced) return S_FALSE;     // Lzma2Decoder.cpp:177-183: stream must end exactly there
-        return S_OK;
+        return dec;
     }
 };
 

@@ -116,31 +116,59 @@ public:
 };
 
 // ------------------------------------------------------------------ decoder
-class CDecoder final : public ICompressCoder, public ICompressSetDecoderProperties2, public ICompressSetCoderMt, CoderBase {
+class CDecoder final : public ICompressCoder, public ICompressSetDecoderProperties2, public ICompressSetCoderMt,
+                       public ICompressSetOutStreamSize, public ICompressSetInStream, public ISequentialInStream, CoderBase {
     std::atomic<UInt32> refs_{0};
     std::vector<Byte> in_;
     PinnedBuf out_;
+    // pull mode (ZstdDecoder.cpp:182-258): SetInStream + SetOutStreamSize, then Read() until it returns 0 bytes
+    ISequentialInStream* pullIn_ = nullptr; bool pullDone_ = false; size_t pullSize_ = 0, pullPos_ = 0;
+    bool haveOutSize_ = false; UInt64 outSize_ = 0;
 public:
+    ~CDecoder() { if (pullIn_) pullIn_->Release(); }
     UInt64 processedIn = 0, processedOut = 0;
     HRESULT QueryInterface(const GUID& iid, void** out) override {
         *out = nullptr;
         if (iid == kIID_IUnknown || iid == b2z_iid(4, kIID_Coder)) *out = static_cast<ICompressCoder*>(this);
         else if (iid == b2z_iid(4, kIID_SetDecProps2)) *out = static_cast<ICompressSetDecoderProperties2*>(this);
         else if (iid == b2z_iid(4, kIID_SetMt)) *out = static_cast<ICompressSetCoderMt*>(this);
+        else if (iid == b2z_iid(4, kIID_SetOutStreamSize)) *out = static_cast<ICompressSetOutStreamSize*>(this);
+        else if (iid == b2z_iid(4, kIID_SetInStream)) *out = static_cast<ICompressSetInStream*>(this);
+        else if (iid == b2z_iid(3, kIID_SeqIn)) *out = static_cast<ISequentialInStream*>(this);
         else return E_NOINTERFACE;
         ++refs_; return S_OK;
     }
     UInt32 AddRef() override { return ++refs_; }
     UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
+    HRESULT SetOutStreamSize(const UInt64* outSize) override {           // ZstdDecoder.cpp:57-64: (re)initialises the stream state
+        haveOutSize_ = outSize != nullptr; outSize_ = outSize ? *outSize : 0;
+        pullDone_ = false; pullSize_ = pullPos_ = 0; processedIn = processedOut = 0;
+        return S_OK;
+    }
+    HRESULT SetInStream(ISequentialInStream* in) override { if (in) in->AddRef(); if (pullIn_) pullIn_->Release(); pullIn_ = in; return S_OK; }
+    HRESULT ReleaseInStream() override { if (pullIn_) pullIn_->Release(); pullIn_ = nullptr; return S_OK; }
+    HRESULT Read(void* data, UInt32 size, UInt32* processed) override {
+        if (processed) *processed = 0;
+        if (!pullIn_) return E_FAIL;
+        if (!pullDone_) {                                                // the GPU decodes a folder's frames together: all on the first Read
+            HRESULT hr = decode_all(pullIn_, haveOutSize_ ? &outSize_ : nullptr, &pullSize_);
+            if (hr != S_OK) return hr;
+            pullDone_ = true; pullPos_ = 0;
+        }
+        size_t n = pullSize_ - pullPos_; if (n > size) n = size;
+        memcpy(data, (const Byte*)out_.p + pullPos_, n); pullPos_ += n;
+        if (processed) *processed = (UInt32)n;
+        return S_OK;
+    }
     HRESULT SetDecoderProperties2(const Byte*, UInt32 size) override {   // ZstdDecoder.cpp:32-49: 1/3/5 bytes, content ignored
         return (size == 1 || size == 3 || size == 5) ? S_OK : E_NOTIMPL;
     }
     HRESULT SetNumberOfThreads(UInt32) override { return S_OK; }         // no-op, as in ZstdDecoder.cpp:260-263
 
-    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
-        processedIn = processedOut = 0;
+    // reads the packed stream to its end, decodes it on the GPU into out_; *produced = decoded bytes
+    HRESULT decode_all(ISequentialInStream* inS, const UInt64* outSize, size_t* produced) {
+        *produced = 0;
         HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
-        // the frames of one Code() input are decoded together: read the packed stream to its end
         in_.clear();
         for (;;) {
             const size_t chunk = (size_t)8 << 20, at = in_.size();
@@ -151,6 +179,7 @@ public:
             if (hr != S_OK) return hr;
             if (got < chunk) break;
         }
+        processedIn = in_.size();
         if (in_.empty()) return S_OK;
         uint64_t content = 0; uint32_t frames = 0;
         int rc = b200z_zstd_frame_info(in_.data(), in_.size(), &content, &frames);
@@ -161,15 +190,22 @@ public:
         else cap = in_.size() * 64 + ((size_t)1 << 20);                  // undeclared size: generous bound, grown on demand
         for (;;) {
             if (!out_.reserve(cap + 64)) return E_OUTOFMEMORY;
-            size_t produced = 0;
-            rc = b200z_zstd_decompress_host(ctx, in_.data(), in_.size(), out_.p, cap, &produced);
+            rc = b200z_zstd_decompress_host(ctx, in_.data(), in_.size(), out_.p, cap, produced);
             if (rc == B200Z_E_DSTSIZE && !(outSize || content)) { cap *= 4; continue; }
             if (rc) return hr_from_b200z(rc);
-            processedIn = in_.size(); processedOut = produced;
-            hr = write_stream(outS, out_.p, produced);
-            if (hr != S_OK) return hr;
             break;
         }
+        processedOut = *produced;
+        return S_OK;
+    }
+
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
+        processedIn = processedOut = 0;
+        size_t produced = 0;
+        HRESULT hr = decode_all(inS, outSize, &produced);                // the frames of one Code() input are decoded together
+        if (hr != S_OK) return hr;
+        hr = write_stream(outS, out_.p, produced);
+        if (hr != S_OK) return hr;
         if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
         return S_OK;
     }

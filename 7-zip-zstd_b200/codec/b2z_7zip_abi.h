@@ -72,11 +72,16 @@ struct ICompressSetDecoderProperties2 : IUnknown { virtual HRESULT SetDecoderPro
 struct ICompressWriteCoderProperties : IUnknown { virtual HRESULT WriteCoderProperties(ISequentialOutStream* out) = 0; };
 struct ICompressSetCoderMt : IUnknown { virtual HRESULT SetNumberOfThreads(UInt32 n) = 0; };
 struct ICompressGetInStreamProcessedSize : IUnknown { virtual HRESULT GetInStreamProcessedSize(UInt64* value) = 0; };   // ICoder.h:202-204
+struct ICompressSetMemLimit : IUnknown { virtual HRESULT SetMemLimit(UInt64 memUsage) = 0; };                             // ICoder.h:221-223
+struct ICompressSetInStream : IUnknown { virtual HRESULT SetInStream(ISequentialInStream* in) = 0; virtual HRESULT ReleaseInStream() = 0; };   // :257-260
+struct ICompressSetOutStreamSize : IUnknown { virtual HRESULT SetOutStreamSize(const UInt64* outSize) = 0; };            // :273-275
+struct ICompressSetBufSize : IUnknown { virtual HRESULT SetInBufSize(UInt32 streamIndex, UInt32 size) = 0; virtual HRESULT SetOutBufSize(UInt32 streamIndex, UInt32 size) = 0; };   // :281-285
 struct ICompressSetFinishMode : IUnknown { virtual HRESULT SetFinishMode(UInt32 finishMode) = 0; };                      // ICoder.h:210-216
 
 enum { kIID_SeqIn = 0x01, kIID_SeqOut = 0x02 };                                          // group 3
 enum { kIID_Progress = 0x04, kIID_Coder = 0x05, kIID_SetPropsOpt = 0x1F, kIID_SetProps = 0x20,
-       kIID_SetDecProps2 = 0x22, kIID_WriteProps = 0x23, kIID_GetInProcessed = 0x24, kIID_SetMt = 0x25, kIID_SetFinishMode = 0x26 };             // group 4
+       kIID_SetDecProps2 = 0x22, kIID_WriteProps = 0x23, kIID_GetInProcessed = 0x24, kIID_SetMt = 0x25, kIID_SetFinishMode = 0x26, kIID_SetMemLimit = 0x28,
+       kIID_SetInStream = 0x31, kIID_SetOutStreamSize = 0x34, kIID_SetBufSize = 0x35 };             // group 4
 static const GUID kIID_IUnknown = { 0, 0, 0, { 0xC0, 0, 0, 0, 0, 0, 0, 0x46 } };
 
 // 7zip/ICoder.h:104-160 (NCoderPropID)

@@ -38,6 +38,27 @@ struct Progress final : ICompressProgressInfo {
     HRESULT SetRatioInfo(const UInt64*, const UInt64*) override { calls++; return S_OK; }
 };
 
+// pull mode, as archive handlers that read from a coder do (ICompressSetInStream + ICompressSetOutStreamSize + ISequentialInStream::Read)
+static int pull_decode(ICompressCoder* dec, const std::vector<Byte>& packed, UInt64 outSize, std::vector<Byte>& out) {
+    ICompressSetInStream* si = nullptr; ICompressSetOutStreamSize* so = nullptr; ISequentialInStream* rd = nullptr;
+    if (dec->QueryInterface(b2z_iid(4, kIID_SetInStream), (void**)&si) != S_OK) return 1;
+    if (dec->QueryInterface(b2z_iid(4, kIID_SetOutStreamSize), (void**)&so) != S_OK) return 2;
+    if (dec->QueryInterface(b2z_iid(3, kIID_SeqIn), (void**)&rd) != S_OK) return 3;
+    MemIn in(packed);
+    if (si->SetInStream(&in) != S_OK || so->SetOutStreamSize(&outSize) != S_OK) return 4;
+    out.clear();
+    std::vector<Byte> buf(1 << 20);
+    for (;;) {
+        UInt32 got = 0;
+        if (rd->Read(buf.data(), (UInt32)buf.size() - 12345u, &got) != S_OK) return 5;
+        if (!got) break;
+        out.insert(out.end(), buf.begin(), buf.begin() + got);
+    }
+    if (si->ReleaseInStream() != S_OK) return 6;
+    si->Release(); so->Release(); rd->Release();
+    return 0;
+}
+
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
 int main(int argc, char** argv) {
@@ -83,6 +104,13 @@ int main(int argc, char** argv) {
         ICompressCoder* ld = (ICompressCoder*)o; ICompressSetDecoderProperties2* lp = nullptr; ICompressSetFinishMode* lf = nullptr; ICompressGetInStreamProcessedSize* lg = nullptr;
         CHECK(ld->QueryInterface(b2z_iid(4, kIID_SetDecProps2), (void**)&lp) == S_OK && ld->QueryInterface(b2z_iid(4, kIID_SetFinishMode), (void**)&lf) == S_OK);
         CHECK(ld->QueryInterface(b2z_iid(4, kIID_GetInProcessed), (void**)&lg) == S_OK);
+        { ICompressSetBufSize* bs = nullptr; ICompressSetMemLimit* ml = nullptr; ICompressSetInStream* si = nullptr; ICompressSetOutStreamSize* so = nullptr; ISequentialInStream* rd = nullptr;
+          CHECK(ld->QueryInterface(b2z_iid(4, kIID_SetBufSize), (void**)&bs) == S_OK && bs->SetInBufSize(0, 1 << 20) == S_OK && bs->SetOutBufSize(0, 1 << 22) == S_OK);
+          CHECK(ld->QueryInterface(b2z_iid(4, kIID_SetMemLimit), (void**)&ml) == S_OK && ml->SetMemLimit((UInt64)1 << 30) == S_OK);
+          CHECK(ld->QueryInterface(b2z_iid(4, kIID_SetInStream), (void**)&si) == S_OK && ld->QueryInterface(b2z_iid(4, kIID_SetOutStreamSize), (void**)&so) == S_OK);
+          CHECK(ld->QueryInterface(b2z_iid(3, kIID_SeqIn), (void**)&rd) == S_OK);
+          UInt32 got = 7; Byte tmp[4]; CHECK(rd->Read(tmp, 4, &got) == E_FAIL && got == 0);              // no input stream set
+          bs->Release(); ml->Release(); si->Release(); so->Release(); rd->Release(); }
         const Byte ok1[1] = { 24 }, bad1[1] = { 41 };
         CHECK(lp->SetDecoderProperties2(ok1, 1) == S_OK && lp->SetDecoderProperties2(bad1, 1) == E_NOTIMPL && lp->SetDecoderProperties2(ok1, 5) == E_NOTIMPL);
         lp->Release(); lf->Release(); lg->Release(); CHECK(ld->Release() == 0);
@@ -113,6 +141,7 @@ int main(int argc, char** argv) {
         if (r != S_OK) { fprintf(stderr, "lzma2 decoder Code() = 0x%08x\n", (unsigned)r); return 1; }
         CHECK(back.d == input);
         UInt64 inProc = 0; CHECK(gp->GetInStreamProcessedSize(&inProc) == S_OK && inProc == packed.d.size());
+        { std::vector<Byte> pulled; int pr = pull_decode(d, packed.d, outSize, pulled); if (pr) { fprintf(stderr, "lzma2 pull mode failed at step %d\n", pr); return 1; } CHECK(pulled == input); }
         { std::vector<Byte> bad(packed.d.begin(), packed.d.begin() + packed.d.size() / 2); MemIn bi(bad); MemOut bo; CHECK(d->Code(&bi, &bo, nullptr, &outSize, nullptr) == S_FALSE); }
         { UInt64 wrong = input.size() + 1; MemIn p2(packed.d); MemOut b2; CHECK(d->Code(&p2, &b2, nullptr, &wrong, nullptr) == S_FALSE); }   // finish mode: sizes must agree
         { FILE* f = fopen(argv[3], "wb"); CHECK(f); fwrite(packed.d.data(), 1, packed.d.size(), f); fclose(f); }
@@ -156,6 +185,7 @@ int main(int argc, char** argv) {
     r = dec->Code(&pin, &back, nullptr, &outSize, nullptr);
     if (r != S_OK) { fprintf(stderr, "decoder Code() = 0x%08x\n", (unsigned)r); return 1; }
     CHECK(back.d == input);
+    { std::vector<Byte> pulled; int pr = pull_decode(dec, packed.d, outSize, pulled); if (pr) { fprintf(stderr, "zstd pull mode failed at step %d\n", pr); return 1; } CHECK(pulled == input); }
     // corrupt stream -> S_FALSE (data error)
     { std::vector<Byte> bad(packed.d.begin(), packed.d.begin() + packed.d.size() / 2); MemIn bi(bad); MemOut bo; CHECK(dec->Code(&bi, &bo, nullptr, &outSize, nullptr) == S_FALSE); }
     { FILE* f = fopen(argv[3], "wb"); CHECK(f); fwrite(packed.d.data(), 1, packed.d.size(), f); fclose(f); }
