@@ -81,3 +81,15 @@ def test_icompresscoder_roundtrip_lzma2(pkg, tmp_path, method):
     if helpers.ref_lzma_available():
         assert helpers.ref_lzma2_decompress(comp, len(data), 16) == (data, len(comp))
     assert comp == helpers.oracle_lzma2_compress(data)[1]
+
+
+def test_binding_parameter_ids_match_header(pkg):
+    """The ctypes binding names parameters by number: they must be the header's B200Z_P_* values."""
+    hdr = open(os.path.join(ROOT, "include", "b200z.h")).read()
+    ids = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+B200Z_P_([A-Z0-9_]+)\s+(\d+)", hdr)}
+    names = dict(level="LEVEL", frame_log="FRAMELOG", hash_log_l="HASHLOG_L", hash_log_s="HASHLOG_S", window_log="WINDOWLOG", flags="FLAGS",
+                 batch_log="BATCH_LOG", host_batch_log="HOST_BATCH_LOG", row_log="ROWLOG", lzma2_model="LZMA2_MODEL", lzma2_slice_log="LZMA2_SLICELOG")
+    assert set(names) == set(pkg.Codec._PARAMS)
+    for k, h in names.items():
+        assert pkg.Codec._PARAMS[k] == ids[h], k
+    assert len(set(ids.values())) == len(ids)
