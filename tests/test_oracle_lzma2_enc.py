@@ -72,3 +72,14 @@ def test_state_reset_slices(pkg):
             assert H.ref_lzma2_decompress_mt(comp, len(data), prop, 4) == (data, True)
         sizes.append(len(comp))
     assert sizes[0] <= sizes[1] <= sizes[2] <= sizes[3] < sizes[0] * 1.01
+
+
+def test_large_frames_hit_the_unpack_limit(pkg):
+    """Frames of 2..16 MiB with very compressible data: chunks close at the 2 MiB - 512 unpack limit, not the pack limit."""
+    data = pkg.corpus.entropy_class(3, 5 << 20).tobytes() + bytes(4 << 20)
+    for fl, sl in ((21, 0), (23, 2), (24, 0)):
+        prop, comp = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=1 | (sl << 8))
+        assert prop == (fl - 12) * 2
+        assert H.oracle_lzma2_decompress(comp, len(data), prop) == (data, len(comp))
+        if H.ref_lzma_available():
+            assert H.ref_lzma2_decompress(comp, len(data), prop) == (data, len(comp))
