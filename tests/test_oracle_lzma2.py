@@ -92,3 +92,38 @@ def test_corruption_parity_with_reference():
             assert o == r, (name, k)
             accepted += o is not None
     assert accepted > 10          # some corruptions are harmless (bytes after the end marker, FL2's trailing hash)
+
+
+def test_chunk_header_rules_host_walk_and_oracle():
+    """Lzma2Dec_UpdateState's needInitLevel rule and property checks (C/Lzma2Dec.c:97-165): the host walk
+    (b200z_lzma2_stream_info) and the oracle decoder reject the same malformed chunk sequences."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(H.ROOT, "7-zip-zstd_b200", "libb200z.so"))
+    lib.b200z_lzma2_stream_info.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t)]
+
+    def walk(b):
+        buf = ctypes.create_string_buffer(b, len(b)); cs, nb, used = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_size_t()
+        return lib.b200z_lzma2_stream_info(buf, len(b), ctypes.byref(cs), ctypes.byref(nb), ctypes.byref(used)), cs.value, nb.value, used.value
+
+    raw = lambda ctl, payload: bytes([ctl, (len(payload) - 1) >> 8, (len(payload) - 1) & 0xFF]) + payload
+    good = raw(1, b"hello") + raw(2, b" world") + b"\x00"
+    assert walk(good) == (0, 11, 1, len(good)) and H.oracle_lzma2_decompress(good, 11, 0) == (b"hello world", len(good))
+    two_blocks = raw(1, b"ab") + raw(1, b"cd") + b"\x00garbage"
+    assert walk(two_blocks)[:3] == (0, 4, 2) and walk(two_blocks)[3] == len(two_blocks) - 7
+    assert walk(b"\x00") == (0, 0, 0, 1) and H.oracle_lzma2_decompress(b"\x00", 0, 0) == (b"", 1)
+    lz = lambda ctl: bytes([ctl, 0, 0, 0, 4]) + (b"\x5d" if ctl >= 0xC0 else b"") + bytes(5) + b"\x00"    # header of a 1-byte LZMA chunk, dummy payload
+    bad = [
+        b"",                                   # no end marker
+        raw(2, b"x") + b"\x00",                # first chunk without a dictionary reset
+        raw(1, b"x"),                          # truncated: end marker missing
+        raw(1, b"x")[:-1],                     # truncated payload
+        b"\x03\x00\x00x\x00",                  # control bytes 3..0x7F do not exist
+        lz(0x80), lz(0xA0), lz(0xC0),          # LZMA chunk before any dictionary reset
+        raw(1, b"x") + lz(0x80), raw(1, b"x") + lz(0xA0),      # after an uncompressed reset the next LZMA chunk needs new properties (>= 0xC0)
+        bytes([0xE0, 0, 0, 0, 4, 225]) + bytes(5) + b"\x00",   # property byte out of range
+        bytes([0xE0, 0, 0, 0, 4, 4 * 9 + 8 + 0]) + bytes(5) + b"\x00",   # lc 8 + lp 4 > 4
+    ]
+    for b in bad:
+        assert walk(b)[0] == -5, b
+        with pytest.raises(ValueError):
+            H.oracle_lzma2_decompress(b, 64, 0)
