@@ -50,6 +50,9 @@
  * chunk in flight */
 #define B2Z_LZ2_FRAME_BOUND(n) ((n) + ((n) / 8192u + 2u) * 8u + 65536u + 128u)
 
+/* flags bit 4: method 21 parses by price (stage C candidates + stage P dynamic programme) instead of the greedy stage M */
+#define B2Z_FLAG_LZ2_OPT 0x10u
+
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL
 #define B2Z_PRIME8 0xCF1BBCDCB7A56463ULL

@@ -7,6 +7,7 @@
  * Shape: the input is cut into frames of 2^frameLog bytes; each frame becomes one dictionary-reset LZMA2 block (the unit
  * the reference's own MT coders use, Lzma2Enc.c:241-330 block split, Lzma2DecMt.c:237).  Inside a frame:
  *   stage M  the match finder / greedy-lazy parser shared with the zstd path (find_sequences of zstd_enc_oracle.c)
+ *            -- or, with flag B2Z_FLAG_LZ2_OPT, stage C + stage P: candidates and the price-based parse (lzma2_opt_oracle.c)
  *   stage R  this file: the sequences are coded as LZMA packets (literal / match / rep0-3) with the adaptive binary range
  *            coder, cut into LZMA2 chunks, with the raw-chunk fallback for chunks that do not shrink.
  *
@@ -210,8 +211,11 @@ int64_t b2zo_lzma2_compress(void *dstv, size_t dstCap, const void *srcv, size_t 
         uint8_t *lits = (uint8_t *)malloc(srcSize);
         uint8_t *tmp = (uint8_t *)malloc(B2Z_LZ2_FRAME_BOUND(F));
         enc_t *e = (enc_t *)malloc(sizeof(enc_t));
-        b2zo_zstd_find_sequences(src, srcSize, p, seqs, nseq, lits, nlit);
         const size_t bpf = F / B2Z_BLOCK;
+        if (p->flags & B2Z_FLAG_LZ2_OPT) {
+            for (size_t f = 0, f0 = 0; f0 < srcSize; f++, f0 += F)
+                b2zo_lzma2_parse_frame(src + f0, (uint32_t)(srcSize - f0 < F ? srcSize - f0 : F), p, NULL, seqs + f * bpf * B2Z_MAXSEQ, nseq + f * bpf);
+        } else b2zo_zstd_find_sequences(src, srcSize, p, seqs, nseq, lits, nlit);
         int fail = 0;
         for (size_t f = 0, f0 = 0; f0 < srcSize; f++, f0 += F) {
             const uint32_t n = (uint32_t)(srcSize - f0 < F ? srcSize - f0 : F);

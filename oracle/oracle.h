@@ -22,7 +22,8 @@ typedef struct {
     uint32_t hashLogS;      /* short (5-byte) hash table log (default 16)                     */
     uint32_t windowLog;     /* max match distance log (default = frameLog)                    */
     uint32_t rowLog;        /* log2 rows of the row-hash match finder (default 14; 0 = dual hash tables) */
-    uint32_t flags;         /* bit0: skippable size hints before each frame; bit1: checksum   */
+    uint32_t flags;         /* bit0: skippable size hints before each frame; bit1: checksum;
+                               bits 8..10: LZMA2 slice log; bit4: LZMA2 price-based parse */
 } b2zo_enc_params;
 
 void   b2zo_enc_default_params(b2zo_enc_params *p, int level);
@@ -43,6 +44,12 @@ int64_t b2zo_lzma2_decompress(void *dst, size_t dstCap, const void *src, size_t 
 /* ---- LZMA2 (method 21) encoder: lzma2_enc_oracle.c (sequential statement of the GPU encoder) ---- */
 size_t  b2zo_lzma2_compress_bound(size_t srcSize, const b2zo_enc_params *p);
 int64_t b2zo_lzma2_compress(void *dst, size_t dstCap, const void *src, size_t srcSize, const b2zo_enc_params *p, uint32_t *dictProp);
+
+/* price-based parse (lzma2_opt_oracle.c; flags bit 4 of b2zo_lzma2_compress selects it).  Stage taps for parity with the GPU:
+ * stage C: candidates of one frame, LZP_NCAND packed words per position (b2z_lzma_model.h);
+ * stage P: one frame -> per-block sequences, block-indexed like b2zo_zstd_find_sequences (cand = stage C's output, or NULL) */
+void b2zo_lzma2_candidates(const void *base, uint32_t n, uint32_t frameLog, uint32_t *cand);
+void b2zo_lzma2_parse_frame(const void *base, uint32_t n, const b2zo_enc_params *P, const uint32_t *cand, uint64_t *seqs, uint32_t *nseq);
 
 #ifdef __cplusplus
 }
