@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 P_LEVEL, P_FRAMELOG, P_HASHLOG_L, P_HASHLOG_S, P_WINDOWLOG, P_FLAGS, P_BATCH_LOG = 1, 2, 3, 4, 5, 6, 7
 S_ENC_MATCH_MS, S_ENC_ENTROPY_MS, S_ENC_ASSEMBLE_MS, S_DEC_ENTROPY_MS, S_DEC_EXEC_MS = 1, 2, 3, 4, 5
 S_KERNEL_LAUNCHES, S_H2D_BYTES, S_D2H_BYTES = 6, 7, 8
+S_DEC_PREPASS_MS, S_ENC_PARSE_MS = 9, 10
 MAXSEQ = 32768
 
 EXPORTS = [
@@ -68,6 +69,7 @@ def load_library():
     L.b200z_lzma2_stream_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(sz)]
     for name in ("b200z_lzma2_decompress_device", "b200z_lzma2_decompress_host"):
         getattr(L, name).argtypes = [vp, vp, sz, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
+    L.b200z_lzma2_enc_stage_cp.argtypes = [vp, vp, sz, vp, vp, vp]
     L.b200z_dev_alloc.argtypes = [vp, ctypes.POINTER(vp), sz]
     L.b200z_dev_free.argtypes = [vp, vp]
     L.b200z_dev_upload.argtypes = [vp, vp, vp, sz]
@@ -115,7 +117,7 @@ class Codec:
             raise B200zError(rc, self.L.b200z_last_error(self.h).decode())
 
     _PARAMS = dict(level=P_LEVEL, frame_log=P_FRAMELOG, hash_log_l=P_HASHLOG_L, hash_log_s=P_HASHLOG_S,
-                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, row_log=9, lzma2_model=10, lzma2_slice_log=11)
+                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, row_log=9, lzma2_model=10, lzma2_slice_log=11, lzma2_parse=12)
 
     def set(self, name, value):
         self._check(self.L.b200z_set_param(self.h, self._PARAMS[name], int(value)))
@@ -258,3 +260,21 @@ class Codec:
         finally:
             self.L.b200z_dev_free(self.h, d)
         return seqs, nseq, lits, nlit
+
+    # ---- test tap: the price-based LZMA2 parse (lzma2_parse=1): stage C candidate words [n, 4] and stage P sequences
+    # (layouts of the oracle's b2zo_lzma2_candidates / b2zo_lzma2_parse_frame, frames back to back)
+    def stage_cp(self, data):
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8)
+        n = src.nbytes
+        nblk = (n + 131071) // 131072
+        d = ctypes.c_void_p()
+        self._check(self.L.b200z_dev_alloc(self.h, ctypes.byref(d), n + 64))
+        try:
+            self._check(self.L.b200z_dev_upload(self.h, d, src.ctypes.data, n))
+            cand = np.zeros(max(n, 1) * 4, dtype=np.uint32)
+            seqs = np.zeros(nblk * MAXSEQ, dtype=np.uint64); nseq = np.zeros(nblk, dtype=np.uint32)
+            self._check(self.L.b200z_lzma2_enc_stage_cp(self.h, d, n, cand.ctypes.data, seqs.ctypes.data, nseq.ctypes.data))
+        finally:
+            self.L.b200z_dev_free(self.h, d)
+        return cand[:n * 4].reshape(-1, 4), seqs, nseq

@@ -8,6 +8,7 @@
 #include <vector>
 #include "b2z_ctx.h"
 #include "b2z_lzma2.h"
+#include "b2z_lzma_model.h"
 
 using namespace b2z;
 
@@ -51,7 +52,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
-                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize };
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize, &ctx->cand };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -75,6 +76,8 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (ctx->geom.flags & ~3u) | (uint32_t)v; return 0;
     case B200Z_P_LZMA2_SLICELOG: if (v < 0 || v > 3) return fail(ctx, B200Z_E_PARAM, "lzma2 sliceLog out of range%s");
                             ctx->geom.flags = (ctx->geom.flags & ~0x700u) | ((uint32_t)v << 8); return 0;
+    case B200Z_P_LZMA2_PARSE: if (v < 0 || v > 1) return fail(ctx, B200Z_E_PARAM, "lzma2 parse mode out of range%s");
+                            ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_LZ2_OPT) | (v ? B2Z_FLAG_LZ2_OPT : 0u); return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
     case B200Z_P_ROWLOG:    if (v < 8 || v > 18) return fail(ctx, B200Z_E_PARAM, "rowLog out of range%s"); ctx->geom.rowLog = (uint32_t)v; return 0;
     case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
@@ -93,6 +96,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_WINDOWLOG: *v = ctx->geom.windowLog; return 0;
     case B200Z_P_FLAGS: *v = ctx->geom.flags & 3u; return 0;
     case B200Z_P_LZMA2_SLICELOG: *v = B2Z_LZ2_SLICELOG(ctx->geom.flags); return 0;
+    case B200Z_P_LZMA2_PARSE: *v = (ctx->geom.flags & B2Z_FLAG_LZ2_OPT) ? 1 : 0; return 0;
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
@@ -119,6 +123,12 @@ static uint32_t match_warps(const b200z_ctx* ctx, uint64_t nFrames) {
     return (uint32_t)(nFrames < cap ? nFrames : cap);
 }
 
+// stage C of the price-based LZMA2 parse: every resident frame-warp owns 7-30 MB of tables
+static uint32_t cand_warps(const b200z_ctx* ctx, uint64_t nFrames) {
+    const uint64_t cap = (uint64_t)ctx->smCount * 8u;
+    return (uint32_t)(nFrames < cap ? nFrames : cap);
+}
+
 static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     const uint64_t F = 1ull << ctx->geom.frameLog;
     const uint64_t nFrames = (batchBytes + F - 1) / F;
@@ -126,6 +136,10 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     const uint32_t nWarps = match_warps(ctx, nFrames);
     const size_t tableBytes = (size_t)64 << ctx->geom.rowLog;           // row-hash table: 2^rowLog rows of 64 bytes per frame-warp
     int bad = 0;
+    if (codec == 1 && (ctx->geom.flags & B2Z_FLAG_LZ2_OPT)) {           // price-based parse: stage C's tables and candidate words
+        bad |= ctx->tables.reserve(lzma2_cand_table_bytes(ctx->geom, cand_warps(ctx, nFrames)));
+        bad |= ctx->cand.reserve((size_t)nFrames * F * LZP_NCAND * 4u);
+    } else
     bad |= ctx->tables.reserve(tableBytes * nWarps);
     bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);
     bad |= ctx->nseq.reserve(nBlocks * 4);
@@ -153,11 +167,30 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     const uint32_t nWarps = match_warps(ctx, nFrames);
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev[0], st));
+    if (codec == 1 && (g.flags & B2Z_FLAG_LZ2_OPT)) {
+        // method 21, price-based parse: stage C (candidates) + stage P (dynamic programme) instead of the greedy stage M
+        if (ready) { CU(cudaEventRecord(ctx->pe[1], ctx->stream2)); CU(cudaStreamWaitEvent(st, ctx->pe[1], 0)); }   // the whole upload first
+        launch_lzma2_cand(d_src, n, g, (uint32_t*)ctx->tables.p, cand_warps(ctx, nFrames), (uint32_t*)ctx->cand.p, st);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[4], st));
+        CU(launch_lzma2_parse(d_src, n, g, (const uint32_t*)ctx->cand.p, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p, st));
+        CU(cudaEventRecord(ctx->ev[1], st));
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 2;
+        if (stageMOnly) {
+            CU(cudaStreamSynchronize(st));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+            cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[1]); ctx->stat[B200Z_S_ENC_PARSE_MS] += ms;
+            return 0;
+        }
+    } else {
     launch_zstd_enc_match(d_src, n, g, (uint32_t*)ctx->tables.p, nWarps, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
                           (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, ready, readyShift, st);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[4], st));
     CU(cudaEventRecord(ctx->ev[1], st));
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+    }
     if (!stageMOnly && codec == 1) {
         // LZMA2: stage R (range coding, one thread per frame) + assembly of the frame slots into one chunk stream
         constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
@@ -183,7 +216,8 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         if ((uint32_t)hs[2]) return fail(ctx, B200Z_E_CUDA, "LZMA2: frame slot overflow%s");
         *produced = hs[0];
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[1]); ctx->stat[B200Z_S_ENC_PARSE_MS] += ms;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_ENC_ENTROPY_MS] += ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stat[B200Z_S_ENC_ASSEMBLE_MS] += ms;
     } else if (!stageMOnly) {
@@ -424,7 +458,9 @@ int b200z_lzma2_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSiz
     if (dictProp) *dictProp = (ctx->geom.frameLog - 12u) * 2u;           // dictionary = frame size (Lzma2Enc_WriteProperties, Lzma2Enc.c:671)
     CU(cudaSetDevice(ctx->device));
     const uint64_t F = 1ull << ctx->geom.frameLog;
-    uint64_t batch = 1ull << ctx->batchLog; if (batch < F) batch = F;
+    uint64_t batch = 1ull << ctx->batchLog;
+    if ((ctx->geom.flags & B2Z_FLAG_LZ2_OPT) && batch > (1ull << 30)) batch = 1ull << 30;    // stage C keeps 16 bytes per input byte
+    if (batch < F) batch = F;
     uint64_t done = 0, outPos = 0;
     while (done < srcSize) {
         const uint64_t n = (srcSize - done) < batch ? (srcSize - done) : batch;
@@ -439,6 +475,23 @@ int b200z_lzma2_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSiz
     return 0;
 }
 
+// Test tap of the price-based parse: stage C's candidate words and stage P's per-block sequences of a device buffer (one batch)
+int b200z_lzma2_enc_stage_cp(b200z_ctx* ctx, const void* d_src, size_t srcSize, uint32_t* cand, uint64_t* seqs, uint32_t* nseq) {
+    if (!ctx || (!d_src && srcSize)) return B200Z_E_PARAM;
+    if (!(ctx->geom.flags & B2Z_FLAG_LZ2_OPT)) return fail(ctx, B200Z_E_PARAM, "set B200Z_P_LZMA2_PARSE to 1 first%s");
+    if (!srcSize) return 0;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t produced = 0;
+    int rc = enc_batch(ctx, (const uint8_t*)d_src, srcSize, nullptr, &produced, true, nullptr, 0, 1);
+    if (rc) return rc;
+    const uint64_t F = 1ull << ctx->geom.frameLog, nFrames = (srcSize + F - 1) / F;
+    const uint64_t nBlocks = (nFrames - 1) * (F >> 17) + ((srcSize - (nFrames - 1) * F + B2Z_BLOCK - 1) / B2Z_BLOCK);   // block-indexed per frame; the last frame may be short
+    if (cand) CU(cudaMemcpy(cand, ctx->cand.p, srcSize * LZP_NCAND * 4u, cudaMemcpyDeviceToHost));
+    if (seqs) CU(cudaMemcpy(seqs, ctx->seqs.p, nBlocks * B2Z_MAXSEQ * 8ull, cudaMemcpyDeviceToHost));
+    if (nseq) CU(cudaMemcpy(nseq, ctx->nseq.p, nBlocks * 4ull, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // Host-pointer form; one batch: chunked upload overlapped with stage M (as the zstd path), kernels, download.
 int b200z_lzma2_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize, uint32_t* dictProp) {
     if (!ctx || !dstSize || (!src && srcSize) || !dst) return B200Z_E_PARAM;
@@ -448,7 +501,9 @@ int b200z_lzma2_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, v
     if (!srcSize) { *(uint8_t*)dst = 0; *dstSize = 1; return 0; }
     CU(cudaSetDevice(ctx->device));
     const uint64_t F = 1ull << ctx->geom.frameLog;
-    uint64_t batch = 1ull << ctx->hostBatchLog; if (batch < F) batch = F;
+    uint64_t batch = 1ull << ctx->hostBatchLog;
+    if ((ctx->geom.flags & B2Z_FLAG_LZ2_OPT) && batch > (1ull << 30)) batch = 1ull << 30;
+    if (batch < F) batch = F;
     const uint64_t maxIn = srcSize < batch ? srcSize : batch;
     if (ctx->dIn.reserve(maxIn + 64) || ctx->dOut.reserve(b200z_lzma2_compress_bound(ctx, maxIn)) || ctx->ready.reserve(256))
         return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");

@@ -8,8 +8,16 @@
 
 namespace b2z {
 
+#ifdef B2Z_CUEMU   // tests/cuemu compiles the kernel sources for the host (logic checks without a GPU): no PTX there
+__device__ __forceinline__ uint32_t lane_id() { return cuemu_lane_id(); }
+__device__ __forceinline__ uint32_t lanemask_lt() { return (1u << cuemu_lane_id()) - 1u; }
+#define B2Z_DYN_SMEM(T, name) T* const name = reinterpret_cast<T*>(cuemu::dyn_smem())
+#else
 __device__ __forceinline__ uint32_t lane_id() { uint32_t l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+// the CTA's dynamic shared memory as one struct
+#define B2Z_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; T* const name = reinterpret_cast<T*>(name##_raw_)
+#endif
 
 // 64-bit funnel: bytes [s/8, s/8+8) of the 16-byte little-endian pair (a, b); s in {0,8,..,56}
 __device__ __forceinline__ uint64_t funnel64(uint64_t a, uint64_t b, uint32_t s) {

@@ -96,6 +96,14 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
 void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nPieces, uint32_t slotStride, uint64_t* pieceOff,
                                uint8_t* dst, uint64_t* outSize, cudaStream_t st);
 
+// ---- encoder, price-based parse (lzma2_parse.cu): stage C (candidates, one warp per frame; nWarps table sets) and stage P
+// (dynamic programme, one warp per state-reset slice) fill the per-block sequence arrays stage R reads
+size_t lzma2_cand_table_bytes(const EncGeom& g, uint32_t nWarps);
+size_t lzma2_parse_smem_bytes();
+void launch_lzma2_cand(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps, uint32_t* cand /* [srcSize * 4] */, cudaStream_t st);
+cudaError_t launch_lzma2_parse(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint32_t* cand, uint64_t* seqs,
+                               uint32_t* nseq /* one counter per 128 KiB block, zeroed here */, cudaStream_t st);
+
 void launch_lzma2_walk(const uint8_t* src, uint64_t srcSize, Lz2Block* blocks, uint32_t cap, Lz2Counts* counts, cudaStream_t st);
 // one warp per block; returns cudaError of the launch configuration (shared memory opt-in)
 size_t lzma2_lit_spill_bytes(uint32_t nBlocks, uint32_t maxLcLp);

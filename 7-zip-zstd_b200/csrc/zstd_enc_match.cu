@@ -235,6 +235,7 @@ zstd_enc_match_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
     }
 }
 
+#ifndef B2Z_CUEMU
 void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,
                            uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, const uint32_t* ready, uint32_t readyShift,
                            cudaStream_t st) {
@@ -243,5 +244,6 @@ void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& 
     const uint32_t grid = (nWarps + warpsPerCta - 1) / warpsPerCta;
     zstd_enc_match_kernel<<<grid, B2Z_MATCH_THREADS, 0, st>>>(src, srcSize, g, tables, seqs, nseq, lits, nlit, ready, readyShift);
 }
+#endif
 
 }  // namespace b2z

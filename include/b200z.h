@@ -51,6 +51,9 @@ extern "C" {
 #define B200Z_P_LZMA2_MODEL 10  /* LZMA2 decoder: literal model in 1 = shared memory (13 warps/SM), 2 = global memory (32 warps/SM), 0 = by block count */
 #define B200Z_P_LZMA2_SLICELOG 11 /* LZMA2 encoder: log2 of the state-reset slices a block's range coding is split into (0..3, default 2):
                                    independent range-coder chains per block, as fast-lzma2's encoder threads (lzma2_enc.c:1937) */
+#define B200Z_P_LZMA2_PARSE 12  /* LZMA2 encoder parse: 0 = greedy/lazy on the finder shared with the zstd path (default), 1 = price-based:
+                                   nearest-occurrence candidates by 3/4/6/8-byte keys + a windowed dynamic programme over the adaptive
+                                   model -- the role of LzmaEnc.c:1225 GetOptimum / fast-lzma2 lzma2_enc.c:949 LZMA_optimalParse */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
@@ -64,6 +67,7 @@ extern "C" {
 #define B200Z_S_H2D_BYTES       7
 #define B200Z_S_D2H_BYTES       8
 #define B200Z_S_DEC_PREPASS_MS  9
+#define B200Z_S_ENC_PARSE_MS    10  /* LZMA2 price-based parse: stage P (stage C is counted as ENC_MATCH_MS) */
 
 typedef struct b200z_ctx b200z_ctx;
 
@@ -124,12 +128,16 @@ int b200z_lzma2_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
  * and returns the 1-byte coder property for the 7z folder (what ICompressWriteCoderProperties emits,
  * Lzma2Encoder.cpp:117-121 / FastLzma2 :353-364).  Replaces NCompress::NLzma2::CEncoder::Code -> Lzma2Enc_Encode2
  * (Lzma2Encoder.cpp:124-134, C/Lzma2Enc.c:717) and CFastEncoder::Code -> FL2_compressStream (Lzma2Encoder.cpp:280-340,
- * C/fast-lzma2/fl2_compress.c).  lc/lp/pb are fixed at 3/0/2. */
+ * C/fast-lzma2/fl2_compress.c).  lc/lp/pb are fixed at 2/0/2. */
 size_t b200z_lzma2_compress_bound(b200z_ctx *ctx, size_t srcSize);
 int b200z_lzma2_compress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize, void *d_dst, size_t dstCap,
                                 size_t *dstSize, uint32_t *dictProp);
 int b200z_lzma2_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap,
                               size_t *dstSize, uint32_t *dictProp);
+
+/* Test tap of the price-based parse (B200Z_P_LZMA2_PARSE = 1): stage C's candidate words (4 per input byte) and stage P's
+ * per-block sequences of a device buffer, layouts of the oracle's b2zo_lzma2_candidates / b2zo_lzma2_parse_frame. */
+int b200z_lzma2_enc_stage_cp(b200z_ctx *ctx, const void *d_src, size_t srcSize, uint32_t *cand, uint64_t *seqs, uint32_t *nseq);
 
 /* device memory helpers so FFI users need no CUDA binding of their own */
 int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);

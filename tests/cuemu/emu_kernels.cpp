@@ -1,0 +1,46 @@
+// emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY: the kernel SOURCES of 7-zip-zstd_b200/csrc compiled for the host through
+// tests/cuemu/cuemu.h (see there), with C entry points the CPU tests call.  Built by tests/cuemu/Makefile into
+// tests/cuemu/libcuemu_kernels.so; never part of libb200z.so.
+#define B2Z_CUEMU 1
+#include "cuemu.h"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_match.cu"
+#include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
+
+using namespace b2z;
+
+static EncGeom geom(uint32_t frameLog, uint32_t windowLog, uint32_t rowLog, uint32_t flags) {
+    EncGeom g; memset(&g, 0, sizeof(g));
+    g.frameLog = frameLog; g.hashLogL = B2Z_DEF_HASHLOG_L; g.hashLogS = B2Z_DEF_HASHLOG_S; g.windowLog = windowLog; g.flags = flags; g.rowLog = rowLog; g.frameSizes = nullptr;
+    return g;
+}
+
+extern "C" {
+
+// stage M (zstd_enc_match_kernel): the GPU-verified kernel, here to check the emulator itself against the oracle
+uint64_t emu_zstd_enc_match(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t rowLog, uint32_t flags, uint32_t nWarps,
+                            uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit) {
+    const EncGeom g = geom(frameLog, windowLog, rowLog, flags);
+    std::vector<uint32_t> tables((size_t)nWarps * (16u << rowLog), 0xCDCDCDCDu);
+    return cuemu::launch(dim3(nWarps), dim3(B2Z_MATCH_THREADS), 0, [&] {
+        zstd_enc_match_kernel(src, srcSize, g, tables.data(), seqs, nseq, lits, nlit, nullptr, 0);
+    });
+}
+
+// stage C (lzma2_cand_kernel)
+uint64_t emu_lzma2_cand(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, uint32_t nWarps, uint32_t* cand) {
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    std::vector<uint32_t> tables((size_t)nWarps * lzma2_cand_table_words(frameLog), 0xCDCDCDCDu);
+    return cuemu::launch(dim3(nWarps), dim3(32), 0, [&] { lzma2_cand_kernel(src, srcSize, g, tables.data(), cand); });
+}
+
+// stage P (lzma2_parse_kernel); nseq is zeroed here as launch_lzma2_parse does
+uint64_t emu_lzma2_parse(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint32_t* cand, uint64_t* seqs, uint32_t* nseq) {
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const uint64_t F = 1ull << frameLog;
+    const uint32_t nFrames = (uint32_t)((srcSize + F - 1) >> frameLog), bpf = (uint32_t)(F >> 17);
+    const uint32_t spf = bpf / B2Z_LZ2_SLICE_BLOCKS(frameLog, flags), nChains = nFrames * spf;
+    memset(nseq, 0, (size_t)nFrames * bpf * sizeof(uint32_t));
+    return cuemu::launch(dim3(nChains), dim3(32), lzma2_parse_smem_bytes(), [&] { lzma2_parse_kernel(src, srcSize, g, cand, seqs, nseq, nChains); });
+}
+
+}

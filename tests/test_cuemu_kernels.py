@@ -1,0 +1,98 @@
+"""CPU: the CUDA kernel SOURCES compiled for the host through tests/cuemu/cuemu.h (a fiber-per-thread emulation of the
+warp-synchronous subset they use) against the oracle.  This is a logic check of the kernel code on a machine without a GPU --
+not a CPU path of the product (libb200z.so is nvcc-only and fails without a device) and no substitute for the `-m gpu` parity
+tests: it cannot see timing, memory-model races between warps or anything about the hardware.
+
+  * zstd_enc_match_kernel (stage M) is GPU-verified against the oracle; here it validates the emulator itself.
+  * lzma2_cand_kernel / lzma2_parse_kernel (stage C / stage P of the price-based LZMA2 parse) were developed against it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OPT = 0x10
+
+
+@pytest.fixture(scope="module")
+def emu():
+    d = os.path.join(HERE, "cuemu")
+    subprocess.check_call(["make", "-s", "-C", d])
+    E = ctypes.CDLL(os.path.join(d, "libcuemu_kernels.so"))
+    vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
+    E.emu_zstd_enc_match.restype = u64; E.emu_zstd_enc_match.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp, vp, vp, vp]
+    E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]
+    E.emu_lzma2_parse.restype = u64; E.emu_lzma2_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp]
+    return E
+
+
+def _mixed(pkg, n_text):
+    return (pkg.corpus.g2(n_text).tobytes() + bytes(5000) + pkg.corpus.entropy_class(3, 70_000).tobytes() + b"ab" * 3000
+            + pkg.corpus.entropy_class(1, 20_000).tobytes() + pkg.corpus.entropy_class(2, 30_000).tobytes())
+
+
+def test_emulated_stage_m_equals_the_oracle(pkg, emu):
+    data = _mixed(pkg, 200_000); n = len(data)
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    nblk = (n + 131071) // 131072
+    for fl, warps in ((17, 2), (18, 1)):
+        seqs, nseq, lits, nlit = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl)
+        s2 = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); ns2 = np.zeros(nblk, dtype=np.uint32); nl2 = np.zeros(nblk, dtype=np.uint32); l2 = np.zeros(n + 64, dtype=np.uint8)
+        assert emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 14, 1 | (2 << 8), warps, s2.ctypes.data, ns2.ctypes.data, l2.ctypes.data, nl2.ctypes.data) > 0
+        assert np.array_equal(nseq, ns2) and np.array_equal(nlit, nl2)
+        for b in range(nblk):
+            assert np.array_equal(seqs[b * H.MAXSEQ:b * H.MAXSEQ + nseq[b]], s2[b * H.MAXSEQ:b * H.MAXSEQ + nseq[b]]), b
+            assert np.array_equal(lits[b * 131072:b * 131072 + nlit[b]], l2[b * 131072:b * 131072 + nlit[b]]), b
+
+
+def _oracle_taps(data, fl, flags):
+    O = H.oracle()
+    O.b2zo_lzma2_candidates.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+    O.b2zo_lzma2_parse_frame.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(H.EncParams)] + [ctypes.c_void_p] * 3
+    n = len(data); F = 1 << fl; bpf = F >> 17; nfr = (n + F - 1) // F
+    src = np.frombuffer(data, dtype=np.uint8)
+    cand = np.zeros(nfr * F * 4, dtype=np.uint32); seqs = np.zeros(nfr * bpf * H.MAXSEQ, dtype=np.uint64); nseq = np.zeros(nfr * bpf, dtype=np.uint32)
+    p = H.enc_params(frameLog=fl, windowLog=fl, flags=flags)
+    for f in range(nfr):
+        f0 = f * F; fn = min(F, n - f0)
+        O.b2zo_lzma2_candidates(src.ctypes.data + f0, fn, fl, cand.ctypes.data + f0 * 16)
+        O.b2zo_lzma2_parse_frame(src.ctypes.data + f0, fn, ctypes.byref(p), cand.ctypes.data + f0 * 16, seqs.ctypes.data + f * bpf * H.MAXSEQ * 8, nseq.ctypes.data + f * bpf * 4)
+    return cand, seqs, nseq
+
+
+@pytest.mark.parametrize("fl,sl,warps", [(18, 1, 2), (17, 0, 3), (19, 2, 1)])
+def test_emulated_stage_c_and_p_equal_the_oracle(pkg, emu, fl, sl, warps):
+    data = _mixed(pkg, 150_000); n = len(data)
+    flags = 1 | (sl << 8) | OPT
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    candO, seqO, nsO = _oracle_taps(data, fl, flags)
+    candE = np.zeros_like(candO)
+    assert emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, warps, candE.ctypes.data) > 0
+    assert np.array_equal(candE[:n * 4], candO[:n * 4])
+    seqE = np.zeros_like(seqO); nsE = np.full_like(nsO, 0xFFFFFFFF)
+    assert emu.emu_lzma2_parse(src.ctypes.data, n, fl, flags, candE.ctypes.data, seqE.ctypes.data, nsE.ctypes.data) > 0
+    assert np.array_equal(nsE, nsO) and int(nsO.sum()) > 10_000
+    for b in range(len(nsO)):
+        assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), b
+
+
+def test_emulated_parse_edge_inputs(pkg, emu):
+    """tiny, ragged and degenerate frames: one byte, shorter than any key, all zeros (every window ends in a long match),
+    a frame that ends one byte into a block"""
+    cases = [b"a", b"ab", b"abcabcabcabc", bytes(70_000), pkg.corpus.g2(131073).tobytes(), b"\x01" * 33, pkg.corpus.g2(40_000).tobytes() * 3]
+    for data in cases:
+        n = len(data); fl = 17; flags = 1 | OPT
+        src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+        candO, seqO, nsO = _oracle_taps(data, fl, flags)
+        candE = np.zeros_like(candO); seqE = np.zeros_like(seqO); nsE = np.full_like(nsO, 0xFFFFFFFF)
+        emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, 2, candE.ctypes.data)
+        assert np.array_equal(candE[:n * 4], candO[:n * 4]), n
+        emu.emu_lzma2_parse(src.ctypes.data, n, fl, flags, candE.ctypes.data, seqE.ctypes.data, nsE.ctypes.data)
+        nb = (n + 131071) // 131072
+        assert np.array_equal(nsE[:nb], nsO[:nb]), n
+        for b in range(nb):
+            assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), (n, b)
