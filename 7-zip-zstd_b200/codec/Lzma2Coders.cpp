@@ -20,6 +20,7 @@ class CLzma2Encoder final : public ICompressCoder, public ICompressSetCoderPrope
     std::atomic<UInt32> refs_{0};
     const bool fast_;
     int frameLog_ = 20;                                        // 1 MiB blocks: thousands of independent blocks per GiB
+    int level_ = -1, algo_ = -1;                               // kLevel / kAlgorithm as given (-1: not given)
     PinnedBuf in_, out_;
 public:
     UInt64 processedIn = 0, processedOut = 0;
@@ -47,10 +48,12 @@ public:
             case NCoderPropID::kNumThreads: if (p.vt != VT_UI4) return E_INVALIDARG; break;
             case NCoderPropID::kNumThreadGroups: if (p.vt != VT_UI4 || p.ulVal >= (1u << 16)) return E_INVALIDARG; break;
             case NCoderPropID::kDictionarySize: if (p.vt != VT_UI4 && p.vt != VT_UI8) return E_INVALIDARG; dictSize = p.vt == VT_UI4 ? p.ulVal : p.uhVal; break;
-            case NCoderPropID::kAlgorithm: if (p.vt != VT_UI4) return E_INVALIDARG; if (fast_ && p.ulVal > 3) return E_INVALIDARG; break;   // Lzma2Encoder.cpp:197-199
+            case NCoderPropID::kAlgorithm: if (p.vt != VT_UI4) return E_INVALIDARG; if (fast_ && p.ulVal > 3) return E_INVALIDARG;      // Lzma2Encoder.cpp:197-199
+                algo_ = (int)p.ulVal; break;
+            case NCoderPropID::kLevel: if (p.vt != VT_UI4) return E_INVALIDARG; level_ = (int)p.ulVal; break;
             case NCoderPropID::kLitContextBits: case NCoderPropID::kLitPosBits: case NCoderPropID::kPosStateBits:
-            case NCoderPropID::kNumFastBytes: case NCoderPropID::kMatchFinderCycles: case NCoderPropID::kLevel:
-                if (p.vt != VT_UI4) return E_INVALIDARG;      // accepted; the GPU coder runs lc3 lp0 pb2 and its own parser
+            case NCoderPropID::kNumFastBytes: case NCoderPropID::kMatchFinderCycles:
+                if (p.vt != VT_UI4) return E_INVALIDARG;      // accepted; the GPU coder runs lc2 lp0 pb2 and its own finder
                 break;
             default: break;                                    // kMatchFinder, kEndMarker, kReduceSize, kAffinity ...: accepted
             }
@@ -59,6 +62,14 @@ public:
         const uint64_t want = (blockSize && blockSize != ~0ull) ? blockSize : dictSize;
         if (want) { int fl = log2_floor(want); frameLog_ = fl < 17 ? 17 : (fl > 24 ? 24 : fl); }
         return S_OK;
+    }
+    // Which parse the level / algorithm asks for, as the reference resolves them: the stock encoder parses by price when
+    // algo != 0, algo defaulting to (level < 5 ? 0 : 1) (LzmaEnc.c:97, :570 fastMode); fast-lzma2's strategy is the given
+    // algorithm, else its level table's: fast at levels 1-2, opt/ultra from 3 (fl2_compress.c:72-84).  No level given: 5.
+    int price_parse() const {
+        const int level = level_ < 0 ? 5 : level_;
+        if (algo_ >= 0) return algo_ != 0;
+        return fast_ ? level >= 3 : level >= 5;
     }
     HRESULT SetCoderPropertiesOpt(const PROPID*, const PROPVARIANT*, UInt32) override { return S_OK; }   // kExpectedDataSize
     HRESULT WriteCoderProperties(ISequentialOutStream* out) override {
@@ -71,6 +82,7 @@ public:
         HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
         b200z_set_param(ctx, B200Z_P_FRAMELOG, frameLog_);
         b200z_set_param(ctx, B200Z_P_WINDOWLOG, frameLog_);
+        b200z_set_param(ctx, B200Z_P_LZMA2_PARSE, price_parse());
         const size_t batch = (size_t)1 << 30;                  // 1 GiB of input per GPU pass (about a thousand blocks)
         if (!in_.reserve(batch) || !out_.reserve(b200z_lzma2_compress_bound(ctx, batch))) return E_OUTOFMEMORY;
         for (;;) {

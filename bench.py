@@ -34,6 +34,10 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=1024, help="bounded sample for the CPU reference arm")
     ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
                     help="zstd: method 4F71101 level 3 (the headline, BASELINE configs[1]); lzma2: method 21 (configs[3])")
+    ap.add_argument("--lzma2-parse", type=int, default=0, choices=[0, 1],
+                    help="--codec lzma2: 0 = greedy parse (the measured round-1 line), 1 = price-based parse (stage C + stage P, DESIGN.md 2c)")
+    ap.add_argument("--frame-log", type=int, default=0, help="log2 of the independent frame / block size (default: the library's, 20)")
+    ap.add_argument("--lzma2-slice-log", type=int, default=-1, help="--codec lzma2: log2 of state-reset slices per block (default: the library's, 2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -189,6 +193,12 @@ def main():
         torch.cuda.synchronize()
 
     codec = pkg.Codec(local)
+    if a.frame_log:
+        codec.set("frame_log", a.frame_log); codec.set("window_log", a.frame_log)
+    if lz and a.lzma2_slice_log >= 0:
+        codec.set("lzma2_slice_log", a.lzma2_slice_log)
+    if lz and a.lzma2_parse:
+        codec.set("lzma2_parse", 1)
     # ---- corpus shard: rank r owns bytes [r*unit, (r+1)*unit) of the seeded G2 stream (weak scaling)
     host_in = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
     pkg.corpus.g2_into(host_in.data_ptr(), unit_bytes, offset=rank * unit_bytes, threads=max(1, (os.cpu_count() or 8) // max(1, world)))
@@ -222,7 +232,7 @@ def main():
     barrier(); T1 = time.perf_counter()
     clocks = sampler.stop(T0, T1)
     elapsed = T1 - T0
-    stats = {k: codec.stat(v) for k, v in dict(match_ms=1, entropy_ms=2, assemble_ms=3, dec_prepass_ms=9, dec_entropy_ms=4, dec_exec_ms=5, launches=6).items()}
+    stats = {k: codec.stat(v) for k, v in dict(match_ms=1, entropy_ms=2, assemble_ms=3, dec_prepass_ms=9, dec_entropy_ms=4, dec_exec_ms=5, launches=6, parse_ms=10).items()}
     if dist:
         t = torch.tensor([elapsed, t_enc, t_dec], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX); elapsed, t_enc, t_dec = (float(x) for x in t.cpu())
@@ -270,20 +280,22 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0); peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
     # LZMA2: the dominant kernel is stage R (lzma2_enc_range_kernel: one serial range-coder chain per 1 MiB block)
-    dom_kernel = "lzma2_enc_range_kernel" if lz else "zstd_enc_match_kernel"
-    match_ms = (stats["entropy_ms"] if lz else stats["match_ms"]) / a.steps
+    #        with the price-based parse it is stage P (lzma2_parse_kernel: one dynamic-programme chain per slice)
+    dom_kernel = ("lzma2_parse_kernel" if a.lzma2_parse else "lzma2_enc_range_kernel") if lz else "zstd_enc_match_kernel"
+    match_ms = ((stats["parse_ms"] if a.lzma2_parse else stats["entropy_ms"]) if lz else stats["match_ms"]) / a.steps
     algo_bytes = unit_bytes * (1.0 + 1.0 / ratio)
     achieved = algo_bytes / 1e9 / (match_ms / 1e3) if match_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lzma2_range_traffic.json" if lz else "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
+        if not (lz and a.lzma2_parse):                              # no ncu capture of stage P yet
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lzma2_range_traffic.json" if lz else "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
     except Exception:
         pass
     line = {
         "metric": metric_name, "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "global_uncompressed_bytes_per_step": world * unit_bytes, "frame_log": codec.get("frame_log"),
-                   "parallelism": f"{world} independent shard(s), no collective", "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
+                   "parallelism": f"{world} independent shard(s), no collective", **({"lzma2_parse": a.lzma2_parse} if lz else {}), "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
                    "ratio": ratio, "enc_MBps": units_mb / t_enc, "dec_MBps": units_mb / t_dec,
                    "kernel_ms_per_step": {k: v / a.steps for k, v in stats.items() if k != "launches"}},
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",

@@ -124,7 +124,7 @@ int main(int argc, char** argv) {
         ICompressCoder* e = (ICompressCoder*)o; ICompressSetCoderProperties* s = nullptr; ICompressWriteCoderProperties* w = nullptr;
         CHECK(e->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&s) == S_OK && e->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&w) == S_OK);
         PROPID ids2[2] = { NCoderPropID::kLevel, NCoderPropID::kNumThreads }; PROPVARIANT pv2[2]; memset(pv2, 0, sizeof(pv2));
-        pv2[0].vt = VT_UI4; pv2[0].ulVal = 5; pv2[1].vt = VT_UI4; pv2[1].ulVal = 8;
+        pv2[0].vt = VT_UI4; pv2[0].ulVal = (UInt32)(argc > 4 ? atoi(argv[4]) : 5); pv2[1].vt = VT_UI4; pv2[1].ulVal = 8;
         CHECK(s->SetCoderProperties(ids2, pv2, 2) == S_OK);
         MemOut ph; CHECK(w->WriteCoderProperties(&ph) == S_OK && ph.d.size() == 1 && ph.d[0] == 16);
         MemIn in(input); MemOut packed; Progress prog;

@@ -65,22 +65,23 @@ def test_icompresscoder_roundtrip(pkg, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method", ["lzma2", "flzma2"])
-def test_icompresscoder_roundtrip_lzma2(pkg, tmp_path, method):
+@pytest.mark.parametrize("method,level,price_parse", [("lzma2", 5, True), ("lzma2", 4, False), ("flzma2", 5, True), ("flzma2", 2, False)])
+def test_icompresscoder_roundtrip_lzma2(pkg, tmp_path, method, level, price_parse):
     """Method 21 through the codec module (CreateEncoder/CreateDecoder by index, as LoadCodecs.cpp does); the packed
-    stream must also be accepted by the reference decoder and liblzma."""
+    stream must also be accepted by the reference decoder and liblzma.  The level picks the parse as the reference's
+    normalisation does (LzmaEnc.c:97 algo = level < 5 ? 0 : 1; fast-lzma2's table: fast below level 3)."""
     import lzma
     data = pkg.corpus.g2(3 * (1 << 20) + 777).tobytes() + bytes(200000) + pkg.corpus.entropy_class(1, 150000).tobytes()
     src = tmp_path / "in.bin"; packed = tmp_path / "packed.lzma2"
     src.write_bytes(data)
-    out = subprocess.run([os.path.join(PKG, "build", "coder_roundtrip"), os.path.join(PKG, "libb200z_7z.so"), str(src), str(packed), "5", method],
+    out = subprocess.run([os.path.join(PKG, "build", "coder_roundtrip"), os.path.join(PKG, "libb200z_7z.so"), str(src), str(packed), str(level), method],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "roundtrip ok" in out.stdout, out.stderr + out.stdout
     comp = packed.read_bytes()
     assert lzma.LZMADecompressor(format=lzma.FORMAT_RAW, filters=[{"id": lzma.FILTER_LZMA2, "dict_size": 1 << 20}]).decompress(comp) == data
     if helpers.ref_lzma_available():
         assert helpers.ref_lzma2_decompress(comp, len(data), 16) == (data, len(comp))
-    assert comp == helpers.oracle_lzma2_compress(data)[1]
+    assert comp == helpers.oracle_lzma2_compress(data, flags=1 | (2 << 8) | (0x10 if price_parse else 0))[1]
 
 
 def test_binding_parameter_ids_match_header(pkg):
