@@ -67,7 +67,11 @@ void b200z_destroy(b200z_ctx* ctx) {
 int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     if (!ctx) return B200Z_E_PARAM;
     switch (param) {
-    case B200Z_P_LEVEL:     if (v < 1 || v > 22) return fail(ctx, B200Z_E_PARAM, "level out of range%s"); ctx->level = (int)v; return 0;
+    case B200Z_P_LEVEL:     if (v < 1 || v > 22) return fail(ctx, B200Z_E_PARAM, "level out of range%s"); ctx->level = (int)v;
+                            // levels 1-7: the level-3-class greedy/lazy stage M; 8-22: the price-based stage C + stage Z
+                            ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v >= B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
+    case B200Z_P_ZSTD_PARSE: if (v < 0 || v > 1) return fail(ctx, B200Z_E_PARAM, "zstd parse mode out of range%s");
+                            ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
     case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");
                             ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v; return 0;
     case B200Z_P_HASHLOG_L: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
@@ -97,6 +101,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_FLAGS: *v = ctx->geom.flags & 3u; return 0;
     case B200Z_P_LZMA2_SLICELOG: *v = B2Z_LZ2_SLICELOG(ctx->geom.flags); return 0;
     case B200Z_P_LZMA2_PARSE: *v = (ctx->geom.flags & B2Z_FLAG_LZ2_OPT) ? 1 : 0; return 0;
+    case B200Z_P_ZSTD_PARSE: *v = (ctx->geom.flags & B2Z_FLAG_ZSTD_OPT) ? 1 : 0; return 0;
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
@@ -123,7 +128,13 @@ static uint32_t match_warps(const b200z_ctx* ctx, uint64_t nFrames) {
     return (uint32_t)(nFrames < cap ? nFrames : cap);
 }
 
-// stage C of the price-based LZMA2 parse: every resident frame-warp owns 7-30 MB of tables
+// does this batch parse by price (stage C + stage P / stage Z) instead of the greedy stage M?  (the per-file batch mode, which
+// sets frameSizes, always runs stage M)
+static bool price_parse(const EncGeom& g, int codec) {
+    return codec == 1 ? (g.flags & B2Z_FLAG_LZ2_OPT) != 0 : ((g.flags & B2Z_FLAG_ZSTD_OPT) != 0 && !g.frameSizes);
+}
+
+// stage C of the price-based parses: every resident frame-warp owns 7-30 MB of tables
 static uint32_t cand_warps(const b200z_ctx* ctx, uint64_t nFrames) {
     const uint64_t cap = (uint64_t)ctx->smCount * 8u;
     return (uint32_t)(nFrames < cap ? nFrames : cap);
@@ -136,7 +147,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     const uint32_t nWarps = match_warps(ctx, nFrames);
     const size_t tableBytes = (size_t)64 << ctx->geom.rowLog;           // row-hash table: 2^rowLog rows of 64 bytes per frame-warp
     int bad = 0;
-    if (codec == 1 && (ctx->geom.flags & B2Z_FLAG_LZ2_OPT)) {           // price-based parse: stage C's tables and candidate words
+    if (price_parse(ctx->geom, codec)) {                                // price-based parse: stage C's tables and candidate words
         bad |= ctx->tables.reserve(lzma2_cand_table_bytes(ctx->geom, cand_warps(ctx, nFrames)));
         bad |= ctx->cand.reserve((size_t)nFrames * F * LZP_NCAND * 4u);
     } else
@@ -167,13 +178,15 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     const uint32_t nWarps = match_warps(ctx, nFrames);
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev[0], st));
-    if (codec == 1 && (g.flags & B2Z_FLAG_LZ2_OPT)) {
-        // method 21, price-based parse: stage C (candidates) + stage P (dynamic programme) instead of the greedy stage M
+    if (price_parse(g, codec)) {
+        // price-based parse: stage C (candidates) + stage P (method 21) / stage Z (zstd) instead of the greedy stage M
         if (ready) { CU(cudaEventRecord(ctx->pe[1], ctx->stream2)); CU(cudaStreamWaitEvent(st, ctx->pe[1], 0)); }   // the whole upload first
         launch_lzma2_cand(d_src, n, g, (uint32_t*)ctx->tables.p, cand_warps(ctx, nFrames), (uint32_t*)ctx->cand.p, st);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[4], st));
-        CU(launch_lzma2_parse(d_src, n, g, (const uint32_t*)ctx->cand.p, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p, st));
+        if (codec == 1) CU(launch_lzma2_parse(d_src, n, g, (const uint32_t*)ctx->cand.p, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p, st));
+        else CU(launch_zstd_enc_parse(d_src, n, g, (const uint32_t*)ctx->cand.p, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
+                                      (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, st));
         CU(cudaEventRecord(ctx->ev[1], st));
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 2;
         if (stageMOnly) {
@@ -235,7 +248,8 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         CU(cudaStreamSynchronize(st));
         *produced = out;
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[1]); ctx->stat[B200Z_S_ENC_PARSE_MS] += ms;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stat[B200Z_S_ENC_ENTROPY_MS] += ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stat[B200Z_S_ENC_ASSEMBLE_MS] += ms;
     } else {
@@ -267,7 +281,9 @@ int b200z_zstd_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize
     }
     // batches are whole frames
     const uint64_t F = 1ull << ctx->geom.frameLog;
-    uint64_t batch = 1ull << ctx->batchLog; if (batch < F) batch = F;
+    uint64_t batch = 1ull << ctx->batchLog;
+    if ((ctx->geom.flags & B2Z_FLAG_ZSTD_OPT) && batch > (1ull << 30)) batch = 1ull << 30;   // stage C keeps 16 bytes per input byte
+    if (batch < F) batch = F;
     uint64_t done = 0, outPos = 0;
     while (done < srcSize) {
         const uint64_t n = (srcSize - done) < batch ? (srcSize - done) : batch;
@@ -290,7 +306,9 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
     if (dstCap < bound) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_bound%s");
     CU(cudaSetDevice(ctx->device));
     const uint64_t F = 1ull << ctx->geom.frameLog;
-    uint64_t batch = 1ull << ctx->hostBatchLog; if (batch < F) batch = F;
+    uint64_t batch = 1ull << ctx->hostBatchLog;
+    if ((ctx->geom.flags & B2Z_FLAG_ZSTD_OPT) && batch > (1ull << 30)) batch = 1ull << 30;
+    if (batch < F) batch = F;
     if (srcSize <= batch) {
         // one batch: the upload is cut into chunks on stream2, each followed by a flag write; stage M starts at once and
         // its frame-warps wait for their chunk, so the H2D time hides under the match kernel

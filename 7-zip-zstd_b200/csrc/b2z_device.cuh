@@ -75,6 +75,16 @@ __device__ __forceinline__ uint32_t match_len_pv(const uint64_t* __restrict__ w,
     return len < maxLen ? len : maxLen;
 }
 
+// common-prefix length of base[q..] and base[p..] beyond the first `from` bytes (known equal), capped at maxLen; warp-uniform
+__device__ __forceinline__ uint32_t warp_extend(const uint8_t* __restrict__ base, uint32_t q, uint32_t p, uint32_t from, uint32_t maxLen, uint32_t lane) {
+    for (uint32_t s = from;; s += 32u) {
+        const uint32_t k = s + lane;
+        const bool eq = k < maxLen && __ldg(base + q + k) == __ldg(base + p + k);
+        const uint32_t mism = __ballot_sync(B2Z_FULL, !eq);
+        if (mism) return s + (uint32_t)(__ffs((int)mism) - 1);
+    }
+}
+
 __device__ __forceinline__ uint32_t highbit32(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, uint32_t* total) {

@@ -26,6 +26,12 @@ void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& 
                            uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit,
                            const uint32_t* ready /* null, or per-chunk arrival flags */, uint32_t readyShift, cudaStream_t st);
 
+// stage Z (zstd_enc_parse.cu): the price-based parse, one warp per 128 KiB block, on stage C's candidate words (lzma2_parse.cu);
+// fills the same arrays as stage M.  Dense frames only.
+size_t zstd_enc_parse_smem_bytes();
+cudaError_t launch_zstd_enc_parse(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint32_t* cand,
+                                  uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, cudaStream_t st);
+
 // stage E: one warp per 128 KiB block -> compressed block (with 3-byte header) in its slot
 void launch_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, const EncGeom& g,
                              const uint64_t* seqs, const uint32_t* nseq, const uint8_t* lits, const uint32_t* nlit,

@@ -52,6 +52,9 @@
 
 /* flags bit 4: method 21 parses by price (stage C candidates + stage P dynamic programme) instead of the greedy stage M */
 #define B2Z_FLAG_LZ2_OPT 0x10u
+/* flags bit 5: the Zstandard encoder parses by price (stage C candidates + stage Z dynamic programme per block) instead of stage M */
+#define B2Z_FLAG_ZSTD_OPT 0x20u
+#define B2Z_ZSTD_OPT_LEVEL 8       /* B200Z_P_LEVEL at or above this selects it */
 
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL

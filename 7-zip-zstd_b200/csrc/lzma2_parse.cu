@@ -126,16 +126,6 @@ struct ParseSmem {                       // one warp's working set
 };
 size_t lzma2_parse_smem_bytes() { return sizeof(ParseSmem); }
 
-// common-prefix length of base[q..] and base[p..] beyond the first `from` bytes (known equal), capped at maxLen; warp-uniform
-__device__ __forceinline__ uint32_t warp_extend(const uint8_t* __restrict__ base, uint32_t q, uint32_t p, uint32_t from, uint32_t maxLen, uint32_t lane) {
-    for (uint32_t s = from;; s += 32u) {
-        const uint32_t k = s + lane;
-        const bool eq = k < maxLen && __ldg(base + q + k) == __ldg(base + p + k);
-        const uint32_t mism = __ballot_sync(B2Z_FULL, !eq);
-        if (mism) return s + (uint32_t)(__ffs((int)mism) - 1);
-    }
-}
-
 __global__ void __launch_bounds__(32)
 lzma2_parse_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint32_t* __restrict__ cand,
                    uint64_t* __restrict__ seqs, uint32_t* __restrict__ nseq, uint32_t nChains) {

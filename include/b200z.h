@@ -39,7 +39,7 @@ extern "C" {
 #define B200Z_E_CHECKSUM   -8   /* content checksum mismatch                 (S_FALSE)       */
 
 /* parameters (b200z_set_param) */
-#define B200Z_P_LEVEL       1   /* 1..22; every level currently maps to the level-3 (dfast-class) parser */
+#define B200Z_P_LEVEL       1   /* 1..22.  1-7: the level-3-class greedy/lazy parse (stage M); 8-22: the price-based parse (sets B200Z_P_ZSTD_PARSE) */
 #define B200Z_P_FRAMELOG    2   /* log2 of the independent frame ("job") size, 17..24, default 22       */
 #define B200Z_P_HASHLOG_L   3   /* accepted for compatibility (dual-table finder of the first version); unused */
 #define B200Z_P_HASHLOG_S   4   /* accepted for compatibility; unused                                        */
@@ -54,6 +54,9 @@ extern "C" {
 #define B200Z_P_LZMA2_PARSE 12  /* LZMA2 encoder parse: 0 = greedy/lazy on the finder shared with the zstd path (default), 1 = price-based:
                                    nearest-occurrence candidates by 3/4/6/8-byte keys + a windowed dynamic programme over the adaptive
                                    model -- the role of LzmaEnc.c:1225 GetOptimum / fast-lzma2 lzma2_enc.c:949 LZMA_optimalParse */
+#define B200Z_P_ZSTD_PARSE  13  /* Zstandard encoder parse: 0 = stage M (greedy/lazy row-hash finder), 1 = price-based: nearest-occurrence
+                                   candidates + a per-block dynamic programme over adaptive code statistics -- the role of
+                                   zstd_opt.c:1077 ZSTD_compressBlock_opt_generic.  B200Z_P_LEVEL sets it (>= 8); set it after the level to override */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
@@ -67,7 +70,7 @@ extern "C" {
 #define B200Z_S_H2D_BYTES       7
 #define B200Z_S_D2H_BYTES       8
 #define B200Z_S_DEC_PREPASS_MS  9
-#define B200Z_S_ENC_PARSE_MS    10  /* LZMA2 price-based parse: stage P (stage C is counted as ENC_MATCH_MS) */
+#define B200Z_S_ENC_PARSE_MS    10  /* price-based parses: stage P / stage Z (stage C is counted as ENC_MATCH_MS) */
 
 typedef struct b200z_ctx b200z_ctx;
 

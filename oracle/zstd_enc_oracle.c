@@ -203,7 +203,8 @@ int64_t b2zo_zstd_find_sequences(const void *srcv, size_t srcSize, const b2zo_en
     size_t F = (size_t)1 << P->frameLog, blkBase = 0;
     for (size_t f0 = 0; f0 < srcSize; f0 += F) {
         size_t fn = srcSize - f0 < F ? srcSize - f0 : F;
-        find_sequences_frame(src + f0, fn, P, seqs + blkBase * B2Z_MAXSEQ, nseq + blkBase, lits + f0, nlit + blkBase);
+        if (P->flags & B2Z_FLAG_ZSTD_OPT) b2zo_zstd_parse_frame(src + f0, (uint32_t)fn, P, NULL, seqs + blkBase * B2Z_MAXSEQ, nseq + blkBase, lits + f0, nlit + blkBase);
+        else find_sequences_frame(src + f0, fn, P, seqs + blkBase * B2Z_MAXSEQ, nseq + blkBase, lits + f0, nlit + blkBase);
         blkBase += (fn + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
     }
     return (int64_t)blkBase;
@@ -610,7 +611,8 @@ int64_t b2zo_zstd_compress(void *dstv, size_t dstCap, const void *srcv, size_t s
         op += write_frame_header(op, fn, P);
         if (fn == 0) { wr24(op, 1); op += 3; }
         else {
-            find_sequences_frame(frame, fn, P, seqs, nseq, lits, nlit);
+            if (P->flags & B2Z_FLAG_ZSTD_OPT) b2zo_zstd_parse_frame(frame, (uint32_t)fn, P, NULL, seqs, nseq, lits, nlit);
+            else find_sequences_frame(frame, fn, P, seqs, nseq, lits, nlit);
             size_t nblk = (fn + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
             for (size_t b = 0; b < nblk; b++) {
                 size_t bs = b * ZF_BLOCK_MAX, bn = fn - bs < ZF_BLOCK_MAX ? fn - bs : ZF_BLOCK_MAX;

@@ -5,6 +5,7 @@
 #include "cuemu.h"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_match.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
 
 using namespace b2z;
 
@@ -41,6 +42,16 @@ uint64_t emu_lzma2_parse(const uint8_t* src, uint64_t srcSize, uint32_t frameLog
     const uint32_t spf = bpf / B2Z_LZ2_SLICE_BLOCKS(frameLog, flags), nChains = nFrames * spf;
     memset(nseq, 0, (size_t)nFrames * bpf * sizeof(uint32_t));
     return cuemu::launch(dim3(nChains), dim3(32), lzma2_parse_smem_bytes(), [&] { lzma2_parse_kernel(src, srcSize, g, cand, seqs, nseq, nChains); });
+}
+
+// stage Z (zstd_enc_parse_kernel)
+uint64_t emu_zstd_enc_parse(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint32_t* cand,
+                            uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit) {
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const uint64_t F = 1ull << frameLog;
+    const uint32_t nFrames = (uint32_t)((srcSize + F - 1) >> frameLog);
+    const uint32_t nBlocks = (nFrames - 1u) * (uint32_t)(F >> 17) + (uint32_t)((srcSize - (uint64_t)(nFrames - 1u) * F + B2Z_BLOCK - 1u) / B2Z_BLOCK);
+    return cuemu::launch(dim3(nBlocks), dim3(32), zstd_enc_parse_smem_bytes(), [&] { zstd_enc_parse_kernel(src, srcSize, g, cand, seqs, nseq, lits, nlit, nBlocks); });
 }
 
 }

@@ -4,7 +4,8 @@ not a CPU path of the product (libb200z.so is nvcc-only and fails without a devi
 tests: it cannot see timing, memory-model races between warps or anything about the hardware.
 
   * zstd_enc_match_kernel (stage M) is GPU-verified against the oracle; here it validates the emulator itself.
-  * lzma2_cand_kernel / lzma2_parse_kernel (stage C / stage P of the price-based LZMA2 parse) were developed against it."""
+  * lzma2_cand_kernel / lzma2_parse_kernel (stage C / stage P of the price-based LZMA2 parse) and zstd_enc_parse_kernel
+    (stage Z, the price-based Zstandard parse) were developed against it."""
 import ctypes
 import os
 import subprocess
@@ -27,6 +28,7 @@ def emu():
     E.emu_zstd_enc_match.restype = u64; E.emu_zstd_enc_match.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp, vp, vp, vp]
     E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]
     E.emu_lzma2_parse.restype = u64; E.emu_lzma2_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp]
+    E.emu_zstd_enc_parse.restype = u64; E.emu_zstd_enc_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp]
     return E
 
 
@@ -96,3 +98,41 @@ def test_emulated_parse_edge_inputs(pkg, emu):
         assert np.array_equal(nsE[:nb], nsO[:nb]), n
         for b in range(nb):
             assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), (n, b)
+
+
+ZOPT = 0x20
+
+
+@pytest.mark.parametrize("fl", [17, 18])
+def test_emulated_stage_z_equals_the_oracle(pkg, emu, fl):
+    data = _mixed(pkg, 200_000) + bytes(150_000); n = len(data)
+    flags = 1 | ZOPT
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    seqO, nsO, litO, nlO = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl, flags=flags)
+    F = 1 << fl; nfr = (n + F - 1) // F
+    cand = np.zeros(nfr * F * 4, dtype=np.uint32)
+    emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, 2, cand.ctypes.data)
+    seqE = np.zeros_like(seqO); nsE = np.full_like(nsO, 0xFFFFFFFF); nlE = np.full_like(nlO, 0xFFFFFFFF); litE = np.zeros(n + 64, dtype=np.uint8)
+    assert emu.emu_zstd_enc_parse(src.ctypes.data, n, fl, flags, cand.ctypes.data, seqE.ctypes.data, nsE.ctypes.data, litE.ctypes.data, nlE.ctypes.data) > 0
+    assert np.array_equal(nsE, nsO) and np.array_equal(nlE, nlO) and int(nsO.sum()) > 10_000
+    for b in range(len(nsO)):
+        assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), b
+        assert np.array_equal(litE[b * 131072:b * 131072 + nlO[b]], litO[b * 131072:b * 131072 + nlO[b]]), b
+
+
+def test_emulated_stage_z_edge_inputs(pkg, emu):
+    cases = [b"a", b"ab", b"abcabcabcabc", bytes(70_000), pkg.corpus.g2(131073).tobytes(), b"\x01" * 33, pkg.corpus.g2(40_000).tobytes() * 3,
+             pkg.corpus.entropy_class(1, 50_000).tobytes()]
+    for data in cases:
+        n = len(data); fl = 17; flags = 1 | ZOPT
+        src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+        seqO, nsO, litO, nlO = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl, flags=flags)
+        nfr = (n + (1 << fl) - 1) >> fl
+        cand = np.zeros(nfr * (1 << fl) * 4, dtype=np.uint32)
+        emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, 1, cand.ctypes.data)
+        seqE = np.zeros_like(seqO); nsE = np.full_like(nsO, 0xFFFFFFFF); nlE = np.full_like(nlO, 0xFFFFFFFF); litE = np.zeros(n + 64, dtype=np.uint8)
+        emu.emu_zstd_enc_parse(src.ctypes.data, n, fl, flags, cand.ctypes.data, seqE.ctypes.data, nsE.ctypes.data, litE.ctypes.data, nlE.ctypes.data)
+        assert np.array_equal(nsE, nsO) and np.array_equal(nlE, nlO), n
+        for b in range(len(nsO)):
+            assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), (n, b)
+            assert np.array_equal(litE[b * 131072:b * 131072 + nlO[b]], litO[b * 131072:b * 131072 + nlO[b]]), (n, b)
