@@ -55,7 +55,7 @@ def test_ratio_class(pkg):
     l3 = len(H.oracle_compress(data))
     opt = len(H.oracle_compress(data, flags=1 | ZOPT))
     opt22 = len(H.oracle_compress(data, flags=1 | ZOPT, frameLog=22, windowLog=22))
-    assert opt < 0.95 * l3 and opt22 < opt                      # measured 2.53 against 2.39; 4 MiB frames 2.60
+    assert opt < 0.95 * l3 and opt22 < opt                      # measured 2.53 against 2.39; 4 MiB frames 2.61
     if H.ref_available():
         ref9 = len(H.ref_compress(data, level=9, windowLog=20))
         ref16 = len(H.ref_compress(data, level=16, windowLog=20))
