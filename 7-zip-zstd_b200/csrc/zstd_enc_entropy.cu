@@ -624,6 +624,7 @@ zstd_enc_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGe
     }
 }
 
+#ifndef B2Z_CUEMU
 void launch_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, const EncGeom& g,
                              const uint64_t* seqs, const uint32_t* nseq, const uint8_t* lits, const uint32_t* nlit,
                              uint8_t* slots, uint32_t* slotSize, uint32_t nBlocks, cudaStream_t st) {
@@ -632,5 +633,6 @@ void launch_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, const EncGeom
     if (grid > 148u * 16u) grid = 148u * 16u;
     zstd_enc_entropy_kernel<<<grid, B2Z_ENT_WARPS * 32, 0, st>>>(src, srcSize, g, seqs, nseq, lits, nlit, slots, slotSize, nBlocks);
 }
+#endif
 
 }  // namespace b2z

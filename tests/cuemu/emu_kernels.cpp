@@ -6,6 +6,7 @@
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_match.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
 
 using namespace b2z;
 
@@ -53,5 +54,15 @@ uint64_t emu_zstd_enc_parse(const uint8_t* src, uint64_t srcSize, uint32_t frame
     const uint32_t nBlocks = (nFrames - 1u) * (uint32_t)(F >> 17) + (uint32_t)((srcSize - (uint64_t)(nFrames - 1u) * F + B2Z_BLOCK - 1u) / B2Z_BLOCK);
     return cuemu::launch(dim3(nBlocks), dim3(32), zstd_enc_parse_smem_bytes(), [&] { zstd_enc_parse_kernel(src, srcSize, g, cand, seqs, nseq, lits, nlit, nBlocks); });
 }
+
+// stage E (zstd_enc_entropy_kernel): per-block compressed bodies in slots of B2Z_SLOT bytes.  GPU-verified on stage M's sequences;
+// here it is also fed stage Z's
+uint64_t emu_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint64_t* seqs, const uint32_t* nseq,
+                              const uint8_t* lits, const uint32_t* nlit, uint8_t* slots, uint32_t* slotSize, uint32_t nBlocks) {
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    return cuemu::launch(dim3((nBlocks + B2Z_ENT_WARPS - 1) / B2Z_ENT_WARPS), dim3(B2Z_ENT_WARPS * 32), 0,
+                         [&] { zstd_enc_entropy_kernel(src, srcSize, g, seqs, nseq, lits, nlit, slots, slotSize, nBlocks); });
+}
+uint32_t emu_slot_bytes() { return B2Z_SLOT; }
 
 }

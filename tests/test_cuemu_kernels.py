@@ -29,6 +29,8 @@ def emu():
     E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]
     E.emu_lzma2_parse.restype = u64; E.emu_lzma2_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp]
     E.emu_zstd_enc_parse.restype = u64; E.emu_zstd_enc_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp]
+    E.emu_zstd_enc_entropy.restype = u64; E.emu_zstd_enc_entropy.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp, vp, u32]
+    E.emu_slot_bytes.restype = u32
     return E
 
 
@@ -136,3 +138,30 @@ def test_emulated_stage_z_edge_inputs(pkg, emu):
         for b in range(len(nsO)):
             assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), (n, b)
             assert np.array_equal(litE[b * 131072:b * 131072 + nlO[b]], litO[b * 131072:b * 131072 + nlO[b]]), (n, b)
+
+
+@pytest.mark.parametrize("fl,flags", [(18, 1 | ZOPT), (17, 1 | ZOPT), (18, 1)])
+def test_emulated_stage_e_codes_stage_z_sequences_like_the_oracle(pkg, emu, fl, flags):
+    """stage E (zstd_enc_entropy_kernel) is GPU-verified on stage M's sequences; stage Z hands it shapes stage M never produces
+    (length-3 matches, tiny offsets, up to 32 768 sequences per block): its emulated output on those must be the oracle's blocks."""
+    import struct
+    data = (pkg.corpus.g2(600_000).tobytes() + bytes(5000) + pkg.corpus.entropy_class(3, 100_000).tobytes() + b"ab" * 3000
+            + pkg.corpus.entropy_class(1, 140_000).tobytes() + bytes(200_000) + pkg.corpus.entropy_class(2, 100_000).tobytes())
+    n = len(data); F = 1 << fl; SLOT = emu.emu_slot_bytes()
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    seqO, nsO, litO, nlO = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl, flags=flags)
+    nblk = len(nsO)
+    lits = np.zeros(n + 64, dtype=np.uint8); lits[:n] = litO
+    slots = np.zeros(nblk * SLOT, dtype=np.uint8); ssz = np.zeros(nblk, dtype=np.uint32)
+    assert emu.emu_zstd_enc_entropy(src.ctypes.data, n, fl, flags, seqO.ctypes.data, nsO.ctypes.data, lits.ctypes.data, nlO.ctypes.data,
+                                    slots.ctypes.data, ssz.ctypes.data, nblk) > 0
+    comp = H.oracle_compress(data, frameLog=fl, windowLog=fl, flags=flags)
+    ip = 0; blk = 0
+    for f0 in range(0, n, F):                                       # the oracle's frames: [12-byte size hint][10-byte header, blocks ...]
+        assert comp[ip:ip + 4] == b"\x50\x2a\x4d\x18"
+        fsize = struct.unpack("<I", comp[ip + 8:ip + 12])[0]; ip += 12
+        body = comp[ip + 10:ip + fsize]; ip += fsize
+        nb = (min(F, n - f0) + 131071) // 131072
+        mine = b"".join(slots[b * SLOT:b * SLOT + ssz[b]].tobytes() for b in range(blk, blk + nb)); blk += nb
+        assert mine == body, f0
+    assert ip == len(comp) and blk == nblk
