@@ -34,6 +34,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=1024, help="bounded sample for the CPU reference arm")
     ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
                     help="zstd: method 4F71101 level 3 (the headline, BASELINE configs[1]); lzma2: method 21 (configs[3])")
+    ap.add_argument("--level", type=int, default=3, help="--codec zstd: B200Z_P_LEVEL (1-7 stage M, the measured headline; 8-22 the price-based stage C + stage Z)")
     ap.add_argument("--lzma2-parse", type=int, default=0, choices=[0, 1],
                     help="--codec lzma2: 0 = greedy parse (the measured round-1 line), 1 = price-based parse (stage C + stage P, DESIGN.md 2c)")
     ap.add_argument("--frame-log", type=int, default=0, help="log2 of the independent frame / block size (default: the library's, 20)")
@@ -153,7 +154,7 @@ def main():
     metric_name = "LZMA2 (method 21) encode+decode throughput" if lz else "zstd-L3 encode+decode throughput"
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     unit_bytes = a.size_mib << 20
-    workload = f"zstd level 3, {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 128 KiB blocks"
+    workload = f"zstd level {a.level}, {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 128 KiB blocks"
     if lz:
         workload = f"LZMA2 / Fast-LZMA2 coder (method 21), {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 1 MiB dictionary-reset blocks"
 
@@ -195,6 +196,8 @@ def main():
     codec = pkg.Codec(local)
     if a.frame_log:
         codec.set("frame_log", a.frame_log); codec.set("window_log", a.frame_log)
+    if not lz and a.level != 3:
+        codec.set("level", a.level)
     if lz and a.lzma2_slice_log >= 0:
         codec.set("lzma2_slice_log", a.lzma2_slice_log)
     if lz and a.lzma2_parse:
@@ -281,13 +284,14 @@ def main():
     peak = peaks.get("hbm_gbs", 6650.0); peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
     # LZMA2: the dominant kernel is stage R (lzma2_enc_range_kernel: one serial range-coder chain per 1 MiB block)
     #        with the price-based parse it is stage P (lzma2_parse_kernel: one dynamic-programme chain per slice)
-    dom_kernel = ("lzma2_parse_kernel" if a.lzma2_parse else "lzma2_enc_range_kernel") if lz else "zstd_enc_match_kernel"
-    match_ms = ((stats["parse_ms"] if a.lzma2_parse else stats["entropy_ms"]) if lz else stats["match_ms"]) / a.steps
+    zparse = (not lz) and a.level >= 8
+    dom_kernel = ("lzma2_parse_kernel" if a.lzma2_parse else "lzma2_enc_range_kernel") if lz else ("zstd_enc_parse_kernel" if zparse else "zstd_enc_match_kernel")
+    match_ms = ((stats["parse_ms"] if a.lzma2_parse else stats["entropy_ms"]) if lz else (stats["parse_ms"] if zparse else stats["match_ms"])) / a.steps
     algo_bytes = unit_bytes * (1.0 + 1.0 / ratio)
     achieved = algo_bytes / 1e9 / (match_ms / 1e3) if match_ms > 0 else 0.0
     traffic = None
     try:
-        if not (lz and a.lzma2_parse):                              # no ncu capture of stage P yet
+        if not (lz and a.lzma2_parse) and not zparse:               # no ncu capture of stage P / stage Z yet
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lzma2_range_traffic.json" if lz else "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
     except Exception:
         pass
@@ -295,7 +299,7 @@ def main():
         "metric": metric_name, "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "global_uncompressed_bytes_per_step": world * unit_bytes, "frame_log": codec.get("frame_log"),
-                   "parallelism": f"{world} independent shard(s), no collective", **({"lzma2_parse": a.lzma2_parse} if lz else {}), "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
+                   "parallelism": f"{world} independent shard(s), no collective", **({"lzma2_parse": a.lzma2_parse} if lz else {"level": a.level}), "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
                    "ratio": ratio, "enc_MBps": units_mb / t_enc, "dec_MBps": units_mb / t_dec,
                    "kernel_ms_per_step": {k: v / a.steps for k, v in stats.items() if k != "launches"}},
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
