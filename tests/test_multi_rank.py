@@ -25,10 +25,12 @@ def _worker(rank, world, port, q):
     shard = pkg.corpus.g2(UNIT, offset=rank * UNIT, threads=2)
     comp = helpers.oracle_compress(shard.tobytes())            # stands in for the rank's GPU (bytes are identical by test_gpu_*)
     lz = helpers.oracle_lzma2_compress(shard.tobytes())[1]     # method 21: the rank's chunk stream (ends with its own 0x00)
+    zp = helpers.oracle_compress(shard.tobytes(), flags=1 | 0x20)                    # the price-based parses shard the same way
+    lp = helpers.oracle_lzma2_compress(shard.tobytes(), flags=1 | (2 << 8) | 0x10)[1]
     t = torch.tensor([0.25 + rank, float(len(comp))], dtype=torch.float64)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    q.put((rank, hashlib.sha256(shard.tobytes()).hexdigest(), comp, float(tmax[0]), float(tsum[1]), lz))
+    q.put((rank, hashlib.sha256(shard.tobytes()).hexdigest(), comp, float(tmax[0]), float(tsum[1]), lz, zp, lp))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -45,7 +47,7 @@ def test_two_rank_sharding(pkg):
         p.join(timeout=60)
         assert p.exitcode == 0
     whole = pkg.corpus.g2(world * UNIT).tobytes()
-    for r, sha, comp, tmax, tsum, _lz in res:
+    for r, sha, comp, tmax, tsum, _lz, _zp, _lp in res:
         assert sha == hashlib.sha256(whole[r * UNIT:(r + 1) * UNIT]).hexdigest()      # shards tile the stream
         assert tmax == 0.25 + (world - 1)                                              # max over ranks
         assert tsum == sum(len(x[2]) for x in res)
@@ -56,3 +58,6 @@ def test_two_rank_sharding(pkg):
     lzj = b"".join(x[5][:-1] for x in res) + b"\x00"
     prop, want = helpers.oracle_lzma2_compress(whole)
     assert lzj == want and helpers.oracle_lzma2_decompress(lzj, len(whole), prop)[0] == whole
+    # the price-based parses (stage C + stage Z / stage P): frames and dictionary-reset blocks are still the only units
+    assert b"".join(x[6] for x in res) == helpers.oracle_compress(whole, flags=1 | 0x20)
+    assert b"".join(x[7][:-1] for x in res) + b"\x00" == helpers.oracle_lzma2_compress(whole, flags=1 | (2 << 8) | 0x10)[1]
