@@ -150,8 +150,9 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     if (price_parse(ctx->geom, codec)) {                                // price-based parse: stage C's tables and candidate words
         bad |= ctx->tables.reserve(lzma2_cand_table_bytes(ctx->geom, cand_warps(ctx, nFrames)));
         bad |= ctx->cand.reserve((size_t)nFrames * F * LZP_NCAND * 4u);
-    } else
-    bad |= ctx->tables.reserve(tableBytes * nWarps);
+    } else {
+        bad |= ctx->tables.reserve(tableBytes * nWarps);
+    }
     bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);
     bad |= ctx->nseq.reserve(nBlocks * 4);
     bad |= ctx->lits.reserve(nBlocks * (size_t)B2Z_BLOCK);
@@ -197,12 +198,12 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
             return 0;
         }
     } else {
-    launch_zstd_enc_match(d_src, n, g, (uint32_t*)ctx->tables.p, nWarps, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
-                          (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, ready, readyShift, st);
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(ctx->ev[4], st));
-    CU(cudaEventRecord(ctx->ev[1], st));
-    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        launch_zstd_enc_match(d_src, n, g, (uint32_t*)ctx->tables.p, nWarps, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
+                              (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, ready, readyShift, st);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[4], st));                      // no separate parse stage: ENC_PARSE_MS stays ~0
+        CU(cudaEventRecord(ctx->ev[1], st));
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
     }
     if (!stageMOnly && codec == 1) {
         // LZMA2: stage R (range coding, one thread per frame) + assembly of the frame slots into one chunk stream

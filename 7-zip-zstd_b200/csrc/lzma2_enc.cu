@@ -2,7 +2,8 @@
 //
 // A frame (2^frameLog input bytes) becomes one dictionary-reset LZMA2 block -- the independent unit the reference's own
 // MT coders use (Lzma2Enc.c:241-330 block split; fast-lzma2 slices, lzma2_enc.c:1937-2099).  Stage M (zstd_enc_match.cu,
-// shared with the zstd path) has already found the frame's sequences; here one thread per frame codes them as LZMA
+// shared with the zstd path) -- or, with B2Z_FLAG_LZ2_OPT, stage C + stage P (lzma2_parse.cu: the price-based parse) -- has
+// already found the frame's sequences; here one thread per frame codes them as LZMA
 // packets with the adaptive binary range coder, which is a strictly serial chain of ~100 instructions per input byte:
 // the parallelism is across frames (thousands per batch), not inside one.
 //   model      11-bit probabilities in shared memory (16 KiB, 13 frames/SM) or, when there are more frames than that
