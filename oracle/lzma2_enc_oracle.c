@@ -36,6 +36,7 @@ typedef struct {
     uint32_t state, rep[4];
     uint64_t low; uint32_t range, cacheSize; uint8_t cache;
     uint8_t *out; size_t op;
+    uint32_t modelResets;                /* chunk_open calls that initialised the model (test tap) */
 } enc_t;
 
 static void rc_shift_low(enc_t *e) {
@@ -125,6 +126,7 @@ static void chunk_open(chunker *c, uint32_t pos) {
     c->hdr = (c->needDict || c->needProps) ? 6 : 5;
     if (c->needDict || c->needProps || c->needState) {
         for (size_t i = 0; i < sizeof(e->probs) / 2; i++) e->probs[i] = PROB_INIT;
+        e->modelResets++;
         e->state = 0; e->rep[0] = e->rep[1] = e->rep[2] = e->rep[3] = 0;
     }
     e->op += c->hdr;
@@ -191,6 +193,21 @@ static size_t encode_frame(enc_t *e, const uint8_t *base, uint32_t n, const uint
     }
     chunk_close(&c, pos);
     return e->op;
+}
+
+/* Test tap: the model stage R ends a frame with (probabilities, state, rep0-3) after coding the given sequences, and how often it
+ * initialised the model on the way (slices + raw-chunk fallbacks).  Lets tests pin stage P's simulated model (b2z_lzma_model.h:
+ * lzm_commit_*) to this independent statement of the coder. */
+int64_t b2zo_lzma2_final_model(const void *basev, uint32_t n, const b2zo_enc_params *P, const uint64_t *seqs, const uint32_t *nseq,
+                               uint16_t *probsOut, uint32_t *ctxOut /* state, rep0..3 */) {
+    enc_t *e = (enc_t *)calloc(1, sizeof(enc_t));
+    uint8_t *tmp = (uint8_t *)malloc(B2Z_LZ2_FRAME_BOUND(n));
+    encode_frame(e, (const uint8_t *)basev, n, seqs, nseq, tmp, B2Z_LZ2_SLICE_BLOCKS(P->frameLog, P->flags));
+    memcpy(probsOut, e->probs, sizeof(e->probs));
+    ctxOut[0] = e->state; for (int i = 0; i < 4; i++) ctxOut[1 + i] = e->rep[i];
+    const int64_t resets = e->modelResets;
+    free(tmp); free(e);
+    return resets;
 }
 
 size_t b2zo_lzma2_compress_bound(size_t n, const b2zo_enc_params *p) {

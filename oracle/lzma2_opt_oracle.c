@@ -66,7 +66,7 @@ static void commit_literal(uint16_t *probs, lzm_ctx *x, const uint8_t *base, uin
     lzm_commit_literal(probs, x, p, p ? base[p - 1] : 0u, base[p], x->state >= 7u ? base[p - x->rep[0] - 1u] : 0u);
 }
 
-static void parse_slice(const uint8_t *base, uint32_t s0, uint32_t s1, const uint32_t *cand, uint16_t *probs, sink_t *sink) {
+static void parse_slice(const uint8_t *base, uint32_t s0, uint32_t s1, const uint32_t *cand, uint16_t *probs, sink_t *sink, lzm_ctx *xOut) {
     node_t nd[LZP_WIN + 1];
     uint32_t path[LZP_WIN + 1];
     lzm_ctx x; x.state = 0; x.rep[0] = x.rep[1] = x.rep[2] = x.rep[3] = 0;
@@ -159,6 +159,7 @@ static void parse_slice(const uint8_t *base, uint32_t s0, uint32_t s1, const uin
         pos += i;
         if (longLen) { lzm_commit_match(probs, &x, pos, longLen, longDist); sink_match(sink, pos, longLen, longDist); pos += longLen; }
     }
+    if (xOut) *xOut = x;
 }
 
 /* one frame -> per-block sequences (block-indexed arrays of the frame, layout of b2zo_zstd_find_sequences); cand = stage C's output */
@@ -173,7 +174,25 @@ void b2zo_lzma2_parse_frame(const void *basev, uint32_t n, const b2zo_enc_params
     for (uint32_t s0 = 0; s0 < n; s0 += sliceBytes) {             /* slices = stage R's state-reset chains: independent models */
         const uint32_t s1 = s0 + sliceBytes < n ? s0 + sliceBytes : n;
         sink_t sink = { seqs, nseq, s0 };
-        parse_slice(base, s0, s1, cand, probs, &sink);
+        parse_slice(base, s0, s1, cand, probs, &sink, NULL);
     }
     free(probs); free(own);
+}
+
+/* Test tap: the model stage P ends the frame's LAST slice with (see b2zo_lzma2_final_model) */
+void b2zo_lzma2_parse_final_model(const void *basev, uint32_t n, const b2zo_enc_params *P, uint64_t *seqs, uint32_t *nseq, uint16_t *probsOut, uint32_t *ctxOut) {
+    const uint8_t *base = (const uint8_t *)basev;
+    uint32_t *cand = (uint32_t *)malloc((size_t)n * LZP_NCAND * 4 + 4);
+    b2zo_lzma2_candidates(base, n, P->frameLog, cand);
+    const uint32_t sliceBytes = B2Z_LZ2_SLICE_BLOCKS(P->frameLog, P->flags) * B2Z_BLOCK;
+    const uint32_t nblk = (n + B2Z_BLOCK - 1) / B2Z_BLOCK;
+    for (uint32_t b = 0; b < nblk; b++) nseq[b] = 0;
+    lzm_ctx x; memset(&x, 0, sizeof(x));
+    for (uint32_t s0 = 0; s0 < n; s0 += sliceBytes) {
+        const uint32_t s1 = s0 + sliceBytes < n ? s0 + sliceBytes : n;
+        sink_t sink = { seqs, nseq, s0 };
+        parse_slice(base, s0, s1, cand, probsOut, &sink, &x);
+    }
+    ctxOut[0] = x.state; for (int i = 0; i < 4; i++) ctxOut[1 + i] = x.rep[i];
+    free(cand);
 }

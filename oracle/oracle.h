@@ -51,6 +51,11 @@ int64_t b2zo_lzma2_compress(void *dst, size_t dstCap, const void *src, size_t sr
 void b2zo_lzma2_candidates(const void *base, uint32_t n, uint32_t frameLog, uint32_t *cand);
 void b2zo_lzma2_parse_frame(const void *base, uint32_t n, const b2zo_enc_params *P, const uint32_t *cand, uint64_t *seqs, uint32_t *nseq);
 
+/* test taps: the coder model (probabilities [1848 + (0x300 << lc)], then state, rep0..3) at the end of a frame as stage R leaves it
+ * after coding seqs (returns how often it initialised the model), and as stage P's simulation leaves it (last slice) */
+int64_t b2zo_lzma2_final_model(const void *base, uint32_t n, const b2zo_enc_params *P, const uint64_t *seqs, const uint32_t *nseq, uint16_t *probsOut, uint32_t *ctxOut);
+void b2zo_lzma2_parse_final_model(const void *base, uint32_t n, const b2zo_enc_params *P, uint64_t *seqs, uint32_t *nseq, uint16_t *probsOut, uint32_t *ctxOut);
+
 /* price-based Zstandard parse (zstd_opt_oracle.c; flags bit 5 of b2zo_zstd_compress / b2zo_zstd_find_sequences selects it):
  * one frame -> per-block sequences and literal bytes, on stage C's candidates (cand, or NULL to compute them here) */
 void b2zo_zstd_parse_frame(const void *base, uint32_t n, const b2zo_enc_params *P, const uint32_t *cand, uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit);

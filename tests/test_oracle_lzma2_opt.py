@@ -114,3 +114,28 @@ def test_slices_and_large_frames(pkg):
         assert H.oracle_lzma2_decompress(comp, len(data), prop) == (data, len(comp))
         if H.ref_lzma_available():
             assert H.ref_lzma2_decompress(comp, len(data), prop) == (data, len(comp))
+
+
+def test_simulated_model_equals_the_coders_model(pkg):
+    """Stage P prices from a model it maintains itself (lzm_commit_* of csrc/b2z_lzma_model.h, the header the kernel shares); stage
+    R's statement (lzma2_enc_oracle.c: enc_literal / enc_match inside the range coder) is written independently.  After the same
+    packets both must hold the same probabilities, state and rep history -- the claim "the parse prices from the coder's model"."""
+    O = H.oracle()
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    O.b2zo_lzma2_final_model.restype = ctypes.c_int64
+    O.b2zo_lzma2_final_model.argtypes = [vp, u32, ctypes.POINTER(H.EncParams), vp, vp, vp, vp]
+    O.b2zo_lzma2_parse_final_model.argtypes = [vp, u32, ctypes.POINTER(H.EncParams), vp, vp, vp, vp]
+    NP = 1848 + (0x300 << 2)
+    for data, fl, sl in ((pkg.corpus.g2(300_000).tobytes(), 20, 0), (pkg.corpus.g2(600_000).tobytes() + b"abcd" * 9000, 20, 1),
+                         (pkg.corpus.entropy_class(3, 200_000).tobytes(), 18, 0)):
+        n = len(data); src = np.frombuffer(data, dtype=np.uint8)
+        p = H.enc_params(frameLog=fl, windowLog=fl, flags=1 | (sl << 8) | OPT)
+        nblk = (n + 131071) // 131072
+        seqs = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); nseq = np.zeros(nblk, dtype=np.uint32)
+        pP = np.zeros(NP, dtype=np.uint16); cP = np.zeros(5, dtype=np.uint32); pR = np.zeros(NP, dtype=np.uint16); cR = np.zeros(5, dtype=np.uint32)
+        O.b2zo_lzma2_parse_final_model(src.ctypes.data, n, ctypes.byref(p), seqs.ctypes.data, nseq.ctypes.data, pP.ctypes.data, cP.ctypes.data)
+        resets = O.b2zo_lzma2_final_model(src.ctypes.data, n, ctypes.byref(p), seqs.ctypes.data, nseq.ctypes.data, pR.ctypes.data, cR.ctypes.data)
+        slice_bytes = (1 << fl) >> sl
+        assert resets == (n + slice_bytes - 1) // slice_bytes        # no raw-chunk fallback reset the coder's model on the way
+        assert np.array_equal(cP, cR) and np.array_equal(pP, pR)
+        assert int((pP != 1024).sum()) > 500                          # and it is a model that has adapted
