@@ -142,6 +142,16 @@ int b200z_lzma2_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, v
  * per-block sequences of a device buffer, layouts of the oracle's b2zo_lzma2_candidates / b2zo_lzma2_parse_frame. */
 int b200z_lzma2_enc_stage_cp(b200z_ctx *ctx, const void *d_src, size_t srcSize, uint32_t *cand, uint64_t *seqs, uint32_t *nseq);
 
+/* ---- digests of the archive layer on the GPU -------------------------------------------------------
+ * CRC32 as C/7zCrc.c:298 CrcCalc returns it (file / folder digests, CPP/7zip/Common/InStreamWithCRC.cpp) and CRC-64/XZ as
+ * C/XzCrc64.c computes it (xz block check).  *_combine: crc(A || B) from crc(A), crc(B), |B| -- host arithmetic, no device. */
+int b200z_crc32_device(b200z_ctx *ctx, const void *d_src, size_t n, uint32_t *crc);
+int b200z_crc64_device(b200z_ctx *ctx, const void *d_src, size_t n, uint64_t *crc);
+int b200z_crc32_host(b200z_ctx *ctx, const void *src, size_t n, uint32_t *crc);
+int b200z_crc64_host(b200z_ctx *ctx, const void *src, size_t n, uint64_t *crc);
+uint32_t b200z_crc32_combine(uint32_t crcA, uint32_t crcB, uint64_t lenB);
+uint64_t b200z_crc64_combine(uint64_t crcA, uint64_t crcB, uint64_t lenB);
+
 /* device memory helpers so FFI users need no CUDA binding of their own */
 int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);
 int b200z_dev_free(b200z_ctx *ctx, void *d_ptr);

@@ -7,6 +7,7 @@
 #include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
+#include "../../7-zip-zstd_b200/csrc/b2z_crc.cu"
 
 using namespace b2z;
 
@@ -64,5 +65,12 @@ uint64_t emu_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, uint32_t fra
                          [&] { zstd_enc_entropy_kernel(src, srcSize, g, seqs, nseq, lits, nlit, slots, slotSize, nBlocks); });
 }
 uint32_t emu_slot_bytes() { return B2Z_SLOT; }
+
+// crc_pieces_kernel: per-piece CRC32 / CRC64 (pieces of 2^pieceLog bytes, or the given ranges)
+uint64_t emu_crc_pieces(const uint8_t* src, uint64_t n, uint32_t pieceLog, const uint64_t* off, const uint64_t* len, uint32_t nPieces, uint32_t width, void* out) {
+    const dim3 grid((nPieces + 127u) / 128u), block(128);
+    if (width == 32) return cuemu::launch(grid, block, 0, [&] { crc_pieces_kernel<uint32_t>(src, n, pieceLog, off, len, nPieces, B2Z_CRC32_POLY, (uint32_t*)out); });
+    return cuemu::launch(grid, block, 0, [&] { crc_pieces_kernel<uint64_t>(src, n, pieceLog, off, len, nPieces, B2Z_CRC64_POLY, (uint64_t*)out); });
+}
 
 }
