@@ -1,6 +1,6 @@
 """CRC32 (7-Zip's file / folder digest, C/7zCrc.c CrcCalc) and CRC-64/XZ (xz block check, C/XzCrc64.c) -- csrc/b2z_crc.cu.
 CPU: the oracle statements against the check values, zlib and the reference's own functions; the library's host-side combine
-arithmetic; the kernel source through the host emulation (tests/cuemu).  The GPU test of the C ABI is tests/test_gpu_zz_crc.py."""
+arithmetic; the kernel source through the host emulation (tests/cuemu).  The GPU test of the C ABI is tests/test_gpu_zzz_crc.py."""
 import ctypes
 import os
 import random
