@@ -70,6 +70,14 @@ def load_library():
     for name in ("b200z_lzma2_decompress_device", "b200z_lzma2_decompress_host"):
         getattr(L, name).argtypes = [vp, vp, sz, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
     L.b200z_lzma2_enc_stage_cp.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.b200z_xz_compress_bound.argtypes = [vp, sz]; L.b200z_xz_compress_bound.restype = sz
+    L.b200z_xz_compress_host.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz), ctypes.c_uint32]
+    L.b200z_xz_decompress_host.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
+    L.b200z_xz_parse.argtypes = [vp, sz, vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)]
+    for name in ("b200z_crc32_host", "b200z_crc32_device"):
+        getattr(L, name).argtypes = [vp, vp, sz, ctypes.POINTER(ctypes.c_uint32)]
+    for name in ("b200z_crc64_host", "b200z_crc64_device"):
+        getattr(L, name).argtypes = [vp, vp, sz, ctypes.POINTER(ctypes.c_uint64)]
     L.b200z_dev_alloc.argtypes = [vp, ctypes.POINTER(vp), sz]
     L.b200z_dev_free.argtypes = [vp, vp]
     L.b200z_dev_upload.argtypes = [vp, vp, vp, sz]
@@ -278,3 +286,38 @@ class Codec:
         finally:
             self.L.b200z_dev_free(self.h, d)
         return cand[:n * 4].reshape(-1, 4), seqs, nseq
+
+    # ---- digests and the .xz container
+    def crc32(self, data) -> int:
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+        v = ctypes.c_uint32()
+        self._check(self.L.b200z_crc32_host(self.h, src.ctypes.data, len(data), ctypes.byref(v)))
+        return v.value
+
+    def crc64(self, data) -> int:
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+        v = ctypes.c_uint64()
+        self._check(self.L.b200z_crc64_host(self.h, src.ctypes.data, len(data), ctypes.byref(v)))
+        return v.value
+
+    def xz_compress(self, data, check=4) -> bytes:
+        """-> .xz file bytes: one Block per frame; check 0 none, 1 CRC32, 4 CRC64"""
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+        cap = self.L.b200z_xz_compress_bound(self.h, len(data))
+        out = np.empty(cap, dtype=np.uint8); sz = ctypes.c_size_t()
+        self._check(self.L.b200z_xz_compress_host(self.h, src.ctypes.data if len(data) else None, len(data), out.ctypes.data, cap, ctypes.byref(sz), check))
+        return out[:sz.value].tobytes()
+
+    def xz_decompress(self, data) -> bytes:
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8)
+        nb, total = ctypes.c_uint32(), ctypes.c_uint64()
+        rc = self.L.b200z_xz_parse(src.ctypes.data, src.nbytes, None, 0, ctypes.byref(nb), ctypes.byref(total))
+        if rc:
+            raise B200zError(rc, "xz: malformed or unsupported container")
+        out = np.empty(max(total.value, 1), dtype=np.uint8); sz = ctypes.c_size_t()
+        self._check(self.L.b200z_xz_decompress_host(self.h, src.ctypes.data, src.nbytes, out.ctypes.data, total.value, ctypes.byref(sz)))
+        return out[:sz.value].tobytes()

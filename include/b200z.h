@@ -152,6 +152,24 @@ int b200z_crc64_host(b200z_ctx *ctx, const void *src, size_t n, uint64_t *crc);
 uint32_t b200z_crc32_combine(uint32_t crcA, uint32_t crcB, uint64_t lenB);
 uint64_t b200z_crc64_combine(uint64_t crcA, uint64_t crcB, uint64_t lenB);
 
+/* ---- .xz container around the LZMA2 coder ----------------------------------------------------------
+ * Replaces NCompress::NXz::CEncoder / CDecoder (CPP/7zip/Compress/XzEncoder.cpp, XzDecoder.cpp) -> Xz_Encode (C/XzEnc.c:1236) /
+ * XzDecMt_Decode (C/XzDec.c) for streams whose Blocks use the LZMA2 filter alone.  The writer emits one Block per 2^FRAMELOG input
+ * bytes with both sizes in the Block header (the layout multi-threaded xz coders write); check type 0 none, 1 CRC32, 4 CRC64
+ * (XZ_CHECK_*, C/Xz.h:31-35).  b200z_xz_wrap / b200z_xz_parse are the host-side container logic alone (no device needed). */
+typedef struct {
+    uint64_t packOff, packSize;      /* the Block's LZMA2 chunk stream inside the file, end marker included */
+    uint64_t unpackSize, check;      /* decoded size; stored check value (low bytes first; 0 when none / longer than 8 bytes) */
+    uint32_t dictProp, checkType;
+} b200z_xz_block;
+size_t b200z_xz_wrap_bound(size_t lzma2Size, uint32_t nBlocks);
+int b200z_xz_wrap(const void *lzma2, size_t lzma2Size, uint32_t dictProp, uint32_t checkType, const uint64_t *checks, uint32_t nChecks,
+                  void *dst, size_t dstCap, size_t *dstSize);
+int b200z_xz_parse(const void *src, size_t srcSize, b200z_xz_block *blocks, uint32_t cap, uint32_t *nBlocks, uint64_t *contentSize);
+size_t b200z_xz_compress_bound(b200z_ctx *ctx, size_t srcSize);
+int b200z_xz_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize, uint32_t checkType);
+int b200z_xz_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize);
+
 /* device memory helpers so FFI users need no CUDA binding of their own */
 int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);
 int b200z_dev_free(b200z_ctx *ctx, void *d_ptr);

@@ -1,0 +1,56 @@
+"""GPU: the .xz container around the GPU LZMA2 coder (csrc/xz_api.cu) through the C ABI: files we write are decoded and verified
+by liblzma and the reference's unpacker; files liblzma writes (and our own) are decoded by the GPU with their Block checks
+verified; damage is reported.  Sorts last: first hardware run of this path (written after the round's GPU budget was spent; the
+container logic and the CRC kernel are checked on the CPU in tests/test_xz_container.py and tests/test_crc.py)."""
+import lzma
+
+import numpy as np
+import pytest
+
+import helpers as H
+from test_xz_container import _ref_unpack
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def inputs(pkg):
+    return H.sample_inputs(pkg, big=False)
+
+
+def test_files_we_write_decode_everywhere(pkg, codec, inputs):
+    for name, data in inputs.items():
+        for check in (0, 1, 4):
+            xz = codec.xz_compress(data, check)
+            assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == data, (name, check)
+            assert codec.xz_decompress(xz) == data, (name, check)
+        r = _ref_unpack(codec.xz_compress(data, 4), len(data))
+        if r:
+            assert r[0] == 0 and r[1] == data and r[3] != 0, name
+    c = pkg.Codec(0, frame_log=18, window_log=18, lzma2_parse=1)     # price-based parse, 256 KiB Blocks
+    data = inputs["mixed"] + inputs["g2_1m"]
+    xz = c.xz_compress(data)
+    assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == data and c.xz_decompress(xz) == data
+    c.close()
+
+
+def test_foreign_files_and_damage(pkg, codec, inputs):
+    data = inputs["g2_1m"]
+    for check in (lzma.CHECK_NONE, lzma.CHECK_CRC32, lzma.CHECK_CRC64, lzma.CHECK_SHA256):
+        assert codec.xz_decompress(lzma.compress(data, format=lzma.FORMAT_XZ, check=check, preset=1)) == data
+    a = lzma.compress(data[:300_000], format=lzma.FORMAT_XZ); b = lzma.compress(data[300_000:], format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC32, preset=0)
+    assert codec.xz_decompress(a + bytes(8) + b) == data              # concatenated Streams
+    xz = bytearray(codec.xz_compress(data, 4))
+    xz[len(xz) // 2] ^= 0x10                                          # inside a Block's payload: the range decoder or the check notices
+    with pytest.raises(pkg.B200zError) as e:
+        codec.xz_decompress(bytes(xz))
+    assert e.value.code in (-5, -8)
+    with pytest.raises(pkg.B200zError):
+        codec.xz_decompress(bytes(xz[:-5]))
+
+
+def test_large_roundtrip_property(pkg, codec):
+    data = pkg.corpus.g2(48 << 20, seed=80)
+    xz = codec.xz_compress(data)
+    out = codec.xz_decompress(xz)
+    assert np.array_equal(np.frombuffer(out, dtype=np.uint8), data)

@@ -1,0 +1,132 @@
+"""CPU: the .xz container logic of csrc/xz_api.cu (b200z_xz_wrap / b200z_xz_parse: host code of libb200z.so, no device needed).
+Writer: oracle LZMA2 streams (both parses) + per-frame CRC32 / CRC64 from the oracle -> .xz that liblzma (Python's lzma) and the
+reference's own unpacker (C/XzDec.c via oracle/_ref/libref_xz.so) decode and VERIFY.  Reader: files written by liblzma (all check
+types, concatenated streams, stream padding) and by our writer parse to the right Block table; damaged fields are rejected."""
+import ctypes
+import lzma
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+OPT = 0x10
+
+
+class XzBlock(ctypes.Structure):
+    _fields_ = [("packOff", ctypes.c_uint64), ("packSize", ctypes.c_uint64), ("unpackSize", ctypes.c_uint64), ("check", ctypes.c_uint64),
+                ("dictProp", ctypes.c_uint32), ("checkType", ctypes.c_uint32)]
+
+
+def _lib(pkg):
+    L = pkg.load_library()
+    vp, sz, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32
+    L.b200z_xz_wrap_bound.restype = sz; L.b200z_xz_wrap_bound.argtypes = [sz, u32]
+    L.b200z_xz_wrap.argtypes = [vp, sz, u32, u32, vp, u32, vp, sz, ctypes.POINTER(sz)]
+    L.b200z_xz_parse.argtypes = [vp, sz, ctypes.POINTER(XzBlock), u32, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_uint64)]
+    return L
+
+
+def _crc(kind, data):
+    O = H.oracle()
+    O.b2zo_crc32.restype = ctypes.c_uint32; O.b2zo_crc32.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    O.b2zo_crc64.restype = ctypes.c_uint64; O.b2zo_crc64.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    return O.b2zo_crc32(data, len(data)) if kind == 1 else (O.b2zo_crc64(data, len(data)) if kind == 4 else 0)
+
+
+def _wrap(L, lz, prop, kind, data, fl):
+    F = 1 << fl
+    checks = np.array([_crc(kind, data[i:i + F]) for i in range(0, len(data), F)] or [0], dtype=np.uint64)
+    src = np.frombuffer(lz, dtype=np.uint8)
+    cap = L.b200z_xz_wrap_bound(len(lz), len(checks)); out = np.zeros(cap, dtype=np.uint8); n = ctypes.c_size_t()
+    rc = L.b200z_xz_wrap(src.ctypes.data, len(lz), prop, kind, checks.ctypes.data, len(checks), out.ctypes.data, cap, ctypes.byref(n))
+    assert rc == 0, rc
+    return out[:n.value].tobytes()
+
+
+def _parse(L, xz, cap=4096):
+    src = np.frombuffer(xz, dtype=np.uint8)
+    blocks = (XzBlock * cap)(); nb = ctypes.c_uint32(); total = ctypes.c_uint64()
+    rc = L.b200z_xz_parse(src.ctypes.data, len(xz), blocks, cap, ctypes.byref(nb), ctypes.byref(total))
+    return rc, [blocks[i] for i in range(min(nb.value, cap))], total.value
+
+
+def _ref_unpack(xz, n):
+    """the reference's unpacker (C/XzDec.c XzUnpacker_Code); verifies Block checks, Index and Footer"""
+    path = os.path.join(H.ROOT, "oracle", "_ref", "libref_xz.so")
+    if not os.path.exists(path):
+        return None
+    R = ctypes.CDLL(path)
+    R.CrcGenerateTable(); R.Crc64GenerateTable()
+    alloc = ctypes.c_void_p.in_dll(R, "g_Alloc")
+    st = ctypes.create_string_buffer(1 << 16)                     # CXzUnpacker (opaque here; a few KB)
+    R.XzUnpacker_Construct.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    R.XzUnpacker_Init.argtypes = [ctypes.c_void_p]; R.XzUnpacker_Free.argtypes = [ctypes.c_void_p]
+    R.XzUnpacker_IsStreamWasFinished.argtypes = [ctypes.c_void_p]
+    R.XzUnpacker_Code.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t),
+                                  ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    R.XzUnpacker_Construct(st, ctypes.addressof(alloc)); R.XzUnpacker_Init(st)
+    src = np.frombuffer(xz, dtype=np.uint8)
+    out = bytearray(); ip = 0; chunk = np.zeros(1 << 20, dtype=np.uint8); status = ctypes.c_int(); rc = 0
+    while True:                                                    # Interface-1 of C/Xz.h:296-308: partial output buffers
+        dl = ctypes.c_size_t(chunk.size); sl = ctypes.c_size_t(len(xz) - ip)
+        rc = R.XzUnpacker_Code(st, chunk.ctypes.data, ctypes.byref(dl), src.ctypes.data + ip, ctypes.byref(sl), 1, 0, ctypes.byref(status))
+        out += chunk[:dl.value].tobytes(); ip += sl.value
+        if rc != 0 or (dl.value == 0 and sl.value == 0):
+            break
+    fin = R.XzUnpacker_IsStreamWasFinished(st)
+    R.XzUnpacker_Free(st)
+    return rc, bytes(out), ip, fin
+
+
+def test_writer_output_is_decoded_and_verified_by_liblzma_and_the_reference(pkg):
+    L = _lib(pkg)
+    data = pkg.corpus.g2(2 * (1 << 20) + 300_001).tobytes() + bytes(50_000) + pkg.corpus.entropy_class(1, 90_000).tobytes()
+    for fl, flags in ((20, 1 | (2 << 8)), (18, 1 | (1 << 8) | OPT), (17, 1)):
+        prop, lz = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=flags)
+        for kind in (0, 1, 4):
+            xz = _wrap(L, lz, prop, kind, data, fl)
+            assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == data, (fl, kind)
+            r = _ref_unpack(xz, len(data))
+            if r:
+                assert r[0] == 0 and r[1] == data and r[2] == len(xz) and r[3] != 0, (fl, kind, r[0])
+            rc, blocks, total = _parse(L, xz)
+            assert rc == 0 and total == len(data) and len(blocks) == (len(data) + (1 << fl) - 1) >> fl
+            assert all(b.checkType == kind and b.dictProp == prop for b in blocks)
+            assert [b.check for b in blocks] == [_crc(kind, data[i:i + (1 << fl)]) for i in range(0, len(data), 1 << fl)]
+    # a wrong check value must be caught by the independent decoders
+    prop, lz = H.oracle_lzma2_compress(data[:300_000])
+    bad = bytearray(_wrap(L, lz, prop, 4, data[:300_000], 20)); rc, blocks, _ = _parse(L, bytes(bad))
+    bad[blocks[0].packOff + ((blocks[0].packSize + 3) & ~3)] ^= 1
+    with pytest.raises(lzma.LZMAError):
+        lzma.decompress(bytes(bad), format=lzma.FORMAT_XZ)
+    # empty input: a Stream with no Blocks
+    prop, lz = H.oracle_lzma2_compress(b"")
+    xz = _wrap(L, lz, prop, 4, b"", 20)
+    assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == b"" and _parse(L, xz)[:1] == (0,) and len(xz) == 32
+
+
+def test_reader_parses_foreign_files_and_rejects_damage(pkg):
+    L = _lib(pkg)
+    data = pkg.corpus.g2(400_000).tobytes()
+    for check, kind in ((lzma.CHECK_NONE, 0), (lzma.CHECK_CRC32, 1), (lzma.CHECK_CRC64, 4), (lzma.CHECK_SHA256, 10)):
+        xz = lzma.compress(data, format=lzma.FORMAT_XZ, check=check, preset=1)
+        rc, blocks, total = _parse(L, xz)
+        assert rc == 0 and total == len(data) and len(blocks) == 1 and blocks[0].checkType == kind
+        b = blocks[0]
+        raw = xz[b.packOff:b.packOff + b.packSize]                # the Block's chunk stream decodes on its own
+        assert H.oracle_lzma2_decompress(raw, len(data), b.dictProp) == (data, len(raw))
+        if kind in (1, 4):
+            assert b.check == _crc(kind, data)
+    a = lzma.compress(data[:100_000], format=lzma.FORMAT_XZ); b = lzma.compress(data[100_000:], format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC32)
+    rc, blocks, total = _parse(L, a + bytes(8) + b + bytes(4))    # concatenated Streams with Stream Padding
+    assert rc == 0 and len(blocks) == 2 and total == len(data) and (blocks[0].checkType, blocks[1].checkType) == (4, 1)
+    xz = lzma.compress(data, format=lzma.FORMAT_XZ)
+    assert _parse(L, xz[:-1])[0] == -5 and _parse(L, xz[:40])[0] == -5 and _parse(L, b"")[0] == -5
+    for pos in (7, 9, 13, 20, len(xz) - 3, len(xz) - 9, len(xz) - 14):     # flags, header CRC, block header, footer fields, index
+        bad = bytearray(xz); bad[pos] ^= 0x40
+        assert _parse(L, bytes(bad))[0] in (-5, -6), pos
+    assert _parse(L, a + bytes(3) + b)[0] == -5                   # Stream Padding must be a multiple of four bytes
+    f = lzma.compress(data[:50_000], format=lzma.FORMAT_XZ, filters=[{"id": lzma.FILTER_DELTA, "dist": 1}, {"id": lzma.FILTER_LZMA2, "preset": 1}])
+    assert _parse(L, f)[0] == -6                                  # a filter in front of LZMA2: unsupported, not corrupt
