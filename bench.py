@@ -88,9 +88,9 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- CPU reference arm
-def cpu_reference(sample_bytes, seed_offset=0):
+def cpu_reference(sample_bytes, seed_offset=0, level=3):
     """The reference's own CPU implementation of the path (oracle/_ref/libref_zstd.so compiled from
-    /root/reference/C/zstd): level 3, zstdmt with all host threads for encode (ZstdEncoder.cpp:300
+    /root/reference/C/zstd): the given level (3 = the headline), zstdmt with all host threads for encode (ZstdEncoder.cpp:300
     nbWorkers = #CPUs), single-threaded decode (ZstdDecoder.cpp:260-263: SetNumberOfThreads is a no-op)."""
     import ctypes
     import numpy as np
@@ -103,7 +103,7 @@ def cpu_reference(sample_bytes, seed_offset=0):
         Z = helpers.ref(); kind = "reference"
         out = np.zeros(Z.ZSTD_compressBound(sample_bytes), dtype=np.uint8)      # pre-faulted: page faults are not the codec
         c = Z.ZSTD_createCCtx()
-        Z.ZSTD_CCtx_setParameter(c, 100, 3); Z.ZSTD_CCtx_setParameter(c, 400, min(cores, 200))
+        Z.ZSTD_CCtx_setParameter(c, 100, level); Z.ZSTD_CCtx_setParameter(c, 400, min(cores, 200))
         t = time.perf_counter(); r = Z.ZSTD_compress2(c, out.ctypes.data, out.size, data.ctypes.data, sample_bytes); t_enc = time.perf_counter() - t
         Z.ZSTD_freeCCtx(c)
         back = np.zeros(sample_bytes, dtype=np.uint8)
@@ -112,7 +112,7 @@ def cpu_reference(sample_bytes, seed_offset=0):
         enc_threads, dec_threads = min(cores, 200), 1
     else:                                                   # oracle port (single-threaded C restatement)
         O = helpers.oracle(); kind = "port"
-        p = helpers.enc_params()
+        p = helpers.enc_params(**({"flags": 1 | 0x20} if level >= 8 else {}))
         out = np.empty(O.b2zo_zstd_compress_bound(sample_bytes, ctypes.byref(p)), dtype=np.uint8)
         t = time.perf_counter(); r = O.b2zo_zstd_compress(out.ctypes.data, out.size, data.ctypes.data, sample_bytes, ctypes.byref(p)); t_enc = time.perf_counter() - t
         back = np.empty(sample_bytes, dtype=np.uint8)
@@ -121,7 +121,7 @@ def cpu_reference(sample_bytes, seed_offset=0):
         enc_threads, dec_threads = 1, 1
     mb = sample_bytes / 1e6
     return {"value": mb / (t_enc + t_dec), "unit": "MB/s", "cores": cores, "kind": kind,
-            "sample": f"{sample_bytes >> 20} MiB of the same G2 text, zstd level 3: encode {enc_threads} threads (zstdmt), decode {dec_threads} thread (reference decoder is single-threaded)",
+            "sample": f"{sample_bytes >> 20} MiB of the same G2 text, zstd level {level}: encode {enc_threads} threads (zstdmt), decode {dec_threads} thread (reference decoder is single-threaded)",
             "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": sample_bytes / r, "t_enc_s": t_enc, "t_dec_s": t_dec}
 
 
@@ -150,8 +150,8 @@ def cpu_reference_lzma2(sample_bytes, seed_offset=0):
 def main():
     a = parse_args()
     lz = a.codec == "lzma2"
-    cpu_ref = cpu_reference_lzma2 if lz else cpu_reference
-    metric_name = "LZMA2 (method 21) encode+decode throughput" if lz else "zstd-L3 encode+decode throughput"
+    cpu_ref = cpu_reference_lzma2 if lz else (lambda nbytes, seed_offset=0: cpu_reference(nbytes, seed_offset, a.level))
+    metric_name = "LZMA2 (method 21) encode+decode throughput" if lz else f"zstd-L{a.level} encode+decode throughput"
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     unit_bytes = a.size_mib << 20
     workload = f"zstd level {a.level}, {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 128 KiB blocks"
