@@ -78,6 +78,8 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz, ctypes.POINTER(ctypes.c_uint32)]
     for name in ("b200z_crc64_host", "b200z_crc64_device"):
         getattr(L, name).argtypes = [vp, vp, sz, ctypes.POINTER(ctypes.c_uint64)]
+    for name in ("b200z_filter_host", "b200z_filter_device"):
+        getattr(L, name).argtypes = [vp, ctypes.c_uint32, ctypes.c_int, vp, sz, ctypes.c_uint32]
     L.b200z_dev_alloc.argtypes = [vp, ctypes.POINTER(vp), sz]
     L.b200z_dev_free.argtypes = [vp, vp]
     L.b200z_dev_upload.argtypes = [vp, vp, vp, sz]
@@ -321,3 +323,10 @@ class Codec:
         out = np.empty(max(total.value, 1), dtype=np.uint8); sz = ctypes.c_size_t()
         self._check(self.L.b200z_xz_decompress_host(self.h, src.ctypes.data, src.nbytes, out.ctypes.data, total.value, ctypes.byref(sz)))
         return out[:sz.value].tobytes()
+
+    def filter(self, method_id, encode, data, prop=0) -> bytes:
+        """Delta (0x03, prop = distance) / branch converters ARM64 0x0A, ARM 0x03030501, PPC 0x03030205, SPARC 0x03030805 (prop = start offset)"""
+        import numpy as np
+        buf = np.frombuffer(bytearray(data), dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+        self._check(self.L.b200z_filter_host(self.h, method_id, 1 if encode else 0, buf.ctypes.data, len(data), prop))
+        return buf[:len(data)].tobytes()

@@ -170,6 +170,13 @@ size_t b200z_xz_compress_bound(b200z_ctx *ctx, size_t srcSize);
 int b200z_xz_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize, uint32_t checkType);
 int b200z_xz_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize);
 
+/* ---- pre/post filters of a 7z folder / xz filter chain on the GPU -----------------------------------
+ * In place.  methodId = 7-Zip's filter id: 0x03 Delta (prop = distance 1..256; CPP/7zip/Compress/DeltaFilter.cpp, C/Delta.c),
+ * 0x0A ARM64, 0x03030501 ARM, 0x03030205 PPC, 0x03030805 SPARC (prop = start offset; BranchMisc.cpp -> C/Bra.c z7_BranchConv_*).
+ * The converters whose scan carries state (x86 BCJ, BCJ2, ARMT, RISCV, IA64) return B200Z_E_UNSUPPORTED. */
+int b200z_filter_device(b200z_ctx *ctx, uint32_t methodId, int encode, void *d_data, size_t n, uint32_t prop);
+int b200z_filter_host(b200z_ctx *ctx, uint32_t methodId, int encode, void *data, size_t n, uint32_t prop);
+
 /* device memory helpers so FFI users need no CUDA binding of their own */
 int b200z_dev_alloc(b200z_ctx *ctx, void **d_ptr, size_t bytes);
 int b200z_dev_free(b200z_ctx *ctx, void *d_ptr);

@@ -11,6 +11,8 @@ extern "C" {
 uint64_t b2zo_xxh64(const void *data, size_t len, uint64_t seed);
 uint32_t b2zo_crc32(const void *data, size_t n);      /* crc_oracle.c: 7-Zip's CRC32 (C/7zCrc.c CrcCalc) */
 uint64_t b2zo_crc64(const void *data, size_t n);      /* CRC-64/XZ (C/XzCrc64.c) */
+/* filter_oracle.c: in-place delta / branch converters by 7-Zip method id; 0 ok, -1 unknown filter or bad property */
+int b2zo_filter(uint32_t methodId, int enc, void *data, size_t n, uint32_t prop);
 
 /* Decode every frame (zstd + skippable) in src; returns size or <0 (-1 corrupt, -2 dst too
  * small, -3 checksum, -4 dictionary needed). */

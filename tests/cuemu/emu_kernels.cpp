@@ -8,6 +8,7 @@
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
 #include "../../7-zip-zstd_b200/csrc/b2z_crc.cu"
+#include "../../7-zip-zstd_b200/csrc/b2z_filter.cu"
 
 using namespace b2z;
 
@@ -71,6 +72,27 @@ uint64_t emu_crc_pieces(const uint8_t* src, uint64_t n, uint32_t pieceLog, const
     const dim3 grid((nPieces + 127u) / 128u), block(128);
     if (width == 32) return cuemu::launch(grid, block, 0, [&] { crc_pieces_kernel<uint32_t>(src, n, pieceLog, off, len, nPieces, B2Z_CRC32_POLY, (uint32_t*)out); });
     return cuemu::launch(grid, block, 0, [&] { crc_pieces_kernel<uint64_t>(src, n, pieceLog, off, len, nPieces, B2Z_CRC64_POLY, (uint64_t*)out); });
+}
+
+// filters (b2z_filter.cu), in place on `data`; same launch shapes as b200z_filter_device
+void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t prop) {
+    if (methodId == B200Z_F_DELTA) {
+        if (enc) {
+            std::vector<uint8_t> copy(data, data + n);
+            cuemu::launch(dim3((uint32_t)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64)), dim3(256), 0, [&] { delta_enc_kernel(copy.data(), data, n, prop); });
+        } else {
+            const uint32_t rows = (65536u / prop) ? (65536u / prop) : 1u;
+            const uint64_t tileBytes = (uint64_t)rows * prop;
+            const uint32_t tiles = (uint32_t)((n + tileBytes - 1) / tileBytes);
+            std::vector<uint8_t> sums((size_t)tiles * prop + 64, 0xCD);
+            cuemu::launch(dim3(tiles), dim3(256), 0, [&] { delta_colsum_kernel(data, n, prop, rows, sums.data()); });
+            cuemu::launch(dim3(1), dim3(256), 0, [&] { delta_scan_kernel(sums.data(), tiles, prop); });
+            cuemu::launch(dim3(tiles), dim3(256), 0, [&] { delta_dec_kernel(data, n, prop, rows, sums.data()); });
+        }
+    } else {
+        const uint64_t nWords = n >> 2;
+        if (nWords) cuemu::launch(dim3((uint32_t)((nWords + 255) / 256 < 32 ? (nWords + 255) / 256 : 32)), dim3(256), 0, [&] { bra_kernel((uint32_t*)data, nWords, methodId, enc, prop); });
+    }
 }
 
 }

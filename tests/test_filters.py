@@ -1,0 +1,120 @@
+"""Delta and the stateless branch converters (ARM64, ARM, PPC, SPARC) -- csrc/b2z_filter.cu, SURVEY.md 8(f) item 3.
+CPU: the oracle's statements (oracle/filter_oracle.c) against the REFERENCE's own converters (C/Bra.c z7_BranchConv_*_Enc/_Dec,
+C/Delta.c, compiled into oracle/_ref/libref_xz.so) on instruction-dense data, word by word; decode(encode(x)) == x; the kernel
+sources through the host emulation (tests/cuemu).  The GPU test of the C ABI is tests/test_gpu_zzz_filters.py."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DELTA, ARM64, PPC, ARM, SPARC = 0x03, 0x0A, 0x03030205, 0x03030501, 0x03030805
+REF_NAME = {ARM64: "ARM64", ARM: "ARM", PPC: "PPC", SPARC: "SPARC"}
+
+
+def oracle_filter(method, enc, data, prop):
+    O = H.oracle()
+    O.b2zo_filter.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32]
+    buf = np.frombuffer(bytearray(data), dtype=np.uint8)
+    assert O.b2zo_filter(method, enc, buf.ctypes.data if len(data) else None, len(data), prop) == 0
+    return buf.tobytes()
+
+
+def ref_filter(method, enc, data, prop):
+    path = os.path.join(H.ROOT, "oracle", "_ref", "libref_xz.so")
+    if not os.path.exists(path):
+        return None
+    R = ctypes.CDLL(path)
+    buf = np.frombuffer(bytearray(data), dtype=np.uint8)
+    if method == DELTA:
+        state = ctypes.create_string_buffer(256)
+        R.Delta_Init(state)
+        f = R.Delta_Encode if enc else R.Delta_Decode
+        f.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t]
+        f(state, prop, buf.ctypes.data, len(data))
+    else:
+        f = getattr(R, f"z7_BranchConv_{REF_NAME[method]}_{'Enc' if enc else 'Dec'}")
+        f.restype = ctypes.c_void_p; f.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32]
+        end = f(buf.ctypes.data, len(data), prop)
+        assert end - buf.ctypes.data == (len(data) & ~3)            # processes whole instructions, leaves the tail
+    return buf.tobytes()
+
+
+def instruction_soup(method, n_words, seed):
+    """words that hit the converters' patterns often, with immediates at and around every range boundary"""
+    rng = random.Random(seed); out = bytearray()
+    for _ in range(n_words):
+        r = rng.random(); w = rng.getrandbits(32)
+        if method == ARM64:
+            if r < 0.3: w = 0x94000000 | rng.getrandbits(26)
+            elif r < 0.7:
+                imm = rng.choice([0, 1, -1, (1 << 17) - 1, 1 << 17, -(1 << 17), -(1 << 17) - 1, (1 << 20) - 1, -(1 << 20), rng.getrandbits(21) - (1 << 20), rng.getrandbits(18) - (1 << 17)]) & 0x1FFFFF
+                w = 0x90000000 | ((imm & 3) << 29) | ((imm >> 2) << 5) | rng.getrandbits(5)
+            le = True
+        elif method == ARM:
+            if r < 0.5: w = 0xEB000000 | rng.getrandbits(24)
+            le = True
+        elif method == PPC:
+            if r < 0.5: w = 0x48000001 | (rng.getrandbits(24) << 2)
+            elif r < 0.6: w = 0x48000000 | rng.getrandbits(26)
+            le = False
+        else:
+            if r < 0.3: w = 0x40000000 | rng.getrandbits(22)
+            elif r < 0.6: w = 0x7FC00000 | rng.getrandbits(22)
+            elif r < 0.7: w = 0x40000000 | rng.getrandbits(30)
+            le = False
+        out += w.to_bytes(4, "little" if le else "big")
+    return bytes(out)
+
+
+@pytest.mark.parametrize("method", [ARM64, ARM, PPC, SPARC])
+def test_branch_converters_equal_the_reference(method):
+    for seed, prop in ((1, 0), (2, 0x1000), (3, 0xFFFFF000), (4, 0x12345678), (5, 0x7FFFFFFC), (6, 0xFFFFFFFC)):
+        data = instruction_soup(method, 60_000, seed) + b"\x94\x00\x00"[: seed % 4]      # ragged tail stays untouched
+        enc = oracle_filter(method, 1, data, prop)
+        assert enc != data and oracle_filter(method, 0, enc, prop) == data       # start offsets are multiples of 4: the coders reject
+                                                                                   # others (BranchMisc.cpp:57,99), as b200z_filter_device does
+        r = ref_filter(method, 1, data, prop)
+        if r is not None:
+            assert enc == r, (hex(method), hex(prop))
+            assert oracle_filter(method, 0, data, prop) == ref_filter(method, 0, data, prop)     # decoding arbitrary words agrees too
+
+
+def test_delta_equals_the_reference(pkg):
+    data = pkg.corpus.entropy_class(2, 100_001).tobytes() + bytes(range(256)) * 40
+    for dist in (1, 2, 3, 4, 7, 16, 255, 256):
+        for n in (0, 1, dist - 1 if dist > 1 else 1, dist, dist + 1, 1000, len(data)):
+            d = data[:n]
+            enc = oracle_filter(DELTA, 1, d, dist)
+            assert oracle_filter(DELTA, 0, enc, dist) == d
+            r = ref_filter(DELTA, 1, d, dist)
+            if r is not None:
+                assert enc == r, (dist, n)
+                assert oracle_filter(DELTA, 0, d, dist) == ref_filter(DELTA, 0, d, dist)
+
+
+def test_emulated_kernels_equal_the_oracle(pkg):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cuemu")])
+    E = ctypes.CDLL(os.path.join(HERE, "cuemu", "libcuemu_kernels.so"))
+    E.emu_filter.restype = None; E.emu_filter.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
+
+    def emu(method, enc, data, prop):
+        buf = np.frombuffer(bytearray(data) + bytearray(8), dtype=np.uint8)
+        E.emu_filter(method, enc, buf.ctypes.data, len(data), prop)
+        return buf[:len(data)].tobytes()
+    for method in (ARM64, ARM, PPC, SPARC):
+        data = instruction_soup(method, 20_000, 9) + b"\x01\x02"
+        for enc in (1, 0):
+            assert emu(method, enc, data, 0x00ABC000) == oracle_filter(method, enc, data, 0x00ABC000), (hex(method), enc)
+            assert emu(method, enc, data, 0xFFFFF000) == oracle_filter(method, enc, data, 0xFFFFF000), (hex(method), enc, "addresses that wrap")
+    data = pkg.corpus.entropy_class(2, 300_001).tobytes()
+    for dist in (1, 3, 4, 255, 256):
+        for n in (1, dist, 65536, 65537, len(data)):                 # around the 64 KiB tiles of the decoder
+            d = data[:n]
+            assert emu(DELTA, 1, d, dist) == oracle_filter(DELTA, 1, d, dist), (dist, n)
+            assert emu(DELTA, 0, d, dist) == oracle_filter(DELTA, 0, d, dist), (dist, n)

@@ -1,0 +1,36 @@
+"""GPU: Delta and the stateless branch converters through the C ABI (csrc/b2z_filter.cu) against the oracle and -- where
+oracle/_ref exists -- the reference's own functions.  Sorts last: first hardware run of these kernels (written after the round's
+GPU budget was spent; their sources are checked through the host emulation in tests/test_filters.py)."""
+import numpy as np
+import pytest
+
+from test_filters import ARM, ARM64, DELTA, PPC, SPARC, instruction_soup, oracle_filter, ref_filter
+
+pytestmark = pytest.mark.gpu
+
+
+def test_branch_converters(pkg, codec):
+    for method in (ARM64, ARM, PPC, SPARC):
+        data = instruction_soup(method, 1_000_000, 21) + b"\x01\x02\x03"
+        for prop in (0, 0x00ABC000):
+            enc = codec.filter(method, True, data, prop)
+            assert enc == oracle_filter(method, 1, data, prop), hex(method)
+            r = ref_filter(method, 1, data, prop)
+            assert r is None or enc == r
+            assert codec.filter(method, False, enc, prop) == data
+    with pytest.raises(pkg.B200zError) as e:
+        codec.filter(0x03030103, True, b"\xe8" * 64, 0)              # x86 BCJ: state-carrying scan, left to the host
+    assert e.value.code == -6
+    with pytest.raises(pkg.B200zError):
+        codec.filter(ARM64, True, bytes(64), 2)                       # start offset must be a multiple of 4 (BranchMisc.cpp:57)
+
+
+def test_delta(pkg, codec):
+    data = pkg.corpus.entropy_class(2, 3_000_001).tobytes() + bytes(range(256)) * 100
+    for dist in (1, 2, 4, 255, 256):
+        enc = codec.filter(DELTA, True, data, dist)
+        assert enc == oracle_filter(DELTA, 1, data, dist), dist
+        assert codec.filter(DELTA, False, enc, dist) == data, dist
+        r = ref_filter(DELTA, 0, data, dist)
+        assert r is None or codec.filter(DELTA, False, data, dist) == r
+    assert codec.filter(DELTA, True, b"", 1) == b"" and codec.filter(DELTA, False, b"abc", 7) == b"abc"
