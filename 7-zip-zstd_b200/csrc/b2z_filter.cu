@@ -7,7 +7,10 @@
 //                  launch goes through a scratch copy).  Decode: per residue class i mod d a running sum, done in three steps:
 //                  column sums of tiles of `rows` x d bytes, an exclusive scan of those sums across tiles, then each tile adds its
 //                  carry while it accumulates (C/Delta.c:20-169 is the sequential statement).
-//   not here       x86 BCJ / BCJ2 / ARMT / RISCV / IA64: their scan carries state from byte to byte (C/Bra86.c:50-170) -- left to the host.
+//   x86_kernel     the x86 BCJ scan carries a 3-bit history from byte to byte (C/Bra86.c:50-170), but the history dies after three
+//                  non-opcode bytes: the buffer falls into clusters of E8 / E9 bytes that convert independently; threads find the
+//                  cluster starts in their 32-byte spans and run the sequential rule per cluster (b2z_filter_ops.h).
+//   not here       BCJ2 (four output streams + a range coder), ARMT, RISCV, IA64 -- left to the host.
 // Oracle statement: oracle/filter_oracle.c; both are checked against the reference's functions (oracle/_ref/libref_xz.so).
 #include "b2z_device.cuh"
 #include "b2z_filter_ops.h"
@@ -28,6 +31,38 @@ bra_kernel(uint32_t* __restrict__ words, uint64_t nWords, uint32_t kind, int enc
         else if (kind == B200Z_F_PPC) out = b2z_bswap32(b2z_conv_ppc(b2z_bswap32(raw), ia, enc));
         else out = b2z_bswap32(b2z_conv_sparc(b2z_bswap32(raw), ia, enc));
         if (out != raw) words[i] = out;
+    }
+}
+
+// x86 BCJ: thread t looks at positions [t * 32, t * 32 + 32) of the ORIGINAL bytes (`in`) for cluster starts -- an opcode byte (E8 / E9
+// with 5 bytes left) with no opcode byte in the three positions before it -- and converts each cluster it finds from its start, with
+// the sequential rule, until four positions pass without an opcode byte.  Clusters touch disjoint bytes; every decision reads `in`
+// (a conversion's operand is never looked at again by the scan), results go to `out`, which starts as a copy of `in`.
+__global__ void __launch_bounds__(128)
+x86_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n, uint32_t pc, int enc) {
+    const uint64_t t0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 32u;
+    if (n < 5u || t0 > n - 5u) return;
+    const uint64_t last = n - 5u;                                   // last position that can hold a convertible opcode
+    uint32_t back = 0;                                              // opcode flags of the three positions before c (bit 0 = c - 1)
+    for (uint32_t k = 1; k <= 3u; k++) if (t0 >= k && b2z_x86_is_opcode(in[t0 - k])) back |= 1u << (k - 1u);
+    for (uint64_t c = t0; c < t0 + 32u && c <= last; c++) {
+        const bool op = b2z_x86_is_opcode(in[c]);
+        if (op && back == 0u) {                                     // ---- a cluster starts here
+            uint32_t hist = 0; uint64_t i = c, rawLast = c;
+            while (i <= last) {
+                if (i - rawLast > 3u) break;                        // three non-opcode bytes passed: whatever follows is another cluster
+                const uint32_t b = in[i];
+                if (!b2z_x86_is_opcode(b)) { hist >>= 1; i++; continue; }
+                rawLast = i;
+                const uint32_t operand = (uint32_t)in[i + 1] | ((uint32_t)in[i + 2] << 8) | ((uint32_t)in[i + 3] << 16) | ((uint32_t)in[i + 4] << 24);
+                uint32_t v;
+                if (!b2z_x86_convert(hist, operand, pc + (uint32_t)i + 5u, enc, &v)) { hist = (hist >> 1) | 4u; i++; continue; }
+                out[i + 1] = (uint8_t)v; out[i + 2] = (uint8_t)(v >> 8); out[i + 3] = (uint8_t)(v >> 16); out[i + 4] = (uint8_t)(v >> 24);
+                for (uint32_t k = 1; k <= 4u; k++) if (i + k <= last && b2z_x86_is_opcode(in[i + k])) rawLast = i + k;   // skipped, but they keep the cluster going
+                hist = 0; i += 5;
+            }
+        }
+        back = ((back << 1) | (op ? 1u : 0u)) & 7u;
     }
 }
 
@@ -93,6 +128,14 @@ int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_d
             b2z::delta_dec_kernel<<<tiles, 256, 0, st>>>((uint8_t*)d_data, n, prop, rows, (const uint8_t*)ctx->batchOff.p);
             ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
         }
+    } else if (methodId == B200Z_F_X86) {
+        if (n >= 5) {
+            if (ctx->batchStage.reserve(n)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
+            CU(cudaMemcpyAsync(ctx->batchStage.p, d_data, n, cudaMemcpyDeviceToDevice, st));
+            const uint64_t threads = (n + 31) / 32;
+            b2z::x86_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->batchStage.p, (uint8_t*)d_data, n, prop, encode);
+            ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        }
     } else if (methodId == B200Z_F_ARM64 || methodId == B200Z_F_ARM || methodId == B200Z_F_PPC || methodId == B200Z_F_SPARC) {
         if ((uintptr_t)d_data & 3u) return fail(ctx, B200Z_E_PARAM, "branch converters need a 4-byte aligned buffer%s");
         if (prop & 3u) return fail(ctx, B200Z_E_UNSUPPORTED, "start offset must be a multiple of the instruction size%s");   // BranchMisc.cpp:57,99: E_INVALIDARG / E_NOTIMPL
@@ -100,7 +143,7 @@ int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_d
         if (!nWords) return 0;
         b2z::bra_kernel<<<(unsigned)((nWords + 255) / 256 < 148u * 64u ? (nWords + 255) / 256 : 148u * 64u), 256, 0, st>>>((uint32_t*)d_data, nWords, methodId, encode, prop);
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
-    } else return fail(ctx, B200Z_E_UNSUPPORTED, "filter not built on the GPU (x86 BCJ / BCJ2 / ARMT / RISCV / IA64 scan with carried state)%s");
+    } else return fail(ctx, B200Z_E_UNSUPPORTED, "filter not built on the GPU (BCJ2 / ARMT / RISCV / IA64)%s");
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     return 0;

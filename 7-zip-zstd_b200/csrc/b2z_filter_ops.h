@@ -12,6 +12,7 @@
 /* 7-Zip method ids of the filters (CPP/7zip/Compress/BranchRegister.cpp, DeltaFilter.cpp; DOC/Methods.txt) */
 #define B200Z_F_DELTA 0x03u
 #define B200Z_F_ARM64 0x0Au
+#define B200Z_F_X86   0x03030103u
 #define B200Z_F_PPC   0x03030205u
 #define B200Z_F_ARM   0x03030501u
 #define B200Z_F_SPARC 0x03030805u
@@ -52,6 +53,28 @@ B2Z_HD uint32_t b2z_conv_sparc(uint32_t w, uint32_t ia, int enc) {
     const uint32_t biased = ((w & 0x3FFFFFu) + (top == 0x100u ? (1u << 22) : 0u)) << 2;      /* (disp + 2^22) * 4, < 2^25 */
     const uint32_t x = (enc ? biased + ia : biased - ia) & ((1u << 25) - 1u);
     return ((x - (1u << 24)) >> 2) | (1u << 30);
+}
+
+/* ---- x86 BCJ (C/Bra86.c:50-170).  CALL / JMP rel32 (E8 / E9) whose operand's top byte is 00 or FF become absolute.  A 3-bit history
+ * of the opcode bytes just passed without a conversion (bit 2 = one byte back ... bit 0 = three back) vetoes or adjusts conversions.
+ * The scan's state dies after three non-opcode bytes, so the buffer falls into CLUSTERS of opcode bytes (successive gaps <= 3) that
+ * are converted independently of each other -- that is what the GPU parallelises over (b2z_filter.cu). */
+B2Z_HD int b2z_x86_is_opcode(uint32_t b) { return (b & 0xFEu) == 0xE8u; }
+B2Z_HD int b2z_x86_is_00_ff(uint32_t b) { b &= 0xFFu; return b == 0u || b == 0xFFu; }
+/* one opcode byte at position i with history hist: returns 1 and the new operand if it is converted.  operand = the 4 bytes after
+ * the opcode (little endian), next = address of the following instruction */
+B2Z_HD int b2z_x86_convert(uint32_t hist, uint32_t operand, uint32_t next, int enc, uint32_t *out) {
+    uint32_t fix = 0;
+    if (hist == 0u) { if (!b2z_x86_is_00_ff(operand >> 24)) return 0; }
+    else if (hist == 1u || hist == 2u || hist == 4u) {
+        fix = hist >> 1;
+        if (b2z_x86_is_00_ff(operand >> (8u * fix)) || !b2z_x86_is_00_ff(operand >> 24)) return 0;
+    } else return 0;
+    uint32_t v = operand + (1u << 24);
+    v = enc ? v + next : v - next;
+    if (hist != 0u && b2z_x86_is_00_ff(v >> (8u * fix))) { v ^= (0x100u << (8u * fix)) - 1u; v = enc ? v + next : v - next; }
+    *out = (v & 0x1FFFFFFu) - (1u << 24);
+    return 1;
 }
 
 #endif

@@ -172,8 +172,8 @@ int b200z_xz_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, vo
 
 /* ---- pre/post filters of a 7z folder / xz filter chain on the GPU -----------------------------------
  * In place.  methodId = 7-Zip's filter id: 0x03 Delta (prop = distance 1..256; CPP/7zip/Compress/DeltaFilter.cpp, C/Delta.c),
- * 0x0A ARM64, 0x03030501 ARM, 0x03030205 PPC, 0x03030805 SPARC (prop = start offset; BranchMisc.cpp -> C/Bra.c z7_BranchConv_*).
- * The converters whose scan carries state (x86 BCJ, BCJ2, ARMT, RISCV, IA64) return B200Z_E_UNSUPPORTED. */
+ * 0x03030103 x86 BCJ (C/Bra86.c), 0x0A ARM64, 0x03030501 ARM, 0x03030205 PPC, 0x03030805 SPARC (prop = start offset;
+ * BranchMisc.cpp -> C/Bra.c z7_BranchConv_*).  BCJ2, ARMT, RISCV, IA64 return B200Z_E_UNSUPPORTED. */
 int b200z_filter_device(b200z_ctx *ctx, uint32_t methodId, int encode, void *d_data, size_t n, uint32_t prop);
 int b200z_filter_host(b200z_ctx *ctx, uint32_t methodId, int encode, void *data, size_t n, uint32_t prop);
 

@@ -15,10 +15,37 @@ static void delta(uint8_t *d, size_t n, uint32_t dist, int enc) {
     else for (size_t i = dist; i < n; i++) d[i] = (uint8_t)(d[i] + d[i - dist]);
 }
 
+/* x86 BCJ (C/Bra86.c:50-170, the whole buffer in one call, state 0): CALL / JMP rel32 (opcodes E8 / E9) whose operand's top byte is
+ * 00 or FF become absolute (address of the next instruction added; subtracted when decoding), kept within 25 bits and sign-extended.
+ * A 3-bit history of the opcode bytes just passed WITHOUT a conversion (bit 2 = one byte back, bit 1 = two, bit 0 = three) vetoes or
+ * adjusts conversions that sit inside what may be another instruction's operand. */
+static int is_00_ff(uint32_t b) { return (b & 0xFF) == 0x00 || (b & 0xFF) == 0xFF; }
+static void x86(uint8_t *d, size_t n, uint32_t pc, int enc) {
+    uint32_t hist = 0;
+    size_t i = 0;
+    while (i + 5 <= n) {
+        if ((d[i] & 0xFE) != 0xE8) { hist >>= 1; i++; continue; }
+        int convert = 0; uint32_t fix = 0;
+        if (hist == 0) convert = is_00_ff(d[i + 4]);
+        else if (hist == 1 || hist == 2 || hist == 4) {              /* exactly one opcode byte in the last three */
+            fix = hist >> 1;                                         /* the operand byte that lines up with it: 0, 1 or 2 */
+            convert = !is_00_ff(d[i + 1 + fix]) && is_00_ff(d[i + 4]);
+        }
+        if (!convert) { hist = (hist >> 1) | 4; i++; continue; }
+        const uint32_t next = pc + (uint32_t)i + 5u;                 /* address of the instruction after this one */
+        uint32_t v = ld_le(d + i + 1) + (1u << 24);                  /* biased: the 25-bit field is 0 .. 2^25 */
+        v = enc ? v + next : v - next;
+        if (hist != 0 && is_00_ff(v >> (8 * fix))) { v ^= (0x100u << (8 * fix)) - 1u; v = enc ? v + next : v - next; }
+        st_le(d + i + 1, (v & 0x1FFFFFFu) - (1u << 24));
+        hist = 0; i += 5;
+    }
+}
+
 /* methodId: 7-Zip's (3 delta, 0xA ARM64, 0x3030205 PPC, 0x3030501 ARM, 0x3030805 SPARC); prop: delta distance 1..256 / start offset */
 int b2zo_filter(uint32_t methodId, int enc, void *datav, size_t n, uint32_t prop) {
     uint8_t *d = (uint8_t *)datav;
     if (methodId == 3) { if (prop < 1 || prop > 256) return -1; delta(d, n, prop, enc); return 0; }
+    if (methodId == 0x03030103u) { x86(d, n, prop, enc); return 0; }
     for (size_t i = 0; i + 4 <= n; i += 4) {
         const uint32_t ia = prop + (uint32_t)i;                    /* address of this instruction */
         if (methodId == 0xA) {

@@ -89,6 +89,12 @@ void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t 
             cuemu::launch(dim3(1), dim3(256), 0, [&] { delta_scan_kernel(sums.data(), tiles, prop); });
             cuemu::launch(dim3(tiles), dim3(256), 0, [&] { delta_dec_kernel(data, n, prop, rows, sums.data()); });
         }
+    } else if (methodId == B200Z_F_X86) {
+        if (n >= 5) {
+            std::vector<uint8_t> copy(data, data + n);
+            const uint64_t threads = (n + 31) / 32;
+            cuemu::launch(dim3((uint32_t)((threads + 127) / 128)), dim3(128), 0, [&] { x86_kernel(copy.data(), data, n, prop, enc); });
+        }
     } else {
         const uint64_t nWords = n >> 2;
         if (nWords) cuemu::launch(dim3((uint32_t)((nWords + 255) / 256 < 32 ? (nWords + 255) / 256 : 32)), dim3(256), 0, [&] { bra_kernel((uint32_t*)data, nWords, methodId, enc, prop); });

@@ -13,7 +13,7 @@ import pytest
 import helpers as H
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DELTA, ARM64, PPC, ARM, SPARC = 0x03, 0x0A, 0x03030205, 0x03030501, 0x03030805
+DELTA, ARM64, PPC, ARM, SPARC, X86 = 0x03, 0x0A, 0x03030205, 0x03030501, 0x03030805, 0x03030103
 REF_NAME = {ARM64: "ARM64", ARM: "ARM", PPC: "PPC", SPARC: "SPARC"}
 
 
@@ -37,6 +37,11 @@ def ref_filter(method, enc, data, prop):
         f = R.Delta_Encode if enc else R.Delta_Decode
         f.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t]
         f(state, prop, buf.ctypes.data, len(data))
+    elif method == X86:
+        f = R.z7_BranchConvSt_X86_Enc if enc else R.z7_BranchConvSt_X86_Dec
+        f.restype = ctypes.c_void_p; f.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
+        state = ctypes.c_uint32(0)
+        f(buf.ctypes.data, len(data), prop, ctypes.byref(state))
     else:
         f = getattr(R, f"z7_BranchConv_{REF_NAME[method]}_{'Enc' if enc else 'Dec'}")
         f.restype = ctypes.c_void_p; f.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32]
@@ -85,6 +90,24 @@ def test_branch_converters_equal_the_reference(method):
             assert oracle_filter(method, 0, data, prop) == ref_filter(method, 0, data, prop)     # decoding arbitrary words agrees too
 
 
+def x86_soup(n, density, seed):
+    """bytes dense in E8 / E9 opcodes and 00 / FF operand tops: long chains of overlapping candidates"""
+    rng = random.Random(seed)
+    return bytes(rng.choice([0xE8, 0xE9]) if rng.random() < density else (rng.choice([0, 0xFF]) if rng.random() < 0.4 else rng.randrange(256)) for _ in range(n))
+
+
+def test_x86_bcj_equals_the_reference():
+    rng = random.Random(2)
+    for it in range(1200):
+        n = rng.choice([0, 1, 4, 5, 6, 9, 17, 100, 1000, 5000]); pc = rng.choice([0, 0x1000, 0xFFFFFF00, rng.getrandbits(32)])
+        data = x86_soup(n, rng.choice([0.02, 0.2, 0.5]), it)
+        enc = oracle_filter(X86, 1, data, pc)
+        assert oracle_filter(X86, 0, enc, pc) == data
+        for e in (1, 0):
+            r = ref_filter(X86, e, data, pc)
+            assert r is None or r == oracle_filter(X86, e, data, pc), (it, n, e)
+
+
 def test_delta_equals_the_reference(pkg):
     data = pkg.corpus.entropy_class(2, 100_001).tobytes() + bytes(range(256)) * 40
     for dist in (1, 2, 3, 4, 7, 16, 255, 256):
@@ -112,6 +135,11 @@ def test_emulated_kernels_equal_the_oracle(pkg):
         for enc in (1, 0):
             assert emu(method, enc, data, 0x00ABC000) == oracle_filter(method, enc, data, 0x00ABC000), (hex(method), enc)
             assert emu(method, enc, data, 0xFFFFF000) == oracle_filter(method, enc, data, 0xFFFFF000), (hex(method), enc, "addresses that wrap")
+    for seed, dens in ((1, 0.02), (2, 0.2), (3, 0.5), (4, 0.9)):       # x86: sparse opcodes ... one endless cluster
+        for n in (0, 4, 5, 31, 32, 33, 37, 100, 4096, 70_001):
+            data = x86_soup(n, dens, seed * 100 + n % 7)
+            for enc in (1, 0):
+                assert emu(X86, enc, data, 0x00400000) == oracle_filter(X86, enc, data, 0x00400000), (dens, n, enc)
     data = pkg.corpus.entropy_class(2, 300_001).tobytes()
     for dist in (1, 3, 4, 255, 256):
         for n in (1, dist, 65536, 65537, len(data)):                 # around the 64 KiB tiles of the decoder

@@ -4,7 +4,7 @@ GPU budget was spent; their sources are checked through the host emulation in te
 import numpy as np
 import pytest
 
-from test_filters import ARM, ARM64, DELTA, PPC, SPARC, instruction_soup, oracle_filter, ref_filter
+from test_filters import ARM, ARM64, DELTA, PPC, SPARC, X86, instruction_soup, oracle_filter, ref_filter, x86_soup
 
 pytestmark = pytest.mark.gpu
 
@@ -19,10 +19,24 @@ def test_branch_converters(pkg, codec):
             assert r is None or enc == r
             assert codec.filter(method, False, enc, prop) == data
     with pytest.raises(pkg.B200zError) as e:
-        codec.filter(0x03030103, True, b"\xe8" * 64, 0)              # x86 BCJ: state-carrying scan, left to the host
+        codec.filter(0x0303011B, True, b"\xe8" * 64, 0)              # BCJ2: four streams + a range coder, left to the host
     assert e.value.code == -6
     with pytest.raises(pkg.B200zError):
         codec.filter(ARM64, True, bytes(64), 2)                       # start offset must be a multiple of 4 (BranchMisc.cpp:57)
+
+
+def test_x86_bcj(pkg, codec):
+    for dens in (0.01, 0.2, 0.6):
+        data = x86_soup(3_000_003, dens, 31)
+        for pc in (0, 0x00400000):
+            enc = codec.filter(X86, True, data, pc)
+            assert enc == oracle_filter(X86, 1, data, pc), dens
+            r = ref_filter(X86, 1, data, pc)
+            assert r is None or enc == r
+            assert codec.filter(X86, False, enc, pc) == data
+    for n in (0, 1, 4, 5, 6):
+        d = b"\xe8\x01\x02\x03\x00\xe8"[:n]
+        assert codec.filter(X86, True, d, 0) == oracle_filter(X86, 1, d, 0)
 
 
 def test_delta(pkg, codec):
