@@ -7,8 +7,9 @@
 //            (the layout `xz -T` / XzEnc.c:1236 Xz_Encode with blockSize write).  Check: none, CRC32 or CRC64 (7-Zip's default, Xz.h:34).
 //   reader   Stream Header / Blocks / Index / Footer are parsed and verified on the host (CRC32 of the small fields); the Blocks'
 //            LZMA2 payloads are spliced into one chunk stream for the GPU decoder (their end markers dropped), the Block checks
-//            are verified on the decoded bytes while they are still in HBM.  A SHA-256 check is skipped (decoded, not verified);
-//            filter chains other than a single LZMA2 are B200Z_E_UNSUPPORTED.
+//            are verified on the decoded bytes while they are still in HBM.  A SHA-256 check is skipped (decoded, not verified).
+//            Filters in front of LZMA2 -- Delta, x86, PowerPC, ARM, SPARC, ARM64 -- are undone on the GPU (b2z_filter.cu) per Block;
+//            IA64, ARM-Thumb and RISC-V chains are B200Z_E_UNSUPPORTED.
 // Format: https://tukaani.org/xz/xz-file-format.txt as implemented by C/Xz.c, C/XzEnc.c:150-330 (headers, index, footer), C/XzDec.c:1126-1600.
 #include <vector>
 #include "b2z_ctx.h"
@@ -123,14 +124,33 @@ int b200z_xz_parse(const void* srcv, size_t n, b200z_xz_block* blocks, uint32_t 
             if (n - ip < hs || get32(s + ip + hs - 4) != crc32_small(s + ip, hs - 4)) return B200Z_E_CORRUPT;
             const uint8_t fl = s[ip + 1];
             if (fl & 0x3C) return B200Z_E_UNSUPPORTED;
-            size_t k = 2; uint64_t pack = ~0ull, unpack = ~0ull, v; size_t m;
+            size_t k = 2; uint64_t pack = ~0ull, unpack = ~0ull; size_t m;
             if (fl & 0x40) { m = get_vli(s + ip + k, hs - 4 - k, &pack); if (!m) return B200Z_E_CORRUPT; k += m; }
             if (fl & 0x80) { m = get_vli(s + ip + k, hs - 4 - k, &unpack); if (!m) return B200Z_E_CORRUPT; k += m; }
-            if ((fl & 3) != 0) return B200Z_E_UNSUPPORTED;          // more than one filter (BCJ / delta in front of LZMA2)
-            m = get_vli(s + ip + k, hs - 4 - k, &v); if (!m) return B200Z_E_CORRUPT; k += m;
-            if (v != 0x21) return B200Z_E_UNSUPPORTED;
-            m = get_vli(s + ip + k, hs - 4 - k, &v); if (!m || v != 1 || k + m >= hs - 4) return B200Z_E_CORRUPT; k += m;
-            const uint32_t dictProp = s[ip + k++];
+            // List of Filter Flags: up to three filters in front of LZMA2, which must come last (xz-file-format 3.1.3 / Xz.h:68 XZ_NUM_FILTERS_MAX).
+            // Kept as 7-Zip method ids + one property each, for b200z_filter_device: Delta 0x03 (distance), x86 0x04, PowerPC 0x05, ARM 0x07,
+            // SPARC 0x09, ARM64 0x0A (start offset); IA64 0x06, ARM-Thumb 0x08, RISC-V 0x0B are not built -> unsupported
+            const uint32_t nf = (fl & 3u) + 1u;
+            uint32_t fId[3] = { 0, 0, 0 }, fProp[3] = { 0, 0, 0 }, dictProp = 0;
+            for (uint32_t f = 0; f < nf; f++) {
+                uint64_t id, psz;
+                m = get_vli(s + ip + k, hs - 4 - k, &id); if (!m) return B200Z_E_CORRUPT; k += m;
+                m = get_vli(s + ip + k, hs - 4 - k, &psz); if (!m || k + m + psz > hs - 4) return B200Z_E_CORRUPT; k += m;
+                if (f + 1 == nf) {
+                    if (id != 0x21) return (id == 0x03 || (id >= 0x04 && id <= 0x0B)) ? B200Z_E_CORRUPT : B200Z_E_UNSUPPORTED;   // a filter that cannot be last / not LZMA2
+                    if (psz != 1) return B200Z_E_CORRUPT;
+                    dictProp = s[ip + k];
+                } else if (id == 0x03) {
+                    if (psz != 1) return B200Z_E_CORRUPT;
+                    fId[f] = 0x03u; fProp[f] = (uint32_t)s[ip + k] + 1u;
+                } else if (id == 0x04 || id == 0x05 || id == 0x07 || id == 0x09 || id == 0x0A) {
+                    if (psz != 0 && psz != 4) return B200Z_E_CORRUPT;
+                    fId[f] = id == 0x04 ? 0x03030103u : (id == 0x05 ? 0x03030205u : (id == 0x07 ? 0x03030501u : (id == 0x09 ? 0x03030805u : 0x0Au)));
+                    fProp[f] = psz ? get32(s + ip + k) : 0u;
+                    if (id != 0x04 && (fProp[f] & 3u)) return B200Z_E_UNSUPPORTED;      // BranchMisc.cpp:99
+                } else return B200Z_E_UNSUPPORTED;                  // 0x21 in front, IA64, ARM-Thumb, RISC-V, unknown ids
+                k += (size_t)psz;
+            }
             if (dictProp > 40) return B200Z_E_CORRUPT;
             for (; k < hs - 4; k++) if (s[ip + k]) return B200Z_E_CORRUPT;
             const size_t dataOff = ip + hs;
@@ -148,6 +168,7 @@ int b200z_xz_parse(const void* srcv, size_t n, b200z_xz_block* blocks, uint32_t 
             if (blocks && nb < cap) {
                 b200z_xz_block& B = blocks[nb];
                 B.packOff = dataOff; B.packSize = pack; B.unpackSize = unpack; B.dictProp = dictProp; B.checkType = checkType; B.check = 0;
+                B.nFilters = nf - 1u; for (uint32_t f = 0; f < 3; f++) { B.filterId[f] = fId[f]; B.filterProp[f] = fProp[f]; }
                 for (uint32_t i = 0; i < cb && i < 8; i++) B.check |= (uint64_t)s[dataOff + padded + i] << (8 * i);
             }
             nb++; tot += unpack;
@@ -256,6 +277,30 @@ int b200z_xz_decompress_host(b200z_ctx* ctx, const void* srcv, size_t n, void* d
             uint64_t acc = 0;
             while (ci < cuts.size() && acc < b.unpackSize) acc += cuts[ci++].dstSize;
             if (acc != b.unpackSize) return fail(ctx, B200Z_E_CORRUPT, "xz: Block size differs from its header%s");
+        }
+    }
+    // Filters in front of LZMA2 (xz --x86, --delta ...): undone per Block, last filter first, on the decoded bytes in HBM; the Block's
+    // bytes are then copied to the caller again.  A filter's position counter starts at its start offset in every Block.
+    {
+        uint64_t pos = 0;
+        for (uint32_t i = 0; i < nb; i++) {
+            const b200z_xz_block& b = blocks[i];
+            if (b.nFilters && b.unpackSize) {
+                uint8_t* d = (uint8_t*)ctx->dOut.p + pos;
+                const bool staged = ((uintptr_t)d & 3u) != 0;                     // the branch converters want 4-byte alignment
+                if (staged) {
+                    if (ctx->slots.reserve((size_t)b.unpackSize + 64)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
+                    CU(cudaMemcpyAsync(ctx->slots.p, d, (size_t)b.unpackSize, cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+                for (int f = (int)b.nFilters - 1; f >= 0; f--) {
+                    rc = b200z_filter_device(ctx, b.filterId[f], 0, staged ? ctx->slots.p : (void*)d, (size_t)b.unpackSize, b.filterProp[f]);
+                    if (rc) return rc;
+                }
+                if (staged) CU(cudaMemcpyAsync(d, ctx->slots.p, (size_t)b.unpackSize, cudaMemcpyDeviceToDevice, ctx->stream));
+                CU(cudaMemcpyAsync((uint8_t*)dst + pos, d, (size_t)b.unpackSize, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
+            pos += b.unpackSize;
         }
     }
     // Block checks on the decoded bytes, which b200z_lzma2_decompress_host left in the context's output arena (Streams of one file

@@ -154,13 +154,16 @@ uint64_t b200z_crc64_combine(uint64_t crcA, uint64_t crcB, uint64_t lenB);
 
 /* ---- .xz container around the LZMA2 coder ----------------------------------------------------------
  * Replaces NCompress::NXz::CEncoder / CDecoder (CPP/7zip/Compress/XzEncoder.cpp, XzDecoder.cpp) -> Xz_Encode (C/XzEnc.c:1236) /
- * XzDecMt_Decode (C/XzDec.c) for streams whose Blocks use the LZMA2 filter alone.  The writer emits one Block per 2^FRAMELOG input
+ * XzDecMt_Decode (C/XzDec.c).  The reader takes Blocks whose filter chain is LZMA2, optionally behind Delta / x86 / PowerPC / ARM / SPARC /
+ * ARM64 filters (undone on the GPU); the writer emits LZMA2 alone.  The writer emits one Block per 2^FRAMELOG input
  * bytes with both sizes in the Block header (the layout multi-threaded xz coders write); check type 0 none, 1 CRC32, 4 CRC64
  * (XZ_CHECK_*, C/Xz.h:31-35).  b200z_xz_wrap / b200z_xz_parse are the host-side container logic alone (no device needed). */
 typedef struct {
     uint64_t packOff, packSize;      /* the Block's LZMA2 chunk stream inside the file, end marker included */
     uint64_t unpackSize, check;      /* decoded size; stored check value (low bytes first; 0 when none / longer than 8 bytes) */
     uint32_t dictProp, checkType;
+    uint32_t nFilters;               /* filters in front of LZMA2 (0..3), in encoding order, as 7-Zip method ids for b200z_filter_* */
+    uint32_t filterId[3], filterProp[3];
 } b200z_xz_block;
 size_t b200z_xz_wrap_bound(size_t lzma2Size, uint32_t nBlocks);
 int b200z_xz_wrap(const void *lzma2, size_t lzma2Size, uint32_t dictProp, uint32_t checkType, const uint64_t *checks, uint32_t nChecks,

@@ -108,6 +108,20 @@ def test_x86_bcj_equals_the_reference():
             assert r is None or r == oracle_filter(X86, e, data, pc), (it, n, e)
 
 
+def test_liblzma_filters_agree(pkg):
+    """an implementation that shares no code with the reference: what liblzma's filters write (read back through a raw LZMA2-only
+    decode) is undone by the oracle's statements -- the xz reader relies on exactly this"""
+    import lzma
+    lz2 = {"id": lzma.FILTER_LZMA2, "preset": 0}
+    cases = [(X86, {"id": lzma.FILTER_X86}, x86_soup(200_003, 0.1, 3), 0), (X86, {"id": lzma.FILTER_X86, "start_offset": 0x1000}, x86_soup(50_000, 0.4, 4), 0x1000),
+             (ARM, {"id": lzma.FILTER_ARM}, instruction_soup(ARM, 30_000, 5), 0), (PPC, {"id": lzma.FILTER_POWERPC}, instruction_soup(PPC, 30_000, 6), 0),
+             (SPARC, {"id": lzma.FILTER_SPARC}, instruction_soup(SPARC, 30_000, 7), 0), (DELTA, {"id": lzma.FILTER_DELTA, "dist": 7}, pkg.corpus.entropy_class(2, 100_000).tobytes(), 7)]
+    for method, f, data, prop in cases:
+        filtered = lzma.decompress(lzma.compress(data, format=lzma.FORMAT_RAW, filters=[f, lz2]), format=lzma.FORMAT_RAW, filters=[lz2])
+        assert filtered == oracle_filter(method, 1, data, prop), hex(method)
+        assert oracle_filter(method, 0, filtered, prop) == data
+
+
 def test_delta_equals_the_reference(pkg):
     data = pkg.corpus.entropy_class(2, 100_001).tobytes() + bytes(range(256)) * 40
     for dist in (1, 2, 3, 4, 7, 16, 255, 256):

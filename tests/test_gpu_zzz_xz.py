@@ -38,6 +38,20 @@ def test_foreign_files_and_damage(pkg, codec, inputs):
     data = inputs["g2_1m"]
     for check in (lzma.CHECK_NONE, lzma.CHECK_CRC32, lzma.CHECK_CRC64, lzma.CHECK_SHA256):
         assert codec.xz_decompress(lzma.compress(data, format=lzma.FORMAT_XZ, check=check, preset=1)) == data
+    # filter chains in front of LZMA2 are undone on the GPU (x86-dense and delta-friendly payloads so that the filters do something)
+    from test_filters import x86_soup
+    lz2 = {"id": lzma.FILTER_LZMA2, "preset": 1}
+    exe = x86_soup(500_003, 0.05, 5); ramp = bytes((i * 3) & 0xFF for i in range(400_001))
+    for payload, filt in ((exe, [{"id": lzma.FILTER_X86}]), (exe, [{"id": lzma.FILTER_X86, "start_offset": 0x1000}]), (ramp, [{"id": lzma.FILTER_DELTA, "dist": 3}]),
+                          (exe, [{"id": lzma.FILTER_ARM}]), (exe, [{"id": lzma.FILTER_POWERPC}]), (exe, [{"id": lzma.FILTER_SPARC}]),
+                          (ramp + exe, [{"id": lzma.FILTER_DELTA, "dist": 1}, {"id": lzma.FILTER_X86}])):
+        xzf = lzma.compress(payload, format=lzma.FORMAT_XZ, filters=filt + [lz2])
+        assert codec.xz_decompress(xzf) == payload, filt
+    two = lzma.compress(exe[:100_001], format=lzma.FORMAT_XZ, filters=[{"id": lzma.FILTER_X86}, lz2]) + lzma.compress(exe[100_001:], format=lzma.FORMAT_XZ, filters=[{"id": lzma.FILTER_ARM}, lz2])
+    assert codec.xz_decompress(two) == exe                            # second Stream's Block starts at an odd offset: staged for alignment
+    with pytest.raises(pkg.B200zError) as e:
+        codec.xz_decompress(lzma.compress(exe[:1000], format=lzma.FORMAT_XZ, filters=[{"id": lzma.FILTER_IA64}, lz2]))
+    assert e.value.code == -6
     a = lzma.compress(data[:300_000], format=lzma.FORMAT_XZ); b = lzma.compress(data[300_000:], format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC32, preset=0)
     assert codec.xz_decompress(a + bytes(8) + b) == data              # concatenated Streams
     xz = bytearray(codec.xz_compress(data, 4))

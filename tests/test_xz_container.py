@@ -16,7 +16,8 @@ OPT = 0x10
 
 class XzBlock(ctypes.Structure):
     _fields_ = [("packOff", ctypes.c_uint64), ("packSize", ctypes.c_uint64), ("unpackSize", ctypes.c_uint64), ("check", ctypes.c_uint64),
-                ("dictProp", ctypes.c_uint32), ("checkType", ctypes.c_uint32)]
+                ("dictProp", ctypes.c_uint32), ("checkType", ctypes.c_uint32), ("nFilters", ctypes.c_uint32),
+                ("filterId", ctypes.c_uint32 * 3), ("filterProp", ctypes.c_uint32 * 3)]
 
 
 def _lib(pkg):
@@ -128,5 +129,14 @@ def test_reader_parses_foreign_files_and_rejects_damage(pkg):
         bad = bytearray(xz); bad[pos] ^= 0x40
         assert _parse(L, bytes(bad))[0] in (-5, -6), pos
     assert _parse(L, a + bytes(3) + b)[0] == -5                   # Stream Padding must be a multiple of four bytes
-    f = lzma.compress(data[:50_000], format=lzma.FORMAT_XZ, filters=[{"id": lzma.FILTER_DELTA, "dist": 1}, {"id": lzma.FILTER_LZMA2, "preset": 1}])
-    assert _parse(L, f)[0] == -6                                  # a filter in front of LZMA2: unsupported, not corrupt
+    # filter chains: the ones the GPU can undo come back as 7-Zip method ids + property; the others are unsupported, not corrupt
+    lz2 = {"id": lzma.FILTER_LZMA2, "preset": 1}
+    for filt, want in (([{"id": lzma.FILTER_DELTA, "dist": 4}], [(0x03, 4)]), ([{"id": lzma.FILTER_X86}], [(0x03030103, 0)]),
+                       ([{"id": lzma.FILTER_X86, "start_offset": 0x1000}], [(0x03030103, 0x1000)]), ([{"id": lzma.FILTER_ARM}], [(0x03030501, 0)]),
+                       ([{"id": lzma.FILTER_POWERPC}], [(0x03030205, 0)]), ([{"id": lzma.FILTER_SPARC}], [(0x03030805, 0)]),
+                       ([{"id": lzma.FILTER_DELTA, "dist": 256}, {"id": lzma.FILTER_X86}], [(0x03, 256), (0x03030103, 0)])):
+        rc, blocks, total = _parse(L, lzma.compress(data[:50_000], format=lzma.FORMAT_XZ, filters=filt + [lz2]))
+        assert rc == 0 and total == 50_000 and blocks[0].nFilters == len(want), filt
+        assert [(blocks[0].filterId[i], blocks[0].filterProp[i]) for i in range(len(want))] == want
+    for filt in ([{"id": lzma.FILTER_IA64}], [{"id": lzma.FILTER_ARMTHUMB}]):
+        assert _parse(L, lzma.compress(data[:50_000], format=lzma.FORMAT_XZ, filters=filt + [lz2]))[0] == -6
