@@ -64,9 +64,7 @@ def test_icompresscoder_roundtrip(pkg, tmp_path):
         assert helpers.ref_decompress(comp, len(data)) == data
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("method,level,price_parse", [("lzma2", 5, True), ("lzma2", 4, False), ("flzma2", 5, True), ("flzma2", 2, False)])
-def test_icompresscoder_roundtrip_lzma2(pkg, tmp_path, method, level, price_parse):
+def codec_module_lzma2_roundtrip(pkg, tmp_path, method, level, price_parse):
     """Method 21 through the codec module (CreateEncoder/CreateDecoder by index, as LoadCodecs.cpp does); the packed
     stream must also be accepted by the reference decoder and liblzma.  The level picks the parse as the reference's
     normalisation does (LzmaEnc.c:97 algo = level < 5 ? 0 : 1; fast-lzma2's table: fast below level 3)."""
@@ -82,6 +80,14 @@ def test_icompresscoder_roundtrip_lzma2(pkg, tmp_path, method, level, price_pars
     if helpers.ref_lzma_available():
         assert helpers.ref_lzma2_decompress(comp, len(data), 16) == (data, len(comp))
     assert comp == helpers.oracle_lzma2_compress(data, flags=1 | (2 << 8) | (0x10 if price_parse else 0))[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,level", [("lzma2", 4), ("flzma2", 2)])
+def test_icompresscoder_roundtrip_lzma2(pkg, tmp_path, method, level):
+    """levels below the reference's switch to its optimal parsers: the greedy parse (the price-based parse at levels >= 5 / 3 is
+    covered by tests/test_gpu_zz_lzma2_parse.py)"""
+    codec_module_lzma2_roundtrip(pkg, tmp_path, method, level, False)
 
 
 def test_binding_parameter_ids_match_header(pkg):

@@ -94,6 +94,12 @@ def test_large_frames_batches_and_ratio(pkg):
     c.close()
 
 
+@pytest.mark.parametrize("method,level", [("lzma2", 5), ("flzma2", 5), ("flzma2", 3)])
+def test_codec_module_selects_the_price_based_parse(pkg, tmp_path, method, level):
+    from test_boundary import codec_module_lzma2_roundtrip
+    codec_module_lzma2_roundtrip(pkg, tmp_path, method, level, True)
+
+
 def test_large_roundtrip_property(pkg):
     """size-independent property at a larger size: decode(encode(x)) == x through both GPU paths, many blocks"""
     data = pkg.corpus.g2(64 << 20, seed=78)
