@@ -67,6 +67,23 @@ def test_level_selects_the_parse_and_checksums(pkg, inputs):
     c.close()
 
 
+def test_codec_module_level_selects_the_parse(pkg, tmp_path):
+    """ICompressCoder::Code() of the ZSTD coder class at level 12 (kLevel -> B200Z_P_LEVEL >= 8): stage Z's frames, accepted by the reference decoder"""
+    import os
+    import subprocess
+    PKG = os.path.join(helpers.ROOT, "7-zip-zstd_b200")
+    data = pkg.corpus.g2(5 * (1 << 20) + 999).tobytes() + bytes(300000)
+    src = tmp_path / "in.bin"; packed = tmp_path / "packed.zst"
+    src.write_bytes(data)
+    out = subprocess.run([os.path.join(PKG, "build", "coder_roundtrip"), os.path.join(PKG, "libb200z_7z.so"), str(src), str(packed), "12"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "roundtrip ok" in out.stdout, out.stderr + out.stdout
+    comp = packed.read_bytes()
+    assert comp == helpers.oracle_compress(data, flags=1 | ZOPT)
+    if helpers.ref_available():
+        assert helpers.ref_decompress(comp, len(data)) == data
+
+
 def test_large_frames_batches_and_ratio(pkg):
     data = pkg.corpus.g2(9 * (1 << 20) + 4321).tobytes()
     c = pkg.Codec(0, frame_log=22, window_log=22, zstd_parse=1)
