@@ -71,7 +71,7 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
     L.b200z_lzma2_enc_stage_cp.argtypes = [vp, vp, sz, vp, vp, vp]
     L.b200z_xz_compress_bound.argtypes = [vp, sz]; L.b200z_xz_compress_bound.restype = sz
-    L.b200z_xz_compress_host.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz), ctypes.c_uint32]
+    L.b200z_xz_compress_host.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
     L.b200z_xz_decompress_host.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.b200z_xz_parse.argtypes = [vp, sz, vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)]
     for name in ("b200z_crc32_host", "b200z_crc32_device"):
@@ -304,13 +304,13 @@ class Codec:
         self._check(self.L.b200z_crc64_host(self.h, src.ctypes.data, len(data), ctypes.byref(v)))
         return v.value
 
-    def xz_compress(self, data, check=4) -> bytes:
-        """-> .xz file bytes: one Block per frame; check 0 none, 1 CRC32, 4 CRC64"""
+    def xz_compress(self, data, check=4, filter_id=0, filter_prop=0) -> bytes:
+        """-> .xz file bytes: one Block per frame; check 0 none, 1 CRC32, 4 CRC64; filter_id: 0 or a Codec.filter id run in front of LZMA2"""
         import numpy as np
         src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
         cap = self.L.b200z_xz_compress_bound(self.h, len(data))
         out = np.empty(cap, dtype=np.uint8); sz = ctypes.c_size_t()
-        self._check(self.L.b200z_xz_compress_host(self.h, src.ctypes.data if len(data) else None, len(data), out.ctypes.data, cap, ctypes.byref(sz), check))
+        self._check(self.L.b200z_xz_compress_host(self.h, src.ctypes.data if len(data) else None, len(data), out.ctypes.data, cap, ctypes.byref(sz), check, filter_id, filter_prop))
         return out[:sz.value].tobytes()
 
     def xz_decompress(self, data) -> bytes:

@@ -21,10 +21,12 @@
 namespace b2z {
 
 __global__ void __launch_bounds__(256)
-bra_kernel(uint32_t* __restrict__ words, uint64_t nWords, uint32_t kind, int enc, uint32_t startOffset) {
+bra_kernel(uint32_t* __restrict__ words, uint64_t nWords, uint32_t kind, int enc, uint32_t startOffset, uint32_t unitLog) {
+    // unitLog != 0: the buffer is a run of independent units of 2^unitLog bytes (xz Blocks): addresses restart in each
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t unitMask = unitLog ? ((1ull << unitLog) - 1ull) : ~0ull;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nWords; i += stride) {
-        const uint32_t raw = words[i], ia = startOffset + (uint32_t)(i << 2);
+        const uint32_t raw = words[i], ia = startOffset + (uint32_t)((i << 2) & unitMask);
         uint32_t out;
         if (kind == B200Z_F_ARM64) out = b2z_conv_arm64(raw, ia, enc);
         else if (kind == B200Z_F_ARM) out = b2z_conv_arm(raw, ia, enc);
@@ -39,8 +41,15 @@ bra_kernel(uint32_t* __restrict__ words, uint64_t nWords, uint32_t kind, int enc
 // the sequential rule, until four positions pass without an opcode byte.  Clusters touch disjoint bytes; every decision reads `in`
 // (a conversion's operand is never looked at again by the scan), results go to `out`, which starts as a copy of `in`.
 __global__ void __launch_bounds__(128)
-x86_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n, uint32_t pc, int enc) {
-    const uint64_t t0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 32u;
+x86_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t nAll, uint32_t pc, int enc, uint32_t unitLog) {
+    // unitLog != 0: independent units of 2^unitLog bytes (xz Blocks; a multiple of the 32-byte span): the scan, its history and the
+    // addresses restart in each, and a unit's last four bytes are never converted
+    const uint64_t tAll = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 32u;
+    if (tAll >= nAll) return;
+    const uint64_t u0 = unitLog ? (tAll >> unitLog) << unitLog : 0ull;              // this span's unit = [u0, u0 + n)
+    const uint64_t n = unitLog ? ((nAll - u0) < (1ull << unitLog) ? (nAll - u0) : (1ull << unitLog)) : nAll;
+    in += u0; out += u0;
+    const uint64_t t0 = tAll - u0;
     if (n < 5u || t0 > n - 5u) return;
     const uint64_t last = n - 5u;                                   // last position that can hold a convertible opcode
     uint32_t back = 0;                                              // opcode flags of the three positions before c (bit 0 = c - 1)
@@ -67,10 +76,11 @@ x86_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n
 }
 
 __global__ void __launch_bounds__(256)
-delta_enc_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n, uint32_t dist) {
+delta_enc_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n, uint32_t dist, uint32_t unitLog) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t unitMask = unitLog ? ((1ull << unitLog) - 1ull) : ~0ull;     // unitLog != 0: the history restarts every 2^unitLog bytes
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (uint8_t)(in[i] - (i >= dist ? in[i - dist] : 0));
+        out[i] = (uint8_t)(in[i] - ((i & unitMask) >= dist ? in[i - dist] : 0));
 }
 
 // tile t = bytes [t * rows * dist, (t + 1) * rows * dist): thread c < dist owns column c (one residue class inside the tile)
@@ -106,8 +116,11 @@ extern "C" {
 
 // In place on a device buffer.  methodId: 7-Zip's filter ids (b2z_filter_ops.h); prop: delta distance (1..256) or the start offset
 // ("pc") of the branch converters.  Branch converters leave a tail of n % 4 bytes untouched, like the reference (C/Bra.h:78-86).
-int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop) {
+}  // extern "C"
+// unitLog != 0 (encode only): the buffer is a run of independent units of 2^unitLog bytes -- the xz writer filters every Block on its own
+int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop, uint32_t unitLog) {
     if (!ctx || (!d_data && n)) return B200Z_E_PARAM;
+    if (unitLog && (!encode || unitLog < 12u)) return fail(ctx, B200Z_E_PARAM, "per-unit filtering is an encoder option (units >= 4 KiB)%s");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (methodId == B200Z_F_DELTA) {
@@ -116,7 +129,7 @@ int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_d
         if (encode) {
             if (ctx->batchStage.reserve(n)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
             CU(cudaMemcpyAsync(ctx->batchStage.p, d_data, n, cudaMemcpyDeviceToDevice, st));
-            b2z::delta_enc_kernel<<<(unsigned)((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535), 256, 0, st>>>((const uint8_t*)ctx->batchStage.p, (uint8_t*)d_data, n, prop);
+            b2z::delta_enc_kernel<<<(unsigned)((n + 255) / 256 < 65535 ? (n + 255) / 256 : 65535), 256, 0, st>>>((const uint8_t*)ctx->batchStage.p, (uint8_t*)d_data, n, prop, unitLog);
             ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
         } else {
             const uint32_t rows = (65536u / prop) ? (65536u / prop) : 1u;
@@ -133,7 +146,7 @@ int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_d
             if (ctx->batchStage.reserve(n)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
             CU(cudaMemcpyAsync(ctx->batchStage.p, d_data, n, cudaMemcpyDeviceToDevice, st));
             const uint64_t threads = (n + 31) / 32;
-            b2z::x86_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->batchStage.p, (uint8_t*)d_data, n, prop, encode);
+            b2z::x86_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->batchStage.p, (uint8_t*)d_data, n, prop, encode, unitLog);
             ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
         }
     } else if (methodId == B200Z_F_ARM64 || methodId == B200Z_F_ARM || methodId == B200Z_F_PPC || methodId == B200Z_F_SPARC) {
@@ -141,12 +154,17 @@ int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_d
         if (prop & 3u) return fail(ctx, B200Z_E_UNSUPPORTED, "start offset must be a multiple of the instruction size%s");   // BranchMisc.cpp:57,99: E_INVALIDARG / E_NOTIMPL
         const uint64_t nWords = n >> 2;
         if (!nWords) return 0;
-        b2z::bra_kernel<<<(unsigned)((nWords + 255) / 256 < 148u * 64u ? (nWords + 255) / 256 : 148u * 64u), 256, 0, st>>>((uint32_t*)d_data, nWords, methodId, encode, prop);
+        b2z::bra_kernel<<<(unsigned)((nWords + 255) / 256 < 148u * 64u ? (nWords + 255) / 256 : 148u * 64u), 256, 0, st>>>((uint32_t*)d_data, nWords, methodId, encode, prop, unitLog);
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
     } else return fail(ctx, B200Z_E_UNSUPPORTED, "filter not built on the GPU (BCJ2 / ARMT / RISCV / IA64)%s");
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     return 0;
+}
+extern "C" {
+
+int b200z_filter_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop) {
+    return b2z_filter_units_device(ctx, methodId, encode, d_data, n, prop, 0);
 }
 
 int b200z_filter_host(b200z_ctx* ctx, uint32_t methodId, int encode, void* data, size_t n, uint32_t prop) {

@@ -20,7 +20,17 @@ template <typename T> cudaError_t launch_crc_pieces(const uint8_t* src, uint64_t
                                                     uint32_t nPieces, T poly, T* out, cudaStream_t st);
 }
 
+int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop, uint32_t unitLog);   // b2z_filter.cu
+
 namespace {
+
+// 7-Zip method id of a filter -> xz Filter ID (xz-file-format 5.3); 0 = not a filter the writer knows
+uint32_t xz_filter_id(uint32_t methodId) {
+    switch (methodId) {
+    case 0x03u: return 0x03u; case 0x03030103u: return 0x04u; case 0x03030205u: return 0x05u; case 0x03030501u: return 0x07u;
+    case 0x03030805u: return 0x09u; case 0x0Au: return 0x0Au; default: return 0u;
+    }
+}
 
 const uint8_t kMagic[6] = { 0xFD, '7', 'z', 'X', 'Z', 0x00 };
 const uint8_t kFooterMagic[2] = { 'Y', 'Z' };
@@ -63,13 +73,15 @@ uint32_t walk_cuts(const uint8_t* lz, size_t n, std::vector<Cut>& cuts, b2z::Lz2
 
 extern "C" {
 
-size_t b200z_xz_wrap_bound(size_t lzma2Size, uint32_t nBlocks) { return lzma2Size + (size_t)nBlocks * 64u + 64u; }
+size_t b200z_xz_wrap_bound(size_t lzma2Size, uint32_t nBlocks) { return lzma2Size + (size_t)nBlocks * 72u + 64u; }
 
 // Host only.  lzma2 = a chunk stream (... 0x00) whose dictionary resets delimit the Blocks; checks[i] = the check value of Block i's
-// uncompressed bytes (ignored for checkType 0).  checkType: 0 none, 1 CRC32, 4 CRC64.
+// uncompressed bytes (ignored for checkType 0).  checkType: 0 none, 1 CRC32, 4 CRC64.  filterId != 0: every Block declares that
+// filter (7-Zip method id; prop = delta distance / start offset) in front of LZMA2 -- the payload must have been filtered per Block.
 int b200z_xz_wrap(const void* lzma2v, size_t lzma2Size, uint32_t dictProp, uint32_t checkType, const uint64_t* checks, uint32_t nChecks,
-                  void* dstv, size_t cap, size_t* out) {
+                  uint32_t filterId, uint32_t filterProp, void* dstv, size_t cap, size_t* out) {
     if (!lzma2v || !dstv || !out || (checkType != 0 && checkType != 1 && checkType != 4) || dictProp > 40) return B200Z_E_PARAM;
+    if (filterId && (!xz_filter_id(filterId) || (filterId == 0x03u && (filterProp < 1 || filterProp > 256)))) return B200Z_E_PARAM;
     const uint8_t* lz = (const uint8_t*)lzma2v; uint8_t* dst = (uint8_t*)dstv;
     std::vector<Cut> cuts;
     b2z::Lz2Counts c;
@@ -84,8 +96,10 @@ int b200z_xz_wrap(const void* lzma2v, size_t lzma2Size, uint32_t dictProp, uint3
     for (size_t b = 0; b < cuts.size(); b++) {
         const uint64_t pack = cuts[b].srcEnd - cuts[b].srcOff + 1;   // + this Block's own end marker
         uint8_t h[64]; size_t k = 1;
-        h[k++] = 0xC0;                                              // one filter; compressed and uncompressed size present
+        h[k++] = (uint8_t)(0xC0 | (filterId ? 1 : 0));              // one or two filters; compressed and uncompressed size present
         k += put_vli(h + k, pack); k += put_vli(h + k, cuts[b].dstSize);
+        if (filterId == 0x03u) { h[k++] = 0x03; h[k++] = 1; h[k++] = (uint8_t)(filterProp - 1u); }
+        else if (filterId) { h[k++] = (uint8_t)xz_filter_id(filterId); h[k++] = filterProp ? 4 : 0; if (filterProp) { put32(h + k, filterProp); k += 4; } }
         h[k++] = 0x21; h[k++] = 1; h[k++] = (uint8_t)dictProp;      // LZMA2, one property byte
         while ((k + 4) & 3) h[k++] = 0;
         h[0] = (uint8_t)((k + 4) / 4 - 1);
@@ -204,19 +218,19 @@ size_t b200z_xz_compress_bound(b200z_ctx* ctx, size_t n) {
     return b200z_xz_wrap_bound(lz, (uint32_t)((n >> fl) + 1));
 }
 
-// XzEncoder.cpp:  .xz with one Block per 2^FRAMELOG input bytes; checkType 0 none, 1 CRC32, 4 CRC64
-int b200z_xz_compress_host(b200z_ctx* ctx, const void* src, size_t n, void* dst, size_t cap, size_t* out, uint32_t checkType) {
+// XzEncoder.cpp:  .xz with one Block per 2^FRAMELOG input bytes; checkType 0 none, 1 CRC32, 4 CRC64.  filterId != 0: that filter
+// (Delta 0x03, x86 0x03030103, PowerPC, ARM, SPARC, ARM64; 7-Zip method ids) runs on the GPU in front of LZMA2, Block by Block
+int b200z_xz_compress_host(b200z_ctx* ctx, const void* src, size_t n, void* dst, size_t cap, size_t* out, uint32_t checkType,
+                           uint32_t filterId, uint32_t filterProp) {
     if (!ctx || !out || (!src && n) || !dst) return B200Z_E_PARAM;
     if (checkType != 0 && checkType != 1 && checkType != 4) return fail(ctx, B200Z_E_PARAM, "xz: check type must be 0 (none), 1 (CRC32) or 4 (CRC64)%s");
+    if (filterId && !xz_filter_id(filterId)) return fail(ctx, B200Z_E_UNSUPPORTED, "xz: filter not built on the GPU%s");
     if (cap < b200z_xz_compress_bound(ctx, n)) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_xz_compress_bound%s");
     CU(cudaSetDevice(ctx->device));
     const size_t lzCap = b200z_lzma2_compress_bound(ctx, n);
     if (ctx->dIn.reserve(n + 64) || ctx->dOut.reserve(lzCap + 64)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
     if (n) { CU(cudaMemcpyAsync(ctx->dIn.p, src, n, cudaMemcpyHostToDevice, ctx->stream)); ctx->stat[B200Z_S_H2D_BYTES] += (double)n; }
-    size_t lzSize = 0; uint32_t prop = 0;
-    int rc = b200z_lzma2_compress_device(ctx, ctx->dIn.p, n, ctx->dOut.p, lzCap, &lzSize, &prop);
-    if (rc) return rc;
-    // Block checks: one piece per frame, on the input while it is still in HBM
+    // Block checks first: they cover the ORIGINAL bytes (one piece per frame, while the input is in HBM)
     const uint32_t fl = ctx->geom.frameLog;
     const uint32_t nFrames = (uint32_t)((n + ((size_t)1 << fl) - 1) >> fl);
     std::vector<uint64_t> checks(nFrames ? nFrames : 1, 0);
@@ -233,10 +247,18 @@ int b200z_xz_compress_host(b200z_ctx* ctx, const void* src, size_t n, void* dst,
         }
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
     }
+    int rc;
+    if (filterId && n) {                                            // every frame = one Block = one independent run of the filter
+        rc = b2z_filter_units_device(ctx, filterId, 1, ctx->dIn.p, n, filterProp, fl);
+        if (rc) return rc;
+    }
+    size_t lzSize = 0; uint32_t prop = 0;
+    rc = b200z_lzma2_compress_device(ctx, ctx->dIn.p, n, ctx->dOut.p, lzCap, &lzSize, &prop);
+    if (rc) return rc;
     std::vector<uint8_t> lz(lzSize);
     CU(cudaMemcpyAsync(lz.data(), ctx->dOut.p, lzSize, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
     ctx->stat[B200Z_S_D2H_BYTES] += (double)lzSize;
-    rc = b200z_xz_wrap(lz.data(), lzSize, prop, checkType, checks.data(), (uint32_t)checks.size(), dst, cap, out);
+    rc = b200z_xz_wrap(lz.data(), lzSize, prop, checkType, checks.data(), (uint32_t)checks.size(), filterId, filterProp, dst, cap, out);
     return rc ? fail(ctx, rc, "xz: container assembly failed%s") : 0;
 }
 

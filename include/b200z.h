@@ -155,7 +155,7 @@ uint64_t b200z_crc64_combine(uint64_t crcA, uint64_t crcB, uint64_t lenB);
 /* ---- .xz container around the LZMA2 coder ----------------------------------------------------------
  * Replaces NCompress::NXz::CEncoder / CDecoder (CPP/7zip/Compress/XzEncoder.cpp, XzDecoder.cpp) -> Xz_Encode (C/XzEnc.c:1236) /
  * XzDecMt_Decode (C/XzDec.c).  The reader takes Blocks whose filter chain is LZMA2, optionally behind Delta / x86 / PowerPC / ARM / SPARC /
- * ARM64 filters (undone on the GPU); the writer emits LZMA2 alone.  The writer emits one Block per 2^FRAMELOG input
+ * ARM64 filters (undone on the GPU); the writer emits LZMA2, optionally behind one of those filters (applied on the GPU per Block).  The writer emits one Block per 2^FRAMELOG input
  * bytes with both sizes in the Block header (the layout multi-threaded xz coders write); check type 0 none, 1 CRC32, 4 CRC64
  * (XZ_CHECK_*, C/Xz.h:31-35).  b200z_xz_wrap / b200z_xz_parse are the host-side container logic alone (no device needed). */
 typedef struct {
@@ -167,10 +167,11 @@ typedef struct {
 } b200z_xz_block;
 size_t b200z_xz_wrap_bound(size_t lzma2Size, uint32_t nBlocks);
 int b200z_xz_wrap(const void *lzma2, size_t lzma2Size, uint32_t dictProp, uint32_t checkType, const uint64_t *checks, uint32_t nChecks,
-                  void *dst, size_t dstCap, size_t *dstSize);
+                  uint32_t filterId, uint32_t filterProp, void *dst, size_t dstCap, size_t *dstSize);
 int b200z_xz_parse(const void *src, size_t srcSize, b200z_xz_block *blocks, uint32_t cap, uint32_t *nBlocks, uint64_t *contentSize);
 size_t b200z_xz_compress_bound(b200z_ctx *ctx, size_t srcSize);
-int b200z_xz_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize, uint32_t checkType);
+int b200z_xz_compress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize, uint32_t checkType,
+                           uint32_t filterId /* 0, or a b200z_filter_* id applied per Block in front of LZMA2 */, uint32_t filterProp);
 int b200z_xz_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, void *dst, size_t dstCap, size_t *dstSize);
 
 /* ---- pre/post filters of a 7z folder / xz filter chain on the GPU -----------------------------------

@@ -75,11 +75,11 @@ uint64_t emu_crc_pieces(const uint8_t* src, uint64_t n, uint32_t pieceLog, const
 }
 
 // filters (b2z_filter.cu), in place on `data`; same launch shapes as b200z_filter_device
-void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t prop) {
+void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t prop, uint32_t unitLog) {
     if (methodId == B200Z_F_DELTA) {
         if (enc) {
             std::vector<uint8_t> copy(data, data + n);
-            cuemu::launch(dim3((uint32_t)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64)), dim3(256), 0, [&] { delta_enc_kernel(copy.data(), data, n, prop); });
+            cuemu::launch(dim3((uint32_t)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64)), dim3(256), 0, [&] { delta_enc_kernel(copy.data(), data, n, prop, unitLog); });
         } else {
             const uint32_t rows = (65536u / prop) ? (65536u / prop) : 1u;
             const uint64_t tileBytes = (uint64_t)rows * prop;
@@ -93,11 +93,11 @@ void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t 
         if (n >= 5) {
             std::vector<uint8_t> copy(data, data + n);
             const uint64_t threads = (n + 31) / 32;
-            cuemu::launch(dim3((uint32_t)((threads + 127) / 128)), dim3(128), 0, [&] { x86_kernel(copy.data(), data, n, prop, enc); });
+            cuemu::launch(dim3((uint32_t)((threads + 127) / 128)), dim3(128), 0, [&] { x86_kernel(copy.data(), data, n, prop, enc, unitLog); });
         }
     } else {
         const uint64_t nWords = n >> 2;
-        if (nWords) cuemu::launch(dim3((uint32_t)((nWords + 255) / 256 < 32 ? (nWords + 255) / 256 : 32)), dim3(256), 0, [&] { bra_kernel((uint32_t*)data, nWords, methodId, enc, prop); });
+        if (nWords) cuemu::launch(dim3((uint32_t)((nWords + 255) / 256 < 32 ? (nWords + 255) / 256 : 32)), dim3(256), 0, [&] { bra_kernel((uint32_t*)data, nWords, methodId, enc, prop, unitLog); });
     }
 }
 

@@ -96,6 +96,25 @@ def x86_soup(n, density, seed):
     return bytes(rng.choice([0xE8, 0xE9]) if rng.random() < density else (rng.choice([0, 0xFF]) if rng.random() < 0.4 else rng.randrange(256)) for _ in range(n))
 
 
+def call_heavy_code(n, seed):
+    """x86-like bytes where BCJ pays: a CALL rel32 every 16 bytes to one of 64 absolute targets -- the relative operands all
+    differ, the absolute ones repeat"""
+    rng = random.Random(seed); targets = [rng.randrange(0, n) for _ in range(64)]
+    out = bytearray(rng.choice(b"\x8b\x45\x89\x55\x48\x83\xc4\x10") for _ in range(n))
+    for pos in range(0, n - 5, 16):
+        rel = (rng.choice(targets) - (pos + 5)) & 0xFFFFFFFF
+        out[pos] = 0xE8; out[pos + 1:pos + 5] = rel.to_bytes(4, "little")
+    return bytes(out)
+
+
+def test_x86_bcj_pays_on_call_heavy_code(pkg):
+    data = call_heavy_code(1 << 20, 3)
+    filtered = oracle_filter(X86, 1, data, 0)
+    assert oracle_filter(X86, 0, filtered, 0) == data
+    plain = len(H.oracle_lzma2_compress(data)[1]); bcj = len(H.oracle_lzma2_compress(filtered)[1])
+    assert bcj < 0.8 * plain, (plain, bcj)
+
+
 def test_x86_bcj_equals_the_reference():
     rng = random.Random(2)
     for it in range(1200):
@@ -138,12 +157,17 @@ def test_delta_equals_the_reference(pkg):
 def test_emulated_kernels_equal_the_oracle(pkg):
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cuemu")])
     E = ctypes.CDLL(os.path.join(HERE, "cuemu", "libcuemu_kernels.so"))
-    E.emu_filter.restype = None; E.emu_filter.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32]
+    E.emu_filter.restype = None; E.emu_filter.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
 
-    def emu(method, enc, data, prop):
+    def emu(method, enc, data, prop, unit_log=0):
         buf = np.frombuffer(bytearray(data) + bytearray(8), dtype=np.uint8)
-        E.emu_filter(method, enc, buf.ctypes.data, len(data), prop)
+        E.emu_filter(method, enc, buf.ctypes.data, len(data), prop, unit_log)
         return buf[:len(data)].tobytes()
+    # per-unit encoding (the xz writer filters every Block on its own): equals the oracle applied unit by unit
+    for method, data, prop in ((X86, x86_soup(3 * 4096 + 1001, 0.3, 8), 0), (ARM64, instruction_soup(ARM64, 3 * 1024 + 100, 8), 0x1000),
+                               (DELTA, bytes((i * 7) & 0xFF for i in range(3 * 4096 + 5)), 3)):
+        want = b"".join(oracle_filter(method, 1, data[i:i + 4096], prop) for i in range(0, len(data), 4096))
+        assert emu(method, 1, data, prop, 12) == want, hex(method)
     for method in (ARM64, ARM, PPC, SPARC):
         data = instruction_soup(method, 20_000, 9) + b"\x01\x02"
         for enc in (1, 0):

@@ -34,6 +34,19 @@ def test_files_we_write_decode_everywhere(pkg, codec, inputs):
     c.close()
 
 
+def test_writer_with_a_gpu_filter_per_block(pkg, codec):
+    from test_filters import x86_soup, instruction_soup
+    exe = x86_soup(3 * (1 << 20) + 12_345, 0.04, 11)
+    for fid, fprop, data in ((0x03030103, 0, exe), (0x03, 4, bytes((i * 5) & 0xFF for i in range((2 << 20) + 77))), (0x03030501, 0, instruction_soup(0x03030501, 600_000, 12))):
+        xz = codec.xz_compress(data, 4, fid, fprop)
+        assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == data, hex(fid)       # liblzma undoes the filter and verifies the CRC64 of the original
+        assert codec.xz_decompress(xz) == data, hex(fid)
+    from test_filters import call_heavy_code
+    code = call_heavy_code(2 << 20, 3)
+    plain = codec.xz_compress(code, 4); bcj = codec.xz_compress(code, 4, 0x03030103, 0)
+    assert len(bcj) < 0.8 * len(plain) and lzma.decompress(bcj, format=lzma.FORMAT_XZ) == code      # absolute call targets repeat; relative ones do not
+
+
 def test_foreign_files_and_damage(pkg, codec, inputs):
     data = inputs["g2_1m"]
     for check in (lzma.CHECK_NONE, lzma.CHECK_CRC32, lzma.CHECK_CRC64, lzma.CHECK_SHA256):

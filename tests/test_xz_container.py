@@ -24,7 +24,7 @@ def _lib(pkg):
     L = pkg.load_library()
     vp, sz, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32
     L.b200z_xz_wrap_bound.restype = sz; L.b200z_xz_wrap_bound.argtypes = [sz, u32]
-    L.b200z_xz_wrap.argtypes = [vp, sz, u32, u32, vp, u32, vp, sz, ctypes.POINTER(sz)]
+    L.b200z_xz_wrap.argtypes = [vp, sz, u32, u32, vp, u32, u32, u32, vp, sz, ctypes.POINTER(sz)]
     L.b200z_xz_parse.argtypes = [vp, sz, ctypes.POINTER(XzBlock), u32, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_uint64)]
     return L
 
@@ -36,12 +36,12 @@ def _crc(kind, data):
     return O.b2zo_crc32(data, len(data)) if kind == 1 else (O.b2zo_crc64(data, len(data)) if kind == 4 else 0)
 
 
-def _wrap(L, lz, prop, kind, data, fl):
+def _wrap(L, lz, prop, kind, data, fl, filter_id=0, filter_prop=0):
     F = 1 << fl
     checks = np.array([_crc(kind, data[i:i + F]) for i in range(0, len(data), F)] or [0], dtype=np.uint64)
     src = np.frombuffer(lz, dtype=np.uint8)
     cap = L.b200z_xz_wrap_bound(len(lz), len(checks)); out = np.zeros(cap, dtype=np.uint8); n = ctypes.c_size_t()
-    rc = L.b200z_xz_wrap(src.ctypes.data, len(lz), prop, kind, checks.ctypes.data, len(checks), out.ctypes.data, cap, ctypes.byref(n))
+    rc = L.b200z_xz_wrap(src.ctypes.data, len(lz), prop, kind, checks.ctypes.data, len(checks), filter_id, filter_prop, out.ctypes.data, cap, ctypes.byref(n))
     assert rc == 0, rc
     return out[:n.value].tobytes()
 
@@ -106,6 +106,27 @@ def test_writer_output_is_decoded_and_verified_by_liblzma_and_the_reference(pkg)
     prop, lz = H.oracle_lzma2_compress(b"")
     xz = _wrap(L, lz, prop, 4, b"", 20)
     assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == b"" and _parse(L, xz)[:1] == (0,) and len(xz) == 32
+
+
+def test_writer_with_a_filter_in_front_of_lzma2(pkg):
+    """what b200z_xz_compress_host(filterId) assembles: every frame filtered on its own (oracle statements of the filters), the
+    filtered bytes through the LZMA2 encoder statement, Blocks that declare the filter -- liblzma and the reference undo it and
+    verify the checks of the ORIGINAL bytes"""
+    from test_filters import oracle_filter, x86_soup, instruction_soup
+    L = _lib(pkg); fl = 17; F = 1 << fl
+    exe = x86_soup(3 * F + 12_345, 0.04, 11)
+    for fid, fprop, data in ((0x03030103, 0, exe), (0x03030103, 0x1000, exe), (0x03, 4, bytes((i * 5) & 0xFF for i in range(2 * F + 77))),
+                             (0x03030501, 0, instruction_soup(0x03030501, (2 * F + 64) // 4, 12)), (0x0A, 0x4000, instruction_soup(0x0A, (2 * F + 64) // 4, 13))):
+        filtered = b"".join(oracle_filter(fid, 1, data[i:i + F], fprop) for i in range(0, len(data), F))
+        prop, lz = H.oracle_lzma2_compress(filtered, frameLog=fl, windowLog=fl, flags=1)
+        xz = _wrap(L, lz, prop, 4, data, fl, fid, fprop)
+        if fid != 0x0A:                                             # this liblzma may predate the ARM64 filter
+            assert lzma.decompress(xz, format=lzma.FORMAT_XZ) == data, hex(fid)
+        r = _ref_unpack(xz, len(data))
+        if r:
+            assert r[0] == 0 and r[1] == data and r[3] != 0, hex(fid)
+        rc, blocks, total = _parse(L, xz)
+        assert rc == 0 and total == len(data) and all(b.nFilters == 1 and b.filterId[0] == fid and b.filterProp[0] == fprop for b in blocks)
 
 
 def test_reader_parses_foreign_files_and_rejects_damage(pkg):
