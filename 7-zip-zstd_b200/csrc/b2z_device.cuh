@@ -12,10 +12,12 @@ namespace b2z {
 __device__ __forceinline__ uint32_t lane_id() { return cuemu_lane_id(); }
 __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << cuemu_lane_id()) - 1u; }
 #define B2Z_DYN_SMEM(T, name) T* const name = reinterpret_cast<T*>(cuemu::dyn_smem())
+#define B2Z_EXTERN_SMEM(T, name) T* const name = reinterpret_cast<T*>(cuemu::dyn_smem())
 #else
 __device__ __forceinline__ uint32_t lane_id() { uint32_t l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
-// the CTA's dynamic shared memory as one struct
+// the CTA's dynamic shared memory as an array (B2Z_EXTERN_SMEM: exactly `extern __shared__ T name[]`) or as one struct
+#define B2Z_EXTERN_SMEM(T, name) extern __shared__ T name[]
 #define B2Z_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; T* const name = reinterpret_cast<T*>(name##_raw_)
 #endif
 

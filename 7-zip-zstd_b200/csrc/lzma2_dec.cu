@@ -34,9 +34,11 @@ __global__ void lzma2_walk_kernel(const uint8_t* __restrict__ src, uint64_t srcS
     *counts = c;
 }
 
+#ifndef B2Z_CUEMU
 void launch_lzma2_walk(const uint8_t* src, uint64_t srcSize, Lz2Block* blocks, uint32_t cap, Lz2Counts* counts, cudaStream_t st) {
     lzma2_walk_kernel<<<1, 32, 0, st>>>(src, srcSize, blocks, cap, counts);
 }
+#endif
 
 enum : uint32_t { OP_END = 0, OP_MATCH = 1, OP_RAW = 2, OP_RESET = 3, OP_ERROR = 4 };
 
@@ -97,7 +99,7 @@ template <bool GLIT>
 __global__ void __launch_bounds__(32)
 lzma2_decode_kernel(const uint8_t* __restrict__ src, const Lz2Block* __restrict__ blocks, uint8_t* __restrict__ dst,
                     uint32_t dictSize, Lz2Counts* counts, uint16_t* __restrict__ litSpill, uint32_t litStride) {
-    extern __shared__ uint16_t probs[];
+    B2Z_EXTERN_SMEM(uint16_t, probs);
     const uint32_t lane = threadIdx.x;
     uint16_t* const lit = GLIT ? litSpill + (size_t)blockIdx.x * litStride : probs + P_LIT;
     const Lz2Block b = blocks[blockIdx.x];
@@ -256,6 +258,7 @@ lzma2_decode_kernel(const uint8_t* __restrict__ src, const Lz2Block* __restrict_
 
 size_t lzma2_lit_spill_bytes(uint32_t nBlocks, uint32_t maxLcLp) { return (size_t)nBlocks * ((size_t)0x300 << maxLcLp) * sizeof(uint16_t); }
 
+#ifndef B2Z_CUEMU
 // mode: 0 = choose by block count, 1 = literal model in shared memory, 2 = literal model in global memory (litSpill required)
 cudaError_t launch_lzma2_decode(const uint8_t* src, const Lz2Block* blocks, uint32_t nBlocks, uint32_t maxLcLp, uint32_t dictSize,
                                 uint8_t* dst, Lz2Counts* counts, uint16_t* litSpill, uint32_t smCount, int mode, cudaStream_t st) {
@@ -273,5 +276,6 @@ cudaError_t launch_lzma2_decode(const uint8_t* src, const Lz2Block* blocks, uint
     }
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace b2z

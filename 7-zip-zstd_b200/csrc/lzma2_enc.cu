@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(64, 16)
 lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint64_t* __restrict__ seqs,
                        const uint32_t* __restrict__ nseq, uint8_t* __restrict__ slots, uint32_t slotStride,
                        uint32_t* __restrict__ slotSize, uint16_t* __restrict__ litSpill, uint32_t* __restrict__ status, uint32_t nChains) {
-    extern __shared__ uint16_t probsAll[];
+    B2Z_EXTERN_SMEM(uint16_t, probsAll);
     constexpr uint32_t LSTEP = 32u / (uint32_t)L;
     if ((threadIdx.x & 31u) % LSTEP) return;                        // one thread per chain; see the header comment
     // chain = (frame, slice): a frame's range coding is split into state-reset slices of sliceBlocks 128 KiB blocks
@@ -248,6 +248,7 @@ size_t lzma2_enc_slot_stride(const EncGeom& g) {
     return ((size_t)B2Z_LZ2_FRAME_BOUND(sliceBytes) + 255u) & ~(size_t)255u;
 }
 
+#ifndef B2Z_CUEMU
 cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
                                    uint8_t* slots, uint32_t* slotSize, uint32_t nFrames, uint16_t* litSpill, uint32_t smCount, int mode,
                                    uint32_t* status, cudaStream_t st) {
@@ -269,6 +270,8 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
     }
     return cudaGetLastError();
 }
+
+#endif
 
 // ---------------------------------------------------------------------------------------------------- assembly
 __global__ void __launch_bounds__(1024)
@@ -333,6 +336,7 @@ lzma2_enc_gather_kernel(const uint8_t* __restrict__ slots, uint32_t slotStride, 
     for (uint32_t i = h + body + tid; i < n; i += 256u) d[i] = s[i];
 }
 
+#ifndef B2Z_CUEMU
 // pieces = chains (frame slices) in stream order
 void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, uint32_t nPieces, uint32_t slotStride, uint64_t* pieceOff,
                                uint8_t* dst, uint64_t* outSize, cudaStream_t st) {
@@ -340,5 +344,6 @@ void launch_lzma2_enc_assemble(const uint8_t* slots, const uint32_t* slotSize, u
     lzma2_enc_offsets_kernel<<<1, 1024, 0, st>>>(slotSize, nPieces, pieceOff, outSize);
     lzma2_enc_gather_kernel<<<dim3(nPieces, 4), 256, 0, st>>>(slots, slotStride, slotSize, pieceOff, nPieces, dst);
 }
+#endif
 
 }  // namespace b2z

@@ -9,6 +9,8 @@
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
 #include "../../7-zip-zstd_b200/csrc/b2z_crc.cu"
 #include "../../7-zip-zstd_b200/csrc/b2z_filter.cu"
+#include "../../7-zip-zstd_b200/csrc/lzma2_enc.cu"
+#include "../../7-zip-zstd_b200/csrc/lzma2_dec.cu"
 
 using namespace b2z;
 
@@ -99,6 +101,44 @@ void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t 
         const uint64_t nWords = n >> 2;
         if (nWords) cuemu::launch(dim3((uint32_t)((nWords + 255) / 256 < 32 ? (nWords + 255) / 256 : 32)), dim3(256), 0, [&] { bra_kernel((uint32_t*)data, nWords, methodId, enc, prop, unitLog); });
     }
+}
+
+// stage R (lzma2_enc_range_kernel, model in shared memory) + assembly: sequences -> the frame-ordered chunk stream with its end marker
+int64_t emu_lzma2_range_and_assemble(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint64_t* seqs, const uint32_t* nseq,
+                                     uint8_t* dst, uint64_t dstCap, int glit) {
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const uint32_t nFrames = (uint32_t)((srcSize + (1ull << frameLog) - 1) >> frameLog);
+    const uint32_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
+    const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
+    constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
+    std::vector<uint8_t> slots((size_t)nChains * stride, 0xCD); std::vector<uint32_t> slotSize(nChains + 1, 0xCDCDCDCDu); uint32_t status = 0;
+    std::vector<uint16_t> spill(glit ? (size_t)nChains * LITN : 1);
+    if (glit) cuemu::launch(dim3((nChains + 1u) / 2u), dim3(64), 2u * P_LIT * sizeof(uint16_t), [&] {
+        lzma2_enc_range_kernel<true, 1>(src, srcSize, g, seqs, nseq, slots.data(), stride, slotSize.data(), spill.data(), &status, nChains); });
+    else cuemu::launch(dim3(nChains), dim3(32), ((size_t)P_LIT + LITN) * sizeof(uint16_t), [&] {
+        lzma2_enc_range_kernel<false, 1>(src, srcSize, g, seqs, nseq, slots.data(), stride, slotSize.data(), nullptr, &status, nChains); });
+    if (status) return -1;
+    std::vector<uint64_t> off(nChains + 2); uint64_t outSize = 0;
+    cuemu::launch(dim3(1), dim3(1024), 0, [&] { lzma2_enc_offsets_kernel(slotSize.data(), nChains, off.data(), &outSize); });
+    if (outSize > dstCap) return -2;
+    cuemu::launch(dim3(nChains, 4), dim3(256), 0, [&] { lzma2_enc_gather_kernel(slots.data(), stride, slotSize.data(), off.data(), nChains, dst); });
+    return (int64_t)outSize;
+}
+
+// LZMA2 decoder (lzma2_walk_kernel + lzma2_decode_kernel): chunk stream -> bytes; returns the decoded size or -(status)
+int64_t emu_lzma2_decode(const uint8_t* src, uint64_t srcSize, uint32_t dictProp, uint8_t* dst, uint64_t dstCap, int glit) {
+    Lz2Counts counts; std::vector<Lz2Block> blocks(srcSize / 8 + 16);
+    cuemu::launch(dim3(1), dim3(32), 0, [&] { lzma2_walk_kernel(src, srcSize, blocks.data(), (uint32_t)blocks.size(), &counts); });
+    if (counts.status) return -(int64_t)counts.status;
+    if (counts.total > dstCap) return -100;
+    const uint32_t dictSize = dictProp == 40 ? 0xFFFFFFFFu : ((2u | (dictProp & 1u)) << (dictProp / 2u + 11u));
+    const uint32_t litCount = 0x300u << counts.maxLcLp;
+    std::vector<uint16_t> spill(glit ? (size_t)counts.nBlocks * litCount : 1);
+    if (counts.nBlocks) {
+        if (glit) cuemu::launch(dim3(counts.nBlocks), dim3(32), P_LIT * sizeof(uint16_t), [&] { lzma2_decode_kernel<true>(src, blocks.data(), dst, dictSize, &counts, spill.data(), litCount); });
+        else cuemu::launch(dim3(counts.nBlocks), dim3(32), ((size_t)P_LIT + litCount) * sizeof(uint16_t), [&] { lzma2_decode_kernel<false>(src, blocks.data(), dst, dictSize, &counts, nullptr, 0); });
+    }
+    return counts.status ? -(int64_t)counts.status : (int64_t)counts.total;
 }
 
 }

@@ -31,6 +31,9 @@ def emu():
     E.emu_zstd_enc_parse.restype = u64; E.emu_zstd_enc_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp]
     E.emu_zstd_enc_entropy.restype = u64; E.emu_zstd_enc_entropy.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp, vp, u32]
     E.emu_slot_bytes.restype = u32
+    i64 = ctypes.c_int64
+    E.emu_lzma2_range_and_assemble.restype = i64; E.emu_lzma2_range_and_assemble.argtypes = [vp, u64, u32, u32, vp, vp, vp, u64, ctypes.c_int]
+    E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
     return E
 
 
@@ -165,3 +168,35 @@ def test_emulated_stage_e_codes_stage_z_sequences_like_the_oracle(pkg, emu, fl, 
         mine = b"".join(slots[b * SLOT:b * SLOT + ssz[b]].tobytes() for b in range(blk, blk + nb)); blk += nb
         assert mine == body, f0
     assert ip == len(comp) and blk == nblk
+
+
+@pytest.mark.parametrize("fl,sl,opt", [(18, 1, True), (17, 0, False), (18, 0, True)])
+def test_emulated_method21_pipeline_end_to_end(pkg, emu, fl, sl, opt):
+    """every kernel of the method-21 encoder and decoder, as sources, in sequence: stage C -> stage P (or the oracle's stage M
+    sequences for the greedy parse) -> stage R -> offsets + gather = the oracle's stream byte for byte (both placements of the
+    literal model); lzma2_walk_kernel + lzma2_decode_kernel restore the input from it"""
+    data = _mixed(pkg, 250_000); n = len(data)
+    flags = 1 | (sl << 8) | (OPT if opt else 0)
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    F = 1 << fl; nfr = (n + F - 1) // F; bpf = F >> 17
+    if opt:
+        cand = np.zeros(nfr * F * 4, dtype=np.uint32)
+        emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, 2, cand.ctypes.data)
+        seqs = np.zeros(nfr * bpf * H.MAXSEQ, dtype=np.uint64); nseq = np.zeros(nfr * bpf, dtype=np.uint32)
+        emu.emu_lzma2_parse(src.ctypes.data, n, fl, flags, cand.ctypes.data, seqs.ctypes.data, nseq.ctypes.data)
+    else:
+        seqs, nseq, _, _ = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl)
+    prop, want = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=flags)
+    for glit in (0, 1):
+        out = np.zeros(len(want) + 200_000, dtype=np.uint8)
+        r = emu.emu_lzma2_range_and_assemble(src.ctypes.data, n, fl, flags, seqs.ctypes.data, nseq.ctypes.data, out.ctypes.data, out.size, glit)
+        assert r == len(want) and out[:r].tobytes() == want, glit
+    lz = np.frombuffer(want, dtype=np.uint8)
+    for glit in (0, 1):
+        back = np.zeros(n + 64, dtype=np.uint8)
+        assert emu.emu_lzma2_decode(lz.ctypes.data, len(want), prop, back.ctypes.data, n, glit) == n and back[:n].tobytes() == data, glit
+    # a stream of the reference's own encoder through the emulated decoder
+    if H.ref_lzma_available():
+        rprop, rlz = H.ref_lzma2_compress(data, level=5, dict_size=1 << 18, block_size=1 << 18)
+        a = np.frombuffer(rlz, dtype=np.uint8); back = np.zeros(n + 64, dtype=np.uint8)
+        assert emu.emu_lzma2_decode(a.ctypes.data, len(rlz), rprop, back.ctypes.data, n, 0) == n and back[:n].tobytes() == data
