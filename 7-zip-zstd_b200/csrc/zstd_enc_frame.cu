@@ -142,6 +142,7 @@ zstd_enc_scatter_kernel(const uint8_t* __restrict__ src, const uint64_t* __restr
     }
 }
 
+#ifndef B2Z_CUEMU
 void launch_zstd_enc_scatter(const uint8_t* src, const uint64_t* off, const uint32_t* size, uint32_t nFrames, uint32_t frameLog,
                              uint8_t* stage, cudaStream_t st) {
     if (nFrames) zstd_enc_scatter_kernel<<<nFrames, 256, 0, st>>>(src, off, size, frameLog, stage);
@@ -156,5 +157,6 @@ void launch_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, const EncGeo
     zstd_enc_offsets_kernel<<<1, 1024, 0, st>>>(srcSize, g, slotSize, nBlocks, blockOff, outSize, frameOff);
     zstd_enc_gather_kernel<<<nBlocks, 256, 0, st>>>(srcSize, g, slots, slotSize, blockOff, nBlocks, dst, cks);
 }
+#endif
 
 }  // namespace b2z

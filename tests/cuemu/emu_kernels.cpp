@@ -7,6 +7,7 @@
 #include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_frame.cu"
 #include "../../7-zip-zstd_b200/csrc/b2z_crc.cu"
 #include "../../7-zip-zstd_b200/csrc/b2z_filter.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_enc.cu"
@@ -139,6 +140,19 @@ int64_t emu_lzma2_decode(const uint8_t* src, uint64_t srcSize, uint32_t dictProp
         else cuemu::launch(dim3(counts.nBlocks), dim3(32), ((size_t)P_LIT + litCount) * sizeof(uint16_t), [&] { lzma2_decode_kernel<false>(src, blocks.data(), dst, dictSize, &counts, nullptr, 0); });
     }
     return counts.status ? -(int64_t)counts.status : (int64_t)counts.total;
+}
+
+// frame assembly (zstd_enc_checksum / offsets / gather kernels): stage E's slots -> the frames, as launch_zstd_enc_assemble runs them
+int64_t emu_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint8_t* slots, const uint32_t* slotSize,
+                              uint32_t nBlocks, uint8_t* dst, uint64_t dstCap) {
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const uint32_t nFrames = (uint32_t)((srcSize + (1ull << frameLog) - 1) >> frameLog);
+    std::vector<uint64_t> blockOff(nBlocks + 2), frameOff(nFrames + 2); std::vector<uint32_t> cks(nFrames + 2, 0xCDCDCDCDu); uint64_t outSize = 0;
+    if (flags & 2u) cuemu::launch(dim3((nFrames + 63) / 64), dim3(64), 0, [&] { zstd_enc_checksum_kernel(src, srcSize, g, cks.data(), nFrames); });
+    cuemu::launch(dim3(1), dim3(1024), 0, [&] { zstd_enc_offsets_kernel(srcSize, g, slotSize, nBlocks, blockOff.data(), &outSize, frameOff.data()); });
+    if (outSize > dstCap) return -2;
+    cuemu::launch(dim3(nBlocks), dim3(256), 0, [&] { zstd_enc_gather_kernel(srcSize, g, slots, slotSize, blockOff.data(), nBlocks, dst, cks.data()); });
+    return (int64_t)outSize;
 }
 
 }

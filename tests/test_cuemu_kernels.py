@@ -33,6 +33,7 @@ def emu():
     E.emu_slot_bytes.restype = u32
     i64 = ctypes.c_int64
     E.emu_lzma2_range_and_assemble.restype = i64; E.emu_lzma2_range_and_assemble.argtypes = [vp, u64, u32, u32, vp, vp, vp, u64, ctypes.c_int]
+    E.emu_zstd_enc_assemble.restype = i64; E.emu_zstd_enc_assemble.argtypes = [vp, u64, u32, u32, vp, vp, u32, vp, u64]
     E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
     return E
 
@@ -200,3 +201,28 @@ def test_emulated_method21_pipeline_end_to_end(pkg, emu, fl, sl, opt):
         rprop, rlz = H.ref_lzma2_compress(data, level=5, dict_size=1 << 18, block_size=1 << 18)
         a = np.frombuffer(rlz, dtype=np.uint8); back = np.zeros(n + 64, dtype=np.uint8)
         assert emu.emu_lzma2_decode(a.ctypes.data, len(rlz), rprop, back.ctypes.data, n, 0) == n and back[:n].tobytes() == data
+
+
+@pytest.mark.parametrize("fl,flags", [(18, 1), (17, 3), (18, 3 | ZOPT), (17, 1 | ZOPT)])
+def test_emulated_zstd_encoder_end_to_end(pkg, emu, fl, flags):
+    """every kernel of the Zstandard encoder, as sources, in sequence: stage M (or stage C + stage Z) -> stage E -> checksum /
+    offsets / gather = the oracle's frames byte for byte (size hints, XXH64 content checksums), which the reference decoder restores"""
+    data = _mixed(pkg, 300_000) + bytes(140_000); n = len(data)
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    F = 1 << fl; nfr = (n + F - 1) // F; nblk = (n + 131071) // 131072
+    seqs = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); nseq = np.zeros(nblk, dtype=np.uint32); nlit = np.zeros(nblk, dtype=np.uint32); lits = np.zeros(n + 64, dtype=np.uint8)
+    if flags & ZOPT:
+        cand = np.zeros(nfr * F * 4, dtype=np.uint32)
+        emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, 2, cand.ctypes.data)
+        emu.emu_zstd_enc_parse(src.ctypes.data, n, fl, flags, cand.ctypes.data, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
+    else:
+        emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 14, flags, 2, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
+    SLOT = emu.emu_slot_bytes()
+    slots = np.zeros(nblk * SLOT, dtype=np.uint8); ssz = np.zeros(nblk, dtype=np.uint32)
+    emu.emu_zstd_enc_entropy(src.ctypes.data, n, fl, flags, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data, slots.ctypes.data, ssz.ctypes.data, nblk)
+    want = H.oracle_compress(data, frameLog=fl, windowLog=fl, flags=flags)
+    out = np.zeros(len(want) + 100_000, dtype=np.uint8)
+    r = emu.emu_zstd_enc_assemble(src.ctypes.data, n, fl, flags, slots.ctypes.data, ssz.ctypes.data, nblk, out.ctypes.data, out.size)
+    assert r == len(want) and out[:r].tobytes() == want
+    if H.ref_available():
+        assert H.ref_decompress(want, n) == data
