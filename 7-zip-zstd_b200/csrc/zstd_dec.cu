@@ -826,6 +826,7 @@ __global__ void zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const De
 }
 
 // ---------------------------------------------------------------- launchers
+#ifndef B2Z_CUEMU
 void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st) {
     if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 63) / 64, 64, 0, st>>>(src, frames, nFrames, dst, counts);
 }
@@ -873,5 +874,6 @@ void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames
     const uint32_t grid = nFrames < 148u * 32u ? nFrames : 148u * 32u;
     zstd_dec_exec_kernel<<<grid, 32, 0, st>>>(src, frames, nFrames, blocks, lits, seqs, dst, counts);
 }
+#endif
 
 }  // namespace b2z

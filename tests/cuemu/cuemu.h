@@ -33,6 +33,8 @@
 
 struct uint4 { uint32_t x, y, z, w; } __attribute__((aligned(16)));
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+struct uint2 { uint32_t x, y; } __attribute__((aligned(8)));
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
 struct dim3 { uint32_t x, y, z; dim3(uint32_t a = 1, uint32_t b = 1, uint32_t c = 1) : x(a), y(b), z(c) {} };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;

@@ -12,6 +12,7 @@
 #include "../../7-zip-zstd_b200/csrc/b2z_filter.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_enc.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_dec.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_dec.cu"
 
 using namespace b2z;
 
@@ -153,6 +154,47 @@ int64_t emu_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, uint32_t fra
     if (outSize > dstCap) return -2;
     cuemu::launch(dim3(nBlocks), dim3(256), 0, [&] { zstd_enc_gather_kernel(srcSize, g, slots, slotSize, blockOff.data(), nBlocks, dst, cks.data()); });
     return (int64_t)outSize;
+}
+
+// Zstandard decoder: the kernels in the order and shapes of dec_impl (zstd_dec_api.cu) / the launch_zstd_dec_* functions.
+// Returns the decoded size or -(status bits).
+int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap) {
+    if (!srcSize) return 0;
+    uint64_t frameCap = srcSize / 9 + 2, blockCap = srcSize / 3 + 2;
+    { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }
+    std::vector<DecFrame> frames(frameCap); std::vector<DecBlock> blocks(blockCap);
+    DecCounts counts; memset(&counts, 0, sizeof(counts)); uint64_t total = 0;
+    cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_find_frames_kernel(src, srcSize, frames.data(), (uint32_t)frameCap, &counts); });
+    if (counts.status) return -(int64_t)counts.status;
+    const uint32_t nFrames = counts.nFrames;
+    const uint32_t g0 = (nFrames + 63) / 64;
+    if (g0) {
+        cuemu::launch(dim3(g0), dim3(64), 0, [&] { zstd_dec_count_blocks_kernel(src, srcSize, frames.data(), nFrames, &counts); });
+        cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_scan_blocks_kernel(frames.data(), nFrames, (uint32_t)blockCap, &counts); });
+        cuemu::launch(dim3(g0), dim3(64), 0, [&] { zstd_dec_fill_blocks_kernel(src, srcSize, frames.data(), nFrames, blocks.data(), (uint32_t)blockCap, &counts); });
+    }
+    if (counts.status) return -(int64_t)counts.status;
+    const uint32_t nBlocks = counts.nBlocks;
+    std::vector<uint8_t> lits((size_t)nBlocks * 131072ull + 64); std::vector<uint64_t> seqs((size_t)nBlocks * B2Z_DEC_MAXSEQ + 8);
+    std::vector<uint8_t> scratch((size_t)nBlocks * (4096u + 1280u * sizeof(SeqEnt) + sizeof(LitJob) + sizeof(SeqJob)) + 256u, 0xCD);
+    if (nBlocks) {
+        uint8_t* p = scratch.data();
+        uint16_t* hufTabs = (uint16_t*)p; p += (size_t)nBlocks * 4096u;
+        SeqEnt* seqTabs = (SeqEnt*)p; p += (size_t)nBlocks * 1280u * sizeof(SeqEnt);
+        LitJob* litJobs = (LitJob*)p; p += (size_t)nBlocks * sizeof(LitJob);
+        SeqJob* seqJobs = (SeqJob*)p;
+        cuemu::launch(dim3((nBlocks + D1_WARPS(0) - 1) / D1_WARPS(0)), dim3(D1_WARPS(0) * 32), 0, [&] { zstd_dec_entropy_kernel<0>(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs, seqTabs, seqJobs); });
+        cuemu::launch(dim3((nBlocks * 4u + 127u) / 128u), dim3(128), 0, [&] { zstd_dec_lit_streams_kernel(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs); });
+        cuemu::launch(dim3((nBlocks + D1_WARPS(1) - 1) / D1_WARPS(1)), dim3(D1_WARPS(1) * 32), 0, [&] { zstd_dec_entropy_kernel<1>(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs, seqTabs, seqJobs); });
+        cuemu::launch(dim3((nBlocks + 127u) / 128u), dim3(128), 0, [&] { zstd_dec_seq_streams_kernel(src, srcSize, blocks.data(), nBlocks, seqs.data(), seqTabs, seqJobs); });
+    }
+    if (nFrames) cuemu::launch(dim3((nFrames + 127) / 128), dim3(128), 0, [&] { zstd_dec_frame_sizes_kernel(frames.data(), nFrames, blocks.data(), &counts); });
+    cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_frame_offsets_kernel(frames.data(), nFrames, dstCap, &counts, &total); });
+    if (nFrames) {
+        cuemu::launch(dim3(nFrames < 64u ? nFrames : 64u), dim3(32), 0, [&] { zstd_dec_exec_kernel(src, frames.data(), nFrames, blocks.data(), lits.data(), seqs.data(), dst, &counts); });
+        cuemu::launch(dim3((nFrames + 63) / 64), dim3(64), 0, [&] { zstd_dec_verify_kernel(src, frames.data(), nFrames, dst, &counts); });
+    }
+    return counts.status ? -(int64_t)counts.status : (int64_t)total;
 }
 
 }

@@ -34,6 +34,7 @@ def emu():
     i64 = ctypes.c_int64
     E.emu_lzma2_range_and_assemble.restype = i64; E.emu_lzma2_range_and_assemble.argtypes = [vp, u64, u32, u32, vp, vp, vp, u64, ctypes.c_int]
     E.emu_zstd_enc_assemble.restype = i64; E.emu_zstd_enc_assemble.argtypes = [vp, u64, u32, u32, vp, vp, u32, vp, u64]
+    E.emu_zstd_decode.restype = i64; E.emu_zstd_decode.argtypes = [vp, u64, vp, u64]
     E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
     return E
 
@@ -226,3 +227,32 @@ def test_emulated_zstd_encoder_end_to_end(pkg, emu, fl, flags):
     assert r == len(want) and out[:r].tobytes() == want
     if H.ref_available():
         assert H.ref_decompress(want, n) == data
+
+
+def test_emulated_zstd_decoder_on_golden_and_reference_frames(pkg, emu):
+    """the Zstandard decoder's kernels (frame discovery, block index, table + stream entropy kernels, layout, execute, checksum
+    verify), as sources in the order dec_impl launches them: the committed golden frames written by the reference encoder
+    (levels -5 .. 19, checksums, the reference's own regression archives' streams), fresh reference-encoder output, and our
+    own frames of both parses"""
+    import hashlib, json
+    golden = os.path.join(HERE, "golden")
+
+    def dec(comp, n):
+        src = np.frombuffer(comp + bytes(64), dtype=np.uint8); dst = np.zeros(n + 64, dtype=np.uint8)
+        r = emu.emu_zstd_decode(src.ctypes.data, len(comp), dst.ctypes.data, n)
+        return r, dst[:max(r, 0)].tobytes()
+    for idx_name in ("frames.json", "regr.json"):
+        for name, meta in json.load(open(os.path.join(golden, idx_name))).items():
+            if not name.endswith(".zst"):
+                continue
+            r, out = dec(open(os.path.join(golden, name), "rb").read(), meta["size"])
+            assert r == meta["size"] and hashlib.sha256(out).hexdigest() == meta["sha256"], name
+    data = _mixed(pkg, 200_000); n = len(data)
+    streams = [H.oracle_compress(data), H.oracle_compress(data, flags=3 | ZOPT, frameLog=17, windowLog=17)]
+    if H.ref_available():
+        streams += [H.ref_compress(data, level=1), H.ref_compress(data, level=19, checksum=1), H.ref_compress(data, level=5, nbWorkers=2)]
+    for k, comp in enumerate(streams):
+        assert dec(comp, n) == (n, data), k
+    bad = bytearray(streams[1]); bad[len(bad) // 2] ^= 0x20          # damage: an error status or a checksum mismatch, never a wrong "success"
+    r, out = dec(bytes(bad), n)
+    assert not (r == n and out == data)
