@@ -127,11 +127,15 @@ template <class F> inline uint64_t launch(dim3 grid, dim3 block, size_t dynSmemB
     Block b; b.bdim = block; b.gdim = grid; b.nThreads = block.x * block.y * block.z;
     b.fibers.resize(b.nThreads);
     for (auto& f : b.fibers) f.stack = (char*)malloc(kStack);
+#ifdef __SANITIZE_ADDRESS__
+    b.dynSmem = (unsigned char*)malloc(dynSmemBytes ? dynSmemBytes : 1);       // exact size: an overrun of the dynamic shared memory hits a redzone
+#else
     b.dynSmem = (unsigned char*)aligned_alloc(128, (dynSmemBytes + 255) & ~(size_t)127);
+#endif
     b.body = call;
     for (uint32_t z = 0; z < grid.z; z++) for (uint32_t y = 0; y < grid.y; y++) for (uint32_t x = 0; x < grid.x; x++) {
         b.bidx = dim3(x, y, z);
-        memset(b.dynSmem, 0xCD, (dynSmemBytes + 255) & ~(size_t)127);
+        memset(b.dynSmem, 0xCD, dynSmemBytes);
         run_block(b);
     }
     for (auto& f : b.fibers) free(f.stack);

@@ -258,3 +258,14 @@ def ref_lzma2_decompress_mt(comp, n, dict_prop, threads):
     if rc != 0:
         raise ValueError(f"reference lzma2 MT decoder error {rc}")
     return dst[:out.value].tobytes(), bool(mt.value)
+
+
+# ---------------------------------------------------------------- host emulation of the kernel sources (tests/cuemu)
+def cuemu_library():
+    """builds and loads tests/cuemu/libcuemu_kernels.so; with B2Z_CUEMU_ASAN=1 the AddressSanitizer variant (run pytest with
+    LD_PRELOAD=$(/usr/bin/gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0)"""
+    import subprocess
+    d = os.path.join(ROOT, "tests", "cuemu")
+    name = "libcuemu_kernels_asan.so" if os.environ.get("B2Z_CUEMU_ASAN") else "libcuemu_kernels.so"
+    subprocess.check_call(["make", "-s", "-C", d, name])
+    return ctypes.CDLL(os.path.join(d, name))

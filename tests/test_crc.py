@@ -60,8 +60,7 @@ def test_library_combine_arithmetic(pkg):
 
 
 def test_emulated_kernel_equals_the_oracle(pkg):
-    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cuemu")])
-    E = ctypes.CDLL(os.path.join(HERE, "cuemu", "libcuemu_kernels.so"))
+    E = H.cuemu_library()
     vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
     E.emu_crc_pieces.restype = u64; E.emu_crc_pieces.argtypes = [vp, u64, u32, vp, vp, u32, u32, vp]
     O = _oracle()

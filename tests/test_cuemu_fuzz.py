@@ -42,9 +42,7 @@ def _gen(rng, pkg):
 
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_fuzz_emulated_kernels_equal_the_oracle(pkg, seed):
-    d = os.path.join(HERE, "cuemu")
-    subprocess.check_call(["make", "-s", "-C", d])
-    E = ctypes.CDLL(os.path.join(d, "libcuemu_kernels.so"))
+    E = H.cuemu_library()
     vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
     E.emu_zstd_enc_parse.restype = u64; E.emu_zstd_enc_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp]
     E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]

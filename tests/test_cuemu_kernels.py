@@ -21,9 +21,7 @@ OPT = 0x10
 
 @pytest.fixture(scope="module")
 def emu():
-    d = os.path.join(HERE, "cuemu")
-    subprocess.check_call(["make", "-s", "-C", d])
-    E = ctypes.CDLL(os.path.join(d, "libcuemu_kernels.so"))
+    E = H.cuemu_library()
     vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
     E.emu_zstd_enc_match.restype = u64; E.emu_zstd_enc_match.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp, vp, vp, vp]
     E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]

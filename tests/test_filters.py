@@ -155,8 +155,7 @@ def test_delta_equals_the_reference(pkg):
 
 
 def test_emulated_kernels_equal_the_oracle(pkg):
-    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cuemu")])
-    E = ctypes.CDLL(os.path.join(HERE, "cuemu", "libcuemu_kernels.so"))
+    E = H.cuemu_library()
     E.emu_filter.restype = None; E.emu_filter.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
 
     def emu(method, enc, data, prop, unit_log=0):
