@@ -266,6 +266,7 @@ def cuemu_library():
     LD_PRELOAD=$(/usr/bin/gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0)"""
     import subprocess
     d = os.path.join(ROOT, "tests", "cuemu")
-    name = "libcuemu_kernels_asan.so" if os.environ.get("B2Z_CUEMU_ASAN") else "libcuemu_kernels.so"
+    name = ("libcuemu_kernels_asan.so" if os.environ.get("B2Z_CUEMU_ASAN") else
+            "libcuemu_kernels_ubsan.so" if os.environ.get("B2Z_CUEMU_UBSAN") else "libcuemu_kernels.so")     # UBSan: LD_PRELOAD libubsan.so, pytest -s
     subprocess.check_call(["make", "-s", "-C", d, name])
     return ctypes.CDLL(os.path.join(d, name))
