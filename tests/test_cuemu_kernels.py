@@ -254,3 +254,28 @@ def test_emulated_zstd_decoder_on_golden_and_reference_frames(pkg, emu):
     bad = bytearray(streams[1]); bad[len(bad) // 2] ^= 0x20          # damage: an error status or a checksum mismatch, never a wrong "success"
     r, out = dec(bytes(bad), n)
     assert not (r == n and out == data)
+
+
+def test_emulated_stage_z_sequence_array_full(pkg, emu):
+    """a block whose parse wants more sequences than its array holds (32 768; random 3-byte tokens give one length-3 match every
+    three bytes): from there on the matches' bytes stay literals -- the same rule in the oracle and the kernel, and the frame decodes"""
+    import random
+    rng = random.Random(1)
+    toks = [bytes(rng.randrange(256) for _ in range(3)) for _ in range(64)]
+    data = b"".join(rng.choice(toks) for _ in range(90_000))[:2 * 131072 + 5000]; n = len(data); fl = 18
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    zs, zn, zl, znl = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl, flags=1 | ZOPT)
+    assert int(zn[0]) == H.MAXSEQ                                   # the case this test is about
+    nfr = (n + (1 << fl) - 1) >> fl
+    cand = np.zeros(nfr * (1 << fl) * 4, dtype=np.uint32)
+    emu.emu_lzma2_cand(src.ctypes.data, n, fl, 1, 1, cand.ctypes.data)
+    seqZ = np.zeros_like(zs); nsZ = np.zeros_like(zn); nlZ = np.zeros_like(znl); litZ = np.zeros(n + 64, dtype=np.uint8)
+    emu.emu_zstd_enc_parse(src.ctypes.data, n, fl, 1 | ZOPT, cand.ctypes.data, seqZ.ctypes.data, nsZ.ctypes.data, litZ.ctypes.data, nlZ.ctypes.data)
+    assert np.array_equal(nsZ, zn) and np.array_equal(nlZ, znl)
+    for b in range(len(zn)):
+        assert np.array_equal(seqZ[b * H.MAXSEQ:b * H.MAXSEQ + zn[b]], zs[b * H.MAXSEQ:b * H.MAXSEQ + zn[b]]), b
+        assert np.array_equal(litZ[b * 131072:b * 131072 + znl[b]], zl[b * 131072:b * 131072 + znl[b]]), b
+    comp = H.oracle_compress(data, frameLog=fl, windowLog=fl, flags=1 | ZOPT)
+    assert H.oracle_decompress(comp, n) == data
+    if H.ref_available():
+        assert H.ref_decompress(comp, n) == data
