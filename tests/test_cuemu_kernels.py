@@ -279,3 +279,13 @@ def test_emulated_stage_z_sequence_array_full(pkg, emu):
     assert H.oracle_decompress(comp, n) == data
     if H.ref_available():
         assert H.ref_decompress(comp, n) == data
+    # 32 768 sequences take the 3-byte form of the sequence count (>= 0x7F00): stage E writes it, the decoder kernels read it
+    nblk = len(zn); SLOT = emu.emu_slot_bytes()
+    lits = np.zeros(n + 64, dtype=np.uint8); lits[:n] = zl
+    slots = np.zeros(nblk * SLOT, dtype=np.uint8); ssz = np.zeros(nblk, dtype=np.uint32)
+    emu.emu_zstd_enc_entropy(src.ctypes.data, n, fl, 1 | ZOPT, zs.ctypes.data, zn.ctypes.data, lits.ctypes.data, znl.ctypes.data, slots.ctypes.data, ssz.ctypes.data, nblk)
+    out = np.zeros(len(comp) + 100_000, dtype=np.uint8)
+    r = emu.emu_zstd_enc_assemble(src.ctypes.data, n, fl, 1 | ZOPT, slots.ctypes.data, ssz.ctypes.data, nblk, out.ctypes.data, out.size)
+    assert r == len(comp) and out[:r].tobytes() == comp
+    c = np.frombuffer(comp + bytes(64), dtype=np.uint8); back = np.zeros(n + 64, dtype=np.uint8)
+    assert emu.emu_zstd_decode(c.ctypes.data, len(comp), back.ctypes.data, n) == n and back[:n].tobytes() == data
