@@ -84,6 +84,20 @@ def test_codec_module_level_selects_the_parse(pkg, tmp_path):
         assert helpers.ref_decompress(comp, len(data)) == data
 
 
+def test_sequence_array_full(pkg, zcodec):
+    """random 3-byte tokens: a block wants more than 32 768 sequences; the rule for the overflow and the 3-byte sequence-count form"""
+    import random
+    rng = random.Random(1)
+    toks = [bytes(rng.randrange(256) for _ in range(3)) for _ in range(64)]
+    data = b"".join(rng.choice(toks) for _ in range(500_000))[:(1 << 20) + 5000]
+    assert int(helpers.oracle_find_sequences(data, flags=1 | ZOPT)[1].max()) == helpers.MAXSEQ
+    comp = zcodec.compress(data)
+    assert comp == helpers.oracle_compress(data, flags=1 | ZOPT)
+    assert zcodec.decompress(comp) == data
+    if helpers.ref_available():
+        assert helpers.ref_decompress(comp, len(data)) == data
+
+
 def test_large_frames_batches_and_ratio(pkg):
     data = pkg.corpus.g2(9 * (1 << 20) + 4321).tobytes()
     c = pkg.Codec(0, frame_log=22, window_log=22, zstd_parse=1)
