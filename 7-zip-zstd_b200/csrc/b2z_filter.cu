@@ -10,7 +10,8 @@
 //   x86_kernel     the x86 BCJ scan carries a 3-bit history from byte to byte (C/Bra86.c:50-170), but the history dies after three
 //                  non-opcode bytes: the buffer falls into clusters of E8 / E9 bytes that convert independently; threads find the
 //                  cluster starts in their 32-byte spans and run the sequential rule per cluster (b2z_filter_ops.h).
-//   not here       BCJ2 (four output streams + a range coder), ARMT, RISCV, IA64 -- left to the host.
+//   armt_kernel    ARM Thumb BL pairs cannot overlap, so they too convert independently: one thread per halfword position.
+//   not here       BCJ2 (four output streams + a range coder), RISCV, IA64 -- left to the host.
 // Oracle statement: oracle/filter_oracle.c; both are checked against the reference's functions (oracle/_ref/libref_xz.so).
 #include "b2z_device.cuh"
 #include "b2z_filter_ops.h"
@@ -33,6 +34,22 @@ bra_kernel(uint32_t* __restrict__ words, uint64_t nWords, uint32_t kind, int enc
         else if (kind == B200Z_F_PPC) out = b2z_bswap32(b2z_conv_ppc(b2z_bswap32(raw), ia, enc));
         else out = b2z_bswap32(b2z_conv_sparc(b2z_bswap32(raw), ia, enc));
         if (out != raw) words[i] = out;
+    }
+}
+
+// ARM Thumb: one thread per halfword position p (2-byte aligned, p + 4 <= n rounded down to even): a BL pair at p converts on its own
+// (b2z_filter_ops.h).  Reads the ORIGINAL halfwords (`in`), writes to `out` (a copy of `in`): a neighbour's result is never an input.
+__global__ void __launch_bounds__(256)
+armt_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint64_t nHalf, int enc, uint32_t startOffset, uint32_t unitLog) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t unitHalf = unitLog ? (1ull << (unitLog - 1u)) : ~0ull;          // halfwords per independent unit
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < nHalf; i += stride) {
+        const uint64_t inUnit = unitLog ? (i & (unitHalf - 1ull)) : i;
+        if (unitLog && inUnit + 1 >= unitHalf) continue;                           // a pair never straddles two units
+        uint32_t h0 = in[i], h1 = in[i + 1];
+        if (!b2z_armt_is_bl(h0, h1)) continue;
+        b2z_conv_armt(&h0, &h1, startOffset + (uint32_t)(inUnit << 1), enc);
+        out[i] = (uint16_t)h0; out[i + 1] = (uint16_t)h1;
     }
 }
 
@@ -149,6 +166,16 @@ int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void*
             b2z::x86_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint8_t*)ctx->batchStage.p, (uint8_t*)d_data, n, prop, encode, unitLog);
             ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
         }
+    } else if (methodId == B200Z_F_ARMT) {
+        if ((uintptr_t)d_data & 1u) return fail(ctx, B200Z_E_PARAM, "the Thumb converter needs a 2-byte aligned buffer%s");
+        if (prop & 1u) return fail(ctx, B200Z_E_UNSUPPORTED, "start offset must be a multiple of the instruction size%s");
+        const uint64_t nHalf = n >> 1;
+        if (nHalf >= 2) {
+            if (ctx->batchStage.reserve(n)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
+            CU(cudaMemcpyAsync(ctx->batchStage.p, d_data, n, cudaMemcpyDeviceToDevice, st));
+            b2z::armt_kernel<<<(unsigned)((nHalf + 255) / 256 < 148u * 64u ? (nHalf + 255) / 256 : 148u * 64u), 256, 0, st>>>((const uint16_t*)ctx->batchStage.p, (uint16_t*)d_data, nHalf, encode, prop, unitLog);
+            ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        }
     } else if (methodId == B200Z_F_ARM64 || methodId == B200Z_F_ARM || methodId == B200Z_F_PPC || methodId == B200Z_F_SPARC) {
         if ((uintptr_t)d_data & 3u) return fail(ctx, B200Z_E_PARAM, "branch converters need a 4-byte aligned buffer%s");
         if (prop & 3u) return fail(ctx, B200Z_E_UNSUPPORTED, "start offset must be a multiple of the instruction size%s");   // BranchMisc.cpp:57,99: E_INVALIDARG / E_NOTIMPL
@@ -156,7 +183,7 @@ int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void*
         if (!nWords) return 0;
         b2z::bra_kernel<<<(unsigned)((nWords + 255) / 256 < 148u * 64u ? (nWords + 255) / 256 : 148u * 64u), 256, 0, st>>>((uint32_t*)d_data, nWords, methodId, encode, prop, unitLog);
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
-    } else return fail(ctx, B200Z_E_UNSUPPORTED, "filter not built on the GPU (BCJ2 / ARMT / RISCV / IA64)%s");
+    } else return fail(ctx, B200Z_E_UNSUPPORTED, "filter not built on the GPU (BCJ2 / RISCV / IA64)%s");
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
     return 0;

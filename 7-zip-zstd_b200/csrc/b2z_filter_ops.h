@@ -15,6 +15,7 @@
 #define B200Z_F_X86   0x03030103u
 #define B200Z_F_PPC   0x03030205u
 #define B200Z_F_ARM   0x03030501u
+#define B200Z_F_ARMT  0x03030701u
 #define B200Z_F_SPARC 0x03030805u
 
 B2Z_HD uint32_t b2z_bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24); }
@@ -41,6 +42,15 @@ B2Z_HD uint32_t b2z_conv_arm(uint32_t w, uint32_t ia, int enc) {
     if ((w >> 24) != 0xEBu) return w;                               /* BL imm24, relative to the instruction after next */
     const uint32_t t = (ia + 8u) >> 2, imm = enc ? w + t : w - t;
     return 0xEB000000u | (imm & 0x00FFFFFFu);
+}
+/* ARM Thumb BL (C/Bra.c:255-340): a pair of halfwords 11110 hhhhhhhhhhh, 11111 lllllllllll at a 2-byte aligned position; the 22-bit
+ * halfword offset h:l is relative to the instruction address + 4.  Two such pairs cannot overlap (the second halfword of one would
+ * have to start with both 11111 and 11110), so every position converts on its own.  h0 / h1: the halfwords, little endian. */
+B2Z_HD int b2z_armt_is_bl(uint32_t h0, uint32_t h1) { return (h0 & 0xF800u) == 0xF000u && (h1 & 0xF800u) == 0xF800u; }
+B2Z_HD void b2z_conv_armt(uint32_t *h0, uint32_t *h1, uint32_t ia, int enc) {
+    const uint32_t off = ((*h0 & 0x7FFu) << 11) | (*h1 & 0x7FFu), t = (ia + 4u) >> 1;
+    const uint32_t v = enc ? off + t : off - t;
+    *h0 = 0xF000u | ((v >> 11) & 0x7FFu); *h1 = 0xF800u | (v & 0x7FFu);
 }
 B2Z_HD uint32_t b2z_conv_ppc(uint32_t w, uint32_t ia, int enc) {
     if ((w & 0xFC000003u) != 0x48000001u) return w;                 /* bl: AA = 0, LK = 1 */

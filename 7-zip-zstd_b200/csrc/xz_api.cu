@@ -8,8 +8,8 @@
 //   reader   Stream Header / Blocks / Index / Footer are parsed and verified on the host (CRC32 of the small fields); the Blocks'
 //            LZMA2 payloads are spliced into one chunk stream for the GPU decoder (their end markers dropped), the Block checks
 //            are verified on the decoded bytes while they are still in HBM.  A SHA-256 check is skipped (decoded, not verified).
-//            Filters in front of LZMA2 -- Delta, x86, PowerPC, ARM, SPARC, ARM64 -- are undone on the GPU (b2z_filter.cu) per Block;
-//            IA64, ARM-Thumb and RISC-V chains are B200Z_E_UNSUPPORTED.
+//            Filters in front of LZMA2 -- Delta, x86, PowerPC, ARM, ARM-Thumb, SPARC, ARM64 -- are undone on the GPU (b2z_filter.cu) per
+//            Block; IA64 and RISC-V chains are B200Z_E_UNSUPPORTED.
 // Format: https://tukaani.org/xz/xz-file-format.txt as implemented by C/Xz.c, C/XzEnc.c:150-330 (headers, index, footer), C/XzDec.c:1126-1600.
 #include <vector>
 #include "b2z_ctx.h"
@@ -28,7 +28,7 @@ namespace {
 uint32_t xz_filter_id(uint32_t methodId) {
     switch (methodId) {
     case 0x03u: return 0x03u; case 0x03030103u: return 0x04u; case 0x03030205u: return 0x05u; case 0x03030501u: return 0x07u;
-    case 0x03030805u: return 0x09u; case 0x0Au: return 0x0Au; default: return 0u;
+    case 0x03030701u: return 0x08u; case 0x03030805u: return 0x09u; case 0x0Au: return 0x0Au; default: return 0u;
     }
 }
 
@@ -143,7 +143,7 @@ int b200z_xz_parse(const void* srcv, size_t n, b200z_xz_block* blocks, uint32_t 
             if (fl & 0x80) { m = get_vli(s + ip + k, hs - 4 - k, &unpack); if (!m) return B200Z_E_CORRUPT; k += m; }
             // List of Filter Flags: up to three filters in front of LZMA2, which must come last (xz-file-format 3.1.3 / Xz.h:68 XZ_NUM_FILTERS_MAX).
             // Kept as 7-Zip method ids + one property each, for b200z_filter_device: Delta 0x03 (distance), x86 0x04, PowerPC 0x05, ARM 0x07,
-            // SPARC 0x09, ARM64 0x0A (start offset); IA64 0x06, ARM-Thumb 0x08, RISC-V 0x0B are not built -> unsupported
+            // ARM-Thumb 0x08, SPARC 0x09, ARM64 0x0A (start offset); IA64 0x06, RISC-V 0x0B are not built -> unsupported
             const uint32_t nf = (fl & 3u) + 1u;
             uint32_t fId[3] = { 0, 0, 0 }, fProp[3] = { 0, 0, 0 }, dictProp = 0;
             for (uint32_t f = 0; f < nf; f++) {
@@ -157,12 +157,12 @@ int b200z_xz_parse(const void* srcv, size_t n, b200z_xz_block* blocks, uint32_t 
                 } else if (id == 0x03) {
                     if (psz != 1) return B200Z_E_CORRUPT;
                     fId[f] = 0x03u; fProp[f] = (uint32_t)s[ip + k] + 1u;
-                } else if (id == 0x04 || id == 0x05 || id == 0x07 || id == 0x09 || id == 0x0A) {
+                } else if (id == 0x04 || id == 0x05 || id == 0x07 || id == 0x08 || id == 0x09 || id == 0x0A) {
                     if (psz != 0 && psz != 4) return B200Z_E_CORRUPT;
-                    fId[f] = id == 0x04 ? 0x03030103u : (id == 0x05 ? 0x03030205u : (id == 0x07 ? 0x03030501u : (id == 0x09 ? 0x03030805u : 0x0Au)));
+                    fId[f] = id == 0x04 ? 0x03030103u : (id == 0x05 ? 0x03030205u : (id == 0x07 ? 0x03030501u : (id == 0x08 ? 0x03030701u : (id == 0x09 ? 0x03030805u : 0x0Au))));
                     fProp[f] = psz ? get32(s + ip + k) : 0u;
-                    if (id != 0x04 && (fProp[f] & 3u)) return B200Z_E_UNSUPPORTED;      // BranchMisc.cpp:99
-                } else return B200Z_E_UNSUPPORTED;                  // 0x21 in front, IA64, ARM-Thumb, RISC-V, unknown ids
+                    if (id != 0x04 && (fProp[f] & (id == 0x08 ? 1u : 3u))) return B200Z_E_UNSUPPORTED;      // BranchMisc.cpp:99
+                } else return B200Z_E_UNSUPPORTED;                  // 0x21 in front, IA64, RISC-V, unknown ids
                 k += (size_t)psz;
             }
             if (dictProp > 40) return B200Z_E_CORRUPT;
@@ -309,7 +309,7 @@ int b200z_xz_decompress_host(b200z_ctx* ctx, const void* srcv, size_t n, void* d
             const b200z_xz_block& b = blocks[i];
             if (b.nFilters && b.unpackSize) {
                 uint8_t* d = (uint8_t*)ctx->dOut.p + pos;
-                const bool staged = ((uintptr_t)d & 3u) != 0;                     // the branch converters want 4-byte alignment
+                const bool staged = ((uintptr_t)d & 3u) != 0;                     // the branch converters want 4-byte (Thumb: 2-byte) alignment
                 if (staged) {
                     if (ctx->slots.reserve((size_t)b.unpackSize + 64)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
                     CU(cudaMemcpyAsync(ctx->slots.p, d, (size_t)b.unpackSize, cudaMemcpyDeviceToDevice, ctx->stream));

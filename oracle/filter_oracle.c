@@ -46,6 +46,19 @@ int b2zo_filter(uint32_t methodId, int enc, void *datav, size_t n, uint32_t prop
     uint8_t *d = (uint8_t *)datav;
     if (methodId == 3) { if (prop < 1 || prop > 256) return -1; delta(d, n, prop, enc); return 0; }
     if (methodId == 0x03030103u) { x86(d, n, prop, enc); return 0; }
+    if (methodId == 0x03030701u) {                                  /* ARM Thumb: BL = halfwords F000..F7FF, F800..FFFF; 22-bit halfword offset from address + 4 */
+        for (size_t i = 0; i + 4 <= (n & ~(size_t)1);) {
+            const uint32_t a = d[i] | ((uint32_t)d[i + 1] << 8), b = d[i + 2] | ((uint32_t)d[i + 3] << 8);
+            if ((a >> 11) != 0x1E || (b >> 11) != 0x1F) { i += 2; continue; }
+            uint32_t off = ((a & 0x7FF) << 11) | (b & 0x7FF);
+            const uint32_t t = ((prop + (uint32_t)i + 4u) >> 1) & 0x3FFFFF;
+            off = (enc ? off + t : off + 0x400000u - t) & 0x3FFFFF;
+            const uint32_t na = 0xF000u | (off >> 11), nb = 0xF800u | (off & 0x7FF);
+            d[i] = (uint8_t)na; d[i + 1] = (uint8_t)(na >> 8); d[i + 2] = (uint8_t)nb; d[i + 3] = (uint8_t)(nb >> 8);
+            i += 4;
+        }
+        return 0;
+    }
     for (size_t i = 0; i + 4 <= n; i += 4) {
         const uint32_t ia = prop + (uint32_t)i;                    /* address of this instruction */
         if (methodId == 0xA) {

@@ -93,6 +93,12 @@ void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t 
             cuemu::launch(dim3(1), dim3(256), 0, [&] { delta_scan_kernel(sums.data(), tiles, prop); });
             cuemu::launch(dim3(tiles), dim3(256), 0, [&] { delta_dec_kernel(data, n, prop, rows, sums.data()); });
         }
+    } else if (methodId == B200Z_F_ARMT) {
+        const uint64_t nHalf = n >> 1;
+        if (nHalf >= 2) {
+            std::vector<uint8_t> copy(data, data + n);
+            cuemu::launch(dim3((uint32_t)((nHalf + 255) / 256 < 32 ? (nHalf + 255) / 256 : 32)), dim3(256), 0, [&] { armt_kernel((const uint16_t*)copy.data(), (uint16_t*)data, nHalf, enc, prop, unitLog); });
+        }
     } else if (methodId == B200Z_F_X86) {
         if (n >= 5) {
             std::vector<uint8_t> copy(data, data + n);

@@ -4,13 +4,13 @@ GPU budget was spent; their sources are checked through the host emulation in te
 import numpy as np
 import pytest
 
-from test_filters import ARM, ARM64, DELTA, PPC, SPARC, X86, instruction_soup, oracle_filter, ref_filter, x86_soup
+from test_filters import ARM, ARM64, ARMT, DELTA, PPC, SPARC, X86, instruction_soup, oracle_filter, ref_filter, x86_soup
 
 pytestmark = pytest.mark.gpu
 
 
 def test_branch_converters(pkg, codec):
-    for method in (ARM64, ARM, PPC, SPARC):
+    for method in (ARM64, ARM, PPC, SPARC, ARMT):
         data = instruction_soup(method, 1_000_000, 21) + b"\x01\x02\x03"
         for prop in (0, 0x00ABC000):
             enc = codec.filter(method, True, data, prop)

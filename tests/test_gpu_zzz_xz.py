@@ -52,11 +52,11 @@ def test_foreign_files_and_damage(pkg, codec, inputs):
     for check in (lzma.CHECK_NONE, lzma.CHECK_CRC32, lzma.CHECK_CRC64, lzma.CHECK_SHA256):
         assert codec.xz_decompress(lzma.compress(data, format=lzma.FORMAT_XZ, check=check, preset=1)) == data
     # filter chains in front of LZMA2 are undone on the GPU (x86-dense and delta-friendly payloads so that the filters do something)
-    from test_filters import x86_soup
+    from test_filters import x86_soup, instruction_soup
     lz2 = {"id": lzma.FILTER_LZMA2, "preset": 1}
     exe = x86_soup(500_003, 0.05, 5); ramp = bytes((i * 3) & 0xFF for i in range(400_001))
     for payload, filt in ((exe, [{"id": lzma.FILTER_X86}]), (exe, [{"id": lzma.FILTER_X86, "start_offset": 0x1000}]), (ramp, [{"id": lzma.FILTER_DELTA, "dist": 3}]),
-                          (exe, [{"id": lzma.FILTER_ARM}]), (exe, [{"id": lzma.FILTER_POWERPC}]), (exe, [{"id": lzma.FILTER_SPARC}]),
+                          (exe, [{"id": lzma.FILTER_ARM}]), (instruction_soup(0x03030701, 100_000, 3), [{"id": lzma.FILTER_ARMTHUMB}]), (exe, [{"id": lzma.FILTER_POWERPC}]), (exe, [{"id": lzma.FILTER_SPARC}]),
                           (ramp + exe, [{"id": lzma.FILTER_DELTA, "dist": 1}, {"id": lzma.FILTER_X86}])):
         xzf = lzma.compress(payload, format=lzma.FORMAT_XZ, filters=filt + [lz2])
         assert codec.xz_decompress(xzf) == payload, filt

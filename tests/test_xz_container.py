@@ -116,7 +116,7 @@ def test_writer_with_a_filter_in_front_of_lzma2(pkg):
     L = _lib(pkg); fl = 17; F = 1 << fl
     exe = x86_soup(3 * F + 12_345, 0.04, 11)
     for fid, fprop, data in ((0x03030103, 0, exe), (0x03030103, 0x1000, exe), (0x03, 4, bytes((i * 5) & 0xFF for i in range(2 * F + 77))),
-                             (0x03030501, 0, instruction_soup(0x03030501, (2 * F + 64) // 4, 12)), (0x0A, 0x4000, instruction_soup(0x0A, (2 * F + 64) // 4, 13))):
+                             (0x03030501, 0, instruction_soup(0x03030501, (2 * F + 64) // 4, 12)), (0x03030701, 0, instruction_soup(0x03030701, (2 * F + 64) // 4, 14)), (0x0A, 0x4000, instruction_soup(0x0A, (2 * F + 64) // 4, 13))):
         filtered = b"".join(oracle_filter(fid, 1, data[i:i + F], fprop) for i in range(0, len(data), F))
         prop, lz = H.oracle_lzma2_compress(filtered, frameLog=fl, windowLog=fl, flags=1)
         xz = _wrap(L, lz, prop, 4, data, fl, fid, fprop)
@@ -155,9 +155,10 @@ def test_reader_parses_foreign_files_and_rejects_damage(pkg):
     for filt, want in (([{"id": lzma.FILTER_DELTA, "dist": 4}], [(0x03, 4)]), ([{"id": lzma.FILTER_X86}], [(0x03030103, 0)]),
                        ([{"id": lzma.FILTER_X86, "start_offset": 0x1000}], [(0x03030103, 0x1000)]), ([{"id": lzma.FILTER_ARM}], [(0x03030501, 0)]),
                        ([{"id": lzma.FILTER_POWERPC}], [(0x03030205, 0)]), ([{"id": lzma.FILTER_SPARC}], [(0x03030805, 0)]),
+                       ([{"id": lzma.FILTER_ARMTHUMB}], [(0x03030701, 0)]),
                        ([{"id": lzma.FILTER_DELTA, "dist": 256}, {"id": lzma.FILTER_X86}], [(0x03, 256), (0x03030103, 0)])):
         rc, blocks, total = _parse(L, lzma.compress(data[:50_000], format=lzma.FORMAT_XZ, filters=filt + [lz2]))
         assert rc == 0 and total == 50_000 and blocks[0].nFilters == len(want), filt
         assert [(blocks[0].filterId[i], blocks[0].filterProp[i]) for i in range(len(want))] == want
-    for filt in ([{"id": lzma.FILTER_IA64}], [{"id": lzma.FILTER_ARMTHUMB}]):
+    for filt in ([{"id": lzma.FILTER_IA64}],):
         assert _parse(L, lzma.compress(data[:50_000], format=lzma.FORMAT_XZ, filters=filt + [lz2]))[0] == -6
