@@ -233,7 +233,8 @@ lzma2_parse_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
 #pragma unroll
                 for (int t = 0; t < 4; t++) if (cl[t] > bl) { bl = cl[t]; bd = cd[t]; capped = LZP_CAND_LEN(craw[t]) == LZP_CAND_LENCAP; }
                 if (bl >= LZP_NICE) {
-                    longLen = capped ? warp_extend(base, p - bd - 1u, p, 224u, maxLen, lane) : bl;
+                    // a capped word says "at least 255": with no more than that left in the slice bl already is the length
+                    longLen = (capped && maxLen > LZP_CAND_LENCAP) ? warp_extend(base, p - bd - 1u, p, 224u, maxLen, lane) : bl;
                     longDist = bd;
                     break;
                 }

@@ -141,7 +141,8 @@ zstd_enc_parse_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom
 #pragma unroll
                 for (int t = 0; t < 4; t++) if (cl[t] > bl) { bl = cl[t]; bo = co[t]; capped = LZP_CAND_LEN(craw[t]) == LZP_CAND_LENCAP; }
                 if (bl >= LZP_NICE) {
-                    longLen = capped ? warp_extend(base, p - bo, p, 224u, maxLen, lane) : bl;
+                    // a capped word says "at least 255": with no more than that left in the block bl already is the length
+                    longLen = (capped && maxLen > LZP_CAND_LENCAP) ? warp_extend(base, p - bo, p, 224u, maxLen, lane) : bl;
                     longOff = bo;
                     break;
                 }

@@ -270,3 +270,15 @@ def cuemu_library():
             "libcuemu_kernels_ubsan.so" if os.environ.get("B2Z_CUEMU_UBSAN") else "libcuemu_kernels.so")     # UBSan: LD_PRELOAD libubsan.so, pytest -s
     subprocess.check_call(["make", "-s", "-C", d, name])
     return ctypes.CDLL(os.path.join(d, name))
+
+
+def capped_match_near_boundary(pkg):
+    """a match of >= 255 bytes (stage C stores the capped length 255) that starts 100 bytes before a 128 KiB block / slice end and
+    is not a repeat of the previous distance: the long-match path must clip it to the boundary (found by the emulator fuzz: the
+    capped candidate used to be extended from byte 224 even when fewer bytes were left)"""
+    noise = pkg.corpus.entropy_class(1, 131072 * 2 + 5000).tobytes()
+    a = bytearray(noise)
+    chunk = bytes(a[1000:5000])
+    a[131072 - 100:131072 - 100 + 4000] = chunk                     # second copy straddles the boundary at 131072
+    a[131072 + 60_000:131072 + 60_000 + 300] = chunk[:300]          # and one whose whole length (300 > 255) fits: the extension proper
+    return bytes(a)

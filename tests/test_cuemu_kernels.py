@@ -289,3 +289,34 @@ def test_emulated_stage_z_sequence_array_full(pkg, emu):
     assert r == len(comp) and out[:r].tobytes() == comp
     c = np.frombuffer(comp + bytes(64), dtype=np.uint8); back = np.zeros(n + 64, dtype=np.uint8)
     assert emu.emu_zstd_decode(c.ctypes.data, len(comp), back.ctypes.data, n) == n and back[:n].tobytes() == data
+
+
+def test_emulated_capped_candidate_is_clipped_at_the_boundary(pkg, emu):
+    data = H.capped_match_near_boundary(pkg); n = len(data); fl = 18
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    F = 1 << fl; nfr = (n + F - 1) // F; bpf = F >> 17
+    cand = np.zeros(nfr * F * 4, dtype=np.uint32)
+    emu.emu_lzma2_cand(src.ctypes.data, n, fl, 1, 1, cand.ctypes.data)
+    assert int((cand & 0xFF).max()) == 255                          # there are capped words
+    # stage Z (block boundary)
+    zs, zn, zl, znl = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl, flags=1 | ZOPT)
+    seqZ = np.zeros_like(zs); nsZ = np.zeros_like(zn); nlZ = np.zeros_like(znl); litZ = np.zeros(n + 64, dtype=np.uint8)
+    emu.emu_zstd_enc_parse(src.ctypes.data, n, fl, 1 | ZOPT, cand.ctypes.data, seqZ.ctypes.data, nsZ.ctypes.data, litZ.ctypes.data, nlZ.ctypes.data)
+    assert np.array_equal(nsZ, zn) and np.array_equal(nlZ, znl)
+    for b in range(len(zn)):
+        assert np.array_equal(seqZ[b * H.MAXSEQ:b * H.MAXSEQ + zn[b]], zs[b * H.MAXSEQ:b * H.MAXSEQ + zn[b]]), b
+    ml0 = [(int(s) >> 43) & 0x3FFFF for s in zs[:zn[0]]]; ml1 = [(int(s) >> 43) & 0x3FFFF for s in zs[H.MAXSEQ:H.MAXSEQ + zn[1]]]
+    assert any(90 <= m <= 100 for m in ml0) and max(ml0) <= 100       # the capped candidate clipped at the block end ...
+    assert 300 in ml1 and max(ml1) > 3000                             # ... and capped candidates extended past 255 where there is room
+    # stage P (slice boundary: two slices of 128 KiB per 256 KiB frame)
+    flags = 1 | (1 << 8) | OPT
+    candO, seqO, nsO = _oracle_taps(data, fl, flags)
+    seqE = np.zeros_like(seqO); nsE = np.zeros_like(nsO)
+    emu.emu_lzma2_parse(src.ctypes.data, n, fl, flags, cand.ctypes.data, seqE.ctypes.data, nsE.ctypes.data)
+    assert np.array_equal(nsE, nsO)
+    for b in range(len(nsO)):
+        assert np.array_equal(seqE[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]], seqO[b * H.MAXSEQ:b * H.MAXSEQ + nsO[b]]), b
+    prop, lz = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=flags)
+    assert H.oracle_lzma2_decompress(lz, n, prop)[0] == data
+    if H.ref_lzma_available():
+        assert H.ref_lzma2_decompress(lz, n, prop)[0] == data

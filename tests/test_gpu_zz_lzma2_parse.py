@@ -100,6 +100,18 @@ def test_codec_module_selects_the_price_based_parse(pkg, tmp_path, method, level
     codec_module_lzma2_roundtrip(pkg, tmp_path, method, level, True)
 
 
+def test_capped_candidate_is_clipped_at_a_slice_end(pkg):
+    """the case the emulator fuzz found after the first hardware run (helpers.capped_match_near_boundary)"""
+    data = helpers.capped_match_near_boundary(pkg)
+    c = pkg.Codec(0, frame_log=18, window_log=18, lzma2_slice_log=1, lzma2_parse=1)
+    prop, comp = c.lzma2_compress(data)
+    assert (prop, comp) == helpers.oracle_lzma2_compress(data, frameLog=18, windowLog=18, flags=1 | (1 << 8) | OPT)
+    assert c.lzma2_decompress(comp, prop) == data
+    if helpers.ref_lzma_available():
+        assert helpers.ref_lzma2_decompress(comp, len(data), prop)[0] == data
+    c.close()
+
+
 def test_large_roundtrip_property(pkg):
     """size-independent property at a larger size: decode(encode(x)) == x through both GPU paths, many blocks"""
     data = pkg.corpus.g2(64 << 20, seed=78)

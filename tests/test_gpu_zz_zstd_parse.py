@@ -98,6 +98,13 @@ def test_sequence_array_full(pkg, zcodec):
         assert helpers.ref_decompress(comp, len(data)) == data
 
 
+def test_capped_candidate_is_clipped_at_a_block_end(pkg, zcodec):
+    data = helpers.capped_match_near_boundary(pkg)
+    comp = zcodec.compress(data)
+    assert comp == helpers.oracle_compress(data, flags=1 | ZOPT)
+    assert zcodec.decompress(comp) == data
+
+
 def test_large_frames_batches_and_ratio(pkg):
     data = pkg.corpus.g2(9 * (1 << 20) + 4321).tobytes()
     c = pkg.Codec(0, frame_log=22, window_log=22, zstd_parse=1)
