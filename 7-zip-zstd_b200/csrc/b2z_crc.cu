@@ -57,7 +57,57 @@ crc_pieces_kernel(const uint8_t* __restrict__ src, uint64_t n, uint32_t pieceLog
     out[piece] = ~crc;
 }
 
+// ---- SHA-256 (FIPS 180-4) of caller-given ranges, one THREAD per range: the third check type of an xz Block (C/Xz.h:35 XZ_CHECK_SHA256,
+// C/Sha256.c).  A range is hashed sequentially (the compression function chains), ranges run in parallel; digests leave as 8 big-endian
+// words = the 32 bytes in file order.
+__device__ __forceinline__ uint32_t sha_rotr(uint32_t x, uint32_t n) { return (x >> n) | (x << (32u - n)); }
+__constant__ uint32_t c_sha256_k[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2 };
+__device__ inline void sha256_block(uint32_t h[8], const uint8_t* blk) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        const uint32_t s0 = sha_rotr(w[i - 15], 7) ^ sha_rotr(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = sha_rotr(w[i - 2], 17) ^ sha_rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+        const uint32_t t1 = hh + (sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25)) + ((e & f) ^ (~e & g)) + c_sha256_k[i] + w[i];
+        const uint32_t t2 = (sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+__global__ void __launch_bounds__(64)
+sha256_pieces_kernel(const uint8_t* __restrict__ src, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len, uint32_t nPieces, uint32_t* __restrict__ out /* [nPieces][8] */) {
+    const uint32_t piece = blockIdx.x * blockDim.x + threadIdx.x;
+    if (piece >= nPieces) return;
+    const uint8_t* p = src + off[piece]; const uint64_t n = len[piece];
+    uint32_t h[8] = { 0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19 };
+    uint64_t i = 0;
+    for (; i + 64 <= n; i += 64) sha256_block(h, p + i);
+    uint8_t tail[128]; uint32_t t = 0;
+    for (; i < n; i++) tail[t++] = p[i];
+    tail[t++] = 0x80;
+    const uint32_t padTo = t <= 56u ? 56u : 120u;
+    while (t < padTo) tail[t++] = 0;
+    const uint64_t bits = n * 8u;
+    for (int k = 7; k >= 0; k--) tail[t++] = (uint8_t)(bits >> (8 * k));
+    sha256_block(h, tail);
+    if (t == 128u) sha256_block(h, tail + 64);
+    for (int k = 0; k < 8; k++) out[(size_t)piece * 8u + k] = h[k];
+}
+
 #ifndef B2Z_CUEMU
+cudaError_t launch_sha256_pieces(const uint8_t* src, const uint64_t* off, const uint64_t* len, uint32_t nPieces, uint32_t* out, cudaStream_t st) {
+    if (!nPieces) return cudaSuccess;
+    sha256_pieces_kernel<<<(nPieces + 63u) / 64u, 64, 0, st>>>(src, off, len, nPieces, out);
+    return cudaGetLastError();
+}
+
 // ---- GF(2) polynomial arithmetic mod P, reflected bit order (bit W-1 = x^0); W = 32 or 64
 template <typename T> static T gf_mul(T a, T b, T poly) {
     const T top = (T)1 << (sizeof(T) * 8 - 1);

@@ -7,7 +7,7 @@
 //            (the layout `xz -T` / XzEnc.c:1236 Xz_Encode with blockSize write).  Check: none, CRC32 or CRC64 (7-Zip's default, Xz.h:34).
 //   reader   Stream Header / Blocks / Index / Footer are parsed and verified on the host (CRC32 of the small fields); the Blocks'
 //            LZMA2 payloads are spliced into one chunk stream for the GPU decoder (their end markers dropped), the Block checks
-//            are verified on the decoded bytes while they are still in HBM.  A SHA-256 check is skipped (decoded, not verified).
+//            are verified on the decoded bytes while they are still in HBM (CRC32, CRC64, SHA-256).
 //            Filters in front of LZMA2 -- Delta, x86, PowerPC, ARM, ARM-Thumb, SPARC, ARM64 -- are undone on the GPU (b2z_filter.cu) per
 //            Block; IA64 and RISC-V chains are B200Z_E_UNSUPPORTED.
 // Format: https://tukaani.org/xz/xz-file-format.txt as implemented by C/Xz.c, C/XzEnc.c:150-330 (headers, index, footer), C/XzDec.c:1126-1600.
@@ -18,6 +18,7 @@
 namespace b2z {
 template <typename T> cudaError_t launch_crc_pieces(const uint8_t* src, uint64_t n, uint32_t pieceLog, const uint64_t* off, const uint64_t* len,
                                                     uint32_t nPieces, T poly, T* out, cudaStream_t st);
+cudaError_t launch_sha256_pieces(const uint8_t* src, const uint64_t* off, const uint64_t* len, uint32_t nPieces, uint32_t* out, cudaStream_t st);
 }
 
 int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop, uint32_t unitLog);   // b2z_filter.cu
@@ -326,7 +327,7 @@ int b200z_xz_decompress_host(b200z_ctx* ctx, const void* srcv, size_t n, void* d
         }
     }
     // Block checks on the decoded bytes, which b200z_lzma2_decompress_host left in the context's output arena (Streams of one file
-    // may carry different check types: one kernel launch per type present; SHA-256 and unknown types are not verified)
+    // may carry different check types: one kernel launch per type present; unknown types are not verified)
     for (uint32_t type = 1; type <= 4; type += 3) {
         std::vector<uint64_t> off, len; std::vector<uint32_t> which;
         uint64_t pos = 0;
@@ -348,6 +349,28 @@ int b200z_xz_decompress_host(b200z_ctx* ctx, const void* srcv, size_t n, void* d
         }
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
         for (uint32_t i = 0; i < m; i++) if (have[i] != blocks[which[i]].check) return fail(ctx, B200Z_E_CHECKSUM, "xz: Block check mismatch%s");
+    }
+    {   // SHA-256 checks (type 10): one thread per Block on the decoded bytes; the 32 check bytes follow the Block's padded payload
+        std::vector<uint64_t> off, len; std::vector<uint32_t> which;
+        uint64_t pos = 0;
+        for (uint32_t i = 0; i < nb; i++) { if (blocks[i].checkType == 10u) { off.push_back(pos); len.push_back(blocks[i].unpackSize); which.push_back(i); } pos += blocks[i].unpackSize; }
+        const uint32_t m = (uint32_t)which.size();
+        if (m) {
+            if (ctx->batchOff.reserve((size_t)m * 8) || ctx->batchSize.reserve((size_t)m * 8) || ctx->cks.reserve((size_t)m * 32 + 64)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
+            CU(cudaMemcpyAsync(ctx->batchOff.p, off.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->batchSize.p, len.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(b2z::launch_sha256_pieces((const uint8_t*)ctx->dOut.p, (const uint64_t*)ctx->batchOff.p, (const uint64_t*)ctx->batchSize.p, m, (uint32_t*)ctx->cks.p, ctx->stream));
+            std::vector<uint32_t> have((size_t)m * 8);
+            CU(cudaMemcpyAsync(have.data(), ctx->cks.p, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
+            ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+            for (uint32_t i = 0; i < m; i++) {
+                const b200z_xz_block& b = blocks[which[i]];
+                const uint8_t* want = s + b.packOff + ((b.packSize + 3) & ~3ull);
+                for (uint32_t k = 0; k < 8; k++)
+                    if (have[(size_t)i * 8 + k] != (((uint32_t)want[4 * k] << 24) | ((uint32_t)want[4 * k + 1] << 16) | ((uint32_t)want[4 * k + 2] << 8) | want[4 * k + 3]))
+                        return fail(ctx, B200Z_E_CHECKSUM, "xz: Block check (SHA-256) mismatch%s");
+            }
+        }
     }
     *out = got;
     return 0;

@@ -203,4 +203,9 @@ int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint
     return counts.status ? -(int64_t)counts.status : (int64_t)total;
 }
 
+// sha256_pieces_kernel: out[i] = 8 big-endian words per range
+void emu_sha256_pieces(const uint8_t* src, const uint64_t* off, const uint64_t* len, uint32_t nPieces, uint32_t* out) {
+    cuemu::launch(dim3((nPieces + 63u) / 64u), dim3(64), 0, [&] { sha256_pieces_kernel(src, off, len, nPieces, out); });
+}
+
 }

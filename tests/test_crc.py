@@ -83,3 +83,17 @@ def test_emulated_kernel_equals_the_oracle(pkg):
         for i in range(200):
             piece = data[int(offs[i]):int(offs[i]) + int(lens[i])]
             assert int(out[i]) == f(piece, len(piece)), (width, i)
+
+
+def test_emulated_sha256_kernel_equals_hashlib(pkg):
+    """the third xz check type (C/Xz.h:35 XZ_CHECK_SHA256): sha256_pieces_kernel, one thread per range, every padding case"""
+    import hashlib
+    E = H.cuemu_library()
+    E.emu_sha256_pieces.restype = None; E.emu_sha256_pieces.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_uint32, ctypes.c_void_p]
+    rng = random.Random(1); data = pkg.corpus.entropy_class(1, 30_000).tobytes()
+    lens = [0, 1, 54, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 1000, 4097, 20_000]; offs = [rng.randrange(0, 10_000) for _ in lens]
+    o = np.array(offs, dtype=np.uint64); ln = np.array(lens, dtype=np.uint64); out = np.zeros(len(lens) * 8, dtype=np.uint32)
+    src = np.frombuffer(data, dtype=np.uint8)
+    E.emu_sha256_pieces(src.ctypes.data, o.ctypes.data, ln.ctypes.data, len(lens), out.ctypes.data)
+    for i in range(len(lens)):
+        assert b"".join(int(w).to_bytes(4, "big") for w in out[i * 8:i * 8 + 8]) == hashlib.sha256(data[offs[i]:offs[i] + lens[i]]).digest(), lens[i]

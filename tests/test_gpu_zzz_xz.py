@@ -67,6 +67,11 @@ def test_foreign_files_and_damage(pkg, codec, inputs):
     assert e.value.code == -6
     a = lzma.compress(data[:300_000], format=lzma.FORMAT_XZ); b = lzma.compress(data[300_000:], format=lzma.FORMAT_XZ, check=lzma.CHECK_CRC32, preset=0)
     assert codec.xz_decompress(a + bytes(8) + b) == data              # concatenated Streams
+    sha = bytearray(lzma.compress(data, format=lzma.FORMAT_XZ, check=lzma.CHECK_SHA256, preset=1))
+    sha[-40] ^= 1                                                     # inside the 32 check bytes: the GPU's SHA-256 disagrees
+    with pytest.raises(pkg.B200zError) as e:
+        codec.xz_decompress(bytes(sha))
+    assert e.value.code == -8
     xz = bytearray(codec.xz_compress(data, 4))
     xz[len(xz) // 2] ^= 0x10                                          # inside a Block's payload: the range decoder or the check notices
     with pytest.raises(pkg.B200zError) as e:
