@@ -6,7 +6,7 @@
 # 3. launch lists + one full ncu capture each of stage P and stage Z (source-level hotspots decide what to optimise)
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_zz_zstd_parse.py tests/test_gpu_zz_lzma2_parse.py -x -q
+timeout 900 python -m pytest tests/test_gpu_zz_lzma2_parse.py tests/test_gpu_zz_zstd_parse.py tests/test_gpu_zzz_crc.py tests/test_gpu_zzz_filters.py tests/test_gpu_zzz_xz.py -q
 timeout 900 python -m pytest tests -m gpu -x -q
 timeout 300 python tools/tools_probe_lzma2_parse.py 4096 20 2
 timeout 300 python tools/tools_probe_lzma2_parse.py 4096 23 3
