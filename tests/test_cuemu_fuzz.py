@@ -69,7 +69,7 @@ def test_fuzz_emulated_kernels_equal_the_oracle(pkg, seed):
     O.b2zo_lzma2_candidates.argtypes = [vp, u32, u32, vp]
     O.b2zo_lzma2_parse_frame.argtypes = [vp, u32, ctypes.POINTER(H.EncParams), vp, vp, vp]
     rng = random.Random(seed)
-    for it in range(14 if seed < 40 else 4):                       # seeds >= 40: the (larger) planted-copy inputs
+    for it in range(14 if seed < 40 else 2):                       # seeds >= 40: the (larger) planted-copy inputs
         data = _gen(rng, pkg, planted=seed >= 40); n = len(data)
         fl = rng.choice([17, 17, 18]); sl = rng.choice([0, 1]) if fl == 18 else 0
         F = 1 << fl; nfr = (n + F - 1) // F; bpf = F >> 17
