@@ -18,8 +18,6 @@
 namespace b2z {
 
 #define B2Z_CRC_PIECE_LOG 16u
-#define B2Z_CRC32_POLY 0xEDB88320u
-#define B2Z_CRC64_POLY 0xC96C5795D7870F42ull
 
 // piece i = bytes [off[i], off[i] + len[i]) of src when off != null, else the i-th 2^pieceLog bytes of [0, n)
 template <typename T>

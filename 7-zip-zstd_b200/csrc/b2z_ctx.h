@@ -49,3 +49,6 @@ static inline int fail(b200z_ctx* c, int code, const char* fmt, const char* deta
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError(); \
     return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? B200Z_E_MEMORY : B200Z_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } } while (0)
 
+// b2z_filter.cu: b200z_filter_device with units -- unitLog != 0 (encode only): the buffer is a run of independent units of 2^unitLog
+// bytes (the xz writer filters every Block on its own)
+int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop, uint32_t unitLog);

@@ -129,11 +129,8 @@ delta_dec_kernel(uint8_t* __restrict__ data, uint64_t n, uint32_t dist, uint32_t
 }  // namespace b2z
 
 #ifndef B2Z_CUEMU
-extern "C" {
-
 // In place on a device buffer.  methodId: 7-Zip's filter ids (b2z_filter_ops.h); prop: delta distance (1..256) or the start offset
 // ("pc") of the branch converters.  Branch converters leave a tail of n % 4 bytes untouched, like the reference (C/Bra.h:78-86).
-}  // extern "C"
 // unitLog != 0 (encode only): the buffer is a run of independent units of 2^unitLog bytes -- the xz writer filters every Block on its own
 int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop, uint32_t unitLog) {
     if (!ctx || (!d_data && n)) return B200Z_E_PARAM;

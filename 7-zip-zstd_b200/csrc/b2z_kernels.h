@@ -47,4 +47,9 @@ void launch_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, const EncGeo
 void launch_zstd_enc_scatter(const uint8_t* src, const uint64_t* off, const uint32_t* size, uint32_t nFrames, uint32_t frameLog,
                              uint8_t* stage, cudaStream_t st);
 
+// digests and filters (b2z_crc.cu, b2z_filter.cu): per-piece CRC32 / CRC64 (pieces of 2^pieceLog bytes, or the given ranges), SHA-256 of ranges
+template <typename T> cudaError_t launch_crc_pieces(const uint8_t* src, uint64_t n, uint32_t pieceLog, const uint64_t* off, const uint64_t* len,
+                                                    uint32_t nPieces, T poly, T* out, cudaStream_t st);
+cudaError_t launch_sha256_pieces(const uint8_t* src, const uint64_t* off, const uint64_t* len, uint32_t nPieces, uint32_t* out /* [nPieces][8] */, cudaStream_t st);
+
 }  // namespace b2z

@@ -56,6 +56,10 @@
 #define B2Z_FLAG_ZSTD_OPT 0x20u
 #define B2Z_ZSTD_OPT_LEVEL 8       /* B200Z_P_LEVEL at or above this selects it */
 
+/* digests (b2z_crc.cu): reflected polynomials of CRC-32 (C/7zCrc.c) and CRC-64/XZ (C/XzCrc64.c) */
+#define B2Z_CRC32_POLY 0xEDB88320u
+#define B2Z_CRC64_POLY 0xC96C5795D7870F42ull
+
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL
 #define B2Z_PRIME8 0xCF1BBCDCB7A56463ULL

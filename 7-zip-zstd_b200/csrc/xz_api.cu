@@ -14,14 +14,7 @@
 #include <vector>
 #include "b2z_ctx.h"
 #include "b2z_lzma2.h"
-
-namespace b2z {
-template <typename T> cudaError_t launch_crc_pieces(const uint8_t* src, uint64_t n, uint32_t pieceLog, const uint64_t* off, const uint64_t* len,
-                                                    uint32_t nPieces, T poly, T* out, cudaStream_t st);
-cudaError_t launch_sha256_pieces(const uint8_t* src, const uint64_t* off, const uint64_t* len, uint32_t nPieces, uint32_t* out, cudaStream_t st);
-}
-
-int b2z_filter_units_device(b200z_ctx* ctx, uint32_t methodId, int encode, void* d_data, size_t n, uint32_t prop, uint32_t unitLog);   // b2z_filter.cu
+#include "b2z_kernels.h"
 
 namespace {
 
@@ -238,12 +231,12 @@ int b200z_xz_compress_host(b200z_ctx* ctx, const void* src, size_t n, void* dst,
     if (checkType && nFrames) {
         if (ctx->cks.reserve((size_t)nFrames * 8 + 64)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
         if (checkType == 1) {
-            CU(b2z::launch_crc_pieces<uint32_t>((const uint8_t*)ctx->dIn.p, n, fl, nullptr, nullptr, nFrames, 0xEDB88320u, (uint32_t*)ctx->cks.p, ctx->stream));
+            CU(b2z::launch_crc_pieces<uint32_t>((const uint8_t*)ctx->dIn.p, n, fl, nullptr, nullptr, nFrames, B2Z_CRC32_POLY, (uint32_t*)ctx->cks.p, ctx->stream));
             std::vector<uint32_t> t(nFrames);
             CU(cudaMemcpyAsync(t.data(), ctx->cks.p, (size_t)nFrames * 4, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
             for (uint32_t i = 0; i < nFrames; i++) checks[i] = t[i];
         } else {
-            CU(b2z::launch_crc_pieces<uint64_t>((const uint8_t*)ctx->dIn.p, n, fl, nullptr, nullptr, nFrames, 0xC96C5795D7870F42ull, (uint64_t*)ctx->cks.p, ctx->stream));
+            CU(b2z::launch_crc_pieces<uint64_t>((const uint8_t*)ctx->dIn.p, n, fl, nullptr, nullptr, nFrames, B2Z_CRC64_POLY, (uint64_t*)ctx->cks.p, ctx->stream));
             CU(cudaMemcpyAsync(checks.data(), ctx->cks.p, (size_t)nFrames * 8, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
         }
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
@@ -339,12 +332,12 @@ int b200z_xz_decompress_host(b200z_ctx* ctx, const void* srcv, size_t n, void* d
         CU(cudaMemcpyAsync(ctx->batchSize.p, len.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<uint64_t> have(m, 0);
         if (type == 1) {
-            CU(b2z::launch_crc_pieces<uint32_t>((const uint8_t*)ctx->dOut.p, got, 0, (const uint64_t*)ctx->batchOff.p, (const uint64_t*)ctx->batchSize.p, m, 0xEDB88320u, (uint32_t*)ctx->cks.p, ctx->stream));
+            CU(b2z::launch_crc_pieces<uint32_t>((const uint8_t*)ctx->dOut.p, got, 0, (const uint64_t*)ctx->batchOff.p, (const uint64_t*)ctx->batchSize.p, m, B2Z_CRC32_POLY, (uint32_t*)ctx->cks.p, ctx->stream));
             std::vector<uint32_t> t(m);
             CU(cudaMemcpyAsync(t.data(), ctx->cks.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
             for (uint32_t i = 0; i < m; i++) have[i] = t[i];
         } else {
-            CU(b2z::launch_crc_pieces<uint64_t>((const uint8_t*)ctx->dOut.p, got, 0, (const uint64_t*)ctx->batchOff.p, (const uint64_t*)ctx->batchSize.p, m, 0xC96C5795D7870F42ull, (uint64_t*)ctx->cks.p, ctx->stream));
+            CU(b2z::launch_crc_pieces<uint64_t>((const uint8_t*)ctx->dOut.p, got, 0, (const uint64_t*)ctx->batchOff.p, (const uint64_t*)ctx->batchSize.p, m, B2Z_CRC64_POLY, (uint64_t*)ctx->cks.p, ctx->stream));
             CU(cudaMemcpyAsync(have.data(), ctx->cks.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream)); CU(cudaStreamSynchronize(ctx->stream));
         }
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
