@@ -20,7 +20,7 @@ EXPORTS = [
     "b200z_device_count", "b200z_create", "b200z_destroy", "b200z_set_param", "b200z_get_param",
     "b200z_last_error", "b200z_get_stat", "b200z_reset_stats", "b200z_zstd_compress_bound",
     "b200z_zstd_compress_device", "b200z_zstd_compress_host", "b200z_zstd_frame_info",
-    "b200z_zstd_decompress_device", "b200z_zstd_decompress_host", "b200z_zstd_enc_stage_m",
+    "b200z_zstd_decompress_device", "b200z_zstd_decompress_host", "b200z_zstd_enc_stage_m", "b200z_zstd_enc_stage_f",
     "b200z_dev_alloc", "b200z_dev_free", "b200z_dev_upload", "b200z_dev_download",
     "b200z_host_alloc_pinned", "b200z_host_free_pinned",
 ]
@@ -61,6 +61,7 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.b200z_zstd_frame_info.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]
     L.b200z_zstd_enc_stage_m.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+    L.b200z_zstd_enc_stage_f.argtypes = [vp, vp, sz, vp]
     L.b200z_zstd_compress_batch_bound.argtypes = [vp, sz, ctypes.c_uint32]; L.b200z_zstd_compress_batch_bound.restype = sz
     L.b200z_zstd_compress_batch_host.argtypes = [vp, vp, vp, ctypes.c_uint32, vp, sz, vp]
     L.b200z_lzma2_compress_bound.argtypes = [vp, sz]; L.b200z_lzma2_compress_bound.restype = sz
@@ -127,7 +128,7 @@ class Codec:
             raise B200zError(rc, self.L.b200z_last_error(self.h).decode())
 
     _PARAMS = dict(level=P_LEVEL, frame_log=P_FRAMELOG, hash_log_l=P_HASHLOG_L, hash_log_s=P_HASHLOG_S,
-                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, row_log=9, lzma2_model=10, lzma2_slice_log=11, lzma2_parse=12, zstd_parse=13)
+                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, chunk_log=9, lzma2_model=10, lzma2_slice_log=11, lzma2_parse=12, zstd_parse=13)
 
     def set(self, name, value):
         self._check(self.L.b200z_set_param(self.h, self._PARAMS[name], int(value)))
@@ -270,6 +271,21 @@ class Codec:
         finally:
             self.L.b200z_dev_free(self.h, d)
         return seqs, nseq, lits, nlit
+
+    # ---- test tap: stage F candidate words, one per input byte (layout of oracle b2zo_zstd_candidates, frames back to back)
+    def stage_f(self, data):
+        import numpy as np
+        src = np.frombuffer(data, dtype=np.uint8)
+        n = src.nbytes
+        d = ctypes.c_void_p()
+        self._check(self.L.b200z_dev_alloc(self.h, ctypes.byref(d), n + 64))
+        try:
+            self._check(self.L.b200z_dev_upload(self.h, d, src.ctypes.data, n))
+            cand = np.zeros(n, dtype=np.uint32)
+            self._check(self.L.b200z_zstd_enc_stage_f(self.h, d, n, cand.ctypes.data))
+        finally:
+            self.L.b200z_dev_free(self.h, d)
+        return cand
 
     # ---- test tap: the price-based LZMA2 parse (lzma2_parse=1): stage C candidate words [n, 4] and stage P sequences
     # (layouts of the oracle's b2zo_lzma2_candidates / b2zo_lzma2_parse_frame, frames back to back)

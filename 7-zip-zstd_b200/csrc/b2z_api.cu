@@ -1,6 +1,6 @@
 // b2z_api.cu -- the extern "C" shim of libb200z.so (see include/b200z.h).
 //
-// Host dispatcher for one device: owns the stream, the scratch arenas (hash tables, per-block
+// Host dispatcher for one device: owns the stream, the scratch arenas (candidate words, per-block
 // sequence/literal/slot arrays) and the staging buffers of the host-pointer entry points.
 // Replaces the job/worker plumbing of C/zstd/zstdmt_compress.c (ZSTDMT_compressStream_generic
 // :1853, ZSTDMT_createCompressionJob :1403, ZSTDMT_flushProduced :1488): frames are the jobs,
@@ -31,17 +31,13 @@ int b200z_create(b200z_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return B200Z_E_NODEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->smCount = (uint32_t)prop.multiProcessorCount;
-    // The match finder's table accesses are random 4-byte reads: ask L2 to fetch 32-byte sectors from DRAM
-    // instead of 64-byte pairs (a hint; B200Z_L2_FETCH overrides it for experiments).
-    { size_t gran = 32; if (const char* e = getenv("B200Z_L2_FETCH")) gran = (size_t)atoi(e);
-      if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200Z_E_CUDA; }
     for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&ctx->pe[i], cudaEventDisableTiming);
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
-    ctx->geom.rowLog = B2Z_DEF_ROWLOG;
+    ctx->geom.chunkLog = B2Z_DEF_CHUNKLOG;
     ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);   // size hints on: lets any decoder (ours included) find frames without walking blocks
     *out = ctx;
     return B200Z_OK;
@@ -52,7 +48,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
-                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize, &ctx->cand };
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize, &ctx->cand, &ctx->choice };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -74,8 +70,9 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
                             ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
     case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");
                             ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v; return 0;
-    case B200Z_P_HASHLOG_L: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
-    case B200Z_P_HASHLOG_S: if (v < 10 || v > 22) return fail(ctx, B200Z_E_PARAM, "hashLogS out of range%s"); ctx->geom.hashLogS = (uint32_t)v; return 0;
+    // both tables live in the shared memory of one SM: 2^L + 2^S entries <= 192 KiB
+    case B200Z_P_HASHLOG_L: if (v < 8 || v > 15 || (1u << v) + (1u << ctx->geom.hashLogS) > B2Z_MAX_HASHLOG_SUM_WORDS) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
+    case B200Z_P_HASHLOG_S: if (v < 8 || v > 15 || (1u << v) + (1u << ctx->geom.hashLogL) > B2Z_MAX_HASHLOG_SUM_WORDS) return fail(ctx, B200Z_E_PARAM, "hashLogS out of range%s"); ctx->geom.hashLogS = (uint32_t)v; return 0;
     case B200Z_P_WINDOWLOG: if (v < 10 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "windowLog out of range%s"); ctx->geom.windowLog = (uint32_t)v; return 0;
     case B200Z_P_FLAGS:     if (v & ~3ll) return fail(ctx, B200Z_E_PARAM, "unknown flag bits%s"); ctx->geom.flags = (ctx->geom.flags & ~3u) | (uint32_t)v; return 0;
     case B200Z_P_LZMA2_SLICELOG: if (v < 0 || v > 3) return fail(ctx, B200Z_E_PARAM, "lzma2 sliceLog out of range%s");
@@ -83,7 +80,7 @@ int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_LZMA2_PARSE: if (v < 0 || v > 1) return fail(ctx, B200Z_E_PARAM, "lzma2 parse mode out of range%s");
                             ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_LZ2_OPT) | (v ? B2Z_FLAG_LZ2_OPT : 0u); return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
-    case B200Z_P_ROWLOG:    if (v < 8 || v > 18) return fail(ctx, B200Z_E_PARAM, "rowLog out of range%s"); ctx->geom.rowLog = (uint32_t)v; return 0;
+    case B200Z_P_CHUNKLOG:  if (v < 5 || v > 8) return fail(ctx, B200Z_E_PARAM, "chunkLog out of range%s"); ctx->geom.chunkLog = (uint32_t)v; return 0;
     case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
@@ -105,7 +102,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
-    case B200Z_P_ROWLOG: *v = ctx->geom.rowLog; return 0;
+    case B200Z_P_CHUNKLOG: *v = ctx->geom.chunkLog; return 0;
     }
     return B200Z_E_PARAM;
 }
@@ -123,9 +120,9 @@ size_t b200z_zstd_compress_bound(b200z_ctx* ctx, size_t n) {
 }  // extern "C"
 
 // ---------------------------------------------------------------- encoder driver
-static uint32_t match_warps(const b200z_ctx* ctx, uint64_t nFrames) {
-    const uint64_t cap = (uint64_t)ctx->smCount * 32u;
-    return (uint32_t)(nFrames < cap ? nFrames : cap);
+// stage F: one CTA per frame, one CTA per SM (its tables fill the SM's shared memory); CTAs loop over frames
+static uint32_t find_ctas(const b200z_ctx* ctx, uint64_t nFrames) {
+    return (uint32_t)(nFrames < ctx->smCount ? nFrames : ctx->smCount);
 }
 
 // does this batch parse by price (stage C + stage P / stage Z) instead of the greedy stage M?  (the per-file batch mode, which
@@ -144,14 +141,13 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     const uint64_t F = 1ull << ctx->geom.frameLog;
     const uint64_t nFrames = (batchBytes + F - 1) / F;
     const uint64_t nBlocks = (batchBytes + B2Z_BLOCK - 1) / B2Z_BLOCK + 1;
-    const uint32_t nWarps = match_warps(ctx, nFrames);
-    const size_t tableBytes = (size_t)64 << ctx->geom.rowLog;           // row-hash table: 2^rowLog rows of 64 bytes per frame-warp
     int bad = 0;
     if (price_parse(ctx->geom, codec)) {                                // price-based parse: stage C's tables and candidate words
         bad |= ctx->tables.reserve(lzma2_cand_table_bytes(ctx->geom, cand_warps(ctx, nFrames)));
         bad |= ctx->cand.reserve((size_t)nFrames * F * LZP_NCAND * 4u);
-    } else {
-        bad |= ctx->tables.reserve(tableBytes * nWarps);
+    } else {                                                            // stage F -> stage G: a candidate word and a choice byte per input byte
+        bad |= ctx->cand.reserve((size_t)(nFrames * F + 16) * 4u);
+        bad |= ctx->choice.reserve((size_t)(nFrames * F + 16));
     }
     bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);
     bad |= ctx->nseq.reserve(nBlocks * 4);
@@ -161,7 +157,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     bad |= ctx->slotSize.reserve(nBlocks * 4);
     bad |= ctx->blockOff.reserve((nBlocks + 1) * 8);
     bad |= ctx->frameOff.reserve((nFrames * (codec == 1 ? lzma2_enc_slices_per_frame(ctx->geom) : 1u) + 2) * 8);
-    bad |= ctx->scalars.reserve(64);
+    bad |= ctx->scalars.reserve(128);                                   // [0] u64 produced bytes, [16] u32 LZMA2 slot overflow, [64] u32 stage F arrival-flag timeout
     bad |= ctx->cks.reserve((nFrames + 2) * 4);
     return bad ? fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s") : 0;
 }
@@ -176,8 +172,9 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     const uint64_t nFrames = (n + F - 1) / F;
     const uint32_t nBlocks = (uint32_t)((n >> 17) + ((n & (B2Z_BLOCK - 1)) ? 1 : 0));
     // blocks are numbered per frame with a fixed stride (frames are multiples of 128 KiB)
-    const uint32_t nWarps = match_warps(ctx, nFrames);
     cudaStream_t st = ctx->stream;
+    uint32_t* const errFlag = (uint32_t*)ctx->scalars.p + 16;
+    CU(cudaMemsetAsync(ctx->scalars.p, 0, 128, st));
     CU(cudaEventRecord(ctx->ev[0], st));
     if (price_parse(g, codec)) {
         // price-based parse: stage C (candidates) + stage P (method 21) / stage Z (zstd) instead of the greedy stage M
@@ -198,12 +195,12 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
             return 0;
         }
     } else {
-        launch_zstd_enc_match(d_src, n, g, (uint32_t*)ctx->tables.p, nWarps, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
-                              (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, ready, readyShift, st);
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(ctx->ev[4], st));                      // no separate parse stage: ENC_PARSE_MS stays ~0
+        CU(launch_zstd_enc_find(d_src, n, g, (uint32_t*)ctx->cand.p, find_ctas(ctx, nFrames), ready, readyShift, errFlag, st));
+        CU(cudaEventRecord(ctx->ev[4], st));
+        CU(launch_zstd_enc_dp(d_src, n, g, (const uint32_t*)ctx->cand.p, (uint8_t*)ctx->choice.p, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
+                              (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, st));
         CU(cudaEventRecord(ctx->ev[1], st));
-        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 2;
     }
     if (!stageMOnly && codec == 1) {
         // LZMA2: stage R (range coding, one thread per frame) + assembly of the frame slots into one chunk stream
@@ -215,7 +212,6 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
             if (ctx->decScratch[5].reserve((size_t)nChains * LITN * 2u)) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");
             spill = (uint16_t*)ctx->decScratch[5].p;
         }
-        CU(cudaMemsetAsync(ctx->scalars.p, 0, 64, st));
         CU(launch_lzma2_enc_range(d_src, n, g, (const uint64_t*)ctx->seqs.p, (const uint32_t*)ctx->nseq.p, (uint8_t*)ctx->slots.p,
                                   (uint32_t*)ctx->slotSize.p, (uint32_t)nFrames, spill, ctx->smCount, ctx->lz2Mode, (uint32_t*)ctx->scalars.p + 4, st));
         CU(cudaEventRecord(ctx->ev[2], st));
@@ -224,9 +220,10 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[3], st));
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
-        uint64_t hs[3] = {0, 0, 0};
-        CU(cudaMemcpyAsync(hs, ctx->scalars.p, 24, cudaMemcpyDeviceToHost, st));
+        uint64_t hs[9] = {0};
+        CU(cudaMemcpyAsync(hs, ctx->scalars.p, 72, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if ((uint32_t)hs[8]) return fail(ctx, B200Z_E_CUDA, "upload stalled: an input chunk never arrived%s");
         if ((uint32_t)hs[2]) return fail(ctx, B200Z_E_CUDA, "LZMA2: frame slot overflow%s");
         *produced = hs[0];
         float ms = 0;
@@ -244,10 +241,11 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev[3], st));
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
-        uint64_t out = 0;
-        CU(cudaMemcpyAsync(&out, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, st));
+        uint64_t hs[9] = {0};
+        CU(cudaMemcpyAsync(hs, ctx->scalars.p, 72, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        *produced = out;
+        if ((uint32_t)hs[8]) return fail(ctx, B200Z_E_CUDA, "upload stalled: an input chunk never arrived%s");
+        *produced = hs[0];
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
         cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[1]); ctx->stat[B200Z_S_ENC_PARSE_MS] += ms;
@@ -256,7 +254,8 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     } else {
         CU(cudaStreamSynchronize(st));
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); ctx->stat[B200Z_S_ENC_MATCH_MS] += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[1]); ctx->stat[B200Z_S_ENC_PARSE_MS] += ms;
     }
     return 0;
 }
@@ -392,6 +391,17 @@ int b200z_zstd_enc_stage_m(b200z_ctx* ctx, const void* d_src, size_t srcSize, ui
         dense += nb;
     }
     CU(cudaMemcpy(lits, ctx->lits.p, srcSize, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200z_zstd_enc_stage_f(b200z_ctx* ctx, const void* d_src, size_t srcSize, uint32_t* cand) {
+    if (!ctx || !d_src || !srcSize || !cand) return B200Z_E_PARAM;
+    if (price_parse(ctx->geom, 0)) return fail(ctx, B200Z_E_PARAM, "stage F belongs to B200Z_P_ZSTD_PARSE 0%s");
+    CU(cudaSetDevice(ctx->device));
+    uint64_t produced = 0;
+    int rc = enc_batch(ctx, (const uint8_t*)d_src, srcSize, nullptr, &produced, true);
+    if (rc) return rc;
+    CU(cudaMemcpy(cand, ctx->cand.p, srcSize * 4u, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -13,12 +13,18 @@ __device__ __forceinline__ uint32_t lane_id() { return cuemu_lane_id(); }
 __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << cuemu_lane_id()) - 1u; }
 #define B2Z_DYN_SMEM(T, name) T* const name = reinterpret_cast<T*>(cuemu::dyn_smem())
 #define B2Z_EXTERN_SMEM(T, name) T* const name = reinterpret_cast<T*>(cuemu::dyn_smem())
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nThreads) { cuemu::named_bar(id, nThreads, true); }
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nThreads) { cuemu::named_bar(id, nThreads, false); }
 #else
 __device__ __forceinline__ uint32_t lane_id() { uint32_t l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 // the CTA's dynamic shared memory as an array (B2Z_EXTERN_SMEM: exactly `extern __shared__ T name[]`) or as one struct
 #define B2Z_EXTERN_SMEM(T, name) extern __shared__ T name[]
 #define B2Z_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; T* const name = reinterpret_cast<T*>(name##_raw_)
+// named barriers (ids 1..15; 0 is __syncthreads): bar_sync waits until nThreads threads have arrived (bar_sync or bar_arrive),
+// bar_arrive only signals.  Memory accesses before an arrive are visible after the matching sync (PTX barrier semantics).
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nThreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nThreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nThreads) : "memory"); }
 #endif
 
 // 64-bit funnel: bytes [s/8, s/8+8) of the 16-byte little-endian pair (a, b); s in {0,8,..,56}

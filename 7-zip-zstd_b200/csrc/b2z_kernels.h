@@ -4,14 +4,14 @@
 #include <stdint.h>
 #include "b2z_params.h"
 
-#define B2Z_MATCH_THREADS   32      // one frame-warp per CTA: spreads few frames over many SMs
+#define B2Z_DP_WARPS        8       // stage G: warps (= blocks of input) per CTA
 #define B2Z_ENT_WARPS       4       // stage E: warps (= blocks of input) per CTA
 #define B2Z_SLOT            (B2Z_BODY_CAP + 64u) // per-block output slot: 3-byte header + body (<= B2Z_BODY_CAP), 16-B multiple
 
 namespace b2z {
 
 struct EncGeom {
-    uint32_t frameLog, hashLogL, hashLogS, windowLog, flags, rowLog;
+    uint32_t frameLog, hashLogL, hashLogS, windowLog, flags, chunkLog;
     const uint32_t* frameSizes;      // null: frames are dense (all 2^frameLog bytes but the last).  Batch mode (frameLog 17, one block
                                      // per frame): bytes of every frame, frames sit at multiples of 2^frameLog in the staging buffer
 };
@@ -21,10 +21,16 @@ __host__ __device__ inline uint32_t enc_frame_bytes(const EncGeom& g, uint64_t s
     return (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
 }
 
-// stage M: one warp per frame -> per-block final sequences + literal bytes
-void launch_zstd_enc_match(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps,
-                           uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit,
-                           const uint32_t* ready /* null, or per-chunk arrival flags */, uint32_t readyShift, cudaStream_t st);
+// stage F (zstd_enc_find.cu): one CTA per frame, both hash tables in shared memory -> one candidate word per position
+size_t zstd_enc_find_smem_bytes(const EncGeom& g);
+cudaError_t launch_zstd_enc_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand /* [srcSize + 16] */, uint32_t nCtas,
+                                 const uint32_t* ready /* null, or per-chunk arrival flags */, uint32_t readyShift,
+                                 uint32_t* errFlag /* set to 1 when an arrival flag never came */, cudaStream_t st);
+// stage G (zstd_enc_dp.cu): one warp per 128 KiB block, one lane per 4 KiB segment: minimum-price parse of stage F's candidates
+// -> per-block final sequences + literal bytes.  choice: one scratch byte per input byte.
+size_t zstd_enc_dp_smem_bytes();
+cudaError_t launch_zstd_enc_dp(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint32_t* cand, uint8_t* choice,
+                               uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, cudaStream_t st);
 
 // stage Z (zstd_enc_parse.cu): the price-based parse, one warp per 128 KiB block, on stage C's candidate words (lzma2_parse.cu);
 // fills the same arrays as stage M.  Dense frames only.

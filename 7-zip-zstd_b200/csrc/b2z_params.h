@@ -11,14 +11,27 @@
 #endif
 
 #define B2Z_DEF_FRAMELOG   20      /* independent zstd frame = 1 MiB of input                */
-#define B2Z_DEF_HASHLOG_L  17      /* long (8-byte) hash table entries  (clevels.h:31 H17)   */
-#define B2Z_DEF_HASHLOG_S  16      /* short (5-byte) hash table entries (clevels.h:31 C16)   */
-#define B2Z_DEF_ROWLOG     14      /* row-hash match finder: 2^14 rows of 64 bytes = 1 MiB per frame-warp   */
-#define B2Z_ROW_WAYS       15u     /* entries per 64-byte row of the row-hash finder (16th word = head) */
-#define B2Z_STEP           32u     /* positions per warp step                                */
-#define B2Z_LAZY_GAIN      2u      /* defer a match when the next position's is this much longer */
+#define B2Z_DEF_HASHLOG_L  15      /* stage F: long (8-byte hash) table entries -- 128 KiB of the CTA's shared memory  */
+#define B2Z_DEF_HASHLOG_S  14      /* stage F: short (5-byte hash) table entries -- 64 KiB of shared memory            */
+#define B2Z_MAX_HASHLOG_SUM_WORDS 49152u  /* 2^L + 2^S entries must fit 192 KiB of shared memory                     */
+#define B2Z_DEF_CHUNKLOG   7       /* stage F: positions whose table reads all precede their table writes (one "turn") */
+#define B2Z_SEG            4096u   /* stage G: bytes parsed by one lane; matches never cross a segment end            */
+#define B2Z_SEGLOG         12
+/* stage G prices, in 1/16 bit: a match costs its offset's extra bits + B2Z_DP_MATCH + the extra bits of its length code;
+ * a literal costs log2(total / count) of its byte in the block's sampled histogram, clamped */
+#define B2Z_DP_MATCH       128u
+#define B2Z_DP_NTRUNC      2u      /* a candidate of length L is also priced at L-1 .. L-NTRUNC                       */
+#define B2Z_DP_MINLEN      4u
+#define B2Z_DP_LIT_MIN     16u
+#define B2Z_DP_LIT_MAX     192u
+/* candidate word of one position (stage F -> stage G): 0 = none, else offset << 7 | length (length <= B2Z_CAP) */
+#define B2Z_CAND(len, off) (((uint32_t)(off) << 7) | (uint32_t)(len))
+#define B2Z_CAND_LEN(c)    ((c) & 127u)
+#define B2Z_CAND_OFF(c)    ((c) >> 7)
+/* bytes of a block that feed the literal histogram: the first 64 of every 256 */
+#define B2Z_DP_SAMPLED(i)  ((((i) >> 6) & 3u) == 0u)
 #define B2Z_MAX_FRAMELOG   24
-#define B2Z_CAP            64u     /* stage-M match length cap (pieces re-joined in stage E) */
+#define B2Z_CAP            64u     /* stage F compares at most this many bytes; stage G extends a chosen match of this length */
 #define B2Z_MAXSEQ         32768u  /* raw sequences per 128 KiB block (min match 4)          */
 #define B2Z_BLOCK          131072u
 #define B2Z_FRAME_HDR_MAX  10
@@ -63,13 +76,5 @@
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL
 #define B2Z_PRIME8 0xCF1BBCDCB7A56463ULL
-
-/* match acceptance: a match must pay for its ~offset bits */
-B2Z_HD int b2z_accept(uint32_t len, uint32_t off) {
-    if (len >= 6) return 1;
-    if (len == 5) return off < (1u << 18);
-    if (len == 4) return off < (1u << 8);
-    return 0;
-}
 
 #endif

@@ -1,0 +1,217 @@
+// zstd_enc_dp.cu -- stage G of the block-parallel Zstandard encoder (sm_100a): the parse.
+//
+// One WARP owns one 128 KiB block, one LANE one 4 KiB segment of it (B2Z_SEG): 32 768 blocks x 32 lanes per 4 GiB, so the
+// strictly sequential part of the parse -- a minimum-price path -- runs as a million independent chains.  Per block:
+//   1. literal prices: byte histogram of the first 64 of every 256 bytes (coalesced 16-byte loads, shared-memory atomics),
+//      price = log2(total / count) in 1/16 bit, clamped;
+//   2. per lane, a backward dynamic programme over its segment: cost[i] = min(literal + cost[i+1], the position's
+//      candidate (stage F) at its length L, L-1, L-2: B2Z_DP_MATCH + offset and length extra bits + cost[i+l]).  Only the
+//      next 64 costs are live (candidates are at most B2Z_CAP long), kept in a per-lane ring in shared memory; the choice
+//      (0 = literal, else the length) goes to a byte array in HBM, four positions per store;
+//   3. per lane, a forward walk that only counts (sequences, literals, where the last match ends) -- a chosen match of
+//      the full B2Z_CAP bytes is extended by direct comparison to the segment end;
+//   4. warp scans turn the counts into each lane's place in the block's sequence and literal arrays and into the literal
+//      run that reaches into a lane from the lanes before it;
+//   5. the same walk again, emitting final (offBase, litLength, matchLength) records and the literal bytes.  The repcode
+//      history is "unknown" at every segment start, so no lane waits for another.
+// A block of one repeated byte becomes the single sequence that stage E stores as an RLE block.
+//
+// Role in the reference: the parse half of ZSTD_compressBlock_doubleFast_noDict_generic (zstd_double_fast.c:103-330: which
+// match to take, ZSTD_storeSeq, ZSTD_updateRep zstd_compress_internal.h:775,817) -- done here by price, which is what pays
+// for stage F's small tables.  Sequential statement: oracle/zstd_enc_oracle.c:parse_frame; outputs must be identical.
+#include "b2z_device.cuh"
+#include "b2z_kernels.h"
+#include "b2z_zstd_cost.h"
+
+namespace b2z {
+
+struct DpWarpSmem {
+    uint32_t ring[64][32];       // cost ring: [position & 63][lane]
+    uint32_t hist[256];
+    uint8_t litc[256];
+};
+
+__device__ __forceinline__ uint32_t dp_ml_price(uint32_t l) { return l >= 35u ? 16u * (highbit32(l - 3u) - 3u) : (l >= 19u ? 16u : 0u); }
+
+// 16 * log2(x) as b2z_zstd_cost.h:zop_log16, with the fraction table in registers
+__device__ __forceinline__ uint32_t dp_log16(uint32_t x) {
+    const uint32_t hb = highbit32(x);
+    const uint32_t k = hb >= 4u ? ((x >> (hb - 4u)) & 15u) : ((x << (4u - hb)) & 15u);
+    // ZOP_FRAC_LIST (1,2,3,5,6,7,8,9 | 10,11,12,13,14,15,15,16) as two words of bytes
+    const uint64_t lo = 0x0908070605030201ull, hi = 0x100F0F0E0D0C0B0Aull;
+    const uint32_t fr = (uint32_t)(((k < 8u ? lo : hi) >> ((k & 7u) * 8u)) & 0xFFu);
+    return 16u * hb + ((k == 0u && (x & (x - 1u)) == 0u) ? 0u : fr);
+}
+
+// forward walk over one segment's choices.  EMIT = false: count only.
+template <bool EMIT>
+__device__ __forceinline__ void dp_walk(const uint8_t* __restrict__ fb /* frame base */, uint32_t segAbs /* frame-relative segment start */,
+                                        uint32_t blkAbs, uint32_t sn, const uint8_t* __restrict__ chc, const uint32_t* __restrict__ cnd,
+                                        uint32_t prevEnd /* block-relative end of the last sequence before this lane */,
+                                        uint64_t* __restrict__ outSeq, uint8_t* __restrict__ outLit,
+                                        uint32_t& cntSeq, uint32_t& cntLit, uint32_t& lastEndAbs) {
+    uint32_t rep0 = 0, rep1 = 0, rep2 = 0, ns = 0, nl = 0;
+    const uint32_t s0 = segAbs - blkAbs;                                       // block-relative
+    for (uint32_t i = 0; i < sn;) {
+        uint32_t l = chc[i];
+        if (!l) { if (EMIT) outLit[nl] = fb[segAbs + i]; nl++; i++; continue; }
+        const uint32_t off = B2Z_CAND_OFF(cnd[i]);
+        if (l == B2Z_CAP) { const uint8_t* a = fb + segAbs + i; const uint8_t* q = a - off; while (i + l < sn && a[l] == q[l]) l++; }
+        if (EMIT) {
+            const uint32_t pos = s0 + i, ll = pos - prevEnd;
+            uint32_t code = 0, offBase;
+            if (ll) { if (off == rep0) code = 1; else if (off == rep1) code = 2; else if (off == rep2) code = 3; }
+            else { if (off == rep1) code = 1; else if (off == rep2) code = 2; else if (rep0 > 1u && off == rep0 - 1u) code = 3; }
+            if (code == 0) { offBase = off + 3u; rep2 = rep1; rep1 = rep0; rep0 = off; }
+            else {
+                offBase = code;
+                const uint32_t idx = code - 1u + (ll == 0u);
+                if (idx != 0) {
+                    const uint32_t cur = idx == 3 ? rep0 - 1u : (idx == 1 ? rep1 : rep2);
+                    if (idx != 1) rep2 = rep1;
+                    rep1 = rep0; rep0 = cur;
+                }
+            }
+            outSeq[ns] = B2Z_PACK_SEQ(offBase, ll, l);
+            prevEnd = pos + l;
+        }
+        ns++; i += l; lastEndAbs = s0 + i;
+    }
+    cntSeq = ns; cntLit = nl;
+}
+
+__global__ void __launch_bounds__(B2Z_DP_WARPS * 32)
+zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint32_t* __restrict__ cand, uint8_t* __restrict__ choice,
+                   uint64_t* __restrict__ seqs, uint32_t* __restrict__ nseq, uint8_t* __restrict__ lits, uint32_t* __restrict__ nlit,
+                   uint32_t nBlockSlots) {
+    B2Z_DYN_SMEM(DpWarpSmem, allSm);
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    DpWarpSmem& sm = allSm[wib];
+    const uint32_t bw = blockIdx.x * B2Z_DP_WARPS + wib;                       // block slot: frame * blocksPerFrame + block in frame
+    if (bw >= nBlockSlots) return;
+    const uint32_t bpf = 1u << (g.frameLog - 17u);
+    const uint64_t f = bw >> (g.frameLog - 17u);
+    const uint32_t b = bw & (bpf - 1u);
+    const uint32_t n = enc_frame_bytes(g, srcSize, f);
+    const uint32_t b0 = b << 17;
+    if (b0 >= n) return;                                                       // the last frame may hold fewer blocks
+    const uint32_t bn = (n - b0) < B2Z_BLOCK ? (n - b0) : B2Z_BLOCK;
+    const uint64_t f0 = f << g.frameLog;
+    const uint8_t* __restrict__ fb = src + f0;
+    const uint8_t* __restrict__ bs = fb + b0;
+    const uint32_t* __restrict__ cndB = cand + f0 + b0;
+    uint8_t* __restrict__ chcB = choice + f0 + b0;
+    uint64_t* __restrict__ out = seqs + (size_t)bw * B2Z_MAXSEQ;
+    uint8_t* __restrict__ lit = lits + f0 + b0;
+
+    // ---- 1. literal prices
+    for (uint32_t i = lane; i < 256u; i += 32u) sm.hist[i] = 0;
+    __syncwarp();
+    for (uint32_t idx = lane;; idx += 32u) {
+        const uint32_t o = (idx >> 2) * 256u + (idx & 3u) * 16u;              // 4 lanes per sampled 64-byte run
+        if ((idx & ~31u) * 64u >= bn) break;                                   // warp-uniform: the step's first run starts past the block
+        if (o + 16u <= bn) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(bs + o));
+            const uint32_t ws[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) { atomicAdd(&sm.hist[ws[k] & 255u], 1u); atomicAdd(&sm.hist[(ws[k] >> 8) & 255u], 1u); atomicAdd(&sm.hist[(ws[k] >> 16) & 255u], 1u); atomicAdd(&sm.hist[ws[k] >> 24], 1u); }
+        } else for (uint32_t k = o; k < bn && k < o + 16u; k++) atomicAdd(&sm.hist[bs[k]], 1u);
+    }
+    __syncwarp();
+    {
+        uint32_t part = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) part += sm.hist[lane * 8u + k];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(B2Z_FULL, part, d);
+        const uint32_t lt = dp_log16(part);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t h = sm.hist[lane * 8u + k];
+            uint32_t v = B2Z_DP_LIT_MAX;
+            if (h) { const uint32_t lh = dp_log16(h); v = lt > lh ? lt - lh : 1u; }
+            sm.litc[lane * 8u + k] = (uint8_t)(v < B2Z_DP_LIT_MIN ? B2Z_DP_LIT_MIN : (v > B2Z_DP_LIT_MAX ? B2Z_DP_LIT_MAX : v));
+        }
+    }
+    __syncwarp();
+
+    // ---- 2. backward dynamic programme over this lane's segment
+    const uint32_t s0 = lane * B2Z_SEG;
+    const bool active = s0 < bn;
+    const uint32_t sn = active ? ((bn - s0) < B2Z_SEG ? (bn - s0) : B2Z_SEG) : 0u;
+    const uint32_t* __restrict__ cnd = cndB + s0;
+    uint8_t* __restrict__ chc = chcB + s0;
+    uint32_t diff = 0;                                                         // any byte of the segment unlike the block's first byte
+    if (active) {
+        const uint32_t first4 = (uint32_t)bs[0] * 0x01010101u;
+        sm.ring[sn & 63u][lane] = 0;
+        for (uint32_t wi = (sn + 3u) >> 2; wi-- > 0;) {
+            const uint4 c4 = __ldcs(reinterpret_cast<const uint4*>(cnd + 4u * wi));
+            const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t*>(bs + s0 + 4u * wi));
+            const uint32_t cw[4] = { c4.x, c4.y, c4.z, c4.w };
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 3; j >= 0; j--) {
+                const uint32_t i = 4u * wi + (uint32_t)j;
+                if (i >= sn) continue;
+                const uint32_t byte = (b4 >> (8 * j)) & 255u;
+                diff |= byte ^ (first4 & 255u);
+                uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & 63u][lane], ch = 0;
+                const uint32_t c = cw[j];
+                if (c) {
+                    const uint32_t len = B2Z_CAND_LEN(c), ob = 16u * highbit32(B2Z_CAND_OFF(c) + 3u) + B2Z_DP_MATCH;
+#pragma unroll
+                    for (uint32_t k = 0; k <= B2Z_DP_NTRUNC; k++) {
+                        if (len >= B2Z_DP_MINLEN + k) {
+                            const uint32_t l = len - k, pr = ob + dp_ml_price(l) + sm.ring[(i + l) & 63u][lane];
+                            if (pr < best) { best = pr; ch = l; }
+                        }
+                    }
+                }
+                sm.ring[i & 63u][lane] = best;
+                packed |= ch << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(chc + 4u * wi) = packed;
+        }
+    }
+    // ---- one repeated byte: the canonical single sequence (stage E emits an RLE block for it)
+    if (!__any_sync(B2Z_FULL, diff != 0u) && bn > 1u) {
+        if (lane == 0) { out[0] = B2Z_PACK_SEQ(1u + 3u, 1u, bn - 1u); lit[0] = bs[0]; nseq[bw] = 1u; nlit[bw] = 1u; }
+        return;
+    }
+
+    // ---- 3. count
+    uint32_t cntSeq = 0, cntLit = 0, lastEnd = 0;
+    if (active) dp_walk<false>(fb, b0 + s0, b0, sn, chc, cnd, 0u, nullptr, nullptr, cntSeq, cntLit, lastEnd);
+    // ---- 4. places: exclusive sums of the counts, exclusive maximum of the last match ends
+    uint32_t seqBase = cntSeq, litBase = cntLit, prevEnd = cntSeq ? lastEnd : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(B2Z_FULL, seqBase, d), c = __shfl_up_sync(B2Z_FULL, litBase, d), e = __shfl_up_sync(B2Z_FULL, prevEnd, d);
+        if (lane >= (uint32_t)d) { seqBase += a; litBase += c; prevEnd = e > prevEnd ? e : prevEnd; }
+    }
+    const uint32_t totSeq = __shfl_sync(B2Z_FULL, seqBase, 31), totLit = __shfl_sync(B2Z_FULL, litBase, 31);
+    seqBase -= cntSeq; litBase -= cntLit;
+    prevEnd = __shfl_up_sync(B2Z_FULL, prevEnd, 1); if (lane == 0) prevEnd = 0;
+    // ---- 5. emit
+    if (active) { uint32_t a, c, e = 0; dp_walk<true>(fb, b0 + s0, b0, sn, chc, cnd, prevEnd, out + seqBase, lit + litBase, a, c, e); }
+    if (lane == 0) { nseq[bw] = totSeq; nlit[bw] = totLit; }
+}
+
+#ifndef B2Z_CUEMU
+size_t zstd_enc_dp_smem_bytes() { return sizeof(DpWarpSmem) * B2Z_DP_WARPS; }
+
+cudaError_t launch_zstd_enc_dp(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint32_t* cand, uint8_t* choice,
+                               uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit, cudaStream_t st) {
+    if (srcSize == 0) return cudaSuccess;
+    const uint64_t F = 1ull << g.frameLog, nFrames = (srcSize + F - 1) >> g.frameLog;
+    const uint32_t nBlockSlots = (uint32_t)(nFrames << (g.frameLog - 17u));
+    cudaError_t e = cudaFuncSetAttribute(zstd_enc_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zstd_enc_dp_smem_bytes());
+    if (e != cudaSuccess) return e;
+    zstd_enc_dp_kernel<<<(nBlockSlots + B2Z_DP_WARPS - 1) / B2Z_DP_WARPS, B2Z_DP_WARPS * 32, zstd_enc_dp_smem_bytes(), st>>>(
+        src, srcSize, g, cand, choice, seqs, nseq, lits, nlit, nBlockSlots);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace b2z

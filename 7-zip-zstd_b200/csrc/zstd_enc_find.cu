@@ -1,0 +1,148 @@
+// zstd_enc_find.cu -- stage F of the block-parallel Zstandard encoder (sm_100a): the match finder.
+//
+// One CTA owns one independent frame (2^frameLog input bytes) and keeps BOTH hash tables of the finder in its shared
+// memory (long: 2^hashLogL entries indexed by the 8-byte hash, short: 2^hashLogS entries indexed by the 5-byte hash;
+// 128 + 64 KiB by default): no table access ever leaves the SM.  An entry is (position + 1) << tagBits | tag, so a
+// candidate is only compared with the input when the tag agrees, and atomicMax on an entry keeps the highest position.
+//
+// The frame is walked in CHUNKS of CH = 32 * WPG positions, thread = position.  The CTA is G groups of WPG warps; chunk c
+// belongs to group c mod G.  A chunk's table accesses form a TURN: read both entries (table state before the chunk),
+// group barrier, atomicMax both entries, hand the turn to the next group (bar.arrive on its named barrier; the next
+// group's bar.sync waits for it).  Everything else -- loading the bytes, hashing, resolving the lanes of a step that share
+// a table index (__match_any_sync: a lane prefers the nearest lower lane of its step to the table's entry), comparing the
+// candidates with the input, packing the result -- happens outside the turn, so while one group holds the turn the
+// other G-1 groups hash or compare.  The serial chain of a frame is therefore two shared-memory accesses and two barrier
+// hops per CH positions; the result is the pure function of the frame's bytes that
+// oracle/zstd_enc_oracle.c:b2zo_zstd_candidates states position by position.
+//
+// Output: one candidate word per position (B2Z_CAND: offset << 7 | length, 0 = none), consumed by stage G
+// (zstd_enc_dp.cu).  Replaces the finder half of zstd_double_fast.c:103-330 (ZSTD_compressBlock_doubleFast_noDict_generic:
+// hashLong / hashSmall look-ups and inserts, ZSTD_count), the table upkeep of zstd_compress.c:4591 and the job slicing of
+// zstdmt_compress.c:1184-1246 (a frame is a job).
+#include "b2z_device.cuh"
+#include "b2z_kernels.h"
+
+namespace b2z {
+
+#define B2Z_FIND_BAR_TURN(g) (1u + (g))        // named barrier ids: turn hand-over into group g ...
+#define B2Z_FIND_BAR_GRP(g)  (8u + (g))        // ... and the read -> write barrier inside group g
+
+template <int WPG, int G>
+__global__ void __launch_bounds__(WPG * G * 32, 1)
+zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cand,
+                     const volatile uint32_t* ready, uint32_t readyShift, uint32_t* __restrict__ errFlag) {
+    B2Z_EXTERN_SMEM(uint32_t, smem);
+    constexpr uint32_t CH = WPG * 32u, NT = CH * G;
+    static_assert(G >= 2 && G <= 7, "named barriers 1..7 and 8..14");
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, grp = tid / CH, tg = tid % CH;
+    const uint32_t HL = g.hashLogL, HS = g.hashLogS;
+    uint32_t* const TL = smem;
+    uint32_t* const TS = smem + (1u << HL);
+    const uint32_t tableWords = (1u << HL) + (1u << HS);
+    const uint32_t tagBits = 32u - (g.frameLog + 1u), tagMask = (1u << tagBits) - 1u;
+    const uint32_t W = g.windowLog >= 32 ? 0xFFFFFFFFu : (1u << g.windowLog);
+    const uint64_t nFrames = (srcSize + (1ull << g.frameLog) - 1) >> g.frameLog;
+    const uint32_t nextGrp = grp + 1u == (uint32_t)G ? 0u : grp + 1u;
+
+    // the first turn of the kernel belongs to group 0 and nobody hands it over: the last group arrives once up front.
+    // Afterwards every frame runs a multiple of G chunks, so the hand-over that closes a frame opens the next one.
+    if (grp == (uint32_t)G - 1u) bar_arrive(B2Z_FIND_BAR_TURN(0), 2u * CH);
+
+    for (uint64_t f = blockIdx.x; f < nFrames; f += gridDim.x) {
+        const uint64_t f0 = f << g.frameLog;
+        const uint32_t n = enc_frame_bytes(g, srcSize, f);
+        const uint64_t* __restrict__ w = reinterpret_cast<const uint64_t*>(src + f0);
+        const uint32_t nWords = (n + 7u) >> 3;
+        uint32_t* __restrict__ out = cand + f0;
+        // host-pointer path: the input is still being uploaded chunk by chunk; a frame starts once the flag of the chunk
+        // that holds its last byte is set (a stream-ordered copy after the chunk).  A flag that never comes is an error
+        // the caller sees (B200Z_E_CUDA), never a frame of whatever the buffer held.
+        if (ready && n) {
+            if (tid == 0) {
+                uint32_t spins = 0;
+                while (ready[(f0 + n - 1u) >> readyShift] == 0u) { if (++spins > (1u << 22)) { atomicExch(errFlag, 1u); break; } __nanosleep(1000); }
+            }
+        }
+        __syncthreads();                                                       // flag seen; previous frame's table accesses done
+        for (uint32_t i = tid; i < tableWords / 4u; i += NT) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+
+        const uint32_t nChunks = (n + CH - 1u) / CH, nIter = (nChunks + G - 1u) / G;
+        for (uint32_t it = 0; it < nIter; it++) {
+            const uint32_t p = (it * G + grp) * CH + tg;
+            // ---- before the turn: bytes, hashes, same-step groups
+            const uint64_t v = ld64u(w, p, nWords);
+            const bool hashable = p + 8u <= n;                                 // p >= n for the padding chunks of the last iteration
+            const uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
+            const uint32_t iL = (uint32_t)(hl >> (64u - HL)), iS = (uint32_t)(hs >> (64u - HS));
+            const uint32_t tL = (uint32_t)(hl >> (64u - HL - tagBits)) & tagMask, tS = (uint32_t)(hs >> (64u - HS - tagBits)) & tagMask;
+            const uint32_t mineL = ((p + 1u) << tagBits) | tL, mineS = ((p + 1u) << tagBits) | tS;
+            const uint32_t gL = __match_any_sync(B2Z_FULL, hashable ? iL : (0x80000000u | lane));
+            const uint32_t gS = __match_any_sync(B2Z_FULL, hashable ? iS : (0x80000000u | lane));
+            const uint32_t lowL = gL & lanemask_lt(), lowS = gS & lanemask_lt();
+            // ---- the turn
+            bar_sync(B2Z_FIND_BAR_TURN(grp), 2u * CH);
+            uint32_t eL = 0, eS = 0;
+            if (hashable) { eL = TL[iL]; eS = TS[iS]; }
+            if (WPG > 1) bar_sync(B2Z_FIND_BAR_GRP(grp), CH); else __syncwarp();
+            if (hashable) {
+                if ((gL >> lane) == 1u) atomicMax(&TL[iL], mineL);             // the highest lane of a same-index group carries the step's newest position
+                if ((gS >> lane) == 1u) atomicMax(&TS[iS], mineS);
+            }
+            bar_arrive(B2Z_FIND_BAR_TURN(nextGrp), 2u * CH);
+            // ---- after the turn: a lower lane of the step with my index is nearer than anything in the table
+            {
+                const uint32_t fromL = __shfl_sync(B2Z_FULL, mineL, lowL ? 31 - __clz((int)lowL) : 0);
+                const uint32_t fromS = __shfl_sync(B2Z_FULL, mineS, lowS ? 31 - __clz((int)lowS) : 0);
+                if (lowL) eL = fromL;
+                if (lowS) eS = fromS;
+            }
+            uint32_t word = 0;
+            if (hashable) {
+                const uint32_t segEnd = ((p | (B2Z_SEG - 1u)) + 1u) < n ? ((p | (B2Z_SEG - 1u)) + 1u) : n;
+                uint32_t maxLen = segEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
+                uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
+                if (eL && (eL & tagMask) == tL) { const uint32_t q = (eL >> tagBits) - 1u; if (p - q <= W) { offL = p - q; lenL = match_len_pv(w, q, p, v, maxLen, nWords); } }
+                if (eS && (eS & tagMask) == tS) { const uint32_t q = (eS >> tagBits) - 1u; if (p - q <= W && p - q != offL) { offS = p - q; lenS = match_len_pv(w, q, p, v, maxLen, nWords); } }
+                uint32_t len = lenL, off = offL;
+                if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
+                if (len >= B2Z_DP_MINLEN) word = B2Z_CAND(len, off);
+            }
+            if (p < n) __stcs(out + p, word);                                  // streaming: the words are next read by another kernel
+        }
+    }
+    // leave the barriers balanced: the hand-over that closed the last frame is consumed by group 0
+    if (grp == 0) bar_sync(B2Z_FIND_BAR_TURN(0), 2u * CH);
+}
+
+#ifndef B2Z_CUEMU
+size_t zstd_enc_find_smem_bytes(const EncGeom& g) { return (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS)) * 4u; }
+
+template <int WPG, int G>
+static cudaError_t launch_find_t(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,
+                                 const uint32_t* ready, uint32_t readyShift, uint32_t* errFlag, cudaStream_t st) {
+    const size_t smem = zstd_enc_find_smem_bytes(g);
+    static size_t configured = 0;                 // per instantiation; the attribute is per function, any device
+    if (configured != smem) {
+        cudaError_t e = cudaFuncSetAttribute(zstd_enc_find_kernel<WPG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    zstd_enc_find_kernel<WPG, G><<<nCtas, WPG * G * 32, smem, st>>>(src, srcSize, g, cand, ready, readyShift, errFlag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zstd_enc_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,
+                                 const uint32_t* ready, uint32_t readyShift, uint32_t* errFlag, cudaStream_t st) {
+    if (srcSize == 0) return cudaSuccess;
+    switch (g.chunkLog) {
+    case 5: return launch_find_t<1, 7>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
+    case 6: return launch_find_t<2, 7>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
+    case 7: return launch_find_t<4, 7>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
+    case 8: return launch_find_t<8, 4>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
+    }
+    return cudaErrorInvalidValue;
+}
+#endif
+
+}  // namespace b2z

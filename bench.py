@@ -274,7 +274,7 @@ def main():
         if dist:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (stage M, zstd_enc_match_kernel): algorithmic bytes per launch
+    # ---- roofline of the dominant kernel (stage F, zstd_enc_find_kernel): algorithmic bytes per launch
     #      = U * (1 + 1/ratio)  (encode reads the input once, writes the compressed stream once)
     peaks = {}
     try:
@@ -285,14 +285,14 @@ def main():
     # LZMA2: the dominant kernel is stage R (lzma2_enc_range_kernel: one serial range-coder chain per 1 MiB block)
     #        with the price-based parse it is stage P (lzma2_parse_kernel: one dynamic-programme chain per slice)
     zparse = (not lz) and a.level >= 8
-    dom_kernel = ("lzma2_parse_kernel" if a.lzma2_parse else "lzma2_enc_range_kernel") if lz else ("zstd_enc_parse_kernel" if zparse else "zstd_enc_match_kernel")
+    dom_kernel = ("lzma2_parse_kernel" if a.lzma2_parse else "lzma2_enc_range_kernel") if lz else ("zstd_enc_parse_kernel" if zparse else "zstd_enc_find_kernel")
     match_ms = ((stats["parse_ms"] if a.lzma2_parse else stats["entropy_ms"]) if lz else (stats["parse_ms"] if zparse else stats["match_ms"])) / a.steps
     algo_bytes = unit_bytes * (1.0 + 1.0 / ratio)
     achieved = algo_bytes / 1e9 / (match_ms / 1e3) if match_ms > 0 else 0.0
     traffic = None
     try:
         if not (lz and a.lzma2_parse) and not zparse:               # no ncu capture of stage P / stage Z yet
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lzma2_range_traffic.json" if lz else "r1_match_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lzma2_range_traffic.json" if lz else "r2_find_traffic.json")))["dram_bytes_per_input_byte"] * unit_bytes
     except Exception:
         pass
     line = {

@@ -39,29 +39,29 @@ extern "C" {
 #define B200Z_E_CHECKSUM   -8   /* content checksum mismatch                 (S_FALSE)       */
 
 /* parameters (b200z_set_param) */
-#define B200Z_P_LEVEL       1   /* 1..22.  1-7: the level-3-class greedy/lazy parse (stage M); 8-22: the price-based parse (sets B200Z_P_ZSTD_PARSE) */
-#define B200Z_P_FRAMELOG    2   /* log2 of the independent frame ("job") size, 17..24, default 22       */
-#define B200Z_P_HASHLOG_L   3   /* accepted for compatibility (dual-table finder of the first version); unused */
-#define B200Z_P_HASHLOG_S   4   /* accepted for compatibility; unused                                        */
+#define B200Z_P_LEVEL       1   /* 1..22.  1-7: the level-3-class path (stage F finder + stage G parse); 8-22: the price-based parse on stage C's candidates (sets B200Z_P_ZSTD_PARSE) */
+#define B200Z_P_FRAMELOG    2   /* log2 of the independent frame ("job") size, 17..24, default 20       */
+#define B200Z_P_HASHLOG_L   3   /* stage F: log2 entries of the long (8-byte hash) table, 8..15, default 15; both tables live in one SM's shared memory */
+#define B200Z_P_HASHLOG_S   4   /* stage F: log2 entries of the short (5-byte hash) table, 8..15, default 14 (2^L + 2^S <= 49152)       */
 #define B200Z_P_WINDOWLOG   5   /* max match distance log, default = frameLog                            */
 #define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention; default on)
                                    bit1: XXH64 content checksum per frame (ZstdHandler.cpp:275 sets it for .zst) */
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 32 (4 GiB)         */
-#define B200Z_P_ROWLOG      9   /* log2 rows of the row-hash match finder (64-byte rows), 8..18, default 14   */
+#define B200Z_P_CHUNKLOG    9   /* stage F: log2 positions per table turn (reads of a chunk precede its writes), 5..8, default 7 */
 #define B200Z_P_LZMA2_MODEL 10  /* LZMA2 decoder: literal model in 1 = shared memory (13 warps/SM), 2 = global memory (32 warps/SM), 0 = by block count */
 #define B200Z_P_LZMA2_SLICELOG 11 /* LZMA2 encoder: log2 of the state-reset slices a block's range coding is split into (0..3, default 2):
                                    independent range-coder chains per block, as fast-lzma2's encoder threads (lzma2_enc.c:1937) */
 #define B200Z_P_LZMA2_PARSE 12  /* LZMA2 encoder parse: 0 = greedy/lazy on the finder shared with the zstd path (default), 1 = price-based:
                                    nearest-occurrence candidates by 3/4/6/8-byte keys + a windowed dynamic programme over the adaptive
                                    model -- the role of LzmaEnc.c:1225 GetOptimum / fast-lzma2 lzma2_enc.c:949 LZMA_optimalParse */
-#define B200Z_P_ZSTD_PARSE  13  /* Zstandard encoder parse: 0 = stage M (greedy/lazy row-hash finder), 1 = price-based: nearest-occurrence
+#define B200Z_P_ZSTD_PARSE  13  /* Zstandard encoder parse: 0 = stage F + stage G (shared-memory dual-hash finder, minimum-price path per 4 KiB segment), 1 = price-based: nearest-occurrence
                                    candidates + a per-block dynamic programme over adaptive code statistics -- the role of
                                    zstd_opt.c:1077 ZSTD_compressBlock_opt_generic.  B200Z_P_LEVEL sets it (>= 8); set it after the level to override */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
  * measured with CUDA events on the context's stream around each stage */
-#define B200Z_S_ENC_MATCH_MS    1
+#define B200Z_S_ENC_MATCH_MS    1   /* the finder: stage F (or stage C of the price-based parses) */
 #define B200Z_S_ENC_ENTROPY_MS  2
 #define B200Z_S_ENC_ASSEMBLE_MS 3
 #define B200Z_S_DEC_ENTROPY_MS  4
@@ -70,7 +70,7 @@ extern "C" {
 #define B200Z_S_H2D_BYTES       7
 #define B200Z_S_D2H_BYTES       8
 #define B200Z_S_DEC_PREPASS_MS  9
-#define B200Z_S_ENC_PARSE_MS    10  /* price-based parses: stage P / stage Z (stage C is counted as ENC_MATCH_MS) */
+#define B200Z_S_ENC_PARSE_MS    10  /* the parse: stage G (or stage P / stage Z of the price-based parses) */
 
 typedef struct b200z_ctx b200z_ctx;
 
@@ -109,10 +109,12 @@ int b200z_zstd_decompress_device(b200z_ctx *ctx, const void *d_src, size_t srcSi
 int b200z_zstd_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
                                void *dst, size_t dstCap, size_t *dstSize);
 
-/* Test tap: run only stage M (match finding + parse) on a device buffer and copy its per-block
- * outputs to host arrays (same layout as the oracle's b2zo_zstd_find_sequences). */
+/* Test taps: run only the finder + parse (stage F + stage G, or stage C + stage Z) on a device buffer and copy the per-block
+ * outputs to host arrays (same layout as the oracle's b2zo_zstd_find_sequences); stage_f: stage F's candidate words, one per
+ * input byte (layout of b2zo_zstd_candidates, frames back to back). */
 int b200z_zstd_enc_stage_m(b200z_ctx *ctx, const void *d_src, size_t srcSize,
                            uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit);
+int b200z_zstd_enc_stage_f(b200z_ctx *ctx, const void *d_src, size_t srcSize, uint32_t *cand);
 
 /* ---- LZMA2 / FLZMA2 (method 21) decoder --------------------------------------------------------------
  * src is the raw LZMA2 chunk stream a 7z folder stores for coder 21 (chunks ... 0x00 end marker); dictProp is the

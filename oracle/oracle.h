@@ -22,10 +22,10 @@ int64_t b2zo_zstd_decompress(void *dst, size_t dstCap, const void *src, size_t s
  * Output is byte-identical to the GPU path for the same parameters. */
 typedef struct {
     uint32_t frameLog;      /* log2 of independent frame size (default 22 = 4 MiB)            */
-    uint32_t hashLogL;      /* long (8-byte) hash table log (default 17)                      */
-    uint32_t hashLogS;      /* short (5-byte) hash table log (default 16)                     */
+    uint32_t hashLogL;      /* stage F long (8-byte hash) table log (default 15)              */
+    uint32_t hashLogS;      /* stage F short (5-byte hash) table log (default 14)             */
     uint32_t windowLog;     /* max match distance log (default = frameLog)                    */
-    uint32_t rowLog;        /* log2 rows of the row-hash match finder (default 14; 0 = dual hash tables) */
+    uint32_t chunkLog;      /* stage F: log2 positions per table turn (default 7)             */
     uint32_t flags;         /* bit0: skippable size hints before each frame; bit1: checksum;
                                bits 8..10: LZMA2 slice log; bit4: LZMA2 price-based parse */
 } b2zo_enc_params;
@@ -34,7 +34,10 @@ void   b2zo_enc_default_params(b2zo_enc_params *p, int level);
 size_t b2zo_zstd_compress_bound(size_t srcSize, const b2zo_enc_params *p);
 int64_t b2zo_zstd_compress(void *dst, size_t dstCap, const void *src, size_t srcSize, const b2zo_enc_params *p);
 
-/* Stage tap for parity with the GPU's stage M: per 128 KiB block, final sequences packed as
+/* Stage tap for parity with the GPU's stage F: one candidate word per position of one frame (B2Z_CAND, b2z_params.h) */
+void b2zo_zstd_candidates(const void *frame, uint32_t n, const b2zo_enc_params *p, uint32_t *cand);
+
+/* Stage tap for parity with the GPU's stage G: per 128 KiB block, final sequences packed as
  * B2Z_PACK_SEQ(offBase, ll, ml) (b2z_params.h) and the literal bytes (at the block's offset). */
 int64_t b2zo_zstd_find_sequences(const void *src, size_t srcSize, const b2zo_enc_params *p,
                                  uint64_t *seqs /* [nblocks*B2Z_MAXSEQ] */, uint32_t *nseq /* [nblocks] */,

@@ -2,14 +2,14 @@
  *
  * TEST INFRASTRUCTURE ONLY (see oracle.h).  This is the single-threaded statement of the
  * algorithm that 7-zip-zstd_b200/csrc/zstd_enc_*.cu implements with one CTA per frame
- * (stage M) and one warp per 128 KiB block (stage E).  Every decision below is integer and
+ * (stage F), one warp per 128 KiB block (stage G, stage E).  Every decision below is integer and
  * order-independent by construction, so the CUDA path must reproduce these bytes exactly;
  * tests compare stage taps (raw sequences, literals) and final frames byte-for-byte.
  *
  * What it replaces in the reference (level 3 = dfast; /root/reference/C/zstd/):
  *   ZSTDMT job slicing ............... zstdmt_compress.c:1184-1246  -> independent frames of 2^frameLog
  *   ZSTD_compress_frameChunk ......... zstd_compress.c:4591          -> 128 KiB blocks, 3-byte headers
- *   ZSTD_compressBlock_doubleFast .... zstd_double_fast.c:103-330    -> stage M (dual hash, all positions)
+ *   ZSTD_compressBlock_doubleFast .... zstd_double_fast.c:103-330    -> stage F (dual hash, all positions) + stage G (parse)
  *   ZSTD_hash5Ptr / ZSTD_hash8Ptr .... zstd_compress_internal.h:903-924 (same multiplicative hashes)
  *   ZSTD_storeSeq / ZSTD_updateRep ... zstd_compress_internal.h:775,817 -> merge + repcode pass
  *   ZSTD_compressLiterals ............ zstd_compress_literals.c:129-235
@@ -24,17 +24,17 @@
  * test exists); parity = the reference decoder round-trips every frame + ratio delta.
  *
  * Parallel semantics restated sequentially:
- *   - one warp owns one frame and walks it in steps of 32 positions; table state + the lower
- *     lanes of the step give each position the nearest previous occurrence of its hash key.
- *   - the parse is the greedy path with one-position lazy deferral inside a step, entered
- *     where the previous step's last match ended.
- *   - match lengths are capped at B2Z_CAP in stage M; stage E re-joins capped pieces.
+ *   - stage F: a CTA owns a frame and walks it in chunks of 2^chunkLog positions; a position sees the tables as they
+ *     stood before its chunk plus the lower lanes of its own 32-position step (b2zo_zstd_candidates);
+ *   - stage G: a warp owns a 128 KiB block, a lane a 4 KiB segment of it: minimum-price path per segment, repcode
+ *     history unknown at every segment start (parse_frame).
  */
 #include <string.h>
 #include <stdlib.h>
 #include "zstd_format.h"
 #include "oracle.h"
 #include "b2z_params.h"
+#include "b2z_zstd_cost.h"
 
 static inline uint64_t rd64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 static inline void wr16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
@@ -44,7 +44,7 @@ static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
     (void)level;
     p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
-    p->windowLog = B2Z_DEF_FRAMELOG; p->rowLog = B2Z_DEF_ROWLOG; p->flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);
+    p->windowLog = B2Z_DEF_FRAMELOG; p->chunkLog = B2Z_DEF_CHUNKLOG; p->flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);
 }
 
 size_t b2zo_zstd_compress_bound(size_t n, const b2zo_enc_params *p) {
@@ -52,7 +52,7 @@ size_t b2zo_zstd_compress_bound(size_t n, const b2zo_enc_params *p) {
     return n + blocks * 3 + frames * (B2Z_FRAME_HDR_MAX + 12 + 4) + 64;
 }
 
-/* ======================================================================= stage M */
+/* ======================================================================= stage F + stage G */
 static size_t count_match(const uint8_t *a, const uint8_t *b, size_t maxLen) {
     size_t n = 0;
     while (n + 8 <= maxLen) {
@@ -64,137 +64,139 @@ static size_t count_match(const uint8_t *a, const uint8_t *b, size_t maxLen) {
     return n;
 }
 
-typedef struct { uint32_t off; uint16_t len; } cand_t;
-
-/* Per-block sequence emitter: joins capped pieces, resolves repcodes, packs (ll, ml, offBase).
- * Sequential per block; rep history is "unknown" (0) at block start so that blocks stay
- * independent of each other (ZSTD_updateRep semantics, zstd_compress_internal.h:817-835). */
-typedef struct {
-    uint32_t rep[3];
-    uint32_t pendPos, pendLen, pendOff, pendLastPiece, pendValid;   /* block-relative */
-    uint32_t prevEnd;                                                /* end of last flushed sequence */
-    uint64_t *out; uint32_t n;
-} emitter_t;
-
-static void emit_flush(emitter_t *e) {
-    if (!e->pendValid) return;
-    uint32_t ll = e->pendPos - e->prevEnd, off = e->pendOff, ll0 = ll == 0, code = 0, offBase;
-    uint32_t *rep = e->rep;
-    if (!ll0) { if (off == rep[0]) code = 1; else if (off == rep[1]) code = 2; else if (off == rep[2]) code = 3; }
-    else { if (off == rep[1]) code = 1; else if (off == rep[2]) code = 2; else if (rep[0] > 1 && off == rep[0] - 1) code = 3; }
-    if (code == 0) { offBase = off + 3; rep[2] = rep[1]; rep[1] = rep[0]; rep[0] = off; }
-    else {
-        offBase = code;
-        uint32_t idx = code - 1 + ll0;                      /* 0..3 */
-        if (idx != 0) {
-            uint32_t cur = idx == 3 ? rep[0] - 1 : rep[idx];
-            if (idx != 1) rep[2] = rep[1];
-            rep[1] = rep[0]; rep[0] = cur;
+/* Stage F, one frame: src[0..n) -> one candidate word per position (b2z_params.h: B2Z_CAND).
+ *
+ * Two direct-mapped tables of position+tag entries, the long one indexed by the 8-byte hash and the short one by the
+ * 5-byte hash of the reference's double-fast finder (zstd_double_fast.c:103-330, constants zstd_compress_internal.h:903-924)
+ * -- sized for the shared memory of one SM (2^15 + 2^14 entries), not for the 2^17 + 2^16 of level 3.  The frame is
+ * walked in CHUNKS of 2^chunkLog positions: a position sees the table as it stood BEFORE its chunk, or -- nearer -- a
+ * lower position of its own 32-position step with the same table index; after a chunk every table entry holds the
+ * highest position of the chunk that indexes it.  That is a pure function of the frame's bytes: the kernel evaluates a
+ * chunk with 2^chunkLog threads (reads, barrier, atomicMax writes) and the steps' lower lanes with __match_any_sync.
+ * Every position is searched and inserted.  Candidates are compared over at most B2Z_CAP bytes and never beyond the end
+ * of their 4 KiB parse segment; the longer of (long, short) wins, the nearer on a tie. */
+void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P, uint32_t *cand) {
+    const uint8_t *src = (const uint8_t *)srcv;
+    const uint32_t HL = P->hashLogL, HS = P->hashLogS, CH = 1u << P->chunkLog;
+    const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
+    const uint64_t W = P->windowLog >= 32 ? 0xFFFFFFFFull : (1ull << P->windowLog);
+    uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
+    uint32_t *iL = (uint32_t *)malloc(CH * 4), *iS = (uint32_t *)malloc(CH * 4), *eLn = (uint32_t *)malloc(CH * 4), *eSn = (uint32_t *)malloc(CH * 4);
+    for (uint32_t c0 = 0; c0 < n; c0 += CH) {
+        const uint32_t c1 = n - c0 < CH ? n : c0 + CH;
+        for (uint32_t p = c0; p < c1; p++) {
+            const uint32_t k = p - c0;
+            iL[k] = iS[k] = 0xFFFFFFFFu; cand[p] = 0;
+            if (p + 8 > n) continue;                                            /* the last 7 positions are neither searched nor inserted */
+            const uint64_t v = rd64(src + p), hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
+            iL[k] = (uint32_t)(hl >> (64 - HL)); iS[k] = (uint32_t)(hs >> (64 - HS));
+            const uint32_t tL = (uint32_t)(hl >> (64 - HL - tagBits)) & tagMask, tS = (uint32_t)(hs >> (64 - HS - tagBits)) & tagMask;
+            eLn[k] = ((p + 1) << tagBits) | tL; eSn[k] = ((p + 1) << tagBits) | tS;
+            uint32_t eL = TL[iL[k]], eS = TS[iS[k]];
+            for (uint32_t q = p & ~31u; q < p; q++) {                          /* lower positions of the same step */
+                if (iL[q - c0] == iL[k]) eL = eLn[q - c0];
+                if (iS[q - c0] == iS[k]) eS = eSn[q - c0];
+            }
+            const uint32_t segEnd = ((p | (B2Z_SEG - 1)) + 1) < n ? ((p | (B2Z_SEG - 1)) + 1) : n;
+            uint32_t maxLen = segEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
+            uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
+            if (eL && (eL & tagMask) == tL) { const uint32_t q = (eL >> tagBits) - 1; if (p - q <= W) { offL = p - q; lenL = (uint32_t)count_match(src + q, src + p, maxLen); } }
+            if (eS && (eS & tagMask) == tS) { const uint32_t q = (eS >> tagBits) - 1; if (p - q <= W && p - q != offL) { offS = p - q; lenS = (uint32_t)count_match(src + q, src + p, maxLen); } }
+            uint32_t len = lenL, off = offL;
+            if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
+            if (len >= B2Z_DP_MINLEN) cand[p] = B2Z_CAND(len, off);
         }
+        for (uint32_t k = 0; k < c1 - c0; k++) if (iL[k] != 0xFFFFFFFFu) { TL[iL[k]] = eLn[k]; TS[iS[k]] = eSn[k]; }   /* ascending: the highest position stays */
     }
-    e->out[e->n++] = B2Z_PACK_SEQ(offBase, ll, e->pendLen);
-    e->prevEnd = e->pendPos + e->pendLen; e->pendValid = 0;
+    free(TL); free(TS); free(iL); free(iS); free(eLn); free(eSn);
 }
 
-/* a match chosen by the parse at block-relative `pos` */
-static void emit_match(emitter_t *e, const uint8_t *blk, uint32_t pos, uint32_t len, uint32_t off) {
-    if (e->pendValid && pos == e->pendPos + e->pendLen && e->pendLastPiece == B2Z_CAP) {
-        int same = off == e->pendOff;
-        if (!same) same = count_match(blk + pos - e->pendOff, blk + pos, len) == len;
-        if (same) { e->pendLen += len; e->pendLastPiece = len; return; }
+/* extra-bit price of a match length in 1/16 bit (ours: a step at 19, then the bit length of the ML code's range) */
+static inline uint32_t dp_ml_price(uint32_t l) { return l >= 35 ? 16 * (zf_highbit32(l - 3) - 3) : (l >= 19 ? 16 : 0); }
+
+typedef struct { uint32_t rep[3]; } seg_rep_t;
+
+/* Stage G, one frame: candidate words -> per 128 KiB block final sequences (B2Z_PACK_SEQ) and literal bytes.
+ *
+ * The role of the parse in ZSTD_compressBlock_doubleFast (greedy + repcode check) is played by a minimum-price path:
+ * a block is cut into SEGMENTS of 4 KiB (one GPU lane each, a warp per block); inside a segment a backward dynamic
+ * programme prices, at every position, the literal (its byte's cost in the block's sampled histogram) against the
+ * position's candidate at its full length and at up to B2Z_DP_NTRUNC shorter lengths (B2Z_DP_MATCH + the offset's and the
+ * length code's extra bits).  The forward walk follows the choices; a chosen match of the full B2Z_CAP bytes is extended
+ * by direct comparison to the segment end and the walk continues with the choice stored where the match ends.
+ * Offsets become offBase with a repcode history that starts "unknown" at every segment (ZSTD_updateRep rules,
+ * zstd_compress_internal.h:817-835), so lanes are independent; literal runs carry across segments.
+ * A block of one repeated byte is emitted as the single sequence stage E turns into an RLE block. */
+static void parse_frame(const uint8_t *src, uint32_t n, const uint32_t *cand,
+                        uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
+    static const zop_tables ZT = ZOP_TABLES_INIT;
+    uint32_t *cost = (uint32_t *)malloc((B2Z_SEG + 1) * 4);
+    uint8_t *choice = (uint8_t *)malloc(B2Z_SEG);
+    const uint32_t nblocks = (n + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+        const uint32_t b0 = blk * ZF_BLOCK_MAX, bn = n - b0 < ZF_BLOCK_MAX ? n - b0 : ZF_BLOCK_MAX;
+        const uint8_t *bs = src + b0;
+        uint64_t *out = seqs + (size_t)blk * B2Z_MAXSEQ;
+        uint8_t *lit = lits + b0;
+        uint32_t ns = 0, nl = 0;
+        /* one repeated byte */
+        { uint32_t i = 1; while (i < bn && bs[i] == bs[0]) i++;
+          if (i == bn && bn > 1) { out[0] = B2Z_PACK_SEQ(1 + 3, 1, bn - 1); lit[0] = bs[0]; nseq[blk] = 1; nlit[blk] = 1; continue; } }
+        /* literal prices from the sampled histogram */
+        uint32_t hist[256] = { 0 }, tot = 0, lc[256];
+        for (uint32_t i = 0; i < bn; i++) if (B2Z_DP_SAMPLED(i)) { hist[bs[i]]++; tot++; }
+        for (uint32_t c = 0; c < 256; c++) {
+            uint32_t v = hist[c] ? zop_cost(&ZT, hist[c], tot) : B2Z_DP_LIT_MAX;
+            lc[c] = v < B2Z_DP_LIT_MIN ? B2Z_DP_LIT_MIN : (v > B2Z_DP_LIT_MAX ? B2Z_DP_LIT_MAX : v);
+        }
+        uint32_t prevEnd = 0;                                                   /* block-relative end of the last sequence */
+        for (uint32_t s0 = 0; s0 < bn; s0 += B2Z_SEG) {
+            const uint32_t s1 = bn - s0 < B2Z_SEG ? bn : s0 + B2Z_SEG, sn = s1 - s0;
+            cost[sn] = 0;
+            for (uint32_t i = sn; i-- > 0;) {
+                const uint32_t c = cand[b0 + s0 + i];
+                uint32_t best = lc[bs[s0 + i]] + cost[i + 1], ch = 0;
+                if (c) {
+                    const uint32_t len = B2Z_CAND_LEN(c), ob = 16 * zf_highbit32(B2Z_CAND_OFF(c) + 3) + B2Z_DP_MATCH;
+                    for (uint32_t k = 0; k <= B2Z_DP_NTRUNC && len >= B2Z_DP_MINLEN + k; k++) {
+                        const uint32_t l = len - k, pr = ob + dp_ml_price(l) + cost[i + l];
+                        if (pr < best) { best = pr; ch = l; }
+                    }
+                }
+                cost[i] = best; choice[i] = (uint8_t)ch;
+            }
+            seg_rep_t R = { { 0, 0, 0 } };
+            for (uint32_t i = 0; i < sn;) {
+                uint32_t l = choice[i];
+                if (!l) { lit[nl++] = bs[s0 + i]; i++; continue; }
+                const uint32_t pos = s0 + i, off = B2Z_CAND_OFF(cand[b0 + pos]);
+                if (l == B2Z_CAP) { const uint8_t *a = bs + pos, *q = a - off;             /* q may point into an earlier block of the frame */
+                                    while (i + l < sn && a[l] == q[l]) l++; }
+                const uint32_t ll = pos - prevEnd, ll0 = ll == 0;
+                uint32_t code = 0, offBase;
+                if (!ll0) { if (off == R.rep[0]) code = 1; else if (off == R.rep[1]) code = 2; else if (off == R.rep[2]) code = 3; }
+                else { if (off == R.rep[1]) code = 1; else if (off == R.rep[2]) code = 2; else if (R.rep[0] > 1 && off == R.rep[0] - 1) code = 3; }
+                if (code == 0) { offBase = off + 3; R.rep[2] = R.rep[1]; R.rep[1] = R.rep[0]; R.rep[0] = off; }
+                else {
+                    offBase = code;
+                    const uint32_t idx = code - 1 + ll0;
+                    if (idx != 0) { const uint32_t cur = idx == 3 ? R.rep[0] - 1 : R.rep[idx]; if (idx != 1) R.rep[2] = R.rep[1]; R.rep[1] = R.rep[0]; R.rep[0] = cur; }
+                }
+                out[ns++] = B2Z_PACK_SEQ(offBase, ll, l);
+                prevEnd = pos + l; i += l;
+            }
+        }
+        nseq[blk] = ns; nlit[blk] = nl;
     }
-    emit_flush(e);
-    e->pendPos = pos; e->pendLen = len; e->pendOff = off; e->pendLastPiece = len; e->pendValid = 1;
+    free(cost); free(choice);
 }
 
-/* One frame: src[0..n).  Emits, per 128 KiB block, final sequences and the literal bytes.
- * The GPU runs this with one warp per frame: a step is B2Z_STEP (=32) consecutive positions,
- * lane i owning position base+i; "tables + lower lanes of the same step" (resolved with
- * __match_any_sync) give every position exactly the nearest previous occurrence of its hash
- * key, which is what the position-by-position loop below states. */
 static void find_sequences_frame(const uint8_t *src, size_t n, const b2zo_enc_params *P,
                                  uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit) {
-    const uint32_t HL = P->hashLogL, HS = P->hashLogS;
-    const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
-    const size_t W = (size_t)1 << P->windowLog;
-    uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
-    const uint32_t ROWLOG = P->rowLog;                   /* 0: dual tables; else log2(rows) of the row-hash finder */
-    uint32_t *TR = ROWLOG ? (uint32_t *)calloc((size_t)16 << ROWLOG, 4) : NULL;
-    cand_t cand[B2Z_STEP];
-    size_t entry = 0;                                       /* path entry point (frame-relative) */
-    size_t nblocks = (n + ZF_BLOCK_MAX - 1) / ZF_BLOCK_MAX;
-    emitter_t em; memset(&em, 0, sizeof(em));
-    for (size_t b = 0; b < nblocks; b++) { nseq[b] = 0; nlit[b] = 0; }
-    for (size_t c0 = 0; c0 < n; c0 += B2Z_STEP) {
-        size_t c1 = c0 + B2Z_STEP < n ? c0 + B2Z_STEP : n;
-        size_t blk = c0 / ZF_BLOCK_MAX, blkStart = blk * ZF_BLOCK_MAX;
-        size_t blkEnd = blkStart + ZF_BLOCK_MAX < n ? blkStart + ZF_BLOCK_MAX : n;
-        if (c0 == blkStart) { memset(&em, 0, sizeof(em)); em.out = seqs + blk * B2Z_MAXSEQ; }
-        int search = entry < c1;                            /* whole step inside a match: insert only */
-        for (size_t p = c0; p < c1; p++) {
-            cand_t best = { 0, 0 };
-            if (p + 8 <= n && ROWLOG) {
-                /* row-hash finder: ONE 64-byte row per position (15 entries + head), row chosen by the 5-byte hash, entries
-                 * tagged with bits of the 8-byte hash.  long candidate = newest entry with my tag, short = newest entry. */
-                uint64_t v = rd64(src + p);
-                uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
-                uint32_t *row = &TR[(hs >> (64 - ROWLOG)) * 16];
-                uint32_t t8 = (uint32_t)(hl >> (64 - tagBits)) & tagMask, head = row[15];
-                if (search) {
-                    uint32_t cl = 0, cs = 0;
-                    for (uint32_t k = 1; k <= B2Z_ROW_WAYS; k++) { uint32_t e = row[(head + B2Z_ROW_WAYS - k) % B2Z_ROW_WAYS]; if (!e) break; if (!cs) cs = e; if ((e & tagMask) == t8) { cl = e; break; } }
-                    size_t maxLen = blkEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
-                    uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
-                    if (cl) { size_t q = (cl >> tagBits) - 1; if (p - q <= W) { offL = (uint32_t)(p - q); lenL = (uint32_t)count_match(src + q, src + p, maxLen); } }
-                    if (cs && cs != cl) { size_t q = (cs >> tagBits) - 1; if (p - q <= W) { offS = (uint32_t)(p - q); lenS = (uint32_t)count_match(src + q, src + p, maxLen); } }
-                    uint32_t len = lenL, off = offL;
-                    if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
-                    if (b2z_accept(len, off)) { best.off = off; best.len = (uint16_t)len; }
-                }
-                row[head] = (((uint32_t)p + 1) << tagBits) | t8; row[15] = (head + 1) % B2Z_ROW_WAYS;
-            } else
-            if (p + 8 <= n) {
-                uint64_t v = rd64(src + p);
-                uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
-                uint32_t *sl = &TL[hl >> (64 - HL)], *ss = &TS[hs >> (64 - HS)];
-                uint32_t tL = (uint32_t)(hl >> (64 - HL - tagBits)) & tagMask;
-                uint32_t tS = (uint32_t)(hs >> (64 - HS - tagBits)) & tagMask;
-                if (search) {
-                    uint32_t eL = *sl, eS = *ss;
-                    size_t maxLen = blkEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
-                    uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
-                    if (eL && (eL & tagMask) == tL) {
-                        size_t q = (eL >> tagBits) - 1;
-                        if (p - q <= W) { offL = (uint32_t)(p - q); lenL = (uint32_t)count_match(src + q, src + p, maxLen); }
-                    }
-                    if (eS && (eS & tagMask) == tS) {
-                        size_t q = (eS >> tagBits) - 1;
-                        if (p - q <= W) { offS = (uint32_t)(p - q); lenS = (uint32_t)count_match(src + q, src + p, maxLen); }
-                    }
-                    uint32_t len = lenL, off = offL;
-                    if (lenS > lenL || (lenS == lenL && offS < offL)) { len = lenS; off = offS; }
-                    if (b2z_accept(len, off)) { best.off = off; best.len = (uint16_t)len; }
-                }
-                *sl = (((uint32_t)p + 1) << tagBits) | tL;  /* latest position wins */
-                *ss = (((uint32_t)p + 1) << tagBits) | tS;
-            }
-            cand[p - c0] = best;
-        }
-        /* ---- path through this step: greedy with one-position lazy deferral inside the step */
-        while (entry < c1) {
-            size_t p = entry;
-            const cand_t *cd = &cand[p - c0];
-            if (cd->len && !(p + 1 < c1 && cand[p + 1 - c0].len >= cd->len + B2Z_LAZY_GAIN)) {
-                emit_match(&em, src + blkStart, (uint32_t)(p - blkStart), cd->len, cd->off);
-                entry = p + cd->len;
-            } else {
-                lits[blkStart + nlit[blk]++] = src[p];
-                entry = p + 1;
-            }
-        }
-        if (c1 == blkEnd) { emit_flush(&em); nseq[blk] = em.n; }
-    }
-    free(TL); free(TS); free(TR);
+    uint32_t *cand = (uint32_t *)malloc((n + 1) * 4);
+    b2zo_zstd_candidates(src, (uint32_t)n, P, cand);
+    parse_frame(src, (uint32_t)n, cand, seqs, nseq, lits, nlit);
+    free(cand);
 }
 
 int64_t b2zo_zstd_find_sequences(const void *srcv, size_t srcSize, const b2zo_enc_params *P,

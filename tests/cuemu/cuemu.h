@@ -56,6 +56,7 @@ struct Warp { uint64_t slot[32], res[2][32]; uint32_t resMask[2], arrivedMask, g
 struct Block {
     std::vector<Fiber> fibers; std::vector<Warp> warps;
     uint32_t cur = 0, nThreads = 0, liveThreads = 0, barArrived = 0, barGen = 0;
+    uint32_t nbArrived[16] = {0}, nbGen[16] = {0};      // named barriers (bar.sync / bar.arrive id, count)
     dim3 bidx, bdim, gdim;
     void* mainSp = nullptr;
     unsigned char* dynSmem = nullptr;
@@ -97,6 +98,7 @@ inline void fiber_entry() { blk()->body(); fiber_exit(); }
 inline void run_block(Block& b) {
     blk() = &b;
     b.liveThreads = b.nThreads; b.barArrived = 0; b.barGen = 0;
+    memset(b.nbArrived, 0, sizeof(b.nbArrived)); memset(b.nbGen, 0, sizeof(b.nbGen));
     b.warps.assign((b.nThreads + 31) / 32, Warp());
     for (auto& w : b.warps) memset(&w, 0, sizeof(w));
     for (uint32_t t = 0; t < b.nThreads; t++) {
@@ -144,6 +146,12 @@ template <class F> inline uint64_t launch(dim3 grid, dim3 block, size_t dynSmemB
     return b.collectives;
 }
 inline void* dyn_smem() { return blk()->dynSmem; }
+// bar.sync id, n (wait = true) / bar.arrive id, n (wait = false): the n-th arrival releases the barrier's generation
+inline void named_bar(uint32_t id, uint32_t n, bool wait) {
+    Block* b = blk(); const uint32_t gen = b->nbGen[id];
+    if (++b->nbArrived[id] == n) { b->nbArrived[id] = 0; b->nbGen[id]++; }
+    else if (wait) while (b->nbGen[id] == gen) yield();
+}
 
 }  // namespace cuemu
 
@@ -175,10 +183,13 @@ inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u)); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
 template <class T, class U> inline void __stcg(T* p, U v) { *p = (T)v; }
 template <class T, class U> inline void __stcs(T* p, U v) { *p = (T)v; }
 inline void __nanosleep(unsigned) { cuemu::yield(); }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
+inline uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t o = *p; if (v > o) *p = v; return o; }
+inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }
 
 inline uint32_t cuemu_lane_id() { return cuemu::lane(); }

@@ -3,7 +3,8 @@
 // tests/cuemu/libcuemu_kernels.so; never part of libb200z.so.
 #define B2Z_CUEMU 1
 #include "cuemu.h"
-#include "../../7-zip-zstd_b200/csrc/zstd_enc_match.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_find.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_dp.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
@@ -16,34 +17,55 @@
 
 using namespace b2z;
 
-static EncGeom geom(uint32_t frameLog, uint32_t windowLog, uint32_t rowLog, uint32_t flags) {
+static EncGeom geom(uint32_t frameLog, uint32_t windowLog, uint32_t chunkLog, uint32_t flags) {
     EncGeom g; memset(&g, 0, sizeof(g));
-    g.frameLog = frameLog; g.hashLogL = B2Z_DEF_HASHLOG_L; g.hashLogS = B2Z_DEF_HASHLOG_S; g.windowLog = windowLog; g.flags = flags; g.rowLog = rowLog; g.frameSizes = nullptr;
+    g.frameLog = frameLog; g.hashLogL = B2Z_DEF_HASHLOG_L; g.hashLogS = B2Z_DEF_HASHLOG_S; g.windowLog = windowLog; g.flags = flags; g.chunkLog = chunkLog; g.frameSizes = nullptr;
     return g;
 }
 
 extern "C" {
 
-// stage M (zstd_enc_match_kernel): the GPU-verified kernel, here to check the emulator itself against the oracle
-uint64_t emu_zstd_enc_match(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t rowLog, uint32_t flags, uint32_t nWarps,
+// stage F (zstd_enc_find_kernel): candidate words, frames back to back; nCtas CTAs loop over the frames
+static uint64_t run_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t nCtas, uint32_t* cand) {
+    const size_t smem = (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS)) * 4u;
+    uint32_t err = 0;
+    switch (g.chunkLog) {
+    case 5: return cuemu::launch(dim3(nCtas), dim3(7 * 32), smem, [&] { zstd_enc_find_kernel<1, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
+    case 6: return cuemu::launch(dim3(nCtas), dim3(14 * 32), smem, [&] { zstd_enc_find_kernel<2, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
+    case 7: return cuemu::launch(dim3(nCtas), dim3(28 * 32), smem, [&] { zstd_enc_find_kernel<4, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
+    case 8: return cuemu::launch(dim3(nCtas), dim3(32 * 32), smem, [&] { zstd_enc_find_kernel<8, 4>(src, srcSize, g, cand, nullptr, 0, &err); });
+    }
+    return 0;
+}
+uint64_t emu_zstd_enc_find(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t chunkLog, uint32_t flags, uint32_t nCtas, uint32_t* cand) {
+    return run_find(src, srcSize, geom(frameLog, windowLog, chunkLog, flags), nCtas, cand);
+}
+
+// stage F + stage G (zstd_enc_find_kernel, zstd_enc_dp_kernel): per-block sequences and literals as the oracle's b2zo_zstd_find_sequences
+uint64_t emu_zstd_enc_match(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t chunkLog, uint32_t flags, uint32_t nCtas,
                             uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit) {
-    const EncGeom g = geom(frameLog, windowLog, rowLog, flags);
-    std::vector<uint32_t> tables((size_t)nWarps * (16u << rowLog), 0xCDCDCDCDu);
-    return cuemu::launch(dim3(nWarps), dim3(B2Z_MATCH_THREADS), 0, [&] {
-        zstd_enc_match_kernel(src, srcSize, g, tables.data(), seqs, nseq, lits, nlit, nullptr, 0);
+    const EncGeom g = geom(frameLog, windowLog, chunkLog, flags);
+    const uint64_t F = 1ull << frameLog, nFrames = (srcSize + F - 1) >> frameLog;
+    std::vector<uint32_t> cand((size_t)nFrames * F + 16, 0xCDCDCDCDu);
+    std::vector<uint8_t> choice((size_t)nFrames * F + 16, 0xCD);
+    uint64_t c = run_find(src, srcSize, g, nCtas, cand.data());
+    const uint32_t nBlockSlots = (uint32_t)(nFrames << (frameLog - 17u));
+    c += cuemu::launch(dim3((nBlockSlots + B2Z_DP_WARPS - 1) / B2Z_DP_WARPS), dim3(B2Z_DP_WARPS * 32), sizeof(DpWarpSmem) * B2Z_DP_WARPS, [&] {
+        zstd_enc_dp_kernel(src, srcSize, g, cand.data(), choice.data(), seqs, nseq, lits, nlit, nBlockSlots);
     });
+    return c;
 }
 
 // stage C (lzma2_cand_kernel)
 uint64_t emu_lzma2_cand(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, uint32_t nWarps, uint32_t* cand) {
-    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     std::vector<uint32_t> tables((size_t)nWarps * lzma2_cand_table_words(frameLog), 0xCDCDCDCDu);
     return cuemu::launch(dim3(nWarps), dim3(32), 0, [&] { lzma2_cand_kernel(src, srcSize, g, tables.data(), cand); });
 }
 
 // stage P (lzma2_parse_kernel); nseq is zeroed here as launch_lzma2_parse does
 uint64_t emu_lzma2_parse(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint32_t* cand, uint64_t* seqs, uint32_t* nseq) {
-    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     const uint64_t F = 1ull << frameLog;
     const uint32_t nFrames = (uint32_t)((srcSize + F - 1) >> frameLog), bpf = (uint32_t)(F >> 17);
     const uint32_t spf = bpf / B2Z_LZ2_SLICE_BLOCKS(frameLog, flags), nChains = nFrames * spf;
@@ -54,7 +76,7 @@ uint64_t emu_lzma2_parse(const uint8_t* src, uint64_t srcSize, uint32_t frameLog
 // stage Z (zstd_enc_parse_kernel)
 uint64_t emu_zstd_enc_parse(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint32_t* cand,
                             uint64_t* seqs, uint32_t* nseq, uint8_t* lits, uint32_t* nlit) {
-    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     const uint64_t F = 1ull << frameLog;
     const uint32_t nFrames = (uint32_t)((srcSize + F - 1) >> frameLog);
     const uint32_t nBlocks = (nFrames - 1u) * (uint32_t)(F >> 17) + (uint32_t)((srcSize - (uint64_t)(nFrames - 1u) * F + B2Z_BLOCK - 1u) / B2Z_BLOCK);
@@ -65,7 +87,7 @@ uint64_t emu_zstd_enc_parse(const uint8_t* src, uint64_t srcSize, uint32_t frame
 // here it is also fed stage Z's
 uint64_t emu_zstd_enc_entropy(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint64_t* seqs, const uint32_t* nseq,
                               const uint8_t* lits, const uint32_t* nlit, uint8_t* slots, uint32_t* slotSize, uint32_t nBlocks) {
-    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     return cuemu::launch(dim3((nBlocks + B2Z_ENT_WARPS - 1) / B2Z_ENT_WARPS), dim3(B2Z_ENT_WARPS * 32), 0,
                          [&] { zstd_enc_entropy_kernel(src, srcSize, g, seqs, nseq, lits, nlit, slots, slotSize, nBlocks); });
 }
@@ -114,7 +136,7 @@ void emu_filter(uint32_t methodId, int enc, uint8_t* data, uint64_t n, uint32_t 
 // stage R (lzma2_enc_range_kernel, model in shared memory) + assembly: sequences -> the frame-ordered chunk stream with its end marker
 int64_t emu_lzma2_range_and_assemble(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint64_t* seqs, const uint32_t* nseq,
                                      uint8_t* dst, uint64_t dstCap, int glit) {
-    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     const uint32_t nFrames = (uint32_t)((srcSize + (1ull << frameLog) - 1) >> frameLog);
     const uint32_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
     const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
@@ -152,7 +174,7 @@ int64_t emu_lzma2_decode(const uint8_t* src, uint64_t srcSize, uint32_t dictProp
 // frame assembly (zstd_enc_checksum / offsets / gather kernels): stage E's slots -> the frames, as launch_zstd_enc_assemble runs them
 int64_t emu_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, const uint8_t* slots, const uint32_t* slotSize,
                               uint32_t nBlocks, uint8_t* dst, uint64_t dstCap) {
-    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_ROWLOG, flags);
+    const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     const uint32_t nFrames = (uint32_t)((srcSize + (1ull << frameLog) - 1) >> frameLog);
     std::vector<uint64_t> blockOff(nBlocks + 2), frameOff(nFrames + 2); std::vector<uint32_t> cks(nFrames + 2, 0xCDCDCDCDu); uint64_t outSize = 0;
     if (flags & 2u) cuemu::launch(dim3((nFrames + 63) / 64), dim3(64), 0, [&] { zstd_enc_checksum_kernel(src, srcSize, g, cks.data(), nFrames); });

@@ -10,7 +10,7 @@ MAXSEQ = 32768
 
 
 class EncParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "rowLog", "flags")]
+    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "chunkLog", "flags")]
 
 
 _oracle = None
@@ -21,9 +21,8 @@ def oracle():
     global _oracle
     if _oracle is None:
         path = os.path.join(ROOT, "oracle", "liboracle.so")
-        if not os.path.exists(path):
-            import subprocess
-            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])     # no-op when up to date; never a stale checker
         O = ctypes.CDLL(path)
         O.b2zo_zstd_decompress.restype = ctypes.c_int64
         O.b2zo_zstd_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
@@ -90,6 +89,19 @@ def oracle_find_sequences(data, **kw):
     r = oracle().b2zo_zstd_find_sequences(src.ctypes.data, n, ctypes.byref(p), seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
     assert r == nblk
     return seqs, nseq, lits[:n], nlit
+
+
+def oracle_candidates(data, **kw):
+    """stage F tap: one candidate word per input byte, frames back to back (b2zo_zstd_candidates per frame)"""
+    p = enc_params(**kw)
+    O = oracle()
+    O.b2zo_zstd_candidates.restype = None
+    O.b2zo_zstd_candidates.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(EncParams), ctypes.c_void_p]
+    src = _np(data); n = len(data); F = 1 << p.frameLog
+    cand = np.zeros(max(n, 1), dtype=np.uint32)
+    for f0 in range(0, n, F):
+        O.b2zo_zstd_candidates(src.ctypes.data + f0, min(F, n - f0), ctypes.byref(p), cand.ctypes.data + 4 * f0)
+    return cand[:n]
 
 
 def oracle_decompress(comp, n) -> bytes:

@@ -130,7 +130,7 @@ def test_fuzz_emulated_pipelines_and_damaged_streams(pkg, seed, planted):
         nblk = (n + 131071) // 131072; F = 1 << fl; nfr = (n + F - 1) // F; bpf = F >> 17
         flagsz = rng.choice([1, 3])
         seqs = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); nseq = np.zeros(nblk, dtype=np.uint32); nlit = np.zeros(nblk, dtype=np.uint32); lits = np.zeros(n + 64, dtype=np.uint8)
-        E.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 14, flagsz, rng.choice([1, 2]), seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
+        E.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 7, flagsz, rng.choice([1, 2]), seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
         slots = np.zeros(nblk * SLOT, dtype=np.uint8); ssz = np.zeros(nblk, dtype=np.uint32)
         E.emu_zstd_enc_entropy(src.ctypes.data, n, fl, flagsz, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data, slots.ctypes.data, ssz.ctypes.data, nblk)
         want = H.oracle_compress(data, frameLog=fl, windowLog=fl, flags=flagsz)

@@ -3,7 +3,8 @@ warp-synchronous subset they use) against the oracle.  This is a logic check of 
 not a CPU path of the product (libb200z.so is nvcc-only and fails without a device) and no substitute for the `-m gpu` parity
 tests: it cannot see timing, memory-model races between warps or anything about the hardware.
 
-  * zstd_enc_match_kernel (stage M) is GPU-verified against the oracle; here it validates the emulator itself.
+  * zstd_enc_find_kernel / zstd_enc_dp_kernel (stage F / stage G: the level-3-class finder and parse) were developed against it
+    (named barriers and shared-memory atomicMax included).
   * lzma2_cand_kernel / lzma2_parse_kernel (stage C / stage P of the price-based LZMA2 parse) and zstd_enc_parse_kernel
     (stage Z, the price-based Zstandard parse) were developed against it."""
 import ctypes
@@ -24,6 +25,7 @@ def emu():
     E = H.cuemu_library()
     vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
     E.emu_zstd_enc_match.restype = u64; E.emu_zstd_enc_match.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp, vp, vp, vp]
+    E.emu_zstd_enc_find.restype = u64; E.emu_zstd_enc_find.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp]
     E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]
     E.emu_lzma2_parse.restype = u64; E.emu_lzma2_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp]
     E.emu_zstd_enc_parse.restype = u64; E.emu_zstd_enc_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp]
@@ -42,6 +44,36 @@ def _mixed(pkg, n_text):
             + pkg.corpus.entropy_class(1, 20_000).tobytes() + pkg.corpus.entropy_class(2, 30_000).tobytes())
 
 
+@pytest.mark.parametrize("fl,cl,ctas", [(17, 7, 2), (18, 5, 1), (17, 8, 3), (19, 6, 1)])
+def test_emulated_stage_f_equals_the_oracle(pkg, emu, fl, cl, ctas):
+    """candidate words of zstd_enc_find_kernel == b2zo_zstd_candidates for every chunk size the kernel is instantiated for"""
+    data = _mixed(pkg, 150_000) + b"xyzw" * 700 + bytes(3); n = len(data)
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    want = H.oracle_candidates(data, frameLog=fl, windowLog=fl, chunkLog=cl)
+    got = np.full(((n + (1 << fl) - 1) >> fl << fl) + 16, 0xCDCDCDCD, dtype=np.uint32)
+    assert emu.emu_zstd_enc_find(src.ctypes.data, n, fl, fl, cl, 1, ctas, got.ctypes.data) > 0
+    assert np.array_equal(got[:n], want)
+    assert int((want != 0).sum()) > n // 4
+
+
+def test_emulated_stage_f_g_edge_inputs(pkg, emu):
+    """tiny, ragged and degenerate frames through stage F + stage G: fewer bytes than a hash, one repeated byte (the RLE-block
+    sequence), a block that ends one byte into a segment, long matches that stage G extends past B2Z_CAP"""
+    cases = [b"a", b"ab", b"abcdefg", b"abcabcabcabc", bytes(70_000), b"\x07" * 131072 + b"\x07", pkg.corpus.g2(131073).tobytes(), b"\x01" * 33,
+             pkg.corpus.g2(40_000).tobytes() * 3, pkg.corpus.g2(4097).tobytes(), (b"0123456789abcdef" * 300 + b"Z") * 9]
+    for data in cases:
+        n = len(data); fl = 17
+        src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+        nblk = (n + 131071) // 131072
+        seqs, nseq, lits, nlit = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl)
+        s2 = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); ns2 = np.zeros(nblk, dtype=np.uint32); nl2 = np.zeros(nblk, dtype=np.uint32); l2 = np.zeros(nblk * 131072 + 64, dtype=np.uint8)
+        emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 7, 1, 2, s2.ctypes.data, ns2.ctypes.data, l2.ctypes.data, nl2.ctypes.data)
+        assert np.array_equal(nseq, ns2) and np.array_equal(nlit, nl2), n
+        for b in range(nblk):
+            assert np.array_equal(seqs[b * H.MAXSEQ:b * H.MAXSEQ + nseq[b]], s2[b * H.MAXSEQ:b * H.MAXSEQ + nseq[b]]), (n, b)
+            assert np.array_equal(lits[b * 131072:b * 131072 + nlit[b]], l2[b * 131072:b * 131072 + nlit[b]]), (n, b)
+
+
 def test_emulated_stage_m_equals_the_oracle(pkg, emu):
     data = _mixed(pkg, 200_000); n = len(data)
     src = np.frombuffer(data + bytes(64), dtype=np.uint8)
@@ -49,7 +81,7 @@ def test_emulated_stage_m_equals_the_oracle(pkg, emu):
     for fl, warps in ((17, 2), (18, 1)):
         seqs, nseq, lits, nlit = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl)
         s2 = np.zeros(nblk * H.MAXSEQ, dtype=np.uint64); ns2 = np.zeros(nblk, dtype=np.uint32); nl2 = np.zeros(nblk, dtype=np.uint32); l2 = np.zeros(n + 64, dtype=np.uint8)
-        assert emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 14, 1 | (2 << 8), warps, s2.ctypes.data, ns2.ctypes.data, l2.ctypes.data, nl2.ctypes.data) > 0
+        assert emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 7, 1 | (2 << 8), warps, s2.ctypes.data, ns2.ctypes.data, l2.ctypes.data, nl2.ctypes.data) > 0
         assert np.array_equal(nseq, ns2) and np.array_equal(nlit, nl2)
         for b in range(nblk):
             assert np.array_equal(seqs[b * H.MAXSEQ:b * H.MAXSEQ + nseq[b]], s2[b * H.MAXSEQ:b * H.MAXSEQ + nseq[b]]), b
@@ -215,7 +247,7 @@ def test_emulated_zstd_encoder_end_to_end(pkg, emu, fl, flags):
         emu.emu_lzma2_cand(src.ctypes.data, n, fl, flags, 2, cand.ctypes.data)
         emu.emu_zstd_enc_parse(src.ctypes.data, n, fl, flags, cand.ctypes.data, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
     else:
-        emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 14, flags, 2, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
+        emu.emu_zstd_enc_match(src.ctypes.data, n, fl, fl, 7, flags, 2, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data)
     SLOT = emu.emu_slot_bytes()
     slots = np.zeros(nblk * SLOT, dtype=np.uint8); ssz = np.zeros(nblk, dtype=np.uint32)
     emu.emu_zstd_enc_entropy(src.ctypes.data, n, fl, flags, seqs.ctypes.data, nseq.ctypes.data, lits.ctypes.data, nlit.ctypes.data, slots.ctypes.data, ssz.ctypes.data, nblk)

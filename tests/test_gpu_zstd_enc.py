@@ -17,8 +17,21 @@ def inputs(pkg):
     return helpers.sample_inputs(pkg, big=True)
 
 
+def test_stage_f_matches_oracle(pkg, codec, inputs):
+    """stage F tap (one candidate word per position) == oracle b2zo_zstd_candidates, default and non-default chunk sizes / table logs."""
+    for name in ("g2_1m", "tile", "zeros", "mixed", "g2_128k+1", "skew", "g2_9m", "seven", "eight"):
+        data = inputs[name]
+        assert np.array_equal(codec.stage_f(data), helpers.oracle_candidates(data)), name
+    data = inputs["mixed"] + inputs["g2_1m"]
+    for cl, hl, hs, fl in ((5, 15, 14, 18), (6, 12, 13, 20), (8, 14, 15, 19), (7, 15, 14, 17)):
+        c = pkg.Codec(0, frame_log=fl, chunk_log=cl, hash_log_l=10, hash_log_s=hs)
+        c.set("hash_log_l", hl)
+        assert np.array_equal(c.stage_f(data), helpers.oracle_candidates(data, frameLog=fl, windowLog=fl, chunkLog=cl, hashLogL=hl, hashLogS=hs)), (cl, hl, hs, fl)
+        c.close()
+
+
 def test_stage_m_matches_oracle(pkg, codec, inputs):
-    """stage M taps (final sequences + literals per block) == oracle find_sequences."""
+    """stage F + stage G taps (final sequences + literals per block) == oracle find_sequences."""
     for name in ("g2_1m", "tile", "zeros", "mixed", "g2_128k+1", "skew", "g2_9m"):
         data = inputs[name]
         seqs, nseq, lits, nlit = codec.stage_m(data)
@@ -50,9 +63,9 @@ def test_frames_equal_oracle_and_roundtrip(pkg, codec, inputs):
 def test_params_and_hints(pkg, inputs):
     """non-default geometry and the skippable size hints stay byte-identical to the oracle and decodable."""
     data = inputs["g2_9m"][: 3 * (1 << 20) + 77]
-    c = pkg.Codec(0, frame_log=19, row_log=12, flags=1)
+    c = pkg.Codec(0, frame_log=19, chunk_log=6, hash_log_s=13, flags=1)
     comp = c.compress(data)
-    assert comp == helpers.oracle_compress(data, frameLog=19, windowLog=19, rowLog=12, flags=1)
+    assert comp == helpers.oracle_compress(data, frameLog=19, windowLog=19, chunkLog=6, hashLogS=13, flags=1)
     assert comp[:4] == b"\x50\x2a\x4d\x18"
     if helpers.ref_available():
         assert helpers.ref_decompress(comp, len(data)) == data

@@ -7,7 +7,7 @@ import torch
 import __graft_entry__ as ge
 pkg = ge.load_package()
 n = int(sys.argv[1]) << 20
-fl = int(sys.argv[2]) if len(sys.argv) > 2 else 22
+fl = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 src = torch.from_numpy(pkg.corpus.g2(n)).cuda()
 c = pkg.Codec(0, frame_log=fl)
@@ -15,4 +15,4 @@ dst = torch.empty(c.compress_bound(n), dtype=torch.uint8, device="cuda")
 for _ in range(reps):
     c.reset_stats()
     m = c.compress_device(src.data_ptr(), n, dst.data_ptr(), dst.numel())
-    print(f"match {c.stat(1):.2f} ms entropy {c.stat(2):.2f} ms assemble {c.stat(3):.2f} ms ratio {n/m:.4f}")
+    print(f"find {c.stat(1):.2f} ms parse {c.stat(10):.2f} ms entropy {c.stat(2):.2f} ms assemble {c.stat(3):.2f} ms ratio {n/m:.4f}")
