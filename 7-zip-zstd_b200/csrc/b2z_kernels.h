@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include "b2z_params.h"
 
-#define B2Z_DP_WARPS        8       // stage G: warps (= blocks of input) per CTA
+#define B2Z_DP_WARPS        4       // stage G: warps (= blocks of input) per CTA
 #define B2Z_ENT_WARPS       4       // stage E: warps (= blocks of input) per CTA
 #define B2Z_SLOT            (B2Z_BODY_CAP + 64u) // per-block output slot: 3-byte header + body (<= B2Z_BODY_CAP), 16-B multiple
 

@@ -25,9 +25,15 @@
 
 namespace b2z {
 
+// Memory access: a lane's segment lies 4 KiB (16 KiB of candidate words) away from its neighbour's, so lanes never read HBM
+// themselves.  The warp moves TILES of 32 positions per lane through shared memory instead: row j of a tile = the 32
+// positions lane j works on next, loaded / stored by the whole warp as 128-byte (candidates) or 32-byte (input bytes,
+// choices) coalesced pieces, read by lane j along its padded row (stride 33 / 9 words: conflict-free).
 struct DpWarpSmem {
     uint32_t ring[64][32];       // cost ring: [position & 63][lane]
-    uint32_t hist[256];
+    uint32_t candTile[32][33];   // [lane][position in tile]; the byte histogram (256 words) lives here before the first tile
+    uint32_t srcTile[32][9];     // [lane][4 input bytes]
+    uint32_t chcTile[32][9];     // [lane][4 choices]
     uint8_t litc[256];
 };
 
@@ -43,41 +49,72 @@ __device__ __forceinline__ uint32_t dp_log16(uint32_t x) {
     return 16u * hb + ((k == 0u && (x & (x - 1u)) == 0u) ? 0u : fr);
 }
 
-// forward walk over one segment's choices.  EMIT = false: count only.
+// tile t of a 32-bit-per-position array: 32 coalesced 128-byte rows.  base = the block's array, bn = positions in the block
+__device__ __forceinline__ void dp_load_cand_tile(DpWarpSmem& sm, const uint32_t* __restrict__ base, uint32_t bn, uint32_t t, uint32_t lane) {
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32u; j++) {
+        const uint32_t pos = j * B2Z_SEG + 32u * t + lane;
+        sm.candTile[j][lane] = pos < bn ? __ldcs(base + pos) : 0u;
+    }
+}
+// tile t of a byte-per-position array: 8 loads of 4 rows x 32 bytes
+__device__ __forceinline__ void dp_load_byte_tile(uint32_t (*tile)[9], const uint8_t* __restrict__ base, uint32_t bn, uint32_t t, uint32_t lane) {
+#pragma unroll
+    for (uint32_t r = 0; r < 8u; r++) {
+        const uint32_t row = 4u * r + (lane >> 3), wd = lane & 7u, pos = row * B2Z_SEG + 32u * t + 4u * wd;
+        tile[row][wd] = pos < bn ? __ldg(reinterpret_cast<const uint32_t*>(base + pos)) : 0u;
+    }
+}
+__device__ __forceinline__ void dp_store_byte_tile(const uint32_t (*tile)[9], uint8_t* __restrict__ base, uint32_t bn, uint32_t t, uint32_t lane) {
+#pragma unroll
+    for (uint32_t r = 0; r < 8u; r++) {
+        const uint32_t row = 4u * r + (lane >> 3), wd = lane & 7u, pos = row * B2Z_SEG + 32u * t + 4u * wd;
+        if (pos < bn) *reinterpret_cast<uint32_t*>(base + pos) = tile[row][wd];
+    }
+}
+
+// per-lane state of the forward walk over a segment's choices
+struct DpWalk {
+    uint32_t i, ns, nl, lastEnd;            // segment-relative position; sequences / literals so far; block-relative end of the last match
+    uint32_t rep0, rep1, rep2, prevEnd;     // EMIT only
+};
+
+// one tile of the forward walk: positions [32 t, 32 t + 32) of the lane's segment, as far as the lane's path touches them
 template <bool EMIT>
-__device__ __forceinline__ void dp_walk(const uint8_t* __restrict__ fb /* frame base */, uint32_t segAbs /* frame-relative segment start */,
-                                        uint32_t blkAbs, uint32_t sn, const uint8_t* __restrict__ chc, const uint32_t* __restrict__ cnd,
-                                        uint32_t prevEnd /* block-relative end of the last sequence before this lane */,
-                                        uint64_t* __restrict__ outSeq, uint8_t* __restrict__ outLit,
-                                        uint32_t& cntSeq, uint32_t& cntLit, uint32_t& lastEndAbs) {
-    uint32_t rep0 = 0, rep1 = 0, rep2 = 0, ns = 0, nl = 0;
-    const uint32_t s0 = segAbs - blkAbs;                                       // block-relative
-    for (uint32_t i = 0; i < sn;) {
-        uint32_t l = chc[i];
-        if (!l) { if (EMIT) outLit[nl] = fb[segAbs + i]; nl++; i++; continue; }
-        const uint32_t off = B2Z_CAND_OFF(cnd[i]);
-        if (l == B2Z_CAP) { const uint8_t* a = fb + segAbs + i; const uint8_t* q = a - off; while (i + l < sn && a[l] == q[l]) l++; }
+__device__ __forceinline__ void dp_walk_tile(DpWarpSmem& sm, DpWalk& k, uint32_t t, uint32_t lane, uint32_t sn, uint32_t s0 /* block-relative */,
+                                             const uint64_t* __restrict__ fw /* frame as words */, uint32_t segAbs /* frame-relative */, uint32_t nWords,
+                                             const uint32_t* __restrict__ cnd /* segment's candidate words */,
+                                             uint64_t* __restrict__ outSeq, uint8_t* __restrict__ outLit) {
+    const uint32_t tEnd = (32u * t + 32u) < sn ? (32u * t + 32u) : sn;
+    while (k.i < tEnd) {
+        const uint32_t w = k.i & 31u;
+        uint32_t l = (sm.chcTile[lane][w >> 2] >> (8u * (w & 3u))) & 255u;
+        if (!l) {
+            if (EMIT) outLit[k.nl] = (uint8_t)(sm.srcTile[lane][w >> 2] >> (8u * (w & 3u)));
+            k.nl++; k.i++; continue;
+        }
+        const uint32_t off = B2Z_CAND_OFF(__ldg(cnd + k.i));
+        if (l == B2Z_CAP) l = match_len(fw, segAbs + k.i - off, segAbs + k.i, sn - k.i, nWords);   // the full common prefix, to the segment end at most
         if (EMIT) {
-            const uint32_t pos = s0 + i, ll = pos - prevEnd;
+            const uint32_t pos = s0 + k.i, ll = pos - k.prevEnd;
             uint32_t code = 0, offBase;
-            if (ll) { if (off == rep0) code = 1; else if (off == rep1) code = 2; else if (off == rep2) code = 3; }
-            else { if (off == rep1) code = 1; else if (off == rep2) code = 2; else if (rep0 > 1u && off == rep0 - 1u) code = 3; }
-            if (code == 0) { offBase = off + 3u; rep2 = rep1; rep1 = rep0; rep0 = off; }
+            if (ll) { if (off == k.rep0) code = 1; else if (off == k.rep1) code = 2; else if (off == k.rep2) code = 3; }
+            else { if (off == k.rep1) code = 1; else if (off == k.rep2) code = 2; else if (k.rep0 > 1u && off == k.rep0 - 1u) code = 3; }
+            if (code == 0) { offBase = off + 3u; k.rep2 = k.rep1; k.rep1 = k.rep0; k.rep0 = off; }
             else {
                 offBase = code;
                 const uint32_t idx = code - 1u + (ll == 0u);
                 if (idx != 0) {
-                    const uint32_t cur = idx == 3 ? rep0 - 1u : (idx == 1 ? rep1 : rep2);
-                    if (idx != 1) rep2 = rep1;
-                    rep1 = rep0; rep0 = cur;
+                    const uint32_t cur = idx == 3 ? k.rep0 - 1u : (idx == 1 ? k.rep1 : k.rep2);
+                    if (idx != 1) k.rep2 = k.rep1;
+                    k.rep1 = k.rep0; k.rep0 = cur;
                 }
             }
-            outSeq[ns] = B2Z_PACK_SEQ(offBase, ll, l);
-            prevEnd = pos + l;
+            outSeq[k.ns] = B2Z_PACK_SEQ(offBase, ll, l);
+            k.prevEnd = pos + l;
         }
-        ns++; i += l; lastEndAbs = s0 + i;
+        k.ns++; k.i += l; k.lastEnd = s0 + k.i;
     }
-    cntSeq = ns; cntLit = nl;
 }
 
 __global__ void __launch_bounds__(B2Z_DP_WARPS * 32)
@@ -103,9 +140,11 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
     uint8_t* __restrict__ chcB = choice + f0 + b0;
     uint64_t* __restrict__ out = seqs + (size_t)bw * B2Z_MAXSEQ;
     uint8_t* __restrict__ lit = lits + f0 + b0;
+    const uint32_t nTiles = ((bn < B2Z_SEG ? bn : B2Z_SEG) + 31u) >> 5;        // tiles of the longest segment (the first)
 
     // ---- 1. literal prices
-    for (uint32_t i = lane; i < 256u; i += 32u) sm.hist[i] = 0;
+    uint32_t* const hist = &sm.candTile[0][0];
+    for (uint32_t i = lane; i < 256u; i += 32u) hist[i] = 0;
     __syncwarp();
     for (uint32_t idx = lane;; idx += 32u) {
         const uint32_t o = (idx >> 2) * 256u + (idx & 3u) * 16u;              // 4 lanes per sampled 64-byte run
@@ -114,20 +153,20 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(bs + o));
             const uint32_t ws[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
-            for (int k = 0; k < 4; k++) { atomicAdd(&sm.hist[ws[k] & 255u], 1u); atomicAdd(&sm.hist[(ws[k] >> 8) & 255u], 1u); atomicAdd(&sm.hist[(ws[k] >> 16) & 255u], 1u); atomicAdd(&sm.hist[ws[k] >> 24], 1u); }
-        } else for (uint32_t k = o; k < bn && k < o + 16u; k++) atomicAdd(&sm.hist[bs[k]], 1u);
+            for (int k = 0; k < 4; k++) { atomicAdd(&hist[ws[k] & 255u], 1u); atomicAdd(&hist[(ws[k] >> 8) & 255u], 1u); atomicAdd(&hist[(ws[k] >> 16) & 255u], 1u); atomicAdd(&hist[ws[k] >> 24], 1u); }
+        } else for (uint32_t k = o; k < bn && k < o + 16u; k++) atomicAdd(&hist[bs[k]], 1u);
     }
     __syncwarp();
     {
         uint32_t part = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) part += sm.hist[lane * 8u + k];
+        for (int k = 0; k < 8; k++) part += hist[lane * 8u + k];
 #pragma unroll
         for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(B2Z_FULL, part, d);
         const uint32_t lt = dp_log16(part);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const uint32_t h = sm.hist[lane * 8u + k];
+            const uint32_t h = hist[lane * 8u + k];
             uint32_t v = B2Z_DP_LIT_MAX;
             if (h) { const uint32_t lh = dp_log16(h); v = lt > lh ? lt - lh : 1u; }
             sm.litc[lane * 8u + k] = (uint8_t)(v < B2Z_DP_LIT_MIN ? B2Z_DP_LIT_MIN : (v > B2Z_DP_LIT_MAX ? B2Z_DP_LIT_MAX : v));
@@ -135,44 +174,49 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
     }
     __syncwarp();
 
-    // ---- 2. backward dynamic programme over this lane's segment
+    // ---- 2. backward dynamic programme, tile by tile from the segment's end
     const uint32_t s0 = lane * B2Z_SEG;
     const bool active = s0 < bn;
     const uint32_t sn = active ? ((bn - s0) < B2Z_SEG ? (bn - s0) : B2Z_SEG) : 0u;
-    const uint32_t* __restrict__ cnd = cndB + s0;
-    uint8_t* __restrict__ chc = chcB + s0;
     uint32_t diff = 0;                                                         // any byte of the segment unlike the block's first byte
-    if (active) {
-        const uint32_t first4 = (uint32_t)bs[0] * 0x01010101u;
-        sm.ring[sn & 63u][lane] = 0;
-        for (uint32_t wi = (sn + 3u) >> 2; wi-- > 0;) {
-            const uint4 c4 = __ldcs(reinterpret_cast<const uint4*>(cnd + 4u * wi));
-            const uint32_t b4 = __ldg(reinterpret_cast<const uint32_t*>(bs + s0 + 4u * wi));
-            const uint32_t cw[4] = { c4.x, c4.y, c4.z, c4.w };
-            uint32_t packed = 0;
+    const uint32_t first = bs[0];
+    if (active) sm.ring[sn & 63u][lane] = 0;
+    for (uint32_t t = nTiles; t-- > 0;) {
+        dp_load_cand_tile(sm, cndB, bn, t, lane);
+        dp_load_byte_tile(sm.srcTile, bs, bn, t, lane);
+        __syncwarp();
+        if (32u * t < sn) {
+#pragma unroll 1
+            for (int wi = 7; wi >= 0; wi--) {
+                const uint32_t b4 = sm.srcTile[lane][wi];
+                uint32_t packed = 0;
 #pragma unroll
-            for (int j = 3; j >= 0; j--) {
-                const uint32_t i = 4u * wi + (uint32_t)j;
-                if (i >= sn) continue;
-                const uint32_t byte = (b4 >> (8 * j)) & 255u;
-                diff |= byte ^ (first4 & 255u);
-                uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & 63u][lane], ch = 0;
-                const uint32_t c = cw[j];
-                if (c) {
-                    const uint32_t len = B2Z_CAND_LEN(c), ob = 16u * highbit32(B2Z_CAND_OFF(c) + 3u) + B2Z_DP_MATCH;
+                for (int j = 3; j >= 0; j--) {
+                    const uint32_t i = 32u * t + 4u * (uint32_t)wi + (uint32_t)j;
+                    if (i >= sn) continue;
+                    const uint32_t byte = (b4 >> (8 * j)) & 255u;
+                    diff |= byte ^ first;
+                    uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & 63u][lane], ch = 0;
+                    const uint32_t c = sm.candTile[lane][4 * wi + j];
+                    if (c) {
+                        const uint32_t len = B2Z_CAND_LEN(c), ob = 16u * highbit32(B2Z_CAND_OFF(c) + 3u) + B2Z_DP_MATCH;
 #pragma unroll
-                    for (uint32_t k = 0; k <= B2Z_DP_NTRUNC; k++) {
-                        if (len >= B2Z_DP_MINLEN + k) {
-                            const uint32_t l = len - k, pr = ob + dp_ml_price(l) + sm.ring[(i + l) & 63u][lane];
-                            if (pr < best) { best = pr; ch = l; }
+                        for (uint32_t k = 0; k <= B2Z_DP_NTRUNC; k++) {
+                            if (len >= B2Z_DP_MINLEN + k) {
+                                const uint32_t l = len - k, pr = ob + dp_ml_price(l) + sm.ring[(i + l) & 63u][lane];
+                                if (pr < best) { best = pr; ch = l; }
+                            }
                         }
                     }
+                    sm.ring[i & 63u][lane] = best;
+                    packed |= ch << (8 * j);
                 }
-                sm.ring[i & 63u][lane] = best;
-                packed |= ch << (8 * j);
+                sm.chcTile[lane][wi] = packed;
             }
-            *reinterpret_cast<uint32_t*>(chc + 4u * wi) = packed;
         }
+        __syncwarp();
+        dp_store_byte_tile(sm.chcTile, chcB, bn, t, lane);
+        __syncwarp();
     }
     // ---- one repeated byte: the canonical single sequence (stage E emits an RLE block for it)
     if (!__any_sync(B2Z_FULL, diff != 0u) && bn > 1u) {
@@ -180,11 +224,20 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
         return;
     }
 
+    const uint64_t* __restrict__ fw = reinterpret_cast<const uint64_t*>(fb);
+    const uint32_t nWords = (n + 7u) >> 3;
+    const uint32_t* __restrict__ cnd = cndB + s0;
     // ---- 3. count
-    uint32_t cntSeq = 0, cntLit = 0, lastEnd = 0;
-    if (active) dp_walk<false>(fb, b0 + s0, b0, sn, chc, cnd, 0u, nullptr, nullptr, cntSeq, cntLit, lastEnd);
+    DpWalk k; k.i = 0; k.ns = 0; k.nl = 0; k.lastEnd = 0; k.rep0 = k.rep1 = k.rep2 = 0; k.prevEnd = 0;
+    for (uint32_t t = 0; t < nTiles; t++) {
+        dp_load_byte_tile(sm.chcTile, chcB, bn, t, lane);
+        __syncwarp();
+        dp_walk_tile<false>(sm, k, t, lane, sn, s0, fw, b0 + s0, nWords, cnd, nullptr, nullptr);
+        __syncwarp();
+    }
+    const uint32_t cntSeq = k.ns, cntLit = k.nl;
     // ---- 4. places: exclusive sums of the counts, exclusive maximum of the last match ends
-    uint32_t seqBase = cntSeq, litBase = cntLit, prevEnd = cntSeq ? lastEnd : 0u;
+    uint32_t seqBase = cntSeq, litBase = cntLit, prevEnd = cntSeq ? k.lastEnd : 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t a = __shfl_up_sync(B2Z_FULL, seqBase, d), c = __shfl_up_sync(B2Z_FULL, litBase, d), e = __shfl_up_sync(B2Z_FULL, prevEnd, d);
@@ -194,7 +247,14 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
     seqBase -= cntSeq; litBase -= cntLit;
     prevEnd = __shfl_up_sync(B2Z_FULL, prevEnd, 1); if (lane == 0) prevEnd = 0;
     // ---- 5. emit
-    if (active) { uint32_t a, c, e = 0; dp_walk<true>(fb, b0 + s0, b0, sn, chc, cnd, prevEnd, out + seqBase, lit + litBase, a, c, e); }
+    k.i = 0; k.ns = 0; k.nl = 0; k.prevEnd = prevEnd;
+    for (uint32_t t = 0; t < nTiles; t++) {
+        dp_load_byte_tile(sm.chcTile, chcB, bn, t, lane);
+        dp_load_byte_tile(sm.srcTile, bs, bn, t, lane);
+        __syncwarp();
+        dp_walk_tile<true>(sm, k, t, lane, sn, s0, fw, b0 + s0, nWords, cnd, out + seqBase, lit + litBase);
+        __syncwarp();
+    }
     if (lane == 0) { nseq[bw] = totSeq; nlit[bw] = totLit; }
 }
 

@@ -27,6 +27,18 @@ namespace b2z {
 #define B2Z_FIND_BAR_TURN(g) (1u + (g))        // named barrier ids: turn hand-over into group g ...
 #define B2Z_FIND_BAR_GRP(g)  (8u + (g))        // ... and the read -> write barrier inside group g
 
+// Keeps everything a turn consumes computed BEFORE its barrier.  ptxas is free to sink arithmetic (and the wait for the bytes'
+// global load) below bar.sync, i.e. into the frame's serial chain; a shared-memory store of a word that depends on all of the
+// turn's inputs cannot cross the barrier, so the inputs are in registers when the turn begins.
+__device__ __forceinline__ void turn_inputs_ready(uint32_t* slot, uint32_t iL, uint32_t iS, uint32_t mineL, uint32_t mineS, uint32_t flags) {
+#ifndef B2Z_CUEMU
+    const uint32_t mix = iL ^ (iS << 8) ^ mineL ^ (mineS >> 3) ^ flags;
+    asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(slot)), "r"(mix) : "memory");
+#else
+    (void)slot; (void)iL; (void)iS; (void)mineL; (void)mineS; (void)flags;
+#endif
+}
+
 template <int WPG, int G>
 __global__ void __launch_bounds__(WPG * G * 32, 1)
 zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cand,
@@ -68,10 +80,11 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
         __syncthreads();
 
         const uint32_t nChunks = (n + CH - 1u) / CH, nIter = (nChunks + G - 1u) / G;
+        uint64_t vNext = ld64u(w, grp * CH + tg, nWords);
         for (uint32_t it = 0; it < nIter; it++) {
             const uint32_t p = (it * G + grp) * CH + tg;
-            // ---- before the turn: bytes, hashes, same-step groups
-            const uint64_t v = ld64u(w, p, nWords);
+            // ---- before the turn: bytes (loaded one iteration ahead), hashes, same-step groups
+            const uint64_t v = vNext;
             const bool hashable = p + 8u <= n;                                 // p >= n for the padding chunks of the last iteration
             const uint64_t hl = v * B2Z_PRIME8, hs = (v << 24) * B2Z_PRIME5;
             const uint32_t iL = (uint32_t)(hl >> (64u - HL)), iS = (uint32_t)(hs >> (64u - HS));
@@ -80,16 +93,19 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
             const uint32_t gL = __match_any_sync(B2Z_FULL, hashable ? iL : (0x80000000u | lane));
             const uint32_t gS = __match_any_sync(B2Z_FULL, hashable ? iS : (0x80000000u | lane));
             const uint32_t lowL = gL & lanemask_lt(), lowS = gS & lanemask_lt();
-            // ---- the turn
+            const bool lastL = hashable && (gL >> lane) == 1u, lastS = hashable && (gS >> lane) == 1u;   // the highest lane of a same-index group carries the step's newest position
+            uint32_t* const aL = TL + iL; uint32_t* const aS = TS + iS;
+            turn_inputs_ready(smem + tableWords + tid, iL, iS, mineL, mineS, (uint32_t)lastL | ((uint32_t)lastS << 1) | ((uint32_t)hashable << 2));
+            // ---- the turn: nothing but the table accesses between the two barrier hops
             bar_sync(B2Z_FIND_BAR_TURN(grp), 2u * CH);
             uint32_t eL = 0, eS = 0;
-            if (hashable) { eL = TL[iL]; eS = TS[iS]; }
+            if (hashable) { eL = *aL; eS = *aS; }
             if (WPG > 1) bar_sync(B2Z_FIND_BAR_GRP(grp), CH); else __syncwarp();
-            if (hashable) {
-                if ((gL >> lane) == 1u) atomicMax(&TL[iL], mineL);             // the highest lane of a same-index group carries the step's newest position
-                if ((gS >> lane) == 1u) atomicMax(&TS[iS], mineS);
-            }
+            if (lastL) atomicMax(aL, mineL);
+            if (lastS) atomicMax(aS, mineS);
             bar_arrive(B2Z_FIND_BAR_TURN(nextGrp), 2u * CH);
+            // ---- after the turn: the next iteration's bytes are requested before this one's candidates are compared
+            vNext = ld64u(w, p + G * CH, nWords);
             // ---- after the turn: a lower lane of the step with my index is nearer than anything in the table
             {
                 const uint32_t fromL = __shfl_sync(B2Z_FULL, mineL, lowL ? 31 - __clz((int)lowL) : 0);
@@ -116,7 +132,7 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
 }
 
 #ifndef B2Z_CUEMU
-size_t zstd_enc_find_smem_bytes(const EncGeom& g) { return (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS)) * 4u; }
+size_t zstd_enc_find_smem_bytes(const EncGeom& g) { return (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS) + 1024u) * 4u; }   // tables + one scratch word per thread
 
 template <int WPG, int G>
 static cudaError_t launch_find_t(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,

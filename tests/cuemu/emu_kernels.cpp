@@ -27,7 +27,7 @@ extern "C" {
 
 // stage F (zstd_enc_find_kernel): candidate words, frames back to back; nCtas CTAs loop over the frames
 static uint64_t run_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t nCtas, uint32_t* cand) {
-    const size_t smem = (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS)) * 4u;
+    const size_t smem = (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS) + 1024u) * 4u;
     uint32_t err = 0;
     switch (g.chunkLog) {
     case 5: return cuemu::launch(dim3(nCtas), dim3(7 * 32), smem, [&] { zstd_enc_find_kernel<1, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
