@@ -37,7 +37,9 @@ struct DpWarpSmem {
     uint8_t litc[256];
 };
 
-__device__ __forceinline__ uint32_t dp_ml_price(uint32_t l) { return l >= 35u ? 16u * (highbit32(l - 3u) - 3u) : (l >= 19u ? 16u : 0u); }
+// extra-bit price of a match length (oracle: dp_ml_price).  The programme only sees lengths <= B2Z_CAP = 64, where the oracle's
+// 16 * (highbit(l - 3) - 3) for l >= 35 is the constant 32: one step at 19, one at 35.
+__device__ __forceinline__ uint32_t dp_ml_price(uint32_t l) { return ((uint32_t)(l >= 19u) + (uint32_t)(l >= 35u)) << 4; }
 
 // 16 * log2(x) as b2z_zstd_cost.h:zop_log16, with the fraction table in registers
 __device__ __forceinline__ uint32_t dp_log16(uint32_t x) {
@@ -93,8 +95,11 @@ __device__ __forceinline__ void dp_walk_tile(DpWarpSmem& sm, DpWalk& k, uint32_t
             if (EMIT) outLit[k.nl] = (uint8_t)(sm.srcTile[lane][w >> 2] >> (8u * (w & 3u)));
             k.nl++; k.i++; continue;
         }
-        const uint32_t off = B2Z_CAND_OFF(__ldg(cnd + k.i));
-        if (l == B2Z_CAP) l = match_len(fw, segAbs + k.i - off, segAbs + k.i, sn - k.i, nWords);   // the full common prefix, to the segment end at most
+        const uint32_t off = EMIT ? B2Z_CAND_OFF(sm.candTile[lane][w]) : 0u;
+        if (l == B2Z_CAP) {                                                    // the full common prefix, to the segment end at most
+            const uint32_t o = EMIT ? off : B2Z_CAND_OFF(__ldg(cnd + k.i));
+            l = match_len(fw, segAbs + k.i - o, segAbs + k.i, sn - k.i, nWords);
+        }
         if (EMIT) {
             const uint32_t pos = s0 + k.i, ll = pos - k.prevEnd;
             uint32_t code = 0, offBase;
@@ -186,27 +191,27 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
         dp_load_byte_tile(sm.srcTile, bs, bn, t, lane);
         __syncwarp();
         if (32u * t < sn) {
-#pragma unroll 1
+            const bool full = 32u * t + 32u <= sn;                             // only the last tile of a short segment is not
+#pragma unroll 2
             for (int wi = 7; wi >= 0; wi--) {
                 const uint32_t b4 = sm.srcTile[lane][wi];
                 uint32_t packed = 0;
 #pragma unroll
                 for (int j = 3; j >= 0; j--) {
                     const uint32_t i = 32u * t + 4u * (uint32_t)wi + (uint32_t)j;
-                    if (i >= sn) continue;
+                    if (!full && i >= sn) continue;
+                    // branch-free: an absent or too short candidate prices at 2^31 and loses against the literal
                     const uint32_t byte = (b4 >> (8 * j)) & 255u;
                     diff |= byte ^ first;
-                    uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & 63u][lane], ch = 0;
                     const uint32_t c = sm.candTile[lane][4 * wi + j];
-                    if (c) {
-                        const uint32_t len = B2Z_CAND_LEN(c), ob = 16u * highbit32(B2Z_CAND_OFF(c) + 3u) + B2Z_DP_MATCH;
+                    const uint32_t len = B2Z_CAND_LEN(c), ob = 16u * highbit32(B2Z_CAND_OFF(c) + 3u) + B2Z_DP_MATCH;
+                    uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & 63u][lane], ch = 0;
 #pragma unroll
-                        for (uint32_t k = 0; k <= B2Z_DP_NTRUNC; k++) {
-                            if (len >= B2Z_DP_MINLEN + k) {
-                                const uint32_t l = len - k, pr = ob + dp_ml_price(l) + sm.ring[(i + l) & 63u][lane];
-                                if (pr < best) { best = pr; ch = l; }
-                            }
-                        }
+                    for (uint32_t k = 0; k <= B2Z_DP_NTRUNC; k++) {
+                        const uint32_t l = len - k;                            // wraps below zero when len < k: the index stays inside the ring, the price is discarded
+                        const uint32_t pr = ob + dp_ml_price(l) + sm.ring[(i + l) & 63u][lane];
+                        const bool take = (len >= B2Z_DP_MINLEN + k) && pr < best;
+                        best = take ? pr : best; ch = take ? l : ch;
                     }
                     sm.ring[i & 63u][lane] = best;
                     packed |= ch << (8 * j);
@@ -251,6 +256,7 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
     for (uint32_t t = 0; t < nTiles; t++) {
         dp_load_byte_tile(sm.chcTile, chcB, bn, t, lane);
         dp_load_byte_tile(sm.srcTile, bs, bn, t, lane);
+        dp_load_cand_tile(sm, cndB, bn, t, lane);
         __syncwarp();
         dp_walk_tile<true>(sm, k, t, lane, sn, s0, fw, b0 + s0, nWords, cnd, out + seqBase, lit + litBase);
         __syncwarp();

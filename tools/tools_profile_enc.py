@@ -10,7 +10,8 @@ n = int(sys.argv[1]) << 20
 fl = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 src = torch.from_numpy(pkg.corpus.g2(n)).cuda()
-c = pkg.Codec(0, frame_log=fl)
+cl = int(sys.argv[4]) if len(sys.argv) > 4 else 7
+c = pkg.Codec(0, frame_log=fl, chunk_log=cl)
 dst = torch.empty(c.compress_bound(n), dtype=torch.uint8, device="cuda")
 for _ in range(reps):
     c.reset_stats()
