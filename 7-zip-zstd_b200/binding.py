@@ -33,7 +33,7 @@ class B200zError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libb200z.so")
+    return os.environ.get("B200Z_LIB") or os.path.join(_HERE, "libb200z.so")      # B200Z_LIB: an experimental build (tools/)
 
 
 _lib = None

@@ -31,7 +31,7 @@
 /* bytes of a block that feed the literal histogram: the first 64 of every 256 */
 #define B2Z_DP_SAMPLED(i)  ((((i) >> 6) & 3u) == 0u)
 #define B2Z_MAX_FRAMELOG   24
-#define B2Z_CAP            64u     /* stage F compares at most this many bytes; stage G extends a chosen match of this length */
+#define B2Z_CAP            16u     /* stage F compares at most this many bytes (two 8-byte words, no loop); stage G extends a chosen match of this length */
 #define B2Z_MAXSEQ         32768u  /* raw sequences per 128 KiB block (min match 4)          */
 #define B2Z_BLOCK          131072u
 #define B2Z_FRAME_HDR_MAX  10

@@ -5,8 +5,8 @@
 //   1. literal prices: byte histogram of the first 64 of every 256 bytes (coalesced 16-byte loads, shared-memory atomics),
 //      price = log2(total / count) in 1/16 bit, clamped;
 //   2. per lane, a backward dynamic programme over its segment: cost[i] = min(literal + cost[i+1], the position's
-//      candidate (stage F) at its length L, L-1, L-2: B2Z_DP_MATCH + offset and length extra bits + cost[i+l]).  Only the
-//      next 64 costs are live (candidates are at most B2Z_CAP long), kept in a per-lane ring in shared memory; the choice
+//      candidate (stage F) at its length L, L-1, L-2: B2Z_DP_MATCH + offset extra bits + cost[i+l]).  Only the
+//      next B2Z_CAP costs are live (candidates are at most B2Z_CAP long), kept in a per-lane ring in shared memory; the choice
 //      (0 = literal, else the length) goes to a byte array in HBM, four positions per store;
 //   3. per lane, a forward walk that only counts (sequences, literals, where the last match ends) -- a chosen match of
 //      the full B2Z_CAP bytes is extended by direct comparison to the segment end;
@@ -29,17 +29,15 @@ namespace b2z {
 // themselves.  The warp moves TILES of 32 positions per lane through shared memory instead: row j of a tile = the 32
 // positions lane j works on next, loaded / stored by the whole warp as 128-byte (candidates) or 32-byte (input bytes,
 // choices) coalesced pieces, read by lane j along its padded row (stride 33 / 9 words: conflict-free).
+constexpr uint32_t DP_RING = 32;
+static_assert(DP_RING > B2Z_CAP && (DP_RING & (DP_RING - 1u)) == 0, "the ring holds cost[i + 1 .. i + B2Z_CAP] while cost[i] is written");
 struct DpWarpSmem {
-    uint32_t ring[64][32];       // cost ring: [position & 63][lane]
+    uint32_t ring[DP_RING][32];  // cost ring: [position & (DP_RING - 1)][lane]; a candidate reaches at most B2Z_CAP positions ahead
     uint32_t candTile[32][33];   // [lane][position in tile]; the byte histogram (256 words) lives here before the first tile
     uint32_t srcTile[32][9];     // [lane][4 input bytes]
     uint32_t chcTile[32][9];     // [lane][4 choices]
     uint8_t litc[256];
 };
-
-// extra-bit price of a match length (oracle: dp_ml_price).  The programme only sees lengths <= B2Z_CAP = 64, where the oracle's
-// 16 * (highbit(l - 3) - 3) for l >= 35 is the constant 32: one step at 19, one at 35.
-__device__ __forceinline__ uint32_t dp_ml_price(uint32_t l) { return ((uint32_t)(l >= 19u) + (uint32_t)(l >= 35u)) << 4; }
 
 // 16 * log2(x) as b2z_zstd_cost.h:zop_log16, with the fraction table in registers
 __device__ __forceinline__ uint32_t dp_log16(uint32_t x) {
@@ -185,7 +183,7 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
     const uint32_t sn = active ? ((bn - s0) < B2Z_SEG ? (bn - s0) : B2Z_SEG) : 0u;
     uint32_t diff = 0;                                                         // any byte of the segment unlike the block's first byte
     const uint32_t first = bs[0];
-    if (active) sm.ring[sn & 63u][lane] = 0;
+    if (active) sm.ring[sn & (DP_RING - 1u)][lane] = 0;
     for (uint32_t t = nTiles; t-- > 0;) {
         dp_load_cand_tile(sm, cndB, bn, t, lane);
         dp_load_byte_tile(sm.srcTile, bs, bn, t, lane);
@@ -205,15 +203,15 @@ zstd_enc_dp_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g,
                     diff |= byte ^ first;
                     const uint32_t c = sm.candTile[lane][4 * wi + j];
                     const uint32_t len = B2Z_CAND_LEN(c), ob = 16u * highbit32(B2Z_CAND_OFF(c) + 3u) + B2Z_DP_MATCH;
-                    uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & 63u][lane], ch = 0;
+                    uint32_t best = (uint32_t)sm.litc[byte] + sm.ring[(i + 1u) & (DP_RING - 1u)][lane], ch = 0;
 #pragma unroll
                     for (uint32_t k = 0; k <= B2Z_DP_NTRUNC; k++) {
                         const uint32_t l = len - k;                            // wraps below zero when len < k: the index stays inside the ring, the price is discarded
-                        const uint32_t pr = ob + dp_ml_price(l) + sm.ring[(i + l) & 63u][lane];
+                        const uint32_t pr = ob + sm.ring[(i + l) & (DP_RING - 1u)][lane];
                         const bool take = (len >= B2Z_DP_MINLEN + k) && pr < best;
                         best = take ? pr : best; ch = take ? l : ch;
                     }
-                    sm.ring[i & 63u][lane] = best;
+                    sm.ring[i & (DP_RING - 1u)][lane] = best;
                     packed |= ch << (8 * j);
                 }
                 sm.chcTile[lane][wi] = packed;

@@ -39,6 +39,16 @@ __device__ __forceinline__ void turn_inputs_ready(uint32_t* slot, uint32_t iL, u
 #endif
 }
 
+// common-prefix length of frame[q..] with the 16 bytes (v, v2) of the searching position, capped at maxLen <= 16: straight-line
+static_assert(B2Z_CAP == 16, "match_len16 compares two 8-byte words");
+__device__ __forceinline__ uint32_t match_len16(const uint64_t* __restrict__ w, uint32_t q, uint64_t v, uint64_t v2, uint32_t maxLen, uint32_t nWords) {
+    const uint32_t qi = q >> 3, qs = (q & 7u) * 8u;
+    const uint64_t qa = ldw(w, qi, nWords), qb = ldw(w, qi + 1u, nWords), qc = qs ? ldw(w, qi + 2u, nWords) : 0ull;
+    const uint64_t x1 = funnel64(qa, qb, qs) ^ v, x2 = funnel64(qb, qc, qs) ^ v2;
+    const uint32_t len = x1 ? ((uint32_t)(__ffsll((long long)x1) - 1) >> 3) : (x2 ? 8u + ((uint32_t)(__ffsll((long long)x2) - 1) >> 3) : 16u);
+    return len < maxLen ? len : maxLen;
+}
+
 template <int WPG, int G>
 __global__ void __launch_bounds__(WPG * G * 32, 1)
 zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cand,
@@ -115,11 +125,13 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
             }
             uint32_t word = 0;
             if (hashable) {
+                // at most B2Z_CAP = 16 bytes are compared: the 8 at p (v) and the next 8 (v2), against three aligned words per candidate
                 const uint32_t segEnd = ((p | (B2Z_SEG - 1u)) + 1u) < n ? ((p | (B2Z_SEG - 1u)) + 1u) : n;
-                uint32_t maxLen = segEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
+                const uint32_t maxLen = (segEnd - p) < B2Z_CAP ? (segEnd - p) : B2Z_CAP;
+                const uint64_t v2 = ld64u(w, p + 8u, nWords);
                 uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;
-                if (eL && (eL & tagMask) == tL) { const uint32_t q = (eL >> tagBits) - 1u; if (p - q <= W) { offL = p - q; lenL = match_len_pv(w, q, p, v, maxLen, nWords); } }
-                if (eS && (eS & tagMask) == tS) { const uint32_t q = (eS >> tagBits) - 1u; if (p - q <= W && p - q != offL) { offS = p - q; lenS = match_len_pv(w, q, p, v, maxLen, nWords); } }
+                if (eL && (eL & tagMask) == tL) { const uint32_t q = (eL >> tagBits) - 1u; if (p - q <= W) { offL = p - q; lenL = match_len16(w, q, v, v2, maxLen, nWords); } }
+                if (eS && (eS & tagMask) == tS) { const uint32_t q = (eS >> tagBits) - 1u; if (p - q <= W && p - q != offL) { offS = p - q; lenS = match_len16(w, q, v, v2, maxLen, nWords); } }
                 uint32_t len = lenL, off = offL;
                 if (lenS > lenL || (lenS == lenL && lenS && offS < offL)) { len = lenS; off = offS; }
                 if (len >= B2Z_DP_MINLEN) word = B2Z_CAND(len, off);
@@ -138,12 +150,8 @@ template <int WPG, int G>
 static cudaError_t launch_find_t(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,
                                  const uint32_t* ready, uint32_t readyShift, uint32_t* errFlag, cudaStream_t st) {
     const size_t smem = zstd_enc_find_smem_bytes(g);
-    static size_t configured = 0;                 // per instantiation; the attribute is per function, any device
-    if (configured != smem) {
-        cudaError_t e = cudaFuncSetAttribute(zstd_enc_find_kernel<WPG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = cudaFuncSetAttribute(zstd_enc_find_kernel<WPG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set on every launch
+    if (e != cudaSuccess) return e;
     zstd_enc_find_kernel<WPG, G><<<nCtas, WPG * G * 32, smem, st>>>(src, srcSize, g, cand, ready, readyShift, errFlag);
     return cudaGetLastError();
 }

@@ -111,9 +111,6 @@ void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P
     free(TL); free(TS); free(iL); free(iS); free(eLn); free(eSn);
 }
 
-/* extra-bit price of a match length in 1/16 bit (ours: a step at 19, then the bit length of the ML code's range) */
-static inline uint32_t dp_ml_price(uint32_t l) { return l >= 35 ? 16 * (zf_highbit32(l - 3) - 3) : (l >= 19 ? 16 : 0); }
-
 typedef struct { uint32_t rep[3]; } seg_rep_t;
 
 /* Stage G, one frame: candidate words -> per 128 KiB block final sequences (B2Z_PACK_SEQ) and literal bytes.
@@ -121,8 +118,8 @@ typedef struct { uint32_t rep[3]; } seg_rep_t;
  * The role of the parse in ZSTD_compressBlock_doubleFast (greedy + repcode check) is played by a minimum-price path:
  * a block is cut into SEGMENTS of 4 KiB (one GPU lane each, a warp per block); inside a segment a backward dynamic
  * programme prices, at every position, the literal (its byte's cost in the block's sampled histogram) against the
- * position's candidate at its full length and at up to B2Z_DP_NTRUNC shorter lengths (B2Z_DP_MATCH + the offset's and the
- * length code's extra bits).  The forward walk follows the choices; a chosen match of the full B2Z_CAP bytes is extended
+ * position's candidate at its full length and at up to B2Z_DP_NTRUNC shorter lengths (B2Z_DP_MATCH + the offset's extra
+ * bits; lengths up to B2Z_CAP have no extra bits).  The forward walk follows the choices; a chosen match of the full B2Z_CAP bytes is extended
  * by direct comparison to the segment end and the walk continues with the choice stored where the match ends.
  * Offsets become offBase with a repcode history that starts "unknown" at every segment (ZSTD_updateRep rules,
  * zstd_compress_internal.h:817-835), so lanes are independent; literal runs carry across segments.
@@ -159,7 +156,7 @@ static void parse_frame(const uint8_t *src, uint32_t n, const uint32_t *cand,
                 if (c) {
                     const uint32_t len = B2Z_CAND_LEN(c), ob = 16 * zf_highbit32(B2Z_CAND_OFF(c) + 3) + B2Z_DP_MATCH;
                     for (uint32_t k = 0; k <= B2Z_DP_NTRUNC && len >= B2Z_DP_MINLEN + k; k++) {
-                        const uint32_t l = len - k, pr = ob + dp_ml_price(l) + cost[i + l];
+                        const uint32_t l = len - k, pr = ob + cost[i + l];
                         if (pr < best) { best = pr; ch = l; }
                     }
                 }
