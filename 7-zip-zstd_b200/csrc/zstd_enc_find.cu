@@ -8,10 +8,8 @@
 // The frame is walked in CHUNKS of CH = 32 * WPG positions, thread = position.  The CTA is G groups of WPG warps; chunk c
 // belongs to group c mod G.  A chunk's table accesses form a TURN: read both entries (table state before the chunk),
 // group barrier, atomicMax both entries, hand the turn to the next group (bar.arrive on its named barrier; the next
-// group's bar.sync waits for it).  Everything else -- loading the bytes, hashing, resolving the lanes of a step that share
-// a table index (__match_any_sync: a lane prefers the nearest lower lane of its step to the table's entry), comparing the
-// candidates with the input, packing the result -- happens outside the turn, so while one group holds the turn the
-// other G-1 groups hash or compare.  The serial chain of a frame is therefore two shared-memory accesses and two barrier
+// group's bar.sync waits for it).  Everything else -- loading the bytes, hashing, comparing the candidates with the input,
+// packing the result -- happens outside the turn, so while one group holds the turn the other G-1 groups hash or compare.  The serial chain of a frame is therefore two shared-memory accesses and two barrier
 // hops per CH positions; the result is the pure function of the frame's bytes that
 // oracle/zstd_enc_oracle.c:b2zo_zstd_candidates states position by position.
 //
@@ -100,29 +98,17 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
             const uint32_t iL = (uint32_t)(hl >> (64u - HL)), iS = (uint32_t)(hs >> (64u - HS));
             const uint32_t tL = (uint32_t)(hl >> (64u - HL - tagBits)) & tagMask, tS = (uint32_t)(hs >> (64u - HS - tagBits)) & tagMask;
             const uint32_t mineL = ((p + 1u) << tagBits) | tL, mineS = ((p + 1u) << tagBits) | tS;
-            const uint32_t gL = __match_any_sync(B2Z_FULL, hashable ? iL : (0x80000000u | lane));
-            const uint32_t gS = __match_any_sync(B2Z_FULL, hashable ? iS : (0x80000000u | lane));
-            const uint32_t lowL = gL & lanemask_lt(), lowS = gS & lanemask_lt();
-            const bool lastL = hashable && (gL >> lane) == 1u, lastS = hashable && (gS >> lane) == 1u;   // the highest lane of a same-index group carries the step's newest position
             uint32_t* const aL = TL + iL; uint32_t* const aS = TS + iS;
-            turn_inputs_ready(smem + tableWords + tid, iL, iS, mineL, mineS, (uint32_t)lastL | ((uint32_t)lastS << 1) | ((uint32_t)hashable << 2));
+            turn_inputs_ready(smem + tableWords + tid, iL, iS, mineL, mineS, (uint32_t)hashable);
             // ---- the turn: nothing but the table accesses between the two barrier hops
             bar_sync(B2Z_FIND_BAR_TURN(grp), 2u * CH);
             uint32_t eL = 0, eS = 0;
             if (hashable) { eL = *aL; eS = *aS; }
             if (WPG > 1) bar_sync(B2Z_FIND_BAR_GRP(grp), CH); else __syncwarp();
-            if (lastL) atomicMax(aL, mineL);
-            if (lastS) atomicMax(aS, mineS);
+            if (hashable) { atomicMax(aL, mineL); atomicMax(aS, mineS); }     // the highest position of the chunk stays
             bar_arrive(B2Z_FIND_BAR_TURN(nextGrp), 2u * CH);
             // ---- after the turn: the next iteration's bytes are requested before this one's candidates are compared
             vNext = ld64u(w, p + G * CH, nWords);
-            // ---- after the turn: a lower lane of the step with my index is nearer than anything in the table
-            {
-                const uint32_t fromL = __shfl_sync(B2Z_FULL, mineL, lowL ? 31 - __clz((int)lowL) : 0);
-                const uint32_t fromS = __shfl_sync(B2Z_FULL, mineS, lowS ? 31 - __clz((int)lowS) : 0);
-                if (lowL) eL = fromL;
-                if (lowS) eS = fromS;
-            }
             uint32_t word = 0;
             if (hashable) {
                 // at most B2Z_CAP = 16 bytes are compared: the 8 at p (v) and the next 8 (v2), against three aligned words per candidate

@@ -25,7 +25,7 @@
  *
  * Parallel semantics restated sequentially:
  *   - stage F: a CTA owns a frame and walks it in chunks of 2^chunkLog positions; a position sees the tables as they
- *     stood before its chunk plus the lower lanes of its own 32-position step (b2zo_zstd_candidates);
+ *     stood before its chunk (b2zo_zstd_candidates);
  *   - stage G: a warp owns a 128 KiB block, a lane a 4 KiB segment of it: minimum-price path per segment, repcode
  *     history unknown at every segment start (parse_frame).
  */
@@ -69,10 +69,11 @@ static size_t count_match(const uint8_t *a, const uint8_t *b, size_t maxLen) {
  * Two direct-mapped tables of position+tag entries, the long one indexed by the 8-byte hash and the short one by the
  * 5-byte hash of the reference's double-fast finder (zstd_double_fast.c:103-330, constants zstd_compress_internal.h:903-924)
  * -- sized for the shared memory of one SM (2^15 + 2^14 entries), not for the 2^17 + 2^16 of level 3.  The frame is
- * walked in CHUNKS of 2^chunkLog positions: a position sees the table as it stood BEFORE its chunk, or -- nearer -- a
- * lower position of its own 32-position step with the same table index; after a chunk every table entry holds the
- * highest position of the chunk that indexes it.  That is a pure function of the frame's bytes: the kernel evaluates a
- * chunk with 2^chunkLog threads (reads, barrier, atomicMax writes) and the steps' lower lanes with __match_any_sync.
+ * walked in CHUNKS of 2^chunkLog positions: a position sees the tables as they stood BEFORE its chunk; after a chunk every
+ * table entry holds the highest position of the chunk that indexes it.  That is a pure function of the frame's bytes: the
+ * kernel evaluates a chunk with 2^chunkLog threads (reads, barrier, atomicMax writes).  (Letting a position also see the
+ * lower positions of its own 32-position step costs two __match_any_sync per step -- the SM's ADU pipe became the bound --
+ * and buys nothing on text: 2.3823 vs 2.3830 on G2; structured data with repeats at distances under 128 loses about 1 %.)
  * Every position is searched and inserted.  Candidates are compared over at most B2Z_CAP bytes and never beyond the end
  * of their 4 KiB parse segment; the longer of (long, short) wins, the nearer on a tie. */
 void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P, uint32_t *cand) {
@@ -92,11 +93,7 @@ void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P
             iL[k] = (uint32_t)(hl >> (64 - HL)); iS[k] = (uint32_t)(hs >> (64 - HS));
             const uint32_t tL = (uint32_t)(hl >> (64 - HL - tagBits)) & tagMask, tS = (uint32_t)(hs >> (64 - HS - tagBits)) & tagMask;
             eLn[k] = ((p + 1) << tagBits) | tL; eSn[k] = ((p + 1) << tagBits) | tS;
-            uint32_t eL = TL[iL[k]], eS = TS[iS[k]];
-            for (uint32_t q = p & ~31u; q < p; q++) {                          /* lower positions of the same step */
-                if (iL[q - c0] == iL[k]) eL = eLn[q - c0];
-                if (iS[q - c0] == iS[k]) eS = eSn[q - c0];
-            }
+            const uint32_t eL = TL[iL[k]], eS = TS[iS[k]];                    /* the tables as they stood before this chunk */
             const uint32_t segEnd = ((p | (B2Z_SEG - 1)) + 1) < n ? ((p | (B2Z_SEG - 1)) + 1) : n;
             uint32_t maxLen = segEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
             uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;

@@ -51,7 +51,7 @@ def test_emulated_stage_f_equals_the_oracle(pkg, emu, fl, cl, ctas):
     src = np.frombuffer(data + bytes(64), dtype=np.uint8)
     want = H.oracle_candidates(data, frameLog=fl, windowLog=fl, chunkLog=cl)
     got = np.full(((n + (1 << fl) - 1) >> fl << fl) + 16, 0xCDCDCDCD, dtype=np.uint32)
-    assert emu.emu_zstd_enc_find(src.ctypes.data, n, fl, fl, cl, 1, ctas, got.ctypes.data) > 0
+    emu.emu_zstd_enc_find(src.ctypes.data, n, fl, fl, cl, 1, ctas, got.ctypes.data)         # (returns the count of warp collectives: stage F has none)
     assert np.array_equal(got[:n], want)
     assert int((want != 0).sum()) > n // 4
 
