@@ -17,7 +17,7 @@ namespace {
 const uint64_t kZstdMethodId = 0x4F71101;
 const uint32_t kZ7Major = 26, kZ7Minor = 1;                // module version reported to the host (C/7zVersion.h)
 const Byte kZstdVerMajor = 1, kZstdVerMinor = 5;           // header bytes (ZstdEncoder.h:17-32)
-const uint32_t kFastLevInc = 32, kUltimateLev = 128;       // ICoder.h:163-166
+const uint32_t kFastLevInc = Z7_ZSTD_FAST_LEV_INC, kUltimateLev = Z7_ZSTD_ULTIMATE_LEV;       // ICoder.h:163-166
 
 // ------------------------------------------------------------------ encoder
 class CEncoder final : public ICompressCoder, public ICompressSetCoderMt, public ICompressSetCoderProperties,
@@ -51,22 +51,29 @@ public:
             UInt32 v = pv[i].ulVal;
             switch (ids[i]) {
             case NCoderPropID::kNumThreads: SetNumberOfThreads(v); break;
-            case NCoderPropID::kAdvMax:
+            case NCoderPropID::kAdvMax:                       // ZstdEncoder.cpp:75-83: sets max, then falls into kLevel with the ultimate level
                 if (!v) break;
-                max_ = true; level_ = 22; props_[2] = (Byte)kUltimateLev; break;
-            case NCoderPropID::kLevel:
-                if (v < 1) v = 1;
-                if (v > 22) {
-                    if (v > kFastLevInc && v != kUltimateLev) { v -= kFastLevInc; goto fast; }   // fast-level inverter
-                    if (v == kUltimateLev) max_ = true;
-                    v = 22;
+                max_ = true; v = kUltimateLev;
+                /* fall through */
+            case NCoderPropID::kLevel: {                      // ZstdEncoder.cpp:84-104
+                UInt32 lev = !max_ ? v : kUltimateLev;
+                if (v < 1) lev = 1;
+                else if (v > 22) {
+                    if (v > kFastLevInc && lev != kUltimateLev) { v -= kFastLevInc; goto fast; }   // inverter: 32 + f selects fast level f
+                    max_ = (lev == kUltimateLev);             // 255 from the GUI / kAdvMax = "max"
+                    lev = 22;
                 }
-                level_ = (int)v; props_[2] = (Byte)(max_ ? kUltimateLev : v); break;
+                level_ = lev == kUltimateLev ? 22 : (int)lev; // (max set earlier and a level <= 22 now: the reference keeps 255, which zstd clamps to its maximum)
+                props_[2] = (Byte)(!max_ ? lev : kUltimateLev);
+                break;
+            }
             case NCoderPropID::kFast:
             fast:
-                if (max_) break;
-                if (v < 1) v = 1; if (v > 64) v = 64;
-                level_ = -(int)v; props_[2] = (Byte)(v + kFastLevInc); break;
+                if (!max_) {
+                    if (v < 1) v = 1; if (v > 64) v = 64;
+                    level_ = -(int)v; props_[2] = (Byte)(v + kFastLevInc); break;
+                }
+                /* fall through (as the reference does when max is set: the value is read as kLong's) */
             case NCoderPropID::kLong: windowLog_ = v == 0 ? 27 : (int)(v < 10 ? 10 : (v > 31 ? 31 : v)); break;
             case NCoderPropID::kWindowLog: if (v < 10 || v > 31) return E_INVALIDARG; windowLog_ = (int)v; break;
             case NCoderPropID::kHashLog: if (v < 6 || v > 30) return E_INVALIDARG; hashLog_ = (int)v; break;

@@ -92,6 +92,9 @@ namespace NCoderPropID { enum {
     kThreadGroup, kAffinityInGroup,
     kStrategy, kFast, kLong, kWindowLog, kHashLog, kChainLog, kSearchLog, kMinMatch, kTargetLen, kOverlapLog,
     kLdmHashLog, kLdmSearchLength, kLdmBucketSizeLog, kLdmHashRateLog, kAdvMax }; }
+// 7zip/ICoder.h:163-166: level bytes of the ZSTD coder's 5-byte property header
+#define Z7_ZSTD_FAST_LEV_INC  32      /* 32 + f = fast level f */
+#define Z7_ZSTD_ULTIMATE_LEV  255     /* "max" */
 // 7zip/ICoder.h:405-419, 440-446
 namespace NMethodPropID { enum { kID, kName, kDecoder, kEncoder, kPackStreams, kUnpackStreams, kDescription,
                                  kDecoderIsAssigned, kEncoderIsAssigned, kDigestSize, kIsFilter }; }

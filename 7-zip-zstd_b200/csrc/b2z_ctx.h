@@ -27,8 +27,9 @@ struct b200z_ctx {
     cudaStream_t stream2 = nullptr;   // side stream (decoder: literals kernel next to the sequences kernel; host path: uploads)
     cudaStream_t stream3 = nullptr;   // host path: downloads
     cudaEvent_t pe[4] = {};           // host-path pipeline events
-    uint32_t hostBatchLog = 32;       // bytes per pipeline batch of the host-pointer entry points (4 GiB: a batch must hold
-                                      // thousands of frames to fill the GPU; larger inputs are pipelined)
+    uint32_t hostBatchLog = 30;       // bytes per pipeline batch of the host-pointer entry points: 1 GiB = 1024 frames = 7 rounds of
+                                      // stage F's one-CTA-per-SM grid, so H2D | kernels | D2H of consecutive batches overlap.  The decoder
+                                      // (one warp per frame in its execute stage) takes batches twice as large
     b2z::EncGeom geom{};
     int level = 3;
     uint32_t batchLog = 32;

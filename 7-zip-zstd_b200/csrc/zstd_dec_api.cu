@@ -188,7 +188,7 @@ int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, 
     if (!srcSize) return 0;
     CU(cudaSetDevice(ctx->device));
     std::vector<HostBatch> batches;
-    const uint64_t target = 1ull << ctx->hostBatchLog;
+    const uint64_t target = 2ull << ctx->hostBatchLog;               // the execute stage is one latency-bound warp per frame: fewer, larger batches
     if (srcSize <= (target >> 2) || !split_frames((const uint8_t*)src, srcSize, target, batches) || batches.size() < 2) {
         // one shot
         if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(dstCap + 64)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");

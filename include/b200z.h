@@ -57,7 +57,7 @@ extern "C" {
 #define B200Z_P_ZSTD_PARSE  13  /* Zstandard encoder parse: 0 = stage F + stage G (shared-memory dual-hash finder, minimum-price path per 4 KiB segment), 1 = price-based: nearest-occurrence
                                    candidates + a per-block dynamic programme over adaptive code statistics -- the role of
                                    zstd_opt.c:1077 ZSTD_compressBlock_opt_generic.  B200Z_P_LEVEL sets it (>= 8); set it after the level to override */
-#define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 32 */
+#define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 30 (the decoder takes twice that) */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
  * measured with CUDA events on the context's stream around each stage */

@@ -169,6 +169,19 @@ int main(int argc, char** argv) {
       e2->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&s2); e2->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&w2);
       CHECK(s2->SetCoderProperties(i2, p2, 1) == S_OK); MemOut h2; w2->WriteCoderProperties(&h2); CHECK(h2.d[2] == 32 + 5);
       s2->Release(); w2->Release(); CHECK(e2->Release() == 0); }
+    // kLevel 255 (what MethodProps.cpp:667 / HandlerOut.cpp:196 send for "max") and kAdvMax write header byte 255 = Z7_ZSTD_ULTIMATE_LEV
+    // (ICoder.h:166; 7zHandler.cpp:607,628 prints it as ZSTD:max); 32 + f through kLevel is the fast-level inverter; > 22 clamps to 22
+    { struct Case { PROPID id; UInt32 val; Byte want; } cases[] = {
+          { NCoderPropID::kLevel, 255, 255 }, { NCoderPropID::kAdvMax, 1, 255 }, { NCoderPropID::kLevel, 32 + 7, 32 + 7 }, { NCoderPropID::kLevel, 30, 22 },
+          { NCoderPropID::kLevel, 0, 1 }, { NCoderPropID::kLevel, 22, 22 }, { NCoderPropID::kFast, 200, 32 + 64 }, { NCoderPropID::kAdvMax, 0, 3 } };
+      for (const Case& c : cases) {
+          void* o2 = nullptr; CHECK(CreateEncoder(0, &iidCoder, &o2) == S_OK);
+          ICompressCoder* e2 = (ICompressCoder*)o2; ICompressSetCoderProperties* s2; ICompressWriteCoderProperties* w2;
+          e2->QueryInterface(b2z_iid(4, kIID_SetProps), (void**)&s2); e2->QueryInterface(b2z_iid(4, kIID_WriteProps), (void**)&w2);
+          PROPID i2[1] = { c.id }; PROPVARIANT p2[1]; memset(p2, 0, sizeof(p2)); p2[0].vt = VT_UI4; p2[0].ulVal = c.val;
+          CHECK(s2->SetCoderProperties(i2, p2, 1) == S_OK); MemOut h2; w2->WriteCoderProperties(&h2);
+          if (h2.d[2] != c.want) { fprintf(stderr, "FAIL prop %u = %u: level byte %u, want %u\n", (unsigned)c.id, (unsigned)c.val, (unsigned)h2.d[2], (unsigned)c.want); return 1; }
+          s2->Release(); w2->Release(); CHECK(e2->Release() == 0); } }
     if (std::string(argv[2]) == "--exports") { printf("exports ok\n"); return 0; }
 
     std::vector<Byte> input;

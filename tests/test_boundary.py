@@ -101,3 +101,25 @@ def test_binding_parameter_ids_match_header(pkg):
     for k, h in names.items():
         assert pkg.Codec._PARAMS[k] == ids[h], k
     assert len(set(ids.values())) == len(ids)
+
+
+def _abi_facts(tmp_path, *flags):
+    exe = str(tmp_path / ("abi_" + str(len(flags))))
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wno-invalid-offsetof", *flags, os.path.join(ROOT, "tests", "cpp", "abi_facts.cpp"), "-o", exe])
+    return subprocess.check_output([exe]).decode()
+
+
+def test_abi_declaration_equals_the_reference_headers(tmp_path):
+    """codec/b2z_7zip_abi.h re-declares the codec-plugin ABI so that the module builds without the 7-Zip tree; this compiles the same
+    fact printer (struct layout, HRESULTs, interface IDs, every NCoderPropID / NMethodPropID value, the ZSTD level bytes, the vtable
+    slot of every interface method) against it AND against the reference's own MyWindows.h / MyCom.h / ICoder.h / IStream.h.
+    Where /root/reference is absent the committed copy of the reference's output (tests/golden/abi_facts_reference.txt) stands in."""
+    ours = _abi_facts(tmp_path)
+    golden = os.path.join(ROOT, "tests", "golden", "abi_facts_reference.txt")
+    if os.path.isdir("/root/reference/CPP/7zip"):
+        ref = _abi_facts(tmp_path, "-DB2Z_REFERENCE_HEADERS", "-I/root/reference/CPP")
+        assert ref == open(golden).read(), "tests/golden/abi_facts_reference.txt is stale: regenerate it with abi_facts.cpp -DB2Z_REFERENCE_HEADERS"
+    else:
+        ref = open(golden).read()
+    assert ours == ref
+    assert "ultimate 255 fast_inc 32" in ours and "slot ICompressCoder::Code 3" in ours
