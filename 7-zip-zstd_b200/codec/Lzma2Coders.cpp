@@ -111,10 +111,15 @@ class CLzma2Decoder final : public ICompressCoder, public ICompressSetDecoderPro
                             public ISequentialInStream, CoderBase {
     std::atomic<UInt32> refs_{0};
     Byte prop_ = 40; bool finishMode_ = false; UInt64 inProcessed_ = 0;
-    std::vector<Byte> in_;
-    PinnedBuf out_;
+    static constexpr size_t kInStep = (size_t)256 << 20;         // granularity of reads / growth of the input staging
+    static constexpr uint64_t kOutTarget = (uint64_t)1 << 30;    // decoded bytes per GPU batch
+    static constexpr uint64_t kOutLimit = (uint64_t)48 << 30;    // a block that needs more staging than this is refused, never attempted
+    PinnedBuf in_, out_;
+    size_t inFill_ = 0; bool inEof_ = false;
+    size_t batchSize_ = 0, batchPos_ = 0;                        // decoded batch in out_ the caller may take / has taken (pull mode)
+    UInt64 produced_ = 0;                                        // decoded bytes of the whole stream (finish mode compares it with the unpack size)
     // pull mode (Lzma2Decoder.cpp:196-265): SetInStream + SetOutStreamSize, then Read() until it returns 0 bytes
-    ISequentialInStream* pullIn_ = nullptr; bool pullDone_ = false; size_t pullSize_ = 0, pullPos_ = 0;
+    ISequentialInStream* pullIn_ = nullptr; bool pullDone_ = false;
     bool haveOutSize_ = false; UInt64 outSize_ = 0;
 public:
     ~CLzma2Decoder() { if (pullIn_) pullIn_->Release(); }
@@ -141,7 +146,7 @@ public:
     HRESULT SetMemLimit(UInt64) override { return S_OK; }                       // limits the reference's MT block buffers; no equivalent
     HRESULT SetOutStreamSize(const UInt64* outSize) override {                  // Lzma2Decoder.cpp:208-243
         haveOutSize_ = outSize != nullptr; outSize_ = outSize ? *outSize : 0;
-        pullDone_ = false; pullSize_ = pullPos_ = 0; processedIn = processedOut = 0; inProcessed_ = 0;
+        pullDone_ = false; batchSize_ = batchPos_ = 0; processedIn = processedOut = 0; inProcessed_ = 0; produced_ = 0; inFill_ = 0; inEof_ = false;
         return S_OK;
     }
     HRESULT SetInStream(ISequentialInStream* in) override { if (in) in->AddRef(); if (pullIn_) pullIn_->Release(); pullIn_ = in; return S_OK; }
@@ -149,13 +154,14 @@ public:
     HRESULT Read(void* data, UInt32 size, UInt32* processed) override {
         if (processed) *processed = 0;
         if (!pullIn_) return E_FAIL;
-        if (!pullDone_) {                                                       // the GPU decodes a folder's blocks together: all on the first Read
-            HRESULT hr = decode_all(pullIn_, haveOutSize_ ? &outSize_ : nullptr, &pullSize_);
+        while (batchPos_ == batchSize_ && !pullDone_) {                         // current batch taken: decode the next one
+            bool end = false;
+            HRESULT hr = next_batch(pullIn_, &end);
             if (hr != S_OK) return hr;
-            pullDone_ = true; pullPos_ = 0;
+            if (end) { pullDone_ = true; if (finishMode_ && haveOutSize_ && outSize_ != produced_ && batchSize_ == 0) return S_FALSE; }
         }
-        size_t n = pullSize_ - pullPos_; if (n > size) n = size;
-        memcpy(data, (const Byte*)out_.p + pullPos_, n); pullPos_ += n;
+        size_t n = batchSize_ - batchPos_; if (n > size) n = size;
+        memcpy(data, (const Byte*)out_.p + batchPos_, n); batchPos_ += n;
         if (processed) *processed = (UInt32)n;
         return S_OK;
     }
@@ -167,45 +173,62 @@ public:
     HRESULT GetInStreamProcessedSize(UInt64* v) override { *v = inProcessed_; return S_OK; }
     HRESULT SetNumberOfThreads(UInt32) override { return S_OK; }                // parallelism = blocks in the stream
 
-    // reads the packed stream to its end, decodes it on the GPU into out_; *toWrite = bytes the caller gets (bounded by outSize)
-    HRESULT decode_all(ISequentialInStream* inS, const UInt64* outSize, size_t* toWrite) {
-        *toWrite = 0;
+    // Decodes the next batch of whole dictionary-reset blocks into out_[0, batchSize_).  The packed stream is read piece by piece into
+    // bounded pinned staging; a batch holds about kOutTarget decoded bytes (one block larger than that still goes alone, and a stream
+    // with a single dictionary reset -- what the reference's encoders write for inputs below their block size -- is one block).
+    // *end: the end marker has been consumed.  Output beyond the folder's unpack size is dropped (Lzma2Decoder.cpp:110-128).
+    HRESULT next_batch(ISequentialInStream* inS, bool* end) {
+        *end = false; batchSize_ = batchPos_ = 0;
         HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
-        in_.clear();
         for (;;) {
-            const size_t chunk = (size_t)8 << 20, at = in_.size();
-            in_.resize(at + chunk);
-            size_t got = chunk;
-            hr = read_stream(inS, in_.data() + at, &got);
-            in_.resize(at + got);
-            if (hr != S_OK) return hr;
-            if (got < chunk) break;
+            if (!inEof_ && (in_.cap - inFill_ < kInStep / 2 + 1 || in_.cap == 0)) { if (!in_.reserve(inFill_ + kInStep + 1)) return E_OUTOFMEMORY; }   // + 1: room for an end marker
+            if (!inEof_ && inFill_ + 1 < in_.cap) {
+                size_t got = in_.cap - 1 - inFill_;
+                hr = read_stream(inS, (Byte*)in_.p + inFill_, &got);
+                if (hr != S_OK) return hr;
+                if (got < in_.cap - 1 - inFill_) inEof_ = true;
+                inFill_ += got;
+            }
+            size_t used = 0; uint64_t content = 0; uint32_t blocks = 0; int ended = 0;
+            const int rc = b200z_lzma2_stream_prefix(in_.p, inFill_, kOutTarget, &used, &content, &blocks, &ended);
+            if (rc) return S_FALSE;
+            if (blocks == 0 && !ended) {
+                if (inEof_) return S_FALSE;                              // the stream ends inside a block / has no end marker
+                if (!in_.reserve(in_.cap + (in_.cap > kInStep ? in_.cap : kInStep))) return E_OUTOFMEMORY;
+                continue;
+            }
+            if (content > kOutLimit) return E_OUTOFMEMORY;
+            size_t produced = 0;
+            if (blocks) {
+                if (!out_.reserve((size_t)content + 64)) return E_OUTOFMEMORY;
+                Byte* p = (Byte*)in_.p; size_t n = used; Byte saved = 0;
+                if (!ended) { saved = p[used]; p[used] = 0; n = used + 1; }          // a batch cut out of a longer stream gets its own end marker
+                const int drc = b200z_lzma2_decompress_host(ctx, p, n, prop_, out_.p, (size_t)content, &produced);
+                if (!ended) p[used] = saved;
+                if (drc) return hr_from_b200z(drc);
+            }
+            memmove(in_.p, (const Byte*)in_.p + used, inFill_ - used); inFill_ -= used;
+            inProcessed_ += used; processedIn = inProcessed_; produced_ += produced;
+            size_t give = produced;
+            if (haveOutSize_) { const UInt64 left = outSize_ > processedOut ? outSize_ - processedOut : 0; if (give > left) give = (size_t)left; }
+            batchSize_ = give; processedOut += give;
+            if (ended) *end = true;
+            return S_OK;
         }
-        uint64_t content = 0; uint32_t blocks = 0; size_t used = 0;
-        int rc = b200z_lzma2_stream_info(in_.data(), in_.size(), &content, &blocks, &used);
-        if (rc) return hr_from_b200z(rc);
-        if (!out_.reserve((size_t)content + 64)) return E_OUTOFMEMORY;
-        size_t produced = 0;
-        rc = b200z_lzma2_decompress_host(ctx, in_.data(), used, prop_, out_.p, (size_t)content, &produced);
-        if (rc) return hr_from_b200z(rc);
-        inProcessed_ = processedIn = used;
-        *toWrite = produced;
-        if (outSize && *outSize < *toWrite) *toWrite = (size_t)*outSize;        // the folder's unpack size bounds the output
-        processedOut = *toWrite;
-        if (finishMode_ && outSize && *outSize != produced) return S_FALSE;     // Lzma2Decoder.cpp:177-183: the stream must end exactly there
-        return S_OK;
     }
 
     HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
-        processedIn = processedOut = 0; inProcessed_ = 0;
-        size_t toWrite = 0;
-        HRESULT dec = decode_all(inS, outSize, &toWrite);
-        if (dec != S_OK && dec != S_FALSE) return dec;
-        if (dec == S_FALSE && toWrite == 0) return S_FALSE;
-        HRESULT hr = write_stream(outS, out_.p, toWrite);
-        if (hr != S_OK) return hr;
-        if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
-        return dec;
+        SetOutStreamSize(outSize);
+        for (;;) {
+            bool end = false;
+            HRESULT hr = next_batch(inS, &end);
+            if (hr != S_OK) return hr;
+            if (batchSize_) { hr = write_stream(outS, out_.p, batchSize_); if (hr != S_OK) return hr; }
+            if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
+            if (end) break;
+        }
+        if (finishMode_ && haveOutSize_ && outSize_ != produced_) return S_FALSE;      // Lzma2Decoder.cpp:177-183: the stream must end exactly there
+        return S_OK;
     }
 };
 

@@ -126,11 +126,17 @@ public:
 class CDecoder final : public ICompressCoder, public ICompressSetDecoderProperties2, public ICompressSetCoderMt,
                        public ICompressSetOutStreamSize, public ICompressSetInStream, public ISequentialInStream, CoderBase {
     std::atomic<UInt32> refs_{0};
-    std::vector<Byte> in_;
-    PinnedBuf out_;
+    // The packed stream is read piece by piece into bounded pinned staging and decoded in BATCHES of whole frames (about kOutTarget
+    // decoded bytes each; one frame larger than that still goes alone): memory is bounded by the batch, not by the folder, and output
+    // reaches the caller batch by batch -- the streaming the reference gets from ZSTD_decompressStream (ZstdDecoder.cpp:108-173).
+    static constexpr size_t kInStep = (size_t)256 << 20;         // granularity of reads / growth of the input staging
+    static constexpr uint64_t kOutTarget = (uint64_t)1 << 30;    // decoded bytes per GPU batch (the staging holds about that much packed data)
+    static constexpr uint64_t kOutLimit = (uint64_t)48 << 30;    // a single frame that needs more staging than this is refused (E_OUTOFMEMORY), never attempted
+    PinnedBuf in_, out_;
+    size_t inFill_ = 0; bool inEof_ = false;
+    size_t outSize_ = 0, outPos_ = 0;                            // current decoded batch in out_ and how much of it the caller has taken (pull mode)
     // pull mode (ZstdDecoder.cpp:182-258): SetInStream + SetOutStreamSize, then Read() until it returns 0 bytes
-    ISequentialInStream* pullIn_ = nullptr; bool pullDone_ = false; size_t pullSize_ = 0, pullPos_ = 0;
-    bool haveOutSize_ = false; UInt64 outSize_ = 0;
+    ISequentialInStream* pullIn_ = nullptr; bool pullDone_ = false;
 public:
     ~CDecoder() { if (pullIn_) pullIn_->Release(); }
     UInt64 processedIn = 0, processedOut = 0;
@@ -147,23 +153,22 @@ public:
     }
     UInt32 AddRef() override { return ++refs_; }
     UInt32 Release() override { UInt32 r = --refs_; if (!r) delete this; return r; }
-    HRESULT SetOutStreamSize(const UInt64* outSize) override {           // ZstdDecoder.cpp:57-64: (re)initialises the stream state
-        haveOutSize_ = outSize != nullptr; outSize_ = outSize ? *outSize : 0;
-        pullDone_ = false; pullSize_ = pullPos_ = 0; processedIn = processedOut = 0;
-        return S_OK;
-    }
+    void reset_stream() { inFill_ = 0; inEof_ = false; outSize_ = outPos_ = 0; pullDone_ = false; processedIn = processedOut = 0; }
+    HRESULT SetOutStreamSize(const UInt64*) override { reset_stream(); return S_OK; }   // ZstdDecoder.cpp:57-64: (re)initialises the stream state; the
+                                                                                        // size itself is not needed: frames end where their last block ends
     HRESULT SetInStream(ISequentialInStream* in) override { if (in) in->AddRef(); if (pullIn_) pullIn_->Release(); pullIn_ = in; return S_OK; }
     HRESULT ReleaseInStream() override { if (pullIn_) pullIn_->Release(); pullIn_ = nullptr; return S_OK; }
     HRESULT Read(void* data, UInt32 size, UInt32* processed) override {
         if (processed) *processed = 0;
         if (!pullIn_) return E_FAIL;
-        if (!pullDone_) {                                                // the GPU decodes a folder's frames together: all on the first Read
-            HRESULT hr = decode_all(pullIn_, haveOutSize_ ? &outSize_ : nullptr, &pullSize_);
+        while (outPos_ == outSize_ && !pullDone_) {                      // current batch taken: decode the next one
+            bool end = false;
+            HRESULT hr = next_batch(pullIn_, &end);
             if (hr != S_OK) return hr;
-            pullDone_ = true; pullPos_ = 0;
+            if (end) pullDone_ = true;
         }
-        size_t n = pullSize_ - pullPos_; if (n > size) n = size;
-        memcpy(data, (const Byte*)out_.p + pullPos_, n); pullPos_ += n;
+        size_t n = outSize_ - outPos_; if (n > size) n = size;
+        memcpy(data, (const Byte*)out_.p + outPos_, n); outPos_ += n;
         if (processed) *processed = (UInt32)n;
         return S_OK;
     }
@@ -172,49 +177,53 @@ public:
     }
     HRESULT SetNumberOfThreads(UInt32) override { return S_OK; }         // no-op, as in ZstdDecoder.cpp:260-263
 
-    // reads the packed stream to its end, decodes it on the GPU into out_; *produced = decoded bytes
-    HRESULT decode_all(ISequentialInStream* inS, const UInt64* outSize, size_t* produced) {
-        *produced = 0;
+    // Decodes the next batch of whole frames into out_[0, outSize_).  *end: the packed stream is exhausted (outSize_ = 0).
+    HRESULT next_batch(ISequentialInStream* inS, bool* end) {
+        *end = false; outSize_ = outPos_ = 0;
         HRESULT hr = ensure_ctx(); if (hr != S_OK) return hr;
-        in_.clear();
         for (;;) {
-            const size_t chunk = (size_t)8 << 20, at = in_.size();
-            in_.resize(at + chunk);
-            size_t got = chunk;
-            hr = read_stream(inS, in_.data() + at, &got);
-            in_.resize(at + got);
-            if (hr != S_OK) return hr;
-            if (got < chunk) break;
+            // top the staging up (a short read is not the end: StreamUtils.cpp:54 semantics live in read_stream)
+            if (!inEof_ && (in_.cap - inFill_ < kInStep / 2 || in_.cap == 0)) { if (!in_.reserve(inFill_ + kInStep)) return E_OUTOFMEMORY; }
+            if (!inEof_ && inFill_ < in_.cap) {
+                size_t got = in_.cap - inFill_;
+                hr = read_stream(inS, (Byte*)in_.p + inFill_, &got);
+                if (hr != S_OK) return hr;
+                if (got < in_.cap - inFill_) inEof_ = true;
+                inFill_ += got;
+            }
+            if (inFill_ == 0) { *end = true; return S_OK; }
+            size_t used = 0; uint64_t bound = 0; uint32_t frames = 0;
+            const int rc = b200z_zstd_frame_prefix(in_.p, inFill_, kOutTarget, &used, &bound, &frames);
+            if (rc == B200Z_E_CORRUPT && frames == 0) return S_FALSE;   // (complete frames in front of the damage are still delivered first)
+            if (frames == 0) {
+                if (inEof_) return S_FALSE;                              // the stream ends inside a frame
+                if (!in_.reserve(in_.cap + (in_.cap > kInStep ? in_.cap : kInStep))) return E_OUTOFMEMORY;   // one frame larger than the staging: grow, read on
+                continue;
+            }
+            if (bound > kOutLimit) return E_OUTOFMEMORY;
+            if (!out_.reserve((size_t)bound + 64)) return E_OUTOFMEMORY;
+            size_t produced = 0;
+            const int drc = b200z_zstd_decompress_host(ctx, in_.p, used, out_.p, (size_t)bound, &produced);
+            if (drc == B200Z_E_DSTSIZE) return S_FALSE;                  // the blocks regenerate more than the frame declared / than blocks can hold
+            if (drc) return hr_from_b200z(drc);
+            memmove(in_.p, (const Byte*)in_.p + used, inFill_ - used); inFill_ -= used;
+            processedIn += used; processedOut += produced;
+            outSize_ = produced;
+            if (produced == 0 && inFill_ == 0 && inEof_) *end = true;   // only empty / skippable frames were left
+            return S_OK;
         }
-        processedIn = in_.size();
-        if (in_.empty()) return S_OK;
-        uint64_t content = 0; uint32_t frames = 0;
-        int rc = b200z_zstd_frame_info(in_.data(), in_.size(), &content, &frames);
-        if (rc == B200Z_E_CORRUPT) return S_FALSE;
-        size_t cap;
-        if (rc == 0) cap = (size_t)content;
-        else if (outSize) cap = (size_t)*outSize;                        // 7z folders pass the unpacked size
-        else cap = in_.size() * 64 + ((size_t)1 << 20);                  // undeclared size: generous bound, grown on demand
-        for (;;) {
-            if (!out_.reserve(cap + 64)) return E_OUTOFMEMORY;
-            rc = b200z_zstd_decompress_host(ctx, in_.data(), in_.size(), out_.p, cap, produced);
-            if (rc == B200Z_E_DSTSIZE && !(outSize || content)) { cap *= 4; continue; }
-            if (rc) return hr_from_b200z(rc);
-            break;
-        }
-        processedOut = *produced;
-        return S_OK;
     }
 
-    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64* outSize, ICompressProgressInfo* progress) override {
-        processedIn = processedOut = 0;
-        size_t produced = 0;
-        HRESULT hr = decode_all(inS, outSize, &produced);                // the frames of one Code() input are decoded together
-        if (hr != S_OK) return hr;
-        hr = write_stream(outS, out_.p, produced);
-        if (hr != S_OK) return hr;
-        if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
-        return S_OK;
+    HRESULT Code(ISequentialInStream* inS, ISequentialOutStream* outS, const UInt64*, const UInt64*, ICompressProgressInfo* progress) override {
+        reset_stream();
+        for (;;) {
+            bool end = false;
+            HRESULT hr = next_batch(inS, &end);
+            if (hr != S_OK) return hr;
+            if (outSize_) { hr = write_stream(outS, out_.p, outSize_); if (hr != S_OK) return hr; }
+            if (progress) { hr = progress->SetRatioInfo(&processedIn, &processedOut); if (hr != S_OK) return hr; }
+            if (end) return S_OK;
+        }
     }
 };
 

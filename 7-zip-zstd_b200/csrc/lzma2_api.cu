@@ -28,6 +28,47 @@ int b200z_lzma2_stream_info(const void* src, size_t srcSize, uint64_t* contentSi
     return c.status ? B200Z_E_CORRUPT : B200Z_OK;
 }
 
+// The complete dictionary-reset blocks at the start of a buffer that may end inside a chunk (streaming callers).  A block is
+// known to be complete once the header of the next reset chunk, or the end marker, has been seen.  *usedBytes = offset of that
+// boundary (past the end marker when *ended), *contentSize = decoded bytes of the blocks before it.  Stops at the first boundary
+// at or beyond maxContent.  The caller decodes [0, usedBytes) -- appending the 0x00 end marker when !*ended -- and goes on from there.
+int b200z_lzma2_stream_prefix(const void* srcv, size_t srcSize, uint64_t maxContent, size_t* usedBytes, uint64_t* contentSize, uint32_t* nBlocks, int* ended) {
+    const uint8_t* src = (const uint8_t*)srcv;
+    uint64_t ip = 0, total = 0, boundary = 0, boundaryTotal = 0;
+    uint32_t nb = 0, nbAtBoundary = 0, needInit = 0xE0;
+    int end = 0, rc = B200Z_OK;
+    while (ip < srcSize) {
+        const uint32_t ctl = src[ip];
+        if (ctl == 0) { boundary = ip + 1; boundaryTotal = total; nbAtBoundary = nb; end = 1; break; }
+        uint64_t hdr, pack, unpack; bool reset;
+        if (ctl <= 2) {
+            if (ip + 3 > srcSize) break;
+            hdr = 3; pack = unpack = (((uint64_t)src[ip + 1] << 8) | src[ip + 2]) + 1; reset = ctl == 1;
+            if (ctl == 1) needInit = 0xC0; else if (needInit == 0xE0) { rc = B200Z_E_CORRUPT; break; }
+        } else {
+            if (ctl < 0x80 || ctl < needInit) { rc = B200Z_E_CORRUPT; break; }
+            needInit = 0;
+            const uint32_t mode = (ctl >> 5) & 3u;
+            hdr = 5 + (mode >= 2 ? 1 : 0);
+            if (ip + hdr > srcSize) break;
+            unpack = ((((uint64_t)ctl & 0x1F) << 16) | ((uint64_t)src[ip + 1] << 8) | src[ip + 2]) + 1;
+            pack = (((uint64_t)src[ip + 3] << 8) | src[ip + 4]) + 1;
+            reset = mode == 3;
+        }
+        if (reset) {                                            // everything before this header is whole blocks
+            boundary = ip; boundaryTotal = total; nbAtBoundary = nb; nb++;
+            if (nbAtBoundary && boundaryTotal >= maxContent) break;
+        }
+        if (ip + hdr + pack > srcSize) break;
+        total += unpack; ip += hdr + pack;
+    }
+    if (usedBytes) *usedBytes = (size_t)boundary;
+    if (contentSize) *contentSize = boundaryTotal;
+    if (nBlocks) *nBlocks = nbAtBoundary;
+    if (ended) *ended = end;
+    return rc;
+}
+
 int b200z_lzma2_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize, uint32_t dictProp,
                                   void* d_dst, size_t dstCap, size_t* dstSize) {
     if (!ctx || !dstSize || (!d_src && srcSize) || (!d_dst && dstCap)) return B200Z_E_PARAM;

@@ -13,8 +13,8 @@ static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); re
 static int dec_status_to_rc(b200z_ctx* ctx, uint32_t st) {
     if (st & B2Z_DERR_TABLE_FULL) return fail(ctx, B200Z_E_UNSUPPORTED, "more frames/blocks than the decoder tables hold%s");
     if (st & B2Z_DERR_UNSUPPORTED) return fail(ctx, B200Z_E_UNSUPPORTED, "dictionary or window > 1 GiB frames are not supported%s");
+    if (st & B2Z_DERR_CORRUPT) return fail(ctx, B200Z_E_CORRUPT, "corrupt zstd data%s");          // a declared size that the blocks contradict is corruption, whatever else was noticed
     if (st & B2Z_DERR_DSTSIZE) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
-    if (st & B2Z_DERR_CORRUPT) return fail(ctx, B200Z_E_CORRUPT, "corrupt zstd data%s");
     if (st & B2Z_DERR_CHECKSUM) return fail(ctx, B200Z_E_CHECKSUM, "content checksum mismatch%s");
     return 0;
 }
@@ -65,6 +65,61 @@ int b200z_zstd_frame_info(const void* srcv, size_t srcSize, uint64_t* contentSiz
     if (nFrames) *nFrames = frames;
     if (contentSize) *contentSize = total;
     return unknown ? B200Z_E_UNSUPPORTED : B200Z_OK;
+}
+
+
+// The complete frames at the start of a buffer that may end inside a frame (streaming callers read the packed stream piece by
+// piece).  *usedBytes = end of the last complete frame taken (skippable frames go with the frame that follows; trailing ones with
+// the frame before), *contentBound = bytes those frames decode to -- exact where a frame declares its size, else the sum over its
+// blocks of what a block can regenerate (raw / RLE: its size field, compressed: 128 KiB).  Stops before a frame that would take
+// the sum past maxContent unless it is the first one.  B200Z_E_CORRUPT: the bytes at a frame start are no frame.
+int b200z_zstd_frame_prefix(const void* srcv, size_t srcSize, uint64_t maxContent, size_t* usedBytes, uint64_t* contentBound, uint32_t* nFrames) {
+    const uint8_t* base = (const uint8_t*)srcv; const uint8_t* ip = base; const uint8_t* iend = ip + srcSize;
+    uint64_t total = 0; uint32_t frames = 0; size_t used = 0;
+    while (ip < iend) {
+        if (iend - ip < 4) break;
+        const uint32_t magic = rd32(ip);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+            if (iend - ip < 8) break;
+            const uint32_t sz = rd32(ip + 4);
+            if ((size_t)(iend - ip) < 8 + (size_t)sz) break;
+            ip += 8 + sz;
+            if (frames) used = (size_t)(ip - base);              // after a frame: belongs to what was taken; before the first: to the frame to come
+            continue;
+        }
+        if (magic != 0xFD2FB528u) { if (usedBytes) *usedBytes = used; return B200Z_E_CORRUPT; }
+        if (iend - ip < 6) break;
+        const uint8_t* p = ip + 5; const uint32_t fhd = ip[4];
+        const uint32_t fcsFlag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, didFlag = fhd & 3;
+        if (fhd & 8) { if (usedBytes) *usedBytes = used; return B200Z_E_CORRUPT; }
+        if (!single) p += 1;
+        p += didFlag == 3 ? 4 : didFlag;
+        const int fcsBytes = fcsFlag == 0 ? (int)single : (fcsFlag == 1 ? 2 : (fcsFlag == 2 ? 4 : 8));
+        if (iend - p < fcsBytes) break;
+        uint64_t fcs = 0; for (int i = 0; i < fcsBytes; i++) fcs |= (uint64_t)p[i] << (8 * i); if (fcsBytes == 2) fcs += 256;
+        p += fcsBytes;
+        uint64_t bound = 0; bool complete = false;
+        for (;;) {
+            if (iend - p < 3) break;
+            const uint32_t bh = p[0] | (p[1] << 8) | (p[2] << 16); p += 3;
+            const uint32_t last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
+            if (type == 3) { if (usedBytes) *usedBytes = used; return B200Z_E_CORRUPT; }
+            const size_t adv = type == 1 ? 1 : bsize;
+            if ((size_t)(iend - p) < adv) break;
+            bound += type == 2 ? 131072u : bsize;
+            p += adv;
+            if (last) { complete = true; break; }
+        }
+        if (!complete) break;
+        if (checksum) { if (iend - p < 4) break; p += 4; }
+        const uint64_t content = fcsBytes ? fcs : bound;
+        if (frames && total + content > maxContent) break;
+        total += content; frames++; ip = p; used = (size_t)(ip - base);
+    }
+    if (usedBytes) *usedBytes = used;
+    if (contentBound) *contentBound = total;
+    if (nFrames) *nFrames = frames;
+    return B200Z_OK;
 }
 
 }  // extern "C"

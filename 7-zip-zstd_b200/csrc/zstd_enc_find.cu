@@ -54,7 +54,7 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
     B2Z_EXTERN_SMEM(uint32_t, smem);
     constexpr uint32_t CH = WPG * 32u, NT = CH * G;
     static_assert(G >= 2 && G <= 7, "named barriers 1..7 and 8..14");
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, grp = tid / CH, tg = tid % CH;
+    const uint32_t tid = threadIdx.x, grp = tid / CH, tg = tid % CH;
     const uint32_t HL = g.hashLogL, HS = g.hashLogS;
     uint32_t* const TL = smem;
     uint32_t* const TS = smem + (1u << HL);

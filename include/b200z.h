@@ -104,6 +104,12 @@ int b200z_zstd_compress_batch_host(b200z_ctx *ctx, const void *src, const uint64
  * cheap block-header walks; returns B200Z_E_UNSUPPORTED if a frame's size is not declared). */
 int b200z_zstd_frame_info(const void *src, size_t srcSize, uint64_t *contentSize, uint32_t *nFrames);
 
+/* For callers that read a packed stream piece by piece (the coder module's decoder): the complete frames at the start of a buffer
+ * that may end inside a frame.  *usedBytes = end of the last complete frame taken, *contentBound = the bytes they decode to (exact
+ * where declared, else an upper bound from the block headers: raw / RLE size fields, 128 KiB per compressed block); stops before a
+ * frame that would take the sum past maxContent unless it is the first.  B200Z_E_CORRUPT if the bytes at a frame start are no frame. */
+int b200z_zstd_frame_prefix(const void *src, size_t srcSize, uint64_t maxContent, size_t *usedBytes, uint64_t *contentBound, uint32_t *nFrames);
+
 int b200z_zstd_decompress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize,
                                  void *d_dst, size_t dstCap, size_t *dstSize);
 int b200z_zstd_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize,
@@ -123,6 +129,10 @@ int b200z_zstd_enc_stage_f(b200z_ctx *ctx, const void *d_src, size_t srcSize, ui
  * Parallel unit: every run of chunks that starts with a dictionary reset (control 0x01 / >= 0xE0), as in
  * Lzma2DecMt_MtCallback_Parse (C/Lzma2DecMt.c:237).  A stream with a single reset decodes on a single warp. */
 int b200z_lzma2_stream_info(const void *src, size_t srcSize, uint64_t *contentSize, uint32_t *nBlocks, size_t *srcUsed);
+/* For callers that read the packed stream piece by piece: the complete dictionary-reset blocks at the start of a buffer that may end
+ * inside a chunk.  *usedBytes = the boundary (past the end marker when *ended), *contentSize = what the blocks before it decode to;
+ * stops at the first boundary at or beyond maxContent.  The caller decodes [0, usedBytes) with a 0x00 end marker appended when !*ended. */
+int b200z_lzma2_stream_prefix(const void *src, size_t srcSize, uint64_t maxContent, size_t *usedBytes, uint64_t *contentSize, uint32_t *nBlocks, int *ended);
 int b200z_lzma2_decompress_device(b200z_ctx *ctx, const void *d_src, size_t srcSize, uint32_t dictProp,
                                   void *d_dst, size_t dstCap, size_t *dstSize);
 int b200z_lzma2_decompress_host(b200z_ctx *ctx, const void *src, size_t srcSize, uint32_t dictProp,
