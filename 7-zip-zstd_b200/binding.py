@@ -17,7 +17,7 @@ S_DEC_PREPASS_MS, S_ENC_PARSE_MS = 9, 10
 MAXSEQ = 32768
 
 EXPORTS = [
-    "b200z_device_count", "b200z_create", "b200z_destroy", "b200z_set_param", "b200z_get_param",
+    "b200z_device_count", "b200z_create", "b200z_create_multi", "b200z_device_list", "b200z_destroy", "b200z_set_param", "b200z_get_param",
     "b200z_last_error", "b200z_get_stat", "b200z_reset_stats", "b200z_zstd_compress_bound",
     "b200z_zstd_compress_device", "b200z_zstd_compress_host", "b200z_zstd_frame_info",
     "b200z_zstd_decompress_device", "b200z_zstd_decompress_host", "b200z_zstd_enc_stage_m", "b200z_zstd_enc_stage_f",
@@ -50,6 +50,8 @@ def load_library():
     L = ctypes.CDLL(path)
     vp, sz, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64
     L.b200z_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    L.b200z_create_multi.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    L.b200z_device_list.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     L.b200z_destroy.argtypes = [vp]; L.b200z_destroy.restype = None
     L.b200z_set_param.argtypes = [vp, ctypes.c_int, i64]
     L.b200z_get_param.argtypes = [vp, ctypes.c_int, ctypes.POINTER(i64)]
@@ -106,10 +108,15 @@ def _addr(buf):
 class Codec:
     """One coder instance on one GPU (NCompress::NZSTD::CEncoder/CDecoder's engine)."""
 
-    def __init__(self, device=0, **params):
+    def __init__(self, device=0, devices=None, **params):
+        """device: one GPU; devices=[...]: one context over several GPUs (the *_host calls deal batches of frames over them)"""
         self.L = load_library()
         h = ctypes.c_void_p()
-        rc = self.L.b200z_create(ctypes.byref(h), device)
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self.L.b200z_create_multi(ctypes.byref(h), arr, len(devices))
+        else:
+            rc = self.L.b200z_create(ctypes.byref(h), device)
         if rc:
             raise B200zError(rc, "b200z_create failed (no CUDA device? there is no CPU fallback)")
         self.h = h

@@ -100,7 +100,8 @@ public:
         if (windowLog_ >= 17) { int64_t fl = 0; b200z_get_param(ctx, B200Z_P_FRAMELOG, &fl); b200z_set_param(ctx, B200Z_P_WINDOWLOG, windowLog_ < fl ? windowLog_ : fl); }
         // batches of whole frames: 1 GiB of input per GPU pass (pinned host memory); a batch has to hold about a
         // thousand 1 MiB frames to keep the frame-parallel match finder busy
-        const size_t batch = (size_t)1 << 30;
+        const int nDev = b200z_device_list(ctx, nullptr, 0);
+        const size_t batch = (size_t)1 << (nDev >= 4 ? 32 : (nDev >= 2 ? 31 : 30));     // the call is dealt over the devices: give them a round each
         if (!in_.reserve(batch) || !out_.reserve(b200z_zstd_compress_bound(ctx, batch))) return E_OUTOFMEMORY;
         bool wroteAny = false;
         for (;;) {

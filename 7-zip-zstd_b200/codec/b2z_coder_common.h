@@ -65,9 +65,24 @@ struct CoderBase {
     b200z_ctx* ctx = nullptr;
     HRESULT ensure_ctx() {
         if (ctx) return S_OK;
-        int dev = 0;
-        if (const char* e = getenv("B200Z_DEVICE")) dev = atoi(e);      // device selection without a new PROPID
-        return hr_from_b200z(b200z_create(&ctx, dev));
+        // device selection without a new PROPID: B200Z_DEVICE=n pins one device; B200Z_DEVICES="0-3" / "0,2,5" / "all" names
+        // the devices one Code() call is dealt over.  Default: every device of the box, as the reference defaults to every core
+        // (ZstdEncoder.cpp:19 nbWorkers = #CPUs).
+        if (const char* e = getenv("B200Z_DEVICE")) return hr_from_b200z(b200z_create(&ctx, atoi(e)));
+        std::vector<int> devs;
+        const int n = b200z_device_count();
+        const char* e = getenv("B200Z_DEVICES");
+        if (!e || !strcmp(e, "all")) { for (int i = 0; i < n; i++) devs.push_back(i); }
+        else {
+            for (const char* p = e; *p;) {
+                char* q; long a = strtol(p, &q, 10); if (q == p) break;
+                long b = a; if (*q == '-') { p = q + 1; b = strtol(p, &q, 10); if (q == p) break; }
+                for (long v = a; v <= b && v < 1024; v++) devs.push_back((int)v);
+                p = q; if (*p == ',') p++;
+            }
+        }
+        if (devs.empty()) return hr_from_b200z(B200Z_E_NODEVICE);
+        return hr_from_b200z(b200z_create_multi(&ctx, devs.data(), (int)devs.size()));
     }
     ~CoderBase() { if (ctx) b200z_destroy(ctx); }
 };

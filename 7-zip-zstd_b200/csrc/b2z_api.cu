@@ -6,6 +6,9 @@
 // :1853, ZSTDMT_createCompressionJob :1403, ZSTDMT_flushProduced :1488): frames are the jobs,
 // warps are the workers, the assemble kernels are the ordered flush.
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 #include "b2z_ctx.h"
 #include "b2z_lzma2.h"
 #include "b2z_lzma_model.h"
@@ -43,8 +46,38 @@ int b200z_create(b200z_ctx** out, int device) {
     return B200Z_OK;
 }
 
+// One context over several devices: the host-pointer entry points (what ICompressCoder::Code() calls) cut their input into
+// batches of whole frames and deal them round-robin to the devices, each with its own streams, staging and scratch; the output is
+// written in input order and does not depend on the device count.  The role of ZSTDMT_createCompressionJob / ZSTDMT_flushProduced
+// (zstdmt_compress.c:1403,1488) and MtCoder_Code (MtCoder.c:445) one level up: devices are the workers.
+int b200z_create_multi(b200z_ctx** out, const int* devices, int nDevices) {
+    if (!out || !devices || nDevices < 1) return B200Z_E_PARAM;
+    *out = nullptr;
+    // (a device may be listed more than once: each entry is a worker with its own streams and scratch)
+    b200z_ctx* first = nullptr;
+    int rc = b200z_create(&first, devices[0]);
+    if (rc) return rc;
+    for (int i = 1; i < nDevices; i++) {
+        b200z_ctx* p = nullptr;
+        rc = b200z_create(&p, devices[i]);
+        if (rc) { b200z_destroy(first); return rc; }
+        first->peers.push_back(p);
+    }
+    *out = first;
+    return B200Z_OK;
+}
+
+int b200z_device_list(b200z_ctx* ctx, int* devices, int cap) {
+    if (!ctx) return 0;
+    const int n = 1 + (int)ctx->peers.size();
+    for (int i = 0; i < n && i < cap && devices; i++) devices[i] = i == 0 ? ctx->device : ctx->peers[(size_t)i - 1]->device;
+    return n;
+}
+
 void b200z_destroy(b200z_ctx* ctx) {
     if (!ctx) return;
+    for (b200z_ctx* p : ctx->peers) b200z_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
@@ -60,8 +93,14 @@ void b200z_destroy(b200z_ctx* ctx) {
     delete ctx;
 }
 
+static int set_param_one(b200z_ctx* ctx, int param, int64_t v);
 int b200z_set_param(b200z_ctx* ctx, int param, int64_t v) {
     if (!ctx) return B200Z_E_PARAM;
+    const int rc = set_param_one(ctx, param, v);
+    if (rc == 0) for (b200z_ctx* p : ctx->peers) set_param_one(p, param, v);         // every device of the group codes with the same parameters
+    return rc;
+}
+static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
     switch (param) {
     case B200Z_P_LEVEL:     if (v < 1 || v > 22) return fail(ctx, B200Z_E_PARAM, "level out of range%s"); ctx->level = (int)v;
                             // levels 1-7: the level-3-class greedy/lazy stage M; 8-22: the price-based stage C + stage Z
@@ -108,8 +147,13 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
 }
 
 const char* b200z_last_error(b200z_ctx* ctx) { return ctx ? ctx->err : "no context"; }
-double b200z_get_stat(b200z_ctx* ctx, int s) { return (ctx && s > 0 && s < 16) ? ctx->stat[s] : 0.0; }
-void b200z_reset_stats(b200z_ctx* ctx) { if (ctx) memset(ctx->stat, 0, sizeof(ctx->stat)); }
+double b200z_get_stat(b200z_ctx* ctx, int s) {
+    if (!ctx || s <= 0 || s >= 16) return 0.0;
+    double v = ctx->stat[s];
+    for (b200z_ctx* p : ctx->peers) v += p->stat[s];                // a group reports the sum over its devices
+    return v;
+}
+void b200z_reset_stats(b200z_ctx* ctx) { if (!ctx) return; memset(ctx->stat, 0, sizeof(ctx->stat)); for (b200z_ctx* p : ctx->peers) memset(p->stat, 0, sizeof(p->stat)); }
 
 size_t b200z_zstd_compress_bound(b200z_ctx* ctx, size_t n) {
     const uint32_t fl = ctx ? ctx->geom.frameLog : B2Z_DEF_FRAMELOG;
@@ -296,6 +340,63 @@ int b200z_zstd_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize
     return 0;
 }
 
+// ---- a host-pointer compress shared by the devices of a context
+struct EncJob {
+    const uint8_t* src = nullptr; size_t srcSize = 0; uint8_t* dst = nullptr; uint64_t batch = 0, nItems = 0;
+    std::mutex m; std::condition_variable cv;
+    std::vector<uint64_t> size; std::vector<char> known;         // compressed bytes of every batch, once known
+    int rc = 0; b200z_ctx* errCtx = nullptr;                     // first error
+    void fail_with(int code, b200z_ctx* c) { std::lock_guard<std::mutex> g(m); if (!rc) { rc = code; errCtx = c; } cv.notify_all(); }
+    void publish(uint64_t i, uint64_t n) { std::lock_guard<std::mutex> g(m); size[i] = n; known[i] = 1; cv.notify_all(); }
+    // output offset of batch i: blocks until the sizes of batches 0 .. i-1 are known; false when another device failed
+    bool offset_of(uint64_t i, uint64_t* off) {
+        std::unique_lock<std::mutex> g(m);
+        uint64_t sum = 0;
+        for (uint64_t k = 0; k < i; k++) { cv.wait(g, [&] { return rc != 0 || known[k]; }); if (rc) return false; sum += size[k]; }
+        *off = sum; return true;
+    }
+};
+
+// one device's share: batches first, first + stride, ... through  H2D (stream2) | kernels (stream) | D2H (stream3), double-buffered
+static void enc_worker(b200z_ctx* ctx, EncJob* job, uint64_t first, uint64_t stride) {
+    auto run = [&]() -> int {
+        CU(cudaSetDevice(ctx->device));
+        const uint64_t batch = job->batch;
+        const size_t batchBound = b200z_zstd_compress_bound(ctx, batch);
+        if (ctx->dIn.reserve(2 * (batch + 64)) || ctx->dOut.reserve(2 * batchBound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+        uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + batch + 64 };
+        uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + batchBound };
+        auto bsize = [&](uint64_t i) { return (size_t)((job->srcSize - i * batch) < batch ? (job->srcSize - i * batch) : batch); };
+        // pe[0..1]: input of buffer b uploaded; pe[2..3]: output of buffer b downloaded
+        CU(cudaMemcpyAsync(dIn[0], job->src + first * batch, bsize(first), cudaMemcpyHostToDevice, ctx->stream2));
+        CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
+        uint64_t k = 0;
+        for (uint64_t i = first; i < job->nItems; i += stride, k++) {
+            const int b = (int)(k & 1);
+            if (i + stride < job->nItems) {                          // upload the next batch while this one is compressed
+                // its buffer was last read by the kernels of the batch before this one, which have been synchronised already
+                CU(cudaMemcpyAsync(dIn[b ^ 1], job->src + (i + stride) * batch, bsize(i + stride), cudaMemcpyHostToDevice, ctx->stream2));
+                CU(cudaEventRecord(ctx->pe[b ^ 1], ctx->stream2));
+            }
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));                 // input there
+            if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0)); // output buffer drained
+            uint64_t produced = 0;
+            int rc = enc_batch(ctx, dIn[b], bsize(i), dOut[b], &produced, false);   // synchronises ctx->stream
+            if (rc) return rc;
+            job->publish(i, produced);
+            uint64_t off = 0;
+            if (!job->offset_of(i, &off)) return 0;                              // another device failed: its error is the job's
+            CU(cudaMemcpyAsync(job->dst + off, dOut[b], produced, cudaMemcpyDeviceToHost, ctx->stream3));
+            CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
+            ctx->stat[B200Z_S_H2D_BYTES] += (double)bsize(i); ctx->stat[B200Z_S_D2H_BYTES] += (double)produced;
+        }
+        CU(cudaStreamSynchronize(ctx->stream3));
+        return 0;
+    };
+    const int rc = run();
+    if (rc) job->fail_with(rc, ctx);
+}
+
 // Host-pointer compress: the stream is cut into batches of whole frames that flow through a three-stage
 // pipeline -- H2D copy of batch i+1 (stream2) | kernels of batch i (stream) | D2H copy of batch i-1 (stream3) --
 // with double-buffered device staging, so PCIe time hides under kernel time when the host buffers are pinned.
@@ -306,10 +407,17 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
     if (dstCap < bound) return fail(ctx, B200Z_E_DSTSIZE, "dstCap < b200z_zstd_compress_bound%s");
     CU(cudaSetDevice(ctx->device));
     const uint64_t F = 1ull << ctx->geom.frameLog;
+    const uint64_t nDev = 1 + ctx->peers.size();
     uint64_t batch = 1ull << ctx->hostBatchLog;
     if ((ctx->geom.flags & B2Z_FLAG_ZSTD_OPT) && batch > (1ull << 30)) batch = 1ull << 30;
+    if (nDev > 1) {                                              // about four batches per device, none smaller than one frame per SM
+        uint64_t per = (srcSize + 4 * nDev - 1) / (4 * nDev), floorB = (uint64_t)ctx->smCount * F;
+        if (per < floorB) per = floorB;
+        per = (per + F - 1) / F * F;
+        if (per < batch) batch = per;
+    }
     if (batch < F) batch = F;
-    if (srcSize <= batch) {
+    if (nDev == 1 && srcSize <= batch) {
         // one batch: the upload is cut into chunks on stream2, each followed by a flag write; stage M starts at once and
         // its frame-warps wait for their chunk, so the H2D time hides under the match kernel
         if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(bound) || ctx->ready.reserve(256)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
@@ -339,35 +447,18 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
         *dstSize = out;
         return 0;
     }
-    const size_t batchBound = b200z_zstd_compress_bound(ctx, batch);
-    if (ctx->dIn.reserve(2 * (batch + 64)) || ctx->dOut.reserve(2 * batchBound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
-    uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + batch + 64 };
-    uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + batchBound };
-    const uint64_t nBatches = (srcSize + batch - 1) / batch;
-    auto bsize = [&](uint64_t i) { return (size_t)((srcSize - i * batch) < batch ? (srcSize - i * batch) : batch); };
-    // pe[0..1]: input of buffer b uploaded; pe[2..3]: output of buffer b downloaded
-    CU(cudaMemcpyAsync(dIn[0], src, bsize(0), cudaMemcpyHostToDevice, ctx->stream2));
-    CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
-    size_t outPos = 0;
-    for (uint64_t i = 0; i < nBatches; i++) {
-        const int b = (int)(i & 1);
-        if (i + 1 < nBatches) {                                   // upload the next batch while this one is compressed
-            // its buffer was last read by the kernels of batch i-1, which have been synchronised already
-            CU(cudaMemcpyAsync(dIn[b ^ 1], (const uint8_t*)src + (i + 1) * batch, bsize(i + 1), cudaMemcpyHostToDevice, ctx->stream2));
-            CU(cudaEventRecord(ctx->pe[b ^ 1], ctx->stream2));
-        }
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));                 // input there
-        if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0)); // output buffer drained
-        uint64_t produced = 0;
-        int rc = enc_batch(ctx, dIn[b], bsize(i), dOut[b], &produced, false);   // synchronises ctx->stream
-        if (rc) return rc;
-        CU(cudaMemcpyAsync((uint8_t*)dst + outPos, dOut[b], produced, cudaMemcpyDeviceToHost, ctx->stream3));
-        CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
-        outPos += produced;
-        ctx->stat[B200Z_S_H2D_BYTES] += (double)bsize(i); ctx->stat[B200Z_S_D2H_BYTES] += (double)produced;
-    }
-    CU(cudaStreamSynchronize(ctx->stream3));
-    *dstSize = outPos;
+    // several batches and / or several devices: batch i goes to device i mod N; every device runs the three-stage pipeline over its
+    // batches, and a batch's download starts once the sizes of all earlier batches are known (they are dealt in order, so that is soon)
+    EncJob job; job.src = (const uint8_t*)src; job.srcSize = srcSize; job.dst = (uint8_t*)dst; job.batch = batch;
+    job.nItems = (srcSize + batch - 1) / batch; job.size.assign(job.nItems, 0); job.known.assign(job.nItems, 0);
+    const uint64_t nWorkers = nDev < job.nItems ? nDev : job.nItems;
+    std::vector<std::thread> threads;
+    for (uint64_t d = 1; d < nWorkers; d++) threads.emplace_back(enc_worker, ctx->peers[d - 1], &job, d, nWorkers);
+    enc_worker(ctx, &job, 0, nWorkers);
+    for (std::thread& t : threads) t.join();
+    if (job.rc) { if (job.errCtx && job.errCtx != ctx) snprintf(ctx->err, sizeof(ctx->err), "device %d: %.200s", job.errCtx->device, job.errCtx->err); return job.rc; }
+    size_t total = 0; for (uint64_t v : job.size) total += (size_t)v;
+    *dstSize = total;
     return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 #include "../../include/b200z.h"
 #include "b2z_kernels.h"
 #include "b2z_dec.h"
@@ -23,6 +24,7 @@ struct Arena {                       // grow-only device buffer
 
 struct b200z_ctx {
     int device = 0;
+    std::vector<b200z_ctx*> peers;    // multi-device context (b200z_create_multi): the contexts of the other devices; this one is device 0 of the group
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // side stream (decoder: literals kernel next to the sequences kernel; host path: uploads)
     cudaStream_t stream3 = nullptr;   // host path: downloads

@@ -5,6 +5,8 @@
 // of it (zstd or skippable) is located by the prepass and decoded in parallel.
 #include "b2z_ctx.h"
 #include <vector>
+#include <thread>
+#include <mutex>
 
 using namespace b2z;
 
@@ -236,6 +238,50 @@ static bool split_frames(const uint8_t* src, size_t srcSize, uint64_t targetOut,
     return true;
 }
 
+// one device's share of a host-pointer decompress: batches first, first + stride, ... through H2D (stream2) | decode kernels (stream)
+// | D2H (stream3), double-buffered.  Every batch knows where its output goes (the frames declare their sizes), so devices never wait
+// for each other.
+struct DecJob {
+    const uint8_t* src = nullptr; uint8_t* dst = nullptr; const std::vector<HostBatch>* batches = nullptr; size_t inStride = 0, outStride = 0;
+    std::mutex m; int rc = 0; b200z_ctx* errCtx = nullptr;
+    void fail_with(int code, b200z_ctx* c) { std::lock_guard<std::mutex> g(m); if (!rc) { rc = code; errCtx = c; } }
+    bool failed() { std::lock_guard<std::mutex> g(m); return rc != 0; }
+};
+static void dec_worker(b200z_ctx* ctx, DecJob* job, size_t first, size_t stride) {
+    auto run = [&]() -> int {
+        CU(cudaSetDevice(ctx->device));
+        const std::vector<HostBatch>& B = *job->batches;
+        if (ctx->dIn.reserve(2 * job->inStride) || ctx->dOut.reserve(2 * job->outStride)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
+        uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + job->inStride };
+        uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + job->outStride };
+        CU(cudaMemcpyAsync(dIn[0], job->src + B[first].srcOff, B[first].srcEnd - B[first].srcOff, cudaMemcpyHostToDevice, ctx->stream2));
+        CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
+        size_t k = 0;
+        for (size_t i = first; i < B.size(); i += stride, k++) {
+            const int b = (int)(k & 1);
+            if (job->failed()) break;
+            if (i + stride < B.size()) {
+                const HostBatch& nx = B[i + stride];
+                CU(cudaMemcpyAsync(dIn[b ^ 1], job->src + nx.srcOff, nx.srcEnd - nx.srcOff, cudaMemcpyHostToDevice, ctx->stream2));
+                CU(cudaEventRecord(ctx->pe[b ^ 1], ctx->stream2));
+            }
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));
+            if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0));
+            size_t out = 0;
+            int rc = dec_impl(ctx, dIn[b], B[i].srcEnd - B[i].srcOff, dOut[b], (size_t)B[i].dstSize, &out, nullptr);
+            if (rc) return rc;
+            if (out != B[i].dstSize) return fail(ctx, B200Z_E_CORRUPT, "frame content size mismatch%s");
+            if (out) CU(cudaMemcpyAsync(job->dst + B[i].dstOff, dOut[b], out, cudaMemcpyDeviceToHost, ctx->stream3));
+            CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
+            ctx->stat[B200Z_S_H2D_BYTES] += (double)(B[i].srcEnd - B[i].srcOff); ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
+        }
+        CU(cudaStreamSynchronize(ctx->stream3));
+        return 0;
+    };
+    const int rc = run();
+    if (rc) job->fail_with(rc, ctx);
+}
+
 // Host-pointer decompress: batches of whole frames flow through H2D (stream2) | decode kernels (stream) | D2H (stream3).
 int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, void* dst, size_t dstCap, size_t* dstSize) {
     if (!ctx || !dstSize || (!src && srcSize) || (!dst && dstCap)) return B200Z_E_PARAM;
@@ -243,8 +289,10 @@ int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, 
     if (!srcSize) return 0;
     CU(cudaSetDevice(ctx->device));
     std::vector<HostBatch> batches;
-    const uint64_t target = 2ull << ctx->hostBatchLog;               // the execute stage is one latency-bound warp per frame: fewer, larger batches
-    if (srcSize <= (target >> 2) || !split_frames((const uint8_t*)src, srcSize, target, batches) || batches.size() < 2) {
+    const size_t nDev = 1 + ctx->peers.size();
+    uint64_t target = 2ull << ctx->hostBatchLog;                     // the execute stage is one latency-bound warp per frame: fewer, larger batches
+    if (nDev > 1) { const uint64_t per = (uint64_t)srcSize * 3 / (2 * nDev) + 1; if (per < target) target = per; }   // about two batches per device (packed size x 3 ~ output)
+    if ((nDev == 1 && srcSize <= (target >> 2)) || !split_frames((const uint8_t*)src, srcSize, target, batches) || (batches.size() < 2 && nDev == 1) || batches.empty()) {
         // one shot
         if (ctx->dIn.reserve(srcSize + 64) || ctx->dOut.reserve(dstCap + 64)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
         CU(cudaMemcpyAsync(ctx->dIn.p, src, srcSize, cudaMemcpyHostToDevice, ctx->stream));
@@ -258,30 +306,14 @@ int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, 
     size_t maxIn = 0; uint64_t maxOut = 0, total = 0;
     for (const HostBatch& b : batches) { if (b.srcEnd - b.srcOff > maxIn) maxIn = b.srcEnd - b.srcOff; if (b.dstSize > maxOut) maxOut = b.dstSize; total += b.dstSize; }
     if (total > dstCap) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
-    const size_t inStride = (maxIn + 64 + 255) & ~(size_t)255, outStride = ((size_t)maxOut + 64 + 255) & ~(size_t)255;
-    if (ctx->dIn.reserve(2 * inStride) || ctx->dOut.reserve(2 * outStride)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
-    uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + inStride };
-    uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + outStride };
-    const size_t nB = batches.size();
-    CU(cudaMemcpyAsync(dIn[0], (const uint8_t*)src + batches[0].srcOff, batches[0].srcEnd - batches[0].srcOff, cudaMemcpyHostToDevice, ctx->stream2));
-    CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
-    for (size_t i = 0; i < nB; i++) {
-        const int b = (int)(i & 1);
-        if (i + 1 < nB) {
-            CU(cudaMemcpyAsync(dIn[b ^ 1], (const uint8_t*)src + batches[i + 1].srcOff, batches[i + 1].srcEnd - batches[i + 1].srcOff, cudaMemcpyHostToDevice, ctx->stream2));
-            CU(cudaEventRecord(ctx->pe[b ^ 1], ctx->stream2));
-        }
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));
-        if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0));
-        size_t out = 0;
-        int rc = b200z_zstd_decompress_device(ctx, dIn[b], batches[i].srcEnd - batches[i].srcOff, dOut[b], (size_t)batches[i].dstSize, &out);
-        if (rc) return rc;
-        if (out != batches[i].dstSize) return fail(ctx, B200Z_E_CORRUPT, "frame content size mismatch%s");
-        if (out) CU(cudaMemcpyAsync((uint8_t*)dst + batches[i].dstOff, dOut[b], out, cudaMemcpyDeviceToHost, ctx->stream3));
-        CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
-        ctx->stat[B200Z_S_H2D_BYTES] += (double)(batches[i].srcEnd - batches[i].srcOff); ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
-    }
-    CU(cudaStreamSynchronize(ctx->stream3));
+    DecJob job; job.src = (const uint8_t*)src; job.dst = (uint8_t*)dst; job.batches = &batches;
+    job.inStride = (maxIn + 64 + 255) & ~(size_t)255; job.outStride = ((size_t)maxOut + 64 + 255) & ~(size_t)255;
+    const size_t nWorkers = nDev < batches.size() ? nDev : batches.size();
+    std::vector<std::thread> threads;
+    for (size_t d = 1; d < nWorkers; d++) threads.emplace_back(dec_worker, ctx->peers[d - 1], &job, d, nWorkers);
+    dec_worker(ctx, &job, 0, nWorkers);
+    for (std::thread& t : threads) t.join();
+    if (job.rc) { if (job.errCtx && job.errCtx != ctx) snprintf(ctx->err, sizeof(ctx->err), "device %d: %.200s", job.errCtx->device, job.errCtx->err); return job.rc; }
     *dstSize = (size_t)total;
     return 0;
 }

@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--frame-log", type=int, default=0, help="log2 of the independent frame / block size (default: the library's, 20)")
     ap.add_argument("--lzma2-slice-log", type=int, default=-1, help="--codec lzma2: log2 of state-reset slices per block (default: the library's, 2)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--one-process", action="store_true",
+                    help="no torchrun: ONE process, one context over --gpus N devices (b200z_create_multi), the whole --size-mib input through the host-pointer calls "
+                         "(strong scaling: what one ICompressCoder::Code() call gets from the box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -147,6 +150,28 @@ def cpu_reference_lzma2(sample_bytes, seed_offset=0):
             "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": sample_bytes / len(comp), "t_enc_s": t_enc, "t_dec_s": t_dec}
 
 
+def one_call_multi_gpu(pkg, devices, host_in, unit_bytes, steps, lz=False):
+    """one context over `devices`: the host-pointer compress + decompress of the SAME input (strong scaling), pinned host buffers"""
+    import torch
+    c = pkg.Codec(devices=devices)
+    bound = c.compress_bound(unit_bytes)
+    host_comp = torch.empty(bound, dtype=torch.uint8).pin_memory()
+    host_back = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
+    n = c.compress_into(host_in.data_ptr(), unit_bytes, host_comp.data_ptr(), bound)          # warm-up (allocations, first touches)
+    c.decompress_into(host_comp.data_ptr(), n, host_back.data_ptr(), unit_bytes)
+    t_enc = t_dec = 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter(); n = c.compress_into(host_in.data_ptr(), unit_bytes, host_comp.data_ptr(), bound); t1 = time.perf_counter()
+        m = c.decompress_into(host_comp.data_ptr(), n, host_back.data_ptr(), unit_bytes); t2 = time.perf_counter()
+        assert m == unit_bytes
+        t_enc += t1 - t0; t_dec += t2 - t1
+    assert torch.equal(host_back, host_in)
+    c.close()
+    mb = steps * unit_bytes / 1e6
+    return {"devices": len(devices), "uncompressed_bytes": unit_bytes, "value": mb / (t_enc + t_dec), "unit": "MB/s", "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec,
+            "ratio": unit_bytes / n, "what": "ONE process, ONE context over all devices, one compress_host + decompress_host call per step on the same input (strong scaling)"}
+
+
 def main():
     a = parse_args()
     lz = a.codec == "lzma2"
@@ -182,6 +207,16 @@ def main():
     pkg = ge.load_package()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    if a.one_process:
+        if lz:
+            raise SystemExit("--one-process: the multi-device dispatcher serves the zstd host calls")
+        ndev = min(a.gpus, torch.cuda.device_count())
+        host_in = torch.empty(unit_bytes, dtype=torch.uint8).pin_memory()
+        pkg.corpus.g2_into(host_in.data_ptr(), unit_bytes)
+        res = one_call_multi_gpu(pkg, list(range(ndev)), host_in, unit_bytes, a.steps)
+        print(json.dumps({"metric": metric_name + " (one call, all devices)", "value": res["value"], "unit": "MB/s", "n_gpus": ndev, "steps": a.steps, "warmup": 1,
+                          "higher_is_better": True, "scaling": "strong", "dtype": "u8", "data": "synthetic", "config": {"workload": workload.replace(" per GPU", " in total")}, "e2e": res}))
+        return
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -270,6 +305,16 @@ def main():
             t = torch.tensor([e_el], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e_el = float(t.cpu()[0])
         e2e = {"value": units_mb / e_el, "unit": "MB/s", "h2d_bytes_per_step": world * (unit_bytes + c), "d2h_bytes_per_step": world * (c + unit_bytes)}
 
+    # ---- one call on all N devices (rank 0; the other ranks wait): the dispatcher inside the product, strong scaling on ONE rank's input
+    multi = None
+    if dist and not lz and not a.no_e2e:
+        barrier()
+        if rank == 0:
+            try:
+                multi = one_call_multi_gpu(pkg, list(range(world)), host_in, unit_bytes, max(1, min(a.steps, 3)))
+            except Exception as e:                                   # e.g. ranks not on devices 0..N-1 of this process's view
+                multi = {"error": str(e)[:200]}
+        barrier()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -306,6 +351,8 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": match_ms},
         "clocks": clocks, "gpu_launches": int(stats["launches"]), "e2e": e2e,
     }
+    if multi:
+        line["extra"] = {"one_call_multi_gpu": multi}
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_ref(a.cpu_sample_mib << 20)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}

@@ -76,6 +76,13 @@ typedef struct b200z_ctx b200z_ctx;
 
 int  b200z_device_count(void);
 int  b200z_create(b200z_ctx **out, int device);
+/* One context over several devices of the box (devices[0] is the primary).  b200z_zstd_compress_host / b200z_zstd_decompress_host --
+ * what ICompressCoder::Code() calls -- then deal batches of whole frames round-robin to the devices, each with its own streams,
+ * staging and scratch, and write the output in input order: the bytes do not depend on the device count.  The other entry points
+ * (device pointers, method 21, digests) run on the primary.  Replaces the worker pool of ZSTDMT_createCompressionJob /
+ * ZSTDMT_flushProduced (C/zstd/zstdmt_compress.c:1403,1488) and MtCoder_Code (C/MtCoder.c:445) one level up. */
+int  b200z_create_multi(b200z_ctx **out, const int *devices, int nDevices);
+int  b200z_device_list(b200z_ctx *ctx, int *devices, int cap);          /* returns the number of devices of the context */
 void b200z_destroy(b200z_ctx *ctx);
 int  b200z_set_param(b200z_ctx *ctx, int param, int64_t value);
 int  b200z_get_param(b200z_ctx *ctx, int param, int64_t *value);

@@ -148,3 +148,22 @@ def test_batch_of_files(codec, pkg):
     parts2, whole2 = c2.compress_batch(files)
     assert whole2 == whole and parts2 == parts
     c2.close()
+
+
+def test_host_batches_and_device_count_are_invisible(pkg):
+    """the host-pointer calls cut their input into batches of whole frames and deal them over the devices of the context: the bytes
+    depend neither on the batch size nor on the number of devices (workers), and the decoder restores the input through the same
+    dispatcher.  Runs with every GPU of the box; on one GPU the same device is listed three times (three workers, own streams and
+    scratch each), which exercises the ordering logic all the same."""
+    import torch
+    data = pkg.corpus.g2(37 * (1 << 20) + 777).tobytes() + bytes(3 << 20) + pkg.corpus.entropy_class(1, 2_000_000).tobytes()
+    want = helpers.oracle_compress(data)
+    n = torch.cuda.device_count()
+    groups = [[0], [0, 0, 0]] + ([list(range(2)), list(range(n))] if n >= 2 else [])
+    for devs in groups:
+        for hb in (22, 24, 30):
+            c = pkg.Codec(devices=devs, host_batch_log=hb)
+            comp = c.compress(data)
+            assert comp == want, (devs, hb, len(comp), len(want))
+            assert c.decompress(comp) == data, (devs, hb)
+            c.close()
