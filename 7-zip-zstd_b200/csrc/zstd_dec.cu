@@ -752,9 +752,17 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
                 const uint64_t mine = lane < cnt ? sq[i0 + lane] : 0ull;
                 const uint32_t ll = lane < cnt ? ((uint32_t)(mine >> 30) & 0x1FFFFu) : 0u;
                 const uint32_t ml = lane < cnt ? ((uint32_t)(mine >> 47) + 3u) : 0u;
-                // 1. repcodes, in order
+                // 1. repcodes.  A batch without repcode sequences (offBase > 3 everywhere: the usual case) needs no walk: every offset is
+                //    explicit and the history is the last three of them; otherwise in order (ZSTD_decodeSequence's rules,
+                //    zstd_decompress_block.c:1290-1312)
                 uint32_t myOff = 0;
-                for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t obMine = (uint32_t)mine & 0x3FFFFFFFu;
+                if (!__any_sync(B2Z_FULL, lane < cnt && obMine <= 3u)) {
+                    myOff = lane < cnt ? obMine - 3u : 0u;
+                    const uint32_t o1 = __shfl_sync(B2Z_FULL, myOff, cnt - 1u), o2 = __shfl_sync(B2Z_FULL, myOff, (cnt - 2u) & 31u), o3 = __shfl_sync(B2Z_FULL, myOff, (cnt - 3u) & 31u);
+                    const uint32_t n2 = cnt >= 2u ? o2 : rep0, n3 = cnt >= 3u ? o3 : (cnt == 2u ? rep0 : rep1);
+                    rep2 = n3; rep1 = n2; rep0 = o1;
+                } else for (uint32_t k = 0; k < cnt; k++) {
                     const uint64_t s = __shfl_sync(B2Z_FULL, mine, k);
                     const uint32_t ob = (uint32_t)s & 0x3FFFFFFFu, llk = (uint32_t)(s >> 30) & 0x1FFFFu;
                     uint32_t offset;
@@ -770,26 +778,38 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
                     }
                     if (lane == k) myOff = offset;
                 }
-                // 2. positions
+                // 2. positions (relative to o, the frame bytes produced before this batch)
                 uint32_t total, litTotal;
                 const uint32_t excl = warp_excl_scan(ll + ml, lane, &total);
                 const uint32_t litExcl = warp_excl_scan(ll, lane, &litTotal);
-                const uint64_t myOut = o + excl, myDst = myOut + ll;                     // frame-relative
+                const uint32_t relDst = excl + ll;
+                const uint64_t myDst = o + relDst;                                       // frame-relative
                 const bool bad = lane < cnt && (myOff == 0 || myOff > myDst || myOff > fr.windowSize);
                 if (__any_sync(B2Z_FULL, bad)) { err = B2Z_DERR_CORRUPT; break; }
-                // 3. literals
-                if (ll <= 32u) { for (uint32_t i = 0; i < ll; i++) out[myOut + i] = lit[lp + litExcl + i]; }
-                for (uint32_t big = __ballot_sync(B2Z_FULL, ll > 32u); big; big &= big - 1u) {
-                    const uint32_t k = (uint32_t)__ffs((int)big) - 1u;
-                    warp_copy_lit(out + __shfl_sync(B2Z_FULL, myOut, k), lit + lp + __shfl_sync(B2Z_FULL, litExcl, k), __shfl_sync(B2Z_FULL, ll, k), lane);
+                // 3. literals.  The batch's literal bytes are contiguous in the literal buffer: lane = byte, 32 per round; byte t belongs to the
+                //    sequence k with litExcl_k <= t < litExcl_k + ll_k (binary search over the lanes' prefix sums) -- one global round trip per
+                //    32 bytes instead of one per byte of the longest run
+                for (uint32_t t0 = 0; t0 < litTotal; t0 += 32u) {
+                    const uint32_t t = t0 + lane;
+                    uint32_t k = 0;
+#pragma unroll
+                    for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(B2Z_FULL, litExcl, (k + st) & 31u); if (k + st < 32u && v <= t) k += st; }
+                    const uint32_t base = __shfl_sync(B2Z_FULL, excl, k), le = __shfl_sync(B2Z_FULL, litExcl, k);
+                    if (t < litTotal) out[o + base + (t - le)] = lit[lp + t];
                 }
-                __syncwarp();
-                // 4. matches that read only bytes produced before this batch
+                // 4. matches that read only bytes produced before this batch: the same flattening over their bytes
                 const bool indep = lane < cnt && (myDst - myOff + ml <= o);
-                if (indep && ml <= 32u) { const uint8_t* m = out + myDst - myOff; for (uint32_t i = 0; i < ml; i++) out[myDst + i] = __ldcg(m + i); }
-                for (uint32_t big = __ballot_sync(B2Z_FULL, indep && ml > 32u); big; big &= big - 1u) {
-                    const uint32_t k = (uint32_t)__ffs((int)big) - 1u;
-                    warp_copy_match(out + __shfl_sync(B2Z_FULL, myDst, k), __shfl_sync(B2Z_FULL, myOff, k), __shfl_sync(B2Z_FULL, ml, k), lane);
+                {
+                    uint32_t indepTotal;
+                    const uint32_t mExcl = warp_excl_scan(indep ? ml : 0u, lane, &indepTotal);
+                    for (uint32_t u0 = 0; u0 < indepTotal; u0 += 32u) {
+                        const uint32_t u = u0 + lane;
+                        uint32_t k = 0;
+#pragma unroll
+                        for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(B2Z_FULL, mExcl, (k + st) & 31u); if (k + st < 32u && v <= u) k += st; }
+                        const uint32_t d = __shfl_sync(B2Z_FULL, relDst, k), of = __shfl_sync(B2Z_FULL, myOff, k), me = __shfl_sync(B2Z_FULL, mExcl, k);
+                        if (u < indepTotal) { uint8_t* q = out + o + d + (u - me); *q = __ldcg(q - of); }
+                    }
                 }
                 __syncwarp();
                 // 5. the rest, in order

@@ -64,7 +64,7 @@ def _payload(pkg, tmp):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,shown", [("-m0=zstd -mx3", "ZSTD:v1.5,l3"), ("-m0=zstd -mx19", "ZSTD:v1.5,l19"), ("-m0=zstd:max", "ZSTD:max"),
+@pytest.mark.parametrize("method,shown", [("-m0=zstd -mx3", "ZSTD:v1.5,l3"), ("-m0=zstd -mx19", "ZSTD:v1.5,l19"), ("-m0=zstd:max", "ZSTD:v1.5,max"),
                                             ("-m0=lzma2 -mx5", "LZMA2:"), ("-m0=flzma2 -mx5", "LZMA2:")])
 def test_archives_written_through_the_module_verify_with_the_stock_reference(host, pkg, tmp_path, method, shown):
     path, data = _payload(pkg, str(tmp_path))
