@@ -31,13 +31,14 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size-mib", type=int, default=4096, help="uncompressed MiB per GPU per step (cfg2: 4 GiB)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample-mib", type=int, default=1024, help="bounded sample for the CPU reference arm")
+    ap.add_argument("--cpu-sample-mib", type=int, default=4096, help="sample for the CPU reference arm (default: the GPU arm's 4 GiB, same config; ~7 s per pass on 128 threads)")
+    ap.add_argument("--no-lzma2-extra", action="store_true", help="skip extra.lzma2 (BASELINE configs[3] measured beside the zstd headline: method 21 as -m0=flzma2 -mx5 selects it)")
     ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
                     help="zstd: method 4F71101 level 3 (the headline, BASELINE configs[1]); lzma2: method 21 (configs[3])")
     ap.add_argument("--level", type=int, default=3, help="--codec zstd: B200Z_P_LEVEL (1-7 stage M, the measured headline; 8-22 the price-based stage C + stage Z)")
-    ap.add_argument("--lzma2-parse", type=int, default=0, choices=[0, 1],
-                    help="--codec lzma2: 0 = greedy parse (the measured round-1 line), 1 = price-based parse (stage C + stage P, DESIGN.md 2c)")
-    ap.add_argument("--frame-log", type=int, default=0, help="log2 of the independent frame / block size (default: the library's, 20)")
+    ap.add_argument("--lzma2-parse", type=int, default=1, choices=[0, 1],
+                    help="--codec lzma2: 1 = price-based parse (stage C + stage P: what levels >= 5 / FLZMA2 >= 3 select in the codec module; the default), 0 = stage F + stage G's parse")
+    ap.add_argument("--frame-log", type=int, default=0, help="log2 of the independent frame / block size (default: 20 for zstd; 23 = the 8 MiB dictionary of flzma2 -mx5 for --codec lzma2)")
     ap.add_argument("--lzma2-slice-log", type=int, default=-1, help="--codec lzma2: log2 of state-reset slices per block (default: the library's, 2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--one-process", action="store_true",
@@ -181,7 +182,7 @@ def main():
     unit_bytes = a.size_mib << 20
     workload = f"zstd level {a.level}, {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 128 KiB blocks"
     if lz:
-        workload = f"LZMA2 / Fast-LZMA2 coder (method 21), {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, 1 MiB dictionary-reset blocks"
+        workload = f"LZMA2 / Fast-LZMA2 coder (method 21), {a.size_mib} MiB synthetic enwik-shape text (generator G2) per GPU, {1 << ((a.frame_log or 23) - 20)} MiB dictionary-reset blocks, parse {a.lzma2_parse}"
 
     if a.impl == "reference":
         if rank != 0:
@@ -229,6 +230,8 @@ def main():
         torch.cuda.synchronize()
 
     codec = pkg.Codec(local)
+    if lz and not a.frame_log:
+        a.frame_log = 23                                            # fl2_compress.c:80: level 5 = 8 MiB dictionary; a frame = one dictionary-reset block
     if a.frame_log:
         codec.set("frame_log", a.frame_log); codec.set("window_log", a.frame_log)
     if not lz and a.level != 3:
@@ -345,6 +348,7 @@ def main():
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "global_uncompressed_bytes_per_step": world * unit_bytes, "frame_log": codec.get("frame_log"),
                    "parallelism": f"{world} independent shard(s), no collective", **({"lzma2_parse": a.lzma2_parse} if lz else {"level": a.level}), "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
+                   "host_batch_log": codec.get("host_batch_log"),
                    "ratio": ratio, "enc_MBps": units_mb / t_enc, "dec_MBps": units_mb / t_dec,
                    "kernel_ms_per_step": {k: v / a.steps for k, v in stats.items() if k != "launches"}},
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -353,6 +357,34 @@ def main():
     }
     if multi:
         line["extra"] = {"one_call_multi_gpu": multi}
+    if not lz and world == 1 and not a.no_lzma2_extra:
+        # BASELINE configs[3] beside the headline: method 21 the way `-m0=flzma2 -mx5` runs it in the codec module (price-based parse,
+        # 8 MiB dictionary-reset blocks), the same 4 GiB resident in HBM, one timed pass after a small warm-up; the reference's FL2 level 5
+        # on a bounded sample of the same text beside it
+        del d_comp, d_back
+        torch.cuda.empty_cache()
+        lc = pkg.Codec(local, lzma2_parse=1, frame_log=23, window_log=23)
+        lb = lc.lzma2_compress_bound(unit_bytes)
+        l_comp = torch.empty(lb, dtype=torch.uint8, device="cuda"); l_back = torch.empty(unit_bytes, dtype=torch.uint8, device="cuda")
+        wn = min(unit_bytes, 256 << 20)
+        c0, p0 = lc.lzma2_compress_device(d_in.data_ptr(), wn, l_comp.data_ptr(), lb); lc.lzma2_decompress_device(l_comp.data_ptr(), c0, p0, l_back.data_ptr(), wn)
+        lc.reset_stats(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); c1, p1 = lc.lzma2_compress_device(d_in.data_ptr(), unit_bytes, l_comp.data_ptr(), lb); t1 = time.perf_counter()
+        nb = lc.lzma2_decompress_device(l_comp.data_ptr(), c1, p1, l_back.data_ptr(), unit_bytes); t2 = time.perf_counter()
+        assert nb == unit_bytes and torch.equal(l_back, d_in), "LZMA2 round trip mismatch"
+        mbs = unit_bytes / 1e6
+        lz_rec = {"workload": f"method 21, price-based parse, 8 MiB dictionary-reset blocks, {a.size_mib} MiB G2 text resident in HBM, 1 pass", "value": mbs / (t2 - t0), "unit": "MB/s",
+                  "enc_MBps": mbs / (t1 - t0), "dec_MBps": mbs / (t2 - t1), "ratio": unit_bytes / c1,
+                  "kernel_ms": {k: lc.stat(v) for k, v in dict(stage_c=1, stage_p=10, stage_r=2, assemble=3, dec_prepass=9, dec=4).items()}}
+        if not a.no_cpu_baseline:
+            try:
+                cb2 = cpu_reference_lzma2(min(unit_bytes, 512 << 20))
+                lz_rec["cpu_baseline"] = {k: cb2[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
+                lz_rec["ratio_delta_vs_reference_pct"] = 100.0 * (lz_rec["ratio"] / cb2["ratio"] - 1.0)
+            except SystemExit as e:
+                lz_rec["cpu_baseline"] = {"unavailable": str(e)[:120]}
+        line.setdefault("extra", {})["lzma2"] = lz_rec
+        lc.close()
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_ref(a.cpu_sample_mib << 20)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
