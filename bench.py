@@ -223,6 +223,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")                      # for waits that must leave the GPUs idle (an NCCL barrier spins on the device)
 
     def barrier():
         if dist:
@@ -312,12 +313,14 @@ def main():
     multi = None
     if dist and not lz and not a.no_e2e:
         barrier()
+        if rank != 0:
+            codec.close(); del d_in, d_comp, d_back; torch.cuda.empty_cache()      # the other ranks leave their GPUs to rank 0's context ...
         if rank == 0:
             try:
                 multi = one_call_multi_gpu(pkg, list(range(world)), host_in, unit_bytes, max(1, min(a.steps, 3)))
             except Exception as e:                                   # e.g. ranks not on devices 0..N-1 of this process's view
                 multi = {"error": str(e)[:200]}
-        barrier()
+        dist.barrier(group=cpu_group)                                # ... and wait on the CPU
     if rank != 0:
         if dist:
             dist.destroy_process_group()
