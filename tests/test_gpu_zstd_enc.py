@@ -167,3 +167,26 @@ def test_host_batches_and_device_count_are_invisible(pkg):
             assert comp == want, (devs, hb, len(comp), len(want))
             assert c.decompress(comp) == data, (devs, hb)
             c.close()
+
+
+def test_more_than_4_gib_in_one_call(pkg):
+    """4.5 GiB through one host-pointer compress and one decompress call: offsets past 2^32, several pipeline batches.  Frames are
+    independent, so the first and the last frames must equal the oracle's frames of the same bytes; the whole must round-trip."""
+    import torch
+    n = (9 << 29) + 12345
+    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    pkg.corpus.g2_into(host.data_ptr(), n)
+    c = pkg.Codec(0)
+    bound = c.compress_bound(n)
+    comp = torch.empty(bound, dtype=torch.uint8).pin_memory()
+    m = c.compress_into(host.data_ptr(), n, comp.data_ptr(), bound)
+    data = host.numpy()
+    first = helpers.oracle_compress(data[:1 << 20].tobytes())
+    assert comp[:len(first)].numpy().tobytes() == first
+    tail_start = (n >> 20) << 20
+    last = helpers.oracle_compress(data[tail_start:].tobytes())
+    assert comp[m - len(last):m].numpy().tobytes() == last
+    back = torch.empty(n, dtype=torch.uint8).pin_memory()
+    assert c.decompress_into(comp.data_ptr(), m, back.data_ptr(), n) == n
+    assert torch.equal(back, host)
+    c.close()
