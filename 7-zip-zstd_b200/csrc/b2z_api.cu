@@ -304,6 +304,7 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
     return 0;
 }
 
+extern "C" size_t b200z_lzma2_compress_bound(b200z_ctx* ctx, size_t srcSize);
 static const uint8_t kEmptyFrame[9] = { 0x28, 0xB5, 0x2F, 0xFD, 0x20, 0x00, 0x01, 0x00, 0x00 };
 
 extern "C" {
@@ -343,6 +344,7 @@ int b200z_zstd_compress_device(b200z_ctx* ctx, const void* d_src, size_t srcSize
 // ---- a host-pointer compress shared by the devices of a context
 struct EncJob {
     const uint8_t* src = nullptr; size_t srcSize = 0; uint8_t* dst = nullptr; uint64_t batch = 0, nItems = 0;
+    int codec = 0;                                               // 0 zstd frames; 1 LZMA2 chunk stream (every batch but the last drops its end marker)
     std::mutex m; std::condition_variable cv;
     std::vector<uint64_t> size; std::vector<char> known;         // compressed bytes of every batch, once known
     int rc = 0; b200z_ctx* errCtx = nullptr;                     // first error
@@ -362,7 +364,7 @@ static void enc_worker(b200z_ctx* ctx, EncJob* job, uint64_t first, uint64_t str
     auto run = [&]() -> int {
         CU(cudaSetDevice(ctx->device));
         const uint64_t batch = job->batch;
-        const size_t batchBound = b200z_zstd_compress_bound(ctx, batch);
+        const size_t batchBound = ((job->codec == 1 ? b200z_lzma2_compress_bound(ctx, batch) : b200z_zstd_compress_bound(ctx, batch)) + 255) & ~(size_t)255;
         if (ctx->dIn.reserve(2 * (batch + 64)) || ctx->dOut.reserve(2 * batchBound)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
         uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + batch + 64 };
         uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + batchBound };
@@ -381,8 +383,9 @@ static void enc_worker(b200z_ctx* ctx, EncJob* job, uint64_t first, uint64_t str
             CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));                 // input there
             if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0)); // output buffer drained
             uint64_t produced = 0;
-            int rc = enc_batch(ctx, dIn[b], bsize(i), dOut[b], &produced, false);   // synchronises ctx->stream
+            int rc = enc_batch(ctx, dIn[b], bsize(i), dOut[b], &produced, false, nullptr, 0, job->codec);   // synchronises ctx->stream
             if (rc) return rc;
+            if (job->codec == 1 && i + 1 < job->nItems) produced -= 1;            // the next batch's chunks follow directly: no end marker in between
             job->publish(i, produced);
             uint64_t off = 0;
             if (!job->offset_of(i, &off)) return 0;                              // another device failed: its error is the job's
@@ -624,6 +627,27 @@ int b200z_lzma2_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, v
     uint64_t batch = 1ull << ctx->hostBatchLog;
     if ((ctx->geom.flags & B2Z_FLAG_LZ2_OPT) && batch > (1ull << 30)) batch = 1ull << 30;
     if (batch < F) batch = F;
+    const uint64_t nDev = 1 + ctx->peers.size();
+    if (nDev > 1) {                                              // about four batches per device, none smaller than a frame per SM (or 16 frames for large frames)
+        uint64_t per = (srcSize + 4 * nDev - 1) / (4 * nDev), floorB = (F >= (1ull << 23) ? 16ull : (uint64_t)ctx->smCount) * F;
+        if (per < floorB) per = floorB;
+        per = (per + F - 1) / F * F;
+        if (per < batch) batch = per;
+    }
+    if (nDev > 1 && srcSize > batch) {
+        // batches of whole dictionary-reset blocks dealt over the devices (the role of MtCoder_Code, MtCoder.c:445, one level up)
+        EncJob job; job.src = (const uint8_t*)src; job.srcSize = srcSize; job.dst = (uint8_t*)dst; job.batch = batch; job.codec = 1;
+        job.nItems = (srcSize + batch - 1) / batch; job.size.assign(job.nItems, 0); job.known.assign(job.nItems, 0);
+        const uint64_t nWorkers = nDev < job.nItems ? nDev : job.nItems;
+        std::vector<std::thread> threads;
+        for (uint64_t d = 1; d < nWorkers; d++) threads.emplace_back(enc_worker, ctx->peers[d - 1], &job, d, nWorkers);
+        enc_worker(ctx, &job, 0, nWorkers);
+        for (std::thread& t : threads) t.join();
+        if (job.rc) { if (job.errCtx && job.errCtx != ctx) snprintf(ctx->err, sizeof(ctx->err), "device %d: %.200s", job.errCtx->device, job.errCtx->err); return job.rc; }
+        size_t total = 0; for (uint64_t v : job.size) total += (size_t)v;
+        *dstSize = total;
+        return 0;
+    }
     const uint64_t maxIn = srcSize < batch ? srcSize : batch;
     if (ctx->dIn.reserve(maxIn + 64) || ctx->dOut.reserve(b200z_lzma2_compress_bound(ctx, maxIn)) || ctx->ready.reserve(256))
         return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");

@@ -68,3 +68,19 @@ def test_large_roundtrip_property(codec, pkg):
     assert codec.lzma2_stream_info(comp)[1] == 96
     out = codec.lzma2_decompress(comp, prop)
     assert np.array_equal(np.frombuffer(out, dtype=np.uint8), data)
+
+
+def test_device_count_is_invisible(pkg):
+    """method 21 through a context over several workers (every GPU of the box; one GPU listed twice where there is only one):
+    batches of whole dictionary-reset blocks are dealt over them and stitched without end markers in between -- the chunk stream
+    equals the single-device / oracle stream"""
+    import torch
+    data = pkg.corpus.g2(40 * (1 << 20) + 4321).tobytes()
+    oprop, want = helpers.oracle_lzma2_compress(data, frameLog=17, windowLog=17)
+    n = torch.cuda.device_count()
+    for devs in ([0, 0], list(range(n)) if n >= 2 else [0, 0, 0]):
+        c = pkg.Codec(devices=devs, frame_log=17)
+        prop, comp = c.lzma2_compress(data)
+        assert prop == oprop and comp == want, devs
+        assert c.lzma2_decompress(comp, prop) == data
+        c.close()
