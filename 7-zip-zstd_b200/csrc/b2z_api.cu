@@ -104,7 +104,10 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
     switch (param) {
     case B200Z_P_LEVEL:     if (v < 1 || v > 22) return fail(ctx, B200Z_E_PARAM, "level out of range%s"); ctx->level = (int)v;
                             // levels 1-7: the level-3-class greedy/lazy stage M; 8-22: the price-based stage C + stage Z
-                            ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v >= B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
+                            ctx->geom.flags = (ctx->geom.flags & ~(B2Z_FLAG_ZSTD_OPT | B2Z_FLAG_FIND_FAST | B2Z_FLAG_FIND_STEP)) | (v >= B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_ZSTD_OPT : 0u) | b2z_level_find_flags((int)v);
+                            // the level ladder of stage F (b2z_params.h): 1-2 the short table alone, in the long table's room; 3-4 both; 5-7 both + same-step lanes
+                            ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = (ctx->geom.flags & B2Z_FLAG_FIND_FAST) ? B2Z_DEF_HASHLOG_L : B2Z_DEF_HASHLOG_S;
+                            return 0;
     case B200Z_P_ZSTD_PARSE: if (v < 0 || v > 1) return fail(ctx, B200Z_E_PARAM, "zstd parse mode out of range%s");
                             ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
     case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");

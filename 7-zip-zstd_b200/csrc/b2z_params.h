@@ -68,6 +68,14 @@
 /* flags bit 5: the Zstandard encoder parses by price (stage C candidates + stage Z dynamic programme per block) instead of stage M */
 #define B2Z_FLAG_ZSTD_OPT 0x20u
 #define B2Z_ZSTD_OPT_LEVEL 8       /* B200Z_P_LEVEL at or above this selects it */
+/* the level ladder below it (the strategies of clevels.h:27-50 as far as stage F has them):
+ *   levels 1-2 and the fast levels: bit 6 -- only the short (5-byte hash) table, grown to 2^15 entries: the role of ZSTD_fast
+ *   levels 3-4: both tables: ZSTD_dfast
+ *   levels 5-7: bit 7 -- a position also sees the lower positions of its own 32-position step (two __match_any_sync per step):
+ *               nearer candidates on data with short-distance repeats, for about twice stage F's time */
+#define B2Z_FLAG_FIND_FAST 0x40u
+#define B2Z_FLAG_FIND_STEP 0x80u
+B2Z_HD uint32_t b2z_level_find_flags(int level) { return level <= 2 ? B2Z_FLAG_FIND_FAST : (level >= 5 && level < B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_FIND_STEP : 0u); }
 
 /* digests (b2z_crc.cu): reflected polynomials of CRC-32 (C/7zCrc.c) and CRC-64/XZ (C/XzCrc64.c) */
 #define B2Z_CRC32_POLY 0xEDB88320u

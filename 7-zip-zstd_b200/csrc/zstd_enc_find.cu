@@ -47,7 +47,9 @@ __device__ __forceinline__ uint32_t match_len16(const uint64_t* __restrict__ w, 
     return len < maxLen ? len : maxLen;
 }
 
-template <int WPG, int G>
+// MODE 0: both tables (levels 3-4); 1: only the short table (levels 1-2, fast levels); 2: both tables + the lower lanes of a
+// position's own step (levels 5-7) -- b2z_params.h: B2Z_FLAG_FIND_FAST / B2Z_FLAG_FIND_STEP
+template <int WPG, int G, int MODE>
 __global__ void __launch_bounds__(WPG * G * 32, 1)
 zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cand,
                      const volatile uint32_t* ready, uint32_t readyShift, uint32_t* __restrict__ errFlag) {
@@ -55,10 +57,11 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
     constexpr uint32_t CH = WPG * 32u, NT = CH * G;
     static_assert(G >= 2 && G <= 7, "named barriers 1..7 and 8..14");
     const uint32_t tid = threadIdx.x, grp = tid / CH, tg = tid % CH;
+    constexpr bool FAST = MODE == 1, STEP = MODE == 2;
     const uint32_t HL = g.hashLogL, HS = g.hashLogS;
-    uint32_t* const TL = smem;
-    uint32_t* const TS = smem + (1u << HL);
-    const uint32_t tableWords = (1u << HL) + (1u << HS);
+    uint32_t* const TL = smem;                                                // (MODE 1 keeps no long table: the short one starts the buffer)
+    uint32_t* const TS = smem + (MODE == 1 ? 0u : (1u << HL));
+    const uint32_t tableWords = (MODE == 1 ? 0u : (1u << HL)) + (1u << HS);
     const uint32_t tagBits = 32u - (g.frameLog + 1u), tagMask = (1u << tagBits) - 1u;
     const uint32_t W = g.windowLog >= 32 ? 0xFFFFFFFFu : (1u << g.windowLog);
     const uint64_t nFrames = (srcSize + (1ull << g.frameLog) - 1) >> g.frameLog;
@@ -99,14 +102,26 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
             const uint32_t tL = (uint32_t)(hl >> (64u - HL - tagBits)) & tagMask, tS = (uint32_t)(hs >> (64u - HS - tagBits)) & tagMask;
             const uint32_t mineL = ((p + 1u) << tagBits) | tL, mineS = ((p + 1u) << tagBits) | tS;
             uint32_t* const aL = TL + iL; uint32_t* const aS = TS + iS;
-            turn_inputs_ready(smem + tableWords + tid, iL, iS, mineL, mineS, (uint32_t)hashable);
+            uint32_t lowL = 0, lowS = 0;
+            if (STEP) {                                                        // lanes of this step with my table index, below me
+                const uint32_t lane = tid & 31u, lt = (1u << lane) - 1u;
+                lowL = __match_any_sync(B2Z_FULL, hashable ? iL : (0x80000000u | lane)) & lt;
+                lowS = __match_any_sync(B2Z_FULL, hashable ? iS : (0x80000000u | lane)) & lt;
+            }
+            turn_inputs_ready(smem + tableWords + tid, iL, iS, mineL, mineS, (uint32_t)hashable ^ lowL ^ (lowS << 1));
             // ---- the turn: nothing but the table accesses between the two barrier hops
             bar_sync(B2Z_FIND_BAR_TURN(grp), 2u * CH);
             uint32_t eL = 0, eS = 0;
-            if (hashable) { eL = *aL; eS = *aS; }
+            if (hashable) { if (!FAST) eL = *aL; eS = *aS; }
             if (WPG > 1) bar_sync(B2Z_FIND_BAR_GRP(grp), CH); else __syncwarp();
-            if (hashable) { atomicMax(aL, mineL); atomicMax(aS, mineS); }     // the highest position of the chunk stays
+            if (hashable) { if (!FAST) atomicMax(aL, mineL); atomicMax(aS, mineS); }     // the highest position of the chunk stays
             bar_arrive(B2Z_FIND_BAR_TURN(nextGrp), 2u * CH);
+            if (STEP) {                                                        // a lower lane of the step with my index is nearer than the table's entry
+                const uint32_t fromL = __shfl_sync(B2Z_FULL, mineL, lowL ? 31 - __clz((int)lowL) : 0);
+                const uint32_t fromS = __shfl_sync(B2Z_FULL, mineS, lowS ? 31 - __clz((int)lowS) : 0);
+                if (lowL) eL = fromL;
+                if (lowS) eS = fromS;
+            }
             // ---- after the turn: the next iteration's bytes are requested before this one's candidates are compared
             vNext = ld64u(w, p + G * CH, nWords);
             uint32_t word = 0;
@@ -130,16 +145,25 @@ zstd_enc_find_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom 
 }
 
 #ifndef B2Z_CUEMU
-size_t zstd_enc_find_smem_bytes(const EncGeom& g) { return (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS) + 1024u) * 4u; }   // tables + one scratch word per thread
+size_t zstd_enc_find_smem_bytes(const EncGeom& g) {          // tables + one scratch word per thread
+    return (((g.flags & B2Z_FLAG_FIND_FAST) ? 0 : ((size_t)1 << g.hashLogL)) + ((size_t)1 << g.hashLogS) + 1024u) * 4u;
+}
 
+template <int WPG, int G, int MODE>
+static cudaError_t launch_find_m(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,
+                                 const uint32_t* ready, uint32_t readyShift, uint32_t* errFlag, cudaStream_t st) {
+    const size_t smem = zstd_enc_find_smem_bytes(g);
+    cudaError_t e = cudaFuncSetAttribute(zstd_enc_find_kernel<WPG, G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set on every launch
+    if (e != cudaSuccess) return e;
+    zstd_enc_find_kernel<WPG, G, MODE><<<nCtas, WPG * G * 32, smem, st>>>(src, srcSize, g, cand, ready, readyShift, errFlag);
+    return cudaGetLastError();
+}
 template <int WPG, int G>
 static cudaError_t launch_find_t(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,
                                  const uint32_t* ready, uint32_t readyShift, uint32_t* errFlag, cudaStream_t st) {
-    const size_t smem = zstd_enc_find_smem_bytes(g);
-    cudaError_t e = cudaFuncSetAttribute(zstd_enc_find_kernel<WPG, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: set on every launch
-    if (e != cudaSuccess) return e;
-    zstd_enc_find_kernel<WPG, G><<<nCtas, WPG * G * 32, smem, st>>>(src, srcSize, g, cand, ready, readyShift, errFlag);
-    return cudaGetLastError();
+    if (g.flags & B2Z_FLAG_FIND_FAST) return launch_find_m<WPG, G, 1>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
+    if (g.flags & B2Z_FLAG_FIND_STEP) return launch_find_m<WPG, G, 2>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
+    return launch_find_m<WPG, G, 0>(src, srcSize, g, cand, nCtas, ready, readyShift, errFlag, st);
 }
 
 cudaError_t launch_zstd_enc_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t nCtas,

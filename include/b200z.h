@@ -39,7 +39,9 @@ extern "C" {
 #define B200Z_E_CHECKSUM   -8   /* content checksum mismatch                 (S_FALSE)       */
 
 /* parameters (b200z_set_param) */
-#define B200Z_P_LEVEL       1   /* 1..22.  1-7: the level-3-class path (stage F finder + stage G parse); 8-22: the price-based parse on stage C's candidates (sets B200Z_P_ZSTD_PARSE) */
+#define B200Z_P_LEVEL       1   /* 1..22.  Stage F + stage G with the finder's rung chosen as ZSTD_getCParams picks a strategy (clevels.h:27-50): 1-2 the short table
+                                   alone (ZSTD_fast's role), 3-4 both tables (ZSTD_dfast), 5-7 both + the lower lanes of a position's own step (nearer candidates, twice
+                                   the finder time); 8-22: the price-based parse on stage C's candidates (sets B200Z_P_ZSTD_PARSE) */
 #define B200Z_P_FRAMELOG    2   /* log2 of the independent frame ("job") size, 17..24, default 20       */
 #define B200Z_P_HASHLOG_L   3   /* stage F: log2 entries of the long (8-byte hash) table, 8..15, default 15; both tables live in one SM's shared memory */
 #define B200Z_P_HASHLOG_S   4   /* stage F: log2 entries of the short (5-byte hash) table, 8..15, default 14 (2^L + 2^S <= 49152)       */

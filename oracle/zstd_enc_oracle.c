@@ -42,9 +42,10 @@ static inline void wr24(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uin
 static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 
 void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
-    (void)level;
     p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
     p->windowLog = B2Z_DEF_FRAMELOG; p->chunkLog = B2Z_DEF_CHUNKLOG; p->flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);
+    p->flags |= b2z_level_find_flags(level) | (level >= B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_ZSTD_OPT : 0u);      /* what B200Z_P_LEVEL sets */
+    if (p->flags & B2Z_FLAG_FIND_FAST) p->hashLogS = B2Z_DEF_HASHLOG_L;                                     /* the single table takes the long table's room */
 }
 
 size_t b2zo_zstd_compress_bound(size_t n, const b2zo_enc_params *p) {
@@ -81,6 +82,7 @@ void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P
     const uint32_t HL = P->hashLogL, HS = P->hashLogS, CH = 1u << P->chunkLog;
     const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
     const uint64_t W = P->windowLog >= 32 ? 0xFFFFFFFFull : (1ull << P->windowLog);
+    const int FAST = (P->flags & B2Z_FLAG_FIND_FAST) != 0, STEP = (P->flags & B2Z_FLAG_FIND_STEP) != 0;
     uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
     uint32_t *iL = (uint32_t *)malloc(CH * 4), *iS = (uint32_t *)malloc(CH * 4), *eLn = (uint32_t *)malloc(CH * 4), *eSn = (uint32_t *)malloc(CH * 4);
     for (uint32_t c0 = 0; c0 < n; c0 += CH) {
@@ -93,7 +95,11 @@ void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P
             iL[k] = (uint32_t)(hl >> (64 - HL)); iS[k] = (uint32_t)(hs >> (64 - HS));
             const uint32_t tL = (uint32_t)(hl >> (64 - HL - tagBits)) & tagMask, tS = (uint32_t)(hs >> (64 - HS - tagBits)) & tagMask;
             eLn[k] = ((p + 1) << tagBits) | tL; eSn[k] = ((p + 1) << tagBits) | tS;
-            const uint32_t eL = TL[iL[k]], eS = TS[iS[k]];                    /* the tables as they stood before this chunk */
+            uint32_t eL = FAST ? 0u : TL[iL[k]], eS = TS[iS[k]];             /* the tables as they stood before this chunk */
+            if (STEP) for (uint32_t q = p & ~31u; q < p; q++) {                /* levels 5-7: nearer, the lower positions of the same 32-position step */
+                if (!FAST && iL[q - c0] == iL[k]) eL = eLn[q - c0];
+                if (iS[q - c0] == iS[k]) eS = eSn[q - c0];
+            }
             const uint32_t segEnd = ((p | (B2Z_SEG - 1)) + 1) < n ? ((p | (B2Z_SEG - 1)) + 1) : n;
             uint32_t maxLen = segEnd - p; if (maxLen > B2Z_CAP) maxLen = B2Z_CAP;
             uint32_t lenL = 0, offL = 0, lenS = 0, offS = 0;

@@ -19,7 +19,7 @@ using namespace b2z;
 
 static EncGeom geom(uint32_t frameLog, uint32_t windowLog, uint32_t chunkLog, uint32_t flags) {
     EncGeom g; memset(&g, 0, sizeof(g));
-    g.frameLog = frameLog; g.hashLogL = B2Z_DEF_HASHLOG_L; g.hashLogS = B2Z_DEF_HASHLOG_S; g.windowLog = windowLog; g.flags = flags; g.chunkLog = chunkLog; g.frameSizes = nullptr;
+    g.frameLog = frameLog; g.hashLogL = B2Z_DEF_HASHLOG_L; g.hashLogS = (flags & B2Z_FLAG_FIND_FAST) ? B2Z_DEF_HASHLOG_L : B2Z_DEF_HASHLOG_S; g.windowLog = windowLog; g.flags = flags; g.chunkLog = chunkLog; g.frameSizes = nullptr;
     return g;
 }
 
@@ -27,14 +27,19 @@ extern "C" {
 
 // stage F (zstd_enc_find_kernel): candidate words, frames back to back; nCtas CTAs loop over the frames
 static uint64_t run_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t nCtas, uint32_t* cand) {
-    const size_t smem = (((size_t)1 << g.hashLogL) + ((size_t)1 << g.hashLogS) + 1024u) * 4u;
+    const size_t smem = (((g.flags & B2Z_FLAG_FIND_FAST) ? 0 : ((size_t)1 << g.hashLogL)) + ((size_t)1 << g.hashLogS) + 1024u) * 4u;
     uint32_t err = 0;
+    const int mode = (g.flags & B2Z_FLAG_FIND_FAST) ? 1 : ((g.flags & B2Z_FLAG_FIND_STEP) ? 2 : 0);
+#define EMU_FIND(WPG, G) (mode == 1 ? cuemu::launch(dim3(nCtas), dim3(WPG * G * 32), smem, [&] { zstd_enc_find_kernel<WPG, G, 1>(src, srcSize, g, cand, nullptr, 0, &err); }) \
+                        : mode == 2 ? cuemu::launch(dim3(nCtas), dim3(WPG * G * 32), smem, [&] { zstd_enc_find_kernel<WPG, G, 2>(src, srcSize, g, cand, nullptr, 0, &err); }) \
+                                    : cuemu::launch(dim3(nCtas), dim3(WPG * G * 32), smem, [&] { zstd_enc_find_kernel<WPG, G, 0>(src, srcSize, g, cand, nullptr, 0, &err); }))
     switch (g.chunkLog) {
-    case 5: return cuemu::launch(dim3(nCtas), dim3(7 * 32), smem, [&] { zstd_enc_find_kernel<1, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
-    case 6: return cuemu::launch(dim3(nCtas), dim3(14 * 32), smem, [&] { zstd_enc_find_kernel<2, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
-    case 7: return cuemu::launch(dim3(nCtas), dim3(28 * 32), smem, [&] { zstd_enc_find_kernel<4, 7>(src, srcSize, g, cand, nullptr, 0, &err); });
-    case 8: return cuemu::launch(dim3(nCtas), dim3(32 * 32), smem, [&] { zstd_enc_find_kernel<8, 4>(src, srcSize, g, cand, nullptr, 0, &err); });
+    case 5: return EMU_FIND(1, 7);
+    case 6: return EMU_FIND(2, 7);
+    case 7: return EMU_FIND(4, 7);
+    case 8: return EMU_FIND(8, 4);
     }
+#undef EMU_FIND
     return 0;
 }
 uint64_t emu_zstd_enc_find(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t chunkLog, uint32_t flags, uint32_t nCtas, uint32_t* cand) {

@@ -56,6 +56,22 @@ def test_emulated_stage_f_equals_the_oracle(pkg, emu, fl, cl, ctas):
     assert int((want != 0).sum()) > n // 4
 
 
+@pytest.mark.parametrize("level,flag", [(1, 0x40), (6, 0x80)])
+def test_emulated_stage_f_level_ladder(pkg, emu, level, flag):
+    """the other rungs of stage F's ladder: levels 1-2 keep only the short table (in the long table's room), levels 5-7 let a position
+    see the lower lanes of its own step (__match_any_sync) -- kernel == oracle for both"""
+    data = _mixed(pkg, 120_000) + b"0123456789" * 2000; n = len(data); fl = 17
+    src = np.frombuffer(data + bytes(64), dtype=np.uint8)
+    p = H.EncParams(); H.oracle().b2zo_enc_default_params(ctypes.byref(p), level)
+    assert p.flags & 0xC0 == flag
+    want = H.oracle_candidates(data, frameLog=fl, windowLog=fl, flags=p.flags, hashLogS=p.hashLogS)
+    got = np.full(((n + (1 << fl) - 1) >> fl << fl) + 16, 0xCDCDCDCD, dtype=np.uint32)
+    emu.emu_zstd_enc_find(src.ctypes.data, n, fl, fl, 7, p.flags, 2, got.ctypes.data)
+    assert np.array_equal(got[:n], want)
+    base = H.oracle_candidates(data, frameLog=fl, windowLog=fl)
+    assert not np.array_equal(base, want)
+
+
 def test_emulated_stage_f_g_edge_inputs(pkg, emu):
     """tiny, ragged and degenerate frames through stage F + stage G: fewer bytes than a hash, one repeated byte (the RLE-block
     sequence), a block that ends one byte into a segment, long matches that stage G extends past B2Z_CAP"""

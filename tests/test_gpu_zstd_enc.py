@@ -190,3 +190,23 @@ def test_more_than_4_gib_in_one_call(pkg):
     assert c.decompress_into(comp.data_ptr(), m, back.data_ptr(), n) == n
     assert torch.equal(back, host)
     c.close()
+
+
+def test_level_ladder_matches_oracle(pkg, inputs):
+    """B200Z_P_LEVEL below the price-based levels selects stage F's rung (1-2: the short table alone; 3-4: both tables; 5-7: both +
+    the lower lanes of a position's step): frames equal the oracle run with the same level's parameters, the reference decoder restores
+    them, and the ladder orders the sizes on data with near repeats"""
+    import ctypes
+    data = inputs["mixed"] + inputs["g2_1m"] + b"0123456789abcdef" * 5000
+    sizes = {}
+    for level in (1, 2, 3, 4, 5, 7):
+        p = helpers.EncParams(); helpers.oracle().b2zo_enc_default_params(ctypes.byref(p), level)
+        c = pkg.Codec(0, level=level)
+        comp = c.compress(data)
+        assert comp == helpers.oracle_compress(data, flags=p.flags, hashLogS=p.hashLogS), level
+        if helpers.ref_available():
+            assert helpers.ref_decompress(comp, len(data)) == data, level
+        sizes[level] = len(comp)
+        c.close()
+    assert sizes[1] == sizes[2] and sizes[3] == sizes[4] and sizes[5] == sizes[7]
+    assert sizes[1] > sizes[3] >= sizes[5], sizes
