@@ -34,8 +34,8 @@ struct b200z_ctx {
                                       // (one warp per frame in its execute stage) takes batches twice as large
     b2z::EncGeom geom{};
     int level = 3;
-    uint32_t batchLog = 30;           // bytes per kernel batch of the device-pointer entry points: 1 GiB keeps the scratch (9.5 bytes per batch byte: candidate
-                                      // words 4, choices 1, sequences 2, literals 1, block slots 1.5) near 10 GiB whatever the input size
+    uint32_t batchLog = 31;           // bytes per kernel batch of the device-pointer entry points: 2 GiB keeps the scratch (9.5 bytes per batch byte: candidate
+                                      // words 4, choices 1, sequences 2, literals 1, block slots 1.5) near 19 GiB whatever the input size (1 GiB batches cost 4 % of speed)
     uint32_t smCount = 148;
     int lz2Mode = 0;                  // LZMA2 decoder literal-model placement: 0 auto, 1 shared memory, 2 global memory
     Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready, batchStage, batchOff, batchSize, cand, choice;

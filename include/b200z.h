@@ -48,7 +48,7 @@ extern "C" {
 #define B200Z_P_WINDOWLOG   5   /* max match distance log, default = frameLog                            */
 #define B200Z_P_FLAGS       6   /* bit0: skippable size hint before each frame (mcmilk MT convention; default on)
                                    bit1: XXH64 content checksum per frame (ZstdHandler.cpp:275 sets it for .zst) */
-#define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 30 (1 GiB; scratch = 9.5 x that) */
+#define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 31 (2 GiB; scratch = 9.5 x that) */
 #define B200Z_P_CHUNKLOG    9   /* stage F: log2 positions per table turn (reads of a chunk precede its writes), 5..8, default 7 */
 #define B200Z_P_LZMA2_MODEL 10  /* LZMA2 decoder: literal model in 1 = shared memory (13 warps/SM), 2 = global memory (32 warps/SM), 0 = by block count */
 #define B200Z_P_LZMA2_SLICELOG 11 /* LZMA2 encoder: log2 of the state-reset slices a block's range coding is split into (0..3, default 2):
