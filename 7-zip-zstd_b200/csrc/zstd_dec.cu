@@ -604,9 +604,25 @@ zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBl
 }
 
 // ---------------------------------------------------------------- D1b: one thread per stream
-__global__ void __launch_bounds__(128)
+// Literal streams.  The decoding tables (up to 4 KiB per block, 128 MB for the 32 768 blocks of 4 GiB) do not fit L2 while every stream
+// of the input is in flight, and a look-up per symbol from HBM was what this kernel waited for (26.6 ms per 4 GiB).  A CTA therefore
+// serves LIT_BLOCKS blocks (4 streams each) and first copies their tables into shared memory: the per-symbol chain is then two shifts,
+// one shared-memory load and an add.
+#define B2Z_LIT_BLOCKS 16u
+__global__ void __launch_bounds__(B2Z_LIT_BLOCKS * 4u)
 zstd_dec_lit_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBlock* __restrict__ blocks, uint32_t nBlocks,
                             uint8_t* __restrict__ lits, const uint16_t* __restrict__ hufTabs, const LitJob* __restrict__ litJobs) {
+    B2Z_EXTERN_SMEM(uint16_t, smTab);                                   // [B2Z_LIT_BLOCKS][2048]
+    const uint32_t b0 = blockIdx.x * B2Z_LIT_BLOCKS;
+    {   // stage the tables of this CTA's blocks (16-byte copies; a block without Huffman streams has none)
+        const uint4* g4 = reinterpret_cast<const uint4*>(hufTabs + (size_t)b0 * 2048u);
+        uint4* s4 = reinterpret_cast<uint4*>(smTab);
+        for (uint32_t i = threadIdx.x; i < B2Z_LIT_BLOCKS * 256u; i += B2Z_LIT_BLOCKS * 4u) {
+            const uint32_t bb = b0 + (i >> 8);
+            if (bb < nBlocks) { const LitJob jj = litJobs[bb]; if (jj.streams && (i & 255u) < ((1u << jj.hufBits) + 7u) / 8u) s4[i] = __ldg(g4 + i); }
+        }
+    }
+    __syncthreads();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t bi = t >> 2, k = t & 3u;
     if (bi >= nBlocks) return;
@@ -614,7 +630,7 @@ zstd_dec_lit_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
     if (!j.streams || blocks[bi].type != 2) return;
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
     uint8_t* lit = lits + (size_t)bi * 131072u;
-    const uint16_t* __restrict__ tab = hufTabs + (size_t)bi * 2048u;
+    const uint16_t* tab = smTab + (size_t)(bi - b0) * 2048u;
     bool ok = true;
     uint64_t off = 0; uint32_t size = 0, cnt = 0; uint8_t* dst = lit;
     if (j.size == 0xFFFFFFFFu) ok = false;
@@ -640,9 +656,27 @@ zstd_dec_lit_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
         if (b.init(&S, off, size)) ok = false;
         else {
             const uint32_t mb = j.hufBits;
-            for (uint32_t i = 0; i < cnt; i++) {
+            // symbols are gathered eight at a time and stored as one aligned word (head and tail byte by byte): every lane writes its own stream
+            uint32_t i = 0;
+            const uint32_t head = (uint32_t)((8u - ((uintptr_t)dst & 7u)) & 7u);
+            for (; i < cnt && i < head; i++) {
                 if (b.consumed > 64u - 11u) b.reload();
-                const uint32_t e = __ldg(tab + (uint32_t)((b.cont << b.consumed) >> (64u - mb)));
+                const uint32_t e = tab[(uint32_t)((b.cont << b.consumed) >> (64u - mb))];
+                dst[i] = (uint8_t)e; b.consumed += (e >> 8);
+            }
+            for (; i + 8u <= cnt; i += 8u) {
+                uint64_t acc = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < 8u; q++) {
+                    if (b.consumed > 64u - 11u) b.reload();
+                    const uint32_t e = tab[(uint32_t)((b.cont << b.consumed) >> (64u - mb))];
+                    acc |= (uint64_t)(e & 255u) << (8u * q); b.consumed += (e >> 8);
+                }
+                *reinterpret_cast<uint64_t*>(dst + i) = acc;
+            }
+            for (; i < cnt; i++) {
+                if (b.consumed > 64u - 11u) b.reload();
+                const uint32_t e = tab[(uint32_t)((b.cont << b.consumed) >> (64u - mb))];
                 dst[i] = (uint8_t)e; b.consumed += (e >> 8);
             }
             ok = b.left() == 0;
@@ -877,7 +911,8 @@ void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blo
     if (stLit != st) { cudaEventRecord(evFork, st); cudaStreamWaitEvent(stLit, evFork, 0); }
     { uint32_t grid = (nBlocks + D1_WARPS(0) - 1) / D1_WARPS(0); if (grid > 148u * 16u) grid = 148u * 16u;
       zstd_dec_entropy_kernel<0><<<grid, D1_WARPS(0) * 32, 0, stLit>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs, seqTabs, seqJobs);
-      zstd_dec_lit_streams_kernel<<<(nBlocks * 4u + 127u) / 128u, 128, 0, stLit>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs); }
+      cudaFuncSetAttribute(zstd_dec_lit_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B2Z_LIT_BLOCKS * 4096u));
+      zstd_dec_lit_streams_kernel<<<(nBlocks + B2Z_LIT_BLOCKS - 1u) / B2Z_LIT_BLOCKS, B2Z_LIT_BLOCKS * 4u, B2Z_LIT_BLOCKS * 4096u, stLit>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs); }
     { uint32_t grid = (nBlocks + D1_WARPS(1) - 1) / D1_WARPS(1); if (grid > 148u * 16u) grid = 148u * 16u;
       zstd_dec_entropy_kernel<1><<<grid, D1_WARPS(1) * 32, 0, st>>>(src, srcSize, blocks, nBlocks, lits, hufTabs, litJobs, seqTabs, seqJobs);
       zstd_dec_seq_streams_kernel<<<(nBlocks + 127u) / 128u, 128, 0, st>>>(src, srcSize, blocks, nBlocks, seqs, seqTabs, seqJobs); }

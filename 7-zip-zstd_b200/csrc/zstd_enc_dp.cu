@@ -79,20 +79,41 @@ struct DpWalk {
     uint32_t rep0, rep1, rep2, prevEnd;     // EMIT only
 };
 
-// one tile of the forward walk: positions [32 t, 32 t + 32) of the lane's segment, as far as the lane's path touches them
+// bit t of the result: byte t of the lane's 32-byte row is not zero (4 bytes per step: carry-free "byte != 0", then a multiply that
+// gathers the four flag bits)
+__device__ __forceinline__ uint32_t dp_nonzero_mask(const uint32_t* row) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t w = row[k];
+        const uint32_t f = ((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u) >> 7;     // bits 0, 8, 16, 24
+        m |= ((f * 0x00204081u) >> 21 & 15u) << (4 * k);
+    }
+    return m;
+}
+
+// one tile of the forward walk: positions [32 t, 32 t + 32) of the lane's segment, as far as the lane's path touches them.  On the
+// path, literals are exactly the positions up to the next non-zero choice, so a whole literal run is one iteration (find-first-set on
+// the tile's "choice != 0" mask), and the loop runs once per match instead of once per position.
 template <bool EMIT>
 __device__ __forceinline__ void dp_walk_tile(DpWarpSmem& sm, DpWalk& k, uint32_t t, uint32_t lane, uint32_t sn, uint32_t s0 /* block-relative */,
                                              const uint64_t* __restrict__ fw /* frame as words */, uint32_t segAbs /* frame-relative */, uint32_t nWords,
                                              const uint32_t* __restrict__ cnd /* segment's candidate words */,
                                              uint64_t* __restrict__ outSeq, uint8_t* __restrict__ outLit) {
     const uint32_t tEnd = (32u * t + 32u) < sn ? (32u * t + 32u) : sn;
+    if (k.i >= tEnd) return;
+    const uint32_t inTile = tEnd - 32u * t;
+    const uint32_t M = dp_nonzero_mask(sm.chcTile[lane]) & (inTile >= 32u ? 0xFFFFFFFFu : ((1u << inTile) - 1u));
     while (k.i < tEnd) {
-        const uint32_t w = k.i & 31u;
-        uint32_t l = (sm.chcTile[lane][w >> 2] >> (8u * (w & 3u))) & 255u;
-        if (!l) {
-            if (EMIT) outLit[k.nl] = (uint8_t)(sm.srcTile[lane][w >> 2] >> (8u * (w & 3u)));
-            k.nl++; k.i++; continue;
+        uint32_t w = k.i & 31u;
+        const uint32_t rem = M >> w;
+        const uint32_t r = rem ? (uint32_t)(__ffs((int)rem) - 1) : (tEnd - k.i);        // literals up to the next match of the tile (or the tile's end)
+        if (r) {
+            if (EMIT) for (uint32_t j = 0; j < r; j++) { const uint32_t ww = w + j; outLit[k.nl + j] = (uint8_t)(sm.srcTile[lane][ww >> 2] >> (8u * (ww & 3u))); }
+            k.nl += r; k.i += r; w += r;
+            if (!rem) break;
         }
+        uint32_t l = (sm.chcTile[lane][w >> 2] >> (8u * (w & 3u))) & 255u;
         const uint32_t off = EMIT ? B2Z_CAND_OFF(sm.candTile[lane][w]) : 0u;
         if (l == B2Z_CAP) {                                                    // the full common prefix, to the segment end at most
             const uint32_t o = EMIT ? off : B2Z_CAND_OFF(__ldg(cnd + k.i));

@@ -217,7 +217,7 @@ int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint
         LitJob* litJobs = (LitJob*)p; p += (size_t)nBlocks * sizeof(LitJob);
         SeqJob* seqJobs = (SeqJob*)p;
         cuemu::launch(dim3((nBlocks + D1_WARPS(0) - 1) / D1_WARPS(0)), dim3(D1_WARPS(0) * 32), 0, [&] { zstd_dec_entropy_kernel<0>(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs, seqTabs, seqJobs); });
-        cuemu::launch(dim3((nBlocks * 4u + 127u) / 128u), dim3(128), 0, [&] { zstd_dec_lit_streams_kernel(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs); });
+        cuemu::launch(dim3((nBlocks + B2Z_LIT_BLOCKS - 1u) / B2Z_LIT_BLOCKS), dim3(B2Z_LIT_BLOCKS * 4u), B2Z_LIT_BLOCKS * 4096u, [&] { zstd_dec_lit_streams_kernel(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs); });
         cuemu::launch(dim3((nBlocks + D1_WARPS(1) - 1) / D1_WARPS(1)), dim3(D1_WARPS(1) * 32), 0, [&] { zstd_dec_entropy_kernel<1>(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs, seqTabs, seqJobs); });
         cuemu::launch(dim3((nBlocks + 127u) / 128u), dim3(128), 0, [&] { zstd_dec_seq_streams_kernel(src, srcSize, blocks.data(), nBlocks, seqs.data(), seqTabs, seqJobs); });
     }
