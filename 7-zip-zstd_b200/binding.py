@@ -66,6 +66,10 @@ def load_library():
     L.b200z_zstd_enc_stage_f.argtypes = [vp, vp, sz, vp]
     L.b200z_zstd_compress_batch_bound.argtypes = [vp, sz, ctypes.c_uint32]; L.b200z_zstd_compress_batch_bound.restype = sz
     L.b200z_zstd_compress_batch_host.argtypes = [vp, vp, vp, ctypes.c_uint32, vp, sz, vp]
+    L.b200z_zstd_compress_batch_crc_host.argtypes = [vp, vp, vp, ctypes.c_uint32, vp, sz, vp, vp]
+    L.b200z_7z_archive_bound.argtypes = [vp, sz, ctypes.c_uint32, sz]; L.b200z_7z_archive_bound.restype = sz
+    L.b200z_7z_build_archive.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
+    L.b200z_7z_write_archive_host.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint32, vp, sz, ctypes.POINTER(sz)]
     L.b200z_lzma2_compress_bound.argtypes = [vp, sz]; L.b200z_lzma2_compress_bound.restype = sz
     for name in ("b200z_lzma2_compress_device", "b200z_lzma2_compress_host"):
         getattr(L, name).argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint32)]
@@ -173,6 +177,21 @@ class Codec:
         out = np.empty(cap, dtype=np.uint8); offs = np.zeros(len(files) + 1, dtype=np.uint64)
         self._check(self.L.b200z_zstd_compress_batch_host(self.h, src.ctypes.data, sizes.ctypes.data, len(files), out.ctypes.data, cap, offs.ctypes.data))
         return [out[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(files))], out[:int(offs[-1])].tobytes()
+
+    def write_7z(self, files, names, mtimes=None) -> bytes:
+        """a complete non-solid .7z archive (method ZSTD, one folder per file) of `files` (list of bytes), one GPU pass"""
+        import numpy as np
+        sizes = np.array([len(f) for f in files], dtype=np.uint64)
+        total = int(sizes.sum())
+        src = np.frombuffer(b"".join(files), dtype=np.uint8) if total else np.zeros(1, dtype=np.uint8)
+        enc = [n.encode("utf-8") for n in names]
+        arr = (ctypes.c_char_p * len(enc))(*enc)
+        mt = np.array(mtimes, dtype=np.uint64) if mtimes is not None else None
+        cap = self.L.b200z_7z_archive_bound(self.h, total, len(files), sum(len(e) + 1 for e in enc))
+        out = np.empty(cap, dtype=np.uint8); n = ctypes.c_size_t()
+        self._check(self.L.b200z_7z_write_archive_host(self.h, src.ctypes.data, sizes.ctypes.data, arr, mt.ctypes.data if mt is not None else None, len(files),
+                                                       out.ctypes.data, cap, ctypes.byref(n)))
+        return out[:n.value].tobytes()
 
     def compress_into(self, src_ptr, n, dst_ptr, cap):
         sz = ctypes.c_size_t()

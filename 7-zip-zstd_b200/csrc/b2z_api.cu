@@ -81,7 +81,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     Arena* all[] = { &ctx->tables, &ctx->seqs, &ctx->nseq, &ctx->lits, &ctx->nlit, &ctx->slots, &ctx->slotSize,
-                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize, &ctx->cand, &ctx->choice };
+                     &ctx->blockOff, &ctx->frameOff, &ctx->scalars, &ctx->dIn, &ctx->dOut, &ctx->cks, &ctx->ready, &ctx->batchStage, &ctx->batchOff, &ctx->batchSize, &ctx->cand, &ctx->choice, &ctx->crcOff, &ctx->crcLen, &ctx->crcOut };
     for (Arena* a : all) a->release();
     for (Arena& a : ctx->decScratch) a.release();
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -308,6 +308,8 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
 }
 
 extern "C" size_t b200z_lzma2_compress_bound(b200z_ctx* ctx, size_t srcSize);
+extern "C" uint32_t b200z_crc32_combine(uint32_t crcA, uint32_t crcB, uint64_t lenB);
+extern "C" int b200z_zstd_compress_batch_crc_host(b200z_ctx* ctx, const void* src, const uint64_t* sizes, uint32_t nFiles, void* dst, size_t dstCap, uint64_t* dstOffsets, uint32_t* crcs);
 static const uint8_t kEmptyFrame[9] = { 0x28, 0xB5, 0x2F, 0xFD, 0x20, 0x00, 0x01, 0x00, 0x00 };
 
 extern "C" {
@@ -514,6 +516,13 @@ size_t b200z_zstd_compress_batch_bound(b200z_ctx* ctx, size_t totalBytes, uint32
 // non-solid 7z archive (7zUpdate.cpp / 7zEncode.cpp:325-332 run one Code() per file; here one call runs them all).
 int b200z_zstd_compress_batch_host(b200z_ctx* ctx, const void* src, const uint64_t* sizes, uint32_t nFiles,
                                    void* dst, size_t dstCap, uint64_t* dstOffsets) {
+    return b200z_zstd_compress_batch_crc_host(ctx, src, sizes, nFiles, dst, dstCap, dstOffsets, nullptr);
+}
+
+// same, and crcs[i] = CRC32 of file i (7-Zip's CrcCalc: what an archive stores per file), computed from the bytes while they are in HBM:
+// 64 KiB pieces on the GPU, folded per file on the host (crc(A||B) = crc(A) x^(8|B|) + crc(B))
+int b200z_zstd_compress_batch_crc_host(b200z_ctx* ctx, const void* src, const uint64_t* sizes, uint32_t nFiles,
+                                       void* dst, size_t dstCap, uint64_t* dstOffsets, uint32_t* crcs) {
     if (!ctx || !sizes || !dstOffsets || !dst) return B200Z_E_PARAM;
     uint64_t total = 0;
     for (uint32_t i = 0; i < nFiles; i++) total += sizes[i];
@@ -552,6 +561,21 @@ int b200z_zstd_compress_batch_host(b200z_ctx* ctx, const void* src, const uint64
                                 (uint8_t*)ctx->batchStage.p, st);
         CU(cudaGetLastError());
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        std::vector<uint32_t> pieceCrc; std::vector<uint64_t> pOff, pLen;
+        if (crcs) {                                              // per-file digests from the uploaded bytes: pieces of <= 64 KiB, one GPU thread each
+            uint64_t at = 0;
+            for (uint32_t i = file0; i < file; i++) { for (uint64_t o = 0; o < sizes[i]; o += 65536) { pOff.push_back(at + o); pLen.push_back(sizes[i] - o < 65536 ? sizes[i] - o : 65536); } at += sizes[i]; }
+            const size_t np = pOff.size();
+            if (np) {
+                if (ctx->crcOff.reserve(np * 8) || ctx->crcLen.reserve(np * 8) || ctx->crcOut.reserve(np * 4)) return fail(ctx, B200Z_E_MEMORY, "device scratch allocation failed%s");
+                CU(cudaMemcpyAsync(ctx->crcOff.p, pOff.data(), np * 8, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(ctx->crcLen.p, pLen.data(), np * 8, cudaMemcpyHostToDevice, st));
+                CU(launch_crc_pieces<uint32_t>((const uint8_t*)ctx->dIn.p, inBytes, 0, (const uint64_t*)ctx->crcOff.p, (const uint64_t*)ctx->crcLen.p, (uint32_t)np, B2Z_CRC32_POLY, (uint32_t*)ctx->crcOut.p, st));
+                pieceCrc.resize(np);
+                CU(cudaMemcpyAsync(pieceCrc.data(), ctx->crcOut.p, np * 4, cudaMemcpyDeviceToHost, st));
+                ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+            }
+        }
         ctx->geom.frameSizes = (const uint32_t*)ctx->batchSize.p;
         uint64_t produced = 0;
         int rc = enc_batch(ctx, (const uint8_t*)ctx->batchStage.p, nFr * F, (uint8_t*)ctx->dOut.p, &produced, false);
@@ -564,6 +588,14 @@ int b200z_zstd_compress_batch_host(b200z_ctx* ctx, const void* src, const uint64
         CU(cudaStreamSynchronize(st));
         ctx->stat[B200Z_S_H2D_BYTES] += (double)inBytes; ctx->stat[B200Z_S_D2H_BYTES] += (double)produced;
         for (uint32_t i = file0, k = 0; i < file; i++, k++) dstOffsets[i] = outPos + fo[firstFrame[k]];   // an empty file owns no frame: zero length
+        if (crcs) {
+            size_t pi = 0;
+            for (uint32_t i = file0; i < file; i++) {
+                uint32_t c = 0;                                  // CRC32 of no bytes
+                for (uint64_t o = 0; o < sizes[i]; o += 65536, pi++) c = o ? b200z_crc32_combine(c, pieceCrc[pi], pLen[pi]) : pieceCrc[pi];
+                crcs[i] = c;
+            }
+        }
         outPos += produced;
     }
     dstOffsets[nFiles] = outPos;

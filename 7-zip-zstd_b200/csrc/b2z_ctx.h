@@ -38,7 +38,7 @@ struct b200z_ctx {
                                       // words 4, choices 1, sequences 2, literals 1, block slots 1.5) near 19 GiB whatever the input size (1 GiB batches cost 4 % of speed)
     uint32_t smCount = 148;
     int lz2Mode = 0;                  // LZMA2 decoder literal-model placement: 0 auto, 1 shared memory, 2 global memory
-    Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready, batchStage, batchOff, batchSize, cand, choice;
+    Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready, batchStage, batchOff, batchSize, cand, choice, crcOff, crcLen, crcOut;
     uint32_t* hostOne = nullptr;      // pinned constant 1 (chunk-arrival flags of the host-pointer path)
     Arena decScratch[8];
     cudaEvent_t ev[8] = {};

@@ -131,6 +131,22 @@ int b200z_zstd_enc_stage_m(b200z_ctx *ctx, const void *d_src, size_t srcSize,
                            uint64_t *seqs, uint32_t *nseq, uint8_t *lits, uint32_t *nlit);
 int b200z_zstd_enc_stage_f(b200z_ctx *ctx, const void *d_src, size_t srcSize, uint32_t *cand);
 
+/* ---- non-solid .7z archives of many files in one pass (BASELINE configs[4]; csrc/sevenz_api.cu) ----------------------------------
+ * The reference's archive layer runs one Code() per file, strictly one after the other (CPP/7zip/Archive/7z/7zUpdate.cpp:2739-2810,
+ * 7zEncode.cpp:482-487).  b200z_zstd_compress_batch_crc_host is b200z_zstd_compress_batch_host that also returns every file's CRC32
+ * (CrcCalc) from the same bytes in HBM; b200z_7z_write_archive_host compresses all files in one GPU pass and writes the container
+ * around them -- signature header, packed streams, uncompressed header: one folder per non-empty file, coder 04F71101 with its 5
+ * property bytes, unpack sizes, CRCs, names (UTF-8 in, UTF-16LE in the archive), optional mtimes (Windows FILETIME) -- the layout of
+ * 7zOut.cpp (WriteHeader :520-820) / DOC/7zFormat.txt.  b200z_7z_build_archive is the container writer alone (host code, no GPU):
+ * packed = the packed streams of the non-empty files back to back. */
+int b200z_zstd_compress_batch_crc_host(b200z_ctx *ctx, const void *src, const uint64_t *sizes, uint32_t nFiles,
+                                       void *dst, size_t dstCap, uint64_t *dstOffsets, uint32_t *crcs);
+size_t b200z_7z_archive_bound(b200z_ctx *ctx, size_t totalBytes, uint32_t nFiles, size_t namesBytes);
+int b200z_7z_build_archive(const void *packed, const uint64_t *packSizes, const uint64_t *unpackSizes, const uint32_t *crcs, const char *const *names,
+                           const uint64_t *mtimes, uint32_t nFiles, uint32_t level, void *dst, size_t dstCap, size_t *dstSize);
+int b200z_7z_write_archive_host(b200z_ctx *ctx, const void *src, const uint64_t *sizes, const char *const *names, const uint64_t *mtimes, uint32_t nFiles,
+                                void *dst, size_t dstCap, size_t *dstSize);
+
 /* ---- LZMA2 / FLZMA2 (method 21) decoder --------------------------------------------------------------
  * src is the raw LZMA2 chunk stream a 7z folder stores for coder 21 (chunks ... 0x00 end marker); dictProp is the
  * coder's 1-byte property (0..40).  Replaces NCompress::NLzma2::CDecoder::Code -> Lzma2DecMt_Decode
