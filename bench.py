@@ -32,6 +32,7 @@ def parse_args():
     ap.add_argument("--size-mib", type=int, default=4096, help="uncompressed MiB per GPU per step (cfg2: 4 GiB)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-mib", type=int, default=4096, help="sample for the CPU reference arm (default: the GPU arm's 4 GiB, same config; ~7 s per pass on 128 threads)")
+    ap.add_argument("--no-files-extra", action="store_true", help="skip extra.many_files_7z (BASELINE configs[4]: 100 000 files of 64 KiB -> one non-solid .7z, one GPU pass)")
     ap.add_argument("--no-lzma2-extra", action="store_true", help="skip extra.lzma2 (BASELINE configs[3] measured beside the zstd headline: method 21 as -m0=flzma2 -mx5 selects it)")
     ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
                     help="zstd: method 4F71101 level 3 (the headline, BASELINE configs[1]); lzma2: method 21 (configs[3])")
@@ -171,6 +172,58 @@ def one_call_multi_gpu(pkg, devices, host_in, unit_bytes, steps, lz=False):
     mb = steps * unit_bytes / 1e6
     return {"devices": len(devices), "uncompressed_bytes": unit_bytes, "value": mb / (t_enc + t_dec), "unit": "MB/s", "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec,
             "ratio": unit_bytes / n, "what": "ONE process, ONE context over all devices, one compress_host + decompress_host call per step on the same input (strong scaling)"}
+
+
+def many_files_7z(pkg, codec, n_files=100_000, file_bytes=65536, cpu_files=4000, cpu=True):
+    """BASELINE configs[4]: n_files mixed-entropy files (SURVEY.md 8(d) cfg5 classes: half text, noise, 16-symbol skew, tiled) -> ONE
+    b200z_7z_write_archive_host call (non-solid: one folder per file).  Beside it the reference's `7zz a -m0=zstd -mx3 -ms=off` on a bounded
+    sample of the same files from tmpfs, all host threads."""
+    import numpy as np, tempfile, shutil
+    text = pkg.corpus.g2(n_files * file_bytes // 2)
+    buf = np.concatenate([text, pkg.corpus.entropy_class(1, n_files * file_bytes // 8), pkg.corpus.entropy_class(2, n_files * file_bytes // 8),
+                          pkg.corpus.entropy_class(3, n_files * file_bytes // 4)])[: n_files * file_bytes]
+    order = np.random.RandomState(5).permutation(n_files)                     # interleave the classes
+    buf = np.ascontiguousarray(buf.reshape(n_files, file_bytes)[order]).reshape(-1)
+    import torch, ctypes
+    hin = torch.from_numpy(buf).pin_memory()
+    sizes = np.full(n_files, file_bytes, dtype=np.uint64)
+    names = [f"d{i % 100:02d}/f{i:06d}.bin".encode() for i in range(n_files)]
+    arr = (ctypes.c_char_p * n_files)(*names)
+    cap = codec.L.b200z_7z_archive_bound(codec.h, buf.nbytes, n_files, sum(len(x) + 1 for x in names))
+    hout = torch.empty(cap, dtype=torch.uint8).pin_memory(); n = ctypes.c_size_t()
+    best = None
+    for _ in range(2):                                                         # first call: allocations
+        t = time.perf_counter()
+        rc = codec.L.b200z_7z_write_archive_host(codec.h, hin.data_ptr(), sizes.ctypes.data, arr, None, n_files, hout.data_ptr(), cap, ctypes.byref(n))
+        t = time.perf_counter() - t
+        assert rc == 0, codec.L.b200z_last_error(codec.h)
+        best = t
+    rec = {"workload": f"{n_files} files x {file_bytes} B (text / noise / skew / tiles), one non-solid .7z (method ZSTD level 3, one folder per file), pinned host buffers, one call",
+           "value": buf.nbytes / 1e6 / best, "unit": "MB/s", "files_per_s": n_files / best, "ms": 1e3 * best, "ratio": buf.nbytes / n.value, "archive_bytes": n.value}
+    stock = os.path.join(ROOT, "oracle", "_ref", "7z", "stock", "7zz")
+    if cpu and os.path.exists(stock):
+        d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            # the archive just written, tested by the reference itself (a sample archive of the first files: the stock decoder is single-threaded)
+            k = min(cpu_files, n_files)
+            for i in range(k):
+                os.makedirs(os.path.join(d, "in", f"d{i % 100:02d}"), exist_ok=True)
+                buf[i * file_bytes:(i + 1) * file_bytes].tofile(os.path.join(d, "in", names[i].decode()))
+            cores = os.cpu_count() or 1
+            t = time.perf_counter()
+            r = subprocess.run([stock, "a", "-m0=zstd", "-mx3", "-ms=off", f"-mmt={cores}", "-bso0", "-bsp0", os.path.join(d, "ref.7z"), "."], cwd=os.path.join(d, "in"), capture_output=True, text=True)
+            t = time.perf_counter() - t
+            if r.returncode == 0:
+                rec["cpu_baseline"] = {"value": k * file_bytes / 1e6 / t, "unit": "MB/s", "files_per_s": k / t, "cores": cores, "kind": "reference",
+                                       "sample": f"7zz a -m0=zstd -mx3 -ms=off -mmt={cores} on the first {k} of the same files from tmpfs",
+                                       "ratio": k * file_bytes / os.path.getsize(os.path.join(d, "ref.7z"))}
+            ours = codec.write_7z([buf[i * file_bytes:(i + 1) * file_bytes].tobytes() for i in range(k)], [x.decode() for x in names[:k]])
+            open(os.path.join(d, "ours.7z"), "wb").write(ours)
+            r = subprocess.run([stock, "t", os.path.join(d, "ours.7z")], capture_output=True, text=True)
+            rec["reference_7zz_verifies_sample_archive"] = bool(r.returncode == 0 and "Everything is Ok" in r.stdout)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return rec
 
 
 def main():
@@ -388,6 +441,13 @@ def main():
                 lz_rec["cpu_baseline"] = {"unavailable": str(e)[:120]}
         line.setdefault("extra", {})["lzma2"] = lz_rec
         lc.close()
+        del l_comp, l_back
+        torch.cuda.empty_cache()
+    if not lz and world == 1 and not a.no_files_extra:
+        try:
+            line.setdefault("extra", {})["many_files_7z"] = many_files_7z(pkg, codec, cpu=not a.no_cpu_baseline)
+        except Exception as e:
+            line.setdefault("extra", {})["many_files_7z"] = {"error": str(e)[:200]}
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_ref(a.cpu_sample_mib << 20)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
