@@ -25,7 +25,7 @@ class CEncoder final : public ICompressCoder, public ICompressSetCoderMt, public
     std::atomic<UInt32> refs_{0};
     Byte props_[5] = { kZstdVerMajor, kZstdVerMinor, 3, 0, 0 };
     int level_ = 3; bool max_ = false; UInt32 numThreads_ = 1;
-    int windowLog_ = -1, hashLog_ = -1, chainLog_ = -1;
+    int windowLog_ = -1, hashLog_ = -1, chainLog_ = -1; bool long_ = false;
     PinnedBuf in_, out_;
 public:
     UInt64 processedIn = 0, processedOut = 0;
@@ -74,7 +74,7 @@ public:
                     level_ = -(int)v; props_[2] = (Byte)(v + kFastLevInc); break;
                 }
                 /* fall through (as the reference does when max is set: the value is read as kLong's) */
-            case NCoderPropID::kLong: windowLog_ = v == 0 ? 27 : (int)(v < 10 ? 10 : (v > 31 ? 31 : v)); break;
+            case NCoderPropID::kLong: long_ = true; windowLog_ = v == 0 ? 27 : (int)(v < 10 ? 10 : (v > 31 ? 31 : v)); break;   // ZstdEncoder.cpp:128-146
             case NCoderPropID::kWindowLog: if (v < 10 || v > 31) return E_INVALIDARG; windowLog_ = (int)v; break;
             case NCoderPropID::kHashLog: if (v < 6 || v > 30) return E_INVALIDARG; hashLog_ = (int)v; break;
             case NCoderPropID::kChainLog: if (v < 6 || v > 30) return E_INVALIDARG; chainLog_ = (int)v; break;
@@ -97,7 +97,13 @@ public:
         b200z_set_param(ctx, B200Z_P_FLAGS, 1);               // mcmilk MT frame convention: size hint before each frame
         if (hashLog_ >= 10 && hashLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_L, hashLog_);
         if (chainLog_ >= 10 && chainLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_S, chainLog_);
-        if (windowLog_ >= 17) { int64_t fl = 0; b200z_get_param(ctx, B200Z_P_FRAMELOG, &fl); b200z_set_param(ctx, B200Z_P_WINDOWLOG, windowLog_ < fl ? windowLog_ : fl); }
+        // long=N (ZstdEncoder.cpp:322-331: long-distance matching on, window 2^N): the engine's long mode, frames and window of 2^N bytes
+        // (17..27; a smaller N has nothing beyond stage F's reach to find, a larger one is cut to the 128 MiB the format's decoders accept by default)
+        if (long_ && windowLog_ >= 17) b200z_set_param(ctx, B200Z_P_LONG, windowLog_ > 27 ? 27 : windowLog_);
+        else {
+            b200z_set_param(ctx, B200Z_P_LONG, 0);
+            if (windowLog_ >= 17) { int64_t fl = 0; b200z_get_param(ctx, B200Z_P_FRAMELOG, &fl); b200z_set_param(ctx, B200Z_P_WINDOWLOG, windowLog_ < fl ? windowLog_ : fl); }
+        }
         // batches of whole frames: 1 GiB of input per GPU pass (pinned host memory); a batch has to hold about a
         // thousand 1 MiB frames to keep the frame-parallel match finder busy
         const int nDev = b200z_device_list(ctx, nullptr, 0);

@@ -42,3 +42,31 @@ def entropy_class(cls, nbytes, seed=5) -> np.ndarray:
     if nbytes:
         _load().b200z_corpus_class(seed, cls, buf.ctypes.data, nbytes)
     return buf
+
+
+def inject_far_copies(buf, every=64 << 20, span=(1 << 20, 4 << 20), back=128 << 20, mutate=0.001, seed=3) -> int:
+    """cfg3: long-range redundancy written into `buf` in place -- at every multiple of `every`, a span of
+    span[0]..span[1] bytes copied from a uniformly random earlier position (at most `back` bytes back), `mutate` of its bytes
+    changed.  Returns the bytes planted."""
+    rng = np.random.default_rng(seed)
+    n = buf.size
+    planted = 0
+    for at in range(every, n, every):
+        ln = min(int(rng.integers(span[0], span[1])), n - at)
+        lo = 0 if back is None else max(0, at - back)
+        if at - ln <= lo:
+            continue
+        srcp = int(rng.integers(lo, at - ln))
+        seg = buf[srcp:srcp + ln].copy()
+        m = rng.random(ln) < mutate
+        seg[m] = rng.integers(0, 256, int(m.sum()), dtype=np.uint8)
+        buf[at:at + ln] = seg
+        planted += ln
+    return planted
+
+
+def g3(nbytes, seed=3) -> np.ndarray:
+    """cfg3's input: G2 text + inject_far_copies with the recipe's constants"""
+    buf = g2(nbytes)
+    inject_far_copies(buf, seed=seed)
+    return buf

@@ -111,7 +111,15 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_ZSTD_PARSE: if (v < 0 || v > 1) return fail(ctx, B200Z_E_PARAM, "zstd parse mode out of range%s");
                             ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
     case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");
-                            ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v; return 0;
+                            ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v;
+                            ctx->geom.regionLog = ctx->geom.ldmLog = 0; return 0;                                    // (leaves the long mode)
+    // long mode: frame = window = 2^v bytes, cut into regions of 1 MiB for stage F, + stage L.  0 leaves it (frames of 1 MiB again).
+    case B200Z_P_LONG:      if (v != 0 && (v < 17 || v > B2Z_MAX_LONGLOG)) return fail(ctx, B200Z_E_PARAM, "long: window log out of range%s");
+                            if (v == 0) { if (ctx->geom.regionLog) { ctx->geom.frameLog = ctx->geom.windowLog = B2Z_DEF_FRAMELOG; } ctx->geom.regionLog = ctx->geom.ldmLog = 0; return 0; }
+                            ctx->geom.frameLog = ctx->geom.windowLog = (uint32_t)v;
+                            ctx->geom.regionLog = v < B2Z_DEF_REGIONLOG ? (uint32_t)v : B2Z_DEF_REGIONLOG;
+                            ctx->geom.ldmLog = v > B2Z_DEF_REGIONLOG ? B2Z_LDM_LOG((uint32_t)v) : 0u;
+                            return 0;
     // both tables live in the shared memory of one SM: 2^L + 2^S entries <= 192 KiB
     case B200Z_P_HASHLOG_L: if (v < 8 || v > 15 || (1u << v) + (1u << ctx->geom.hashLogS) > B2Z_MAX_HASHLOG_SUM_WORDS) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
     case B200Z_P_HASHLOG_S: if (v < 8 || v > 15 || (1u << v) + (1u << ctx->geom.hashLogL) > B2Z_MAX_HASHLOG_SUM_WORDS) return fail(ctx, B200Z_E_PARAM, "hashLogS out of range%s"); ctx->geom.hashLogS = (uint32_t)v; return 0;
@@ -145,6 +153,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
     case B200Z_P_CHUNKLOG: *v = ctx->geom.chunkLog; return 0;
+    case B200Z_P_LONG: *v = ctx->geom.regionLog ? ctx->geom.frameLog : 0; return 0;
     }
     return B200Z_E_PARAM;
 }
@@ -175,8 +184,11 @@ static uint32_t find_ctas(const b200z_ctx* ctx, uint64_t nFrames) {
 // does this batch parse by price (stage C + stage P / stage Z) instead of the greedy stage M?  (the per-file batch mode, which
 // sets frameSizes, always runs stage M)
 static bool price_parse(const EncGeom& g, int codec) {
-    return codec == 1 ? (g.flags & B2Z_FLAG_LZ2_OPT) != 0 : ((g.flags & B2Z_FLAG_ZSTD_OPT) != 0 && !g.frameSizes);
+    return codec == 1 ? (g.flags & B2Z_FLAG_LZ2_OPT) != 0 : ((g.flags & B2Z_FLAG_ZSTD_OPT) != 0 && !g.frameSizes && !g.regionLog);
 }
+// the long mode of the Zstandard encoder: frames of many regions (stage F's unit) + stage L.  Per-file batches and method 21 have none.
+static bool long_mode(const EncGeom& g, int codec) { return codec == 0 && !g.frameSizes && g.regionLog && g.regionLog < g.frameLog; }
+static bool ldm_on(const EncGeom& g, int codec) { return long_mode(g, codec) && g.ldmLog; }
 
 // stage C of the price-based parses: every resident frame-warp owns 7-30 MB of tables
 static uint32_t cand_warps(const b200z_ctx* ctx, uint64_t nFrames) {
@@ -195,6 +207,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     } else {                                                            // stage F -> stage G: a candidate word and a choice byte per input byte
         bad |= ctx->cand.reserve((size_t)(nFrames * F + 16) * 4u);
         bad |= ctx->choice.reserve((size_t)(nFrames * F + 16));
+        if (ldm_on(ctx->geom, codec)) bad |= ctx->tables.reserve(zstd_enc_ldm_table_words(ctx->geom, nFrames) * 4u);
     }
     bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);
     bad |= ctx->nseq.reserve(nBlocks * 4);
@@ -242,7 +255,13 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
             return 0;
         }
     } else {
-        CU(launch_zstd_enc_find(d_src, n, g, (uint32_t*)ctx->cand.p, find_ctas(ctx, nFrames), ready, readyShift, errFlag, st));
+        EncGeom gF = g;                                                 // stage F's unit: the frame, or the region of a long frame
+        if (long_mode(g, codec)) gF.frameLog = g.regionLog;
+        CU(launch_zstd_enc_find(d_src, n, gF, (uint32_t*)ctx->cand.p, find_ctas(ctx, (n + (1ull << gF.frameLog) - 1) >> gF.frameLog), ready, readyShift, errFlag, st));
+        if (ldm_on(g, codec)) {
+            CU(launch_zstd_enc_ldm(d_src, n, g, (uint32_t*)ctx->cand.p, (uint32_t*)ctx->tables.p, ctx->smCount, st));
+            ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 2;
+        }
         CU(cudaEventRecord(ctx->ev[4], st));
         CU(launch_zstd_enc_dp(d_src, n, g, (const uint32_t*)ctx->cand.p, (uint8_t*)ctx->choice.p, (uint64_t*)ctx->seqs.p, (uint32_t*)ctx->nseq.p,
                               (uint8_t*)ctx->lits.p, (uint32_t*)ctx->nlit.p, st));

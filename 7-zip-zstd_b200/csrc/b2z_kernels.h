@@ -12,6 +12,7 @@ namespace b2z {
 
 struct EncGeom {
     uint32_t frameLog, hashLogL, hashLogS, windowLog, flags, chunkLog;
+    uint32_t regionLog, ldmLog;      // long mode (B200Z_P_LONG): stage F's unit inside a frame (0 = the frame) and stage L's table log (0 = no stage L)
     const uint32_t* frameSizes;      // null: frames are dense (all 2^frameLog bytes but the last).  Batch mode (frameLog 17, one block
                                      // per frame): bytes of every frame, frames sit at multiples of 2^frameLog in the staging buffer
 };
@@ -26,6 +27,9 @@ size_t zstd_enc_find_smem_bytes(const EncGeom& g);
 cudaError_t launch_zstd_enc_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand /* [srcSize + 16] */, uint32_t nCtas,
                                  const uint32_t* ready /* null, or per-chunk arrival flags */, uint32_t readyShift,
                                  uint32_t* errFlag /* set to 1 when an arrival flag never came */, cudaStream_t st);
+// stage L (zstd_enc_ldm.cu), long mode: far matches through a per-frame table of first occurrences of sampled positions; overwrites candidate words
+size_t zstd_enc_ldm_table_words(const EncGeom& g, uint64_t nFrames);
+cudaError_t launch_zstd_enc_ldm(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t* tables /* [nFrames << ldmLog] */, uint32_t smCount, cudaStream_t st);
 // stage G (zstd_enc_dp.cu): one warp per 128 KiB block, one lane per 4 KiB segment: minimum-price parse of stage F's candidates
 // -> per-block final sequences + literal bytes.  choice: one scratch byte per input byte.
 size_t zstd_enc_dp_smem_bytes();

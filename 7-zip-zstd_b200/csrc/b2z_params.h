@@ -24,13 +24,23 @@
 #define B2Z_DP_MINLEN      4u
 #define B2Z_DP_LIT_MIN     16u
 #define B2Z_DP_LIT_MAX     192u
-/* candidate word of one position (stage F -> stage G): 0 = none, else offset << 7 | length (length <= B2Z_CAP) */
-#define B2Z_CAND(len, off) (((uint32_t)(off) << 7) | (uint32_t)(len))
-#define B2Z_CAND_LEN(c)    ((c) & 127u)
-#define B2Z_CAND_OFF(c)    ((c) >> 7)
+/* candidate word of one position (stage F / stage L -> stage G): 0 = none, else offset << 5 | length (length <= B2Z_CAP = 16,
+ * offset < 2^27: the widest window of the long mode) */
+#define B2Z_CAND(len, off) (((uint32_t)(off) << 5) | (uint32_t)(len))
+#define B2Z_CAND_LEN(c)    ((c) & 31u)
+#define B2Z_CAND_OFF(c)    ((c) >> 5)
 /* bytes of a block that feed the literal histogram: the first 64 of every 256 */
 #define B2Z_DP_SAMPLED(i)  ((((i) >> 6) & 3u) == 0u)
 #define B2Z_MAX_FRAMELOG   24
+/* long mode (B200Z_P_LONG, the reference's long=N / ZSTD_c_enableLongDistanceMatching, zstd_ldm.c): a frame of up to 2^27 bytes is
+ * cut into REGIONS of 2^regionLog bytes, stage F's unit (its tables start empty in every region); stage L then looks, for one
+ * position in 2^B2Z_LDM_RATELOG, for the first place of the frame that holds the same B2Z_LDM_MINMATCH bytes */
+#define B2Z_MAX_LONGLOG    27
+#define B2Z_DEF_REGIONLOG  20
+#define B2Z_LDM_MINMATCH   64u
+#define B2Z_LDM_RATELOG    7u
+#define B2Z_LDM_LOG(windowLog) ((windowLog) - 5u)   /* entries of the per-frame sample table: four per sample of a full frame */
+#define B2Z_LDM_TAGBITS    4u      /* entry = position << 4 | tag, 0xFFFFFFFF = empty                                    */
 #define B2Z_CAP            16u     /* stage F compares at most this many bytes (two 8-byte words, no loop); stage G extends a chosen match of this length */
 #define B2Z_MAXSEQ         32768u  /* raw sequences per 128 KiB block (min match 4)          */
 #define B2Z_BLOCK          131072u
@@ -39,11 +49,11 @@
 #define B2Z_LIT_RLE_MIN    8u
 #define B2Z_BODY_CAP       196608u /* a block body whose size upper bound exceeds this is stored raw */
 
-/* final sequence record: offBase (25 bits) | litLength (18) | matchLength (18) */
-#define B2Z_PACK_SEQ(offBase, ll, ml) ((uint64_t)(offBase) | ((uint64_t)(ll) << 25) | ((uint64_t)(ml) << 43))
-#define B2Z_SEQ_OFFBASE(s) ((uint32_t)((s) & 0x1FFFFFFu))
-#define B2Z_SEQ_LL(s)      ((uint32_t)(((s) >> 25) & 0x3FFFFu))
-#define B2Z_SEQ_ML(s)      ((uint32_t)(((s) >> 43) & 0x3FFFFu))
+/* final sequence record: offBase (28 bits) | litLength (18) | matchLength (18) */
+#define B2Z_PACK_SEQ(offBase, ll, ml) ((uint64_t)(offBase) | ((uint64_t)(ll) << 28) | ((uint64_t)(ml) << 46))
+#define B2Z_SEQ_OFFBASE(s) ((uint32_t)((s) & 0xFFFFFFFu))
+#define B2Z_SEQ_LL(s)      ((uint32_t)(((s) >> 28) & 0x3FFFFu))
+#define B2Z_SEQ_ML(s)      ((uint32_t)(((s) >> 46) & 0x3FFFFu))
 
 /* ---- LZMA2 encoder (stage R: range coding of the stage-M sequences of one frame = one dictionary-reset block) ---- */
 #define B2Z_LZ2_LC 2u      /* 2 codes G2 text as well as 3 (2.3961 vs 2.3955) and halves the literal model: the whole model fits shared memory */
@@ -80,6 +90,14 @@ B2Z_HD uint32_t b2z_level_find_flags(int level) { return level <= 2 ? B2Z_FLAG_F
 /* digests (b2z_crc.cu): reflected polynomials of CRC-32 (C/7zCrc.c) and CRC-64/XZ (C/XzCrc64.c) */
 #define B2Z_CRC32_POLY 0xEDB88320u
 #define B2Z_CRC64_POLY 0xC96C5795D7870F42ull
+
+/* stage L: is position p (8 bytes v there) a sample, and the key of the 32 bytes there */
+B2Z_HD int b2z_ldm_sampled(uint64_t v) { return ((v * 0x9E3779B185EBCA87ULL) >> (64 - B2Z_LDM_RATELOG)) == (1u << B2Z_LDM_RATELOG) - 1u; }   /* a run of zeros is never one */
+B2Z_HD uint64_t b2z_ldm_key(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3) {
+    uint64_t k = w0 * 0xCF1BBCDCB7A56463ULL;
+    k = (k ^ (k >> 29) ^ w1) * 0xCF1BBCDCB7A56463ULL; k = (k ^ (k >> 29) ^ w2) * 0xCF1BBCDCB7A56463ULL; k = (k ^ (k >> 29) ^ w3) * 0xCF1BBCDCB7A56463ULL;
+    return k ^ (k >> 32);
+}
 
 /* multiplicative hashes: same constants as the reference (zstd_compress_internal.h:903-924) */
 #define B2Z_PRIME5 889523592379ULL

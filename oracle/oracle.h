@@ -28,6 +28,8 @@ typedef struct {
     uint32_t chunkLog;      /* stage F: log2 positions per table turn (default 7)             */
     uint32_t flags;         /* bit0: skippable size hints before each frame; bit1: checksum;
                                bits 8..10: LZMA2 slice log; bit4: LZMA2 price-based parse */
+    uint32_t regionLog;     /* long mode: stage F's unit inside a frame (0 = the frame)        */
+    uint32_t ldmLog;        /* long mode: log2 entries of stage L's per-frame sample table (0 = no stage L) */
 } b2zo_enc_params;
 
 void   b2zo_enc_default_params(b2zo_enc_params *p, int level);

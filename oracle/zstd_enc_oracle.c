@@ -44,6 +44,7 @@ static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
     p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
     p->windowLog = B2Z_DEF_FRAMELOG; p->chunkLog = B2Z_DEF_CHUNKLOG; p->flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);
+    p->regionLog = 0; p->ldmLog = 0;
     p->flags |= b2z_level_find_flags(level) | (level >= B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_ZSTD_OPT : 0u);      /* what B200Z_P_LEVEL sets */
     if (p->flags & B2Z_FLAG_FIND_FAST) p->hashLogS = B2Z_DEF_HASHLOG_L;                                     /* the single table takes the long table's room */
 }
@@ -77,10 +78,9 @@ static size_t count_match(const uint8_t *a, const uint8_t *b, size_t maxLen) {
  * and buys nothing on text: 2.3823 vs 2.3830 on G2; structured data with repeats at distances under 128 loses about 1 %.)
  * Every position is searched and inserted.  Candidates are compared over at most B2Z_CAP bytes and never beyond the end
  * of their 4 KiB parse segment; the longer of (long, short) wins, the nearer on a tie. */
-void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P, uint32_t *cand) {
-    const uint8_t *src = (const uint8_t *)srcv;
+static void candidates_region(const uint8_t *src, uint32_t n, const b2zo_enc_params *P, uint32_t unitLog, uint32_t *cand) {
     const uint32_t HL = P->hashLogL, HS = P->hashLogS, CH = 1u << P->chunkLog;
-    const uint32_t tagBits = 32 - (P->frameLog + 1), tagMask = (1u << tagBits) - 1;
+    const uint32_t tagBits = 32 - (unitLog + 1), tagMask = (1u << tagBits) - 1;
     const uint64_t W = P->windowLog >= 32 ? 0xFFFFFFFFull : (1ull << P->windowLog);
     const int FAST = (P->flags & B2Z_FLAG_FIND_FAST) != 0, STEP = (P->flags & B2Z_FLAG_FIND_STEP) != 0;
     uint32_t *TL = (uint32_t *)calloc((size_t)1 << HL, 4), *TS = (uint32_t *)calloc((size_t)1 << HS, 4);
@@ -112,6 +112,61 @@ void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P
         for (uint32_t k = 0; k < c1 - c0; k++) if (iL[k] != 0xFFFFFFFFu) { TL[iL[k]] = eLn[k]; TS[iS[k]] = eSn[k]; }   /* ascending: the highest position stays */
     }
     free(TL); free(TS); free(iL); free(iS); free(eLn); free(eSn);
+}
+
+/* Stage L, one frame of the long mode (the role of zstd_ldm.c:333-470, ZSTD_ldm_generateSequences: rolling-hash split points, a
+ * bucketed table of checksums, matches of >= minMatchLength 64 bytes found far behind the reach of the block finder).  Restated
+ * for the device as a pure function of the frame's bytes, in two passes that are each parallel over every position:
+ *   - position p is a SAMPLE when a hash of its 8 bytes has its top B2Z_LDM_RATELOG bits set (content-defined, so both ends of a
+ *     far copy sample the same places); its key hashes the 32 bytes at p;
+ *   - pass 1: one direct-mapped table per frame, entry = position << 4 | tag, keeps the LOWEST sample of every index (atomicMin
+ *     on the device): the first occurrence in the frame;
+ *   - pass 2: a sample whose entry is a lower position with its tag, at most a window back, and whose 64 bytes verify, is walked
+ *     BACK to where the agreement starts (not past the segment start, not onto a lower sample -- every position has one owner);
+ *     the candidate word there becomes (min(B2Z_CAP, bytes to the segment end), distance) unless stage F's candidate there is
+ *     as long AND itself verifies 64 bytes (it is nearer, so cheaper).
+ * Stage G prices the word like any other; chosen, it is extended by direct comparison to its true length (or the segment end). */
+static void ldm_frame(const uint8_t *src, uint32_t n, const b2zo_enc_params *P, uint32_t *cand) {
+    const uint32_t L = P->ldmLog;
+    const uint64_t W = P->windowLog >= 32 ? 0xFFFFFFFFull : (1ull << P->windowLog);
+    const uint32_t tagMask = (1u << B2Z_LDM_TAGBITS) - 1;
+    if (n < B2Z_LDM_MINMATCH) return;
+    uint32_t *T = (uint32_t *)malloc((size_t)4 << L);
+    memset(T, 0xFF, (size_t)4 << L);
+    for (int pass = 0; pass < 2; pass++)
+        for (uint32_t p = 0; p + B2Z_LDM_MINMATCH <= n; p++) {
+            if (!b2z_ldm_sampled(rd64(src + p))) continue;
+            const uint64_t key = b2z_ldm_key(rd64(src + p), rd64(src + p + 8), rd64(src + p + 16), rd64(src + p + 24));
+            const uint32_t idx = (uint32_t)(key >> (64 - L)), tag = (uint32_t)(key >> (64 - L - B2Z_LDM_TAGBITS)) & tagMask;
+            if (pass == 0) { const uint32_t e = (p << B2Z_LDM_TAGBITS) | tag; if (e < T[idx]) T[idx] = e; continue; }
+            const uint32_t e = T[idx];
+            if ((e & tagMask) != tag) continue;                                  /* (an index somebody wrote is never empty here) */
+            const uint32_t q = e >> B2Z_LDM_TAGBITS;
+            if (q >= p) continue;                                                /* this is the first occurrence itself */
+            const uint32_t d = p - q;
+            if (d > W || count_match(src + q, src + p, B2Z_LDM_MINMATCH) < B2Z_LDM_MINMATCH) continue;
+            uint32_t s0 = p; const uint32_t segStart = p & ~(B2Z_SEG - 1);
+            while (s0 > segStart && s0 > d && src[s0 - 1] == src[s0 - 1 - d] && !b2z_ldm_sampled(rd64(src + s0 - 1))) s0--;
+            const uint32_t segEnd = ((p | (B2Z_SEG - 1)) + 1) < n ? ((p | (B2Z_SEG - 1)) + 1) : n;
+            const uint32_t maxLen = segEnd - s0 > B2Z_CAP ? B2Z_CAP : segEnd - s0;
+            if (maxLen < B2Z_DP_MINLEN) continue;
+            const uint32_t c = cand[s0];
+            if (c && B2Z_CAND_LEN(c) >= maxLen &&
+                (maxLen < B2Z_CAP || count_match(src + s0 - B2Z_CAND_OFF(c), src + s0, B2Z_LDM_MINMATCH) >= B2Z_LDM_MINMATCH)) continue;
+            cand[s0] = B2Z_CAND(maxLen, d);
+        }
+    free(T);
+}
+
+/* candidate words of one frame: stage F per region, then stage L */
+void b2zo_zstd_candidates(const void *srcv, uint32_t n, const b2zo_enc_params *P, uint32_t *cand) {
+    const uint8_t *src = (const uint8_t *)srcv;
+    const uint32_t RL = P->regionLog && P->regionLog < P->frameLog ? P->regionLog : P->frameLog, R = 1u << RL;
+    for (uint32_t r0 = 0; r0 < n || r0 == 0; r0 += R) {
+        candidates_region(src + r0, n - r0 < R ? n - r0 : R, P, RL, cand + r0);
+        if (n - r0 <= R) break;
+    }
+    if (P->ldmLog) ldm_frame(src, n, P, cand);
 }
 
 typedef struct { uint32_t rep[3]; } seg_rep_t;

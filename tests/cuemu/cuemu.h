@@ -190,6 +190,7 @@ inline void __nanosleep(unsigned) { cuemu::yield(); }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
 inline uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t o = *p; if (v > o) *p = v; return o; }
+inline uint32_t atomicMin(uint32_t* p, uint32_t v) { const uint32_t o = *p; if (v < o) *p = v; return o; }
 inline uint32_t atomicExch(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = v; return o; }
 
 inline uint32_t cuemu_lane_id() { return cuemu::lane(); }

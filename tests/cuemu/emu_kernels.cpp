@@ -5,6 +5,7 @@
 #include "cuemu.h"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_find.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_dp.cu"
+#include "../../7-zip-zstd_b200/csrc/zstd_enc_ldm.cu"
 #include "../../7-zip-zstd_b200/csrc/lzma2_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_parse.cu"
 #include "../../7-zip-zstd_b200/csrc/zstd_enc_entropy.cu"
@@ -44,6 +45,18 @@ static uint64_t run_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g,
 }
 uint64_t emu_zstd_enc_find(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t chunkLog, uint32_t flags, uint32_t nCtas, uint32_t* cand) {
     return run_find(src, srcSize, geom(frameLog, windowLog, chunkLog, flags), nCtas, cand);
+}
+
+// long mode: stage F per region, then stage L per frame (zstd_enc_ldm_kernel): candidate words as the oracle's b2zo_zstd_candidates
+uint64_t emu_zstd_enc_find_long(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t regionLog, uint32_t ldmLog, uint32_t nCtas, uint32_t* cand) {
+    EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, 0); g.regionLog = regionLog; g.ldmLog = ldmLog;
+    EncGeom gF = g; gF.frameLog = regionLog;
+    uint64_t c = run_find(src, srcSize, gF, nCtas, cand);
+    const uint64_t nFrames = (srcSize + (1ull << frameLog) - 1) >> frameLog;
+    std::vector<uint32_t> tables((size_t)nFrames << ldmLog, 0xFFFFFFFFu);                // (launch_zstd_enc_ldm: cudaMemsetAsync 0xFF)
+    c += cuemu::launch(dim3(nCtas), dim3(B2Z_LDM_THREADS), 0, [&] { zstd_enc_ldm_kernel<0>(src, srcSize, g, cand, tables.data()); });
+    c += cuemu::launch(dim3(nCtas), dim3(B2Z_LDM_THREADS), 0, [&] { zstd_enc_ldm_kernel<1>(src, srcSize, g, cand, tables.data()); });
+    return c;
 }
 
 // stage F + stage G (zstd_enc_find_kernel, zstd_enc_dp_kernel): per-block sequences and literals as the oracle's b2zo_zstd_find_sequences

@@ -9,8 +9,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MAXSEQ = 32768
 
 
+def seq_fields(s):
+    """(offBase, litLength, matchLength) of one packed sequence record (b2z_params.h B2Z_PACK_SEQ)"""
+    s = int(s)
+    return s & 0xFFFFFFF, (s >> 28) & 0x3FFFF, (s >> 46) & 0x3FFFF
+
+
 class EncParams(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "chunkLog", "flags")]
+    _fields_ = [(n, ctypes.c_uint32) for n in ("frameLog", "hashLogL", "hashLogS", "windowLog", "chunkLog", "flags", "regionLog", "ldmLog")]
 
 
 _oracle = None
@@ -102,6 +108,13 @@ def oracle_candidates(data, **kw):
     for f0 in range(0, n, F):
         O.b2zo_zstd_candidates(src.ctypes.data + f0, min(F, n - f0), ctypes.byref(p), cand.ctypes.data + 4 * f0)
     return cand[:n]
+
+
+def far_copies(pkg, n, every, span, seed=3, mutate=0.001, back=None):
+    """text (the G2 generator) with long-range redundancy: BASELINE configs[2]'s recipe (corpus.inject_far_copies) at a test's scale"""
+    d = pkg.corpus.g2(n)
+    pkg.corpus.inject_far_copies(d, every=every, span=span, back=back, mutate=mutate, seed=seed)
+    return d.tobytes()
 
 
 def oracle_decompress(comp, n) -> bytes:

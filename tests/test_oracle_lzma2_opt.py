@@ -82,7 +82,7 @@ def test_parse_taps_cover_the_frame_and_reference_valid_history(pkg):
             pos = max(pos, b << 17)
             for i in range(int(nseq[b])):
                 s = int(seqs[b * H.MAXSEQ + i])
-                off = (s & 0x1FFFFFF) - 3; ll = (s >> 25) & 0x3FFFF; ml = (s >> 43) & 0x3FFFF
+                ob_, ll, ml = H.seq_fields(s); off = ob_ - 3
                 assert off >= 1 and 2 <= ml <= 273
                 pos += ll
                 assert pos - off >= 0 and pos + ml <= n

@@ -29,7 +29,7 @@ def test_sequences_are_valid_and_cover_every_block(pkg):
             bn = min(131072, fn - b0)
             rep = [0, 0, 0]; pos = 0; nl = 0
             for i in range(int(nseq[blk])):
-                s = int(seqs[blk * H.MAXSEQ + i]); ob = s & 0x1FFFFFF; ll = (s >> 25) & 0x3FFFF; ml = (s >> 43) & 0x3FFFF
+                ob, ll, ml = H.seq_fields(seqs[blk * H.MAXSEQ + i])
                 assert ml >= 3
                 lit_bytes = bytes(lits[f0 + b0 + nl:f0 + b0 + nl + ll]); assert lit_bytes == data[f0 + b0 + pos:f0 + b0 + pos + ll]
                 pos += ll; nl += ll
