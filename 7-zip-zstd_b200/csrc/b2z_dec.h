@@ -22,7 +22,7 @@ struct DecFrame {
     uint64_t regen;         // D0: end offset of the frame in src; from D2 on: sum of block sizes
     uint32_t firstBlock, nBlocks;
     uint32_t checksum;      // 1 if a 4-byte content checksum follows the last block
-    uint32_t pad;           // D0 scratch (frame header bytes)
+    uint32_t pad;           // D0: scratch (frame header bytes); from D2 on: index of the frame's first execution unit
     uint64_t endOff;        // offset just past the frame in src (the checksum, if any, is the 4 bytes before it)
 };
 
@@ -38,9 +38,18 @@ struct DecBlock {
     uint32_t nbSeq;         // sequences decoded           (stage D1)
     uint32_t litSize;       // literals decoded            (stage D1)
     uint32_t status;        // B2Z_DERR_* bits             (stage D1 / D3)
+    // repcode history across the block, symbolically (stage D1): after the block, slot s holds repX[s] if its 2 bits of repSym are 0,
+    // else (slot (bits - 1) of the history BEFORE the block) - repX[s].  Lets stage D2 hand every block its starting history
+    // without anybody walking the frame's sequences in order.
+    uint32_t repX[3], repSym;
+    uint32_t repInit[3];    // history at the block's first sequence (stage D2)
+    uint32_t pad2;
+    uint64_t outRel;        // first output byte of the block, relative to its frame (stage D2)
 };
 
-struct DecCounts { uint32_t nFrames, nBlocks, status, pad; uint64_t srcUsed; };
+#define B2Z_DEC_UNIT_BLOCKS 8u       // stage D3: consecutive blocks of a frame executed by one warp (1 MiB of output when the blocks are full)
+
+struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; };
 
 // stage D0: frame discovery (1 thread; hops over mcmilk size hints when present), then per-frame block indexing
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st);
@@ -51,11 +60,13 @@ void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blo
                              uint8_t* lits, uint64_t* seqs, void* scratch, cudaStream_t st, cudaStream_t stLit, cudaEvent_t evFork, cudaEvent_t evJoin);
 size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks);
 // stage D2: per-frame sizes and output offsets
-void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* blocks, uint64_t dstCap,
+void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap,
                             DecCounts* counts, uint64_t* total, cudaStream_t st);
-// stage D3: one warp per frame: execute sequences block after block
-void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks,
-                          const uint8_t* lits, const uint64_t* seqs, uint8_t* dst, DecCounts* counts, cudaStream_t st);
+// stage D3: one warp per unit of B2Z_DEC_UNIT_BLOCKS consecutive blocks of a frame, units taken in order; a match that reaches
+// behind its unit waits for the unit that writes those bytes.  unitState: [0] ticket, [1 + u] done flag of unit u -- zeroed here.
+size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks);
+void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks,
+                          const uint8_t* lits, const uint64_t* seqs, uint8_t* dst, DecCounts* counts, uint32_t* unitState, cudaStream_t st);
 
 // content checksums (XXH64 low 32 bits) of the frames that carry one: one thread per frame, after D3
 void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st);

@@ -702,6 +702,9 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
         if (b.left() < 0) err = B2Z_DERR_CORRUPT;
         uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
         uint32_t litUsed = 0, total = 0;
+        // the repcode history as a function of the history before the block (b2z_dec.h DecBlock::repX): slot = value (sym 0) or
+        // (initial slot sym - 1) minus value.  ZSTD_decodeSequence's update rules, zstd_decompress_block.c:1290-1312
+        uint32_t v0 = 0, v1 = 0, v2 = 0, y0 = 1, y1 = 2, y2 = 3;
         for (uint32_t i = 0; i < j.nbSeq && !err; i++) {
             const uint2 rL = __ldg(tab + sL), rO = __ldg(tab + 512u + sO), rM = __ldg(tab + 768u + sM);     // {base, nbAdd | nbBits<<8 | next<<16}
             const uint32_t aL = rL.y & 255u, aO = rO.y & 255u, aM = rM.y & 255u;
@@ -718,7 +721,15 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
             litUsed += ll; total += ll + ml;
             if (b.left() < 0 || litUsed > j.litRegen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
             out[i] = SEQ_PACK(ob, ll, ml);
+            if (ob > 3u) { v2 = v1; y2 = y1; v1 = v0; y1 = y0; v0 = ob - 3u; y0 = 0u; }
+            else {
+                const uint32_t idx = ob - 1u + (ll == 0u);
+                if (idx == 1u) { const uint32_t tv = v0, ty = y0; v0 = v1; y0 = y1; v1 = tv; y1 = ty; }
+                else if (idx == 2u) { const uint32_t tv = v2, ty = y2; v2 = v1; y2 = y1; v1 = v0; y1 = y0; v0 = tv; y0 = ty; }
+                else if (idx == 3u) { v2 = v1; y2 = y1; v1 = v0; y1 = y0; v0 = y0 ? v0 + 1u : v0 - 1u; }      // rep0 - 1: one more to subtract, or a smaller value
+            }
         }
+        blocks[bi].repX[0] = v0; blocks[bi].repX[1] = v1; blocks[bi].repX[2] = v2; blocks[bi].repSym = y0 | (y1 << 2) | (y2 << 4);
         if (!err && b.left() != 0) err = B2Z_DERR_CORRUPT;
         regen = total + (j.litRegen - litUsed);
         if (regen > 131072u) err = B2Z_DERR_CORRUPT;
@@ -728,53 +739,88 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
 }
 
 // ---------------------------------------------------------------- D2: layout
-__global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, const DecBlock* __restrict__ blocks, DecCounts* counts) {
+__global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, DecBlock* __restrict__ blocks, DecCounts* counts) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFrames) return;
     uint64_t total = 0; uint32_t st = 0;
     const uint32_t b0 = frames[f].firstBlock, nb = frames[f].nBlocks;
-    for (uint32_t i = 0; i < nb; i++) { total += blocks[b0 + i].regen; st |= blocks[b0 + i].status; }
+    uint32_t r0 = 1, r1 = 4, r2 = 8;                                         // the format's starting history
+    for (uint32_t i = 0; i < nb; i++) {
+        DecBlock& B = blocks[b0 + i];
+        B.outRel = total; B.repInit[0] = r0; B.repInit[1] = r1; B.repInit[2] = r2;
+        total += B.regen; st |= B.status;
+        if (B.type == 2 && B.nbSeq) {                                         // apply the block's symbolic history (stage D1)
+            const uint32_t in[3] = { r0, r1, r2 }, y = B.repSym;
+            r0 = (y & 3u) ? in[(y & 3u) - 1u] - B.repX[0] : B.repX[0];
+            r1 = ((y >> 2) & 3u) ? in[((y >> 2) & 3u) - 1u] - B.repX[1] : B.repX[1];
+            r2 = ((y >> 4) & 3u) ? in[((y >> 4) & 3u) - 1u] - B.repX[2] : B.repX[2];
+        }
+    }
     if (frames[f].contentSize != ~0ull && frames[f].contentSize != total) st |= B2Z_DERR_CORRUPT;
     frames[f].regen = total;
     if (st) atomicOr(&counts->status, st);
 }
 __global__ void zstd_dec_frame_offsets_kernel(DecFrame* frames, uint32_t nFrames, uint64_t dstCap, DecCounts* counts, uint64_t* total) {
     if (threadIdx.x || blockIdx.x) return;
-    uint64_t o = 0;
-    for (uint32_t f = 0; f < nFrames; f++) { frames[f].dstOff = o; o += frames[f].regen; }
-    *total = o;
+    uint64_t o = 0; uint32_t u = 0;
+    for (uint32_t f = 0; f < nFrames; f++) {
+        frames[f].dstOff = o; o += frames[f].regen;
+        frames[f].pad = u; u += (frames[f].nBlocks + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
+    }
+    *total = o; counts->nUnits = u;
     if (o > dstCap) atomicOr(&counts->status, B2Z_DERR_DSTSIZE);
 }
 
 // ---------------------------------------------------------------- D3: execute
-// One warp per frame, blocks in order.  Sequences are taken 32 at a time (one per lane):
+// One warp per UNIT of B2Z_DEC_UNIT_BLOCKS consecutive blocks of a frame (a frame of up to 1 MiB is one unit).  Units are taken from
+// a ticket counter, so a running unit only ever has lower-numbered units running or finished beside it; stage D2 gave every block its
+// output offset and its starting repcode history, so a unit needs nothing from its predecessors but the BYTES its matches copy.
+// A match whose source starts before the unit's first byte waits for the done flag of the unit(s) that write those bytes -- in the
+// frames of this encoder's long mode that is a far match into a region finished long ago; in a frame with a sliding window the
+// units simply run one behind the other, as one warp per frame did.
+// Inside a unit, blocks in order; sequences are taken 32 at a time (one per lane):
 //   1. repcode history is resolved in order (warp-uniform registers) -> every lane knows its offset;
 //   2. prefix sums give every lane its output position and literal source;
 //   3. all literal runs are copied in parallel;
 //   4. every match whose source ends before the batch's first output byte is copied in parallel;
 //   5. the remaining matches (source overlaps this batch's output) are copied in sequence order,
 //      each as a periodic extension (dst[i] = src[i mod offset]) so its bytes are independent.
-// Long runs (> 32 bytes) are copied by the whole warp instead of one lane.
-__device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane) {
-    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
-}
 __device__ __forceinline__ void warp_copy_match(uint8_t* dst, uint32_t offset, uint32_t n, uint32_t lane) {
     const uint8_t* m = dst - offset;
     if (offset >= n) { for (uint32_t i = lane; i < n; i += 32) dst[i] = __ldcg(m + i); }
     else { for (uint32_t i = lane; i < n; i += 32) dst[i] = __ldcg(m + (i % offset)); }
 }
+// index (within the frame) of the block that writes frame byte `pos`
+__device__ __forceinline__ uint32_t dec_block_of(const DecBlock* __restrict__ fb, uint32_t nb, uint64_t pos) {
+    uint32_t k = (uint32_t)(pos >> 17);                                       // exact while every earlier block is full
+    if (k < nb && fb[k].outRel <= pos && pos < fb[k].outRel + fb[k].regen) return k;
+    uint32_t lo = 0, hi = nb;                                                 // last block with outRel <= pos
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (fb[mid].outRel <= pos) lo = mid; else hi = mid; }
+    return lo;
+}
 
 __global__ void __launch_bounds__(32)
 zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ frames, uint32_t nFrames, DecBlock* __restrict__ blocks,
-                     const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* dst, DecCounts* counts) {
-    if (counts->status) return;                                  // a failed stage: nothing is written
+                     const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* dst, DecCounts* counts, uint32_t* unitState) {
+    if (counts->status) return;                                  // a failed stage: nothing is written (and nobody waits)
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t f = blockIdx.x; f < nFrames; f += gridDim.x) {
+    const uint32_t nUnits = counts->nUnits;
+    volatile uint32_t* done = unitState + 1;
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(unitState, 1u);
+        u = __shfl_sync(B2Z_FULL, u, 0);
+        if (u >= nUnits) break;
+        uint32_t f;                                              // the frame of unit u: last frame with first unit <= u that has blocks
+        { uint32_t lo = 0, hi = nFrames; while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (frames[mid].pad <= u) lo = mid; else hi = mid; } f = lo; }
         const DecFrame fr = frames[f];
+        const DecBlock* __restrict__ fblk = blocks + fr.firstBlock;
+        const uint32_t k0 = (u - fr.pad) * B2Z_DEC_UNIT_BLOCKS, k1 = k0 + B2Z_DEC_UNIT_BLOCKS < fr.nBlocks ? k0 + B2Z_DEC_UNIT_BLOCKS : fr.nBlocks;
         uint8_t* out = dst + fr.dstOff;
-        uint64_t o = 0;                                          // bytes produced in this frame
-        uint32_t rep0 = 1, rep1 = 4, rep2 = 8, err = 0;
-        for (uint32_t bi = fr.firstBlock; bi < fr.firstBlock + fr.nBlocks && !err; bi++) {
+        const uint64_t unitStart = fblk[k0].outRel;
+        uint64_t o = unitStart;                                  // frame bytes produced before the next sequence
+        uint32_t rep0 = fblk[k0].repInit[0], rep1 = fblk[k0].repInit[1], rep2 = fblk[k0].repInit[2], err = 0;
+        for (uint32_t bi = fr.firstBlock + k0; bi < fr.firstBlock + k1 && !err; bi++) {
             const DecBlock blk = blocks[bi];
             if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = src[blk.srcOff + i]; o += blk.rawSize; __syncwarp(); continue; }
             if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = v; o += blk.rawSize; __syncwarp(); continue; }
@@ -820,6 +866,17 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
                 const uint64_t myDst = o + relDst;                                       // frame-relative
                 const bool bad = lane < cnt && (myOff == 0 || myOff > myDst || myOff > fr.windowSize);
                 if (__any_sync(B2Z_FULL, bad)) { err = B2Z_DERR_CORRUPT; break; }
+                // 2b. a source that starts before this unit's first byte: wait for the unit(s) that write it
+                const bool behind = lane < cnt && myDst - myOff < unitStart;
+                if (__any_sync(B2Z_FULL, behind)) {
+                    if (behind) {
+                        const uint64_t a = myDst - myOff, e = (a + ml < unitStart ? a + ml : unitStart) - 1u;
+                        const uint32_t ua = fr.pad + dec_block_of(fblk, fr.nBlocks, a) / B2Z_DEC_UNIT_BLOCKS, ue = fr.pad + dec_block_of(fblk, fr.nBlocks, e) / B2Z_DEC_UNIT_BLOCKS;
+                        for (uint32_t x = ua; x <= ue && x < u; x++) while (done[x] == 0u) __nanosleep(256);
+                        __threadfence();
+                    }
+                    __syncwarp();
+                }
                 // 3. literals.  The batch's literal bytes are contiguous in the literal buffer: lane = byte, 32 per round; byte t belongs to the
                 //    sequence k with litExcl_k <= t < litExcl_k + ll_k (binary search over the lanes' prefix sums) -- one global round trip per
                 //    32 bytes instead of one per byte of the longest run
@@ -837,12 +894,12 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
                     uint32_t indepTotal;
                     const uint32_t mExcl = warp_excl_scan(indep ? ml : 0u, lane, &indepTotal);
                     for (uint32_t u0 = 0; u0 < indepTotal; u0 += 32u) {
-                        const uint32_t u = u0 + lane;
+                        const uint32_t uu = u0 + lane;
                         uint32_t k = 0;
 #pragma unroll
-                        for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(B2Z_FULL, mExcl, (k + st) & 31u); if (k + st < 32u && v <= u) k += st; }
+                        for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(B2Z_FULL, mExcl, (k + st) & 31u); if (k + st < 32u && v <= uu) k += st; }
                         const uint32_t d = __shfl_sync(B2Z_FULL, relDst, k), of = __shfl_sync(B2Z_FULL, myOff, k), me = __shfl_sync(B2Z_FULL, mExcl, k);
-                        if (u < indepTotal) { uint8_t* q = out + o + d + (u - me); *q = __ldcg(q - of); }
+                        if (uu < indepTotal) { uint8_t* q = out + o + d + (uu - me); *q = __ldcg(q - of); }
                     }
                 }
                 __syncwarp();
@@ -856,9 +913,13 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
             }
             if (!err) { const uint32_t tail = blk.litSize - lp; for (uint32_t i = lane; i < tail; i += 32) out[o + i] = lit[lp + i]; o += tail; }
             __syncwarp();
+            if (!err && o != blk.outRel + blk.regen) err = B2Z_DERR_CORRUPT;              // the block wrote what stage D1 said it would
         }
-        if (!err && o != fr.regen) err = B2Z_DERR_CORRUPT;
         if (err && lane == 0) atomicOr(&counts->status, err);
+        // every unit signals, failed or not: nobody waits for ever
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(unitState + 1 + u, 1u);
     }
 }
 
@@ -919,15 +980,18 @@ void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blo
     if (stLit != st) { cudaEventRecord(evJoin, stLit); cudaStreamWaitEvent(st, evJoin, 0); }
 }
 size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks) { return (size_t)nBlocks * (4096u + 1280u * sizeof(SeqEnt) + sizeof(LitJob) + sizeof(SeqJob)) + 256u; }
-void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, const DecBlock* blocks, uint64_t dstCap, DecCounts* counts, uint64_t* total, cudaStream_t st) {
+void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap, DecCounts* counts, uint64_t* total, cudaStream_t st) {
     if (nFrames) zstd_dec_frame_sizes_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(frames, nFrames, blocks, counts);
     zstd_dec_frame_offsets_kernel<<<1, 32, 0, st>>>(frames, nFrames, dstCap, counts, total);
 }
-void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, const uint8_t* lits, const uint64_t* seqs,
-                          uint8_t* dst, DecCounts* counts, cudaStream_t st) {
+size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks) { return ((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u) * 4u; }
+void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
+                          uint8_t* dst, DecCounts* counts, uint32_t* unitState, cudaStream_t st) {
     if (!nFrames) return;
-    const uint32_t grid = nFrames < 148u * 32u ? nFrames : 148u * 32u;
-    zstd_dec_exec_kernel<<<grid, 32, 0, st>>>(src, frames, nFrames, blocks, lits, seqs, dst, counts);
+    cudaMemsetAsync(unitState, 0, zstd_dec_unit_state_bytes(nFrames, nBlocks), st);
+    const uint32_t maxUnits = nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames;          // every frame rounds up once
+    const uint32_t grid = maxUnits < 148u * 32u ? maxUnits : 148u * 32u;        // resident warps; the others' units are taken by whoever finishes
+    zstd_dec_exec_kernel<<<grid, 32, 0, st>>>(src, frames, nFrames, blocks, lits, seqs, dst, counts, unitState);
 }
 #endif
 

@@ -161,15 +161,16 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
     if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64) ||
-        ctx->decScratch[5].reserve(zstd_dec_entropy_scratch_bytes(hc.nBlocks)))
+        ctx->decScratch[5].reserve(zstd_dec_entropy_scratch_bytes(hc.nBlocks) + zstd_dec_unit_state_bytes(hc.nFrames, hc.nBlocks) + 64))
         return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (input too large for one pass)%s");
     launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, ctx->decScratch[5].p, st, st, ctx->ev[4], ctx->ev[5]);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
     launch_zstd_dec_layout(frames, hc.nFrames, blocks, dstCap, counts, total, st);
     CU(cudaGetLastError());
-    launch_zstd_dec_exec((const uint8_t*)d_src, frames, hc.nFrames, blocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
-                         (uint8_t*)d_dst, counts, st);
+    uint32_t* unitState = (uint32_t*)((uint8_t*)ctx->decScratch[5].p + ((zstd_dec_entropy_scratch_bytes(hc.nBlocks) + 15u) & ~(size_t)15u));   // behind D1's scratch
+    launch_zstd_dec_exec((const uint8_t*)d_src, frames, hc.nFrames, blocks, hc.nBlocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
+                         (uint8_t*)d_dst, counts, unitState, st);
     CU(cudaGetLastError());
     launch_zstd_dec_verify((const uint8_t*)d_src, frames, hc.nFrames, (const uint8_t*)d_dst, counts, st);
     CU(cudaGetLastError());

@@ -187,6 +187,7 @@ template <class T> inline T __ldcs(const T* p) { return *p; }
 template <class T, class U> inline void __stcg(T* p, U v) { *p = (T)v; }
 template <class T, class U> inline void __stcs(T* p, U v) { *p = (T)v; }
 inline void __nanosleep(unsigned) { cuemu::yield(); }
+inline void __threadfence() {}
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p |= v; return o; }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
 inline uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t o = *p; if (v > o) *p = v; return o; }

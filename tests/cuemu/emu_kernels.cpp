@@ -237,7 +237,8 @@ int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint
     if (nFrames) cuemu::launch(dim3((nFrames + 127) / 128), dim3(128), 0, [&] { zstd_dec_frame_sizes_kernel(frames.data(), nFrames, blocks.data(), &counts); });
     cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_frame_offsets_kernel(frames.data(), nFrames, dstCap, &counts, &total); });
     if (nFrames) {
-        cuemu::launch(dim3(nFrames < 64u ? nFrames : 64u), dim3(32), 0, [&] { zstd_dec_exec_kernel(src, frames.data(), nFrames, blocks.data(), lits.data(), seqs.data(), dst, &counts); });
+        std::vector<uint32_t> unitState((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u, 0u);
+        cuemu::launch(dim3(nFrames < 5u ? nFrames : 5u), dim3(32), 0, [&] { zstd_dec_exec_kernel(src, frames.data(), nFrames, blocks.data(), lits.data(), seqs.data(), dst, &counts, unitState.data()); });
         cuemu::launch(dim3((nFrames + 63) / 64), dim3(64), 0, [&] { zstd_dec_verify_kernel(src, frames.data(), nFrames, dst, &counts); });
     }
     return counts.status ? -(int64_t)counts.status : (int64_t)total;

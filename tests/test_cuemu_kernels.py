@@ -321,6 +321,27 @@ def test_emulated_zstd_decoder_on_golden_and_reference_frames(pkg, emu):
     assert not (r == n and out == data)
 
 
+def test_emulated_zstd_decoder_frames_of_several_units(pkg, emu):
+    """frames longer than one execution unit (8 blocks): every unit starts from the repcode history stage D2 derived from the blocks'
+    symbolic histories, and a match that reaches behind its unit waits for the unit that wrote the bytes.  Reference-written frames
+    with a sliding window (repcodes and matches cross every unit boundary), a frame of this encoder's long mode (far matches into
+    other regions), blocks of zeros (RLE), noise (raw blocks) and repcode-only stretches in between"""
+    def dec(comp, n):
+        src = np.frombuffer(comp + bytes(64), dtype=np.uint8); dst = np.zeros(n + 64, dtype=np.uint8)
+        r = emu.emu_zstd_decode(src.ctypes.data, len(comp), dst.ctypes.data, n)
+        return r, dst[:max(r, 0)].tobytes()
+    data = (H.far_copies(pkg, (3 << 20) + 777, every=1 << 19, span=(30_000, 90_000), seed=2) + bytes(300_000) + pkg.corpus.entropy_class(1, 200_000).tobytes()
+            + b"abcdefghij" * 40_000 + pkg.corpus.g2(400_000).tobytes())
+    n = len(data)
+    streams = [H.oracle_compress(data, frameLog=23, windowLog=23, regionLog=18, ldmLog=14), H.oracle_compress(data, frameLog=22, windowLog=22)]
+    if H.ref_available():
+        streams += [H.ref_compress(data, level=3), H.ref_compress(data, level=1, checksum=1), H.ref_compress(data, level=12),
+                    H.ref_compress(data, level=3, windowLog=23, enableLongDistanceMatching=1)]
+    for k, comp in enumerate(streams):
+        r, out = dec(comp, n)
+        assert r == n and out == data, k
+
+
 def test_emulated_stage_z_sequence_array_full(pkg, emu):
     """a block whose parse wants more sequences than its array holds (32 768; random 3-byte tokens give one length-3 match every
     three bytes): from there on the matches' bytes stay literals -- the same rule in the oracle and the kernel, and the frame decodes"""
