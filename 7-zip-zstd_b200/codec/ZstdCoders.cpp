@@ -97,9 +97,9 @@ public:
         b200z_set_param(ctx, B200Z_P_FLAGS, 1);               // mcmilk MT frame convention: size hint before each frame
         if (hashLog_ >= 10 && hashLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_L, hashLog_);
         if (chainLog_ >= 10 && chainLog_ <= 22) b200z_set_param(ctx, B200Z_P_HASHLOG_S, chainLog_);
-        // long=N (ZstdEncoder.cpp:322-331: long-distance matching on, window 2^N): the engine's long mode, frames and window of 2^N bytes
-        // (17..27; a smaller N has nothing beyond stage F's reach to find, a larger one is cut to the 128 MiB the format's decoders accept by default)
-        if (long_ && windowLog_ >= 17) b200z_set_param(ctx, B200Z_P_LONG, windowLog_ > 27 ? 27 : windowLog_);
+        // long=N (ZstdEncoder.cpp:322-331: long-distance matching on, window 2^N): the engine's long mode, window 2^N in frames of 8 windows
+        // (21..27; a smaller N has nothing beyond stage F's reach to find, a larger one is cut to the 128 MiB the format's decoders accept by default)
+        if (long_ && windowLog_ >= 21) b200z_set_param(ctx, B200Z_P_LONG, windowLog_ > 27 ? 27 : windowLog_);
         else {
             b200z_set_param(ctx, B200Z_P_LONG, 0);
             if (windowLog_ >= 17) { int64_t fl = 0; b200z_get_param(ctx, B200Z_P_FRAMELOG, &fl); b200z_set_param(ctx, B200Z_P_WINDOWLOG, windowLog_ < fl ? windowLog_ : fl); }

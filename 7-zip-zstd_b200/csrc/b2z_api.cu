@@ -113,12 +113,12 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");
                             ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v;
                             ctx->geom.regionLog = ctx->geom.ldmLog = 0; return 0;                                    // (leaves the long mode)
-    // long mode: frame = window = 2^v bytes, cut into regions of 1 MiB for stage F, + stage L.  0 leaves it (frames of 1 MiB again).
-    case B200Z_P_LONG:      if (v != 0 && (v < 17 || v > B2Z_MAX_LONGLOG)) return fail(ctx, B200Z_E_PARAM, "long: window log out of range%s");
+    // long mode: window 2^v bytes, frames of 8 windows (at most 1 GiB) cut into regions of 1 MiB for stage F, + stage L.
+    // 0 leaves it (frames of 1 MiB again).
+    case B200Z_P_LONG:      if (v != 0 && (v < 21 || v > B2Z_MAX_LONGLOG)) return fail(ctx, B200Z_E_PARAM, "long: window log out of range%s");
                             if (v == 0) { if (ctx->geom.regionLog) { ctx->geom.frameLog = ctx->geom.windowLog = B2Z_DEF_FRAMELOG; } ctx->geom.regionLog = ctx->geom.ldmLog = 0; return 0; }
-                            ctx->geom.frameLog = ctx->geom.windowLog = (uint32_t)v;
-                            ctx->geom.regionLog = v < B2Z_DEF_REGIONLOG ? (uint32_t)v : B2Z_DEF_REGIONLOG;
-                            ctx->geom.ldmLog = v > B2Z_DEF_REGIONLOG ? B2Z_LDM_LOG((uint32_t)v) : 0u;
+                            ctx->geom.windowLog = (uint32_t)v; ctx->geom.frameLog = B2Z_LONG_FRAMELOG((uint32_t)v);
+                            ctx->geom.regionLog = B2Z_DEF_REGIONLOG; ctx->geom.ldmLog = B2Z_LDM_LOG((uint32_t)v);
                             return 0;
     // both tables live in the shared memory of one SM: 2^L + 2^S entries <= 192 KiB
     case B200Z_P_HASHLOG_L: if (v < 8 || v > 15 || (1u << v) + (1u << ctx->geom.hashLogS) > B2Z_MAX_HASHLOG_SUM_WORDS) return fail(ctx, B200Z_E_PARAM, "hashLogL out of range%s"); ctx->geom.hashLogL = (uint32_t)v; return 0;
@@ -153,7 +153,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
     case B200Z_P_CHUNKLOG: *v = ctx->geom.chunkLog; return 0;
-    case B200Z_P_LONG: *v = ctx->geom.regionLog ? ctx->geom.frameLog : 0; return 0;
+    case B200Z_P_LONG: *v = ctx->geom.regionLog ? ctx->geom.windowLog : 0; return 0;
     }
     return B200Z_E_PARAM;
 }
@@ -207,7 +207,7 @@ static int enc_reserve(b200z_ctx* ctx, uint64_t batchBytes, int codec = 0) {
     } else {                                                            // stage F -> stage G: a candidate word and a choice byte per input byte
         bad |= ctx->cand.reserve((size_t)(nFrames * F + 16) * 4u);
         bad |= ctx->choice.reserve((size_t)(nFrames * F + 16));
-        if (ldm_on(ctx->geom, codec)) bad |= ctx->tables.reserve(zstd_enc_ldm_table_words(ctx->geom, nFrames) * 4u);
+        if (ldm_on(ctx->geom, codec)) bad |= ctx->tables.reserve(zstd_enc_ldm_table_words(ctx->geom, nFrames * F) * 4u);
     }
     bad |= ctx->seqs.reserve(nBlocks * B2Z_MAXSEQ * 8ull);
     bad |= ctx->nseq.reserve(nBlocks * 4);
@@ -438,7 +438,8 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
     uint64_t batch = 1ull << ctx->hostBatchLog;
     if ((ctx->geom.flags & B2Z_FLAG_ZSTD_OPT) && batch > (1ull << 30)) batch = 1ull << 30;
     if (nDev > 1) {                                              // about four batches per device, none smaller than one frame per SM
-        uint64_t per = (srcSize + 4 * nDev - 1) / (4 * nDev), floorB = (uint64_t)ctx->smCount * F;
+        const uint64_t unit = long_mode(ctx->geom, 0) ? 1ull << ctx->geom.regionLog : F;        // what one CTA of stage F takes
+        uint64_t per = (srcSize + 4 * nDev - 1) / (4 * nDev), floorB = (uint64_t)ctx->smCount * unit;
         if (per < floorB) per = floorB;
         per = (per + F - 1) / F * F;
         if (per < batch) batch = per;

@@ -27,9 +27,9 @@ size_t zstd_enc_find_smem_bytes(const EncGeom& g);
 cudaError_t launch_zstd_enc_find(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand /* [srcSize + 16] */, uint32_t nCtas,
                                  const uint32_t* ready /* null, or per-chunk arrival flags */, uint32_t readyShift,
                                  uint32_t* errFlag /* set to 1 when an arrival flag never came */, cudaStream_t st);
-// stage L (zstd_enc_ldm.cu), long mode: far matches through a per-frame table of first occurrences of sampled positions; overwrites candidate words
-size_t zstd_enc_ldm_table_words(const EncGeom& g, uint64_t nFrames);
-cudaError_t launch_zstd_enc_ldm(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t* tables /* [nFrames << ldmLog] */, uint32_t smCount, cudaStream_t st);
+// stage L (zstd_enc_ldm.cu), long mode: far matches through per-epoch tables of first occurrences of sampled positions; overwrites candidate words
+size_t zstd_enc_ldm_table_words(const EncGeom& g, uint64_t srcSize);
+cudaError_t launch_zstd_enc_ldm(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t* tables /* [zstd_enc_ldm_table_words] */, uint32_t smCount, cudaStream_t st);
 // stage G (zstd_enc_dp.cu): one warp per 128 KiB block, one lane per 4 KiB segment: minimum-price parse of stage F's candidates
 // -> per-block final sequences + literal bytes.  choice: one scratch byte per input byte.
 size_t zstd_enc_dp_smem_bytes();

@@ -32,15 +32,17 @@
 /* bytes of a block that feed the literal histogram: the first 64 of every 256 */
 #define B2Z_DP_SAMPLED(i)  ((((i) >> 6) & 3u) == 0u)
 #define B2Z_MAX_FRAMELOG   24
-/* long mode (B200Z_P_LONG, the reference's long=N / ZSTD_c_enableLongDistanceMatching, zstd_ldm.c): a frame of up to 2^27 bytes is
+/* long mode (B200Z_P_LONG, the reference's long=N / ZSTD_c_enableLongDistanceMatching, zstd_ldm.c): a frame of 8 windows (window <= 2^27) is
  * cut into REGIONS of 2^regionLog bytes, stage F's unit (its tables start empty in every region); stage L then looks, for one
  * position in 2^B2Z_LDM_RATELOG, for the first place of the frame that holds the same B2Z_LDM_MINMATCH bytes */
 #define B2Z_MAX_LONGLOG    27
 #define B2Z_DEF_REGIONLOG  20
 #define B2Z_LDM_MINMATCH   64u
 #define B2Z_LDM_RATELOG    7u
-#define B2Z_LDM_LOG(windowLog) ((windowLog) - 5u)   /* entries of the per-frame sample table: four per sample of a full frame */
-#define B2Z_LDM_TAGBITS    4u      /* entry = position << 4 | tag, 0xFFFFFFFF = empty                                    */
+#define B2Z_LDM_EPOCHLOG(windowLog) ((windowLog) - 1u)   /* stage L keeps one table per EPOCH of half a window: a position's own epoch and the two before it cover its window */
+#define B2Z_LDM_LOG(windowLog) ((windowLog) - 6u)   /* entries of an epoch's sample table: four per sample of the epoch */
+#define B2Z_LDM_TAGBITS    4u      /* entry = position in the epoch << 4 | tag, 0xFFFFFFFF = empty                       */
+#define B2Z_LONG_FRAMELOG(windowLog) ((windowLog) + 3u > 30u ? 30u : (windowLog) + 3u)   /* long mode: a frame is 8 windows (at most 1 GiB) */
 #define B2Z_CAP            16u     /* stage F compares at most this many bytes (two 8-byte words, no loop); stage G extends a chosen match of this length */
 #define B2Z_MAXSEQ         32768u  /* raw sequences per 128 KiB block (min match 4)          */
 #define B2Z_BLOCK          131072u

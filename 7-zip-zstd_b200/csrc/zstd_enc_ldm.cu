@@ -1,13 +1,15 @@
-// zstd_enc_ldm.cu -- stage L of the Zstandard encoder's long mode (sm_100a): far matches inside frames of up to 128 MiB.
+// zstd_enc_ldm.cu -- stage L of the Zstandard encoder's long mode (sm_100a): matches up to a window of 128 MiB back, in frames of 8 windows.
 //
 // The long mode (B200Z_P_LONG; the reference's long=N -> ZSTD_c_enableLongDistanceMatching + windowLog N, ZstdEncoder.cpp:128-146,
 // 322-331, algorithm zstd_ldm.c:333-470) keeps stage F as it is -- one CTA per REGION of 2^regionLog bytes, tables in shared
 // memory, reach of some tens of KiB -- and adds this stage for what lies further back.  Where the reference walks the input once
 // with a rolling hash and a bucketed table that always holds the recent past, this stage is two passes that are each parallel
 // over every position of the batch (oracle: zstd_enc_oracle.c ldm_frame):
-//   pass 1  every SAMPLE (one position in 128, chosen by the content of its 8 bytes) puts position << 4 | tag into its frame's
-//           direct-mapped table with atomicMin: the table ends up holding the FIRST occurrence of every index -- a pure function;
-//   pass 2  every sample reads its entry; a lower position whose 64 bytes verify is a far match.  It is walked back to where the
+//   pass 1  every SAMPLE (one position in 128, chosen by the content of its 8 bytes) puts position << 4 | tag into the direct-mapped
+//           table of its EPOCH (half a window of the frame) with atomicMin: a table ends up holding the FIRST occurrence of every
+//           index in its epoch -- a pure function;
+//   pass 2  every sample reads its entry in its own epoch's table and in the two before (together: the window), nearest first; a
+//           lower position at most a window back whose 64 bytes verify is a far match.  It is walked back to where the
 //           agreement starts (not past the segment start, not onto a lower sample: one owner per position, so the writes do not
 //           race) and replaces the candidate word there unless stage F's word is as long and itself verifies 64 bytes.
 // Stage G prices the word like any other and extends it by direct comparison when it chooses it.
@@ -37,8 +39,8 @@ __device__ __forceinline__ bool ldm_same64(const uint64_t* __restrict__ w8, uint
 template <int PASS>
 __global__ void __launch_bounds__(B2Z_LDM_THREADS)
 zstd_enc_ldm_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ cand, uint32_t* __restrict__ tables) {
-    const uint32_t L = g.ldmLog;
-    const uint32_t W = g.windowLog >= 32 ? 0xFFFFFFFFu : (1u << g.windowLog);
+    const uint32_t L = g.ldmLog, E = B2Z_LDM_EPOCHLOG(g.windowLog);
+    const uint32_t W = 1u << g.windowLog;
     const uint32_t tagMask = (1u << B2Z_LDM_TAGBITS) - 1u;
     const uint64_t* __restrict__ all8 = reinterpret_cast<const uint64_t*>(src);
     const uint64_t nWords = (srcSize + 7u) >> 3;
@@ -58,19 +60,23 @@ zstd_enc_ldm_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g
         if (!hits) continue;
         const uint8_t* __restrict__ fb = src + f0;
         const uint64_t* __restrict__ w8 = reinterpret_cast<const uint64_t*>(fb);
-        uint32_t* __restrict__ T = tables + ((size_t)f << L);
         uint32_t* __restrict__ out = cand + f0;
+        const uint64_t ep0 = f0 >> E;                                          // frames are whole epochs: the frame's first table
         for (; hits; hits &= hits - 1u) {
             const uint32_t p = p0 + (uint32_t)__ffs((int)hits) - 1u;
             const uint64_t key = b2z_ldm_key(ldm_ld64(w8, p), ldm_ld64(w8, p + 8u), ldm_ld64(w8, p + 16u), ldm_ld64(w8, p + 24u));
             const uint32_t idx = (uint32_t)(key >> (64u - L)), tag = (uint32_t)(key >> (64u - L - B2Z_LDM_TAGBITS)) & tagMask;
-            if (PASS == 0) { atomicMin(&T[idx], (p << B2Z_LDM_TAGBITS) | tag); continue; }
-            const uint32_t e = T[idx];
-            if ((e & tagMask) != tag) continue;
-            const uint32_t q = e >> B2Z_LDM_TAGBITS;
-            if (q >= p) continue;                                              // the first occurrence itself
-            const uint32_t d = p - q;
-            if (d > W || !ldm_same64(w8, q, p)) continue;
+            const uint32_t ep = p >> E;
+            if (PASS == 0) { atomicMin(&tables[((ep0 + ep) << L) + idx], ((p - (ep << E)) << B2Z_LDM_TAGBITS) | tag); continue; }
+            uint32_t d = 0;
+            for (uint32_t back = 0; back <= 2u && back <= ep && !d; back++) {
+                const uint32_t e = tables[((ep0 + ep - back) << L) + idx];
+                if (e == 0xFFFFFFFFu || (e & tagMask) != tag) continue;
+                const uint32_t q = ((ep - back) << E) + (e >> B2Z_LDM_TAGBITS);
+                if (q >= p || p - q >= W) continue;                            // the first occurrence itself / beyond the window
+                if (ldm_same64(w8, q, p)) d = p - q;
+            }
+            if (!d) continue;
             uint32_t s0 = p; const uint32_t segStart = p & ~(B2Z_SEG - 1u);
             while (s0 > segStart && s0 > d && fb[s0 - 1u] == fb[s0 - 1u - d] && !b2z_ldm_sampled(ldm_ld64(w8, s0 - 1u))) s0--;
             const uint32_t segEnd = ((p | (B2Z_SEG - 1u)) + 1u) < n ? ((p | (B2Z_SEG - 1u)) + 1u) : n;
@@ -84,12 +90,15 @@ zstd_enc_ldm_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g
 }
 
 #ifndef B2Z_CUEMU
-size_t zstd_enc_ldm_table_words(const EncGeom& g, uint64_t nFrames) { return (size_t)nFrames << g.ldmLog; }
+size_t zstd_enc_ldm_table_words(const EncGeom& g, uint64_t srcSize) {       // one table per epoch (frames are whole epochs, the last one may be ragged)
+    const uint32_t E = B2Z_LDM_EPOCHLOG(g.windowLog);
+    return (size_t)((srcSize + (1ull << E) - 1) >> E) << g.ldmLog;
+}
 
 cudaError_t launch_zstd_enc_ldm(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* cand, uint32_t* tables, uint32_t smCount, cudaStream_t st) {
     if (srcSize == 0 || !g.ldmLog) return cudaSuccess;
-    const uint64_t nFrames = (srcSize + (1ull << g.frameLog) - 1) >> g.frameLog, nWords = (srcSize + 7u) >> 3;
-    cudaError_t e = cudaMemsetAsync(tables, 0xFF, zstd_enc_ldm_table_words(g, nFrames) * 4u, st);
+    const uint64_t nWords = (srcSize + 7u) >> 3;
+    cudaError_t e = cudaMemsetAsync(tables, 0xFF, zstd_enc_ldm_table_words(g, srcSize) * 4u, st);
     if (e != cudaSuccess) return e;
     uint64_t ctas = (nWords + B2Z_LDM_THREADS - 1) / B2Z_LDM_THREADS;
     if (ctas > (uint64_t)smCount * 8u) ctas = (uint64_t)smCount * 8u;

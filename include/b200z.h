@@ -60,10 +60,10 @@ extern "C" {
                                    candidates + a per-block dynamic programme over adaptive code statistics -- the role of
                                    zstd_opt.c:1077 ZSTD_compressBlock_opt_generic.  B200Z_P_LEVEL sets it (>= 8); set it after the level to override */
 #define B200Z_P_LONG        14  /* Zstandard encoder, long mode (the reference's long=N: ZstdEncoder.cpp:128-146 -> ZSTD_c_enableLongDistanceMatching + windowLog N,
-                                   zstd_ldm.c): 0 = off (default), 17..27 = frames and window of 2^N bytes.  A frame is cut into 1 MiB regions, stage F's unit;
-                                   stage L finds matches of >= 64 bytes in earlier regions of the frame through a table of content-chosen samples.
-                                   The parse is stage G's at every level (the price-based stage C + Z works on frames of <= 16 MiB).  Sets FRAMELOG and WINDOWLOG;
-                                   set B200Z_P_FRAMELOG afterwards to leave the mode */
+                                   zstd_ldm.c): 0 = off (default), 21..27 = window of 2^N bytes in frames of 8 windows (at most 1 GiB).  A frame is cut into
+                                   1 MiB regions, stage F's unit; stage L finds matches of >= 64 bytes up to a window back through tables of content-chosen
+                                   samples.  The parse is stage G's at every level (the price-based stage C + Z works on frames of <= 16 MiB).
+                                   Sets FRAMELOG and WINDOWLOG; set B200Z_P_FRAMELOG afterwards to leave the mode */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 30 (the decoder takes twice that) */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,

@@ -119,32 +119,37 @@ static void candidates_region(const uint8_t *src, uint32_t n, const b2zo_enc_par
  * for the device as a pure function of the frame's bytes, in two passes that are each parallel over every position:
  *   - position p is a SAMPLE when a hash of its 8 bytes has its top B2Z_LDM_RATELOG bits set (content-defined, so both ends of a
  *     far copy sample the same places); its key hashes the 32 bytes at p;
- *   - pass 1: one direct-mapped table per frame, entry = position << 4 | tag, keeps the LOWEST sample of every index (atomicMin
- *     on the device): the first occurrence in the frame;
- *   - pass 2: a sample whose entry is a lower position with its tag, at most a window back, and whose 64 bytes verify, is walked
+ *   - the frame is cut into EPOCHS of half a window; pass 1: one direct-mapped table per epoch, entry = position in the epoch
+ *     << 4 | tag, keeps the LOWEST sample of every index (atomicMin on the device): the first occurrence in the epoch;
+ *   - pass 2: a sample looks its index up in its own epoch's table and the two before it (together they cover the window), nearest
+ *     first; the first entry that is a lower position with its tag, at most a window back, and whose 64 bytes verify, is walked
  *     BACK to where the agreement starts (not past the segment start, not onto a lower sample -- every position has one owner);
  *     the candidate word there becomes (min(B2Z_CAP, bytes to the segment end), distance) unless stage F's candidate there is
  *     as long AND itself verifies 64 bytes (it is nearer, so cheaper).
  * Stage G prices the word like any other; chosen, it is extended by direct comparison to its true length (or the segment end). */
 static void ldm_frame(const uint8_t *src, uint32_t n, const b2zo_enc_params *P, uint32_t *cand) {
-    const uint32_t L = P->ldmLog;
-    const uint64_t W = P->windowLog >= 32 ? 0xFFFFFFFFull : (1ull << P->windowLog);
+    const uint32_t L = P->ldmLog, E = B2Z_LDM_EPOCHLOG(P->windowLog), nE = (uint32_t)(((uint64_t)n + (1u << E) - 1) >> E);
+    const uint64_t W = 1ull << P->windowLog;
     const uint32_t tagMask = (1u << B2Z_LDM_TAGBITS) - 1;
     if (n < B2Z_LDM_MINMATCH) return;
-    uint32_t *T = (uint32_t *)malloc((size_t)4 << L);
-    memset(T, 0xFF, (size_t)4 << L);
+    uint32_t *T = (uint32_t *)malloc(((size_t)nE << L) * 4);
+    memset(T, 0xFF, ((size_t)nE << L) * 4);
     for (int pass = 0; pass < 2; pass++)
         for (uint32_t p = 0; p + B2Z_LDM_MINMATCH <= n; p++) {
             if (!b2z_ldm_sampled(rd64(src + p))) continue;
             const uint64_t key = b2z_ldm_key(rd64(src + p), rd64(src + p + 8), rd64(src + p + 16), rd64(src + p + 24));
             const uint32_t idx = (uint32_t)(key >> (64 - L)), tag = (uint32_t)(key >> (64 - L - B2Z_LDM_TAGBITS)) & tagMask;
-            if (pass == 0) { const uint32_t e = (p << B2Z_LDM_TAGBITS) | tag; if (e < T[idx]) T[idx] = e; continue; }
-            const uint32_t e = T[idx];
-            if ((e & tagMask) != tag) continue;                                  /* (an index somebody wrote is never empty here) */
-            const uint32_t q = e >> B2Z_LDM_TAGBITS;
-            if (q >= p) continue;                                                /* this is the first occurrence itself */
-            const uint32_t d = p - q;
-            if (d > W || count_match(src + q, src + p, B2Z_LDM_MINMATCH) < B2Z_LDM_MINMATCH) continue;
+            const uint32_t ep = p >> E;
+            if (pass == 0) { uint32_t *t = T + ((size_t)ep << L) + idx; const uint32_t e = ((p - (ep << E)) << B2Z_LDM_TAGBITS) | tag; if (e < *t) *t = e; continue; }
+            uint32_t d = 0;
+            for (uint32_t back = 0; back <= 2 && back <= ep && !d; back++) {
+                const uint32_t e = T[((size_t)(ep - back) << L) + idx];
+                if (e == 0xFFFFFFFFu || (e & tagMask) != tag) continue;
+                const uint32_t q = ((ep - back) << E) + (e >> B2Z_LDM_TAGBITS);
+                if (q >= p || p - q >= W) continue;                              /* the first occurrence itself / beyond the window */
+                if (count_match(src + q, src + p, B2Z_LDM_MINMATCH) >= B2Z_LDM_MINMATCH) d = p - q;
+            }
+            if (!d) continue;
             uint32_t s0 = p; const uint32_t segStart = p & ~(B2Z_SEG - 1);
             while (s0 > segStart && s0 > d && src[s0 - 1] == src[s0 - 1 - d] && !b2z_ldm_sampled(rd64(src + s0 - 1))) s0--;
             const uint32_t segEnd = ((p | (B2Z_SEG - 1)) + 1) < n ? ((p | (B2Z_SEG - 1)) + 1) : n;

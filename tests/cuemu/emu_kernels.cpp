@@ -48,12 +48,12 @@ uint64_t emu_zstd_enc_find(const uint8_t* src, uint64_t srcSize, uint32_t frameL
 }
 
 // long mode: stage F per region, then stage L per frame (zstd_enc_ldm_kernel): candidate words as the oracle's b2zo_zstd_candidates
-uint64_t emu_zstd_enc_find_long(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t regionLog, uint32_t ldmLog, uint32_t nCtas, uint32_t* cand) {
-    EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, 0); g.regionLog = regionLog; g.ldmLog = ldmLog;
+uint64_t emu_zstd_enc_find_long(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t windowLog, uint32_t regionLog, uint32_t ldmLog, uint32_t nCtas, uint32_t* cand) {
+    EncGeom g = geom(frameLog, windowLog, B2Z_DEF_CHUNKLOG, 0); g.regionLog = regionLog; g.ldmLog = ldmLog;
     EncGeom gF = g; gF.frameLog = regionLog;
     uint64_t c = run_find(src, srcSize, gF, nCtas, cand);
-    const uint64_t nFrames = (srcSize + (1ull << frameLog) - 1) >> frameLog;
-    std::vector<uint32_t> tables((size_t)nFrames << ldmLog, 0xFFFFFFFFu);                // (launch_zstd_enc_ldm: cudaMemsetAsync 0xFF)
+    const uint32_t E = B2Z_LDM_EPOCHLOG(windowLog);
+    std::vector<uint32_t> tables((size_t)((srcSize + (1ull << E) - 1) >> E) << ldmLog, 0xFFFFFFFFu);   // (launch_zstd_enc_ldm: cudaMemsetAsync 0xFF)
     c += cuemu::launch(dim3(nCtas), dim3(B2Z_LDM_THREADS), 0, [&] { zstd_enc_ldm_kernel<0>(src, srcSize, g, cand, tables.data()); });
     c += cuemu::launch(dim3(nCtas), dim3(B2Z_LDM_THREADS), 0, [&] { zstd_enc_ldm_kernel<1>(src, srcSize, g, cand, tables.data()); });
     return c;

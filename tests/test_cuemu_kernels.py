@@ -26,7 +26,7 @@ def emu():
     vp, u32, u64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64
     E.emu_zstd_enc_match.restype = u64; E.emu_zstd_enc_match.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp, vp, vp, vp]
     E.emu_zstd_enc_find.restype = u64; E.emu_zstd_enc_find.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp]
-    E.emu_zstd_enc_find_long.restype = u64; E.emu_zstd_enc_find_long.argtypes = [vp, u64, u32, u32, u32, u32, vp]
+    E.emu_zstd_enc_find_long.restype = u64; E.emu_zstd_enc_find_long.argtypes = [vp, u64, u32, u32, u32, u32, u32, vp]
     E.emu_lzma2_cand.restype = u64; E.emu_lzma2_cand.argtypes = [vp, u64, u32, u32, u32, vp]
     E.emu_lzma2_parse.restype = u64; E.emu_lzma2_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp]
     E.emu_zstd_enc_parse.restype = u64; E.emu_zstd_enc_parse.argtypes = [vp, u64, u32, u32, vp, vp, vp, vp, vp]
@@ -73,19 +73,23 @@ def test_emulated_stage_f_level_ladder(pkg, emu, level, flag):
     assert not np.array_equal(base, want)
 
 
-@pytest.mark.parametrize("fl,rl,ll,ctas", [(20, 17, 12, 2), (19, 17, 10, 1), (21, 18, 13, 3)])
-def test_emulated_long_mode_candidates_equal_the_oracle(pkg, emu, fl, rl, ll, ctas):
-    """long mode: stage F per region + zstd_enc_ldm_kernel per frame == b2zo_zstd_candidates (regions, stage L's samples, the walk back
-    to the start of the agreement, the keep-the-nearer rule), on data with copies planted in other regions of the frame, some mutated"""
+@pytest.mark.parametrize("fl,wl,rl,ll,ctas", [(20, 19, 17, 12, 2), (19, 19, 17, 10, 1), (21, 18, 17, 11, 3)])
+def test_emulated_long_mode_candidates_equal_the_oracle(pkg, emu, fl, wl, rl, ll, ctas):
+    """long mode: stage F per region + the two passes of zstd_enc_ldm_kernel == b2zo_zstd_candidates (regions, stage L's samples and
+    epoch tables, the window, the walk back to the start of the agreement, the keep-the-nearer rule), on data with copies planted
+    all over the frame, some mutated"""
     data = H.far_copies(pkg, (5 << 18) + 12345, every=1 << 17, span=(20_000, 60_000), seed=fl)
     n = len(data)
     src = np.frombuffer(data + bytes(64), dtype=np.uint8)
-    want = H.oracle_candidates(data, frameLog=fl, windowLog=fl, regionLog=rl, ldmLog=ll)
-    plain = H.oracle_candidates(data, frameLog=fl, windowLog=fl, regionLog=rl, ldmLog=0)
-    far = int(((want >> 5) >= (1 << rl)).sum())
-    assert far > 50 and not np.array_equal(want, plain)                     # stage L did find matches further back than a region
+    want = H.oracle_candidates(data, frameLog=fl, windowLog=wl, regionLog=rl, ldmLog=ll)
+    plain = H.oracle_candidates(data, frameLog=fl, windowLog=wl, regionLog=rl, ldmLog=0)
+    off = want >> 5
+    assert int((off >= (1 << rl)).sum()) > 50 and not np.array_equal(want, plain)          # stage L did find matches further back than a region
+    assert int(off.max()) < (1 << wl)                                                        # ... and none beyond the window
+    if fl > wl:
+        assert int((off > (1 << (wl - 1))).sum()) > 5                                         # found through the table of an earlier epoch
     got = np.full(((n + (1 << fl) - 1) >> fl << fl) + 16, 0xCDCDCDCD, dtype=np.uint32)
-    emu.emu_zstd_enc_find_long(src.ctypes.data, n, fl, rl, ll, ctas, got.ctypes.data)
+    emu.emu_zstd_enc_find_long(src.ctypes.data, n, fl, wl, rl, ll, ctas, got.ctypes.data)
     assert np.array_equal(got[:n], want)
 
 

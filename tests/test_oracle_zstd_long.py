@@ -26,10 +26,10 @@ def test_long_mode_finds_far_copies_and_stays_valid(pkg):
     n = (24 << 20) + 777
     data = H.far_copies(pkg, n, every=4 << 20, span=(256 << 10, 1 << 20))
     plain = H.oracle_compress(data)
-    long_ = H.oracle_compress(data, frameLog=25, windowLog=25, regionLog=20, ldmLog=20)
+    long_ = H.oracle_compress(data, frameLog=28, windowLog=25, regionLog=20, ldmLog=19)      # what B200Z_P_LONG 25 sets
     assert H.oracle_decompress(long_, n) == data
     fr = _frames(long_)
-    assert [(w, s) for w, s, _ in fr] == [(25, n)]                             # one frame, window 2^25
+    assert [(w, s) for w, s, _ in fr] == [(25, n)]                             # one frame (of up to 8 windows), window 2^25
     gain = len(plain) - len(long_)
     assert gain > 1_000_000
     if H.ref_available():
@@ -49,23 +49,23 @@ def test_long_mode_without_far_copies_changes_little(pkg):
     assert H.oracle_compress(data[:1 << 20], frameLog=20, windowLog=20, regionLog=20, ldmLog=13) == H.oracle_compress(data[:1 << 20])
 
 
-def test_frames_of_128_mib_reach_the_whole_window(pkg):
-    """long=27: one full 128 MiB frame and a ragged second one; copies planted up to ~100 MiB back are coded as matches
-    (offsets beyond 64 MiB appear), and the reference decodes the stream with its default window limit (2^27)"""
-    n = (1 << 27) + (9 << 20) + 12345
-    data = H.far_copies(pkg, n, every=16 << 20, span=(1 << 20, 2 << 20), seed=5)
-    p = dict(frameLog=27, windowLog=27, regionLog=20, ldmLog=22)
+def test_window_of_128_mib(pkg):
+    """long=27: window 2^27 in a frame of up to 1 GiB; copies planted up to 128 MiB back are coded as matches (offsets beyond
+    64 MiB appear, none beyond the window), and the reference decodes the stream with its default window limit (2^27)"""
+    n = (1 << 27) + (41 << 20) + 12345
+    data = H.far_copies(pkg, n, every=16 << 20, span=(1 << 20, 2 << 20), seed=5, back=128 << 20)
+    p = dict(frameLog=30, windowLog=27, regionLog=20, ldmLog=21)
     comp = H.oracle_compress(data, **p)
     fr = _frames(comp)
-    assert [(w, s) for w, s, _ in fr] == [(27, 1 << 27), (24, n - (1 << 27))]
-    seqs, nseq, lits, nlit = H.oracle_find_sequences(data[:1 << 27], **p)
-    far = 0
+    assert [(w, s) for w, s, _ in fr] == [(27, n)]
+    seqs, nseq, lits, nlit = H.oracle_find_sequences(data, **p)
+    far = 0; top = 0
     for b in range(len(nseq)):
         ob = seqs[b * H.MAXSEQ:b * H.MAXSEQ + int(nseq[b])] & np.uint64(0xFFFFFFF)
-        far += int((ob > (64 << 20) + 3).sum())
-    assert far > 10
+        far += int((ob > (64 << 20) + 3).sum()); top = max(top, int(ob.max()) if len(ob) else 0)
+    assert far > 10 and top - 3 < (1 << 27)
     assert H.oracle_decompress(comp, n) == data
     if H.ref_available():
         assert H.ref_decompress(comp, n) == data
     plain = H.oracle_compress(data[:32 << 20])
-    assert len(comp) < len(plain) * (n / (32 << 20)) * 0.97                    # 8 spans of 1-2 MiB in 137 MiB: some 4 % less than without
+    assert len(comp) < len(plain) * (n / (32 << 20)) * 0.97                    # 10 spans of 1-2 MiB in 169 MiB: some 4 % less than without

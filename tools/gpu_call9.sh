@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_zstd_long.py tests/test_gpu_zstd_enc.py tests/test_gpu_lzma2_enc.py tests/test_gpu_zz_zstd_parse.py tests/test_gpu_zstd_dec.py tests/test_ref_7z_host.py -q > gpurun_out/c9_tests.txt 2>&1; echo "tests exit $?" >> gpurun_out/c9_tests.txt
+timeout 900 python -m pytest tests/test_gpu_zstd_long.py -q > gpurun_out/c9_tests.txt 2>&1; echo "tests exit $?" >> gpurun_out/c9_tests.txt
 tail -8 gpurun_out/c9_tests.txt
 timeout 900 python tools/tools_probe_long.py 8192 27 > gpurun_out/c9_long.txt 2>&1; tail -5 gpurun_out/c9_long.txt
