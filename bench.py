@@ -34,6 +34,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=4096, help="sample for the CPU reference arm (default: the GPU arm's 4 GiB, same config; ~7 s per pass on 128 threads)")
     ap.add_argument("--no-files-extra", action="store_true", help="skip extra.many_files_7z (BASELINE configs[4]: 100 000 files of 64 KiB -> one non-solid .7z, one GPU pass)")
     ap.add_argument("--no-lzma2-extra", action="store_true", help="skip extra.lzma2 (BASELINE configs[3] measured beside the zstd headline: method 21 as -m0=flzma2 -mx5 selects it)")
+    ap.add_argument("--no-long-extra", action="store_true", help="skip extra.long_range (BASELINE configs[2]: 8 GiB of text with far copies, long=27)")
+    ap.add_argument("--long-mib", type=int, default=8192, help="extra.long_range: MiB of G3 input (configs[2]: 8 GiB)")
     ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
                     help="zstd: method 4F71101 level 3 (the headline, BASELINE configs[1]); lzma2: method 21 (configs[3])")
     ap.add_argument("--level", type=int, default=3, help="--codec zstd: B200Z_P_LEVEL (1-7 stage M, the measured headline; 8-22 the price-based stage C + stage Z)")
@@ -128,6 +130,77 @@ def cpu_reference(sample_bytes, seed_offset=0, level=3):
     return {"value": mb / (t_enc + t_dec), "unit": "MB/s", "cores": cores, "kind": kind,
             "sample": f"{sample_bytes >> 20} MiB of the same G2 text, zstd level {level}: encode {enc_threads} threads (zstdmt), decode {dec_threads} thread (reference decoder is single-threaded)",
             "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": sample_bytes / r, "t_enc_s": t_enc, "t_dec_s": t_dec}
+
+
+def cpu_reference_long(data, level, job_mib=0):
+    """configs[2] on the host cores: the reference's encoder as `-m0=zstd:x<level>:long=27` sets it (ZstdEncoder.cpp:300-331: level,
+    nbWorkers = #CPUs, enableLongDistanceMatching, windowLog 27) on `data` (a numpy sample of the G3 input).  job_mib != 0 sets
+    ZSTD_c_jobSize: zstdmt's default job for a 128 MiB window is 512 MiB -- two jobs per GiB, two busy threads -- so the level-19
+    sample is run with smaller jobs to use the cores within the bench's time; the ratio it gets is the reference's at that job size."""
+    import numpy as np
+    import helpers
+    Z = helpers.ref()
+    cores = os.cpu_count() or 1
+    n = data.size
+    c = Z.ZSTD_createCCtx()
+    for k, v in ((100, level), (160, 1), (101, 27), (400, min(cores, 200))) + (((402, job_mib << 20),) if job_mib else ()):
+        Z.ZSTD_CCtx_setParameter(c, k, v)
+    out = np.zeros(Z.ZSTD_compressBound(n), dtype=np.uint8)
+    t = time.perf_counter(); r = Z.ZSTD_compress2(c, out.ctypes.data, out.size, data.ctypes.data, n); t_enc = time.perf_counter() - t
+    Z.ZSTD_freeCCtx(c)
+    assert not Z.ZSTD_isError(r)
+    back = np.zeros(n, dtype=np.uint8)
+    t = time.perf_counter(); d = Z.ZSTD_decompress(back.ctypes.data, n, out.ctypes.data, r); t_dec = time.perf_counter() - t
+    assert d == n
+    mb = n / 1e6
+    return {"value": mb / (t_enc + t_dec), "unit": "MB/s", "cores": cores, "kind": "reference", "level": level,
+            "sample": f"first {n >> 20} MiB of the same G3 input, zstd level {level} long=27, {min(cores, 200)} workers, job size {str(job_mib) + ' MiB' if job_mib else 'default (4 windows)'}",
+            "enc_MBps": mb / t_enc, "dec_MBps": mb / t_dec, "ratio": n / r}
+
+
+def long_range(pkg, local, mib, cpu=True):
+    """BASELINE configs[2]: text with long-range redundancy (G3: every 64 MiB a span of 1-4 MiB copied from up to 128 MiB back, 0.1 %
+    of its bytes changed), `long=27`: the engine's long mode (frames of 1 GiB, window 128 MiB, stage L), resident in HBM, one timed
+    pass after a warm-up; the plain mode on the same bytes beside it, and the reference's levels 3 and 19 with long=27 on a sample."""
+    import torch
+    n = mib << 20
+    host = pkg.corpus.g3(n)
+    d_in = torch.from_numpy(host).cuda()
+    rec = {"workload": f"zstd long=27 (window 128 MiB, frames of 1 GiB), {mib} MiB G3 (G2 text + far copies, seed 3) resident in HBM, 1 timed pass"}
+    for name, params in (("plain", {}), ("long27", {"long": 27})):
+        c = pkg.Codec(local, **params)
+        d_comp = torch.empty(c.compress_bound(n), dtype=torch.uint8, device="cuda"); d_back = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+        wn = min(n, 1 << 30)
+        m = c.compress_device(d_in.data_ptr(), wn, d_comp.data_ptr(), d_comp.numel()); c.decompress_device(d_comp.data_ptr(), m, d_back.data_ptr(), wn)
+        c.reset_stats(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); m = c.compress_device(d_in.data_ptr(), n, d_comp.data_ptr(), d_comp.numel()); torch.cuda.synchronize(); t1 = time.perf_counter()
+        r = c.decompress_device(d_comp.data_ptr(), m, d_back.data_ptr(), n); torch.cuda.synchronize(); t2 = time.perf_counter()
+        assert r == n and torch.equal(d_back[:n], d_in), "long-range round trip mismatch"
+        mb = n / 1e6
+        rec[name] = {"value": mb / (t2 - t0), "unit": "MB/s", "enc_MBps": mb / (t1 - t0), "dec_MBps": mb / (t2 - t1), "ratio": n / m,
+                     "kernel_ms": {k: c.stat(v) for k, v in dict(find_and_ldm=1, parse=10, entropy=2, assemble=3, dec_prepass=9, dec_entropy=4, dec_exec=5).items()}}
+        c.close(); del d_comp, d_back
+    rec["value"] = rec["long27"]["value"]; rec["unit"] = "MB/s"; rec["ratio"] = rec["long27"]["ratio"]
+    rec["gain_over_plain_pct"] = 100.0 * (rec["long27"]["ratio"] / rec["plain"]["ratio"] - 1.0)
+    del d_in
+    torch.cuda.empty_cache()
+    if cpu:
+        import helpers
+        if helpers.ref_available():
+            sample = host[:min(n, 1 << 30)]
+            c = pkg.Codec(local, long=27)                                  # the same sample through the engine, for a like-for-like ratio
+            ours = len(c.compress(sample)); c.close()
+            rec["sample_ratio"] = sample.size / ours
+            cb = cpu_reference_long(sample, 3)
+            cb["ratio_delta_pct"] = 100.0 * (rec["sample_ratio"] / cb["ratio"] - 1.0)
+            rec["cpu_reference_L3"] = cb
+            try:                                                           # level 19 takes minutes per GiB: measured once with tools/ref_cfg3.py on the same sample
+                l19 = json.load(open(os.path.join(ROOT, "profiles", "r2_cfg3_reference.json")))["L19"]
+                rec["reference_L19_recorded"] = {"ratio": l19["ratio"], "enc_MBps": l19["enc_MBps"], "cores": l19["cores"], "sample_MiB": l19["sample_MiB"], "job_MiB": l19["jobSize_MiB"],
+                                                 "ratio_delta_pct": 100.0 * (rec["sample_ratio"] / l19["ratio"] - 1.0), "source": "profiles/r2_cfg3_reference.json"}
+            except Exception:
+                pass
+    return rec
 
 
 def cpu_reference_lzma2(sample_bytes, seed_offset=0):
@@ -448,6 +521,13 @@ def main():
             line.setdefault("extra", {})["many_files_7z"] = many_files_7z(pkg, codec, cpu=not a.no_cpu_baseline)
         except Exception as e:
             line.setdefault("extra", {})["many_files_7z"] = {"error": str(e)[:200]}
+    if not lz and world == 1 and not a.no_long_extra:
+        try:
+            del d_in
+            torch.cuda.empty_cache()
+            line.setdefault("extra", {})["long_range"] = long_range(pkg, local, a.long_mib, cpu=not a.no_cpu_baseline)
+        except Exception as e:
+            line.setdefault("extra", {})["long_range"] = {"error": str(e)[:200]}
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_ref(a.cpu_sample_mib << 20)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
