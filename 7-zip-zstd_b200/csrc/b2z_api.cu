@@ -15,6 +15,20 @@
 
 using namespace b2z;
 
+__global__ void b2z_store_small_kernel(uint64_t* __restrict__ hostDst, const uint64_t* __restrict__ src, uint32_t nWords) {
+    if (threadIdx.x < nWords) hostDst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+int b2z_fetch_small(b200z_ctx* ctx, void* hostDst, const void* d_src, size_t bytes, cudaStream_t st) {
+    if (bytes > 256 || (bytes & 7u)) return fail(ctx, B200Z_E_PARAM, "b2z_fetch_small: size%s");
+    if (!ctx->hostSmall && cudaHostAlloc((void**)&ctx->hostSmall, 256, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return fail(ctx, B200Z_E_MEMORY, "pinned allocation failed%s"); }
+    b2z_store_small_kernel<<<1, 32, 0, st>>>(ctx->hostSmall, (const uint64_t*)d_src, (uint32_t)(bytes / 8));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    memcpy(hostDst, ctx->hostSmall, bytes);
+    return 0;
+}
+
 extern "C" {
 
 int b200z_device_count(void) {
@@ -90,6 +104,7 @@ void b200z_destroy(b200z_ctx* ctx) {
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     for (int i = 0; i < 4; i++) if (ctx->pe[i]) cudaEventDestroy(ctx->pe[i]);
     if (ctx->hostOne) cudaFreeHost(ctx->hostOne);
+    if (ctx->hostSmall) cudaFreeHost(ctx->hostSmall);
     delete ctx;
 }
 
@@ -287,8 +302,7 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         CU(cudaEventRecord(ctx->ev[3], st));
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
         uint64_t hs[9] = {0};
-        CU(cudaMemcpyAsync(hs, ctx->scalars.p, 72, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        { const int frc = b2z_fetch_small(ctx, hs, ctx->scalars.p, 72, st); if (frc) return frc; }
         if ((uint32_t)hs[8]) return fail(ctx, B200Z_E_CUDA, "upload stalled: an input chunk never arrived%s");
         if ((uint32_t)hs[2]) return fail(ctx, B200Z_E_CUDA, "LZMA2: frame slot overflow%s");
         *produced = hs[0];
@@ -308,8 +322,7 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         CU(cudaEventRecord(ctx->ev[3], st));
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
         uint64_t hs[9] = {0};
-        CU(cudaMemcpyAsync(hs, ctx->scalars.p, 72, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        { const int frc = b2z_fetch_small(ctx, hs, ctx->scalars.p, 72, st); if (frc) return frc; }
         if ((uint32_t)hs[8]) return fail(ctx, B200Z_E_CUDA, "upload stalled: an input chunk never arrived%s");
         *produced = hs[0];
         float ms = 0;

@@ -40,6 +40,7 @@ struct b200z_ctx {
     int lz2Mode = 0;                  // LZMA2 decoder literal-model placement: 0 auto, 1 shared memory, 2 global memory
     Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready, batchStage, batchOff, batchSize, cand, choice, crcOff, crcLen, crcOut;
     uint32_t* hostOne = nullptr;      // pinned constant 1 (chunk-arrival flags of the host-pointer path)
+    uint64_t* hostSmall = nullptr;    // 256 pinned bytes the device writes its counters into (b2z_fetch_small)
     Arena decScratch[8];
     cudaEvent_t ev[8] = {};
     double stat[16] = {0};
@@ -52,6 +53,11 @@ static inline int fail(b200z_ctx* c, int code, const char* fmt, const char* deta
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError(); \
     return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? B200Z_E_MEMORY : B200Z_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } } while (0)
+
+// Counters back to the host WITHOUT the copy engine: a one-warp kernel stores them into pinned host memory, then the stream is synchronised.
+// (A cudaMemcpyAsync of a few bytes queues behind whatever the device-to-host engine is doing -- in the host-pointer pipelines the
+// gigabyte download of the previous batch: measured, the kernels of batch k+1 started only when the download of batch k had ended.)
+int b2z_fetch_small(b200z_ctx* ctx, void* hostDst, const void* d_src, size_t bytes /* multiple of 8, <= 256 */, cudaStream_t st);
 
 // b2z_filter.cu: b200z_filter_device with units -- unitLog != 0 (encode only): the buffer is a run of independent units of 2^unitLog
 // bytes (the xz writer filters every Block on its own)

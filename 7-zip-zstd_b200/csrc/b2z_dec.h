@@ -47,6 +47,8 @@ struct DecBlock {
     uint64_t outRel;        // first output byte of the block, relative to its frame (stage D2)
 };
 
+#define B2Z_DEC_ROUNDS 4u            // stage D3: 32-byte rounds of a batch's literal / match copies whose loads are issued together
+#define B2Z_DEC_RING 4096u           // stage D3: bytes of its own latest output a warp mirrors in shared memory
 #define B2Z_DEC_UNIT_BLOCKS 8u       // stage D3: consecutive blocks of a frame executed by one warp (1 MiB of output when the blocks are full)
 
 struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; };

@@ -88,8 +88,7 @@ int b200z_lzma2_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcS
         if (aBlocks.reserve(cap * sizeof(Lz2Block))) return fail(ctx, B200Z_E_MEMORY, "LZMA2: table allocation failed%s");
         launch_lzma2_walk((const uint8_t*)d_src, srcSize, (Lz2Block*)aBlocks.p, (uint32_t)cap, counts, st);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
         ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
         if (hc.status) return lz2_status_to_rc(ctx, hc.status);
         if (hc.nBlocks <= cap) break;
@@ -109,8 +108,7 @@ int b200z_lzma2_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcS
     CU(launch_lzma2_decode((const uint8_t*)d_src, (const Lz2Block*)aBlocks.p, hc.nBlocks, hc.maxLcLp, dictSize, (uint8_t*)d_dst, counts,
                            spill, ctx->smCount, mode, st));
     CU(cudaEventRecord(ctx->ev[2], st));
-    CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += hc.nBlocks ? 1 : 0;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stat[B200Z_S_DEC_PREPASS_MS] += ms;

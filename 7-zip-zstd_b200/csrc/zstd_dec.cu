@@ -803,6 +803,10 @@ __global__ void __launch_bounds__(32)
 zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ frames, uint32_t nFrames, DecBlock* __restrict__ blocks,
                      const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* dst, DecCounts* counts, uint32_t* unitState) {
     if (counts->status) return;                                  // a failed stage: nothing is written (and nobody waits)
+    // the last B2Z_DEC_RING output bytes of this warp, position p at ring[p % B2Z_DEC_RING]: a match that copies bytes of its own batch
+    // (step 5) finds them here after a shared-memory round trip instead of a store-to-L2 / load-from-L2 one.  Batches that write more
+    // than half the ring bypass it; ringFrom = first frame position from which the ring mirrors the output without gaps.
+    __shared__ uint8_t ring[B2Z_DEC_RING];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t nUnits = counts->nUnits;
     volatile uint32_t* done = unitState + 1;
@@ -819,17 +823,20 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
         uint8_t* out = dst + fr.dstOff;
         const uint64_t unitStart = fblk[k0].outRel;
         uint64_t o = unitStart;                                  // frame bytes produced before the next sequence
+        uint64_t ringFrom = unitStart;
         uint32_t rep0 = fblk[k0].repInit[0], rep1 = fblk[k0].repInit[1], rep2 = fblk[k0].repInit[2], err = 0;
         for (uint32_t bi = fr.firstBlock + k0; bi < fr.firstBlock + k1 && !err; bi++) {
             const DecBlock blk = blocks[bi];
-            if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = src[blk.srcOff + i]; o += blk.rawSize; __syncwarp(); continue; }
-            if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = v; o += blk.rawSize; __syncwarp(); continue; }
+            if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = src[blk.srcOff + i]; o += blk.rawSize; ringFrom = o; __syncwarp(); continue; }
+            if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = v; o += blk.rawSize; ringFrom = o; __syncwarp(); continue; }
             const uint8_t* lit = lits + (size_t)bi * 131072u;
             const uint64_t* sq = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
             uint32_t lp = 0;
+            uint64_t ahead = lane < blk.nbSeq ? sq[lane] : 0ull;                             // the next batch's sequences are fetched a batch ahead
             for (uint32_t i0 = 0; i0 < blk.nbSeq && !err; i0 += 32) {
                 const uint32_t cnt = (blk.nbSeq - i0) < 32u ? (blk.nbSeq - i0) : 32u;
-                const uint64_t mine = lane < cnt ? sq[i0 + lane] : 0ull;
+                const uint64_t mine = ahead;
+                ahead = i0 + 32u + lane < blk.nbSeq ? sq[i0 + 32u + lane] : 0ull;
                 const uint32_t ll = lane < cnt ? ((uint32_t)(mine >> 30) & 0x1FFFFu) : 0u;
                 const uint32_t ml = lane < cnt ? ((uint32_t)(mine >> 47) + 3u) : 0u;
                 // 1. repcodes.  A batch without repcode sequences (offBase > 3 everywhere: the usual case) needs no walk: every offset is
@@ -877,41 +884,71 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
                     }
                     __syncwarp();
                 }
+                const bool useRing = total <= B2Z_DEC_RING / 2u;                           // (warp-uniform)
                 // 3. literals.  The batch's literal bytes are contiguous in the literal buffer: lane = byte, 32 per round; byte t belongs to the
-                //    sequence k with litExcl_k <= t < litExcl_k + ll_k (binary search over the lanes' prefix sums) -- one global round trip per
-                //    32 bytes instead of one per byte of the longest run
-                for (uint32_t t0 = 0; t0 < litTotal; t0 += 32u) {
-                    const uint32_t t = t0 + lane;
-                    uint32_t k = 0;
+                //    sequence k with litExcl_k <= t < litExcl_k + ll_k (binary search over the lanes' prefix sums).  B2Z_DEC_ROUNDS rounds are
+                //    taken together: all their loads are issued before the first store needs its byte, so the rounds cost one global
+                //    round trip, not one each (they were 2/3 of this kernel's time: ~10 dependent round trips per 32 sequences)
+                for (uint32_t t0 = 0; t0 < litTotal; t0 += 32u * B2Z_DEC_ROUNDS) {
+                    uint8_t v[B2Z_DEC_ROUNDS];
 #pragma unroll
-                    for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(B2Z_FULL, litExcl, (k + st) & 31u); if (k + st < 32u && v <= t) k += st; }
-                    const uint32_t base = __shfl_sync(B2Z_FULL, excl, k), le = __shfl_sync(B2Z_FULL, litExcl, k);
-                    if (t < litTotal) out[o + base + (t - le)] = lit[lp + t];
+                    for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) { const uint32_t t = t0 + r * 32u + lane; v[r] = t < litTotal ? lit[lp + t] : (uint8_t)0; }
+#pragma unroll
+                    for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) {
+                        const uint32_t t = t0 + r * 32u + lane;
+                        if (t0 + r * 32u >= litTotal) break;                                     // (warp-uniform)
+                        uint32_t k = 0;
+#pragma unroll
+                        for (uint32_t st = 16; st; st >>= 1) { const uint32_t w = __shfl_sync(B2Z_FULL, litExcl, (k + st) & 31u); if (k + st < 32u && w <= t) k += st; }
+                        const uint32_t base = __shfl_sync(B2Z_FULL, excl, k), le = __shfl_sync(B2Z_FULL, litExcl, k);
+                        if (t < litTotal) { const uint64_t pos = o + base + (t - le); out[pos] = v[r]; if (useRing) ring[pos & (B2Z_DEC_RING - 1u)] = v[r]; }
+                    }
                 }
-                // 4. matches that read only bytes produced before this batch: the same flattening over their bytes
+                // 4. matches that read only bytes produced before this batch: the same flattening over their bytes, the same grouping of rounds
                 const bool indep = lane < cnt && (myDst - myOff + ml <= o);
                 {
                     uint32_t indepTotal;
                     const uint32_t mExcl = warp_excl_scan(indep ? ml : 0u, lane, &indepTotal);
-                    for (uint32_t u0 = 0; u0 < indepTotal; u0 += 32u) {
-                        const uint32_t uu = u0 + lane;
-                        uint32_t k = 0;
+                    for (uint32_t u0 = 0; u0 < indepTotal; u0 += 32u * B2Z_DEC_ROUNDS) {
+                        uint64_t pos[B2Z_DEC_ROUNDS]; uint32_t of[B2Z_DEC_ROUNDS]; uint8_t v[B2Z_DEC_ROUNDS];
 #pragma unroll
-                        for (uint32_t st = 16; st; st >>= 1) { const uint32_t v = __shfl_sync(B2Z_FULL, mExcl, (k + st) & 31u); if (k + st < 32u && v <= uu) k += st; }
-                        const uint32_t d = __shfl_sync(B2Z_FULL, relDst, k), of = __shfl_sync(B2Z_FULL, myOff, k), me = __shfl_sync(B2Z_FULL, mExcl, k);
-                        if (uu < indepTotal) { uint8_t* q = out + o + d + (uu - me); *q = __ldcg(q - of); }
+                        for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) {
+                            const uint32_t uu = u0 + r * 32u + lane;
+                            uint32_t k = 0;
+#pragma unroll
+                            for (uint32_t st = 16; st; st >>= 1) { const uint32_t w = __shfl_sync(B2Z_FULL, mExcl, (k + st) & 31u); if (k + st < 32u && w <= uu) k += st; }
+                            const uint32_t d = __shfl_sync(B2Z_FULL, relDst, k), me = __shfl_sync(B2Z_FULL, mExcl, k);
+                            of[r] = __shfl_sync(B2Z_FULL, myOff, k); pos[r] = o + d + (uu - me);
+                        }
+#pragma unroll
+                        for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) v[r] = u0 + r * 32u + lane < indepTotal ? __ldcg(out + pos[r] - of[r]) : (uint8_t)0;
+#pragma unroll
+                        for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++)
+                            if (u0 + r * 32u + lane < indepTotal) { out[pos[r]] = v[r]; if (useRing) ring[pos[r] & (B2Z_DEC_RING - 1u)] = v[r]; }
                     }
                 }
                 __syncwarp();
                 // 5. the rest, in order
                 for (uint32_t dep = __ballot_sync(B2Z_FULL, lane < cnt && !indep); dep; dep &= dep - 1u) {
                     const uint32_t k = (uint32_t)__ffs((int)dep) - 1u;
-                    warp_copy_match(out + __shfl_sync(B2Z_FULL, myDst, k), __shfl_sync(B2Z_FULL, myOff, k), __shfl_sync(B2Z_FULL, ml, k), lane);
+                    const uint64_t dk = __shfl_sync(B2Z_FULL, myDst, k);
+                    const uint32_t ok = __shfl_sync(B2Z_FULL, myOff, k), mk = __shfl_sync(B2Z_FULL, ml, k);
+                    if (useRing && ok <= B2Z_DEC_RING / 2u && dk - ok >= ringFrom) {       // the whole source is in the ring
+                        const uint32_t sk = (uint32_t)(dk - ok);
+                        for (uint32_t i = lane; i < mk; i += 32) {
+                            const uint8_t v = ring[(sk + (ok >= mk ? i : i % ok)) & (B2Z_DEC_RING - 1u)];
+                            out[dk + i] = v; ring[((uint32_t)dk + i) & (B2Z_DEC_RING - 1u)] = v;
+                        }
+                    } else {
+                        warp_copy_match(out + dk, ok, mk, lane);
+                        if (useRing) { __syncwarp(); for (uint32_t i = lane; i < mk; i += 32) ring[((uint32_t)dk + i) & (B2Z_DEC_RING - 1u)] = __ldcg(out + dk + i); }
+                    }
                     __syncwarp();
                 }
+                if (!useRing) ringFrom = o + total;
                 o += total; lp += litTotal;
             }
-            if (!err) { const uint32_t tail = blk.litSize - lp; for (uint32_t i = lane; i < tail; i += 32) out[o + i] = lit[lp + i]; o += tail; }
+            if (!err) { const uint32_t tail = blk.litSize - lp; for (uint32_t i = lane; i < tail; i += 32) out[o + i] = lit[lp + i]; o += tail; if (tail) ringFrom = o; }
             __syncwarp();
             if (!err && o != blk.outRel + blk.regen) err = B2Z_DERR_CORRUPT;              // the block wrote what stage D1 said it would
         }

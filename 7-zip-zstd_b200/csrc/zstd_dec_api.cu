@@ -150,14 +150,13 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     launch_zstd_dec_find_frames((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, counts, st);
     CU(cudaGetLastError());
     DecCounts hc;
-    CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    static_assert(sizeof(DecCounts) == 24, "DecCounts is fetched as three words");
+    { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
     launch_zstd_dec_index_blocks((const uint8_t*)d_src, srcSize, frames, hc.nFrames, blocks, (uint32_t)blockCap, counts, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[3], st));
-    CU(cudaMemcpyAsync(&hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
     if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64) ||
@@ -175,10 +174,8 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     launch_zstd_dec_verify((const uint8_t*)d_src, frames, hc.nFrames, (const uint8_t*)d_dst, counts, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[2], st));
-    struct { DecCounts c; uint64_t total; } hr;
-    CU(cudaMemcpyAsync(&hr.c, counts, sizeof(DecCounts), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&hr.total, total, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    struct { DecCounts c; uint64_t pad; uint64_t total; } hr;                  // counts at +0, the total at +32 of the same 64-byte scratch
+    { const int frc = b2z_fetch_small(ctx, &hr, counts, 40, st); if (frc) return frc; }
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 7;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stat[B200Z_S_DEC_PREPASS_MS] += ms;
@@ -255,6 +252,11 @@ static void dec_worker(b200z_ctx* ctx, DecJob* job, size_t first, size_t stride)
         if (ctx->dIn.reserve(2 * job->inStride) || ctx->dOut.reserve(2 * job->outStride)) return fail(ctx, B200Z_E_MEMORY, "device staging allocation failed%s");
         uint8_t* dIn[2] = { (uint8_t*)ctx->dIn.p, (uint8_t*)ctx->dIn.p + job->inStride };
         uint8_t* dOut[2] = { (uint8_t*)ctx->dOut.p, (uint8_t*)ctx->dOut.p + job->outStride };
+        // B200Z_TRACE=1: per-batch timeline on stderr (ms since the call began): upload done | kernels begin..end | download done
+        const bool trace = getenv("B200Z_TRACE") != nullptr;
+        std::vector<cudaEvent_t> tev;
+        auto mark = [&](cudaStream_t s) { if (!trace) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); };
+        mark(ctx->stream2);
         CU(cudaMemcpyAsync(dIn[0], job->src + B[first].srcOff, B[first].srcEnd - B[first].srcOff, cudaMemcpyHostToDevice, ctx->stream2));
         CU(cudaEventRecord(ctx->pe[0], ctx->stream2));
         size_t k = 0;
@@ -268,15 +270,26 @@ static void dec_worker(b200z_ctx* ctx, DecJob* job, size_t first, size_t stride)
             }
             CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[b], 0));
             if (k >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->pe[2 + b], 0));
+            mark(ctx->stream);
             size_t out = 0;
             int rc = dec_impl(ctx, dIn[b], B[i].srcEnd - B[i].srcOff, dOut[b], (size_t)B[i].dstSize, &out, nullptr);
             if (rc) return rc;
+            mark(ctx->stream);
             if (out != B[i].dstSize) return fail(ctx, B200Z_E_CORRUPT, "frame content size mismatch%s");
             if (out) CU(cudaMemcpyAsync(job->dst + B[i].dstOff, dOut[b], out, cudaMemcpyDeviceToHost, ctx->stream3));
             CU(cudaEventRecord(ctx->pe[2 + b], ctx->stream3));
+            mark(ctx->stream3);
             ctx->stat[B200Z_S_H2D_BYTES] += (double)(B[i].srcEnd - B[i].srcOff); ctx->stat[B200Z_S_D2H_BYTES] += (double)out;
         }
         CU(cudaStreamSynchronize(ctx->stream3));
+        if (trace) {
+            for (size_t j = 1; j + 2 < tev.size() + 0 && j + 2 <= tev.size() - 0; j += 3) {
+                float a = 0, b2 = 0, c = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[j]); cudaEventElapsedTime(&b2, tev[0], tev[j + 1]); cudaEventElapsedTime(&c, tev[0], tev[j + 2]);
+                fprintf(stderr, "[b200z dec dev %d] batch %zu: kernels %.1f..%.1f  download done %.1f\n", ctx->device, (j - 1) / 3, a, b2, c);
+            }
+            for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        }
         return 0;
     };
     const int rc = run();
