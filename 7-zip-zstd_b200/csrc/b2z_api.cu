@@ -458,6 +458,10 @@ int b200z_zstd_compress_host(b200z_ctx* ctx, const void* src, size_t srcSize, vo
         if (per < batch) batch = per;
     }
     if (batch < F) batch = F;
+    {   // whole rounds of stage F's grid (one CTA per SM, one region each): a batch of 1024 regions would end with a round of 136 of 148 CTAs
+        const uint64_t unit = long_mode(ctx->geom, 0) ? 1ull << ctx->geom.regionLog : F, round = (uint64_t)ctx->smCount * unit;
+        if (!(ctx->geom.flags & B2Z_FLAG_ZSTD_OPT) && batch > round && srcSize > batch) { const uint64_t b = batch / round * round; if (b % F == 0) batch = b; }
+    }
     if (nDev == 1 && srcSize <= batch) {
         // one batch: the upload is cut into chunks on stream2, each followed by a flag write; stage M starts at once and
         // its frame-warps wait for their chunk, so the H2D time hides under the match kernel

@@ -34,6 +34,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=4096, help="sample for the CPU reference arm (default: the GPU arm's 4 GiB, same config; ~7 s per pass on 128 threads)")
     ap.add_argument("--no-files-extra", action="store_true", help="skip extra.many_files_7z (BASELINE configs[4]: 100 000 files of 64 KiB -> one non-solid .7z, one GPU pass)")
     ap.add_argument("--no-lzma2-extra", action="store_true", help="skip extra.lzma2 (BASELINE configs[3] measured beside the zstd headline: method 21 as -m0=flzma2 -mx5 selects it)")
+    ap.add_argument("--no-refstreams-extra", action="store_true", help="skip extra.reference_streams (reference-written single-frame zstd and stock LZMA2 streams through the engine's decoders)")
     ap.add_argument("--no-long-extra", action="store_true", help="skip extra.long_range (BASELINE configs[2]: 8 GiB of text with far copies, long=27)")
     ap.add_argument("--long-mib", type=int, default=8192, help="extra.long_range: MiB of G3 input (configs[2]: 8 GiB)")
     ap.add_argument("--codec", default="zstd", choices=["zstd", "lzma2"],
@@ -200,6 +201,47 @@ def long_range(pkg, local, mib, cpu=True):
                                                  "ratio_delta_pct": 100.0 * (rec["sample_ratio"] / l19["ratio"] - 1.0), "source": "profiles/r2_cfg3_reference.json"}
             except Exception:
                 pass
+    return rec
+
+
+def reference_streams(pkg, local, mib=1024, lz_mib=64):
+    """Streams the REFERENCE wrote, through the engine's host-pointer decoders (what the codec module's CDecoder does with a stock archive):
+    zstd level 3 from zstdmt -- ONE frame whatever the thread count (jobs become blocks of one frame, zstdmt_compress.c:1403), 2 MiB sliding
+    window -- and the stock LZMA2 encoder at level 5 (`-m0=lzma2 -mx5`: Lzma2Enc.c, 16 MiB dictionary, a dictionary reset per 64 MiB block
+    when it runs block-threaded).  The engine's parallelism is over independent units: a single sliding-window frame is one chain for the
+    execute stage (entropy decoding stays parallel per block), a raw LZMA2 stream is one chain per dictionary reset."""
+    import numpy as np, torch
+    import helpers
+    rec = {}
+    if not helpers.ref_available():
+        return {"unavailable": "oracle/_ref/libref_zstd.so missing"}
+    cores = os.cpu_count() or 1
+    n = mib << 20
+    data = pkg.corpus.g2(n)
+    c = pkg.Codec(local)
+    comp = helpers.ref_compress(data, level=3, nbWorkers=min(cores, 64))
+    hc = torch.from_numpy(np.frombuffer(comp, dtype=np.uint8).copy()).pin_memory(); hb = torch.empty(n, dtype=torch.uint8).pin_memory()
+    c.decompress_into(hc.data_ptr(), len(comp), hb.data_ptr(), n)                      # warm-up (allocations)
+    c.reset_stats()
+    t = time.perf_counter(); r = c.decompress_into(hc.data_ptr(), len(comp), hb.data_ptr(), n); dt = time.perf_counter() - t
+    assert r == n and torch.equal(hb, torch.from_numpy(data)), "reference-written zstd stream: round trip mismatch"
+    rec["zstd_single_frame"] = {"workload": f"{mib} MiB G2 text, reference zstd level 3 ({min(cores, 64)} workers): one frame, window 2 MiB", "packed_bytes": len(comp),
+                                "dec_MBps": n / 1e6 / dt, "ms": dt * 1e3,
+                                "kernel_ms": {k: c.stat(v) for k, v in dict(prepass=9, entropy=4, layout_exec_verify=5).items()}}
+    del hc, hb
+    if helpers.ref_lzma_available():
+        m = lz_mib << 20
+        prop, lcomp = helpers.ref_lzma2_compress(data[:m], 5, threads=min(cores, 32))
+        blocks = c.lzma2_stream_info(lcomp)[1]
+        hc = torch.from_numpy(np.frombuffer(lcomp, dtype=np.uint8).copy()).pin_memory(); hb = torch.empty(m, dtype=torch.uint8).pin_memory()
+        wprop, wcomp = helpers.ref_lzma2_compress(data[:1 << 20], 5)                    # warm-up on a small stream (one chain of 64 MiB takes seconds)
+        wc = torch.from_numpy(np.frombuffer(wcomp, dtype=np.uint8).copy()).pin_memory()
+        c.lzma2_decompress_into(wc.data_ptr(), len(wcomp), wprop, hb.data_ptr(), 1 << 20)
+        t = time.perf_counter(); r = c.lzma2_decompress_into(hc.data_ptr(), len(lcomp), prop, hb.data_ptr(), m); dt = time.perf_counter() - t
+        assert r == m and torch.equal(hb, torch.from_numpy(data[:m])), "reference-written LZMA2 stream: round trip mismatch"
+        rec["lzma2_mx5"] = {"workload": f"{lz_mib} MiB G2 text, reference Lzma2Enc level 5 ({min(cores, 32)} threads)", "packed_bytes": len(lcomp), "independent_blocks": int(blocks),
+                            "dec_MBps": m / 1e6 / dt, "ms": dt * 1e3}
+    c.close()
     return rec
 
 
@@ -528,6 +570,11 @@ def main():
             line.setdefault("extra", {})["long_range"] = long_range(pkg, local, a.long_mib, cpu=not a.no_cpu_baseline)
         except Exception as e:
             line.setdefault("extra", {})["long_range"] = {"error": str(e)[:200]}
+    if not lz and world == 1 and not a.no_refstreams_extra and not a.no_cpu_baseline:
+        try:
+            line.setdefault("extra", {})["reference_streams"] = reference_streams(pkg, local)
+        except Exception as e:
+            line.setdefault("extra", {})["reference_streams"] = {"error": str(e)[:200]}
     if not a.no_cpu_baseline and world == 1:
         cb = cpu_ref(a.cpu_sample_mib << 20)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "enc_MBps", "dec_MBps", "ratio")}
