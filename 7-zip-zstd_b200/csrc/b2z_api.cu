@@ -54,7 +54,7 @@ int b200z_create(b200z_ctx** out, int device) {
     for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&ctx->pe[i], cudaEventDisableTiming);
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     ctx->geom.frameLog = B2Z_DEF_FRAMELOG; ctx->geom.hashLogL = B2Z_DEF_HASHLOG_L; ctx->geom.hashLogS = B2Z_DEF_HASHLOG_S;
-    ctx->geom.chunkLog = B2Z_DEF_CHUNKLOG;
+    ctx->geom.chunkLog = B2Z_DEF_CHUNKLOG; ctx->geom.regionLog = B2Z_DEF_PLAIN_REGIONLOG;
     ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);   // size hints on: lets any decoder (ours included) find frames without walking blocks
     *out = ctx;
     return B200Z_OK;
@@ -127,11 +127,11 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
                             ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_ZSTD_OPT) | (v ? B2Z_FLAG_ZSTD_OPT : 0u); return 0;
     case B200Z_P_FRAMELOG:  if (v < 17 || v > B2Z_MAX_FRAMELOG) return fail(ctx, B200Z_E_PARAM, "frameLog out of range%s");
                             ctx->geom.frameLog = (uint32_t)v; if (ctx->geom.windowLog > v) ctx->geom.windowLog = (uint32_t)v;
-                            ctx->geom.regionLog = ctx->geom.ldmLog = 0; return 0;                                    // (leaves the long mode)
+                            ctx->geom.regionLog = v > B2Z_DEF_PLAIN_REGIONLOG ? B2Z_DEF_PLAIN_REGIONLOG : 0u; ctx->geom.ldmLog = 0; return 0;   // (leaves the long mode)
     // long mode: window 2^v bytes, frames of 8 windows (at most 1 GiB) cut into regions of 1 MiB for stage F, + stage L.
     // 0 leaves it (frames of 1 MiB again).
     case B200Z_P_LONG:      if (v != 0 && (v < 21 || v > B2Z_MAX_LONGLOG)) return fail(ctx, B200Z_E_PARAM, "long: window log out of range%s");
-                            if (v == 0) { if (ctx->geom.regionLog) { ctx->geom.frameLog = ctx->geom.windowLog = B2Z_DEF_FRAMELOG; } ctx->geom.regionLog = ctx->geom.ldmLog = 0; return 0; }
+                            if (v == 0) { if (ctx->geom.ldmLog) { ctx->geom.frameLog = ctx->geom.windowLog = B2Z_DEF_FRAMELOG; ctx->geom.regionLog = B2Z_DEF_PLAIN_REGIONLOG; } ctx->geom.ldmLog = 0; return 0; }
                             ctx->geom.windowLog = (uint32_t)v; ctx->geom.frameLog = B2Z_LONG_FRAMELOG((uint32_t)v);
                             ctx->geom.regionLog = B2Z_DEF_REGIONLOG; ctx->geom.ldmLog = B2Z_LDM_LOG((uint32_t)v);
                             return 0;
@@ -145,6 +145,8 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_LZMA2_PARSE: if (v < 0 || v > 1) return fail(ctx, B200Z_E_PARAM, "lzma2 parse mode out of range%s");
                             ctx->geom.flags = (ctx->geom.flags & ~B2Z_FLAG_LZ2_OPT) | (v ? B2Z_FLAG_LZ2_OPT : 0u); return 0;
     case B200Z_P_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "batchLog out of range%s"); ctx->batchLog = (uint32_t)v; return 0;
+    case B200Z_P_REGIONLOG: if (v != 0 && (v < 17 || v > (int64_t)ctx->geom.frameLog)) return fail(ctx, B200Z_E_PARAM, "regionLog out of range%s");
+                            ctx->geom.regionLog = (uint32_t)v; return 0;
     case B200Z_P_CHUNKLOG:  if (v < 5 || v > 8) return fail(ctx, B200Z_E_PARAM, "chunkLog out of range%s"); ctx->geom.chunkLog = (uint32_t)v; return 0;
     case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
@@ -168,7 +170,8 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
     case B200Z_P_CHUNKLOG: *v = ctx->geom.chunkLog; return 0;
-    case B200Z_P_LONG: *v = ctx->geom.regionLog ? ctx->geom.windowLog : 0; return 0;
+    case B200Z_P_LONG: *v = ctx->geom.ldmLog ? ctx->geom.windowLog : 0; return 0;
+    case B200Z_P_REGIONLOG: *v = ctx->geom.regionLog; return 0;
     }
     return B200Z_E_PARAM;
 }
@@ -199,7 +202,7 @@ static uint32_t find_ctas(const b200z_ctx* ctx, uint64_t nFrames) {
 // does this batch parse by price (stage C + stage P / stage Z) instead of the greedy stage M?  (the per-file batch mode, which
 // sets frameSizes, always runs stage M)
 static bool price_parse(const EncGeom& g, int codec) {
-    return codec == 1 ? (g.flags & B2Z_FLAG_LZ2_OPT) != 0 : ((g.flags & B2Z_FLAG_ZSTD_OPT) != 0 && !g.frameSizes && !g.regionLog);
+    return codec == 1 ? (g.flags & B2Z_FLAG_LZ2_OPT) != 0 : ((g.flags & B2Z_FLAG_ZSTD_OPT) != 0 && !g.frameSizes && !g.ldmLog);
 }
 // the long mode of the Zstandard encoder: frames of many regions (stage F's unit) + stage L.  Per-file batches and method 21 have none.
 static bool long_mode(const EncGeom& g, int codec) { return codec == 0 && !g.frameSizes && g.regionLog && g.regionLog < g.frameLog; }

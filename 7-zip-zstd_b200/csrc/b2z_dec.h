@@ -49,7 +49,7 @@ struct DecBlock {
 
 #define B2Z_DEC_ROUNDS 4u            // stage D3: 32-byte rounds of a batch's literal / match copies whose loads are issued together
 #define B2Z_DEC_RING 4096u           // stage D3: bytes of its own latest output a warp mirrors in shared memory
-#define B2Z_DEC_UNIT_BLOCKS 8u       // stage D3: consecutive blocks of a frame executed by one warp (1 MiB of output when the blocks are full)
+#define B2Z_DEC_UNIT_BLOCKS 4u       // stage D3: consecutive blocks of a frame executed by one warp (512 KiB of output when the blocks are full)
 
 struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; };
 

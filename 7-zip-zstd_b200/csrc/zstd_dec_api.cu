@@ -304,7 +304,7 @@ int b200z_zstd_decompress_host(b200z_ctx* ctx, const void* src, size_t srcSize, 
     CU(cudaSetDevice(ctx->device));
     std::vector<HostBatch> batches;
     const size_t nDev = 1 + ctx->peers.size();
-    uint64_t target = 2ull << ctx->hostBatchLog;                     // the execute stage is one latency-bound warp per frame: fewer, larger batches
+    uint64_t target = 1ull << ctx->hostBatchLog;                     // decoded bytes per batch
     if (nDev > 1) { const uint64_t per = (uint64_t)srcSize * 3 / (2 * nDev) + 1; if (per < target) target = per; }   // about two batches per device (packed size x 3 ~ output)
     if ((nDev == 1 && srcSize <= (target >> 2)) || !split_frames((const uint8_t*)src, srcSize, target, batches) || (batches.size() < 2 && nDev == 1) || batches.empty()) {
         // one shot

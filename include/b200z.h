@@ -64,6 +64,8 @@ extern "C" {
                                    1 MiB regions, stage F's unit; stage L finds matches of >= 64 bytes up to a window back through tables of content-chosen
                                    samples.  The parse is stage G's at every level (the price-based stage C + Z works on frames of <= 16 MiB).
                                    Sets FRAMELOG and WINDOWLOG; set B200Z_P_FRAMELOG afterwards to leave the mode */
+#define B200Z_P_REGIONLOG   15  /* Zstandard encoder: log2 of the finder's unit inside a frame (stage F starts with empty tables in every region, so no match
+                                   crosses a region start: regions decode as independent chains), 17..FRAMELOG; 0 = the frame */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 30 (the decoder takes twice that) */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,

@@ -232,7 +232,8 @@ int64_t b2zo_lzma2_compress(void *dstv, size_t dstCap, const void *srcv, size_t 
         if (p->flags & B2Z_FLAG_LZ2_OPT) {
             for (size_t f = 0, f0 = 0; f0 < srcSize; f++, f0 += F)
                 b2zo_lzma2_parse_frame(src + f0, (uint32_t)(srcSize - f0 < F ? srcSize - f0 : F), p, NULL, seqs + f * bpf * B2Z_MAXSEQ, nseq + f * bpf);
-        } else b2zo_zstd_find_sequences(src, srcSize, p, seqs, nseq, lits, nlit);
+        } else { b2zo_enc_params q = *p; q.regionLog = 0; q.ldmLog = 0;              /* method 21 has no regions: a block is stage F's unit */
+                 b2zo_zstd_find_sequences(src, srcSize, &q, seqs, nseq, lits, nlit); }
         int fail = 0;
         for (size_t f = 0, f0 = 0; f0 < srcSize; f++, f0 += F) {
             const uint32_t n = (uint32_t)(srcSize - f0 < F ? srcSize - f0 : F);

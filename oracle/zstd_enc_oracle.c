@@ -44,7 +44,7 @@ static inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 void b2zo_enc_default_params(b2zo_enc_params *p, int level) {
     p->frameLog = B2Z_DEF_FRAMELOG; p->hashLogL = B2Z_DEF_HASHLOG_L; p->hashLogS = B2Z_DEF_HASHLOG_S;
     p->windowLog = B2Z_DEF_FRAMELOG; p->chunkLog = B2Z_DEF_CHUNKLOG; p->flags = 1u | (B2Z_DEF_LZ2_SLICELOG << 8);
-    p->regionLog = 0; p->ldmLog = 0;
+    p->regionLog = B2Z_DEF_PLAIN_REGIONLOG; p->ldmLog = 0;
     p->flags |= b2z_level_find_flags(level) | (level >= B2Z_ZSTD_OPT_LEVEL ? B2Z_FLAG_ZSTD_OPT : 0u);      /* what B200Z_P_LEVEL sets */
     if (p->flags & B2Z_FLAG_FIND_FAST) p->hashLogS = B2Z_DEF_HASHLOG_L;                                     /* the single table takes the long table's room */
 }

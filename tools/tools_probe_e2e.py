@@ -17,8 +17,8 @@ hback = torch.empty(n, dtype=torch.uint8).pin_memory()
 for _ in range(2):
     torch.cuda.synchronize(); t = time.perf_counter(); hback.copy_(d, non_blocking=True); torch.cuda.synchronize(); dt = time.perf_counter() - t
 print(f"D2H pinned {n/1e9/dt:.1f} GB/s")
-for hb in (28, 29, 30, 31, 32):
-    c = pkg.Codec(0, host_batch_log=hb)
+for hb in (28, 29, 30, 31):
+    c = pkg.Codec(0, host_batch_log=hb, **({'region_log': int(os.environ['B200Z_REGION'])} if os.environ.get('B200Z_REGION') else {}))
     bound = c.compress_bound(n)
     hcomp = torch.empty(bound, dtype=torch.uint8).pin_memory()
     for it in range(2):
