@@ -37,11 +37,12 @@ struct b200z_ctx {
     uint32_t batchLog = 31;           // bytes per kernel batch of the device-pointer entry points: 2 GiB keeps the scratch (9.5 bytes per batch byte: candidate
                                       // words 4, choices 1, sequences 2, literals 1, block slots 1.5) near 19 GiB whatever the input size (1 GiB batches cost 4 % of speed)
     uint32_t smCount = 148;
+    int decJump = 1;                  // Zstandard decoder, stage J (frames resolved by pointer jumping): 0 never, 1 frames whose units form a chain, 2 every frame
     int lz2Mode = 0;                  // LZMA2 decoder literal-model placement: 0 auto, 1 shared memory, 2 global memory
     Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready, batchStage, batchOff, batchSize, cand, choice, crcOff, crcLen, crcOut;
     uint32_t* hostOne = nullptr;      // pinned constant 1 (chunk-arrival flags of the host-pointer path)
     uint64_t* hostSmall = nullptr;    // 256 pinned bytes the device writes its counters into (b2z_fetch_small)
-    Arena decScratch[8];
+    Arena decScratch[10];
     cudaEvent_t ev[8] = {};
     double stat[16] = {0};
     char err[256] = {0};

@@ -24,6 +24,8 @@ struct DecFrame {
     uint32_t checksum;      // 1 if a 4-byte content checksum follows the last block
     uint32_t pad;           // D0: scratch (frame header bytes); from D2 on: index of the frame's first execution unit
     uint64_t endOff;        // offset just past the frame in src (the checksum, if any, is the 4 bytes before it)
+    uint32_t jump;          // D2: 1 = the frame's matches are resolved by pointer jumping (stage J) instead of by execution units
+    uint32_t pad3;
 };
 
 struct DecBlock {
@@ -43,7 +45,7 @@ struct DecBlock {
     // without anybody walking the frame's sequences in order.
     uint32_t repX[3], repSym;
     uint32_t repInit[3];    // history at the block's first sequence (stage D2)
-    uint32_t pad2;
+    uint32_t nearBehind;    // stage D1: 1 = a match with an explicit offset starts at most one unit's span (512 KiB) before the block's first byte
     uint64_t outRel;        // first output byte of the block, relative to its frame (stage D2)
 };
 
@@ -51,7 +53,11 @@ struct DecBlock {
 #define B2Z_DEC_RING 4096u           // stage D3: bytes of its own latest output a warp mirrors in shared memory
 #define B2Z_DEC_UNIT_BLOCKS 4u       // stage D3: consecutive blocks of a frame executed by one warp (512 KiB of output when the blocks are full)
 
-struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; };
+#define B2Z_DEC_JUMP_MIN_UNITS 8u    // stage J, automatic mode: frames of at least this many units ...
+#define B2Z_DEC_JUMP_FINAL 0x80000000u   // stage J: pointer bit "the position pointed at holds a literal byte" (batches of < 2 GiB of output)
+#define B2Z_DEC_JUMP_ROUNDS 32u      // pointer doubling: a chain of n links is resolved after ceil(log2 n) rounds, n < 2^31
+
+struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; uint32_t maxFrameBlocks, nJump; };
 
 // stage D0: frame discovery (1 thread; hops over mcmilk size hints when present), then per-frame block indexing
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st);
@@ -62,8 +68,13 @@ void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blo
                              uint8_t* lits, uint64_t* seqs, void* scratch, cudaStream_t st, cudaStream_t stLit, cudaEvent_t evFork, cudaEvent_t evJoin);
 size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks);
 // stage D2: per-frame sizes and output offsets
+// jumpMode: 0 = every frame by units (stage D3), 1 = frames whose units form a chain go to stage J, 2 = every frame with a block goes to stage J
 void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap,
-                            DecCounts* counts, uint64_t* total, cudaStream_t st);
+                            DecCounts* counts, uint64_t* total, uint32_t jumpMode, cudaStream_t st);
+// stage J (frames with DecFrame::jump): literals and one pointer per output byte (J1), pointer doubling (J2), byte gather (J3).
+// ptr: one word per output byte of the batch; flags: B2Z_DEC_JUMP_ROUNDS + 1 words
+void launch_zstd_dec_jump(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
+                          uint8_t* dst, uint64_t total, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st);
 // stage D3: one warp per unit of B2Z_DEC_UNIT_BLOCKS consecutive blocks of a frame, units taken in order; a match that reaches
 // behind its unit waits for the unit that writes those bytes.  unitState: [0] ticket, [1 + u] done flag of unit u -- zeroed here.
 size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks);

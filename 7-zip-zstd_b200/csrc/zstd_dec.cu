@@ -147,7 +147,7 @@ __device__ uint32_t walk_blocks(const Src& S, uint64_t ip, uint64_t srcSize, uin
             if (firstBlock + nb >= blockCap) return B2Z_DERR_TABLE_FULL;
             const int32_t self = (int32_t)(firstBlock + nb);
             DecBlock b; b.srcOff = ip; b.type = type; b.frame = frameIdx; b.hufSrc = -1; b.tblSrc[0] = b.tblSrc[1] = b.tblSrc[2] = -1;
-            b.regen = 0; b.nbSeq = 0; b.litSize = 0; b.status = 0; b.rawSize = 0; b.cSize = cSize;
+            b.regen = 0; b.nbSeq = 0; b.litSize = 0; b.status = 0; b.rawSize = 0; b.cSize = cSize; b.nearBehind = 0;
             if (type != 2) { b.rawSize = bsize; b.regen = bsize; }
             else {
                 const LitHdr lh = parse_lit_hdr(S, ip, bsize);
@@ -231,9 +231,9 @@ __global__ void zstd_dec_count_blocks_kernel(const uint8_t* __restrict__ src, ui
 
 __global__ void zstd_dec_scan_blocks_kernel(DecFrame* frames, uint32_t nFrames, uint32_t blockCap, DecCounts* counts) {
     if (threadIdx.x || blockIdx.x) return;
-    uint32_t total = 0;
-    for (uint32_t f = 0; f < nFrames; f++) { frames[f].firstBlock = total; total += frames[f].nBlocks; }
-    counts->nBlocks = total;
+    uint32_t total = 0, most = 0;
+    for (uint32_t f = 0; f < nFrames; f++) { frames[f].firstBlock = total; total += frames[f].nBlocks; if (frames[f].nBlocks > most) most = frames[f].nBlocks; }
+    counts->nBlocks = total; counts->maxFrameBlocks = most;
     if (total > blockCap) counts->status |= B2Z_DERR_TABLE_FULL;
 }
 
@@ -701,7 +701,7 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
         uint32_t sL = b.read(j.logs & 255u), sO = b.read((j.logs >> 8) & 255u), sM = b.read((j.logs >> 16) & 255u);   // <= 26 bits
         if (b.left() < 0) err = B2Z_DERR_CORRUPT;
         uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
-        uint32_t litUsed = 0, total = 0;
+        uint32_t litUsed = 0, total = 0, near = 0;
         // the repcode history as a function of the history before the block (b2z_dec.h DecBlock::repX): slot = value (sym 0) or
         // (initial slot sym - 1) minus value.  ZSTD_decodeSequence's update rules, zstd_decompress_block.c:1290-1312
         uint32_t v0 = 0, v1 = 0, v2 = 0, y0 = 1, y1 = 2, y2 = 3;
@@ -721,6 +721,8 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
             litUsed += ll; total += ll + ml;
             if (b.left() < 0 || litUsed > j.litRegen || total > 131072u || ob >= (1u << 30)) { err = B2Z_DERR_CORRUPT; break; }
             out[i] = SEQ_PACK(ob, ll, ml);
+            // a source at most one unit's span before the block: the block's unit cannot run beside the unit before it (stage D2 counts these)
+            near |= (uint32_t)(ob > 3u && ob - 3u > total - ml && ob - 3u - (total - ml) <= B2Z_DEC_UNIT_BLOCKS * 131072u);
             if (ob > 3u) { v2 = v1; y2 = y1; v1 = v0; y1 = y0; v0 = ob - 3u; y0 = 0u; }
             else {
                 const uint32_t idx = ob - 1u + (ll == 0u);
@@ -730,6 +732,7 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
             }
         }
         blocks[bi].repX[0] = v0; blocks[bi].repX[1] = v1; blocks[bi].repX[2] = v2; blocks[bi].repSym = y0 | (y1 << 2) | (y2 << 4);
+        blocks[bi].nearBehind = near;
         if (!err && b.left() != 0) err = B2Z_DERR_CORRUPT;
         regen = total + (j.litRegen - litUsed);
         if (regen > 131072u) err = B2Z_DERR_CORRUPT;
@@ -739,16 +742,20 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
 }
 
 // ---------------------------------------------------------------- D2: layout
-__global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, DecBlock* __restrict__ blocks, DecCounts* counts) {
+// jumpMode (b2z_dec.h): which frames leave the execution units for stage J.  Automatic: a frame of >= B2Z_DEC_JUMP_MIN_UNITS units of which
+// at least three in four start with a block that copies from the unit before it -- a sliding-window frame (what the reference's encoder
+// writes: one frame per stream, ZstdEncoder.cpp:250-340), whose units would run one behind the other.
+__global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, DecBlock* __restrict__ blocks, DecCounts* counts, uint32_t jumpMode) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFrames) return;
-    uint64_t total = 0; uint32_t st = 0;
+    uint64_t total = 0; uint32_t st = 0, chained = 0;
     const uint32_t b0 = frames[f].firstBlock, nb = frames[f].nBlocks;
     uint32_t r0 = 1, r1 = 4, r2 = 8;                                         // the format's starting history
     for (uint32_t i = 0; i < nb; i++) {
         DecBlock& B = blocks[b0 + i];
         B.outRel = total; B.repInit[0] = r0; B.repInit[1] = r1; B.repInit[2] = r2;
         total += B.regen; st |= B.status;
+        if (i && i % B2Z_DEC_UNIT_BLOCKS == 0u && B.type == 2 && B.nearBehind) chained++;
         if (B.type == 2 && B.nbSeq) {                                         // apply the block's symbolic history (stage D1)
             const uint32_t in[3] = { r0, r1, r2 }, y = B.repSym;
             r0 = (y & 3u) ? in[(y & 3u) - 1u] - B.repX[0] : B.repX[0];
@@ -758,16 +765,24 @@ __global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, 
     }
     if (frames[f].contentSize != ~0ull && frames[f].contentSize != total) st |= B2Z_DERR_CORRUPT;
     frames[f].regen = total;
+    const uint32_t units = (nb + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
+    frames[f].jump = (uint32_t)(!st && total && total < 0x7FFFFFFFull &&
+                                (jumpMode == 2u || (jumpMode == 1u && units >= B2Z_DEC_JUMP_MIN_UNITS && chained * 4u >= (units - 1u) * 3u)));
     if (st) atomicOr(&counts->status, st);
 }
 __global__ void zstd_dec_frame_offsets_kernel(DecFrame* frames, uint32_t nFrames, uint64_t dstCap, DecCounts* counts, uint64_t* total) {
     if (threadIdx.x || blockIdx.x) return;
-    uint64_t o = 0; uint32_t u = 0;
+    uint64_t o = 0; uint32_t u = 0, nj = 0;
+    for (uint32_t f = 0; f < nFrames; f++) o += frames[f].regen;
+    const bool jumpOk = o < 0x7FFFFFFFull;                                    // stage J's pointers are 31-bit offsets into the batch's output
+    o = 0;
     for (uint32_t f = 0; f < nFrames; f++) {
         frames[f].dstOff = o; o += frames[f].regen;
-        frames[f].pad = u; u += (frames[f].nBlocks + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
+        if (!jumpOk) frames[f].jump = 0;
+        nj += frames[f].jump;
+        frames[f].pad = u; if (!frames[f].jump) u += (frames[f].nBlocks + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
     }
-    *total = o; counts->nUnits = u;
+    *total = o; counts->nUnits = u; counts->nJump = nj;
     if (o > dstCap) atomicOr(&counts->status, B2Z_DERR_DSTSIZE);
 }
 
@@ -960,6 +975,166 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
     }
 }
 
+// ---------------------------------------------------------------- stage J: frames resolved by pointer jumping
+// A frame the reference's encoder wrote is ONE frame with a sliding window (zstdmt's jobs become blocks of one frame,
+// zstdmt_compress.c:1403): every unit copies from the unit before it and stage D3 degrades to one chain.  Stage D1 has already
+// decoded every sequence of every block and stage D2 placed every block, so the only thing left that is sequential is "a match
+// copies bytes that a match before it produced" -- and that is a forest over the output bytes: a literal byte is a root, a match byte
+// points at its source byte.  J1 writes the literal bytes and one pointer per output byte (one warp per block, all blocks at once);
+// J2 doubles the pointers (ptr[i] = ptr[ptr[i]], in place: any value a neighbour holds meanwhile is an ancestor, so stale reads only
+// cost a round) until every pointer names a literal -- ceil(log2(longest chain)) rounds of streaming passes; J3 fetches the bytes.
+// A pointer is the byte's offset in the batch's output (batches of < 2 GiB), bit 31 = "names a literal byte".
+// Role in the reference: ZSTD_execSequence over the whole frame (zstd_decompress_block.c:1001-1100), which is strictly sequential.
+__global__ void __launch_bounds__(128)
+zstd_dec_jump_build_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, const DecBlock* __restrict__ blocks, uint32_t nBlocks,
+                           const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* __restrict__ dst, DecCounts* counts,
+                           uint32_t* __restrict__ ptr) {
+    if (counts->status) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; bi < nBlocks; bi += nWarps) {
+        const DecBlock blk = blocks[bi];
+        const DecFrame* fp = frames + blk.frame;
+        if (!fp->jump) continue;
+        const uint64_t windowSize = fp->windowSize;
+        const uint32_t fbase = (uint32_t)fp->dstOff;                 // batch offset of the frame's first byte (< 2^31: stage D2)
+        uint8_t* out = dst + fbase;
+        uint32_t* P = ptr + fbase;
+        uint32_t o = (uint32_t)blk.outRel, err = 0;                  // frame bytes produced before the next sequence (jump frames are < 2 GiB)
+        if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) { out[o + i] = src[blk.srcOff + i]; P[o + i] = (fbase + o + i) | B2Z_DEC_JUMP_FINAL; } continue; }
+        if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) { out[o + i] = v; P[o + i] = (fbase + o + i) | B2Z_DEC_JUMP_FINAL; } continue; }
+        const uint8_t* __restrict__ lit = lits + (size_t)bi * 131072u;
+        const uint64_t* __restrict__ sq = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+        uint32_t lp = 0, rep0 = blk.repInit[0], rep1 = blk.repInit[1], rep2 = blk.repInit[2];
+        uint64_t ahead = lane < blk.nbSeq ? sq[lane] : 0ull;
+        for (uint32_t i0 = 0; i0 < blk.nbSeq && !err; i0 += 32) {
+            const uint32_t cnt = (blk.nbSeq - i0) < 32u ? (blk.nbSeq - i0) : 32u;
+            const uint64_t mine = ahead;
+            ahead = i0 + 32u + lane < blk.nbSeq ? sq[i0 + 32u + lane] : 0ull;
+            const uint32_t ll = lane < cnt ? ((uint32_t)(mine >> 30) & 0x1FFFFu) : 0u;
+            const uint32_t ml = lane < cnt ? ((uint32_t)(mine >> 47) + 3u) : 0u;
+            // offsets: the repcode rules of stage D3 (zstd_decompress_block.c:1290-1312), history from stage D2
+            uint32_t myOff = 0;
+            const uint32_t obMine = (uint32_t)mine & 0x3FFFFFFFu;
+            if (!__any_sync(B2Z_FULL, lane < cnt && obMine <= 3u)) {
+                myOff = lane < cnt ? obMine - 3u : 0u;
+                const uint32_t o1 = __shfl_sync(B2Z_FULL, myOff, cnt - 1u), o2 = __shfl_sync(B2Z_FULL, myOff, (cnt - 2u) & 31u), o3 = __shfl_sync(B2Z_FULL, myOff, (cnt - 3u) & 31u);
+                const uint32_t n2 = cnt >= 2u ? o2 : rep0, n3 = cnt >= 3u ? o3 : (cnt == 2u ? rep0 : rep1);
+                rep2 = n3; rep1 = n2; rep0 = o1;
+            } else for (uint32_t k = 0; k < cnt; k++) {
+                const uint64_t s = __shfl_sync(B2Z_FULL, mine, k);
+                const uint32_t ob = (uint32_t)s & 0x3FFFFFFFu, llk = (uint32_t)(s >> 30) & 0x1FFFFu;
+                uint32_t offset;
+                if (ob > 3) { offset = ob - 3u; rep2 = rep1; rep1 = rep0; rep0 = offset; }
+                else {
+                    const uint32_t idx = ob - 1u + (llk == 0u);
+                    if (idx == 0) offset = rep0;
+                    else {
+                        offset = idx == 3 ? rep0 - 1u : (idx == 1 ? rep1 : rep2);
+                        if (idx != 1) rep2 = rep1;
+                        rep1 = rep0; rep0 = offset;
+                    }
+                }
+                if (lane == k) myOff = offset;
+            }
+            uint32_t total, litTotal;
+            const uint32_t excl = warp_excl_scan(ll + ml, lane, &total);
+            const uint32_t litExcl = warp_excl_scan(ll, lane, &litTotal);
+            const uint32_t myDst = o + excl + ll;                                        // frame-relative start of the lane's match
+            const bool bad = lane < cnt && (myOff == 0 || myOff > myDst || myOff > windowSize);
+            if (__any_sync(B2Z_FULL, bad)) { err = B2Z_DERR_CORRUPT; break; }
+            // lane = byte of the batch, B2Z_DEC_ROUNDS rounds of 32 taken together (their literal loads are issued before the first store);
+            // byte t belongs to the sequence k with excl_k <= t < excl_k + ll_k + ml_k (binary search over the lanes' prefix sums)
+            for (uint32_t t0 = 0; t0 < total; t0 += 32u * B2Z_DEC_ROUNDS) {
+                uint8_t v[B2Z_DEC_ROUNDS]; uint32_t w[B2Z_DEC_ROUNDS];
+#pragma unroll
+                for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) {
+                    const uint32_t t = t0 + r * 32u + lane;
+                    uint32_t k = 0;
+#pragma unroll
+                    for (uint32_t st = 16; st; st >>= 1) { const uint32_t x = __shfl_sync(B2Z_FULL, excl, (k + st) & 31u); if (k + st < 32u && x <= t) k += st; }
+                    const uint32_t e = __shfl_sync(B2Z_FULL, excl, k), l = __shfl_sync(B2Z_FULL, ll, k), le = __shfl_sync(B2Z_FULL, litExcl, k), of = __shfl_sync(B2Z_FULL, myOff, k);
+                    const uint32_t rr = t - e;
+                    v[r] = 0; w[r] = 0;
+                    if (t < total) {
+                        if (rr < l) { v[r] = lit[lp + le + rr]; w[r] = (fbase + o + t) | B2Z_DEC_JUMP_FINAL; }
+                        else {
+                            // a match byte points at its source; inside an overlapping match (offset < length) at the byte of the period
+                            // before the match, not at the match's own earlier byte: no chain inside one match
+                            const uint32_t m = rr - l;
+                            w[r] = fbase + o + e + l - of + (m < of ? m : m % of);
+                        }
+                    }
+                }
+#pragma unroll
+                for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) {
+                    const uint32_t t = t0 + r * 32u + lane;
+                    if (t < total) { P[o + t] = w[r]; if (w[r] & B2Z_DEC_JUMP_FINAL) out[o + t] = v[r]; }
+                }
+            }
+            o += total; lp += litTotal;
+        }
+        if (!err) {
+            const uint32_t tail = blk.litSize - lp;
+            for (uint32_t i = lane; i < tail; i += 32) { out[o + i] = lit[lp + i]; P[o + i] = (fbase + o + i) | B2Z_DEC_JUMP_FINAL; }
+            o += tail;
+            if (o != (uint32_t)blk.outRel + blk.regen) err = B2Z_DERR_CORRUPT;
+        }
+        if (err && lane == 0) atomicOr(&counts->status, err);
+    }
+}
+
+// the frame that holds batch offset i: the last frame with dstOff <= i (frames without output share their successor's offset)
+__device__ __forceinline__ uint32_t dec_frame_of(const DecFrame* __restrict__ frames, uint32_t nFrames, uint64_t i) {
+    uint32_t lo = 0, hi = nFrames;
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (frames[mid].dstOff <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// J2 (LAST = false): one round of pointer doubling over every jump frame's pointers, four per thread.  flags[r] = round r left a pointer
+// that does not yet name a literal; a round whose predecessor left none returns at once (all rounds are launched up front).
+// J3 (LAST = true): dst[i] = dst[ptr[i]] for the match bytes.
+template <bool LAST> __global__ void __launch_bounds__(256)
+zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames, uint64_t total, uint32_t* __restrict__ ptr, uint32_t* flags,
+                           uint32_t round, uint8_t* dst, DecCounts* counts) {
+    if (counts->status) return;
+    if (!LAST && round && !flags[round - 1u]) return;
+    const uint64_t nGroups = (total + 3u) >> 2;
+    bool pending = false, broken = false;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i0 = g << 2;
+        uint32_t f = nFrames > 1u ? dec_frame_of(frames, nFrames, i0) : 0u;
+        uint64_t fEnd = frames[f].dstOff + frames[f].regen; bool fj = frames[f].jump != 0u;
+        uint4 q4 = *reinterpret_cast<const uint4*>(ptr + i0);
+        uint32_t q[4] = { q4.x, q4.y, q4.z, q4.w }; bool take[4]; uint32_t r[4];
+#pragma unroll
+        for (uint32_t e = 0; e < 4; e++) {
+            const uint64_t i = i0 + e;
+            take[e] = false;
+            if (i < total) {
+                while (i >= fEnd) { f++; fEnd = frames[f].dstOff + frames[f].regen; fj = frames[f].jump != 0u; }
+                take[e] = fj && (LAST ? q[e] != ((uint32_t)i | B2Z_DEC_JUMP_FINAL) : !(q[e] & B2Z_DEC_JUMP_FINAL));
+            }
+        }
+        if (!LAST) {
+#pragma unroll
+            for (uint32_t e = 0; e < 4; e++) r[e] = take[e] ? __ldcg(ptr + q[e]) : q[e];
+            if (take[0] | take[1] | take[2] | take[3]) {
+#pragma unroll
+                for (uint32_t e = 0; e < 4; e++) pending |= take[e] && !(r[e] & B2Z_DEC_JUMP_FINAL);
+                *reinterpret_cast<uint4*>(ptr + i0) = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+        } else {
+#pragma unroll
+            for (uint32_t e = 0; e < 4; e++) { broken |= take[e] && !(q[e] & B2Z_DEC_JUMP_FINAL); r[e] = take[e] ? dst[q[e] & ~B2Z_DEC_JUMP_FINAL] : 0u; }
+#pragma unroll
+            for (uint32_t e = 0; e < 4; e++) if (take[e]) dst[i0 + e] = (uint8_t)r[e];
+        }
+    }
+    if (!LAST && pending) flags[round] = 1u;
+    if (LAST && broken) atomicOr(&counts->status, B2Z_DERR_CORRUPT);       // a pointer no round resolved: cannot happen (pointers strictly decrease)
+}
+
 // ---------------------------------------------------------------- checksum verification
 __global__ void zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, uint32_t nFrames,
                                        const uint8_t* __restrict__ dst, DecCounts* counts) {
@@ -1017,9 +1192,20 @@ void launch_zstd_dec_entropy(const uint8_t* src, uint64_t srcSize, DecBlock* blo
     if (stLit != st) { cudaEventRecord(evJoin, stLit); cudaStreamWaitEvent(st, evJoin, 0); }
 }
 size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks) { return (size_t)nBlocks * (4096u + 1280u * sizeof(SeqEnt) + sizeof(LitJob) + sizeof(SeqJob)) + 256u; }
-void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap, DecCounts* counts, uint64_t* total, cudaStream_t st) {
-    if (nFrames) zstd_dec_frame_sizes_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(frames, nFrames, blocks, counts);
+void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap, DecCounts* counts, uint64_t* total, uint32_t jumpMode, cudaStream_t st) {
+    if (nFrames) zstd_dec_frame_sizes_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(frames, nFrames, blocks, counts, jumpMode);
     zstd_dec_frame_offsets_kernel<<<1, 32, 0, st>>>(frames, nFrames, dstCap, counts, total);
+}
+void launch_zstd_dec_jump(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
+                          uint8_t* dst, uint64_t total, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st) {
+    if (!nFrames || !nBlocks || !total) return;
+    cudaMemsetAsync(flags, 0, (B2Z_DEC_JUMP_ROUNDS + 1u) * 4u, st);
+    { const uint32_t want = (nBlocks + 3u) / 4u, grid = want < 148u * 16u ? want : 148u * 16u;
+      zstd_dec_jump_build_kernel<<<grid, 128, 0, st>>>(src, frames, blocks, nBlocks, lits, seqs, dst, counts, ptr); }
+    const uint64_t groups = (total + 3u) >> 2;
+    const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 148u * 16u ? (groups + 255u) / 256u : 148u * 16u);
+    for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++) zstd_dec_jump_round_kernel<false><<<grid, 256, 0, st>>>(frames, nFrames, total, ptr, flags, r, dst, counts);
+    zstd_dec_jump_round_kernel<true><<<grid, 256, 0, st>>>(frames, nFrames, total, ptr, flags, 0, dst, counts);
 }
 size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks) { return ((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u) * 4u; }
 void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,

@@ -150,7 +150,7 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     launch_zstd_dec_find_frames((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, counts, st);
     CU(cudaGetLastError());
     DecCounts hc;
-    static_assert(sizeof(DecCounts) == 24, "DecCounts is fetched as three words");
+    static_assert(sizeof(DecCounts) == 32, "DecCounts is fetched as four words");
     { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
     launch_zstd_dec_index_blocks((const uint8_t*)d_src, srcSize, frames, hc.nFrames, blocks, (uint32_t)blockCap, counts, st);
@@ -165,8 +165,26 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, ctx->decScratch[5].p, st, st, ctx->ev[4], ctx->ev[5]);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[1], st));
-    launch_zstd_dec_layout(frames, hc.nFrames, blocks, dstCap, counts, total, st);
+    // stage J (zstd_dec.cu): frames whose units would form one chain -- what the reference's encoder writes -- are resolved by pointer
+    // jumping.  Only a stream with a frame of enough blocks pays for the extra look at the counters.
+    const uint32_t jumpMode = (uint32_t)ctx->decJump;
+    const bool maybeJump = jumpMode == 2u || (jumpMode == 1u && (hc.maxFrameBlocks + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS >= B2Z_DEC_JUMP_MIN_UNITS);
+    launch_zstd_dec_layout(frames, hc.nFrames, blocks, dstCap, counts, total, maybeJump ? jumpMode : 0u, st);
     CU(cudaGetLastError());
+    if (maybeJump) {
+        struct { DecCounts c; uint64_t total; } hj;
+        { const int frc = b2z_fetch_small(ctx, &hj, counts, 40, st); if (frc) return frc; }
+        if (hj.c.status) return dec_status_to_rc(ctx, hj.c.status);
+        if (hj.c.nJump) {
+            Arena& aPtr = ctx->decScratch[8];
+            if (aPtr.reserve(256 + ((size_t)hj.total + 16) * 4)) return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (stage J pointers)%s");
+            launch_zstd_dec_jump((const uint8_t*)d_src, frames, hc.nFrames, blocks, hc.nBlocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
+                                 (uint8_t*)d_dst, hj.total, counts, (uint32_t*)((uint8_t*)aPtr.p + 256), (uint32_t*)aPtr.p, st);
+            CU(cudaGetLastError());
+            ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 2 + B2Z_DEC_JUMP_ROUNDS;
+            ctx->stat[B200Z_S_DEC_JUMP_FRAMES] += hj.c.nJump;
+        }
+    }
     uint32_t* unitState = (uint32_t*)((uint8_t*)ctx->decScratch[5].p + ((zstd_dec_entropy_scratch_bytes(hc.nBlocks) + 15u) & ~(size_t)15u));   // behind D1's scratch
     launch_zstd_dec_exec((const uint8_t*)d_src, frames, hc.nFrames, blocks, hc.nBlocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
                          (uint8_t*)d_dst, counts, unitState, st);
@@ -174,7 +192,7 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     launch_zstd_dec_verify((const uint8_t*)d_src, frames, hc.nFrames, (const uint8_t*)d_dst, counts, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[2], st));
-    struct { DecCounts c; uint64_t pad; uint64_t total; } hr;                  // counts at +0, the total at +32 of the same 64-byte scratch
+    struct { DecCounts c; uint64_t total; } hr;                                // counts at +0, the total at +32 of the same 64-byte scratch
     { const int frc = b2z_fetch_small(ctx, &hr, counts, 40, st); if (frc) return frc; }
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 7;
     float ms = 0;

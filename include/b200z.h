@@ -66,6 +66,9 @@ extern "C" {
                                    Sets FRAMELOG and WINDOWLOG; set B200Z_P_FRAMELOG afterwards to leave the mode */
 #define B200Z_P_REGIONLOG   15  /* Zstandard encoder: log2 of the finder's unit inside a frame (stage F starts with empty tables in every region, so no match
                                    crosses a region start: regions decode as independent chains), 17..FRAMELOG; 0 = the frame */
+#define B200Z_P_DEC_JUMP    16  /* Zstandard decoder: which frames are resolved by pointer jumping (stage J: one pointer per output byte, doubled until it names a
+                                   literal) instead of by execution units: 0 = none, 1 = frames of >= 8 units (4 MiB) whose units copy from one another -- the single
+                                   sliding-window frame the reference's encoder writes (default), 2 = every frame (tests) */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 30 (the decoder takes twice that) */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,
@@ -80,6 +83,7 @@ extern "C" {
 #define B200Z_S_D2H_BYTES       8
 #define B200Z_S_DEC_PREPASS_MS  9
 #define B200Z_S_ENC_PARSE_MS    10  /* the parse: stage G (or stage P / stage Z of the price-based parses) */
+#define B200Z_S_DEC_JUMP_FRAMES 11  /* Zstandard frames the decoder resolved by pointer jumping (stage J) */
 
 typedef struct b200z_ctx b200z_ctx;
 

@@ -204,7 +204,14 @@ int64_t emu_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, uint32_t fra
 
 // Zstandard decoder: the kernels in the order and shapes of dec_impl (zstd_dec_api.cu) / the launch_zstd_dec_* functions.
 // Returns the decoded size or -(status bits).
-int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap) {
+static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap, uint32_t jumpMode, uint32_t* nJumpOut);
+int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap) { return emu_zstd_decode_mode(src, srcSize, dst, dstCap, 1u, nullptr); }
+// jumpMode as B200Z_P_DEC_JUMP; *nJump = frames that went through stage J
+int64_t emu_zstd_decode_jump(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap, uint32_t jumpMode, uint32_t* nJump) {
+    return emu_zstd_decode_mode(src, srcSize, dst, dstCap, jumpMode, nJump);
+}
+static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap, uint32_t jumpMode, uint32_t* nJumpOut) {
+    if (nJumpOut) *nJumpOut = 0;
     if (!srcSize) return 0;
     uint64_t frameCap = srcSize / 9 + 2, blockCap = srcSize / 3 + 2;
     { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }
@@ -234,8 +241,19 @@ int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint
         cuemu::launch(dim3((nBlocks + D1_WARPS(1) - 1) / D1_WARPS(1)), dim3(D1_WARPS(1) * 32), 0, [&] { zstd_dec_entropy_kernel<1>(src, srcSize, blocks.data(), nBlocks, lits.data(), hufTabs, litJobs, seqTabs, seqJobs); });
         cuemu::launch(dim3((nBlocks + 127u) / 128u), dim3(128), 0, [&] { zstd_dec_seq_streams_kernel(src, srcSize, blocks.data(), nBlocks, seqs.data(), seqTabs, seqJobs); });
     }
-    if (nFrames) cuemu::launch(dim3((nFrames + 127) / 128), dim3(128), 0, [&] { zstd_dec_frame_sizes_kernel(frames.data(), nFrames, blocks.data(), &counts); });
+    const bool maybeJump = jumpMode == 2u || (jumpMode == 1u && (counts.maxFrameBlocks + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS >= B2Z_DEC_JUMP_MIN_UNITS);
+    if (nFrames) cuemu::launch(dim3((nFrames + 127) / 128), dim3(128), 0, [&] { zstd_dec_frame_sizes_kernel(frames.data(), nFrames, blocks.data(), &counts, maybeJump ? jumpMode : 0u); });
     cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_frame_offsets_kernel(frames.data(), nFrames, dstCap, &counts, &total); });
+    if (nJumpOut) *nJumpOut = counts.nJump;
+    if (maybeJump && !counts.status && counts.nJump && nBlocks && total) {             // launch_zstd_dec_jump
+        std::vector<uint32_t> ptr((size_t)total + 16, 0xCDCDCDCDu), flags(B2Z_DEC_JUMP_ROUNDS + 1u, 0u);
+        cuemu::launch(dim3((nBlocks + 3u) / 4u < 3u ? (nBlocks + 3u) / 4u : 3u), dim3(128), 0, [&] { zstd_dec_jump_build_kernel(src, frames.data(), blocks.data(), nBlocks, lits.data(), seqs.data(), dst, &counts, ptr.data()); });
+        const uint64_t groups = (total + 3u) >> 2;
+        const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 2u ? (groups + 255u) / 256u : 2u);
+        for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++)
+            cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<false>(frames.data(), nFrames, total, ptr.data(), flags.data(), r, dst, &counts); });
+        cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<true>(frames.data(), nFrames, total, ptr.data(), flags.data(), 0, dst, &counts); });
+    }
     if (nFrames) {
         std::vector<uint32_t> unitState((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u, 0u);
         cuemu::launch(dim3(nFrames < 5u ? nFrames : 5u), dim3(32), 0, [&] { zstd_dec_exec_kernel(src, frames.data(), nFrames, blocks.data(), lits.data(), seqs.data(), dst, &counts, unitState.data()); });

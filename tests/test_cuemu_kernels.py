@@ -37,6 +37,7 @@ def emu():
     E.emu_zstd_enc_assemble.restype = i64; E.emu_zstd_enc_assemble.argtypes = [vp, u64, u32, u32, vp, vp, u32, vp, u64]
     E.emu_zstd_decode.restype = i64; E.emu_zstd_decode.argtypes = [vp, u64, vp, u64]
     E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
+    E.emu_zstd_decode_jump.restype = i64; E.emu_zstd_decode_jump.argtypes = [vp, u64, vp, u64, u32, vp]
     return E
 
 
@@ -344,6 +345,48 @@ def test_emulated_zstd_decoder_frames_of_several_units(pkg, emu):
     for k, comp in enumerate(streams):
         r, out = dec(comp, n)
         assert r == n and out == data, k
+
+
+def test_emulated_zstd_decoder_stage_j_pointer_jumping(pkg, emu):
+    """stage J (zstd_dec_jump_build / _round kernels): literal bytes + one pointer per output byte, pointer doubling, byte gather.
+    Forced on every frame (mode 2) it must give what the execution units give -- golden frames of the reference encoder, frames with
+    raw / RLE blocks, long runs (offset 1: the chain inside a match is cut by the periodic source), repcodes across blocks, several
+    frames in one stream, damaged streams; in automatic mode (1) a reference-written sliding-window frame of >= 8 units is taken by
+    stage J and frames of this encoder (independent regions, or too short) are not"""
+    import hashlib, json
+    def dec(comp, n, mode):
+        src = np.frombuffer(comp + bytes(64), dtype=np.uint8); dst = np.full(n + 64, 0xEE, dtype=np.uint8); nj = ctypes.c_uint32(0)
+        r = emu.emu_zstd_decode_jump(src.ctypes.data, len(comp), dst.ctypes.data, n, mode, ctypes.byref(nj))
+        return r, dst[:max(r, 0)].tobytes(), nj.value
+    golden = os.path.join(HERE, "golden")
+    for idx_name in ("frames.json", "regr.json"):
+        for name, meta in json.load(open(os.path.join(golden, idx_name))).items():
+            if not name.endswith(".zst"):
+                continue
+            r, out, nj = dec(open(os.path.join(golden, name), "rb").read(), meta["size"], 2)
+            assert r == meta["size"] and hashlib.sha256(out).hexdigest() == meta["sha256"] and (nj > 0 or r == 0), name
+    data = _mixed(pkg, 300_000) + bytes(400_000) + b"abcdefghij" * 30_000 + pkg.corpus.g2(200_000).tobytes(); n = len(data)
+    streams = [H.oracle_compress(data), H.oracle_compress(data, frameLog=22, windowLog=22), H.oracle_compress(data, flags=3 | ZOPT, frameLog=17, windowLog=17)]
+    if H.ref_available():
+        streams += [H.ref_compress(data, level=1), H.ref_compress(data, level=19, checksum=1), H.ref_compress(data, level=5, nbWorkers=2)]
+    for k, comp in enumerate(streams):
+        r, out, nj = dec(comp, n, 2)
+        assert (r, out) == (n, data) and nj > 0, k
+        assert dec(comp, n, 0) == (n, data, 0), k
+    bad = bytearray(streams[1]); bad[len(bad) // 2] ^= 0x20
+    r, out, nj = dec(bytes(bad), n, 2)
+    assert not (r == n and out == data)
+    # automatic mode: 5 MiB, one frame
+    big = pkg.corpus.g2(5 << 20).tobytes() + b"q" * 70_000; nb = len(big)
+    ours = H.oracle_compress(big, frameLog=23, windowLog=23, regionLog=19, ldmLog=14)
+    r, out, nj = dec(ours, nb, 1)
+    assert (r, out) == (nb, big) and nj == 0                     # regions are independent: the units run side by side
+    if H.ref_available():
+        ref = H.ref_compress(big, level=3)
+        r, out, nj = dec(ref, nb, 1)
+        assert (r, out) == (nb, big) and nj == 1                 # one sliding-window frame: stage J
+        r, out, nj = dec(ref + H.oracle_compress(data) + ref, 2 * nb + n, 1)
+        assert (r, out) == (2 * nb + n, big + data + big) and nj == 2
 
 
 def test_emulated_stage_z_sequence_array_full(pkg, emu):

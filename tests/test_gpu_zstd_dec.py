@@ -146,3 +146,49 @@ def test_reference_regression_archives(codec):
         comp = open(os.path.join(GOLDEN, name), "rb").read()
         out = codec.decompress(comp, max_size=meta["size"]) if meta["method"] == "zstd" else codec.lzma2_decompress(comp, meta["dict_prop"])
         assert len(out) == meta["size"] and hashlib.sha256(out).hexdigest() == meta["sha256"], name
+
+
+@pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref not built")
+def test_stage_j_pointer_jumping(pkg, inputs):
+    """stage J on hardware: forced on every frame (mode 2) it restores what the execution units restore -- reference frames of several
+    levels, frames with raw / RLE blocks and long runs, several frames in one call, a damaged stream (same verdict as the oracle decoder);
+    in automatic mode a reference-written 48 MiB frame (sliding window: its units would run one behind the other) is taken by stage J, a
+    long-mode frame of this encoder (independent regions) and the short frames are not; host batches and the device-pointer call agree"""
+    S_JUMP = 11
+    off, auto, force = pkg.Codec(0, dec_jump=0), pkg.Codec(0), pkg.Codec(0, dec_jump=2)
+    for name, d in inputs.items():
+        for comp in (helpers.ref_compress(d, 3), helpers.ref_compress(d, 19 if len(d) < 600_000 else 5, 1), off.compress(d)):
+            force.reset_stats()
+            assert force.decompress(comp, max_size=len(d)) == d, name
+            assert force.stat(S_JUMP) > 0 or not d, name
+            assert off.decompress(comp, max_size=len(d)) == d and off.stat(S_JUMP) == 0
+    d = inputs["mixed"]
+    comp = helpers.ref_compress(d, 4)
+    for pos in (len(comp) // 3, len(comp) // 2, len(comp) - 9):
+        bad = bytearray(comp); bad[pos] ^= 0x41
+        try:
+            want = helpers.oracle_decompress(bytes(bad), len(d))
+        except ValueError:
+            want = None
+        try:
+            got = force.decompress(bytes(bad), max_size=len(d))
+        except pkg.B200zError:
+            got = None
+        assert got == want, pos
+    big = helpers.far_copies(pkg, 48 << 20, every=1 << 22, span=(100_000, 900_000), seed=5) + bytes(1 << 20) + b"ab" * 300_000
+    ref = helpers.ref_compress(big, 3, 0, nbWorkers=4)
+    for c, jumped in ((auto, 1), (force, 1), (off, 0)):
+        c.reset_stats()
+        assert c.decompress(ref, max_size=len(big)) == big
+        assert c.stat(S_JUMP) == jumped
+    lng = pkg.Codec(0, long=24)
+    ours = lng.compress(big); lng.close()
+    auto.reset_stats()
+    assert auto.decompress(ours) == big and auto.stat(S_JUMP) == 0
+    multi = ref + off.compress(d) + ref
+    auto.reset_stats()
+    assert auto.decompress(multi, max_size=2 * len(big) + len(d)) == big + d + big and auto.stat(S_JUMP) == 2
+    small = pkg.Codec(0, host_batch_log=24)                             # 16 MiB batches: every reference frame is a batch of its own
+    assert small.decompress(multi, max_size=2 * len(big) + len(d)) == big + d + big and small.stat(S_JUMP) == 2
+    for c in (off, auto, force, small):
+        c.close()
