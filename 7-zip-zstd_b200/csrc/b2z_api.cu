@@ -293,6 +293,10 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
         uint16_t* spill = nullptr;
         const uint64_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
+        if (ctx->lz2Mode == 0) {                                    // 32 chains per warp: every chain's whole model in global memory
+            if (ctx->decScratch[5].reserve(lzma2_enc_model_bytes((uint32_t)nChains))) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");
+            spill = (uint16_t*)ctx->decScratch[5].p;
+        } else
         if (ctx->lz2Mode != 1 && nChains > 11ull * ctx->smCount && ctx->decScratch[5].reserve((size_t)nChains * LITN * 2u) == 0) spill = (uint16_t*)ctx->decScratch[5].p;
         if (ctx->lz2Mode == 2 && !spill) {
             if (ctx->decScratch[5].reserve((size_t)nChains * LITN * 2u)) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");

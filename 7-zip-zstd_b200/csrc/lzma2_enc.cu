@@ -241,12 +241,271 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
     slotSize[chain] = e.op;
 }
 
+// ---------------------------------------------------------------------------------------------------- stage R, 32 chains per warp
+// The kernel above spends a warp on one chain: 31 of 32 lanes of every issued instruction are idle, and putting several chains on the
+// lanes of one warp (template parameter L) only made it slower because the chains' control flow differs at every coded bit.  What does
+// NOT differ is the coding of one binary decision -- load the probability, split the range, adapt, renormalise -- so this kernel separates
+// the two: every lane owns a chain and
+//   phase A (per lane, divergent but short): turns its next packets into a QUEUE of decisions in shared memory -- (probability index, bit)
+//           pairs, 13 + 1 bits each; which probabilities a packet touches and with which bits is a function of the input alone, never of
+//           the probabilities -- until the queue holds B2Z_R32_FILL decisions;
+//   phase B (lock-step): B2Z_R32_FILL times, all 32 lanes pop a decision and code it.  The probabilities of the steps to come are loaded
+//           B2Z_R32_DEPTH steps ahead (a step that adapts one of them forwards the new value).
+// The models live in global memory, interleaved by lane (probability i of lane l at [i][l]).  Chunk rules are the single-chain kernel's:
+// a packet may be queued ahead of its coding only while the chunk cannot reach its packed limit before it (a decision emits at most one
+// byte, so `packed + queued < limit` is a proof); near the limit a lane queues one packet at a time and decides with an empty queue, which
+// is the sequential rule exactly.  Bytes are those of the kernel above (and of oracle/lzma2_enc_oracle.c).
+// Replaces (reference): the per-thread slices of fast-lzma2 (lzma2_enc.c:1937-2099) / range_enc.h:62-108 -- there one slice per CPU thread.
+#define B2Z_R32_QCAP   128u      // queue slots per lane (a packet is at most 48 decisions: fill < 32 + 48)
+#define B2Z_R32_FILL   32u
+#define B2Z_R32_DEPTH  4
+#define B2Z_R32_DIRECT 0x1FFFu   // "probability index" of a direct bit (range halves, no model)
+#define B2Z_R32_WARPS  2u
+static_assert(P_LIT + (0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP)) < B2Z_R32_DIRECT, "a queue entry holds a 13-bit probability index");
+
+__device__ __forceinline__ void rce32_shift_low(RcE& e) {
+    if ((uint32_t)e.low < 0xFF000000u || (uint32_t)(e.low >> 32) != 0u) {
+        const uint32_t carry = (uint32_t)(e.low >> 32);
+        uint8_t* o = e.out + e.op;
+        o[0] = (uint8_t)(e.cache + carry);
+        for (uint32_t k = 1; k < e.cacheSize; k++) o[k] = (uint8_t)(0xFFu + carry);
+        e.op += e.cacheSize; e.cacheSize = 0;
+        e.cache = ((uint32_t)e.low >> 24) & 0xFFu;
+    }
+    e.cacheSize++;
+    e.low = (e.low & 0x00FFFFFFull) << 8;
+}
+
+__global__ void __launch_bounds__(32 * B2Z_R32_WARPS)
+lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, const uint64_t* __restrict__ seqs,
+                         const uint32_t* __restrict__ nseq, uint8_t* __restrict__ slots, uint32_t slotStride,
+                         uint32_t* __restrict__ slotSize, uint16_t* models, uint32_t* __restrict__ status, uint32_t nChains) {
+    B2Z_EXTERN_SMEM(uint16_t, queues);
+    constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP), NPROBS = P_LIT + LITN;
+    constexpr uint32_t PBM = (1u << B2Z_LZ2_PB) - 1u, LPM = (1u << B2Z_LZ2_LP) - 1u;
+    const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+    const uint32_t group = blockIdx.x * (blockDim.x >> 5) + wic, chain = group * 32u + lane;
+    uint16_t* const q = queues + (size_t)wic * B2Z_R32_QCAP * 32u + lane;                 // slot s of this lane: q[(s % QCAP) * 32]
+    uint16_t* const model = models + (size_t)group * NPROBS * 32u + lane;                 // probability i of this lane: model[i * 32]
+    uint32_t head = 0, tail = 0;                                                           // decisions coded / queued so far
+    auto put = [&](uint32_t idx, uint32_t bit) { q[(tail & (B2Z_R32_QCAP - 1u)) * 32u] = (uint16_t)((idx << 1) | bit); tail++; };
+    auto put_tree = [&](uint32_t base, uint32_t bits, uint32_t v) { uint32_t m = 1; for (uint32_t i = bits; i--;) { const uint32_t b = (v >> i) & 1u; put(base + m, b); m = (m << 1) | b; } };
+    auto put_tree_rev = [&](uint32_t base, uint32_t bits, uint32_t v) { uint32_t m = 1; for (uint32_t i = 0; i < bits; i++) { const uint32_t b = (v >> i) & 1u; put(base + m, b); m = (m << 1) | b; } };
+    auto put_len = [&](uint32_t l, uint32_t len, uint32_t ps) {
+        len -= 2u;
+        if (len < 8u) { put(l + L_CHOICE, 0); put_tree(l + L_LOW + ps * 8u, 3, len); }
+        else if (len < 16u) { put(l + L_CHOICE, 1); put(l + L_CHOICE2, 0); put_tree(l + L_MID + ps * 8u, 3, len - 8u); }
+        else { put(l + L_CHOICE, 1); put(l + L_CHOICE2, 1); put_tree(l + L_HIGH, 8, len - 16u); }
+    };
+
+    // the chain (frame, slice) of this lane, as in the kernel above
+    const uint64_t F = 1ull << g.frameLog;
+    const uint32_t bpf = (uint32_t)(F >> 17), sliceBlocks = B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags), spf = bpf / sliceBlocks;
+    const uint32_t f = chain / spf, sl = chain - f * spf;
+    const uint64_t f0 = (uint64_t)f << g.frameLog;
+    bool done = chain >= nChains;
+    const uint32_t n = done ? 0u : (uint32_t)((srcSize - f0) < F ? (srcSize - f0) : F);
+    const uint8_t* __restrict__ base = src + (done ? 0ull : f0);
+    const uint32_t nblkFrame = (n + B2Z_BLOCK - 1u) / B2Z_BLOCK;
+    const uint32_t b0 = sl * sliceBlocks, b1 = (b0 + sliceBlocks) < nblkFrame ? (b0 + sliceBlocks) : nblkFrame;
+    if (!done && b0 >= nblkFrame) { slotSize[chain] = 0; done = true; }                   // slice beyond the end of a short last frame
+
+    RcE e; e.low = 0; e.range = 0; e.cacheSize = 0; e.cache = 0; e.out = slots + (size_t)(done ? 0u : chain) * slotStride; e.op = 0;
+    uint32_t state = 0, rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
+    uint32_t chunkPos = 0, chunkOut = 0, hdr = 0;
+    bool open = false, needDict = sl == 0, needProps = true, needState = true, overflow = false, finishing = false;
+
+    auto chunk_close = [&](uint32_t pos) {                                              // (queue empty)
+        for (int i = 0; i < 5; i++) rce32_shift_low(e);
+        const uint32_t unpack = pos - chunkPos, pack = e.op - chunkOut - hdr;
+        uint8_t* h = e.out + chunkOut;
+        if (pack + 2u >= unpack) {                                                      // store the chunk uncompressed
+            h[0] = needDict ? 1 : 2; h[1] = (uint8_t)((unpack - 1u) >> 8); h[2] = (uint8_t)(unpack - 1u);
+            const uint8_t* s = base + chunkPos;
+            for (uint32_t i = 0; i < unpack; i++) h[3u + i] = __ldg(s + i);
+            e.op = chunkOut + 3u + unpack;
+            needDict = false; needState = true;
+        } else {
+            const uint32_t mode = needDict ? 3u : (needProps ? 2u : (needState ? 1u : 0u));
+            h[0] = (uint8_t)(0x80u | (mode << 5) | ((unpack - 1u) >> 16)); h[1] = (uint8_t)((unpack - 1u) >> 8); h[2] = (uint8_t)(unpack - 1u);
+            h[3] = (uint8_t)((pack - 1u) >> 8); h[4] = (uint8_t)(pack - 1u);
+            if (mode >= 2u) h[5] = (uint8_t)B2Z_LZ2_PROPS;
+            needDict = needProps = needState = false;
+        }
+        open = false;
+    };
+    auto chunk_open = [&](uint32_t pos) {                                               // (queue empty)
+        if (e.op + 65536u + 96u > slotStride) { overflow = true; return; }
+        chunkPos = pos; chunkOut = e.op;
+        hdr = (needDict || needProps) ? 6u : 5u;
+        if (needDict || needProps || needState) {
+            for (uint32_t i = 0; i < NPROBS; i++) model[i * 32u] = 0x0400u;
+            state = 0; rep0 = rep1 = rep2 = rep3 = 0;
+        }
+        e.op += hdr;
+        e.low = 0; e.range = 0xFFFFFFFFu; e.cache = 0; e.cacheSize = 1;
+        open = true;
+    };
+
+    // the producer's cursor: block b, sequence i of ns, what is left of the current sequence (litLeft literals, then mlLeft match bytes at
+    // distance mdist + 1), the zstd repcode history of the block (to undo offBase, Emitter::flush), and the bytes the next packet needs
+    uint32_t b = b0, i = 0, ns = 0, bend = 0, litLeft = 0, mlLeft = 0, mdist = 0, z0 = 0, z1 = 0, z2 = 0;
+    const uint64_t* __restrict__ sq = seqs;
+    uint64_t sNext = 0;
+    uint32_t pos = b0 * B2Z_BLOCK, cur = 0, prev = 0, mb = 0;
+    auto block_begin = [&]() {
+        bend = (b + 1u) * B2Z_BLOCK < n ? (b + 1u) * B2Z_BLOCK : n;
+        sq = seqs + ((size_t)f * bpf + b) * B2Z_MAXSEQ;
+        ns = nseq[(size_t)f * bpf + b]; i = 0; z0 = z1 = z2 = 0;
+        sNext = ns ? __ldg(sq) : 0ull;
+    };
+    if (!done) { cur = __ldg(base + pos); prev = pos ? (uint32_t)__ldg(base + pos - 1u) : 0u; block_begin(); }
+
+    auto literal = [&]() {
+        const uint32_t nxt = (pos + 1u < n) ? (uint32_t)__ldg(base + pos + 1u) : 0u;     // for the next packet
+        put(P_ISMATCH + state * 16u + (pos & PBM), 0);
+        const uint32_t p = P_LIT + 0x300u * (((pos & LPM) << B2Z_LZ2_LC) + (prev >> (8u - B2Z_LZ2_LC)));
+        uint32_t m = 1, k = 8;
+        if (state >= 7u) {                                          // matched literal: context follows the byte at rep0 while it agrees
+            while (k) {
+                --k;
+                const uint32_t bt = (cur >> k) & 1u, mbit = (mb >> k) & 1u;
+                put(p + ((1u + mbit) << 8) + m, bt);
+                m = (m << 1) | bt;
+                if (mbit != bt) break;
+            }
+        }
+        while (k) { --k; const uint32_t bt = (cur >> k) & 1u; put(p + m, bt); m = (m << 1) | bt; }
+        state = state < 4u ? 0u : (state < 10u ? state - 3u : state - 6u);
+        prev = cur; cur = nxt; pos++;
+    };
+    auto match = [&](uint32_t len, uint32_t dist) {                  // dist = distance - 1
+        const uint32_t pN = pos + len;
+        const uint32_t nxt = (pN < n) ? (uint32_t)__ldg(base + pN) : 0u, prevN = __ldg(base + pN - 1u), mbN = __ldg(base + pN - dist - 1u);
+        const uint32_t ps = pos & PBM;
+        put(P_ISMATCH + state * 16u + ps, 1);
+        const int r = dist == rep0 ? 0 : (dist == rep1 ? 1 : (dist == rep2 ? 2 : (dist == rep3 ? 3 : -1)));
+        if (r < 0) {
+            put(P_ISREP + state, 0);
+            put_len(P_LEN, len, ps);
+            state = state < 7u ? 7u : 10u;
+            uint32_t slot;
+            if (dist < 4u) slot = dist; else { const uint32_t nb = highbit32(dist); slot = (nb << 1) | ((dist >> (nb - 1u)) & 1u); }
+            put_tree(P_POSSLOT + (len - 2u < 4u ? len - 2u : 3u) * 64u, 6, slot);
+            if (slot >= 4u) {
+                const uint32_t fb = (slot >> 1) - 1u, bs = (2u | (slot & 1u)) << fb, red = dist - bs;
+                if (slot < 14u) put_tree_rev(P_SPECPOS + bs - slot - 1u, fb, red);
+                else { for (uint32_t k = fb - 4u; k--;) put(B2Z_R32_DIRECT, ((red >> 4) >> k) & 1u); put_tree_rev(P_ALIGN, 4, red & 15u); }
+            }
+            rep3 = rep2; rep2 = rep1; rep1 = rep0; rep0 = dist;
+        } else {
+            put(P_ISREP + state, 1);
+            if (r == 0) { put(P_ISREPG0 + state, 0); put(P_ISREP0LONG + state * 16u + ps, 1); }
+            else {
+                put(P_ISREPG0 + state, 1);
+                if (r == 1) put(P_ISREPG1 + state, 0);
+                else { put(P_ISREPG1 + state, 1); put(P_ISREPG2 + state, (uint32_t)(r - 2)); }
+                if (r == 3) rep3 = rep2;
+                if (r >= 2) rep2 = rep1;
+                rep1 = rep0; rep0 = dist;
+            }
+            put_len(P_REPLEN, len, ps);
+            state = state < 7u ? 8u : 11u;
+        }
+        cur = nxt; prev = prevN; mb = mbN; pos = pN;
+    };
+
+    for (;;) {
+        // ---- phase A: queue packets until B2Z_R32_FILL decisions wait (or the lane has to see its queue drain first)
+        while (!done && !finishing && tail - head < B2Z_R32_FILL) {
+            if (!litLeft && !mlLeft) {                                                  // next sequence / block tail / next block
+                for (;;) {
+                    if (i < ns) {
+                        const uint64_t s = sNext;
+                        if (++i < ns) sNext = __ldg(sq + i);
+                        const uint32_t ll = B2Z_SEQ_LL(s), ob = B2Z_SEQ_OFFBASE(s); uint32_t off;
+                        if (ob > 3u) { off = ob - 3u; z2 = z1; z1 = z0; z0 = off; }
+                        else {
+                            const uint32_t idx = ob - 1u + (ll == 0u);
+                            off = idx == 3u ? z0 - 1u : (idx == 0u ? z0 : (idx == 1u ? z1 : z2));
+                            if (idx != 0u) { if (idx != 1u) z2 = z1; z1 = z0; z0 = off; }
+                        }
+                        litLeft = ll; mlLeft = B2Z_SEQ_ML(s); mdist = off - 1u;
+                        if (litLeft | mlLeft) break;
+                        continue;
+                    }
+                    if (pos < bend) { litLeft = bend - pos; break; }
+                    if (++b >= b1) { finishing = true; break; }
+                    block_begin();
+                }
+                if (finishing) break;
+            }
+            if (open) {                                                                 // the single-chain kernel's chunk_step, see the header
+                const uint32_t packed = e.op - chunkOut - hdr + e.cacheSize, queued = tail - head;
+                if (packed + queued >= B2Z_LZ2_PACK_LIMIT || pos - chunkPos >= B2Z_LZ2_UNPACK_LIMIT) {
+                    if (queued) break;
+                    if (packed >= B2Z_LZ2_PACK_LIMIT || pos - chunkPos >= B2Z_LZ2_UNPACK_LIMIT) chunk_close(pos);
+                }
+            }
+            if (!open) { chunk_open(pos); if (overflow) { done = true; atomicOr(status, 1u); slotSize[chain] = e.op; break; } }
+            if (litLeft) { literal(); litLeft--; }
+            else {
+                uint32_t len = mlLeft > B2Z_LZ2_MAXLEN ? B2Z_LZ2_MAXLEN : mlLeft;
+                if (mlLeft - len == 1u) len--;
+                match(len, mdist); mlLeft -= len;
+            }
+        }
+        if (finishing && !done && tail == head) { if (open) chunk_close(pos); slotSize[chain] = e.op; done = true; }
+        if (__all_sync(B2Z_FULL, done)) break;
+        __syncwarp();
+        // ---- phase B: every lane codes up to B2Z_R32_FILL of its queued decisions, in lock-step
+        const uint32_t myN = done ? 0u : ((tail - head) < B2Z_R32_FILL ? (tail - head) : B2Z_R32_FILL);
+        uint32_t maxN = myN;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(B2Z_FULL, maxN, d); maxN = o > maxN ? o : maxN; }
+        uint32_t ent[B2Z_R32_DEPTH], pv[B2Z_R32_DEPTH];                                  // decisions of steps s .. s + DEPTH - 1 and their probabilities
+#pragma unroll
+        for (int j = 0; j < B2Z_R32_DEPTH; j++) {
+            ent[j] = 0xFFFFu; pv[j] = 0;
+            if ((uint32_t)j < myN) { ent[j] = q[((head + (uint32_t)j) & (B2Z_R32_QCAP - 1u)) * 32u]; if ((ent[j] >> 1) != B2Z_R32_DIRECT) pv[j] = model[(ent[j] >> 1) * 32u]; }
+        }
+        for (uint32_t s = 0; s < maxN; s++) {
+            const uint32_t en = ent[0], v = pv[0], idx = en >> 1, bit = en & 1u;
+#pragma unroll
+            for (int j = 0; j + 1 < B2Z_R32_DEPTH; j++) { ent[j] = ent[j + 1]; pv[j] = pv[j + 1]; }
+            ent[B2Z_R32_DEPTH - 1] = 0xFFFFu; pv[B2Z_R32_DEPTH - 1] = 0;
+            if (s + B2Z_R32_DEPTH < myN) {                                               // issue the loads of step s + DEPTH
+                const uint32_t x = q[((head + s + B2Z_R32_DEPTH) & (B2Z_R32_QCAP - 1u)) * 32u];
+                ent[B2Z_R32_DEPTH - 1] = x;
+                if ((x >> 1) != B2Z_R32_DIRECT) pv[B2Z_R32_DEPTH - 1] = model[(x >> 1) * 32u];
+            }
+            if (s < myN) {
+                if (idx == B2Z_R32_DIRECT) { e.range >>= 1; if (bit) e.low += e.range; }
+                else {
+                    const uint32_t bound = (e.range >> 11) * v;
+                    const uint32_t nv = (uint32_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5)) & 0xFFFFu;
+                    model[idx * 32u] = (uint16_t)nv;
+#pragma unroll
+                    for (int j = 0; j < B2Z_R32_DEPTH; j++) if ((ent[j] >> 1) == idx) pv[j] = nv;   // loaded before this store
+                    if (!bit) e.range = bound; else { e.low += bound; e.range -= bound; }
+                }
+                if (e.range < (1u << 24)) { e.range <<= 8; rce32_shift_low(e); }
+            }
+        }
+        head += myN;
+        __syncwarp();
+    }
+}
+
 uint32_t lzma2_enc_slices_per_frame(const EncGeom& g) { return (1u << (g.frameLog - 17u)) / B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags); }
 // slot of one chain (slice): worst case of its chunk stream while it is being produced
 size_t lzma2_enc_slot_stride(const EncGeom& g) {
     const uint32_t sliceBytes = B2Z_LZ2_SLICE_BLOCKS(g.frameLog, g.flags) * B2Z_BLOCK;
     return ((size_t)B2Z_LZ2_FRAME_BOUND(sliceBytes) + 255u) & ~(size_t)255u;
 }
+
+// bytes of model memory the lock-step kernel needs for nChains chains (whole groups of 32)
+size_t lzma2_enc_model_bytes(uint32_t nChains) { return (size_t)((nChains + 31u) / 32u) * 32u * (P_LIT + (0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP))) * sizeof(uint16_t); }
 
 #ifndef B2Z_CUEMU
 cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
@@ -261,7 +520,12 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
     // (9.6 KiB at lc = 2, 23 chains per SM): 1226 ms -- residency beats the ~6 extra instructions per literal bit.
     const bool glit = mode == 2 || (mode == 0 && litSpill && nChains > slotsResident);
     const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
-    if (glit) {     // two warps (chains) per CTA: 32 CTAs/SM would otherwise cap residency below the register limit
+    if (mode == 0) {                                                // 32 chains per warp; litSpill holds whole models here (lzma2_enc_model_bytes)
+        if (!litSpill) return cudaErrorInvalidValue;
+        const uint32_t groups = (nChains + 31u) / 32u;
+        lzma2_enc_range32_kernel<<<(groups + B2Z_R32_WARPS - 1u) / B2Z_R32_WARPS, 32 * B2Z_R32_WARPS, B2Z_R32_WARPS * B2Z_R32_QCAP * 32u * sizeof(uint16_t), st>>>(
+            src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);
+    } else if (glit) {     // two warps (chains) per CTA: 32 CTAs/SM would otherwise cap residency below the register limit
         lzma2_enc_range_kernel<true, 1><<<(nChains + 1u) / 2u, 64, 2u * P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);
     } else {
         cudaError_t e = cudaFuncSetAttribute(lzma2_enc_range_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemFull);

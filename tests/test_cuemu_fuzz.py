@@ -145,7 +145,7 @@ def test_fuzz_emulated_pipelines_and_damaged_streams(pkg, seed, planted):
             for k in range((min(F, n - f * F) + 131071) // 131072):
                 seqf[(f * bpf + k) * H.MAXSEQ:(f * bpf + k + 1) * H.MAXSEQ] = so[b * H.MAXSEQ:(b + 1) * H.MAXSEQ]; nsf[f * bpf + k] = no[b]; b += 1
         outl = np.zeros(len(wantl) + 200_000, dtype=np.uint8)
-        r = E.emu_lzma2_range_and_assemble(src.ctypes.data, n, fl, flagsl, seqf.ctypes.data, nsf.ctypes.data, outl.ctypes.data, outl.size, rng.choice([0, 1]))
+        r = E.emu_lzma2_range_and_assemble(src.ctypes.data, n, fl, flagsl, seqf.ctypes.data, nsf.ctypes.data, outl.ctypes.data, outl.size, rng.choice([0, 1, 2, 2]))
         assert r == len(wantl) and outl[:r].tobytes() == wantl, ("lzma2 R -> assemble", seed, it, n, fl, sl)
         for comp, kind in ((want, "z"), (wantl, "l")):
             for mut in range(3):
@@ -161,7 +161,7 @@ def test_fuzz_emulated_pipelines_and_damaged_streams(pkg, seed, planted):
                 if kind == "z":
                     r = E.emu_zstd_decode(cb.ctypes.data, len(c), back.ctypes.data, n)
                 else:
-                    r = E.emu_lzma2_decode(cb.ctypes.data, len(c), prop, back.ctypes.data, n, rng.choice([0, 1])) if len(c) else -1
+                    r = E.emu_lzma2_decode(cb.ctypes.data, len(c), prop, back.ctypes.data, n, rng.choice([0, 1, 2, 2])) if len(c) else -1
                 if not mut:
                     assert r == n and back[:n].tobytes() == data, ("decode", kind, seed, it, n)
                 else:

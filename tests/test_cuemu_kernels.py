@@ -257,7 +257,7 @@ def test_emulated_method21_pipeline_end_to_end(pkg, emu, fl, sl, opt):
     else:
         seqs, nseq, _, _ = H.oracle_find_sequences(data, frameLog=fl, windowLog=fl)
     prop, want = H.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl, flags=flags)
-    for glit in (0, 1):
+    for glit in (0, 1, 2):                                              # 2 = 32 chains per warp in lock-step (lzma2_enc_range32_kernel)
         out = np.zeros(len(want) + 200_000, dtype=np.uint8)
         r = emu.emu_lzma2_range_and_assemble(src.ctypes.data, n, fl, flags, seqs.ctypes.data, nseq.ctypes.data, out.ctypes.data, out.size, glit)
         assert r == len(want) and out[:r].tobytes() == want, glit

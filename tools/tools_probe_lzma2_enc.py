@@ -14,7 +14,7 @@ d_src = torch.from_numpy(data).cuda()
 cap = c.lzma2_compress_bound(n)
 d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
 d_out = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
-for model in ([int(sys.argv[2])] if len(sys.argv) > 2 else (1, 2)):
+for model in ([int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (0, 2)):
     c.set("lzma2_model", model)
     for it in range(2):
         c.reset_stats(); torch.cuda.synchronize(); t0 = time.time()
