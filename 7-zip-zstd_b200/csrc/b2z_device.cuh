@@ -155,4 +155,64 @@ __device__ inline uint64_t xxh64_device_unaligned(const uint8_t* data, uint64_t 
     return h;
 }
 
+
+// XXH64 by one warp, for the one big frame the reference's .zst handler writes with a content checksum (ZstdHandler.cpp:262-282).
+// The four stripe accumulators are four strictly sequential chains -- lanes 0-3 run one each, ~25 cycles of dependent 64-bit
+// arithmetic per 32 input bytes, which is the floor for this hash on any machine that cannot multiply faster.  What the other lanes
+// add is the memory pipeline: the warp loads the next tile (aligned 16-byte words, coalesced, any byte alignment of `data`) into
+// registers while the four lanes work on the current one from shared memory.  tileMem: 2 * B2Z_XXH_TILE_BYTES, 16-byte aligned.
+#define B2Z_XXH_TILE 4096u
+#define B2Z_XXH_TILE_BYTES (B2Z_XXH_TILE + 32u)
+__device__ inline uint64_t xxh64_warp(const uint8_t* data, uint64_t len, uint8_t* tileMem, uint32_t lane) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 15u);
+    const uint4* __restrict__ aw = reinterpret_cast<const uint4*>(data - sh);            // aligned words; word j holds data bytes [16 j - sh, 16 j - sh + 16)
+    const uint64_t nStripes = len >> 5, stripeBytes = nStripes << 5;
+    const uint64_t nWordsValid = (sh + len + 15u) >> 4;                                    // words that hold at least one byte of the buffer
+    constexpr uint32_t WPT = B2Z_XXH_TILE / 16u + 1u, PER = (WPT + 31u) / 32u;             // words per tile (one more for the shift), per lane
+    uint64_t acc = lane == 0 ? P1 + P2 : (lane == 1 ? P2 : (lane == 2 ? 0ull : 0ull - P1));
+    const uint64_t nTiles = (stripeBytes + B2Z_XXH_TILE - 1u) / B2Z_XXH_TILE;
+    uint4 r[PER];
+    auto fetch = [&](uint64_t t) {
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) {
+            const uint32_t j = k * 32u + lane; const uint64_t wj = t * (B2Z_XXH_TILE / 16u) + j;
+            r[k] = (j < WPT && wj < nWordsValid) ? aw[wj] : make_uint4(0, 0, 0, 0);
+        }
+    };
+    auto stash = [&](uint32_t buf) {
+        uint4* d = reinterpret_cast<uint4*>(tileMem + buf * B2Z_XXH_TILE_BYTES);
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) { const uint32_t j = k * 32u + lane; if (j < WPT) d[j] = r[k]; }
+    };
+    if (nTiles) { fetch(0); stash(0); }
+    __syncwarp();
+    for (uint64_t t = 0; t < nTiles; t++) {
+        if (t + 1 < nTiles) fetch(t + 1);                                                  // in flight while lanes 0-3 hash tile t
+        if (lane < 4u) {
+            const uint64_t* w = reinterpret_cast<const uint64_t*>(tileMem + (uint32_t)(t & 1u) * B2Z_XXH_TILE_BYTES);
+            const uint64_t left = stripeBytes - t * B2Z_XXH_TILE;
+            const uint32_t ns = (uint32_t)((left < B2Z_XXH_TILE ? left : B2Z_XXH_TILE) >> 5), bsh = (sh & 7u) * 8u;
+            uint32_t o = ((sh & 8u) >> 3) + lane;                                          // 8-byte word index of this lane's first input
+            for (uint32_t k = 0; k < ns; k++, o += 4u) acc = xxh_round(acc, funnel64(w[o], w[o + 1u], bsh));
+        }
+        __syncwarp();
+        if (t + 1 < nTiles) stash((uint32_t)((t + 1) & 1u));
+        __syncwarp();
+    }
+    const uint64_t v1 = __shfl_sync(B2Z_FULL, acc, 0), v2 = __shfl_sync(B2Z_FULL, acc, 1), v3 = __shfl_sync(B2Z_FULL, acc, 2), v4 = __shfl_sync(B2Z_FULL, acc, 3);
+    uint64_t h;
+    if (len >= 32) {
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    } else h = P5;
+    h += len;
+    uint64_t i = stripeBytes;                                                              // < 32 bytes left: every lane repeats them (byte loads)
+    for (; i + 8 <= len; i += 8) { uint64_t v = 0; for (int b = 0; b < 8; b++) v |= (uint64_t)data[i + b] << (8 * b); h ^= xxh_round(0, v); h = xxh_rotl(h, 27) * P1 + P4; }
+    if (i + 4 <= len) { uint32_t v = 0; for (int b = 0; b < 4; b++) v |= (uint32_t)data[i + b] << (8 * b); h ^= (uint64_t)v * P1; h = xxh_rotl(h, 23) * P2 + P3; i += 4; }
+    for (; i < len; i++) { h ^= data[i] * P5; h = xxh_rotl(h, 11) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
 }  // namespace b2z

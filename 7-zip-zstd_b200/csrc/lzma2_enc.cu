@@ -365,17 +365,14 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
         const uint32_t nxt = (pos + 1u < n) ? (uint32_t)__ldg(base + pos + 1u) : 0u;     // for the next packet
         put(P_ISMATCH + state * 16u + (pos & PBM), 0);
         const uint32_t p = P_LIT + 0x300u * (((pos & LPM) << B2Z_LZ2_LC) + (prev >> (8u - B2Z_LZ2_LC)));
-        uint32_t m = 1, k = 8;
-        if (state >= 7u) {                                          // matched literal: context follows the byte at rep0 while it agrees
-            while (k) {
-                --k;
-                const uint32_t bt = (cur >> k) & 1u, mbit = (mb >> k) & 1u;
-                put(p + ((1u + mbit) << 8) + m, bt);
-                m = (m << 1) | bt;
-                if (mbit != bt) break;
-            }
+        uint32_t m = 1; bool matched = state >= 7u;                 // matched literal: the context follows the byte at rep0 while it agrees
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {                              // one shape for every lane: no early exit
+            const uint32_t bt = (cur >> k) & 1u, mbit = (mb >> k) & 1u;
+            put(p + (matched ? ((1u + mbit) << 8) : 0u) + m, bt);
+            m = (m << 1) | bt;
+            matched = matched && mbit == bt;
         }
-        while (k) { --k; const uint32_t bt = (cur >> k) & 1u; put(p + m, bt); m = (m << 1) | bt; }
         state = state < 4u ? 0u : (state < 10u ? state - 3u : state - 6u);
         prev = cur; cur = nxt; pos++;
     };
@@ -416,9 +413,15 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
     };
 
     for (;;) {
-        // ---- phase A: queue packets until B2Z_R32_FILL decisions wait (or the lane has to see its queue drain first)
-        while (!done && !finishing && tail - head < B2Z_R32_FILL) {
-            if (!litLeft && !mlLeft) {                                                  // next sequence / block tail / next block
+        // ---- phase A: queue packets until B2Z_R32_FILL decisions wait (or the lane has to see its queue drain first).  Every pass of the
+        // loop is one packet per lane; the __syncwarp()s are there for the hardware, not for the data: without a convergence point after
+        // each section the lanes drift apart and the warp executes them one after the other (measured: 2.4 s per 4 GiB, the cost of 32
+        // serial chains)
+        bool blocked = false;
+        for (;;) {
+            bool go = !done && !finishing && !blocked && tail - head < B2Z_R32_FILL;
+            if (!__any_sync(B2Z_FULL, go)) break;
+            if (go && !litLeft && !mlLeft) {                                            // next sequence / block tail / next block
                 for (;;) {
                     if (i < ns) {
                         const uint64_t s = sNext;
@@ -435,25 +438,29 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
                         continue;
                     }
                     if (pos < bend) { litLeft = bend - pos; break; }
-                    if (++b >= b1) { finishing = true; break; }
+                    if (++b >= b1) { finishing = true; go = false; break; }
                     block_begin();
                 }
-                if (finishing) break;
             }
-            if (open) {                                                                 // the single-chain kernel's chunk_step, see the header
+            __syncwarp();
+            if (go && open) {                                                           // the single-chain kernel's chunk_step, see the header
                 const uint32_t packed = e.op - chunkOut - hdr + e.cacheSize, queued = tail - head;
                 if (packed + queued >= B2Z_LZ2_PACK_LIMIT || pos - chunkPos >= B2Z_LZ2_UNPACK_LIMIT) {
-                    if (queued) break;
-                    if (packed >= B2Z_LZ2_PACK_LIMIT || pos - chunkPos >= B2Z_LZ2_UNPACK_LIMIT) chunk_close(pos);
+                    if (queued) { blocked = true; go = false; }
+                    else if (packed >= B2Z_LZ2_PACK_LIMIT || pos - chunkPos >= B2Z_LZ2_UNPACK_LIMIT) chunk_close(pos);
                 }
             }
-            if (!open) { chunk_open(pos); if (overflow) { done = true; atomicOr(status, 1u); slotSize[chain] = e.op; break; } }
-            if (litLeft) { literal(); litLeft--; }
-            else {
+            if (go && !open) { chunk_open(pos); if (overflow) { done = true; go = false; atomicOr(status, 1u); slotSize[chain] = e.op; } }
+            __syncwarp();
+            const bool lit = go && litLeft;
+            if (lit) { literal(); litLeft--; }
+            __syncwarp();
+            if (go && !lit) {
                 uint32_t len = mlLeft > B2Z_LZ2_MAXLEN ? B2Z_LZ2_MAXLEN : mlLeft;
                 if (mlLeft - len == 1u) len--;
                 match(len, mdist); mlLeft -= len;
             }
+            __syncwarp();
         }
         if (finishing && !done && tail == head) { if (open) chunk_close(pos); slotSize[chain] = e.op; done = true; }
         if (__all_sync(B2Z_FULL, done)) break;
@@ -491,6 +498,7 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
                 }
                 if (e.range < (1u << 24)) { e.range <<= 8; rce32_shift_low(e); }
             }
+            __syncwarp();                                                                // (convergence, see phase A)
         }
         head += myN;
         __syncwarp();

@@ -1136,26 +1136,26 @@ zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames
 }
 
 // ---------------------------------------------------------------- checksum verification
-__global__ void zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, uint32_t nFrames,
-                                       const uint8_t* __restrict__ dst, DecCounts* counts) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per frame (xxh64_warp: lanes 0-3 hash, the warp streams the frame through shared memory)
+__global__ void __launch_bounds__(128)
+zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, uint32_t nFrames,
+                       const uint8_t* __restrict__ dst, DecCounts* counts) {
+    __shared__ __align__(16) uint8_t tiles[4][2 * B2Z_XXH_TILE_BYTES];
+    const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+    const uint32_t f = blockIdx.x * (blockDim.x >> 5) + wic;
     if (f >= nFrames || counts->status) return;
     const DecFrame fr = frames[f];
     if (!fr.checksum) return;
     const uint8_t* c = src + fr.endOff - 4;
     const uint32_t want = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
-    // frame outputs start at arbitrary byte offsets: hash from the aligned base when possible, else byte-wise tail rules apply
-    const uint8_t* p = dst + fr.dstOff;
-    uint64_t h;
-    if (((uintptr_t)p & 7u) == 0) h = xxh64_device(p, fr.regen);
-    else h = xxh64_device_unaligned(p, fr.regen);
-    if ((uint32_t)h != want) atomicOr(&counts->status, B2Z_DERR_CHECKSUM);
+    const uint64_t h = xxh64_warp(dst + fr.dstOff, fr.regen, tiles[wic], lane);        // frame outputs start at arbitrary byte offsets
+    if (lane == 0 && (uint32_t)h != want) atomicOr(&counts->status, B2Z_DERR_CHECKSUM);
 }
 
 // ---------------------------------------------------------------- launchers
 #ifndef B2Z_CUEMU
 void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st) {
-    if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 63) / 64, 64, 0, st>>>(src, frames, nFrames, dst, counts);
+    if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 3) / 4, 128, 0, st>>>(src, frames, nFrames, dst, counts);
 }
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st) {
     zstd_dec_find_frames_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, counts);
