@@ -162,9 +162,12 @@ int b200z_xz_parse(const void* srcv, size_t n, b200z_xz_block* blocks, uint32_t 
             if (dictProp > 40) return B200Z_E_CORRUPT;
             for (; k < hs - 4; k++) if (s[ip + k]) return B200Z_E_CORRUPT;
             const size_t dataOff = ip + hs;
-            if (pack == ~0ull || unpack == ~0ull) {                 // sizes not in the header: walk the chunk headers to the end marker
+            {   // every Block's payload is walked chunk header by chunk header, declared sizes or not: it must be ONE complete LZMA2 stream --
+                // first chunk a dictionary reset, end marker exactly where the Compressed Size says, chunk sizes adding up to the
+                // Uncompressed Size -- which is what XzDec / liblzma enforce by decoding Block by Block (C/XzDec.c:1100-1300)
                 b2z::Lz2Counts c;
-                b2z::lzma2_walk(s + dataOff, n - dataOff, c, CutEmit{ nullptr, 0 });
+                const size_t avail = (pack != ~0ull && pack < n - dataOff) ? (size_t)pack : n - dataOff;
+                b2z::lzma2_walk(s + dataOff, avail, c, CutEmit{ nullptr, 0 });
                 if (c.status) return B200Z_E_CORRUPT;
                 if (pack != ~0ull && pack != c.srcUsed) return B200Z_E_CORRUPT;
                 if (unpack != ~0ull && unpack != c.total) return B200Z_E_CORRUPT;
@@ -179,6 +182,7 @@ int b200z_xz_parse(const void* srcv, size_t n, b200z_xz_block* blocks, uint32_t 
                 B.nFilters = nf - 1u; for (uint32_t f = 0; f < 3; f++) { B.filterId[f] = fId[f]; B.filterProp[f] = fProp[f]; }
                 for (uint32_t i = 0; i < cb && i < 8; i++) B.check |= (uint64_t)s[dataOff + padded + i] << (8 * i);
             }
+            if (tot + unpack < tot) return B200Z_E_CORRUPT;          // (64-bit wrap of the declared sizes)
             nb++; tot += unpack;
             recs.emplace_back((uint64_t)hs + pack + cb, unpack);
             ip = dataOff + padded + cb;

@@ -191,3 +191,33 @@ def test_reader_agrees_with_liblzma_on_damaged_container_fields(pkg):
         except lzma.LZMAError:
             ok = False
         assert (rc == 0) == ok, (it, pos, rc)
+
+
+def test_reader_walks_every_block_payload(pkg):
+    """a Block whose header declares both sizes is still walked chunk header by chunk header: an end marker before the declared
+    Compressed Size, a chunk that runs past it, or chunk sizes that do not add up to the Uncompressed Size are rejected by the parser
+    itself (as XzDec / liblzma reject them by decoding Block by Block), not left to whatever the spliced stream happens to decode to"""
+    L = _lib(pkg)
+    data = pkg.corpus.g2(600_000).tobytes()
+    prop, lz = H.oracle_lzma2_compress(data, frameLog=18, windowLog=18, flags=1)        # 256 KiB Blocks: two chunks each
+    xz = _wrap(L, lz, prop, 4, data, 18)
+    rc, blocks, total = _parse(L, xz)
+    assert rc == 0 and len(blocks) == 3 and total == len(data)
+    b = blocks[1]
+    def chunk_offsets(off, size):                                   # offsets of the chunk headers of one Block's payload
+        out, ip = [], off
+        while xz[ip] != 0:
+            out.append(ip); c = xz[ip]
+            ip += (3 + ((xz[ip + 1] << 8) | xz[ip + 2]) + 1) if c <= 2 else ((6 if c >= 0xC0 else 5) + ((xz[ip + 3] << 8) | xz[ip + 4]) + 1)
+        assert ip == off + size - 1
+        return out
+    heads = chunk_offsets(b.packOff, b.packSize)
+    assert len(heads) >= 2
+    for mutate in (lambda s: s.__setitem__(heads[1], 0),                                   # end marker in the middle of the Block
+                   lambda s: s.__setitem__(heads[-1] + 4, (s[heads[-1] + 4] + 1) & 255),    # last chunk one byte longer: runs over the end marker
+                   lambda s: s.__setitem__(heads[-1] + 2, (s[heads[-1] + 2] + 1) & 255),    # chunk sizes no longer add up to the Uncompressed Size
+                   lambda s: s.__setitem__(heads[0], 0x80)):                                # first chunk of a Block without a dictionary reset
+        s = bytearray(xz); mutate(s)
+        assert _parse(L, bytes(s))[0] == -5
+        with pytest.raises(lzma.LZMAError):
+            lzma.decompress(bytes(s), format=lzma.FORMAT_XZ)
