@@ -60,7 +60,7 @@ struct DecBlock {
 struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; uint32_t maxFrameBlocks, nJump; };
 
 // stage D0: frame discovery (1 thread; hops over mcmilk size hints when present), then per-frame block indexing
-void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st);
+void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, bool useHints, cudaStream_t st);
 void launch_zstd_dec_index_blocks(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames,
                                   DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st);
 // stage D1: tables (one warp per block) then streams (one thread per stream); literals | sequences on two CUDA streams

@@ -453,7 +453,14 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
             if (go && !open) { chunk_open(pos); if (overflow) { done = true; go = false; atomicOr(status, 1u); slotSize[chain] = e.op; } }
             __syncwarp();
             const bool lit = go && litLeft;
-            if (lit) { literal(); litLeft--; }
+            if (lit) {                                                                  // up to three literals per pass (a match is about as many decisions)
+                const uint32_t pk = e.op - chunkOut - hdr + e.cacheSize + (tail - head);
+                const bool room = pk + 18u < B2Z_LZ2_PACK_LIMIT && pos + 2u - chunkPos < B2Z_LZ2_UNPACK_LIMIT;   // the chunk rule holds for all three
+                const uint32_t c = (room && litLeft >= 3u) ? 3u : (room && litLeft == 2u ? 2u : 1u);
+#pragma unroll 1
+                for (uint32_t k = 0; k < c; k++) literal();
+                litLeft -= c;
+            }
             __syncwarp();
             if (go && !lit) {
                 uint32_t len = mlLeft > B2Z_LZ2_MAXLEN ? B2Z_LZ2_MAXLEN : mlLeft;
@@ -470,35 +477,47 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
         uint32_t maxN = myN;
 #pragma unroll
         for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(B2Z_FULL, maxN, d); maxN = o > maxN ? o : maxN; }
-        uint32_t ent[B2Z_R32_DEPTH], pv[B2Z_R32_DEPTH];                                  // decisions of steps s .. s + DEPTH - 1 and their probabilities
+        // slot k of the pipeline holds the decision of step s with s % DEPTH == k and its probability, loaded DEPTH steps ahead.  A step that
+        // adapts a probability some slot has already loaded marks that slot stale; a stale slot loads again when its turn comes (rare: the
+        // same index within DEPTH decisions).  The stale mark is a flag, not a forwarded value, so that nothing touches a slot's register
+        // before its load has had DEPTH steps to arrive (forwarding into it made every step wait for the load it had just issued: 40 % of
+        // the kernel's time in the first version)
+        uint32_t ent[B2Z_R32_DEPTH], pv[B2Z_R32_DEPTH], stale = 0;
 #pragma unroll
         for (int j = 0; j < B2Z_R32_DEPTH; j++) {
             ent[j] = 0xFFFFu; pv[j] = 0;
             if ((uint32_t)j < myN) { ent[j] = q[((head + (uint32_t)j) & (B2Z_R32_QCAP - 1u)) * 32u]; if ((ent[j] >> 1) != B2Z_R32_DIRECT) pv[j] = model[(ent[j] >> 1) * 32u]; }
         }
-        for (uint32_t s = 0; s < maxN; s++) {
-            const uint32_t en = ent[0], v = pv[0], idx = en >> 1, bit = en & 1u;
+        for (uint32_t s0 = 0; s0 < maxN; s0 += B2Z_R32_DEPTH) {
 #pragma unroll
-            for (int j = 0; j + 1 < B2Z_R32_DEPTH; j++) { ent[j] = ent[j + 1]; pv[j] = pv[j + 1]; }
-            ent[B2Z_R32_DEPTH - 1] = 0xFFFFu; pv[B2Z_R32_DEPTH - 1] = 0;
-            if (s + B2Z_R32_DEPTH < myN) {                                               // issue the loads of step s + DEPTH
-                const uint32_t x = q[((head + s + B2Z_R32_DEPTH) & (B2Z_R32_QCAP - 1u)) * 32u];
-                ent[B2Z_R32_DEPTH - 1] = x;
-                if ((x >> 1) != B2Z_R32_DIRECT) pv[B2Z_R32_DEPTH - 1] = model[(x >> 1) * 32u];
-            }
-            if (s < myN) {
-                if (idx == B2Z_R32_DIRECT) { e.range >>= 1; if (bit) e.low += e.range; }
-                else {
-                    const uint32_t bound = (e.range >> 11) * v;
-                    const uint32_t nv = (uint32_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5)) & 0xFFFFu;
-                    model[idx * 32u] = (uint16_t)nv;
-#pragma unroll
-                    for (int j = 0; j < B2Z_R32_DEPTH; j++) if ((ent[j] >> 1) == idx) pv[j] = nv;   // loaded before this store
-                    if (!bit) e.range = bound; else { e.low += bound; e.range -= bound; }
+            for (int k = 0; k < B2Z_R32_DEPTH; k++) {
+                const uint32_t s = s0 + (uint32_t)k;
+                if (s >= maxN) break;                                                    // (warp-uniform)
+                const uint32_t en = ent[k], idx = en >> 1, bit = en & 1u;
+                const bool act = s < myN, dir = idx == B2Z_R32_DIRECT;
+                uint32_t v = pv[k];
+                if (act && ((stale >> k) & 1u)) v = model[idx * 32u];
+                stale &= ~(1u << k);
+                ent[k] = 0xFFFFu; pv[k] = 0;
+                if (s + B2Z_R32_DEPTH < myN) {                                           // issue the loads of step s + DEPTH
+                    const uint32_t x = q[((head + s + B2Z_R32_DEPTH) & (B2Z_R32_QCAP - 1u)) * 32u];
+                    ent[k] = x;
+                    if ((x >> 1) != B2Z_R32_DIRECT) pv[k] = model[(x >> 1) * 32u];
                 }
-                if (e.range < (1u << 24)) { e.range <<= 8; rce32_shift_low(e); }
+                if (act) {
+                    const uint32_t half = e.range >> 1, bound = (e.range >> 11) * v;
+                    if (!dir) {
+                        model[idx * 32u] = (uint16_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5));
+#pragma unroll
+                        for (int j = 0; j < B2Z_R32_DEPTH; j++) if ((ent[j] >> 1) == idx) stale |= 1u << j;
+                    }
+                    const uint32_t cut = dir ? half : bound;                              // a direct bit halves the range, no model
+                    if (bit) e.low += cut;
+                    e.range = dir ? half : (bit ? e.range - bound : bound);
+                    if (e.range < (1u << 24)) { e.range <<= 8; rce32_shift_low(e); }
+                }
+                __syncwarp();                                                            // (convergence, see phase A)
             }
-            __syncwarp();                                                                // (convergence, see phase A)
         }
         head += myN;
         __syncwarp();

@@ -175,8 +175,12 @@ __device__ uint32_t walk_blocks(const Src& S, uint64_t ip, uint64_t srcSize, uin
     return 0;
 }
 
-__global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts) {
+// useHints: trust mcmilk's 12-byte size hints (a skippable frame 0x184D2A50 whose 4-byte payload is the compressed size of the zstd frame
+// behind it).  counts->nUnits (unused before stage D2) returns how many were trusted: when the stream then fails to index, the caller
+// walks it again without them -- a skippable frame that merely looks like a hint is user data the reference skips (zstd_decompress.c:702).
+__global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, uint32_t useHints) {
     if (threadIdx.x || blockIdx.x) return;
+    uint32_t hinted = 0;
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
     uint64_t ip = 0; uint32_t nf = 0, status = 0;
     while (ip < srcSize && !status) {
@@ -187,13 +191,13 @@ __global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uin
             const uint64_t sz = S.le32(ip + 4);
             if (srcSize - ip < 8 + sz) { status = B2Z_DERR_CORRUPT; break; }
             // a size hint? (payload = compressed size of the zstd frame that follows; verified by D0b)
-            if (magic == 0x184D2A50u && sz == 4 && srcSize - ip >= 16 && S.le32(ip + 12) == 0xFD2FB528u) {
+            if (useHints && magic == 0x184D2A50u && sz == 4 && srcSize - ip >= 16 && S.le32(ip + 12) == 0xFD2FB528u) {
                 const uint64_t fsz = S.le32(ip + 8);
                 if (fsz >= 9 && srcSize - (ip + 12) >= fsz) {
                     if (nf >= frameCap) { status = B2Z_DERR_TABLE_FULL; break; }
                     DecFrame fr; fr.srcOff = ip + 12; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = ip + 12 + fsz;   // regen: end offset (until D2)
                     fr.firstBlock = 0; fr.nBlocks = 0; fr.checksum = 0; fr.pad = 1; fr.endOff = ip + 12 + fsz;                          // pad: 1 = end offset is a hint
-                    frames[nf++] = fr;
+                    frames[nf++] = fr; hinted++;
                     ip += 12 + fsz; continue;
                 }
             }
@@ -211,7 +215,7 @@ __global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uin
         frames[nf++] = fr;
         ip = end;
     }
-    counts->nFrames = nf; counts->nBlocks = 0; counts->status = status; counts->srcUsed = ip;
+    counts->nFrames = nf; counts->nBlocks = 0; counts->status = status; counts->srcUsed = ip; counts->nUnits = hinted;
 }
 
 __global__ void zstd_dec_count_blocks_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames, DecCounts* counts) {
@@ -1157,8 +1161,8 @@ zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restri
 void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st) {
     if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 3) / 4, 128, 0, st>>>(src, frames, nFrames, dst, counts);
 }
-void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, cudaStream_t st) {
-    zstd_dec_find_frames_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, counts);
+void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, bool useHints, cudaStream_t st) {
+    zstd_dec_find_frames_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, counts, useHints ? 1u : 0u);
 }
 void launch_zstd_dec_index_blocks(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t nFrames,
                                   DecBlock* blocks, uint32_t blockCap, DecCounts* counts, cudaStream_t st) {

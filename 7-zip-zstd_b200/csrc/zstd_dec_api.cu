@@ -145,19 +145,27 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
         return fail(ctx, B200Z_E_MEMORY, "decoder table allocation failed%s");
     DecFrame* frames = (DecFrame*)aFrames.p; DecBlock* blocks = (DecBlock*)aBlocks.p;
     DecCounts* counts = (DecCounts*)aCounts.p; uint64_t* total = (uint64_t*)((uint8_t*)aCounts.p + 32);
-    CU(cudaMemsetAsync(aCounts.p, 0, 64, st));
     CU(cudaEventRecord(ctx->ev[0], st));
-    launch_zstd_dec_find_frames((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, counts, st);
-    CU(cudaGetLastError());
     DecCounts hc;
     static_assert(sizeof(DecCounts) == 32, "DecCounts is fetched as four words");
-    { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
-    if (hc.status) return dec_status_to_rc(ctx, hc.status);
-    launch_zstd_dec_index_blocks((const uint8_t*)d_src, srcSize, frames, hc.nFrames, blocks, (uint32_t)blockCap, counts, st);
-    CU(cudaGetLastError());
+    // stage D0, first with mcmilk's size hints trusted (one hop per frame); a stream that then fails to index -- a skippable frame that only
+    // looks like a hint -- is walked again block header by block header, as the reference does for every stream
+    for (int pass = 0; pass < 2; pass++) {
+        CU(cudaMemsetAsync(aCounts.p, 0, 64, st));
+        launch_zstd_dec_find_frames((const uint8_t*)d_src, srcSize, frames, (uint32_t)frameCap, counts, pass == 0, st);
+        CU(cudaGetLastError());
+        { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
+        const uint32_t hinted = hc.nUnits;
+        ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 1;
+        if (!hc.status) {
+            launch_zstd_dec_index_blocks((const uint8_t*)d_src, srcSize, frames, hc.nFrames, blocks, (uint32_t)blockCap, counts, st);
+            CU(cudaGetLastError());
+            { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
+            ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 3;
+        }
+        if (!hc.status || !hinted || (hc.status & ~B2Z_DERR_CORRUPT)) break;       // fine, or not the hints' fault
+    }
     CU(cudaEventRecord(ctx->ev[3], st));
-    { const int frc = b2z_fetch_small(ctx, &hc, counts, sizeof(hc), st); if (frc) return frc; }
-    ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 4;
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
     if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64) ||
         ctx->decScratch[5].reserve(zstd_dec_entropy_scratch_bytes(hc.nBlocks) + zstd_dec_unit_state_bytes(hc.nFrames, hc.nBlocks) + 64))

@@ -220,14 +220,19 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }
     std::vector<DecFrame> frames(frameCap); std::vector<DecBlock> blocks(blockCap);
     DecCounts counts; memset(&counts, 0, sizeof(counts)); uint64_t total = 0;
-    cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_find_frames_kernel(src, srcSize, frames.data(), (uint32_t)frameCap, &counts); });
-    if (counts.status) return -(int64_t)counts.status;
-    const uint32_t nFrames = counts.nFrames;
-    const uint32_t g0 = (nFrames + 63) / 64;
-    if (g0) {
-        cuemu::launch(dim3(g0), dim3(64), 0, [&] { zstd_dec_count_blocks_kernel(src, srcSize, frames.data(), nFrames, &counts); });
-        cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_scan_blocks_kernel(frames.data(), nFrames, (uint32_t)blockCap, &counts); });
-        cuemu::launch(dim3(g0), dim3(64), 0, [&] { zstd_dec_fill_blocks_kernel(src, srcSize, frames.data(), nFrames, blocks.data(), (uint32_t)blockCap, &counts); });
+    uint32_t nFrames = 0;
+    for (int pass = 0; pass < 2; pass++) {                                               // dec_impl: size hints trusted first, walked again if that fails
+        memset(&counts, 0, sizeof(counts));
+        cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_find_frames_kernel(src, srcSize, frames.data(), (uint32_t)frameCap, &counts, pass == 0 ? 1u : 0u); });
+        const uint32_t hinted = counts.nUnits;
+        nFrames = counts.nFrames;
+        const uint32_t g0 = (nFrames + 63) / 64;
+        if (!counts.status && g0) {
+            cuemu::launch(dim3(g0), dim3(64), 0, [&] { zstd_dec_count_blocks_kernel(src, srcSize, frames.data(), nFrames, &counts); });
+            cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_scan_blocks_kernel(frames.data(), nFrames, (uint32_t)blockCap, &counts); });
+            cuemu::launch(dim3(g0), dim3(64), 0, [&] { zstd_dec_fill_blocks_kernel(src, srcSize, frames.data(), nFrames, blocks.data(), (uint32_t)blockCap, &counts); });
+        }
+        if (!counts.status || !hinted || (counts.status & ~B2Z_DERR_CORRUPT)) break;
     }
     if (counts.status) return -(int64_t)counts.status;
     const uint32_t nBlocks = counts.nBlocks;

@@ -324,6 +324,11 @@ def test_emulated_zstd_decoder_on_golden_and_reference_frames(pkg, emu):
     bad = bytearray(streams[1]); bad[len(bad) // 2] ^= 0x20          # damage: an error status or a checksum mismatch, never a wrong "success"
     r, out = dec(bytes(bad), n)
     assert not (r == n and out == data)
+    # a skippable frame that only LOOKS like mcmilk's size hint (0x184D2A50, 4 bytes of payload >= 9 that are not the next frame's size)
+    # is user data: the stream is walked again without hints and decodes, as with the reference (which never reads hints)
+    import struct
+    fake = struct.pack("<III", 0x184D2A50, 4, 4242)
+    assert dec(fake + streams[0] + fake + streams[1], 2 * n) == (2 * n, data + data)
 
 
 def test_emulated_zstd_decoder_frames_of_several_units(pkg, emu):
