@@ -148,7 +148,7 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
     case B200Z_P_REGIONLOG: if (v != 0 && (v < 17 || v > (int64_t)ctx->geom.frameLog)) return fail(ctx, B200Z_E_PARAM, "regionLog out of range%s");
                             ctx->geom.regionLog = (uint32_t)v; return 0;
     case B200Z_P_CHUNKLOG:  if (v < 5 || v > 8) return fail(ctx, B200Z_E_PARAM, "chunkLog out of range%s"); ctx->geom.chunkLog = (uint32_t)v; return 0;
-    case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
+    case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 3) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
     case B200Z_P_DEC_JUMP: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "decoder jump mode out of range%s"); ctx->decJump = (int)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
@@ -293,7 +293,7 @@ static int enc_batch(b200z_ctx* ctx, const uint8_t* d_src, uint64_t n, uint8_t* 
         constexpr uint32_t LITN = 0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP);
         uint16_t* spill = nullptr;
         const uint64_t nChains = nFrames * lzma2_enc_slices_per_frame(g);
-        if (ctx->lz2Mode == 0) {                                    // 32 chains per warp: every chain's whole model in global memory
+        if (ctx->lz2Mode == 3) {                                    // 32 chains per warp: every chain's whole model in global memory
             if (ctx->decScratch[5].reserve(lzma2_enc_model_bytes((uint32_t)nChains))) return fail(ctx, B200Z_E_MEMORY, "LZMA2: model allocation failed%s");
             spill = (uint16_t*)ctx->decScratch[5].p;
         } else

@@ -194,7 +194,17 @@ __device__ inline uint64_t xxh64_warp(const uint8_t* data, uint64_t len, uint8_t
             const uint64_t left = stripeBytes - t * B2Z_XXH_TILE;
             const uint32_t ns = (uint32_t)((left < B2Z_XXH_TILE ? left : B2Z_XXH_TILE) >> 5), bsh = (sh & 7u) * 8u;
             uint32_t o = ((sh & 8u) >> 3) + lane;                                          // 8-byte word index of this lane's first input
-            for (uint32_t k = 0; k < ns; k++, o += 4u) acc = xxh_round(acc, funnel64(w[o], w[o + 1u], bsh));
+            // eight stripes per pass, their sixteen shared-memory loads first: issue is in order, so a loop of one stripe waits for its own
+            // loads every time (70 cycles per stripe measured; the arithmetic chain alone is ~25)
+            uint32_t k = 0;
+            for (; k + 8u <= ns; k += 8u, o += 32u) {
+                uint64_t in[8];
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; j++) in[j] = funnel64(w[o + 4u * j], w[o + 4u * j + 1u], bsh) * P2;
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; j++) acc = xxh_rotl(acc + in[j], 31) * P1;
+            }
+            for (; k < ns; k++, o += 4u) acc = xxh_round(acc, funnel64(w[o], w[o + 1u], bsh));
         }
         __syncwarp();
         if (t + 1 < nTiles) stash((uint32_t)((t + 1) & 1u));

@@ -89,7 +89,7 @@ enum : uint32_t {
 struct EncGeom;
 size_t lzma2_enc_slot_stride(const EncGeom& g);
 uint32_t lzma2_enc_slices_per_frame(const EncGeom& g);
-size_t lzma2_enc_model_bytes(uint32_t nChains);      // mode 0 (32 chains per warp): the chains' models, passed as litSpill
+size_t lzma2_enc_model_bytes(uint32_t nChains);      // mode 3 (32 chains per warp): the chains' models, passed as litSpill
 cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint64_t* seqs, const uint32_t* nseq,
                                    uint8_t* slots, uint32_t* slotSize, uint32_t nFrames, uint16_t* litSpill, uint32_t smCount, int mode,
                                    uint32_t* status, cudaStream_t st);

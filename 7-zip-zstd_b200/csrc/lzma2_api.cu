@@ -96,7 +96,7 @@ int b200z_lzma2_decompress_device(b200z_ctx* ctx, const void* d_src, size_t srcS
     }
     if (hc.total > dstCap) return fail(ctx, B200Z_E_DSTSIZE, "destination too small%s");
     CU(cudaEventRecord(ctx->ev[3], st));
-    const int mode = ctx->lz2Mode;
+    const int mode = ctx->lz2Mode == 3 ? 0 : ctx->lz2Mode;          // (3 is an encoder-only choice)
     uint16_t* spill = nullptr;
     if (mode != 1 && hc.nBlocks > 13u * ctx->smCount / 2u) {          // worth leaving shared memory only with many blocks
         if (ctx->decScratch[5].reserve(lzma2_lit_spill_bytes(hc.nBlocks, hc.maxLcLp)) == 0) spill = (uint16_t*)ctx->decScratch[5].p;

@@ -251,6 +251,12 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
 //           the probabilities -- until the queue holds B2Z_R32_FILL decisions;
 //   phase B (lock-step): B2Z_R32_FILL times, all 32 lanes pop a decision and code it.  The probabilities of the steps to come are loaded
 //           B2Z_R32_DEPTH steps ahead (a step that adapts one of them forwards the new value).
+// STATUS: parity-green on B200 (bytes of the kernel above) but not the default: measured 1.9 s per 4 GiB (929 ms per GiB at a quarter of the
+// warps) against 0.98 s for one chain per warp.  ncu (profiles/r2_range32_ncu.txt): 17 of 32 lanes active on average, 31 warp
+// instructions per chain byte instead of 164 -- the instruction stream is 5x shorter -- but every coding step waits for the slowest of
+// 32 scattered model accesses (L1 hit rate 45 %, one lane in 70 goes to DRAM: one step in three), and with 0.9 - 3.5 warps per SM nothing
+// else is there to run meanwhile.  What it needs next: the round's distinct probabilities gathered into shared memory with all their loads
+// in flight at once, and the producer's input bytes fetched a packet ahead.  Selected with B200Z_P_LZMA2_MODEL = 3.
 // The models live in global memory, interleaved by lane (probability i of lane l at [i][l]).  Chunk rules are the single-chain kernel's:
 // a packet may be queued ahead of its coding only while the chunk cannot reach its packed limit before it (a decision emits at most one
 // byte, so `packed + queued < limit` is a proof); near the limit a lane queues one packet at a time and decides with an empty queue, which
@@ -547,7 +553,7 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
     // (9.6 KiB at lc = 2, 23 chains per SM): 1226 ms -- residency beats the ~6 extra instructions per literal bit.
     const bool glit = mode == 2 || (mode == 0 && litSpill && nChains > slotsResident);
     const uint32_t stride = (uint32_t)lzma2_enc_slot_stride(g);
-    if (mode == 0) {                                                // 32 chains per warp; litSpill holds whole models here (lzma2_enc_model_bytes)
+    if (mode == 3) {                                                // 32 chains per warp (experimental, see the kernel's header); litSpill holds whole models here (lzma2_enc_model_bytes)
         if (!litSpill) return cudaErrorInvalidValue;
         const uint32_t groups = (nChains + 31u) / 32u;
         lzma2_enc_range32_kernel<<<(groups + B2Z_R32_WARPS - 1u) / B2Z_R32_WARPS, 32 * B2Z_R32_WARPS, B2Z_R32_WARPS * B2Z_R32_QCAP * 32u * sizeof(uint16_t), st>>>(

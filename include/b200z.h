@@ -50,9 +50,9 @@ extern "C" {
                                    bit1: XXH64 content checksum per frame (ZstdHandler.cpp:275 sets it for .zst) */
 #define B200Z_P_BATCH_LOG   7   /* log2 of bytes compressed per kernel batch, default 31 (2 GiB; scratch = 9.5 x that) */
 #define B200Z_P_CHUNKLOG    9   /* stage F: log2 positions per table turn (reads of a chunk precede its writes), 5..8, default 7 */
-#define B200Z_P_LZMA2_MODEL 10  /* LZMA2 coders, where the probability models live.  Decoder: literal model in 1 = shared memory (13 warps/SM), 2 = global memory
-                                   (32 warps/SM), 0 = by block count.  Encoder (stage R): 0 = 32 chains per warp coded in lock-step, models in global memory
-                                   (default); 1 / 2 = one chain per warp with the literal model in shared / global memory (the round-1 kernel; same bytes) */
+#define B200Z_P_LZMA2_MODEL 10  /* LZMA2 coders, where the probability models live: literal model in 1 = shared memory (13 warps/SM), 2 = global memory (32 warps/SM),
+                                   0 = by block / chain count (default).  Encoder only: 3 = 32 chains per warp coded in lock-step from per-lane decision queues,
+                                   models in global memory (same bytes; experimental -- slower than one chain per warp so far, csrc/lzma2_enc.cu) */
 #define B200Z_P_LZMA2_SLICELOG 11 /* LZMA2 encoder: log2 of the state-reset slices a block's range coding is split into (0..3, default 2):
                                    independent range-coder chains per block, as fast-lzma2's encoder threads (lzma2_enc.c:1937) */
 #define B200Z_P_LZMA2_PARSE 12  /* LZMA2 encoder parse: 0 = greedy/lazy on the finder shared with the zstd path (default), 1 = price-based:

@@ -42,7 +42,7 @@ def test_geometry_model_placement_and_batches(pkg, inputs):
     data = inputs["g2_9m"]
     want = {fl: helpers.oracle_lzma2_compress(data, frameLog=fl, windowLog=fl) for fl in (17, 20)}
     for fl in (17, 20):
-        for model in (0, 1, 2):                            # 0 = 32 chains per warp in lock-step (the default), 1 / 2 = one chain per warp
+        for model in (1, 2, 3):                            # literal model in shared / global memory (one chain per warp), 3 = 32 chains per warp in lock-step
             c = pkg.Codec(0, frame_log=fl, window_log=fl, lzma2_model=model)
             assert c.lzma2_compress(data) == want[fl], (fl, model)
             c.close()
