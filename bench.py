@@ -208,8 +208,10 @@ def reference_streams(pkg, local, mib=1024, lz_mib=64):
     """Streams the REFERENCE wrote, through the engine's host-pointer decoders (what the codec module's CDecoder does with a stock archive):
     zstd level 3 from zstdmt -- ONE frame whatever the thread count (jobs become blocks of one frame, zstdmt_compress.c:1403), 2 MiB sliding
     window -- and the stock LZMA2 encoder at level 5 (`-m0=lzma2 -mx5`: Lzma2Enc.c, 16 MiB dictionary, a dictionary reset per 64 MiB block
-    when it runs block-threaded).  The engine's parallelism is over independent units: a single sliding-window frame is one chain for the
-    execute stage (entropy decoding stays parallel per block), a raw LZMA2 stream is one chain per dictionary reset."""
+    when it runs block-threaded).  The zstd frame's blocks are entropy-decoded in parallel and its matches resolved by pointer jumping
+    (stage J, csrc/zstd_dec.cu; `units_ms`: the same stream through the execution units, which form one chain on it); the same frame with a
+    content checksum -- what the reference's .zst handler writes (ZstdHandler.cpp:262-282) -- adds one XXH64 over the whole output, four
+    sequential accumulators whatever the machine; a raw LZMA2 stream is one chain per dictionary reset."""
     import numpy as np, torch
     import helpers
     rec = {}
@@ -226,9 +228,24 @@ def reference_streams(pkg, local, mib=1024, lz_mib=64):
     t = time.perf_counter(); r = c.decompress_into(hc.data_ptr(), len(comp), hb.data_ptr(), n); dt = time.perf_counter() - t
     assert r == n and torch.equal(hb, torch.from_numpy(data)), "reference-written zstd stream: round trip mismatch"
     rec["zstd_single_frame"] = {"workload": f"{mib} MiB G2 text, reference zstd level 3 ({min(cores, 64)} workers): one frame, window 2 MiB", "packed_bytes": len(comp),
-                                "dec_MBps": n / 1e6 / dt, "ms": dt * 1e3,
+                                "dec_MBps": n / 1e6 / dt, "ms": dt * 1e3, "frames_by_pointer_jumping": int(c.stat(11)),
                                 "kernel_ms": {k: c.stat(v) for k, v in dict(prepass=9, entropy=4, layout_exec_verify=5).items()}}
-    del hc, hb
+    # the same frame with a content checksum (one XXH64 chain over the output), and through the execution units on a quarter of it
+    comp_ck = helpers.ref_compress(data, level=3, checksum=1, nbWorkers=min(cores, 64))
+    hk = torch.from_numpy(np.frombuffer(comp_ck, dtype=np.uint8).copy()).pin_memory()
+    c.reset_stats()
+    t = time.perf_counter(); r = c.decompress_into(hk.data_ptr(), len(comp_ck), hb.data_ptr(), n); dt = time.perf_counter() - t
+    assert r == n and torch.equal(hb, torch.from_numpy(data)), "reference-written zstd stream with checksum: round trip mismatch"
+    rec["zstd_single_frame"]["with_content_checksum"] = {"dec_MBps": n / 1e6 / dt, "ms": dt * 1e3, "layout_exec_verify_ms": c.stat(5)}
+    q = n >> 2
+    comp_q = helpers.ref_compress(data[:q], level=3, nbWorkers=min(cores, 64))
+    hq = torch.from_numpy(np.frombuffer(comp_q, dtype=np.uint8).copy()).pin_memory()
+    cu = pkg.Codec(local, dec_jump=0)
+    t = time.perf_counter(); r = cu.decompress_into(hq.data_ptr(), len(comp_q), hb.data_ptr(), q); dtu = time.perf_counter() - t
+    assert r == q
+    cu.close()
+    rec["zstd_single_frame"]["units_ms"] = {"sample_MiB": q >> 20, "ms": dtu * 1e3, "dec_MBps": q / 1e6 / dtu}
+    del hc, hb, hk, hq
     if helpers.ref_lzma_available():
         m = lz_mib << 20
         prop, lcomp = helpers.ref_lzma2_compress(data[:m], 5, threads=min(cores, 32))
