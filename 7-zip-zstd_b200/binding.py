@@ -139,7 +139,7 @@ class Codec:
             raise B200zError(rc, self.L.b200z_last_error(self.h).decode())
 
     _PARAMS = dict(level=P_LEVEL, frame_log=P_FRAMELOG, hash_log_l=P_HASHLOG_L, hash_log_s=P_HASHLOG_S,
-                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, chunk_log=9, lzma2_model=10, lzma2_slice_log=11, lzma2_parse=12, zstd_parse=13, long=14, region_log=15, dec_jump=16)
+                   window_log=P_WINDOWLOG, flags=P_FLAGS, batch_log=P_BATCH_LOG, host_batch_log=8, chunk_log=9, lzma2_model=10, lzma2_slice_log=11, lzma2_parse=12, zstd_parse=13, long=14, region_log=15, dec_jump=16, dec_jump_seg_log=17)
 
     def set(self, name, value):
         self._check(self.L.b200z_set_param(self.h, self._PARAMS[name], int(value)))

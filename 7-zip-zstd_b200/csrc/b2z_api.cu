@@ -149,6 +149,7 @@ static int set_param_one(b200z_ctx* ctx, int param, int64_t v) {
                             ctx->geom.regionLog = (uint32_t)v; return 0;
     case B200Z_P_CHUNKLOG:  if (v < 5 || v > 8) return fail(ctx, B200Z_E_PARAM, "chunkLog out of range%s"); ctx->geom.chunkLog = (uint32_t)v; return 0;
     case B200Z_P_LZMA2_MODEL: if (v < 0 || v > 3) return fail(ctx, B200Z_E_PARAM, "lzma2 model placement out of range%s"); ctx->lz2Mode = (int)v; return 0;
+    case B200Z_P_DEC_JUMP_SEGLOG: if (v < 16 || v > B2Z_DEC_JUMP_SEGLOG) return fail(ctx, B200Z_E_PARAM, "decoder jump segment log out of range%s"); ctx->decJumpSegLog = (uint32_t)v; return 0;
     case B200Z_P_DEC_JUMP: if (v < 0 || v > 2) return fail(ctx, B200Z_E_PARAM, "decoder jump mode out of range%s"); ctx->decJump = (int)v; return 0;
     case B200Z_P_HOST_BATCH_LOG: if (v < 22 || v > 36) return fail(ctx, B200Z_E_PARAM, "hostBatchLog out of range%s"); ctx->hostBatchLog = (uint32_t)v; return 0;
     }
@@ -170,6 +171,7 @@ int b200z_get_param(b200z_ctx* ctx, int param, int64_t* v) {
     case B200Z_P_BATCH_LOG: *v = ctx->batchLog; return 0;
     case B200Z_P_HOST_BATCH_LOG: *v = ctx->hostBatchLog; return 0;
     case B200Z_P_DEC_JUMP: *v = ctx->decJump; return 0;
+    case B200Z_P_DEC_JUMP_SEGLOG: *v = ctx->decJumpSegLog; return 0;
     case B200Z_P_LZMA2_MODEL: *v = ctx->lz2Mode; return 0;
     case B200Z_P_CHUNKLOG: *v = ctx->geom.chunkLog; return 0;
     case B200Z_P_LONG: *v = ctx->geom.ldmLog ? ctx->geom.windowLog : 0; return 0;

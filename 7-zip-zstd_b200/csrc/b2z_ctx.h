@@ -37,6 +37,7 @@ struct b200z_ctx {
     uint32_t batchLog = 31;           // bytes per kernel batch of the device-pointer entry points: 2 GiB keeps the scratch (9.5 bytes per batch byte: candidate
                                       // words 4, choices 1, sequences 2, literals 1, block slots 1.5) near 19 GiB whatever the input size (1 GiB batches cost 4 % of speed)
     uint32_t smCount = 148;
+    uint32_t decJumpSegLog = B2Z_DEC_JUMP_SEGLOG;   // stage J: bytes of output resolved per pass (B200Z_P_DEC_JUMP_SEGLOG; tests use small segments)
     int decJump = 1;                  // Zstandard decoder, stage J (frames resolved by pointer jumping): 0 never, 1 frames whose units form a chain, 2 every frame
     int lz2Mode = 0;                  // LZMA2 decoder literal-model placement: 0 auto, 1 shared memory, 2 global memory
     Arena tables, seqs, nseq, lits, nlit, slots, slotSize, blockOff, frameOff, scalars, dIn, dOut, cks, ready, batchStage, batchOff, batchSize, cand, choice, crcOff, crcLen, crcOut;

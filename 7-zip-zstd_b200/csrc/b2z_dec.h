@@ -54,7 +54,9 @@ struct DecBlock {
 #define B2Z_DEC_UNIT_BLOCKS 4u       // stage D3: consecutive blocks of a frame executed by one warp (512 KiB of output when the blocks are full)
 
 #define B2Z_DEC_JUMP_MIN_UNITS 8u    // stage J, automatic mode: frames of at least this many units ...
-#define B2Z_DEC_JUMP_FINAL 0x80000000u   // stage J: pointer bit "the position pointed at holds a literal byte" (batches of < 2 GiB of output)
+#define B2Z_DEC_JUMP_FINAL 0x80000000u   // stage J: pointer bit "the byte pointed at is final" (a literal of the segment, or any byte before the segment)
+#define B2Z_DEC_JUMP_BIAS  0x40000000u   // stage J: pointer = position - segment start + this (sources reach at most a window, <= 2^30 - 16, back)
+#define B2Z_DEC_JUMP_SEGLOG 30u          // stage J: the batch's output is resolved in segments of this many bytes, in order
 #define B2Z_DEC_JUMP_ROUNDS 32u      // pointer doubling: a chain of n links is resolved after ceil(log2 n) rounds, n < 2^31
 
 struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; uint32_t maxFrameBlocks, nJump; };
@@ -72,9 +74,9 @@ size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks);
 void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap,
                             DecCounts* counts, uint64_t* total, uint32_t jumpMode, cudaStream_t st);
 // stage J (frames with DecFrame::jump): literals and one pointer per output byte (J1), pointer doubling (J2), byte gather (J3).
-// ptr: one word per output byte of the batch; flags: B2Z_DEC_JUMP_ROUNDS + 1 words
+// ptr: one word per output byte of a segment (min(total, 2^segLog) + 16); flags: B2Z_DEC_JUMP_ROUNDS + 1 words
 void launch_zstd_dec_jump(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
-                          uint8_t* dst, uint64_t total, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st);
+                          uint8_t* dst, uint64_t total, uint32_t segLog /* <= B2Z_DEC_JUMP_SEGLOG */, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st);
 // stage D3: one warp per unit of B2Z_DEC_UNIT_BLOCKS consecutive blocks of a frame, units taken in order; a match that reaches
 // behind its unit waits for the unit that writes those bytes.  unitState: [0] ticket, [1 + u] done flag of unit u -- zeroed here.
 size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks);

@@ -770,19 +770,15 @@ __global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, 
     if (frames[f].contentSize != ~0ull && frames[f].contentSize != total) st |= B2Z_DERR_CORRUPT;
     frames[f].regen = total;
     const uint32_t units = (nb + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
-    frames[f].jump = (uint32_t)(!st && total && total < 0x7FFFFFFFull &&
+    frames[f].jump = (uint32_t)(!st && total &&
                                 (jumpMode == 2u || (jumpMode == 1u && units >= B2Z_DEC_JUMP_MIN_UNITS && chained * 4u >= (units - 1u) * 3u)));
     if (st) atomicOr(&counts->status, st);
 }
 __global__ void zstd_dec_frame_offsets_kernel(DecFrame* frames, uint32_t nFrames, uint64_t dstCap, DecCounts* counts, uint64_t* total) {
     if (threadIdx.x || blockIdx.x) return;
     uint64_t o = 0; uint32_t u = 0, nj = 0;
-    for (uint32_t f = 0; f < nFrames; f++) o += frames[f].regen;
-    const bool jumpOk = o < 0x7FFFFFFFull;                                    // stage J's pointers are 31-bit offsets into the batch's output
-    o = 0;
     for (uint32_t f = 0; f < nFrames; f++) {
         frames[f].dstOff = o; o += frames[f].regen;
-        if (!jumpOk) frames[f].jump = 0;
         nj += frames[f].jump;
         frames[f].pad = u; if (!frames[f].jump) u += (frames[f].nBlocks + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
     }
@@ -987,26 +983,33 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
 // points at its source byte.  J1 writes the literal bytes and one pointer per output byte (one warp per block, all blocks at once);
 // J2 doubles the pointers (ptr[i] = ptr[ptr[i]], in place: any value a neighbour holds meanwhile is an ancestor, so stale reads only
 // cost a round) until every pointer names a literal -- ceil(log2(longest chain)) rounds of streaming passes; J3 fetches the bytes.
-// A pointer is the byte's offset in the batch's output (batches of < 2 GiB), bit 31 = "names a literal byte".
+// The batch's output is taken in segments of at most 1 GiB, in order, so that a pointer fits 31 bits whatever the frame's size: a pointer is
+// (position - segment start + 2^30) -- a source lies at most a window (<= 2^30 - 16) before its byte -- and bit 31 says "the byte there is
+// final": a literal of this segment, or anything before the segment.
 // Role in the reference: ZSTD_execSequence over the whole frame (zstd_decompress_block.c:1001-1100), which is strictly sequential.
 __global__ void __launch_bounds__(128)
 zstd_dec_jump_build_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, const DecBlock* __restrict__ blocks, uint32_t nBlocks,
                            const uint8_t* __restrict__ lits, const uint64_t* __restrict__ seqs, uint8_t* __restrict__ dst, DecCounts* counts,
-                           uint32_t* __restrict__ ptr) {
+                           uint32_t* __restrict__ ptr, uint64_t segS, uint64_t segE) {
     if (counts->status) return;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t nWarps = (gridDim.x * blockDim.x) >> 5;
+    // pointer of the byte at batch offset P (inside the segment): its own place if it is a literal, else its source Q; a source before the
+    // segment is final already (earlier segments are complete)
+    auto put = [&](uint64_t P, uint64_t Q, bool literal) {
+        if (P < segS || P >= segE) return;
+        ptr[P - segS] = (uint32_t)(Q + B2Z_DEC_JUMP_BIAS - segS) | ((literal || Q < segS) ? B2Z_DEC_JUMP_FINAL : 0u);
+    };
     for (uint32_t bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; bi < nBlocks; bi += nWarps) {
         const DecBlock blk = blocks[bi];
         const DecFrame* fp = frames + blk.frame;
         if (!fp->jump) continue;
-        const uint64_t windowSize = fp->windowSize;
-        const uint32_t fbase = (uint32_t)fp->dstOff;                 // batch offset of the frame's first byte (< 2^31: stage D2)
-        uint8_t* out = dst + fbase;
-        uint32_t* P = ptr + fbase;
-        uint32_t o = (uint32_t)blk.outRel, err = 0;                  // frame bytes produced before the next sequence (jump frames are < 2 GiB)
-        if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) { out[o + i] = src[blk.srcOff + i]; P[o + i] = (fbase + o + i) | B2Z_DEC_JUMP_FINAL; } continue; }
-        if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) { out[o + i] = v; P[o + i] = (fbase + o + i) | B2Z_DEC_JUMP_FINAL; } continue; }
+        const uint64_t windowSize = fp->windowSize, fbase = fp->dstOff;          // batch offset of the frame's first byte
+        if (fbase + blk.outRel >= segE || fbase + blk.outRel + blk.regen <= segS) continue;     // the block writes nothing into this segment
+        uint64_t o = blk.outRel;                                             // frame bytes produced before the next sequence
+        uint32_t err = 0;
+        if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) { const uint64_t P = fbase + o + i; if (P >= segS && P < segE) dst[P] = src[blk.srcOff + i]; put(P, P, true); } continue; }
+        if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) { const uint64_t P = fbase + o + i; if (P >= segS && P < segE) dst[P] = v; put(P, P, true); } continue; }
         const uint8_t* __restrict__ lit = lits + (size_t)bi * 131072u;
         const uint64_t* __restrict__ sq = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
         uint32_t lp = 0, rep0 = blk.repInit[0], rep1 = blk.repInit[1], rep2 = blk.repInit[2];
@@ -1044,13 +1047,14 @@ zstd_dec_jump_build_kernel(const uint8_t* __restrict__ src, const DecFrame* __re
             uint32_t total, litTotal;
             const uint32_t excl = warp_excl_scan(ll + ml, lane, &total);
             const uint32_t litExcl = warp_excl_scan(ll, lane, &litTotal);
-            const uint32_t myDst = o + excl + ll;                                        // frame-relative start of the lane's match
+            const uint64_t myDst = o + excl + ll;                                        // frame-relative start of the lane's match
             const bool bad = lane < cnt && (myOff == 0 || myOff > myDst || myOff > windowSize);
             if (__any_sync(B2Z_FULL, bad)) { err = B2Z_DERR_CORRUPT; break; }
             // lane = byte of the batch, B2Z_DEC_ROUNDS rounds of 32 taken together (their literal loads are issued before the first store);
             // byte t belongs to the sequence k with excl_k <= t < excl_k + ll_k + ml_k (binary search over the lanes' prefix sums)
+            if (fbase + o < segE && fbase + o + total > segS)                            // (warp-uniform) the pass touches the segment
             for (uint32_t t0 = 0; t0 < total; t0 += 32u * B2Z_DEC_ROUNDS) {
-                uint8_t v[B2Z_DEC_ROUNDS]; uint32_t w[B2Z_DEC_ROUNDS];
+                uint8_t v[B2Z_DEC_ROUNDS]; uint64_t w[B2Z_DEC_ROUNDS]; bool isLit[B2Z_DEC_ROUNDS];
 #pragma unroll
                 for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) {
                     const uint32_t t = t0 + r * 32u + lane;
@@ -1059,9 +1063,9 @@ zstd_dec_jump_build_kernel(const uint8_t* __restrict__ src, const DecFrame* __re
                     for (uint32_t st = 16; st; st >>= 1) { const uint32_t x = __shfl_sync(B2Z_FULL, excl, (k + st) & 31u); if (k + st < 32u && x <= t) k += st; }
                     const uint32_t e = __shfl_sync(B2Z_FULL, excl, k), l = __shfl_sync(B2Z_FULL, ll, k), le = __shfl_sync(B2Z_FULL, litExcl, k), of = __shfl_sync(B2Z_FULL, myOff, k);
                     const uint32_t rr = t - e;
-                    v[r] = 0; w[r] = 0;
+                    v[r] = 0; w[r] = 0; isLit[r] = false;
                     if (t < total) {
-                        if (rr < l) { v[r] = lit[lp + le + rr]; w[r] = (fbase + o + t) | B2Z_DEC_JUMP_FINAL; }
+                        if (rr < l) { v[r] = lit[lp + le + rr]; w[r] = fbase + o + t; isLit[r] = true; }
                         else {
                             // a match byte points at its source; inside an overlapping match (offset < length) at the byte of the period
                             // before the match, not at the match's own earlier byte: no chain inside one match
@@ -1073,16 +1077,16 @@ zstd_dec_jump_build_kernel(const uint8_t* __restrict__ src, const DecFrame* __re
 #pragma unroll
                 for (uint32_t r = 0; r < B2Z_DEC_ROUNDS; r++) {
                     const uint32_t t = t0 + r * 32u + lane;
-                    if (t < total) { P[o + t] = w[r]; if (w[r] & B2Z_DEC_JUMP_FINAL) out[o + t] = v[r]; }
+                    if (t < total) { const uint64_t P = fbase + o + t; put(P, w[r], isLit[r]); if (isLit[r] && P >= segS && P < segE) dst[P] = v[r]; }
                 }
             }
             o += total; lp += litTotal;
         }
         if (!err) {
             const uint32_t tail = blk.litSize - lp;
-            for (uint32_t i = lane; i < tail; i += 32) { out[o + i] = lit[lp + i]; P[o + i] = (fbase + o + i) | B2Z_DEC_JUMP_FINAL; }
+            for (uint32_t i = lane; i < tail; i += 32) { const uint64_t P = fbase + o + i; if (P >= segS && P < segE) dst[P] = lit[lp + i]; put(P, P, true); }
             o += tail;
-            if (o != (uint32_t)blk.outRel + blk.regen) err = B2Z_DERR_CORRUPT;
+            if (o != blk.outRel + blk.regen) err = B2Z_DERR_CORRUPT;
         }
         if (err && lane == 0) atomicOr(&counts->status, err);
     }
@@ -1099,15 +1103,15 @@ __device__ __forceinline__ uint32_t dec_frame_of(const DecFrame* __restrict__ fr
 // that does not yet name a literal; a round whose predecessor left none returns at once (all rounds are launched up front).
 // J3 (LAST = true): dst[i] = dst[ptr[i]] for the match bytes.
 template <bool LAST> __global__ void __launch_bounds__(256)
-zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames, uint64_t total, uint32_t* __restrict__ ptr, uint32_t* flags,
+zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames, uint64_t segS, uint64_t segE, uint32_t* __restrict__ ptr, uint32_t* flags,
                            uint32_t round, uint8_t* dst, DecCounts* counts) {
     if (counts->status) return;
     if (!LAST && round && !flags[round - 1u]) return;
-    const uint64_t nGroups = (total + 3u) >> 2;
+    const uint64_t n = segE - segS, nGroups = (n + 3u) >> 2;
     bool pending = false, broken = false;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i0 = g << 2;
-        uint32_t f = nFrames > 1u ? dec_frame_of(frames, nFrames, i0) : 0u;
+        uint32_t f = nFrames > 1u ? dec_frame_of(frames, nFrames, segS + i0) : 0u;
         uint64_t fEnd = frames[f].dstOff + frames[f].regen; bool fj = frames[f].jump != 0u;
         uint4 q4 = *reinterpret_cast<const uint4*>(ptr + i0);
         uint32_t q[4] = { q4.x, q4.y, q4.z, q4.w }; bool take[4]; uint32_t r[4];
@@ -1115,14 +1119,14 @@ zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames
         for (uint32_t e = 0; e < 4; e++) {
             const uint64_t i = i0 + e;
             take[e] = false;
-            if (i < total) {
-                while (i >= fEnd) { f++; fEnd = frames[f].dstOff + frames[f].regen; fj = frames[f].jump != 0u; }
-                take[e] = fj && (LAST ? q[e] != ((uint32_t)i | B2Z_DEC_JUMP_FINAL) : !(q[e] & B2Z_DEC_JUMP_FINAL));
+            if (i < n) {
+                while (segS + i >= fEnd) { f++; fEnd = frames[f].dstOff + frames[f].regen; fj = frames[f].jump != 0u; }
+                take[e] = fj && (LAST ? q[e] != (((uint32_t)i + B2Z_DEC_JUMP_BIAS) | B2Z_DEC_JUMP_FINAL) : !(q[e] & B2Z_DEC_JUMP_FINAL));
             }
         }
         if (!LAST) {
 #pragma unroll
-            for (uint32_t e = 0; e < 4; e++) r[e] = take[e] ? __ldcg(ptr + q[e]) : q[e];
+            for (uint32_t e = 0; e < 4; e++) r[e] = take[e] ? __ldcg(ptr + (q[e] - B2Z_DEC_JUMP_BIAS)) : q[e];   // not final: the source lies in this segment
             if (take[0] | take[1] | take[2] | take[3]) {
 #pragma unroll
                 for (uint32_t e = 0; e < 4; e++) pending |= take[e] && !(r[e] & B2Z_DEC_JUMP_FINAL);
@@ -1130,9 +1134,12 @@ zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames
             }
         } else {
 #pragma unroll
-            for (uint32_t e = 0; e < 4; e++) { broken |= take[e] && !(q[e] & B2Z_DEC_JUMP_FINAL); r[e] = take[e] ? dst[q[e] & ~B2Z_DEC_JUMP_FINAL] : 0u; }
+            for (uint32_t e = 0; e < 4; e++) {                                               // the source's batch offset: segS + pointer - bias (>= 0: a byte of the batch)
+                broken |= take[e] && !(q[e] & B2Z_DEC_JUMP_FINAL);
+                r[e] = take[e] ? dst[segS + (q[e] & ~B2Z_DEC_JUMP_FINAL) - B2Z_DEC_JUMP_BIAS] : 0u;
+            }
 #pragma unroll
-            for (uint32_t e = 0; e < 4; e++) if (take[e]) dst[i0 + e] = (uint8_t)r[e];
+            for (uint32_t e = 0; e < 4; e++) if (take[e]) dst[segS + i0 + e] = (uint8_t)r[e];
         }
     }
     if (!LAST && pending) flags[round] = 1u;
@@ -1201,15 +1208,19 @@ void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks
     zstd_dec_frame_offsets_kernel<<<1, 32, 0, st>>>(frames, nFrames, dstCap, counts, total);
 }
 void launch_zstd_dec_jump(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
-                          uint8_t* dst, uint64_t total, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st) {
+                          uint8_t* dst, uint64_t total, uint32_t segLog, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st) {
     if (!nFrames || !nBlocks || !total) return;
-    cudaMemsetAsync(flags, 0, (B2Z_DEC_JUMP_ROUNDS + 1u) * 4u, st);
-    { const uint32_t want = (nBlocks + 3u) / 4u, grid = want < 148u * 16u ? want : 148u * 16u;
-      zstd_dec_jump_build_kernel<<<grid, 128, 0, st>>>(src, frames, blocks, nBlocks, lits, seqs, dst, counts, ptr); }
-    const uint64_t groups = (total + 3u) >> 2;
-    const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 148u * 16u ? (groups + 255u) / 256u : 148u * 16u);
-    for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++) zstd_dec_jump_round_kernel<false><<<grid, 256, 0, st>>>(frames, nFrames, total, ptr, flags, r, dst, counts);
-    zstd_dec_jump_round_kernel<true><<<grid, 256, 0, st>>>(frames, nFrames, total, ptr, flags, 0, dst, counts);
+    const uint64_t seg = 1ull << segLog;
+    for (uint64_t S = 0; S < total; S += seg) {                        // segments in order: what lies before a segment is complete
+        const uint64_t E = S + seg < total ? S + seg : total;
+        cudaMemsetAsync(flags, 0, (B2Z_DEC_JUMP_ROUNDS + 1u) * 4u, st);
+        { const uint32_t want = (nBlocks + 3u) / 4u, grid = want < 148u * 16u ? want : 148u * 16u;
+          zstd_dec_jump_build_kernel<<<grid, 128, 0, st>>>(src, frames, blocks, nBlocks, lits, seqs, dst, counts, ptr, S, E); }
+        const uint64_t groups = (E - S + 3u) >> 2;
+        const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 148u * 16u ? (groups + 255u) / 256u : 148u * 16u);
+        for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++) zstd_dec_jump_round_kernel<false><<<grid, 256, 0, st>>>(frames, nFrames, S, E, ptr, flags, r, dst, counts);
+        zstd_dec_jump_round_kernel<true><<<grid, 256, 0, st>>>(frames, nFrames, S, E, ptr, flags, 0, dst, counts);
+    }
 }
 size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks) { return ((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u) * 4u; }
 void launch_zstd_dec_exec(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,

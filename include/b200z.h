@@ -71,6 +71,7 @@ extern "C" {
 #define B200Z_P_DEC_JUMP    16  /* Zstandard decoder: which frames are resolved by pointer jumping (stage J: one pointer per output byte, doubled until it names a
                                    literal) instead of by execution units: 0 = none, 1 = frames of >= 8 units (4 MiB) whose units copy from one another -- the single
                                    sliding-window frame the reference's encoder writes (default), 2 = every frame (tests) */
+#define B200Z_P_DEC_JUMP_SEGLOG 17 /* stage J resolves the output in segments of 2^this bytes, in order (16..30, default 30: 4 GiB of pointers at most, frames of any size) */
 #define B200Z_P_HOST_BATCH_LOG 8 /* log2 of bytes per H2D|kernels|D2H pipeline batch of the *_host calls, default 30 (the decoder takes twice that) */
 
 /* statistics (b200z_get_stat): device milliseconds accumulated since the last b200z_reset_stats,

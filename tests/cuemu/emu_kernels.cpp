@@ -207,6 +207,8 @@ int64_t emu_zstd_enc_assemble(const uint8_t* src, uint64_t srcSize, uint32_t fra
 
 // Zstandard decoder: the kernels in the order and shapes of dec_impl (zstd_dec_api.cu) / the launch_zstd_dec_* functions.
 // Returns the decoded size or -(status bits).
+static uint32_t g_emu_jump_seglog = B2Z_DEC_JUMP_SEGLOG;                                   // stage J segment size (tests shrink it)
+void emu_set_jump_seglog(uint32_t v) { g_emu_jump_seglog = v; }
 static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap, uint32_t jumpMode, uint32_t* nJumpOut);
 int64_t emu_zstd_decode(const uint8_t* src, uint64_t srcSize, uint8_t* dst, uint64_t dstCap) { return emu_zstd_decode_mode(src, srcSize, dst, dstCap, 1u, nullptr); }
 // jumpMode as B200Z_P_DEC_JUMP; *nJump = frames that went through stage J
@@ -254,13 +256,18 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_frame_offsets_kernel(frames.data(), nFrames, dstCap, &counts, &total); });
     if (nJumpOut) *nJumpOut = counts.nJump;
     if (maybeJump && !counts.status && counts.nJump && nBlocks && total) {             // launch_zstd_dec_jump
-        std::vector<uint32_t> ptr((size_t)total + 16, 0xCDCDCDCDu), flags(B2Z_DEC_JUMP_ROUNDS + 1u, 0u);
-        cuemu::launch(dim3((nBlocks + 3u) / 4u < 3u ? (nBlocks + 3u) / 4u : 3u), dim3(128), 0, [&] { zstd_dec_jump_build_kernel(src, frames.data(), blocks.data(), nBlocks, lits.data(), seqs.data(), dst, &counts, ptr.data()); });
-        const uint64_t groups = (total + 3u) >> 2;
-        const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 2u ? (groups + 255u) / 256u : 2u);
-        for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++)
-            cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<false>(frames.data(), nFrames, total, ptr.data(), flags.data(), r, dst, &counts); });
-        cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<true>(frames.data(), nFrames, total, ptr.data(), flags.data(), 0, dst, &counts); });
+        const uint64_t seg = 1ull << g_emu_jump_seglog;
+        std::vector<uint32_t> ptr((size_t)(total < seg ? total : seg) + 16, 0xCDCDCDCDu), flags(B2Z_DEC_JUMP_ROUNDS + 1u, 0u);
+        for (uint64_t S = 0; S < total; S += seg) {
+            const uint64_t E = S + seg < total ? S + seg : total;
+            std::fill(flags.begin(), flags.end(), 0u);
+            cuemu::launch(dim3((nBlocks + 3u) / 4u < 3u ? (nBlocks + 3u) / 4u : 3u), dim3(128), 0, [&] { zstd_dec_jump_build_kernel(src, frames.data(), blocks.data(), nBlocks, lits.data(), seqs.data(), dst, &counts, ptr.data(), S, E); });
+            const uint64_t groups = (E - S + 3u) >> 2;
+            const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 2u ? (groups + 255u) / 256u : 2u);
+            for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++)
+                cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<false>(frames.data(), nFrames, S, E, ptr.data(), flags.data(), r, dst, &counts); });
+            cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<true>(frames.data(), nFrames, S, E, ptr.data(), flags.data(), 0, dst, &counts); });
+        }
     }
     if (nFrames) {
         std::vector<uint32_t> unitState((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u, 0u);

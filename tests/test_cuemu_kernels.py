@@ -364,6 +364,8 @@ def test_emulated_zstd_decoder_stage_j_pointer_jumping(pkg, emu):
         r = emu.emu_zstd_decode_jump(src.ctypes.data, len(comp), dst.ctypes.data, n, mode, ctypes.byref(nj))
         return r, dst[:max(r, 0)].tobytes(), nj.value
     golden = os.path.join(HERE, "golden")
+    emu.emu_set_jump_seglog.argtypes = [ctypes.c_uint32]; emu.emu_set_jump_seglog.restype = None
+    emu.emu_set_jump_seglog(30)
     for idx_name in ("frames.json", "regr.json"):
         for name, meta in json.load(open(os.path.join(golden, idx_name))).items():
             if not name.endswith(".zst"):
@@ -381,6 +383,14 @@ def test_emulated_zstd_decoder_stage_j_pointer_jumping(pkg, emu):
     bad = bytearray(streams[1]); bad[len(bad) // 2] ^= 0x20
     r, out, nj = dec(bytes(bad), n, 2)
     assert not (r == n and out == data)
+    # segments: the output resolved in pieces of 64 KiB / 128 KiB, in order (what lets a frame of any size through 31-bit pointers): blocks
+    # straddle the cuts, sources lie segments back
+    for seglog in (16, 17):
+        emu.emu_set_jump_seglog(seglog)
+        for k, comp in enumerate(streams):
+            r, out, nj = dec(comp, n, 2)
+            assert (r, out) == (n, data) and nj > 0, (seglog, k)
+    emu.emu_set_jump_seglog(30)
     # automatic mode: 5 MiB, one frame
     big = pkg.corpus.g2(5 << 20).tobytes() + b"q" * 70_000; nb = len(big)
     ours = H.oracle_compress(big, frameLog=23, windowLog=23, regionLog=19, ldmLog=14)

@@ -188,7 +188,28 @@ def test_stage_j_pointer_jumping(pkg, inputs):
     multi = ref + off.compress(d) + ref
     auto.reset_stats()
     assert auto.decompress(multi, max_size=2 * len(big) + len(d)) == big + d + big and auto.stat(S_JUMP) == 2
+    seg = pkg.Codec(0, dec_jump_seg_log=20)                             # the output resolved in 1 MiB segments, in order: blocks straddle the cuts
+    assert seg.decompress(multi, max_size=2 * len(big) + len(d)) == big + d + big and seg.stat(S_JUMP) == 2
+    seg.close()
     small = pkg.Codec(0, host_batch_log=24)                             # 16 MiB batches: every reference frame is a batch of its own
     assert small.decompress(multi, max_size=2 * len(big) + len(d)) == big + d + big and small.stat(S_JUMP) == 2
     for c in (off, auto, force, small):
         c.close()
+
+
+@pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref not built")
+def test_stage_j_frame_beyond_2gib(pkg):
+    """one reference-written frame of 2.5 GiB (zstdmt, level 1): stage J takes it in segments of 1 GiB -- pointers stay 31 bits whatever
+    the frame's size -- and the output equals the input (compared on the device)"""
+    import torch
+    n = (5 << 29) + 12345
+    data = pkg.corpus.g2(n)
+    comp = helpers.ref_compress(data, 1, 0, nbWorkers=min(os.cpu_count() or 1, 64))
+    c = pkg.Codec(0)
+    src = torch.frombuffer(bytearray(comp + bytes(64)), dtype=torch.uint8).cuda()
+    back = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    got = c.decompress_device(src.data_ptr(), len(comp), back.data_ptr(), n)
+    assert got == n and c.stat(11) == 1
+    want = torch.from_numpy(data).cuda()
+    assert bool(torch.equal(back[:n], want))
+    c.close()
