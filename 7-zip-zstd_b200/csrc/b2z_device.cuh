@@ -163,7 +163,8 @@ __device__ inline uint64_t xxh64_device_unaligned(const uint8_t* data, uint64_t 
 // registers while the four lanes work on the current one from shared memory.  tileMem: 2 * B2Z_XXH_TILE_BYTES, 16-byte aligned.
 #define B2Z_XXH_TILE 4096u
 #define B2Z_XXH_TILE_BYTES (B2Z_XXH_TILE + 32u)
-__device__ inline uint64_t xxh64_warp(const uint8_t* data, uint64_t len, uint8_t* tileMem, uint32_t lane) {
+#define B2Z_XXH_WS_BYTES (2u * B2Z_XXH_TILE_BYTES + B2Z_XXH_TILE)       /* two raw tiles + the tile's inputs times P2 */
+__device__ inline uint64_t xxh64_warp(const uint8_t* data, uint64_t len, uint8_t* tileMem /* B2Z_XXH_WS_BYTES, 16-byte aligned */, uint32_t lane) {
     const uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 15u);
     const uint4* __restrict__ aw = reinterpret_cast<const uint4*>(data - sh);            // aligned words; word j holds data bytes [16 j - sh, 16 j - sh + 16)
@@ -172,6 +173,7 @@ __device__ inline uint64_t xxh64_warp(const uint8_t* data, uint64_t len, uint8_t
     constexpr uint32_t WPT = B2Z_XXH_TILE / 16u + 1u, PER = (WPT + 31u) / 32u;             // words per tile (one more for the shift), per lane
     uint64_t acc = lane == 0 ? P1 + P2 : (lane == 1 ? P2 : (lane == 2 ? 0ull : 0ull - P1));
     const uint64_t nTiles = (stripeBytes + B2Z_XXH_TILE - 1u) / B2Z_XXH_TILE;
+    uint64_t* const pre = reinterpret_cast<uint64_t*>(tileMem + 2u * B2Z_XXH_TILE_BYTES);  // pre[m] = (m-th 8-byte input of the tile) * P2
     uint4 r[PER];
     auto fetch = [&](uint64_t t) {
 #pragma unroll
@@ -188,23 +190,25 @@ __device__ inline uint64_t xxh64_warp(const uint8_t* data, uint64_t len, uint8_t
     if (nTiles) { fetch(0); stash(0); }
     __syncwarp();
     for (uint64_t t = 0; t < nTiles; t++) {
-        if (t + 1 < nTiles) fetch(t + 1);                                                  // in flight while lanes 0-3 hash tile t
-        if (lane < 4u) {
+        if (t + 1 < nTiles) fetch(t + 1);                                                  // in flight while this tile is hashed
+        const uint64_t left = stripeBytes - t * B2Z_XXH_TILE;
+        const uint32_t ns = (uint32_t)((left < B2Z_XXH_TILE ? left : B2Z_XXH_TILE) >> 5);
+        {   // every lane: the alignment shift and the multiplication by P2, which do not depend on the accumulators
             const uint64_t* w = reinterpret_cast<const uint64_t*>(tileMem + (uint32_t)(t & 1u) * B2Z_XXH_TILE_BYTES);
-            const uint64_t left = stripeBytes - t * B2Z_XXH_TILE;
-            const uint32_t ns = (uint32_t)((left < B2Z_XXH_TILE ? left : B2Z_XXH_TILE) >> 5), bsh = (sh & 7u) * 8u;
-            uint32_t o = ((sh & 8u) >> 3) + lane;                                          // 8-byte word index of this lane's first input
-            // eight stripes per pass, their sixteen shared-memory loads first: issue is in order, so a loop of one stripe waits for its own
-            // loads every time (70 cycles per stripe measured; the arithmetic chain alone is ~25)
-            uint32_t k = 0;
-            for (; k + 8u <= ns; k += 8u, o += 32u) {
+            const uint32_t bsh = (sh & 7u) * 8u, o0 = (sh & 8u) >> 3;
+            for (uint32_t m = lane; m < ns * 4u; m += 32u) pre[m] = funnel64(w[o0 + m], w[o0 + m + 1u], bsh) * P2;
+        }
+        __syncwarp();
+        if (lane < 4u) {                                                                   // the four sequential chains: add, rotate, multiply
+            uint32_t k = 0, o = lane;
+            for (; k + 8u <= ns; k += 8u, o += 32u) {                                      // eight stripes per pass, their loads first (issue is in order)
                 uint64_t in[8];
 #pragma unroll
-                for (uint32_t j = 0; j < 8u; j++) in[j] = funnel64(w[o + 4u * j], w[o + 4u * j + 1u], bsh) * P2;
+                for (uint32_t j = 0; j < 8u; j++) in[j] = pre[o + 4u * j];
 #pragma unroll
                 for (uint32_t j = 0; j < 8u; j++) acc = xxh_rotl(acc + in[j], 31) * P1;
             }
-            for (; k < ns; k++, o += 4u) acc = xxh_round(acc, funnel64(w[o], w[o + 1u], bsh));
+            for (; k < ns; k++, o += 4u) acc = xxh_rotl(acc + pre[o], 31) * P1;
         }
         __syncwarp();
         if (t + 1 < nTiles) stash((uint32_t)((t + 1) & 1u));

@@ -1148,10 +1148,10 @@ zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames
 
 // ---------------------------------------------------------------- checksum verification
 // one warp per frame (xxh64_warp: lanes 0-3 hash, the warp streams the frame through shared memory)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restrict__ frames, uint32_t nFrames,
                        const uint8_t* __restrict__ dst, DecCounts* counts) {
-    __shared__ __align__(16) uint8_t tiles[4][2 * B2Z_XXH_TILE_BYTES];
+    __shared__ __align__(16) uint8_t tiles[2][B2Z_XXH_WS_BYTES];
     const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
     const uint32_t f = blockIdx.x * (blockDim.x >> 5) + wic;
     if (f >= nFrames || counts->status) return;
@@ -1166,7 +1166,7 @@ zstd_dec_verify_kernel(const uint8_t* __restrict__ src, const DecFrame* __restri
 // ---------------------------------------------------------------- launchers
 #ifndef B2Z_CUEMU
 void launch_zstd_dec_verify(const uint8_t* src, const DecFrame* frames, uint32_t nFrames, const uint8_t* dst, DecCounts* counts, cudaStream_t st) {
-    if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 3) / 4, 128, 0, st>>>(src, frames, nFrames, dst, counts);
+    if (nFrames) zstd_dec_verify_kernel<<<(nFrames + 1) / 2, 64, 0, st>>>(src, frames, nFrames, dst, counts);
 }
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, bool useHints, cudaStream_t st) {
     zstd_dec_find_frames_kernel<<<1, 32, 0, st>>>(src, srcSize, frames, frameCap, counts, useHints ? 1u : 0u);

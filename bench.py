@@ -358,6 +358,35 @@ def many_files_7z(pkg, codec, n_files=100_000, file_bytes=65536, cpu_files=4000,
     return rec
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the cores of the NUMA node its GPU hangs off, BEFORE any pinned buffer is allocated (first touch then places the
+    staging memory next to the GPU's PCIe root: 8 ranks x 12 GB of H2D + D2H per step otherwise cross the socket link for half the GPUs).
+    Best effort: returns the node or None and never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                               # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     a = parse_args()
     lz = a.codec == "lzma2"
@@ -404,6 +433,7 @@ def main():
                           "higher_is_better": True, "scaling": "strong", "dtype": "u8", "data": "synthetic", "config": {"workload": workload.replace(" per GPU", " in total")}, "e2e": res}))
         return
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -536,7 +566,7 @@ def main():
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "global_uncompressed_bytes_per_step": world * unit_bytes, "frame_log": codec.get("frame_log"),
                    "parallelism": f"{world} independent shard(s), no collective", **({"lzma2_parse": a.lzma2_parse} if lz else {"level": a.level}), "l2": f"inputs ({a.size_mib} MiB per GPU) larger than L2; no flush needed",
-                   "host_batch_log": codec.get("host_batch_log"),
+                   "host_batch_log": codec.get("host_batch_log"), "rank0_numa_node": numa_node,
                    "ratio": ratio, "enc_MBps": units_mb / t_enc, "dec_MBps": units_mb / t_dec,
                    "kernel_ms_per_step": {k: v / a.steps for k, v in stats.items() if k != "launches"}},
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",

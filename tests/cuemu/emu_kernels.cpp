@@ -272,7 +272,7 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     if (nFrames) {
         std::vector<uint32_t> unitState((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u, 0u);
         cuemu::launch(dim3(nFrames < 5u ? nFrames : 5u), dim3(32), 0, [&] { zstd_dec_exec_kernel(src, frames.data(), nFrames, blocks.data(), lits.data(), seqs.data(), dst, &counts, unitState.data()); });
-        cuemu::launch(dim3((nFrames + 3) / 4), dim3(128), 0, [&] { zstd_dec_verify_kernel(src, frames.data(), nFrames, dst, &counts); });
+        cuemu::launch(dim3((nFrames + 1) / 2), dim3(64), 0, [&] { zstd_dec_verify_kernel(src, frames.data(), nFrames, dst, &counts); });
     }
     return counts.status ? -(int64_t)counts.status : (int64_t)total;
 }
