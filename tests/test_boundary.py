@@ -96,7 +96,7 @@ def test_binding_parameter_ids_match_header(pkg):
     ids = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+B200Z_P_([A-Z0-9_]+)\s+(\d+)", hdr)}
     names = dict(level="LEVEL", frame_log="FRAMELOG", hash_log_l="HASHLOG_L", hash_log_s="HASHLOG_S", window_log="WINDOWLOG", flags="FLAGS",
                  batch_log="BATCH_LOG", host_batch_log="HOST_BATCH_LOG", chunk_log="CHUNKLOG", lzma2_model="LZMA2_MODEL", lzma2_slice_log="LZMA2_SLICELOG",
-                 lzma2_parse="LZMA2_PARSE", zstd_parse="ZSTD_PARSE", long="LONG", region_log="REGIONLOG")
+                 lzma2_parse="LZMA2_PARSE", zstd_parse="ZSTD_PARSE", long="LONG", region_log="REGIONLOG", dec_jump="DEC_JUMP", dec_jump_seg_log="DEC_JUMP_SEGLOG")
     assert set(names) == set(pkg.Codec._PARAMS)
     for k, h in names.items():
         assert pkg.Codec._PARAMS[k] == ids[h], k
