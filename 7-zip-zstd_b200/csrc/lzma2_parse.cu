@@ -2,7 +2,7 @@
 //
 // Two kernels in front of stage R (lzma2_enc.cu), replacing the greedy stage M for this mode:
 //
-//   stage C  lzma2_cand_kernel -- one warp per frame and table, 32 positions per step.  For every position and each of four direct-mapped
+//   stage C  lzma2_cand_kernel -- one warp per frame, 32 positions per step.  For every position and each of four direct-mapped
 //            tables (keys of 3, 4, 6 and 8 bytes) the NEAREST earlier position whose key falls into the same table entry, and the
 //            common-prefix length with it: LZP_NCAND packed words per position.  Lanes of one step that hit the same entry are
 //            resolved with __match_any_sync (a lane takes the highest lower lane of its group, the group's highest lane writes
@@ -32,20 +32,20 @@ __host__ __device__ inline uint32_t lzma2_cand_table_words(uint32_t frameLog) {
     return w;
 }
 
-// One warp per (frame, table): the four tables of a frame do not depend on one another, so they run as four warps side by side -- the
-// kernel is a chain of dependent DRAM round trips per step (table entry, then the candidate's bytes), and four times the chains in flight
-// is what the memory system was waiting for (one warp per frame: 5.9 s per 4 GiB at 8 MiB frames).  Warp (slot, t) = blockIdx.x.
 __global__ void __launch_bounds__(32)
 lzma2_cand_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, uint32_t* __restrict__ tables, uint32_t* __restrict__ cand) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warpSlot = blockIdx.x / LZP_NCAND, t = blockIdx.x % LZP_NCAND, nWarps = gridDim.x / LZP_NCAND;
+    const uint32_t warpSlot = blockIdx.x, nWarps = gridDim.x;
     const uint64_t F = 1ull << g.frameLog;
     const uint64_t nFrames = (srcSize + F - 1) >> g.frameLog;
     const uint32_t tableWords = lzma2_cand_table_words(g.frameLog);
-    uint32_t toff = 0;
-    for (uint32_t k = 0; k < t; k++) toff += 1u << lzp_table_log(k, g.frameLog);
-    const uint32_t lg = lzp_table_log(t, g.frameLog), kb = lzp_key_bytes(t);
-    uint32_t* const T = tables + (size_t)warpSlot * tableWords + toff;
+    uint32_t* const T0 = tables + (size_t)warpSlot * tableWords;
+    uint32_t lg[LZP_NCAND], toff[LZP_NCAND];
+    {
+        uint32_t o = 0;
+#pragma unroll
+        for (uint32_t t = 0; t < LZP_NCAND; t++) { lg[t] = lzp_table_log(t, g.frameLog); toff[t] = o; o += 1u << lg[t]; }
+    }
     const uint32_t ltMask = (1u << lane) - 1u;
 
     for (uint64_t f = warpSlot; f < nFrames; f += nWarps) {
@@ -54,37 +54,46 @@ lzma2_cand_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeom g, 
         const uint64_t* __restrict__ w = reinterpret_cast<const uint64_t*>(src + f0);
         const uint32_t nWords = (n + 7u) >> 3;
         {
-            uint4* t4 = reinterpret_cast<uint4*>(T);
+            uint4* t4 = reinterpret_cast<uint4*>(T0);
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = lane; i < (1u << lg) / 4u; i += 32u) __stcg(t4 + i, z);
+            for (uint32_t i = lane; i < tableWords / 4u; i += 32u) __stcg(t4 + i, z);
             __syncwarp();
         }
-        uint32_t* const out = cand + f0 * LZP_NCAND + t;                 // word t of every position's four
+        uint4* const out = reinterpret_cast<uint4*>(cand) + f0;
         for (uint32_t base = 0; base < n; base += 32u) {
             const uint32_t p = base + lane;
             const bool live = p < n;
             const uint64_t v = live ? ld64u(w, p, nWords) : 0ull;
+            uint32_t q1[LZP_NCAND], idx[LZP_NCAND]; bool writer[LZP_NCAND];
             // ---- read phase: the entry as the previous steps left it, or the nearest lower lane of this step with the same entry
-            const bool valid = live && p + kb <= n;
-            const uint32_t idx = lzp_table_index(v, kb, lg);
-            const uint32_t grp = __match_any_sync(B2Z_FULL, valid ? idx : (0x80000000u | lane));
-            const uint32_t lower = grp & ltMask;
-            uint32_t q1 = 0; bool writer = false;
-            if (valid) {
-                q1 = lower ? base + (31u - (uint32_t)__clz((int)lower)) + 1u : __ldcg(T + idx);
-                writer = (grp >> lane) == 1u;                                // no higher lane in the group
+#pragma unroll
+            for (uint32_t t = 0; t < LZP_NCAND; t++) {
+                const bool valid = live && p + lzp_key_bytes(t) <= n;
+                idx[t] = lzp_table_index(v, lzp_key_bytes(t), lg[t]);
+                const uint32_t grp = __match_any_sync(B2Z_FULL, valid ? idx[t] : (0x80000000u | lane));
+                const uint32_t lower = grp & ltMask;
+                q1[t] = 0; writer[t] = false;
+                if (valid) {
+                    q1[t] = lower ? base + (31u - (uint32_t)__clz((int)lower)) + 1u : __ldcg(T0 + toff[t] + idx[t]);
+                    writer[t] = (grp >> lane) == 1u;                 // no higher lane in the group
+                }
             }
             __syncwarp();
             // ---- write phase: the newest position of every entry touched by this step
-            if (writer) __stcg(T + idx, p + 1u);
-            // ---- verify: common-prefix length with the candidate
-            uint32_t c = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < LZP_NCAND; t++) if (writer[t]) __stcg(T0 + toff[t] + idx[t], p + 1u);
+            // ---- verify: common-prefix length with each candidate
+            uint32_t c[LZP_NCAND];
             const uint32_t maxLen = live ? ((n - p) < B2Z_LZ2_MAXLEN ? (n - p) : B2Z_LZ2_MAXLEN) : 0u;
-            if (q1) {
-                const uint32_t l = match_len_pv(w, q1 - 1u, p, v, maxLen, nWords);
-                if (l >= 2u) c = LZP_PACK_CAND(p - q1, l < LZP_CAND_LENCAP ? l : LZP_CAND_LENCAP);
+#pragma unroll
+            for (uint32_t t = 0; t < LZP_NCAND; t++) {
+                c[t] = 0;
+                if (q1[t]) {
+                    const uint32_t l = match_len_pv(w, q1[t] - 1u, p, v, maxLen, nWords);
+                    if (l >= 2u) c[t] = LZP_PACK_CAND(p - q1[t], l < LZP_CAND_LENCAP ? l : LZP_CAND_LENCAP);
+                }
             }
-            if (live) out[(size_t)p * LZP_NCAND] = c;
+            if (live) __stcs(out + p, make_uint4(c[0], c[1], c[2], c[3]));
             __syncwarp();                                            // this step's entries are visible to the next step's reads
         }
         __syncwarp();
@@ -333,7 +342,7 @@ size_t lzma2_cand_table_bytes(const EncGeom& g, uint32_t nWarps) { return (size_
 void launch_lzma2_cand(const uint8_t* src, uint64_t srcSize, const EncGeom& g, uint32_t* tables, uint32_t nWarps, uint32_t* cand, cudaStream_t st) {
     if (!srcSize) return;
     const uint32_t nFrames = (uint32_t)((srcSize + (1ull << g.frameLog) - 1) >> g.frameLog);
-    lzma2_cand_kernel<<<(nWarps < nFrames ? nWarps : nFrames) * LZP_NCAND, 32, 0, st>>>(src, srcSize, g, tables, cand);     // a warp per (frame slot, table)
+    lzma2_cand_kernel<<<nWarps < nFrames ? nWarps : nFrames, 32, 0, st>>>(src, srcSize, g, tables, cand);
 }
 
 cudaError_t launch_lzma2_parse(const uint8_t* src, uint64_t srcSize, const EncGeom& g, const uint32_t* cand, uint64_t* seqs, uint32_t* nseq, cudaStream_t st) {

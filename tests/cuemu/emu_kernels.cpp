@@ -78,7 +78,7 @@ uint64_t emu_zstd_enc_match(const uint8_t* src, uint64_t srcSize, uint32_t frame
 uint64_t emu_lzma2_cand(const uint8_t* src, uint64_t srcSize, uint32_t frameLog, uint32_t flags, uint32_t nWarps, uint32_t* cand) {
     const EncGeom g = geom(frameLog, frameLog, B2Z_DEF_CHUNKLOG, flags);
     std::vector<uint32_t> tables((size_t)nWarps * lzma2_cand_table_words(frameLog), 0xCDCDCDCDu);
-    return cuemu::launch(dim3(nWarps * LZP_NCAND), dim3(32), 0, [&] { lzma2_cand_kernel(src, srcSize, g, tables.data(), cand); });
+    return cuemu::launch(dim3(nWarps), dim3(32), 0, [&] { lzma2_cand_kernel(src, srcSize, g, tables.data(), cand); });
 }
 
 // stage P (lzma2_parse_kernel); nseq is zeroed here as launch_lzma2_parse does
