@@ -122,6 +122,8 @@ def test_fuzz_emulated_pipelines_and_damaged_streams(pkg, seed, planted):
     E.emu_zstd_decode.restype = i64; E.emu_zstd_decode.argtypes = [vp, u64, vp, u64]
     E.emu_lzma2_range_and_assemble.restype = i64; E.emu_lzma2_range_and_assemble.argtypes = [vp, u64, u32, u32, vp, vp, vp, u64, ctypes.c_int]
     E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
+    E.emu_zstd_decode_jump.restype = i64; E.emu_zstd_decode_jump.argtypes = [vp, u64, vp, u64, u32, vp]
+    E.emu_set_jump_seglog.restype = None; E.emu_set_jump_seglog.argtypes = [u32]
     SLOT = E.emu_slot_bytes(); rng = random.Random(seed)
     for it in range(5 if planted else 12):
         data = _gen(rng, pkg, planted); n = len(data)
@@ -159,7 +161,11 @@ def test_fuzz_emulated_pipelines_and_damaged_streams(pkg, seed, planted):
                         else: c = c[:rng.randrange(len(c) + 1)]
                 cb = np.frombuffer(bytes(c) + bytes(64), dtype=np.uint8); back = np.zeros(n + 64, dtype=np.uint8)
                 if kind == "z":
-                    r = E.emu_zstd_decode(cb.ctypes.data, len(c), back.ctypes.data, n)
+                    if rng.random() < 0.5:                          # stage J forced on every frame, the output resolved in small segments
+                        E.emu_set_jump_seglog(rng.choice([16, 17, 30]))
+                        r = E.emu_zstd_decode_jump(cb.ctypes.data, len(c), back.ctypes.data, n, 2, None)
+                    else:
+                        r = E.emu_zstd_decode(cb.ctypes.data, len(c), back.ctypes.data, n)
                 else:
                     r = E.emu_lzma2_decode(cb.ctypes.data, len(c), prop, back.ctypes.data, n, rng.choice([0, 1, 2, 2])) if len(c) else -1
                 if not mut:
@@ -175,6 +181,8 @@ def test_emulated_decoders_give_the_oracle_decoders_verdict_on_damaged_streams(p
     vp, u32, u64, i64 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
     E.emu_lzma2_decode.restype = i64; E.emu_lzma2_decode.argtypes = [vp, u64, u32, vp, u64, ctypes.c_int]
     E.emu_zstd_decode.restype = i64; E.emu_zstd_decode.argtypes = [vp, u64, vp, u64]
+    E.emu_zstd_decode_jump.restype = i64; E.emu_zstd_decode_jump.argtypes = [vp, u64, vp, u64, u32, vp]
+    E.emu_set_jump_seglog.restype = None; E.emu_set_jump_seglog.argtypes = [u32]
     data = pkg.corpus.g2(120_000).tobytes() + bytes(3000) + pkg.corpus.entropy_class(1, 30_000).tobytes(); n = len(data)
     prop, lz = H.oracle_lzma2_compress(data, frameLog=17, windowLog=17, flags=1)
     zs = H.oracle_compress(data, frameLog=17, windowLog=17, flags=3)
@@ -193,8 +201,13 @@ def test_emulated_decoders_give_the_oracle_decoders_verdict_on_damaged_streams(p
                 want = H.oracle_lzma2_decompress(bytes(c), n, prop)[0] if kind == "l" else H.oracle_decompress(bytes(c), n)
             except ValueError:
                 want = None
-            r = (E.emu_lzma2_decode(cb.ctypes.data, len(c), prop, back.ctypes.data, n, it & 1) if kind == "l"
-                 else E.emu_zstd_decode(cb.ctypes.data, len(c), back.ctypes.data, n))
+            if kind == "z" and it % 3 == 2:                          # every third mutant through stage J (forced), 64 KiB segments
+                E.emu_set_jump_seglog(16)
+                r = E.emu_zstd_decode_jump(cb.ctypes.data, len(c), back.ctypes.data, n, 2, None)
+                E.emu_set_jump_seglog(30)
+            else:
+                r = (E.emu_lzma2_decode(cb.ctypes.data, len(c), prop, back.ctypes.data, n, it & 1) if kind == "l"
+                     else E.emu_zstd_decode(cb.ctypes.data, len(c), back.ctypes.data, n))
             assert (r >= 0) == (want is not None), (kind, it, k, r)
             if want is not None:
                 assert back[:r].tobytes() == want, (kind, it, k)
