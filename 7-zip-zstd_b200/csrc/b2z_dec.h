@@ -74,9 +74,10 @@ size_t zstd_dec_entropy_scratch_bytes(uint32_t nBlocks);
 void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint64_t dstCap,
                             DecCounts* counts, uint64_t* total, uint32_t jumpMode, cudaStream_t st);
 // stage J (frames with DecFrame::jump): literals and one pointer per output byte (J1), pointer doubling (J2), byte gather (J3).
-// ptr: one word per output byte of a segment (min(total, 2^segLog) + 16); flags: B2Z_DEC_JUMP_ROUNDS + 1 words
+// scratch: zstd_dec_jump_scratch_bytes(total, segLog) -- round flags, one word per output byte of a segment, one byte per 128 of them
+size_t zstd_dec_jump_scratch_bytes(uint64_t total, uint32_t segLog /* <= B2Z_DEC_JUMP_SEGLOG */);
 void launch_zstd_dec_jump(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
-                          uint8_t* dst, uint64_t total, uint32_t segLog /* <= B2Z_DEC_JUMP_SEGLOG */, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st);
+                          uint8_t* dst, uint64_t total, uint32_t segLog, DecCounts* counts, void* scratch, cudaStream_t st);
 // stage D3: one warp per unit of B2Z_DEC_UNIT_BLOCKS consecutive blocks of a frame, units taken in order; a match that reaches
 // behind its unit waits for the unit that writes those bytes.  unitState: [0] ticket, [1 + u] done flag of unit u -- zeroed here.
 size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks);

@@ -1099,47 +1099,58 @@ __device__ __forceinline__ uint32_t dec_frame_of(const DecFrame* __restrict__ fr
     return lo;
 }
 
-// J2 (LAST = false): one round of pointer doubling over every jump frame's pointers, four per thread.  flags[r] = round r left a pointer
-// that does not yet name a literal; a round whose predecessor left none returns at once (all rounds are launched up front).
+// J2 (LAST = false): one round of pointer doubling over every jump frame's pointers; a warp takes 128 consecutive positions, four per lane.
+// flags[r] = round r left a pointer that does not yet name a final byte; a round whose predecessor left none returns at once (all rounds are
+// launched up front).  tileDone[w] = the 128 pointers of warp tile w are all final: later rounds read one byte instead of 512 (most of a round
+// is streaming the pointer array, and after a few rounds most tiles have nothing left to do).
 // J3 (LAST = true): dst[i] = dst[ptr[i]] for the match bytes.
 template <bool LAST> __global__ void __launch_bounds__(256)
 zstd_dec_jump_round_kernel(const DecFrame* __restrict__ frames, uint32_t nFrames, uint64_t segS, uint64_t segE, uint32_t* __restrict__ ptr, uint32_t* flags,
-                           uint32_t round, uint8_t* dst, DecCounts* counts) {
+                           uint8_t* __restrict__ tileDone, uint32_t round, uint8_t* dst, DecCounts* counts) {
     if (counts->status) return;
     if (!LAST && round && !flags[round - 1u]) return;
-    const uint64_t n = segE - segS, nGroups = (n + 3u) >> 2;
+    const uint64_t n = segE - segS, nTiles = (n + 127u) >> 7;
+    const uint32_t lane = threadIdx.x & 31u;
     bool pending = false, broken = false;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i0 = g << 2;
-        uint32_t f = nFrames > 1u ? dec_frame_of(frames, nFrames, segS + i0) : 0u;
-        uint64_t fEnd = frames[f].dstOff + frames[f].regen; bool fj = frames[f].jump != 0u;
-        uint4 q4 = *reinterpret_cast<const uint4*>(ptr + i0);
-        uint32_t q[4] = { q4.x, q4.y, q4.z, q4.w }; bool take[4]; uint32_t r[4];
+    for (uint64_t tile = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < nTiles; tile += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+        if (!LAST && tileDone[tile]) continue;                                       // (warp-uniform)
+        const uint64_t i0 = (tile << 7) + (lane << 2);
+        bool mine = false;                                                            // one of this lane's pointers is not final after this round
+        if (i0 < n) {
+            uint32_t f = nFrames > 1u ? dec_frame_of(frames, nFrames, segS + i0) : 0u;
+            uint64_t fEnd = frames[f].dstOff + frames[f].regen; bool fj = frames[f].jump != 0u;
+            uint4 q4 = *reinterpret_cast<const uint4*>(ptr + i0);
+            uint32_t q[4] = { q4.x, q4.y, q4.z, q4.w }; bool take[4]; uint32_t r[4];
 #pragma unroll
-        for (uint32_t e = 0; e < 4; e++) {
-            const uint64_t i = i0 + e;
-            take[e] = false;
-            if (i < n) {
-                while (segS + i >= fEnd) { f++; fEnd = frames[f].dstOff + frames[f].regen; fj = frames[f].jump != 0u; }
-                take[e] = fj && (LAST ? q[e] != (((uint32_t)i + B2Z_DEC_JUMP_BIAS) | B2Z_DEC_JUMP_FINAL) : !(q[e] & B2Z_DEC_JUMP_FINAL));
+            for (uint32_t e = 0; e < 4; e++) {
+                const uint64_t i = i0 + e;
+                take[e] = false;
+                if (i < n) {
+                    while (segS + i >= fEnd) { f++; fEnd = frames[f].dstOff + frames[f].regen; fj = frames[f].jump != 0u; }
+                    take[e] = fj && (LAST ? q[e] != (((uint32_t)i + B2Z_DEC_JUMP_BIAS) | B2Z_DEC_JUMP_FINAL) : !(q[e] & B2Z_DEC_JUMP_FINAL));
+                }
+            }
+            if (!LAST) {
+#pragma unroll
+                for (uint32_t e = 0; e < 4; e++) r[e] = take[e] ? __ldcg(ptr + (q[e] - B2Z_DEC_JUMP_BIAS)) : q[e];   // not final: the source lies in this segment
+                if (take[0] | take[1] | take[2] | take[3]) {
+#pragma unroll
+                    for (uint32_t e = 0; e < 4; e++) mine |= take[e] && !(r[e] & B2Z_DEC_JUMP_FINAL);
+                    *reinterpret_cast<uint4*>(ptr + i0) = make_uint4(r[0], r[1], r[2], r[3]);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t e = 0; e < 4; e++) {                                           // the source's batch offset: segS + pointer - bias (>= 0: a byte of the batch)
+                    broken |= take[e] && !(q[e] & B2Z_DEC_JUMP_FINAL);
+                    r[e] = take[e] ? dst[segS + (q[e] & ~B2Z_DEC_JUMP_FINAL) - B2Z_DEC_JUMP_BIAS] : 0u;
+                }
+#pragma unroll
+                for (uint32_t e = 0; e < 4; e++) if (take[e]) dst[segS + i0 + e] = (uint8_t)r[e];
             }
         }
         if (!LAST) {
-#pragma unroll
-            for (uint32_t e = 0; e < 4; e++) r[e] = take[e] ? __ldcg(ptr + (q[e] - B2Z_DEC_JUMP_BIAS)) : q[e];   // not final: the source lies in this segment
-            if (take[0] | take[1] | take[2] | take[3]) {
-#pragma unroll
-                for (uint32_t e = 0; e < 4; e++) pending |= take[e] && !(r[e] & B2Z_DEC_JUMP_FINAL);
-                *reinterpret_cast<uint4*>(ptr + i0) = make_uint4(r[0], r[1], r[2], r[3]);
-            }
-        } else {
-#pragma unroll
-            for (uint32_t e = 0; e < 4; e++) {                                               // the source's batch offset: segS + pointer - bias (>= 0: a byte of the batch)
-                broken |= take[e] && !(q[e] & B2Z_DEC_JUMP_FINAL);
-                r[e] = take[e] ? dst[segS + (q[e] & ~B2Z_DEC_JUMP_FINAL) - B2Z_DEC_JUMP_BIAS] : 0u;
-            }
-#pragma unroll
-            for (uint32_t e = 0; e < 4; e++) if (take[e]) dst[segS + i0 + e] = (uint8_t)r[e];
+            pending |= mine;
+            if (!__any_sync(B2Z_FULL, mine) && lane == 0) tileDone[tile] = 1;
         }
     }
     if (!LAST && pending) flags[round] = 1u;
@@ -1207,19 +1218,26 @@ void launch_zstd_dec_layout(DecFrame* frames, uint32_t nFrames, DecBlock* blocks
     if (nFrames) zstd_dec_frame_sizes_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(frames, nFrames, blocks, counts, jumpMode);
     zstd_dec_frame_offsets_kernel<<<1, 32, 0, st>>>(frames, nFrames, dstCap, counts, total);
 }
+size_t zstd_dec_jump_scratch_bytes(uint64_t total, uint32_t segLog) {         // flags | pointers of one segment | one byte per 128 pointers
+    const uint64_t seg = total < (1ull << segLog) ? total : (1ull << segLog);
+    return 256 + ((size_t)seg + 16) * 4 + (size_t)((seg + 127) >> 7) + 64;
+}
 void launch_zstd_dec_jump(const uint8_t* src, DecFrame* frames, uint32_t nFrames, DecBlock* blocks, uint32_t nBlocks, const uint8_t* lits, const uint64_t* seqs,
-                          uint8_t* dst, uint64_t total, uint32_t segLog, DecCounts* counts, uint32_t* ptr, uint32_t* flags, cudaStream_t st) {
+                          uint8_t* dst, uint64_t total, uint32_t segLog, DecCounts* counts, void* scratch, cudaStream_t st) {
     if (!nFrames || !nBlocks || !total) return;
-    const uint64_t seg = 1ull << segLog;
+    const uint64_t seg = 1ull << segLog, segWords = total < seg ? total : seg;
+    uint32_t* flags = (uint32_t*)scratch; uint32_t* ptr = (uint32_t*)((uint8_t*)scratch + 256);
+    uint8_t* tileDone = (uint8_t*)(ptr + segWords + 16);
     for (uint64_t S = 0; S < total; S += seg) {                        // segments in order: what lies before a segment is complete
         const uint64_t E = S + seg < total ? S + seg : total;
         cudaMemsetAsync(flags, 0, (B2Z_DEC_JUMP_ROUNDS + 1u) * 4u, st);
+        cudaMemsetAsync(tileDone, 0, (size_t)((E - S + 127) >> 7), st);
         { const uint32_t want = (nBlocks + 3u) / 4u, grid = want < 148u * 16u ? want : 148u * 16u;
           zstd_dec_jump_build_kernel<<<grid, 128, 0, st>>>(src, frames, blocks, nBlocks, lits, seqs, dst, counts, ptr, S, E); }
         const uint64_t groups = (E - S + 3u) >> 2;
         const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 148u * 16u ? (groups + 255u) / 256u : 148u * 16u);
-        for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++) zstd_dec_jump_round_kernel<false><<<grid, 256, 0, st>>>(frames, nFrames, S, E, ptr, flags, r, dst, counts);
-        zstd_dec_jump_round_kernel<true><<<grid, 256, 0, st>>>(frames, nFrames, S, E, ptr, flags, 0, dst, counts);
+        for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++) zstd_dec_jump_round_kernel<false><<<grid, 256, 0, st>>>(frames, nFrames, S, E, ptr, flags, tileDone, r, dst, counts);
+        zstd_dec_jump_round_kernel<true><<<grid, 256, 0, st>>>(frames, nFrames, S, E, ptr, flags, tileDone, 0, dst, counts);
     }
 }
 size_t zstd_dec_unit_state_bytes(uint32_t nFrames, uint32_t nBlocks) { return ((size_t)nBlocks / B2Z_DEC_UNIT_BLOCKS + nFrames + 2u) * 4u; }

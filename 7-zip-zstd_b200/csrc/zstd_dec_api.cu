@@ -186,10 +186,9 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
         if (hj.c.nJump) {
             Arena& aPtr = ctx->decScratch[8];
             const uint32_t segLog = ctx->decJumpSegLog;
-            const uint64_t segWords = hj.total < (1ull << segLog) ? hj.total : (1ull << segLog);
-            if (aPtr.reserve(256 + ((size_t)segWords + 16) * 4)) return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (stage J pointers)%s");
+            if (aPtr.reserve(zstd_dec_jump_scratch_bytes(hj.total, segLog))) return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (stage J pointers)%s");
             launch_zstd_dec_jump((const uint8_t*)d_src, frames, hc.nFrames, blocks, hc.nBlocks, (const uint8_t*)aLits.p, (const uint64_t*)aSeqs.p,
-                                 (uint8_t*)d_dst, hj.total, segLog, counts, (uint32_t*)((uint8_t*)aPtr.p + 256), (uint32_t*)aPtr.p, st);
+                                 (uint8_t*)d_dst, hj.total, segLog, counts, aPtr.p, st);
             CU(cudaGetLastError());
             ctx->stat[B200Z_S_KERNEL_LAUNCHES] += (2 + B2Z_DEC_JUMP_ROUNDS) * ((hj.total + (1ull << segLog) - 1) >> segLog);
             ctx->stat[B200Z_S_DEC_JUMP_FRAMES] += hj.c.nJump;

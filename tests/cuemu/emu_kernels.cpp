@@ -258,15 +258,16 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     if (maybeJump && !counts.status && counts.nJump && nBlocks && total) {             // launch_zstd_dec_jump
         const uint64_t seg = 1ull << g_emu_jump_seglog;
         std::vector<uint32_t> ptr((size_t)(total < seg ? total : seg) + 16, 0xCDCDCDCDu), flags(B2Z_DEC_JUMP_ROUNDS + 1u, 0u);
+        std::vector<uint8_t> tileDone((size_t)(((total < seg ? total : seg) + 127) >> 7) + 1, 0);
         for (uint64_t S = 0; S < total; S += seg) {
             const uint64_t E = S + seg < total ? S + seg : total;
-            std::fill(flags.begin(), flags.end(), 0u);
+            std::fill(flags.begin(), flags.end(), 0u); std::fill(tileDone.begin(), tileDone.end(), (uint8_t)0);
             cuemu::launch(dim3((nBlocks + 3u) / 4u < 3u ? (nBlocks + 3u) / 4u : 3u), dim3(128), 0, [&] { zstd_dec_jump_build_kernel(src, frames.data(), blocks.data(), nBlocks, lits.data(), seqs.data(), dst, &counts, ptr.data(), S, E); });
             const uint64_t groups = (E - S + 3u) >> 2;
             const uint32_t grid = (uint32_t)((groups + 255u) / 256u < 2u ? (groups + 255u) / 256u : 2u);
             for (uint32_t r = 0; r < B2Z_DEC_JUMP_ROUNDS; r++)
-                cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<false>(frames.data(), nFrames, S, E, ptr.data(), flags.data(), r, dst, &counts); });
-            cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<true>(frames.data(), nFrames, S, E, ptr.data(), flags.data(), 0, dst, &counts); });
+                cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<false>(frames.data(), nFrames, S, E, ptr.data(), flags.data(), tileDone.data(), r, dst, &counts); });
+            cuemu::launch(dim3(grid), dim3(256), 0, [&] { zstd_dec_jump_round_kernel<true>(frames.data(), nFrames, S, E, ptr.data(), flags.data(), tileDone.data(), 0, dst, &counts); });
         }
     }
     if (nFrames) {
