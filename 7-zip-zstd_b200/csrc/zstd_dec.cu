@@ -126,6 +126,7 @@ __device__ FrameHdr parse_frame_hdr(const Src& S, uint64_t ip, uint64_t srcSize)
     if (fcsBytes) { uint64_t fcs = 0; for (uint32_t i = 0; i < fcsBytes; i++) fcs |= (uint64_t)S.u8(ip + i) << (8 * i); if (fcsBytes == 2) fcs += 256; h.contentSize = fcs; }
     ip += fcsBytes;
     if (single) h.windowSize = h.contentSize;
+    else if (h.contentSize != ~0ull && h.contentSize < h.windowSize) h.windowSize = h.contentSize;     // no offset can exceed the content (zstd --long=31 on a small file)
     if (h.windowSize > (1ull << 30) - 16) { h.status = B2Z_DERR_UNSUPPORTED; return h; }
     h.hdrBytes = (uint32_t)(ip - ip0);
     return h;

@@ -329,6 +329,16 @@ def test_emulated_zstd_decoder_on_golden_and_reference_frames(pkg, emu):
     import struct
     fake = struct.pack("<III", 0x184D2A50, 4, 4242)
     assert dec(fake + streams[0] + fake + streams[1], 2 * n) == (2 * n, data + data)
+    # a window descriptor far beyond what the decoder's offsets cover (2^30, 2^31) is fine when the declared content is small: no offset can
+    # exceed the content (zstd_decompress.c:482-560 only bounds the window by ZSTD_WINDOWLOG_MAX); without a content size it stays unsupported
+    if H.ref_available():
+        f = bytearray(H.ref_compress(data, level=3, windowLog=17))
+        assert f[4] & 0x20 == 0 and f[4] >> 6                       # not single-segment, content size present
+        for wd in (0xA0, 0xA8):
+            f[5] = wd
+            assert dec(bytes(f), n) == (n, data), hex(wd)
+        g = bytearray(H.ref_compress(data, level=3, windowLog=17, contentSizeFlag=0)); g[5] = 0xA8
+        assert dec(bytes(g), n)[0] == -2                            # B2Z_DERR_UNSUPPORTED
 
 
 def test_emulated_zstd_decoder_frames_of_several_units(pkg, emu):
