@@ -374,21 +374,10 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
         ns = nseq[(size_t)f * bpf + b]; i = 0; z0 = z1 = z2 = 0;
         sNext = ns ? __ldg(sq) : 0ull;
     };
-    // input bytes ahead of the producer: the 8-byte word that holds byte pos + 1 and the one after it (a literal takes its successor from
-    // there: one load per eight literals, issued eight literals early), and -- fetched when a sequence is decoded, one or more packets before
-    // they are needed -- the three bytes the packet after the sequence's match starts from and the word for the literals behind it
-    const uint32_t lim8 = done ? 0u : (uint32_t)((((srcSize - f0) < (F + 8u) ? (srcSize - f0) : (F + 8u)) + 7u) & ~7ull);   // bytes that may be read from base, in whole words
-    auto word_at = [&](uint32_t a) -> uint64_t { return a + 8u <= lim8 ? __ldg(reinterpret_cast<const uint64_t*>(base + a)) : 0ull; };
-    uint32_t wA = 0, postNxt = 0, postPrev = 0, postMb = 0; uint64_t wb = 0, wn = 0, postW = 0;
-    if (!done) {
-        cur = __ldg(base + pos); prev = pos ? (uint32_t)__ldg(base + pos - 1u) : 0u; block_begin();
-        wA = (pos + 1u) & ~7u; wb = word_at(wA); wn = word_at(wA + 8u);
-    }
+    if (!done) { cur = __ldg(base + pos); prev = pos ? (uint32_t)__ldg(base + pos - 1u) : 0u; block_begin(); }
 
     auto literal = [&]() {
-        const uint32_t p1 = pos + 1u;
-        if (p1 - wA >= 8u) { wA += 8u; wb = wn; wn = word_at(wA + 8u); }                  // (p1 advances by one: never further than the next word)
-        const uint32_t nxt = p1 < n ? (uint32_t)(wb >> ((p1 & 7u) * 8u)) & 0xFFu : 0u;   // for the next packet
+        const uint32_t nxt = (pos + 1u < n) ? (uint32_t)__ldg(base + pos + 1u) : 0u;     // for the next packet
         put(P_ISMATCH + state * 16u + (pos & PBM), 0);
         const uint32_t p = P_LIT + 0x300u * (((pos & LPM) << B2Z_LZ2_LC) + (prev >> (8u - B2Z_LZ2_LC)));
         uint32_t m = 1; bool matched = state >= 7u;                 // matched literal: the context follows the byte at rep0 while it agrees
@@ -402,8 +391,9 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
         state = state < 4u ? 0u : (state < 10u ? state - 3u : state - 6u);
         prev = cur; cur = nxt; pos++;
     };
-    auto match = [&](uint32_t len, uint32_t dist, bool last) {       // dist = distance - 1; last: the sequence's final piece
+    auto match = [&](uint32_t len, uint32_t dist) {                  // dist = distance - 1
         const uint32_t pN = pos + len;
+        const uint32_t nxt = (pN < n) ? (uint32_t)__ldg(base + pN) : 0u, prevN = __ldg(base + pN - 1u), mbN = __ldg(base + pN - dist - 1u);
         const uint32_t ps = pos & PBM;
         put(P_ISMATCH + state * 16u + ps, 1);
         const int r = dist == rep0 ? 0 : (dist == rep1 ? 1 : (dist == rep2 ? 2 : (dist == rep3 ? 3 : -1)));
@@ -434,11 +424,7 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
             put_len(P_REPLEN, len, ps);
             state = state < 7u ? 8u : 11u;
         }
-        pos = pN;
-        if (last) {                                                  // what the next packet starts from was fetched when the sequence was decoded
-            cur = postNxt; prev = postPrev; mb = postMb;
-            wA = (pN + 1u) & ~7u; wb = postW; wn = word_at(wA + 8u);
-        }
+        cur = nxt; prev = prevN; mb = mbN; pos = pN;
     };
 
     for (;;) {
@@ -463,11 +449,6 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
                             if (idx != 0u) { if (idx != 1u) z2 = z1; z1 = z0; z0 = off; }
                         }
                         litLeft = ll; mlLeft = B2Z_SEQ_ML(s); mdist = off - 1u;
-                        if (mlLeft) {
-                            const uint32_t pE = pos + ll + mlLeft;                         // first byte behind the sequence
-                            postNxt = pE < n ? (uint32_t)__ldg(base + pE) : 0u; postPrev = __ldg(base + pE - 1u); postMb = __ldg(base + pE - off);
-                            postW = word_at((pE + 1u) & ~7u);
-                        }
                         if (litLeft | mlLeft) break;
                         continue;
                     }
@@ -499,7 +480,7 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
             if (go && !lit) {
                 uint32_t len = mlLeft > B2Z_LZ2_MAXLEN ? B2Z_LZ2_MAXLEN : mlLeft;
                 if (mlLeft - len == 1u) len--;
-                match(len, mdist, mlLeft == len); mlLeft -= len;
+                match(len, mdist); mlLeft -= len;
             }
             __syncwarp();
         }
