@@ -251,12 +251,15 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
 //           the probabilities -- until the queue holds B2Z_R32_FILL decisions;
 //   phase B (lock-step): B2Z_R32_FILL times, all 32 lanes pop a decision and code it.  The probabilities of the steps to come are loaded
 //           B2Z_R32_DEPTH steps ahead (a step that adapts one of them forwards the new value).
-// STATUS: parity-green on B200 (bytes of the kernel above) but not the default: measured 1.9 s per 4 GiB (929 ms per GiB at a quarter of the
-// warps) against 0.98 s for one chain per warp.  ncu (profiles/r2_range32_ncu.txt): 17 of 32 lanes active on average, 31 warp
-// instructions per chain byte instead of 164 -- the instruction stream is 5x shorter -- but every coding step waits for the slowest of
-// 32 scattered model accesses (L1 hit rate 45 %, one lane in 70 goes to DRAM: one step in three), and with 0.9 - 3.5 warps per SM nothing
-// else is there to run meanwhile.  What it needs next: the round's distinct probabilities gathered into shared memory with all their loads
-// in flight at once, and the producer's input bytes fetched a packet ahead.  Selected with B200Z_P_LZMA2_MODEL = 3.
+// STATUS: parity-green on B200 (bytes of the kernel above) but not the default: 1.9 s per 4 GiB against 0.98 s for one chain per warp.
+// Why, in numbers (profiles/r2_range32_ncu.txt): the warp executes ~185 instructions per step of 32 decisions -- 6 per decision where the
+// single-chain kernel spends 30 -- so the whole job is 4x fewer instructions.  But the single-chain kernel is ISSUE-bound (32 resident warps
+// per SM keep the schedulers at 0.7 instructions per cycle), while 16 384 chains are only 512 lock-step warps, 3.5 per SM, each issuing one
+// instruction per ~6-7 cycles (dependent arithmetic, shared-memory and L1/L2 latencies, nothing else to run): chip-wide 11 decisions per cycle
+// against 34.  A third version that gathered a round's distinct probabilities into a shared-memory hash table with all their loads in flight
+// at once and prefetched the producer's input bytes removed the DRAM waits and was no faster (2.2 s: 229 instructions per step) -- the bound
+// is instructions per step x latency per instruction at this warp count, not memory.  Lock-step pays only with >= ~24 such warps per SM, i.e.
+// ~100 000 chains (slices of ~40 KiB: a ratio cost nobody wants), or below ~75 instructions per step.  Selected with B200Z_P_LZMA2_MODEL = 3.
 // The models live in global memory, interleaved by lane (probability i of lane l at [i][l]).  Chunk rules are the single-chain kernel's:
 // a packet may be queued ahead of its coding only while the chunk cannot reach its packed limit before it (a decision emits at most one
 // byte, so `packed + queued < limit` is a proof); near the limit a lane queues one packet at a time and decides with an empty queue, which
@@ -267,8 +270,6 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
 #define B2Z_R32_DEPTH  4
 #define B2Z_R32_DIRECT 0x1FFFu   // "probability index" of a direct bit (range halves, no model)
 #define B2Z_R32_WARPS  2u
-#define B2Z_R32_HSLOTS 64u       // hash slots of a lane's working set (at most B2Z_R32_FILL distinct indices per round)
-#define B2Z_R32_WARP_WORDS (B2Z_R32_QCAP * 32u + 2u * B2Z_R32_HSLOTS * 32u + B2Z_R32_FILL * 32u / 2u)   // 16-bit words of shared memory per warp: queue | keys | values | list (bytes)
 static_assert(P_LIT + (0x300u << (B2Z_LZ2_LC + B2Z_LZ2_LP)) < B2Z_R32_DIRECT, "a queue entry holds a 13-bit probability index");
 
 __device__ __forceinline__ void rce32_shift_low(RcE& e) {
@@ -293,14 +294,7 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
     constexpr uint32_t PBM = (1u << B2Z_LZ2_PB) - 1u, LPM = (1u << B2Z_LZ2_LP) - 1u;
     const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
     const uint32_t group = blockIdx.x * (blockDim.x >> 5) + wic, chain = group * 32u + lane;
-    uint16_t* const wsm = queues + (size_t)wic * B2Z_R32_WARP_WORDS;
-    uint16_t* const q = wsm + lane;                                                        // slot s of this lane: q[(s % QCAP) * 32]
-    // the round's working set (phase B): a 64-slot hash table of the distinct probability indices of the lane's next decisions -- key,
-    // value -- and the list of its occupied slots in order of insertion
-    uint16_t* const hkey = wsm + B2Z_R32_QCAP * 32u + lane;                                // hkey[slot * 32]
-    uint16_t* const hval = hkey + B2Z_R32_HSLOTS * 32u;                                    // hval[slot * 32]
-    uint8_t* const hlst = reinterpret_cast<uint8_t*>(hval + B2Z_R32_HSLOTS * 32u - lane) + lane;   // hlst[j * 32]
-    for (uint32_t k = 0; k < B2Z_R32_HSLOTS; k++) hkey[k * 32u] = 0xFFFFu;                 // empty
+    uint16_t* const q = queues + (size_t)wic * B2Z_R32_QCAP * 32u + lane;                 // slot s of this lane: q[(s % QCAP) * 32]
     uint16_t* const model = models + (size_t)group * NPROBS * 32u + lane;                 // probability i of this lane: model[i * 32]
     uint32_t head = 0, tail = 0;                                                           // decisions coded / queued so far
     auto put = [&](uint32_t idx, uint32_t bit) { q[(tail & (B2Z_R32_QCAP - 1u)) * 32u] = (uint16_t)((idx << 1) | bit); tail++; };
@@ -492,62 +486,48 @@ lzma2_enc_range32_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncG
         uint32_t maxN = myN;
 #pragma unroll
         for (int d = 16; d; d >>= 1) { const uint32_t o = __shfl_xor_sync(B2Z_FULL, maxN, d); maxN = o > maxN ? o : maxN; }
-        // B0 gather: the distinct probability indices of the round go into the lane's hash table (linear probing, at most half full); the
-        //    queue entry keeps the table slot instead of the index.  B1 load: all of them at once -- one wait for the slowest instead of one per
-        //    step.  B2 code: 32 steps on shared memory.  B3 write back and empty the table.
-        uint32_t cnt = 0;
-        for (uint32_t s = 0; s < maxN; s++) {
-            if (s < myN) {
-                uint16_t* qe = q + ((head + s) & (B2Z_R32_QCAP - 1u)) * 32u;
-                const uint32_t en = *qe, idx = en >> 1;
-                uint32_t h = B2Z_R32_HSLOTS;                                              // (a direct bit keeps "slot" HSLOTS)
-                if (idx != B2Z_R32_DIRECT) {
-                    h = (idx ^ (idx >> 6)) & (B2Z_R32_HSLOTS - 1u);
-                    for (;;) {
-                        const uint32_t k = hkey[h * 32u];
-                        if (k == idx) break;
-                        if (k == 0xFFFFu) { hkey[h * 32u] = (uint16_t)idx; hlst[cnt * 32u] = (uint8_t)h; cnt++; break; }
-                        h = (h + 1u) & (B2Z_R32_HSLOTS - 1u);
-                    }
+        // slot k of the pipeline holds the decision of step s with s % DEPTH == k and its probability, loaded DEPTH steps ahead.  A step that
+        // adapts a probability some slot has already loaded marks that slot stale; a stale slot loads again when its turn comes (rare: the
+        // same index within DEPTH decisions).  The stale mark is a flag, not a forwarded value, so that nothing touches a slot's register
+        // before its load has had DEPTH steps to arrive (forwarding into it made every step wait for the load it had just issued: 40 % of
+        // the kernel's time in the first version)
+        uint32_t ent[B2Z_R32_DEPTH], pv[B2Z_R32_DEPTH], stale = 0;
+#pragma unroll
+        for (int j = 0; j < B2Z_R32_DEPTH; j++) {
+            ent[j] = 0xFFFFu; pv[j] = 0;
+            if ((uint32_t)j < myN) { ent[j] = q[((head + (uint32_t)j) & (B2Z_R32_QCAP - 1u)) * 32u]; if ((ent[j] >> 1) != B2Z_R32_DIRECT) pv[j] = model[(ent[j] >> 1) * 32u]; }
+        }
+        for (uint32_t s0 = 0; s0 < maxN; s0 += B2Z_R32_DEPTH) {
+#pragma unroll
+            for (int k = 0; k < B2Z_R32_DEPTH; k++) {
+                const uint32_t s = s0 + (uint32_t)k;
+                if (s >= maxN) break;                                                    // (warp-uniform)
+                const uint32_t en = ent[k], idx = en >> 1, bit = en & 1u;
+                const bool act = s < myN, dir = idx == B2Z_R32_DIRECT;
+                uint32_t v = pv[k];
+                if (act && ((stale >> k) & 1u)) v = model[idx * 32u];
+                stale &= ~(1u << k);
+                ent[k] = 0xFFFFu; pv[k] = 0;
+                if (s + B2Z_R32_DEPTH < myN) {                                           // issue the loads of step s + DEPTH
+                    const uint32_t x = q[((head + s + B2Z_R32_DEPTH) & (B2Z_R32_QCAP - 1u)) * 32u];
+                    ent[k] = x;
+                    if ((x >> 1) != B2Z_R32_DIRECT) pv[k] = model[(x >> 1) * 32u];
                 }
-                *qe = (uint16_t)((h << 1) | (en & 1u));
-            }
-            __syncwarp();
-        }
-        {
-            uint32_t pv[B2Z_R32_FILL];
-#pragma unroll
-            for (uint32_t j = 0; j < B2Z_R32_FILL; j++) { pv[j] = 0; if (j < cnt) pv[j] = model[(uint32_t)hkey[(uint32_t)hlst[j * 32u] * 32u] * 32u]; }
-#pragma unroll
-            for (uint32_t j = 0; j < B2Z_R32_FILL; j++) if (j < cnt) hval[(uint32_t)hlst[j * 32u] * 32u] = (uint16_t)pv[j];
-        }
-        __syncwarp();
-        {
-            uint32_t en = myN ? q[(head & (B2Z_R32_QCAP - 1u)) * 32u] : 0u;
-            for (uint32_t s = 0; s < maxN; s++) {
-                const bool act = s < myN;
-                const uint32_t slot = en >> 1, bit = en & 1u;
-                const bool dir = slot == B2Z_R32_HSLOTS;
-                const uint32_t enNext = s + 1u < myN ? q[((head + s + 1u) & (B2Z_R32_QCAP - 1u)) * 32u] : 0u;
                 if (act) {
-                    const uint32_t v = dir ? 0u : hval[slot * 32u];
                     const uint32_t half = e.range >> 1, bound = (e.range >> 11) * v;
-                    if (!dir) hval[slot * 32u] = (uint16_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5));
+                    if (!dir) {
+                        model[idx * 32u] = (uint16_t)((int32_t)v + (((bit ? 31 : 2048) - (int32_t)v) >> 5));
+#pragma unroll
+                        for (int j = 0; j < B2Z_R32_DEPTH; j++) if ((ent[j] >> 1) == idx) stale |= 1u << j;
+                    }
                     const uint32_t cut = dir ? half : bound;                              // a direct bit halves the range, no model
                     if (bit) e.low += cut;
                     e.range = dir ? half : (bit ? e.range - bound : bound);
                     if (e.range < (1u << 24)) { e.range <<= 8; rce32_shift_low(e); }
                 }
-                en = enNext;
                 __syncwarp();                                                            // (convergence, see phase A)
             }
         }
-        for (uint32_t j = 0; j < cnt; j++) {                                             // B3
-            const uint32_t h = hlst[j * 32u], idx = hkey[h * 32u];
-            model[idx * 32u] = hval[h * 32u];
-            hkey[h * 32u] = 0xFFFFu;
-        }
-        __syncwarp();
         head += myN;
         __syncwarp();
     }
@@ -579,7 +559,7 @@ cudaError_t launch_lzma2_enc_range(const uint8_t* src, uint64_t srcSize, const E
     if (mode == 3) {                                                // 32 chains per warp (experimental, see the kernel's header); litSpill holds whole models here (lzma2_enc_model_bytes)
         if (!litSpill) return cudaErrorInvalidValue;
         const uint32_t groups = (nChains + 31u) / 32u;
-        lzma2_enc_range32_kernel<<<(groups + B2Z_R32_WARPS - 1u) / B2Z_R32_WARPS, 32 * B2Z_R32_WARPS, B2Z_R32_WARPS * B2Z_R32_WARP_WORDS * sizeof(uint16_t), st>>>(
+        lzma2_enc_range32_kernel<<<(groups + B2Z_R32_WARPS - 1u) / B2Z_R32_WARPS, 32 * B2Z_R32_WARPS, B2Z_R32_WARPS * B2Z_R32_QCAP * 32u * sizeof(uint16_t), st>>>(
             src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);
     } else if (glit) {     // two warps (chains) per CTA: 32 CTAs/SM would otherwise cap residency below the register limit
         lzma2_enc_range_kernel<true, 1><<<(nChains + 1u) / 2u, 64, 2u * P_LIT * sizeof(uint16_t), st>>>(src, srcSize, g, seqs, nseq, slots, stride, slotSize, litSpill, status, nChains);

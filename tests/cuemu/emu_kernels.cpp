@@ -162,7 +162,7 @@ int64_t emu_lzma2_range_and_assemble(const uint8_t* src, uint64_t srcSize, uint3
     std::vector<uint8_t> slots((size_t)nChains * stride, 0xCD); std::vector<uint32_t> slotSize(nChains + 1, 0xCDCDCDCDu); uint32_t status = 0;
     std::vector<uint16_t> spill(glit == 1 ? (size_t)nChains * LITN : 1);
     std::vector<uint16_t> models(glit == 2 ? lzma2_enc_model_bytes(nChains) / 2 : 1, 0xCDCD);
-    if (glit == 2) cuemu::launch(dim3(((nChains + 31u) / 32u + B2Z_R32_WARPS - 1u) / B2Z_R32_WARPS), dim3(32 * B2Z_R32_WARPS), B2Z_R32_WARPS * B2Z_R32_WARP_WORDS * sizeof(uint16_t), [&] {
+    if (glit == 2) cuemu::launch(dim3(((nChains + 31u) / 32u + B2Z_R32_WARPS - 1u) / B2Z_R32_WARPS), dim3(32 * B2Z_R32_WARPS), B2Z_R32_WARPS * B2Z_R32_QCAP * 32u * sizeof(uint16_t), [&] {
         lzma2_enc_range32_kernel(src, srcSize, g, seqs, nseq, slots.data(), stride, slotSize.data(), models.data(), &status, nChains); });
     else if (glit) cuemu::launch(dim3((nChains + 1u) / 2u), dim3(64), 2u * P_LIT * sizeof(uint16_t), [&] {
         lzma2_enc_range_kernel<true, 1>(src, srcSize, g, seqs, nseq, slots.data(), stride, slotSize.data(), spill.data(), &status, nChains); });
