@@ -293,7 +293,10 @@ def cuemu_library():
     d = os.path.join(ROOT, "tests", "cuemu")
     name = ("libcuemu_kernels_asan.so" if os.environ.get("B2Z_CUEMU_ASAN") else
             "libcuemu_kernels_ubsan.so" if os.environ.get("B2Z_CUEMU_UBSAN") else "libcuemu_kernels.so")     # UBSan: LD_PRELOAD libubsan.so, pytest -s
-    subprocess.check_call(["make", "-s", "-C", d, name])
+    import fcntl
+    with open(os.path.join(d, ".build.lock"), "w") as lock:         # pytest-xdist workers would otherwise run make on the same target at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        subprocess.check_call(["make", "-s", "-C", d, name])
     return ctypes.CDLL(os.path.join(d, name))
 
 
