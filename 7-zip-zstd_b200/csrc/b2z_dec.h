@@ -25,7 +25,9 @@ struct DecFrame {
     uint32_t pad;           // D0: scratch (frame header bytes); from D2 on: index of the frame's first execution unit
     uint64_t endOff;        // offset just past the frame in src (the checksum, if any, is the 4 bytes before it)
     uint32_t jump;          // D2: 1 = the frame's matches are resolved by pointer jumping (stage J) instead of by execution units
-    uint32_t pad3;
+    uint32_t nComp;         // D0: compressed blocks of the frame (the only ones that own literal / sequence scratch)
+    uint32_t firstSlot;     // D0: scratch slot of the frame's first compressed block
+    uint32_t pad4;
 };
 
 struct DecBlock {
@@ -47,6 +49,8 @@ struct DecBlock {
     uint32_t repInit[3];    // history at the block's first sequence (stage D2)
     uint32_t nearBehind;    // stage D1: 1 = a match with an explicit offset starts at most one unit's span (512 KiB) before the block's first byte
     uint64_t outRel;        // first output byte of the block, relative to its frame (stage D2)
+    uint32_t slot;          // index of the block's 128 KiB literal buffer and 64 Ki-sequence array (compressed blocks, numbered densely; ~0 otherwise)
+    uint32_t pad4;
 };
 
 #define B2Z_DEC_ROUNDS 4u            // stage D3: 32-byte rounds of a batch's literal / match copies whose loads are issued together
@@ -59,7 +63,7 @@ struct DecBlock {
 #define B2Z_DEC_JUMP_SEGLOG 30u          // stage J: the batch's output is resolved in segments of this many bytes, in order
 #define B2Z_DEC_JUMP_ROUNDS 32u      // pointer doubling: a chain of n links is resolved after ceil(log2 n) rounds, n < 2^31
 
-struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; uint32_t maxFrameBlocks, nJump; };
+struct DecCounts { uint32_t nFrames, nBlocks, status, nUnits; uint64_t srcUsed; uint32_t maxFrameBlocks, nJump, nSlots, pad; };
 
 // stage D0: frame discovery (1 thread; hops over mcmilk size hints when present), then per-frame block indexing
 void launch_zstd_dec_find_frames(const uint8_t* src, uint64_t srcSize, DecFrame* frames, uint32_t frameCap, DecCounts* counts, bool useHints, cudaStream_t st);

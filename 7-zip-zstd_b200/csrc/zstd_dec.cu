@@ -135,8 +135,8 @@ __device__ FrameHdr parse_frame_hdr(const Src& S, uint64_t ip, uint64_t srcSize)
 // Walk the block headers of one frame starting at `ip` (first block header). Returns the status; *nb = blocks,
 // *ipEnd = offset after the last block.  With `out` != null also fills the block entries.
 __device__ uint32_t walk_blocks(const Src& S, uint64_t ip, uint64_t srcSize, uint32_t* nbOut, uint64_t* ipEnd,
-                                DecBlock* out, uint32_t firstBlock, uint32_t frameIdx, uint32_t blockCap) {
-    uint32_t nb = 0; int32_t lastHuf = -1, lastTbl[3] = { -1, -1, -1 };
+                                DecBlock* out, uint32_t firstBlock, uint32_t frameIdx, uint32_t blockCap, uint32_t firstSlot = 0, uint32_t* nCompOut = nullptr) {
+    uint32_t nb = 0, nComp = 0; int32_t lastHuf = -1, lastTbl[3] = { -1, -1, -1 };
     for (;;) {
         if (srcSize < ip || srcSize - ip < 3) return B2Z_DERR_CORRUPT;
         const uint32_t bh = S.le24(ip); ip += 3;
@@ -149,6 +149,7 @@ __device__ uint32_t walk_blocks(const Src& S, uint64_t ip, uint64_t srcSize, uin
             const int32_t self = (int32_t)(firstBlock + nb);
             DecBlock b; b.srcOff = ip; b.type = type; b.frame = frameIdx; b.hufSrc = -1; b.tblSrc[0] = b.tblSrc[1] = b.tblSrc[2] = -1;
             b.regen = 0; b.nbSeq = 0; b.litSize = 0; b.status = 0; b.rawSize = 0; b.cSize = cSize; b.nearBehind = 0;
+            b.slot = type == 2 ? firstSlot + nComp : 0xFFFFFFFFu; b.pad4 = 0;              // only compressed blocks own literal / sequence scratch
             if (type != 2) { b.rawSize = bsize; b.regen = bsize; }
             else {
                 const LitHdr lh = parse_lit_hdr(S, ip, bsize);
@@ -168,11 +169,11 @@ __device__ uint32_t walk_blocks(const Src& S, uint64_t ip, uint64_t srcSize, uin
             }
             out[firstBlock + nb] = b;
         }
-        nb++;
+        nb++; nComp += type == 2;
         ip += cSize;
         if (last) break;
     }
-    *nbOut = nb; *ipEnd = ip;
+    *nbOut = nb; *ipEnd = ip; if (nCompOut) *nCompOut = nComp;
     return 0;
 }
 
@@ -197,7 +198,7 @@ __global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uin
                 if (fsz >= 9 && srcSize - (ip + 12) >= fsz) {
                     if (nf >= frameCap) { status = B2Z_DERR_TABLE_FULL; break; }
                     DecFrame fr; fr.srcOff = ip + 12; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = ip + 12 + fsz;   // regen: end offset (until D2)
-                    fr.firstBlock = 0; fr.nBlocks = 0; fr.checksum = 0; fr.pad = 1; fr.endOff = ip + 12 + fsz;                          // pad: 1 = end offset is a hint
+                    fr.firstBlock = 0; fr.nBlocks = 0; fr.checksum = 0; fr.pad = 1; fr.endOff = ip + 12 + fsz; fr.jump = 0; fr.nComp = 0; fr.firstSlot = 0; fr.pad4 = 0;                          // pad: 1 = end offset is a hint
                     frames[nf++] = fr; hinted++;
                     ip += 12 + fsz; continue;
                 }
@@ -212,7 +213,7 @@ __global__ void zstd_dec_find_frames_kernel(const uint8_t* __restrict__ src, uin
         status = walk_blocks(S, ip + h.hdrBytes, srcSize, &nb, &end, nullptr, 0, nf, 0);
         if (status) break;
         if (h.checksum) { if (srcSize - end < 4) { status = B2Z_DERR_CORRUPT; break; } end += 4; }
-        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = end; fr.firstBlock = 0; fr.nBlocks = nb; fr.checksum = 0; fr.pad = 0; fr.endOff = end;
+        DecFrame fr; fr.srcOff = ip; fr.dstOff = 0; fr.contentSize = ~0ull; fr.windowSize = 0; fr.regen = end; fr.firstBlock = 0; fr.nBlocks = nb; fr.checksum = 0; fr.pad = 0; fr.endOff = end; fr.jump = 0; fr.nComp = 0; fr.firstSlot = 0; fr.pad4 = 0;
         frames[nf++] = fr;
         ip = end;
     }
@@ -225,20 +226,23 @@ __global__ void zstd_dec_count_blocks_kernel(const uint8_t* __restrict__ src, ui
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
     DecFrame fr = frames[f];
     const FrameHdr h = parse_frame_hdr(S, fr.srcOff, srcSize);
-    uint32_t status = h.status, nb = 0; uint64_t end = 0;
-    if (!status) status = walk_blocks(S, fr.srcOff + h.hdrBytes, srcSize, &nb, &end, nullptr, 0, f, 0);
+    uint32_t status = h.status, nb = 0, nComp = 0; uint64_t end = 0;
+    if (!status) status = walk_blocks(S, fr.srcOff + h.hdrBytes, srcSize, &nb, &end, nullptr, 0, f, 0, 0, &nComp);
     if (!status && h.checksum) { if (srcSize - end < 4) status = B2Z_DERR_CORRUPT; else end += 4; }
     if (!status && end != fr.regen) status = B2Z_DERR_CORRUPT;          // a size hint that does not match its frame
-    fr.contentSize = h.contentSize; fr.windowSize = h.windowSize; fr.checksum = h.checksum; fr.nBlocks = nb; fr.pad = h.hdrBytes;
+    fr.contentSize = h.contentSize; fr.windowSize = h.windowSize; fr.checksum = h.checksum; fr.nBlocks = nb; fr.pad = h.hdrBytes; fr.nComp = nComp;
     frames[f] = fr;
     if (status) atomicOr(&counts->status, status);
 }
 
 __global__ void zstd_dec_scan_blocks_kernel(DecFrame* frames, uint32_t nFrames, uint32_t blockCap, DecCounts* counts) {
     if (threadIdx.x || blockIdx.x) return;
-    uint32_t total = 0, most = 0;
-    for (uint32_t f = 0; f < nFrames; f++) { frames[f].firstBlock = total; total += frames[f].nBlocks; if (frames[f].nBlocks > most) most = frames[f].nBlocks; }
-    counts->nBlocks = total; counts->maxFrameBlocks = most;
+    uint32_t total = 0, most = 0, slots = 0;
+    for (uint32_t f = 0; f < nFrames; f++) {
+        frames[f].firstBlock = total; total += frames[f].nBlocks; if (frames[f].nBlocks > most) most = frames[f].nBlocks;
+        frames[f].firstSlot = slots; slots += frames[f].nComp;
+    }
+    counts->nBlocks = total; counts->maxFrameBlocks = most; counts->nSlots = slots;
     if (total > blockCap) counts->status |= B2Z_DERR_TABLE_FULL;
 }
 
@@ -249,7 +253,7 @@ __global__ void zstd_dec_fill_blocks_kernel(const uint8_t* __restrict__ src, uin
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
     const DecFrame fr = frames[f];
     uint32_t nb; uint64_t end;
-    const uint32_t status = walk_blocks(S, fr.srcOff + fr.pad, srcSize, &nb, &end, blocks, fr.firstBlock, f, blockCap);
+    const uint32_t status = walk_blocks(S, fr.srcOff + fr.pad, srcSize, &nb, &end, blocks, fr.firstBlock, f, blockCap, fr.firstSlot);
     frames[f].regen = 0; frames[f].pad = 0;
     if (status) atomicOr(&counts->status, status);
 }
@@ -518,7 +522,7 @@ zstd_dec_entropy_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, DecBl
         if (blk.type != 2) continue;
         uint32_t err = 0;
         const LitHdr lh = parse_lit_hdr(S, blk.srcOff, blk.cSize);
-        uint8_t* lit = lits + (size_t)bi * 131072u;
+        uint8_t* lit = lits + (size_t)blk.slot * 131072u;
         // ---- literals
         if (ROLE == 0) {
         if (lh.type == 0) { for (uint32_t i = lane; i < lh.regen; i += 32) lit[i] = (uint8_t)S.u8(blk.srcOff + lh.hdr + i); }
@@ -634,7 +638,7 @@ zstd_dec_lit_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
     const LitJob j = litJobs[bi];
     if (!j.streams || blocks[bi].type != 2) return;
     Src S; S.w = reinterpret_cast<const uint64_t*>(src); S.nWords = (srcSize + 7) >> 3; S.size = srcSize;
-    uint8_t* lit = lits + (size_t)bi * 131072u;
+    uint8_t* lit = lits + (size_t)blocks[bi].slot * 131072u;
     const uint16_t* tab = smTab + (size_t)(bi - b0) * 2048u;
     bool ok = true;
     uint64_t off = 0; uint32_t size = 0, cnt = 0; uint8_t* dst = lit;
@@ -705,7 +709,7 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
     else {
         uint32_t sL = b.read(j.logs & 255u), sO = b.read((j.logs >> 8) & 255u), sM = b.read((j.logs >> 16) & 255u);   // <= 26 bits
         if (b.left() < 0) err = B2Z_DERR_CORRUPT;
-        uint64_t* out = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+        uint64_t* out = seqs + (size_t)blocks[bi].slot * B2Z_DEC_MAXSEQ;
         uint32_t litUsed = 0, total = 0, near = 0;
         // the repcode history as a function of the history before the block (b2z_dec.h DecBlock::repX): slot = value (sym 0) or
         // (initial slot sym - 1) minus value.  ZSTD_decodeSequence's update rules, zstd_decompress_block.c:1290-1312
@@ -845,8 +849,8 @@ zstd_dec_exec_kernel(const uint8_t* __restrict__ src, DecFrame* __restrict__ fra
             const DecBlock blk = blocks[bi];
             if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = src[blk.srcOff + i]; o += blk.rawSize; ringFrom = o; __syncwarp(); continue; }
             if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) out[o + i] = v; o += blk.rawSize; ringFrom = o; __syncwarp(); continue; }
-            const uint8_t* lit = lits + (size_t)bi * 131072u;
-            const uint64_t* sq = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+            const uint8_t* lit = lits + (size_t)blk.slot * 131072u;
+            const uint64_t* sq = seqs + (size_t)blk.slot * B2Z_DEC_MAXSEQ;
             uint32_t lp = 0;
             uint64_t ahead = lane < blk.nbSeq ? sq[lane] : 0ull;                             // the next batch's sequences are fetched a batch ahead
             for (uint32_t i0 = 0; i0 < blk.nbSeq && !err; i0 += 32) {
@@ -1011,8 +1015,8 @@ zstd_dec_jump_build_kernel(const uint8_t* __restrict__ src, const DecFrame* __re
         uint32_t err = 0;
         if (blk.type == 0) { for (uint32_t i = lane; i < blk.rawSize; i += 32) { const uint64_t P = fbase + o + i; if (P >= segS && P < segE) dst[P] = src[blk.srcOff + i]; put(P, P, true); } continue; }
         if (blk.type == 1) { const uint8_t v = src[blk.srcOff]; for (uint32_t i = lane; i < blk.rawSize; i += 32) { const uint64_t P = fbase + o + i; if (P >= segS && P < segE) dst[P] = v; put(P, P, true); } continue; }
-        const uint8_t* __restrict__ lit = lits + (size_t)bi * 131072u;
-        const uint64_t* __restrict__ sq = seqs + (size_t)bi * B2Z_DEC_MAXSEQ;
+        const uint8_t* __restrict__ lit = lits + (size_t)blk.slot * 131072u;
+        const uint64_t* __restrict__ sq = seqs + (size_t)blk.slot * B2Z_DEC_MAXSEQ;
         uint32_t lp = 0, rep0 = blk.repInit[0], rep1 = blk.repInit[1], rep2 = blk.repInit[2];
         uint64_t ahead = lane < blk.nbSeq ? sq[lane] : 0ull;
         for (uint32_t i0 = 0; i0 < blk.nbSeq && !err; i0 += 32) {

@@ -137,17 +137,17 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     cudaStream_t st = ctx->stream;
     // table capacities: frames >= 9 bytes each, blocks >= 3 bytes each; bounded to keep the tables small
     uint64_t frameCap = srcSize / 9 + 2; if (frameCap > (1u << 22)) frameCap = 1u << 22;
-    uint64_t blockCap = srcSize / 3 + 2; { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }
+    uint64_t blockCap = srcSize / 3 + 2; { const uint64_t lim = srcSize / 128 + (1u << 20); if (blockCap > lim) blockCap = lim; }     // raw / RLE blocks cost a table entry only
     if (blockCap > 0x7FFFFFFFull) blockCap = 0x7FFFFFFFull;
     Arena& aFrames = ctx->decScratch[0]; Arena& aBlocks = ctx->decScratch[1]; Arena& aCounts = ctx->decScratch[2];
     Arena& aLits = ctx->decScratch[3]; Arena& aSeqs = ctx->decScratch[4];
     if (aFrames.reserve(frameCap * sizeof(DecFrame)) || aBlocks.reserve(blockCap * sizeof(DecBlock)) || aCounts.reserve(64))
         return fail(ctx, B200Z_E_MEMORY, "decoder table allocation failed%s");
     DecFrame* frames = (DecFrame*)aFrames.p; DecBlock* blocks = (DecBlock*)aBlocks.p;
-    DecCounts* counts = (DecCounts*)aCounts.p; uint64_t* total = (uint64_t*)((uint8_t*)aCounts.p + 32);
+    DecCounts* counts = (DecCounts*)aCounts.p; uint64_t* total = (uint64_t*)((uint8_t*)aCounts.p + 40);
     CU(cudaEventRecord(ctx->ev[0], st));
     DecCounts hc;
-    static_assert(sizeof(DecCounts) == 32, "DecCounts is fetched as four words");
+    static_assert(sizeof(DecCounts) == 40, "DecCounts is fetched as five words");
     // stage D0, first with mcmilk's size hints trusted (one hop per frame); a stream that then fails to index -- a skippable frame that only
     // looks like a hint -- is walked again block header by block header, as the reference does for every stream
     for (int pass = 0; pass < 2; pass++) {
@@ -167,7 +167,7 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     }
     CU(cudaEventRecord(ctx->ev[3], st));
     if (hc.status) return dec_status_to_rc(ctx, hc.status);
-    if (aLits.reserve((size_t)hc.nBlocks * 131072ull + 64) || aSeqs.reserve((size_t)hc.nBlocks * B2Z_DEC_MAXSEQ * 8ull + 64) ||
+    if (aLits.reserve((size_t)hc.nSlots * 131072ull + 64) || aSeqs.reserve((size_t)hc.nSlots * B2Z_DEC_MAXSEQ * 8ull + 64) ||
         ctx->decScratch[5].reserve(zstd_dec_entropy_scratch_bytes(hc.nBlocks) + zstd_dec_unit_state_bytes(hc.nFrames, hc.nBlocks) + 64))
         return fail(ctx, B200Z_E_MEMORY, "decoder scratch allocation failed (input too large for one pass)%s");
     launch_zstd_dec_entropy((const uint8_t*)d_src, srcSize, blocks, hc.nBlocks, (uint8_t*)aLits.p, (uint64_t*)aSeqs.p, ctx->decScratch[5].p, st, st, ctx->ev[4], ctx->ev[5]);
@@ -181,7 +181,7 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     CU(cudaGetLastError());
     if (maybeJump) {
         struct { DecCounts c; uint64_t total; } hj;
-        { const int frc = b2z_fetch_small(ctx, &hj, counts, 40, st); if (frc) return frc; }
+        { const int frc = b2z_fetch_small(ctx, &hj, counts, 48, st); if (frc) return frc; }
         if (hj.c.status) return dec_status_to_rc(ctx, hj.c.status);
         if (hj.c.nJump) {
             Arena& aPtr = ctx->decScratch[8];
@@ -201,8 +201,8 @@ static int dec_impl(b200z_ctx* ctx, const void* d_src, size_t srcSize, void* d_d
     launch_zstd_dec_verify((const uint8_t*)d_src, frames, hc.nFrames, (const uint8_t*)d_dst, counts, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[2], st));
-    struct { DecCounts c; uint64_t total; } hr;                                // counts at +0, the total at +32 of the same 64-byte scratch
-    { const int frc = b2z_fetch_small(ctx, &hr, counts, 40, st); if (frc) return frc; }
+    struct { DecCounts c; uint64_t total; } hr;                                // counts at +0, the total at +40 of the same 64-byte scratch
+    { const int frc = b2z_fetch_small(ctx, &hr, counts, 48, st); if (frc) return frc; }
     ctx->stat[B200Z_S_KERNEL_LAUNCHES] += 7;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stat[B200Z_S_DEC_PREPASS_MS] += ms;

@@ -219,7 +219,7 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     if (nJumpOut) *nJumpOut = 0;
     if (!srcSize) return 0;
     uint64_t frameCap = srcSize / 9 + 2, blockCap = srcSize / 3 + 2;
-    { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }
+    { const uint64_t lim = srcSize / 128 + 65536; if (blockCap > lim) blockCap = lim; }                  // (the product adds 2^20: table entries only)
     std::vector<DecFrame> frames(frameCap); std::vector<DecBlock> blocks(blockCap);
     DecCounts counts; memset(&counts, 0, sizeof(counts)); uint64_t total = 0;
     uint32_t nFrames = 0;
@@ -238,7 +238,8 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     }
     if (counts.status) return -(int64_t)counts.status;
     const uint32_t nBlocks = counts.nBlocks;
-    std::vector<uint8_t> lits((size_t)nBlocks * 131072ull + 64); std::vector<uint64_t> seqs((size_t)nBlocks * B2Z_DEC_MAXSEQ + 8);
+    const uint32_t nSlots = counts.nSlots;                                               // compressed blocks: the only ones with literal / sequence scratch
+    std::vector<uint8_t> lits((size_t)nSlots * 131072ull + 64); std::vector<uint64_t> seqs((size_t)nSlots * B2Z_DEC_MAXSEQ + 8);
     std::vector<uint8_t> scratch((size_t)nBlocks * (4096u + 1280u * sizeof(SeqEnt) + sizeof(LitJob) + sizeof(SeqJob)) + 256u, 0xCD);
     if (nBlocks) {
         uint8_t* p = scratch.data();

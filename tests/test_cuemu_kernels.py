@@ -362,6 +362,21 @@ def test_emulated_zstd_decoder_frames_of_several_units(pkg, emu):
         assert r == n and out == data, k
 
 
+def test_emulated_zstd_decoder_scratch_follows_compressed_blocks(pkg, emu):
+    """raw and RLE blocks own no literal / sequence scratch (DecBlock::slot numbers the compressed blocks only): a reference frame of
+    128 RLE blocks of zeros, 16 raw blocks of noise and a little text decodes with scratch for the text's blocks alone -- through the
+    execution units and through stage J"""
+    if not H.ref_available():
+        pytest.skip("oracle/_ref not built")
+    data = bytes(16 << 20) + pkg.corpus.entropy_class(1, 2 << 20).tobytes() + pkg.corpus.g2(300_000).tobytes() + bytes(1 << 20); n = len(data)
+    comp = H.ref_compress(data, level=3)
+    src = np.frombuffer(comp + bytes(64), dtype=np.uint8)
+    for mode in (0, 2):
+        dst = np.full(n + 64, 0xEE, dtype=np.uint8); nj = ctypes.c_uint32(0)
+        r = emu.emu_zstd_decode_jump(src.ctypes.data, len(comp), dst.ctypes.data, n, mode, ctypes.byref(nj))
+        assert r == n and dst[:n].tobytes() == data, mode
+
+
 def test_emulated_zstd_decoder_stage_j_pointer_jumping(pkg, emu):
     """stage J (zstd_dec_jump_build / _round kernels): literal bytes + one pointer per output byte, pointer doubling, byte gather.
     Forced on every frame (mode 2) it must give what the execution units give -- golden frames of the reference encoder, frames with
