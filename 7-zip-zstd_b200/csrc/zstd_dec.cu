@@ -751,20 +751,24 @@ zstd_dec_seq_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
 }
 
 // ---------------------------------------------------------------- D2: layout
-// jumpMode (b2z_dec.h): which frames leave the execution units for stage J.  Automatic: a frame of >= B2Z_DEC_JUMP_MIN_UNITS units of which
-// at least three in four start with a block that copies from the unit before it -- a sliding-window frame (what the reference's encoder
-// writes: one frame per stream, ZstdEncoder.cpp:250-340), whose units would run one behind the other.
+// jumpMode (b2z_dec.h): which frames leave the execution units for stage J.  Automatic: a frame of >= B2Z_DEC_JUMP_MIN_UNITS units in which
+// three consecutive units (or three in four of all) start with a block that copies from the unit before it -- a sliding-window frame (what
+// the reference's encoder writes: one frame per stream, ZstdEncoder.cpp:250-340), whose units would run one behind the other.  The test is
+// deliberately easy to pass: a frame taken by stage J for nothing costs ~35 ms per GiB instead of ~4, a chain left to the units ~12 s per GiB
+// (binaries compressed at level >= 3 split their blocks and copy by repcodes: only two units in three show the dependency in their first block).
 __global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, DecBlock* __restrict__ blocks, DecCounts* counts, uint32_t jumpMode) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFrames) return;
-    uint64_t total = 0; uint32_t st = 0, chained = 0;
+    uint64_t total = 0; uint32_t st = 0, chained = 0, run = 0, longest = 0;
     const uint32_t b0 = frames[f].firstBlock, nb = frames[f].nBlocks;
     uint32_t r0 = 1, r1 = 4, r2 = 8;                                         // the format's starting history
     for (uint32_t i = 0; i < nb; i++) {
         DecBlock& B = blocks[b0 + i];
         B.outRel = total; B.repInit[0] = r0; B.repInit[1] = r1; B.repInit[2] = r2;
         total += B.regen; st |= B.status;
-        if (i && i % B2Z_DEC_UNIT_BLOCKS == 0u && B.type == 2 && B.nearBehind) chained++;
+        if (i && i % B2Z_DEC_UNIT_BLOCKS == 0u) {                             // a unit's first block: does it copy from the unit before it?
+            if (B.type == 2 && B.nearBehind) { chained++; run++; if (run > longest) longest = run; } else run = 0;
+        }
         if (B.type == 2 && B.nbSeq) {                                         // apply the block's symbolic history (stage D1)
             const uint32_t in[3] = { r0, r1, r2 }, y = B.repSym;
             r0 = (y & 3u) ? in[(y & 3u) - 1u] - B.repX[0] : B.repX[0];
@@ -776,7 +780,7 @@ __global__ void zstd_dec_frame_sizes_kernel(DecFrame* frames, uint32_t nFrames, 
     frames[f].regen = total;
     const uint32_t units = (nb + B2Z_DEC_UNIT_BLOCKS - 1u) / B2Z_DEC_UNIT_BLOCKS;
     frames[f].jump = (uint32_t)(!st && total &&
-                                (jumpMode == 2u || (jumpMode == 1u && units >= B2Z_DEC_JUMP_MIN_UNITS && chained * 4u >= (units - 1u) * 3u)));
+                                (jumpMode == 2u || (jumpMode == 1u && units >= B2Z_DEC_JUMP_MIN_UNITS && (longest >= 3u || chained * 4u >= (units - 1u) * 3u))));
     if (st) atomicOr(&counts->status, st);
 }
 __global__ void zstd_dec_frame_offsets_kernel(DecFrame* frames, uint32_t nFrames, uint64_t dstCap, DecCounts* counts, uint64_t* total) {

@@ -256,6 +256,13 @@ static int64_t emu_zstd_decode_mode(const uint8_t* src, uint64_t srcSize, uint8_
     if (nFrames) cuemu::launch(dim3((nFrames + 127) / 128), dim3(128), 0, [&] { zstd_dec_frame_sizes_kernel(frames.data(), nFrames, blocks.data(), &counts, maybeJump ? jumpMode : 0u); });
     cuemu::launch(dim3(1), dim3(32), 0, [&] { zstd_dec_frame_offsets_kernel(frames.data(), nFrames, dstCap, &counts, &total); });
     if (nJumpOut) *nJumpOut = counts.nJump;
+    if (getenv("B2Z_EMU_JUMP_DEBUG")) for (uint32_t f = 0; f < nFrames; f++) {
+        uint32_t t[3] = {0, 0, 0}, firstNear = 0, firstComp = 0, anyNear = 0;
+        for (uint32_t k = 0; k < frames[f].nBlocks; k++) { const DecBlock& b = blocks[frames[f].firstBlock + k]; t[b.type]++; anyNear += b.nearBehind;
+            if (k && k % B2Z_DEC_UNIT_BLOCKS == 0) { firstComp += b.type == 2; firstNear += b.type == 2 && b.nearBehind; } }
+        fprintf(stderr, "frame %u: blocks %u (raw %u rle %u comp %u) units %u firstComp %u firstNear %u anyNear %u jump %u\n", f, frames[f].nBlocks, t[0], t[1], t[2],
+                (frames[f].nBlocks + B2Z_DEC_UNIT_BLOCKS - 1) / B2Z_DEC_UNIT_BLOCKS, firstComp, firstNear, anyNear, frames[f].jump);
+    }
     if (maybeJump && !counts.status && counts.nJump && nBlocks && total) {             // launch_zstd_dec_jump
         const uint64_t seg = 1ull << g_emu_jump_seglog;
         std::vector<uint32_t> ptr((size_t)(total < seg ? total : seg) + 16, 0xCDCDCDCDu), flags(B2Z_DEC_JUMP_ROUNDS + 1u, 0u);

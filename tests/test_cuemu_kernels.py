@@ -427,6 +427,11 @@ def test_emulated_zstd_decoder_stage_j_pointer_jumping(pkg, emu):
         assert (r, out) == (nb, big) and nj == 1                 # one sliding-window frame: stage J
         r, out, nj = dec(ref + H.oracle_compress(data) + ref, 2 * nb + n, 1)
         assert (r, out) == (2 * nb + n, big + data + big) and nj == 2
+        # half the frame is RLE blocks: the text half is still a chain of six units -- three consecutive chained units are enough
+        half = bytes(3 << 20) + pkg.corpus.g2(3 << 20).tobytes()
+        for lv in (1, 9):
+            r, out, nj = dec(H.ref_compress(half, level=lv), len(half), 1)
+            assert (r, out) == (len(half), half) and nj == 1, lv
 
 
 def test_emulated_stage_z_sequence_array_full(pkg, emu):
