@@ -250,7 +250,7 @@ lzma2_enc_range_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, EncGeo
 //           pairs, 13 + 1 bits each; which probabilities a packet touches and with which bits is a function of the input alone, never of
 //           the probabilities -- until the queue holds B2Z_R32_FILL decisions;
 //   phase B (lock-step): B2Z_R32_FILL times, all 32 lanes pop a decision and code it.  The probabilities of the steps to come are loaded
-//           B2Z_R32_DEPTH steps ahead (a step that adapts one of them forwards the new value).
+//           B2Z_R32_DEPTH steps ahead (a step that adapts one of them marks the slot stale; a stale slot loads again at its turn).
 // STATUS: parity-green on B200 (bytes of the kernel above) but not the default: 1.9 s per 4 GiB against 0.98 s for one chain per warp.
 // Why, in numbers (profiles/r2_range32_ncu.txt): the warp executes ~185 instructions per step of 32 decisions -- 6 per decision where the
 // single-chain kernel spends 30 -- so the whole job is 4x fewer instructions.  But the single-chain kernel is ISSUE-bound (32 resident warps
