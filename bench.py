@@ -171,7 +171,7 @@ def long_range(pkg, local, mib, cpu=True):
     for name, params in (("plain", {}), ("long27", {"long": 27})):
         c = pkg.Codec(local, **params)
         d_comp = torch.empty(c.compress_bound(n), dtype=torch.uint8, device="cuda"); d_back = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
-        wn = min(n, 1 << 30)
+        wn = n                                                              # warm-up at the full size: the scratch arenas grow here, not inside the timed pass
         m = c.compress_device(d_in.data_ptr(), wn, d_comp.data_ptr(), d_comp.numel()); c.decompress_device(d_comp.data_ptr(), m, d_back.data_ptr(), wn)
         c.reset_stats(); torch.cuda.synchronize()
         t0 = time.perf_counter(); m = c.compress_device(d_in.data_ptr(), n, d_comp.data_ptr(), d_comp.numel()); torch.cuda.synchronize(); t1 = time.perf_counter()
