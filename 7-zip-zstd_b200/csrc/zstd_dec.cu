@@ -628,7 +628,10 @@ zstd_dec_lit_streams_kernel(const uint8_t* __restrict__ src, uint64_t srcSize, D
         uint4* s4 = reinterpret_cast<uint4*>(smTab);
         for (uint32_t i = threadIdx.x; i < B2Z_LIT_BLOCKS * 256u; i += B2Z_LIT_BLOCKS * 4u) {
             const uint32_t bb = b0 + (i >> 8);
-            if (bb < nBlocks) { const LitJob jj = litJobs[bb]; if (jj.streams && (i & 255u) < ((1u << jj.hufBits) + 7u) / 8u) s4[i] = __ldg(g4 + i); }
+            if (bb < nBlocks && blocks[bb].type == 2) {                  // (raw / RLE blocks have no job record: nothing was written there)
+                const LitJob jj = litJobs[bb];
+                if (jj.streams && (i & 255u) < ((1u << jj.hufBits) + 7u) / 8u) s4[i] = __ldg(g4 + i);
+            }
         }
     }
     __syncthreads();
